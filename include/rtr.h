@@ -1,0 +1,196 @@
+/* rtr.h — C ABI of librtr.so: the B200 (sm_100a) drop-in for the model-to-scene registration path
+ * of ICCD/RealTime_Robot.
+ *
+ * Conventions (taken from the only FFI the reference has, `ComputeTDFWithCuda`,
+ * RealTimeRobot/key_point.h:35-36 + kernel.cu:34-106):
+ *   - plain pointers and sizes, no C++ / torch types;
+ *   - every function returns an int status, 0 == success (cudaSuccess); on failure one tagged line
+ *     goes to stderr and nothing is thrown across the boundary;
+ *   - "host" pointers are caller-owned host memory; "dev" pointers are device memory on the
+ *     context's GPU; handles (rtr_context, rtr_cloud) are created / destroyed explicitly.
+ *   - points are the 16-byte pcl::PointXYZ layout: float x, y, z, pad (= 1.0f) — i.e. one float4.
+ *   - 4x4 poses are 16 floats, COLUMN-major (Eigen::Matrix4f::data() order), mapping source -> target.
+ *
+ * Each entry point cites the reference interface it replaces (file:line under
+ * /root/reference/RealTimeRobot).  Stages that exist only inside PCL 1.8.0 in the reference
+ * cite the PCL class the reference instantiates and the reference call site.
+ */
+#ifndef RTR_H_
+#define RTR_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTR_OK                0
+#define RTR_ERR_INVALID       1   /* bad argument (mirrors cudaErrorInvalidValue == 1) */
+#define RTR_ERR_CAPACITY      3   /* caller buffer too small; required size reported through the count argument */
+#define RTR_ERR_NOT_READY     4   /* a prerequisite stage has not been run on this cloud */
+/* any other non-zero value is the cudaError_t of the failing CUDA call */
+
+#define RTR_FPFH_DIM   33
+#define RTR_TDF_DIM    30
+#define RTR_TDF_VOXELS 27000   /* KeyPoint::grid_value[27000], key_point.h:65 */
+
+typedef struct rtr_context rtr_context;
+typedef struct rtr_cloud   rtr_cloud;
+
+/* ------------------------------------------------------------------ parameters */
+
+/* pcl::SampleConsensusPrerejective<PointXYZ,PointXYZ,FPFHSignature33> knobs.
+ * The reference has no such stage (its consensus is function.h:35-109); the defaults are the PCL
+ * tutorial's and are NOT reference parameters. */
+typedef struct rtr_ransac_params {
+    long long          max_iterations;               /* 50000 */
+    long long          hypothesis_begin;             /* shard [begin, end) of 0..max_iterations; */
+    long long          hypothesis_end;               /*   end <= 0 means max_iterations          */
+    unsigned long long seed;                         /* counter-RNG key: hypothesis h depends on (seed, h) only */
+    int                correspondence_k;             /* setCorrespondenceRandomness, 5 */
+    float              similarity_threshold;         /* 0.9  (edge-length ratio, compared squared) */
+    float              max_correspondence_distance;  /* 0.0365 (inlier iff nn d^2 < this^2) */
+    float              inlier_fraction;              /* 0.25 */
+} rtr_ransac_params;
+
+/* pcl::IterativeClosestPoint<PointXYZ,PointXYZ> knobs; defaults = PCL's, which is what
+ * keyPointICP() runs (function.h:111-117). */
+typedef struct rtr_icp_params {
+    int    max_iterations;                /* 10 */
+    int    force_iterations;              /* 1: ignore convergence tests, always run max_iterations (bench cfg 3) */
+    float  max_correspondence_distance;   /* <= 0: unlimited (PCL default sqrt(DBL_MAX)) */
+    float  pad_;
+    double mse_threshold_absolute;        /* 1e-12 (DefaultConvergenceCriteria) */
+} rtr_icp_params;
+
+typedef struct rtr_register_params {
+    float normal_radius;        /* 0.05  == Harris radius, model_point.h:130 */
+    float harris_radius;        /* 0.05  model_point.h:130, scan_point.h:88 */
+    float harris_threshold;     /* 0.01  model_point.h:131, scan_point.h:89 */
+    int   harris_nms;           /* 1     model_point.h:129 */
+    int   harris_refine;        /* 1     PCL default */
+    float fpfh_radius;          /* 0.10  builder-chosen (no FPFH in the reference) */
+    int   run_icp;              /* 1 */
+    int   pad_;
+    rtr_ransac_params ransac;
+    rtr_icp_params    icp;
+} rtr_register_params;
+
+/* fixed 128-byte record: the unit of the multi-GPU all-gather. */
+typedef struct rtr_pose_result {
+    float     pose[16];        /* column-major source->target */
+    float     fitness;         /* mean squared NN distance (RANSAC: over inliers; ICP: all, getFitnessScore) */
+    int       inliers;         /* RANSAC inlier count of the winner (ICP: correspondences of last iteration) */
+    long long hypothesis;      /* winning hypothesis id, -1 if none accepted */
+    long long evaluated;       /* hypotheses that passed polygon prerejection in this shard */
+    int       converged;       /* RANSAC: any accepted; ICP: convergence state (1 iterations, 2 transform, 3 abs mse, 0 no) */
+    int       iterations;      /* ICP iterations performed */
+    int       model_id;        /* caller tag, copied through */
+    int       n_keypoints_src; /* Harris corners found (register only) */
+    int       n_keypoints_tgt;
+    int       pad_[5];
+} rtr_pose_result;
+
+void rtr_default_register_params(rtr_register_params* p);
+
+/* ------------------------------------------------------------------ context / clouds */
+
+/* One context per GPU (device id, one stream, a grow-only workspace arena).  Replaces the
+ * cudaSetDevice(0) + cudaMalloc/cudaFree done on EVERY call at kernel.cu:43-56,101-102. */
+int rtr_context_create(int device, rtr_context** out);
+int rtr_context_destroy(rtr_context* ctx);
+int rtr_context_sync(rtr_context* ctx);
+/* cudaStream_t of the context, as void* (so callers can record CUDA events on it). */
+void* rtr_context_stream(rtr_context* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches). */
+long long rtr_context_launches(rtr_context* ctx);
+
+/* Upload a pcl::PointCloud<pcl::PointXYZ>::points array (n x 16 B, host).  Replaces the cloud hand-off
+ * ModelPoint(Ptr) / ScanPoint(Ptr), model_point.h:165-168, scan_point.h:43-54. */
+int rtr_cloud_upload(rtr_context* ctx, const float* host_xyz1, int n, rtr_cloud** out);
+/* Same, from a device buffer (copied). */
+int rtr_cloud_from_device(rtr_context* ctx, const float* dev_xyz1, int n, rtr_cloud** out);
+int rtr_cloud_free(rtr_cloud* c);
+int rtr_cloud_size(const rtr_cloud* c);
+/* Apply a 4x4 (column-major) to the cloud in place: pcl::transformPointCloud(*c, *c, m)
+ * (model_point.h:111, RealTimeRobot.cpp:105).  Invalidates cached stages. */
+int rtr_cloud_transform(rtr_cloud* c, const float* pose16);
+/* Copy points back to host (n x 4 floats). */
+int rtr_cloud_download(rtr_cloud* c, float* host_xyz1);
+
+/* ------------------------------------------------------------------ neighbour index */
+
+/* Exact radius neighbour sets over the uniform grid, for queries == the cloud's own points:
+ * pcl::search::KdTree::radiusSearch as used inside HarrisKeypoint3D (model_point.h:127-136):
+ * d^2 < r^2 strict, self included.  counts[n]; if indices != NULL it receives, per query i at
+ * offsets[i] (exclusive prefix of counts, also returned), the neighbour indices in ascending order.
+ * *total receives sum(counts); RTR_ERR_CAPACITY if capacity < *total. */
+int rtr_radius_neighbors(rtr_cloud* c, float radius, int* host_counts, long long* host_offsets,
+                         int* host_indices, long long capacity, long long* total);
+
+/* Exact 1-NN of each query (host, nq x 16 B) in the cloud: KdTreeFLANN::nearestKSearch(q,1) as used by
+ * IterativeClosestPoint (function.h:112-117).  Ties -> lowest index. */
+int rtr_nearest(rtr_cloud* target, const float* host_queries_xyz1, int nq, int* host_idx, float* host_d2);
+
+/* ------------------------------------------------------------------ per-cloud stages (results cached on device) */
+
+/* pcl::NormalEstimation (run implicitly by HarrisKeypoint3D, model_point.h:127-136; App. A.2).
+ * host_normals4 (optional): n x {nx, ny, nz, curvature}. */
+int rtr_normals(rtr_cloud* c, float radius, float* host_normals4);
+
+/* pcl::HarrisKeypoint3D<PointXYZ,PointXYZI,Normal>::compute — ModelPoint::getKeypoint (model_point.h:99-156),
+ * ScanPoint::getKeypoint (scan_point.h:57-113).  Needs rtr_normals first (same radius in the reference).
+ * host_response (optional) n floats; keypoints: original indices (ascending) + refined xyz1. */
+int rtr_harris3d(rtr_cloud* c, float radius, float threshold, int nms, int refine,
+                 float* host_response, int* host_kp_index, float* host_kp_xyz1, int capacity, int* n_keypoints);
+
+/* pcl::FPFHEstimation<PointXYZ,Normal,FPFHSignature33> over all points (input == surface; App. A.4).
+ * Needs rtr_normals.  host_fpfh (optional): n x 33 floats. */
+int rtr_fpfh(rtr_cloud* c, float radius, float* host_fpfh);
+
+/* k nearest target features of every source feature, 33-D squared L2, ascending, ties -> lowest index:
+ * KdTreeFLANN<FPFHSignature33>::nearestKSearch inside SampleConsensusPrerejective::findSimilarFeatures
+ * (App. A.5).  Both clouds need rtr_fpfh.  Result cached on `source`; host outputs optional (ns x k). */
+int rtr_match_features(rtr_cloud* source, rtr_cloud* target, int k, int* host_idx, float* host_dist);
+
+/* ------------------------------------------------------------------ pose stages */
+
+/* SampleConsensusPrerejective::computeTransformation over hypotheses [begin,end) (App. A.5).
+ * Needs rtr_match_features(source, target, k >= correspondence_k). */
+int rtr_ransac_prerejective(rtr_cloud* source, rtr_cloud* target, const rtr_ransac_params* p,
+                            rtr_pose_result* host_result);
+
+/* pcl::IterativeClosestPoint::align with an initial guess — keyPointICP (function.h:111-123).
+ * init_pose16 may be NULL (identity). */
+int rtr_icp(rtr_cloud* source, rtr_cloud* target, const rtr_icp_params* p, const float* init_pose16,
+            rtr_pose_result* host_result);
+
+/* The whole model-to-scene registration the north star names, device-resident end to end:
+ * grid -> normals -> Harris -> FPFH (both clouds) -> feature k-NN -> prerejective RANSAC -> ICP.
+ * Sequencing counterpart of main(), RealTimeRobot.cpp:39-105. */
+int rtr_register(rtr_cloud* model, rtr_cloud* scene, const rtr_register_params* p, rtr_pose_result* host_result);
+
+/* One-call form with HOST clouds in and a HOST result out (upload + register + free): the e2e
+ * entry point a pcl::PointCloud<PointXYZ> caller uses. */
+int rtr_register_host(rtr_context* ctx, const float* host_model_xyz1, int n_model,
+                      const float* host_scene_xyz1, int n_scene, const rtr_register_params* p,
+                      rtr_pose_result* host_result);
+
+/* ------------------------------------------------------------------ reference-native descriptor path */
+
+/* THE reference FFI, exported unchanged (key_point.h:35-36, kernel.cu:34-35).  Host pointers;
+ * voxel_grid_occ = num_occ packed (x,y,z) int32; voxel_grid_TDF = 27000 floats in/out
+ * (only the first dim^3 are written); synchronous; returns cudaSuccess (0) or the failing code. */
+int ComputeTDFWithCuda(const int* voxel_grid_occ, float* voxel_grid_TDF, int voxel_grid_dim, int num_occ);
+
+/* Batched form: n_grids keypoints in one launch.  occ = concatenated triples, occ_offsets[n_grids+1]
+ * in triples; tdf_out = n_grids x dim^3 floats.  All host pointers.  Replaces the per-keypoint loop
+ * RealTimeRobot.cpp:62-69 -> key_point.h:313. */
+int rtr_tdf_batch(rtr_context* ctx, const int* host_occ, const int* host_occ_offsets, int n_grids,
+                  int dim, float* host_tdf_out);
+/* Same with device pointers, asynchronous on the context stream. */
+int rtr_tdf_batch_dev(rtr_context* ctx, const int* dev_occ, const int* dev_occ_offsets, int n_grids,
+                      int dim, float* dev_tdf_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTR_H_ */

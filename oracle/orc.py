@@ -1,0 +1,168 @@
+"""ctypes binding of oracle/liboracle.so — TEST INFRASTRUCTURE (see oracle/oracle.cpp header).
+
+Imported only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from realtime_robot_b200.params import IcpParams, PoseResult, RansacParams, RegisterParams
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+        _LIB.orc_radius_neighbors.restype = C.c_longlong
+        _LIB.orc_harris3d.restype = C.c_int
+        _LIB.orc_hypothesis.restype = C.c_int
+        _LIB.orc_get_threads.restype = C.c_int
+    return _LIB
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a, t=C.c_float):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def set_threads(t: int):
+    lib().orc_set_threads(C.c_int(t))
+    return lib().orc_get_threads()
+
+
+def tdf(occ, dim=30):
+    occ = np.ascontiguousarray(occ, dtype=np.int32).reshape(-1, 3)
+    out = np.zeros(dim ** 3, dtype=np.float32)
+    lib().orc_tdf(_p(occ, C.c_int), C.c_int(len(occ)), C.c_int(dim), _p(out))
+    return out
+
+
+def radius_neighbors(xyz1, radius, method=1):
+    xyz1 = _f(xyz1)
+    n = len(xyz1)
+    counts = np.zeros(n, dtype=np.int32)
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    total = lib().orc_radius_neighbors(_p(xyz1), n, C.c_float(radius), method, _p(counts, C.c_int),
+                                       _p(offsets, C.c_longlong), None, C.c_longlong(0))
+    idx = np.zeros(max(total, 1), dtype=np.int32)
+    lib().orc_radius_neighbors(_p(xyz1), n, C.c_float(radius), method, _p(counts, C.c_int),
+                               _p(offsets, C.c_longlong), _p(idx, C.c_int), C.c_longlong(total))
+    return counts, offsets, idx[:total]
+
+
+def nearest(tgt, q, method=1):
+    tgt, q = _f(tgt), _f(q)
+    idx = np.zeros(len(q), dtype=np.int32)
+    d2 = np.zeros(len(q), dtype=np.float32)
+    lib().orc_nearest(_p(tgt), len(tgt), _p(q), len(q), method, _p(idx, C.c_int), _p(d2))
+    return idx, d2
+
+
+def normals(xyz1, radius, mode=0):
+    xyz1 = _f(xyz1)
+    out = np.zeros((len(xyz1), 4), dtype=np.float32)
+    lib().orc_normals(_p(xyz1), len(xyz1), C.c_float(radius), mode, _p(out))
+    return out
+
+
+def harris3d(xyz1, normals4, radius, threshold, nms=1, refine=1):
+    xyz1, normals4 = _f(xyz1), _f(normals4)
+    n = len(xyz1)
+    resp = np.zeros(n, dtype=np.float32)
+    kidx = np.zeros(n, dtype=np.int32)
+    kxyz = np.zeros((n, 4), dtype=np.float32)
+    m = lib().orc_harris3d(_p(xyz1), n, _p(normals4), C.c_float(radius), C.c_float(threshold), nms, refine,
+                           _p(resp), _p(kidx, C.c_int), _p(kxyz), n)
+    return resp, kidx[:m].copy(), kxyz[:m].copy()
+
+
+def fpfh(xyz1, normals4, radius):
+    xyz1, normals4 = _f(xyz1), _f(normals4)
+    out = np.zeros((len(xyz1), 33), dtype=np.float32)
+    lib().orc_fpfh(_p(xyz1), len(xyz1), _p(normals4), C.c_float(radius), _p(out))
+    return out
+
+
+def match_features(fa, fb, k):
+    fa, fb = _f(fa), _f(fb)
+    idx = np.zeros((len(fa), k), dtype=np.int32)
+    dist = np.zeros((len(fa), k), dtype=np.float32)
+    lib().orc_match_features(_p(fa), len(fa), _p(fb), len(fb), k, _p(idx, C.c_int), _p(dist))
+    return idx, dist
+
+
+def ransac(src, tgt, knn, params: RansacParams) -> PoseResult:
+    src, tgt = _f(src), _f(tgt)
+    knn = np.ascontiguousarray(knn, dtype=np.int32)
+    res = PoseResult()
+    lib().orc_ransac_prerejective(_p(src), len(src), _p(tgt), len(tgt), _p(knn, C.c_int), knn.shape[1],
+                                  C.byref(params), C.byref(res))
+    return res
+
+
+def hypothesis(src, tgt, knn, params: RansacParams, h: int):
+    src, tgt = _f(src), _f(tgt)
+    knn = np.ascontiguousarray(knn, dtype=np.int32)
+    s6 = np.zeros(6, dtype=np.int32)
+    pose = np.zeros(16, dtype=np.float32)
+    ok = lib().orc_hypothesis(_p(src), len(src), _p(tgt), len(tgt), _p(knn, C.c_int), knn.shape[1], C.byref(params),
+                              C.c_longlong(h), _p(s6, C.c_int), _p(pose))
+    return ok, s6, pose.reshape(4, 4).T.copy()
+
+
+def icp(src, tgt, params: IcpParams, init=None) -> PoseResult:
+    src, tgt = _f(src), _f(tgt)
+    res = PoseResult()
+    ini = None if init is None else np.ascontiguousarray(np.asarray(init, dtype=np.float32).reshape(4, 4).T).reshape(16)
+    lib().orc_icp(_p(src), len(src), _p(tgt), len(tgt), C.byref(params), _p(ini), C.byref(res))
+    return res
+
+
+def pose_from_pairs(src, tgt):
+    src, tgt = _f(src), _f(tgt)
+    pose = np.zeros(16, dtype=np.float32)
+    lib().orc_pose_from_pairs(_p(src), _p(tgt), len(src), _p(pose))
+    return pose.reshape(4, 4).T.copy()
+
+
+def transform(xyz1, pose):
+    xyz1 = _f(xyz1)
+    out = np.zeros_like(xyz1)
+    m = np.ascontiguousarray(np.asarray(pose, dtype=np.float32).reshape(4, 4).T).reshape(16)
+    lib().orc_transform(_p(xyz1), len(xyz1), _p(m), _p(out))
+    return out
+
+
+def jacobi(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    n = a.shape[0]
+    ev = np.zeros(n)
+    vec = np.zeros((n, n))
+    lib().orc_jacobi(a.ctypes.data_as(C.POINTER(C.c_double)), n, ev.ctypes.data_as(C.POINTER(C.c_double)),
+                     vec.ctypes.data_as(C.POINTER(C.c_double)))
+    return ev, vec
+
+
+def register(model, scene, params: RegisterParams) -> PoseResult:
+    model, scene = _f(model), _f(scene)
+    res = PoseResult()
+    lib().orc_register(_p(model), len(model), _p(scene), len(scene), C.byref(params), C.byref(res))
+    return res
