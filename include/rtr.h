@@ -102,6 +102,9 @@ int rtr_context_sync(rtr_context* ctx);
 void* rtr_context_stream(rtr_context* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches). */
 long long rtr_context_launches(rtr_context* ctx);
+/* CUDA-event timing on the context's own stream: record into slot 0..15, elapsed between two slots (syncs on b). */
+int rtr_event_record(rtr_context* ctx, int slot);
+int rtr_event_elapsed_ms(rtr_context* ctx, int slot_a, int slot_b, float* ms);
 
 /* Upload a pcl::PointCloud<pcl::PointXYZ>::points array (n x 16 B, host).  Replaces the cloud hand-off
  * ModelPoint(Ptr) / ScanPoint(Ptr), model_point.h:165-168, scan_point.h:43-54. */

@@ -1,0 +1,73 @@
+"""Loader for librtr.so (the hand-written sm_100a CUDA library behind include/rtr.h).
+
+There is no CPU fallback: if the library is missing or cannot be loaded, importing the compute API raises.
+"""
+import ctypes as C
+import os
+
+from .params import IcpParams, PoseResult, RansacParams, RegisterParams
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librtr.so")
+_LIB = None
+
+# every symbol include/rtr.h declares (tests check that the library exports each one)
+EXPORTS = [
+    "rtr_default_register_params", "rtr_context_create", "rtr_context_destroy", "rtr_context_sync", "rtr_context_stream",
+    "rtr_context_launches", "rtr_event_record", "rtr_event_elapsed_ms", "rtr_cloud_upload", "rtr_cloud_from_device",
+    "rtr_cloud_free", "rtr_cloud_size", "rtr_cloud_transform", "rtr_cloud_download", "rtr_radius_neighbors", "rtr_nearest",
+    "rtr_normals", "rtr_harris3d", "rtr_fpfh", "rtr_match_features", "rtr_ransac_prerejective", "rtr_icp", "rtr_register",
+    "rtr_register_host", "ComputeTDFWithCuda", "rtr_tdf_batch", "rtr_tdf_batch_dev",
+]
+
+
+class RtrError(RuntimeError):
+    def __init__(self, fn, code):
+        super().__init__(f"{fn} failed with status {code}")
+        self.code = code
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C realtime_robot_b200/csrc). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        vp, ip, fp, ll = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_longlong
+        L.rtr_context_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.rtr_context_destroy.argtypes = [vp]
+        L.rtr_context_sync.argtypes = [vp]
+        L.rtr_context_stream.argtypes = [vp]
+        L.rtr_context_stream.restype = vp
+        L.rtr_context_launches.argtypes = [vp]
+        L.rtr_context_launches.restype = ll
+        L.rtr_event_record.argtypes = [vp, C.c_int]
+        L.rtr_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, fp]
+        L.rtr_cloud_upload.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
+        L.rtr_cloud_from_device.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
+        L.rtr_cloud_free.argtypes = [vp]
+        L.rtr_cloud_size.argtypes = [vp]
+        L.rtr_cloud_transform.argtypes = [vp, vp]
+        L.rtr_cloud_download.argtypes = [vp, vp]
+        L.rtr_radius_neighbors.argtypes = [vp, C.c_float, vp, vp, vp, ll, C.POINTER(ll)]
+        L.rtr_nearest.argtypes = [vp, vp, C.c_int, vp, vp]
+        L.rtr_normals.argtypes = [vp, C.c_float, vp]
+        L.rtr_harris3d.argtypes = [vp, C.c_float, C.c_float, C.c_int, C.c_int, vp, vp, vp, C.c_int, ip]
+        L.rtr_fpfh.argtypes = [vp, C.c_float, vp]
+        L.rtr_match_features.argtypes = [vp, vp, C.c_int, vp, vp]
+        L.rtr_ransac_prerejective.argtypes = [vp, vp, C.POINTER(RansacParams), C.POINTER(PoseResult)]
+        L.rtr_icp.argtypes = [vp, vp, C.POINTER(IcpParams), vp, C.POINTER(PoseResult)]
+        L.rtr_register.argtypes = [vp, vp, C.POINTER(RegisterParams), C.POINTER(PoseResult)]
+        L.rtr_register_host.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.POINTER(RegisterParams), C.POINTER(PoseResult)]
+        L.ComputeTDFWithCuda.argtypes = [vp, vp, C.c_int, C.c_int]
+        L.rtr_tdf_batch.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
+        L.rtr_tdf_batch_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
+        L.rtr_default_register_params.argtypes = [C.POINTER(RegisterParams)]
+        _LIB = L
+    return _LIB
+
+
+def check(fn, code):
+    if code != 0:
+        raise RtrError(fn, code)

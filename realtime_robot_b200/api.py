@@ -1,0 +1,186 @@
+"""Host-side mirror of the reference's registration surface over the C ABI (include/rtr.h).
+
+Names follow the reference: a cloud object owns the points and its per-cloud stages the way ModelPoint / ScanPoint do
+(model_point.h:81-96, scan_point.h:43-54: getKeypoint), and the free functions mirror function.h (keyPointICP -> icp,
+Ransac -> ransac_prerejective).  Everything here is plumbing: ctypes calls into librtr.so.  No compute happens in Python
+and there is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .params import (IcpParams, PoseResult, RansacParams, RegisterParams, default_register_params,  # noqa: F401
+                     pose_to_colmajor)
+
+
+def _f32(a, cols=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if cols is not None and (a.ndim != 2 or a.shape[1] != cols):
+        raise ValueError(f"expected an (N, {cols}) float32 array, got {a.shape}")
+    return a
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """One per GPU: device id, one stream, stream-ordered memory pool (rtr_context_create)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _lib.check("rtr_context_create", _lib.lib().rtr_context_create(device, C.byref(self._h)))
+        self.device = device
+
+    def sync(self):
+        _lib.check("rtr_context_sync", _lib.lib().rtr_context_sync(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(_lib.lib().rtr_context_launches(self._h))
+
+    def record(self, slot: int):
+        _lib.check("rtr_event_record", _lib.lib().rtr_event_record(self._h, slot))
+
+    def elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        _lib.check("rtr_event_elapsed_ms", _lib.lib().rtr_event_elapsed_ms(self._h, a, b, C.byref(ms)))
+        return float(ms.value)
+
+    def close(self):
+        if self._h:
+            _lib.lib().rtr_context_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Cloud:
+    """Device-resident pcl::PointCloud<pcl::PointXYZ> (n x 16 B) plus its cached stages."""
+
+    def __init__(self, ctx: Context, xyz1=None, device_ptr=None, n=None):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        if device_ptr is not None:
+            _lib.check("rtr_cloud_from_device", _lib.lib().rtr_cloud_from_device(ctx._h, C.c_void_p(device_ptr), n, C.byref(self._h)))
+            self.n = n
+        else:
+            xyz1 = _f32(xyz1, 4)
+            self.n = len(xyz1)
+            _lib.check("rtr_cloud_upload", _lib.lib().rtr_cloud_upload(ctx._h, _ptr(xyz1), self.n, C.byref(self._h)))
+            ctx.sync()   # the numpy buffer may be released as soon as we return
+
+    def free(self):
+        if self._h:
+            _lib.lib().rtr_cloud_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def download(self) -> np.ndarray:
+        out = np.zeros((self.n, 4), dtype=np.float32)
+        _lib.check("rtr_cloud_download", _lib.lib().rtr_cloud_download(self._h, _ptr(out)))
+        return out
+
+    def transform(self, pose):
+        m = pose_to_colmajor(pose)
+        _lib.check("rtr_cloud_transform", _lib.lib().rtr_cloud_transform(self._h, _ptr(m)))
+
+    def radius_neighbors(self, radius: float):
+        counts = np.zeros(self.n, dtype=np.int32)
+        offsets = np.zeros(self.n + 1, dtype=np.int64)
+        total = C.c_longlong()
+        _lib.check("rtr_radius_neighbors", _lib.lib().rtr_radius_neighbors(self._h, radius, _ptr(counts), _ptr(offsets), None, 0, C.byref(total)))
+        idx = np.zeros(max(total.value, 1), dtype=np.int32)
+        _lib.check("rtr_radius_neighbors", _lib.lib().rtr_radius_neighbors(self._h, radius, _ptr(counts), _ptr(offsets), _ptr(idx), total.value, C.byref(total)))
+        return counts, offsets, idx[:total.value]
+
+    def nearest(self, queries_xyz1):
+        q = _f32(queries_xyz1, 4)
+        idx = np.zeros(len(q), dtype=np.int32)
+        d2 = np.zeros(len(q), dtype=np.float32)
+        _lib.check("rtr_nearest", _lib.lib().rtr_nearest(self._h, _ptr(q), len(q), _ptr(idx), _ptr(d2)))
+        return idx, d2
+
+    def normals(self, radius: float) -> np.ndarray:
+        out = np.zeros((self.n, 4), dtype=np.float32)
+        _lib.check("rtr_normals", _lib.lib().rtr_normals(self._h, radius, _ptr(out)))
+        return out
+
+    def harris3d(self, radius: float, threshold: float, nms: int = 1, refine: int = 1):
+        """ModelPoint::getKeypoint / ScanPoint::getKeypoint: returns (response, corner indices, corner xyz1)."""
+        resp = np.zeros(self.n, dtype=np.float32)
+        idx = np.zeros(max(self.n, 1), dtype=np.int32)
+        xyz = np.zeros((max(self.n, 1), 4), dtype=np.float32)
+        m = C.c_int()
+        _lib.check("rtr_harris3d", _lib.lib().rtr_harris3d(self._h, radius, threshold, nms, refine, _ptr(resp), _ptr(idx), _ptr(xyz), self.n, C.byref(m)))
+        return resp, idx[:m.value].copy(), xyz[:m.value].copy()
+
+    def fpfh(self, radius: float) -> np.ndarray:
+        out = np.zeros((self.n, 33), dtype=np.float32)
+        _lib.check("rtr_fpfh", _lib.lib().rtr_fpfh(self._h, radius, _ptr(out)))
+        return out
+
+    def match_features(self, target: "Cloud", k: int):
+        idx = np.zeros((self.n, k), dtype=np.int32)
+        dist = np.zeros((self.n, k), dtype=np.float32)
+        _lib.check("rtr_match_features", _lib.lib().rtr_match_features(self._h, target._h, k, _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+
+def ransac_prerejective(source: Cloud, target: Cloud, params: RansacParams) -> PoseResult:
+    res = PoseResult()
+    _lib.check("rtr_ransac_prerejective", _lib.lib().rtr_ransac_prerejective(source._h, target._h, C.byref(params), C.byref(res)))
+    return res
+
+
+def icp(source: Cloud, target: Cloud, params: IcpParams, init=None) -> PoseResult:
+    """keyPointICP (function.h:111-123): source = model, target = scan."""
+    res = PoseResult()
+    m = None if init is None else pose_to_colmajor(init)
+    _lib.check("rtr_icp", _lib.lib().rtr_icp(source._h, target._h, C.byref(params), _ptr(m), C.byref(res)))
+    return res
+
+
+def register(model: Cloud, scene: Cloud, params: RegisterParams) -> PoseResult:
+    res = PoseResult()
+    _lib.check("rtr_register", _lib.lib().rtr_register(model._h, scene._h, C.byref(params), C.byref(res)))
+    return res
+
+
+def register_host(ctx: Context, model_xyz1, scene_xyz1, params: RegisterParams) -> PoseResult:
+    """Host clouds in, host result out: upload + register + free inside one C-ABI call."""
+    m, s = _f32(model_xyz1, 4), _f32(scene_xyz1, 4)
+    res = PoseResult()
+    _lib.check("rtr_register_host", _lib.lib().rtr_register_host(ctx._h, _ptr(m), len(m), _ptr(s), len(s), C.byref(params), C.byref(res)))
+    return res
+
+
+def compute_tdf_with_cuda(voxel_grid_occ, voxel_grid_tdf, voxel_grid_dim: int, num_occ: int) -> int:
+    """The reference FFI, unchanged (key_point.h:35-36).  voxel_grid_tdf: 27000 float32, modified in place."""
+    occ = np.ascontiguousarray(voxel_grid_occ, dtype=np.int32)
+    if voxel_grid_tdf.dtype != np.float32 or not voxel_grid_tdf.flags["C_CONTIGUOUS"] or voxel_grid_tdf.size < 27000:
+        raise ValueError("voxel_grid_tdf must be a contiguous float32 array of >= 27000 elements")
+    return int(_lib.lib().ComputeTDFWithCuda(_ptr(occ) if occ.size else None, _ptr(voxel_grid_tdf), voxel_grid_dim, num_occ))
+
+
+def tdf_batch(ctx: Context, occ_lists, dim: int = 30) -> np.ndarray:
+    """All keypoints of a cloud in one launch; occ_lists: sequence of (k_i, 3) int arrays."""
+    offs = np.zeros(len(occ_lists) + 1, dtype=np.int32)
+    for i, o in enumerate(occ_lists):
+        offs[i + 1] = offs[i] + len(o)
+    occ = (np.concatenate([np.asarray(o, dtype=np.int32).reshape(-1, 3) for o in occ_lists]) if len(occ_lists)
+           else np.zeros((0, 3), dtype=np.int32))
+    occ = np.ascontiguousarray(occ, dtype=np.int32)
+    out = np.zeros((len(occ_lists), dim ** 3), dtype=np.float32)
+    _lib.check("rtr_tdf_batch", _lib.lib().rtr_tdf_batch(ctx._h, _ptr(occ) if occ.size else None, _ptr(offs), len(occ_lists), dim, _ptr(out)))
+    return out

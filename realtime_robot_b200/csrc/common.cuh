@@ -1,0 +1,354 @@
+// common.cuh — shared host/device definitions of librtr.so (sm_100a only).
+//
+// Arithmetic contract (DESIGN.md "Parity contract"): neighbour membership is decided by the float expression
+// (dx*dx + dy*dy) + dz*dz with no FMA (FLANN L2_Simple); reductions accumulate in fp64 and are
+// stored as fp32; small solves are cyclic Jacobi in fp64 using + - * / sqrt only.  The library is compiled with
+// -fmad=false so that no contraction changes those operation sequences.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cfloat>
+#include <map>
+#include <vector>
+#include "../../include/rtr.h"
+
+#define RTR_NUM_EVENTS 16
+
+// ----------------------------------------------------------------------------- host-side objects
+struct DevGrid {
+    float h = 0.f, inv_h = 0.f;
+    float mnx = 0.f, mny = 0.f, mnz = 0.f;
+    int dx = 1, dy = 1, dz = 1;
+    int ncells = 1;
+    int n = 0;
+    int* cell_begin = nullptr;       // ncells + 1
+    float4* sorted = nullptr;        // points in cell order; .w carries the ORIGINAL index (int bits)
+    float4* sorted_normals = nullptr;  // optional: normals4 permuted into this grid's order
+    int normals_version = -1;
+};
+
+// what the kernels see (passed by value)
+struct GridView {
+    float inv_h, h;
+    float mnx, mny, mnz;
+    int dx, dy, dz;
+    int n;
+    const int* __restrict__ cell_begin;
+    const float4* __restrict__ sorted;
+};
+
+struct rtr_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    int sm_count = 148;
+    cudaEvent_t events[RTR_NUM_EVENTS] = {};
+    // small pinned staging area for results / counters
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+
+struct rtr_cloud {
+    rtr_context* ctx = nullptr;
+    int n = 0;
+    float4* pts = nullptr;                    // original order
+    float bb_min[3] = {0, 0, 0}, bb_max[3] = {0, 0, 0};
+    bool bbox_valid = false;
+    std::map<int, DevGrid> grids;             // keyed by float bits of the requested cell size
+    float4* normals = nullptr;   float normals_radius = -1.f;  int normals_version = 0;
+    float*  response = nullptr;
+    float*  fpfh = nullptr;      float fpfh_radius = -1.f;
+    int*    knn = nullptr;       float* knn_dist = nullptr;    int knn_k = 0;   int knn_target_n = 0;
+    int n_keypoints = -1;
+};
+
+#define RTR_CHECK(call, tag)                                                                       \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            fprintf(stderr, "rtr[%s] %s failed: %s\n", tag, #call, cudaGetErrorString(e__));       \
+            return (int)e__;                                                                       \
+        }                                                                                          \
+    } while (0)
+
+#define RTR_LAUNCH_CHECK(ctx, tag)                                                                 \
+    do {                                                                                           \
+        (ctx)->launches++;                                                                         \
+        cudaError_t e__ = cudaGetLastError();                                                      \
+        if (e__ != cudaSuccess) {                                                                  \
+            fprintf(stderr, "rtr[%s] kernel launch failed: %s\n", tag, cudaGetErrorString(e__));   \
+            return (int)e__;                                                                       \
+        }                                                                                          \
+    } while (0)
+
+static inline int rtr_fail(const char* tag, const char* msg, int code) {
+    fprintf(stderr, "rtr[%s] %s\n", tag, msg);
+    return code;
+}
+
+template <typename T>
+static inline int dev_alloc(rtr_context* ctx, T** p, size_t count, const char* tag) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    RTR_CHECK(cudaMallocAsync((void**)p, count * sizeof(T), ctx->stream), tag);
+    return 0;
+}
+template <typename T>
+static inline void dev_free(rtr_context* ctx, T* p) {
+    if (p) cudaFreeAsync((void*)p, ctx->stream);
+}
+
+// internal API between translation units
+int  rtr_get_grid(rtr_cloud* c, float cell, DevGrid** out);          // build-or-fetch a grid with cell size >= `cell`
+int  rtr_grid_normals(rtr_cloud* c, DevGrid* g);                     // make g->sorted_normals current
+GridView rtr_view(const DevGrid* g);
+int  rtr_ensure_bbox(rtr_cloud* c);
+void rtr_invalidate(rtr_cloud* c);
+float rtr_icp_cell(const rtr_cloud* c);
+int  rtr_normals_dev(rtr_cloud* c, float radius);
+int  rtr_harris_dev(rtr_cloud* c, float radius, float threshold, int nms, int refine, int** d_kp_idx, float4** d_kp_xyz,
+                    int** d_count);
+int  rtr_fpfh_dev(rtr_cloud* c, float radius);
+int  rtr_match_dev(rtr_cloud* src, rtr_cloud* tgt, int k);
+int  rtr_ransac_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_ransac_params* p, rtr_pose_result* d_result);
+int  rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const float* d_init_pose16, int init_from_result,
+                 rtr_pose_result* d_result);
+
+// ----------------------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float dist2f(float ax, float ay, float az, float bx, float by, float bz) {
+    float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// pcl::transformPointCloud semantics: ((m00*x + m01*y) + m02*z) + m03, column-major m, float, no FMA
+__device__ __forceinline__ float4 xform(const float* __restrict__ m, float4 p) {
+    float4 o;
+    o.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], p.x), __fmul_rn(m[4], p.y)), __fmul_rn(m[8], p.z)), m[12]);
+    o.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[1], p.x), __fmul_rn(m[5], p.y)), __fmul_rn(m[9], p.z)), m[13]);
+    o.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[2], p.x), __fmul_rn(m[6], p.y)), __fmul_rn(m[10], p.z)), m[14]);
+    o.w = 1.0f;
+    return o;
+}
+
+// c = a * b (4x4 column-major float), k left to right, no FMA
+__device__ __forceinline__ void matmul4(const float* a, const float* b, float* c) {
+    float out[16];
+#pragma unroll
+    for (int col = 0; col < 4; ++col)
+#pragma unroll
+        for (int row = 0; row < 4; ++row) {
+            float acc = __fmul_rn(a[row], b[col * 4]);
+#pragma unroll
+            for (int k = 1; k < 4; ++k) acc = __fadd_rn(acc, __fmul_rn(a[k * 4 + row], b[col * 4 + k]));
+            out[col * 4 + row] = acc;
+        }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = out[i];
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint32_t rand_below(uint64_t seed, uint64_t h, uint32_t draw, uint32_t n) {
+    uint64_t r = mix64(mix64(seed + 0x9E3779B97F4A7C15ULL * (h + 1)) + 0x9E3779B97F4A7C15ULL * (uint64_t)(draw + 1));
+    return (uint32_t)(((r >> 32) * (uint64_t)n) >> 32);
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// unclamped cell coordinate of a float coordinate
+__device__ __forceinline__ int cell_coord(float v, float mn, float inv_h) {
+    float f = floorf(__fmul_rn(__fsub_rn(v, mn), inv_h));
+    // keep the int conversion defined for far-away / non-finite queries
+    if (!(f > -1.0e9f)) f = -1.0e9f;
+    if (f > 1.0e9f) f = 1.0e9f;
+    return (int)f;
+}
+
+__device__ __forceinline__ int cell_key(const GridView& g, int x, int y, int z) { return (z * g.dy + y) * g.dx + x; }
+
+// Visit every point of the 3x3x3 cell block around q: f(point_with_index, d2).  The three x-adjacent cells of a row are
+// one contiguous range of the cell-sorted array, so a query touches 9 ranges.  Returns false if q is farther than one
+// cell outside the grid (no neighbour within h possible).
+template <typename F>
+__device__ __forceinline__ bool for_block27(const GridView& g, float qx, float qy, float qz, F&& f) {
+    int cx = cell_coord(qx, g.mnx, g.inv_h), cy = cell_coord(qy, g.mny, g.inv_h), cz = cell_coord(qz, g.mnz, g.inv_h);
+    if (cx < -1 || cy < -1 || cz < -1 || cx > g.dx || cy > g.dy || cz > g.dz) return false;
+    cx = clampi(cx, 0, g.dx - 1); cy = clampi(cy, 0, g.dy - 1); cz = clampi(cz, 0, g.dz - 1);
+    int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
+    for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
+        for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y) {
+            int s0 = __ldg(g.cell_begin + cell_key(g, x0, y, z));
+            int s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
+            for (int s = s0; s < s1; ++s) {
+                float4 p = __ldg(g.sorted + s);
+                f(s, p, dist2f(qx, qy, qz, p.x, p.y, p.z));
+            }
+        }
+    return true;
+}
+
+// exact nearest neighbour with expanding Chebyshev rings; ties -> lowest original index.
+__device__ __forceinline__ void grid_nearest(const GridView& g, float qx, float qy, float qz, int& best, float& best_d2) {
+    best = -1; best_d2 = FLT_MAX;
+    if (g.n == 0) return;
+    int cx = clampi(cell_coord(qx, g.mnx, g.inv_h), 0, g.dx - 1);
+    int cy = clampi(cell_coord(qy, g.mny, g.inv_h), 0, g.dy - 1);
+    int cz = clampi(cell_coord(qz, g.mnz, g.inv_h), 0, g.dz - 1);
+    // rings 0 and 1 together: 9 contiguous row ranges
+    {
+        int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
+        for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
+            for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y) {
+                int s0 = __ldg(g.cell_begin + cell_key(g, x0, y, z));
+                int s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
+                for (int s = s0; s < s1; ++s) {
+                    float4 p = __ldg(g.sorted + s);
+                    float d = dist2f(qx, qy, qz, p.x, p.y, p.z);
+                    int id = __float_as_int(p.w);
+                    if (d < best_d2 || (d == best_d2 && id < best)) { best_d2 = d; best = id; }
+                }
+            }
+    }
+    int maxr = max(g.dx, max(g.dy, g.dz));
+    for (int R = 1; R <= maxr; ++R) {
+        if (best >= 0) {
+            double lim = (double)R * (double)g.h * 0.999;
+            if ((double)best_d2 <= lim * lim) return;
+        }
+        int Rn = R + 1;   // visit shell Rn: rows whose (y,z) is on the shell take the full x span, others only the two x caps
+        for (int z = cz - Rn; z <= cz + Rn; ++z) {
+            if (z < 0 || z >= g.dz) continue;
+            for (int y = cy - Rn; y <= cy + Rn; ++y) {
+                if (y < 0 || y >= g.dy) continue;
+                bool full = (abs(z - cz) == Rn) || (abs(y - cy) == Rn);
+                int nseg = full ? 1 : 2;
+                for (int seg = 0; seg < nseg; ++seg) {
+                    int xa, xb;
+                    if (full) { xa = max(cx - Rn, 0); xb = min(cx + Rn, g.dx - 1); }
+                    else if (seg == 0) { xa = xb = cx - Rn; }
+                    else { xa = xb = cx + Rn; }
+                    if (xa < 0 || xb >= g.dx || xa > xb) continue;
+                    int s0 = __ldg(g.cell_begin + cell_key(g, xa, y, z));
+                    int s1 = __ldg(g.cell_begin + cell_key(g, xb, y, z) + 1);
+                    for (int s = s0; s < s1; ++s) {
+                        float4 p = __ldg(g.sorted + s);
+                        float d = dist2f(qx, qy, qz, p.x, p.y, p.z);
+                        int id = __float_as_int(p.w);
+                        if (d < best_d2 || (d == best_d2 && id < best)) { best_d2 = d; best = id; }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// cyclic Jacobi, symmetric NxN, fp64, + - * / sqrt only (same operation sequence as the oracle's restatement)
+template <int N>
+__device__ __forceinline__ void jacobi_eig(double (&a)[N][N], double (&v)[N][N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 24; ++sweep) {
+        double off = 0.0;
+#pragma unroll
+        for (int p = 0; p < N; ++p)
+#pragma unroll
+            for (int q = p + 1; q < N; ++q) off += fabs(a[p][q]);
+        if (off == 0.0) break;
+#pragma unroll
+        for (int p = 0; p < N; ++p)
+#pragma unroll
+            for (int q = p + 1; q < N; ++q) {
+                double apq = a[p][q];
+                if (apq != 0.0) {
+                    double g = 100.0 * fabs(apq);
+                    if (sweep > 3 && fabs(a[p][p]) + g == fabs(a[p][p]) && fabs(a[q][q]) + g == fabs(a[q][q])) {
+                        a[p][q] = 0.0; a[q][p] = 0.0;
+                    } else {
+                        double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
+                        double t = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        if (theta < 0) t = -t;
+                        double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                        a[p][p] = a[p][p] - t * apq;
+                        a[q][q] = a[q][q] + t * apq;
+                        a[p][q] = 0.0; a[q][p] = 0.0;
+#pragma unroll
+                        for (int r = 0; r < N; ++r) {
+                            if (r != p && r != q) {
+                                double arp = a[r][p], arq = a[r][q];
+                                a[r][p] = c * arp - s * arq; a[p][r] = a[r][p];
+                                a[r][q] = s * arp + c * arq; a[q][r] = a[r][q];
+                            }
+                            double vrp = v[r][p], vrq = v[r][q];
+                            v[r][p] = c * vrp - s * vrq;
+                            v[r][q] = s * vrp + c * vrq;
+                        }
+                    }
+                }
+            }
+    }
+}
+
+// Horn's unit-quaternion rigid fit from raw fp64 sums (ss = sum s, st = sum t, m[a][b] = sum s_a t_b, n pairs);
+// writes a column-major float 4x4 (source -> target).
+__device__ __forceinline__ void horn_pose(const double* ss, const double* st, const double* m9, double n, float* pose) {
+    double cs[3], ct[3], S[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { cs[a] = ss[a] / n; ct[a] = st[a] / n; }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) S[a][b] = m9[a * 3 + b] - n * cs[a] * ct[b];
+    double N[4][4], V[4][4];
+    N[0][0] = S[0][0] + S[1][1] + S[2][2];
+    N[0][1] = S[1][2] - S[2][1]; N[0][2] = S[2][0] - S[0][2]; N[0][3] = S[0][1] - S[1][0];
+    N[1][1] = S[0][0] - S[1][1] - S[2][2];
+    N[1][2] = S[0][1] + S[1][0]; N[1][3] = S[2][0] + S[0][2];
+    N[2][2] = -S[0][0] + S[1][1] - S[2][2];
+    N[2][3] = S[1][2] + S[2][1];
+    N[3][3] = -S[0][0] - S[1][1] + S[2][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (j < i) N[i][j] = N[j][i];
+    jacobi_eig<4>(N, V);
+    double best = N[0][0], q0 = V[0][0], q1 = V[1][0], q2 = V[2][0], q3 = V[3][0];
+#pragma unroll
+    for (int i = 1; i < 4; ++i) if (N[i][i] > best) { best = N[i][i]; q0 = V[0][i]; q1 = V[1][i]; q2 = V[2][i]; q3 = V[3][i]; }
+    double nq = sqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+    q0 /= nq; q1 /= nq; q2 /= nq; q3 /= nq;
+    double R[3][3];
+    R[0][0] = q0 * q0 + q1 * q1 - q2 * q2 - q3 * q3; R[0][1] = 2.0 * (q1 * q2 - q0 * q3); R[0][2] = 2.0 * (q1 * q3 + q0 * q2);
+    R[1][0] = 2.0 * (q1 * q2 + q0 * q3); R[1][1] = q0 * q0 - q1 * q1 + q2 * q2 - q3 * q3; R[1][2] = 2.0 * (q2 * q3 - q0 * q1);
+    R[2][0] = 2.0 * (q1 * q3 - q0 * q2); R[2][1] = 2.0 * (q2 * q3 + q0 * q1); R[2][2] = q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        double t = ct[r] - ((R[r][0] * cs[0] + R[r][1] * cs[1]) + R[r][2] * cs[2]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) pose[c * 4 + r] = (float)R[r][c];
+        pose[12 + r] = (float)t;
+    }
+    pose[3] = 0.f; pose[7] = 0.f; pose[11] = 0.f; pose[15] = 1.f;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ bool finite3(float4 n) { return isfinite(n.x) && isfinite(n.y) && isfinite(n.z); }
+
+#endif  // __CUDACC__

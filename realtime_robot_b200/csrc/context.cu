@@ -1,0 +1,458 @@
+// context.cu — contexts, device-resident clouds, the uniform-grid neighbour index, and the two index-level entry
+// points (radius sets, 1-NN).  The grid replaces pcl::search::KdTree / KdTreeFLANN, which the reference only reaches
+// through HarrisKeypoint3D (model_point.h:127-136) and IterativeClosestPoint (function.h:112-117).
+//
+// Layout in HBM: a cloud is n x float4 (pcl::PointXYZ's own 16-byte layout).  A grid holds the same points permuted
+// into cell order (key = (z*dy + y)*dx + x, stable, so in-cell order is ascending original index) with the original
+// index in .w, plus cell_begin[ncells+1].  The three x-adjacent cells of a row are one contiguous range, so a
+// 27-cell query is 9 coalesced range scans.
+#include "common.cuh"
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+// ----------------------------------------------------------------------------- kernels
+__global__ void k_cell_keys(const float4* __restrict__ pts, int n, float mnx, float mny, float mnz, float inv_h, int dx,
+                            int dy, int dz, int* __restrict__ keys, int* __restrict__ vals, int* __restrict__ counts) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = __ldg(pts + i);
+    int cx = clampi(cell_coord(p.x, mnx, inv_h), 0, dx - 1);
+    int cy = clampi(cell_coord(p.y, mny, inv_h), 0, dy - 1);
+    int cz = clampi(cell_coord(p.z, mnz, inv_h), 0, dz - 1);
+    int key = (cz * dy + cy) * dx + cx;
+    keys[i] = key;
+    vals[i] = i;
+    atomicAdd(counts + key, 1);
+}
+
+__global__ void k_gather_sorted(const float4* __restrict__ pts, const int* __restrict__ order, int n, float4* __restrict__ sorted) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int i = order[s];
+    float4 p = __ldg(pts + i);
+    p.w = __int_as_float(i);
+    sorted[s] = p;
+}
+
+__global__ void k_permute4(const float4* __restrict__ src, const float4* __restrict__ sorted, int n, float4* __restrict__ dst) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    dst[s] = __ldg(src + __float_as_int(__ldg(sorted + s).w));
+}
+
+__device__ __forceinline__ unsigned enc_f(float f) { unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__host__ __device__ __forceinline__ float dec_f(unsigned u) {
+    unsigned v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    float f;
+#ifdef __CUDA_ARCH__
+    f = __uint_as_float(v);
+#else
+    memcpy(&f, &v, 4);
+#endif
+    return f;
+}
+
+// bounding box of finite points: 6 ordered-uint atomics (min x,y,z, max x,y,z)
+__global__ void k_bbox(const float4* __restrict__ pts, int n, unsigned* __restrict__ box) {
+    unsigned mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 p = __ldg(pts + i);
+        if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+            unsigned e[3] = {enc_f(p.x), enc_f(p.y), enc_f(p.z)};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { mn[a] = min(mn[a], e[a]); mx[a] = max(mx[a], e[a]); }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = min(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = max(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+        if ((threadIdx.x & 31) == 0) { atomicMin(box + a, mn[a]); atomicMax(box + 3 + a, mx[a]); }
+    }
+}
+
+__global__ void k_transform_inplace(float4* __restrict__ pts, int n, const float* __restrict__ pose) {
+    __shared__ float m[16];
+    if (threadIdx.x < 16) m[threadIdx.x] = pose[threadIdx.x];
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pts[i] = xform(m, pts[i]);
+}
+
+// radius sets of the cloud's own points: pass 0 counts, pass 1 fills (then sorts each list ascending in place)
+__global__ void k_radius_count(GridView g, float r2, int* __restrict__ counts) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= g.n) return;
+    float4 q = __ldg(g.sorted + s);
+    int c = 0;
+    for_block27(g, q.x, q.y, q.z, [&](int, float4, float d2) { if (d2 < r2) ++c; });
+    counts[__float_as_int(q.w)] = c;
+}
+__global__ void k_radius_fill(GridView g, float r2, const long long* __restrict__ offsets, int* __restrict__ indices) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= g.n) return;
+    float4 q = __ldg(g.sorted + s);
+    int* out = indices + offsets[__float_as_int(q.w)];
+    int c = 0;
+    for_block27(g, q.x, q.y, q.z, [&](int, float4 p, float d2) {
+        if (d2 < r2) {   // insertion keeps the list ascending
+            int id = __float_as_int(p.w), j = c++;
+            while (j > 0 && out[j - 1] > id) { out[j] = out[j - 1]; --j; }
+            out[j] = id;
+        }
+    });
+}
+
+__global__ void k_nearest(GridView g, const float4* __restrict__ q, int nq, int* __restrict__ idx, float* __restrict__ d2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    float4 p = __ldg(q + i);
+    int b; float bd;
+    grid_nearest(g, p.x, p.y, p.z, b, bd);
+    idx[i] = b; d2[i] = bd;
+}
+
+// ----------------------------------------------------------------------------- host
+static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+
+GridView rtr_view(const DevGrid* g) {
+    GridView v;
+    v.inv_h = g->inv_h; v.h = g->h; v.mnx = g->mnx; v.mny = g->mny; v.mnz = g->mnz;
+    v.dx = g->dx; v.dy = g->dy; v.dz = g->dz; v.n = g->n; v.cell_begin = g->cell_begin; v.sorted = g->sorted;
+    return v;
+}
+
+int rtr_ensure_bbox(rtr_cloud* c) {
+    if (c->bbox_valid) return 0;
+    rtr_context* ctx = c->ctx;
+    unsigned* d_box = nullptr;
+    if (int e = dev_alloc(ctx, &d_box, 6, "bbox")) return e;
+    unsigned init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    RTR_CHECK(cudaMemcpyAsync(d_box, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream), "bbox");
+    if (c->n > 0) {
+        k_bbox<<<std::min(nblk(c->n, 256), 4 * ctx->sm_count), 256, 0, ctx->stream>>>(c->pts, c->n, d_box);
+        RTR_LAUNCH_CHECK(ctx, "bbox");
+    }
+    unsigned h_box[6];
+    RTR_CHECK(cudaMemcpyAsync(h_box, d_box, sizeof(h_box), cudaMemcpyDeviceToHost, ctx->stream), "bbox");
+    RTR_CHECK(cudaStreamSynchronize(ctx->stream), "bbox");
+    dev_free(ctx, d_box);
+    for (int a = 0; a < 3; ++a) {
+        if (h_box[a] == 0xffffffffu && h_box[3 + a] == 0u) { c->bb_min[a] = 0.f; c->bb_max[a] = 0.f; }
+        else { c->bb_min[a] = dec_f(h_box[a]); c->bb_max[a] = dec_f(h_box[3 + a]); }
+    }
+    c->bbox_valid = true;
+    return 0;
+}
+
+static void free_grid(rtr_context* ctx, DevGrid& g) {
+    dev_free(ctx, g.cell_begin); dev_free(ctx, g.sorted); dev_free(ctx, g.sorted_normals);
+    g.cell_begin = nullptr; g.sorted = nullptr; g.sorted_normals = nullptr;
+}
+
+void rtr_invalidate(rtr_cloud* c) {
+    rtr_context* ctx = c->ctx;
+    for (auto& kv : c->grids) free_grid(ctx, kv.second);
+    c->grids.clear();
+    dev_free(ctx, c->normals); c->normals = nullptr; c->normals_radius = -1.f; c->normals_version++;
+    dev_free(ctx, c->response); c->response = nullptr;
+    dev_free(ctx, c->fpfh); c->fpfh = nullptr; c->fpfh_radius = -1.f;
+    dev_free(ctx, c->knn); c->knn = nullptr; dev_free(ctx, c->knn_dist); c->knn_dist = nullptr; c->knn_k = 0;
+    c->n_keypoints = -1;
+}
+
+float rtr_icp_cell(const rtr_cloud* c) {
+    // ~2x the mean sample spacing, estimated from the bounding-box surface (clouds here are surface samples)
+    double ex = (double)c->bb_max[0] - c->bb_min[0], ey = (double)c->bb_max[1] - c->bb_min[1], ez = (double)c->bb_max[2] - c->bb_min[2];
+    double area = 2.0 * (ex * ey + ey * ez + ex * ez);
+    double cell = 2.0 * std::sqrt(std::max(area, 1e-12) / (double)std::max(c->n, 1));
+    return (float)std::max(cell, 1e-4);
+}
+
+int rtr_get_grid(rtr_cloud* c, float cell, DevGrid** out) {
+    int keybits;
+    memcpy(&keybits, &cell, 4);
+    auto it = c->grids.find(keybits);
+    if (it != c->grids.end()) { *out = &it->second; return 0; }
+    rtr_context* ctx = c->ctx;
+    if (int e = rtr_ensure_bbox(c)) return e;
+    DevGrid g;
+    g.n = c->n;
+    // the cell is 0.1 % wider than the radius it serves so that float cell assignment can never put two points that
+    // are within the radius more than one cell apart (DESIGN.md "grid exactness")
+    double h = (double)cell * 1.001;
+    for (;;) {
+        double cells = 1;
+        bool ok = true;
+        int d[3];
+        for (int a = 0; a < 3; ++a) {
+            double ext = (double)c->bb_max[a] - (double)c->bb_min[a];
+            double da = std::floor(ext / h) + 2;     // +1 for the floor, +1 slack for float rounding at the upper face
+            if (da > 2048) ok = false;
+            d[a] = (int)std::min(da, 4096.0);
+            cells *= d[a];
+        }
+        if (ok && cells <= 67108864.0) { g.dx = d[0]; g.dy = d[1]; g.dz = d[2]; break; }
+        h *= 1.25;
+    }
+    g.h = (float)h; g.inv_h = 1.0f / g.h;
+    g.mnx = c->bb_min[0]; g.mny = c->bb_min[1]; g.mnz = c->bb_min[2];
+    g.ncells = g.dx * g.dy * g.dz;
+    int n = c->n;
+    int *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr, *counts = nullptr;
+    if (int e = dev_alloc(ctx, &keys, n, "grid")) return e;
+    if (int e = dev_alloc(ctx, &vals, n, "grid")) return e;
+    if (int e = dev_alloc(ctx, &keys2, n, "grid")) return e;
+    if (int e = dev_alloc(ctx, &vals2, n, "grid")) return e;
+    if (int e = dev_alloc(ctx, &counts, (size_t)g.ncells + 1, "grid")) return e;
+    if (int e = dev_alloc(ctx, &g.cell_begin, (size_t)g.ncells + 1, "grid")) return e;
+    if (int e = dev_alloc(ctx, &g.sorted, n, "grid")) return e;
+    RTR_CHECK(cudaMemsetAsync(counts, 0, ((size_t)g.ncells + 1) * sizeof(int), ctx->stream), "grid");
+    if (n > 0) {
+        k_cell_keys<<<nblk(n, 256), 256, 0, ctx->stream>>>(c->pts, n, g.mnx, g.mny, g.mnz, g.inv_h, g.dx, g.dy, g.dz, keys, vals, counts);
+        RTR_LAUNCH_CHECK(ctx, "grid.keys");
+    }
+    int end_bit = 1;
+    while ((1LL << end_bit) < (long long)g.ncells) ++end_bit;
+    size_t tb_sort = 0, tb_scan = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb_sort, keys, keys2, vals, vals2, n, 0, end_bit, ctx->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb_scan, counts, g.cell_begin, g.ncells + 1, ctx->stream);
+    void* temp = nullptr;
+    size_t tb = std::max(tb_sort, tb_scan);
+    if (int e = dev_alloc(ctx, (char**)&temp, tb, "grid")) return e;
+    if (n > 0) RTR_CHECK(cub::DeviceRadixSort::SortPairs(temp, tb_sort, keys, keys2, vals, vals2, n, 0, end_bit, ctx->stream), "grid.sort");
+    RTR_CHECK(cub::DeviceScan::ExclusiveSum(temp, tb_scan, counts, g.cell_begin, g.ncells + 1, ctx->stream), "grid.scan");
+    if (n > 0) {
+        k_gather_sorted<<<nblk(n, 256), 256, 0, ctx->stream>>>(c->pts, vals2, n, g.sorted);
+        RTR_LAUNCH_CHECK(ctx, "grid.gather");
+    }
+    dev_free(ctx, (char*)temp); dev_free(ctx, keys); dev_free(ctx, vals); dev_free(ctx, keys2); dev_free(ctx, vals2); dev_free(ctx, counts);
+    auto ins = c->grids.emplace(keybits, g);
+    *out = &ins.first->second;
+    return 0;
+}
+
+int rtr_grid_normals(rtr_cloud* c, DevGrid* g) {
+    if (!c->normals) return rtr_fail("grid.normals", "normals have not been computed on this cloud", RTR_ERR_NOT_READY);
+    if (g->sorted_normals && g->normals_version == c->normals_version) return 0;
+    rtr_context* ctx = c->ctx;
+    if (!g->sorted_normals) if (int e = dev_alloc(ctx, &g->sorted_normals, c->n, "grid.normals")) return e;
+    if (c->n > 0) {
+        k_permute4<<<nblk(c->n, 256), 256, 0, ctx->stream>>>(c->normals, g->sorted, c->n, g->sorted_normals);
+        RTR_LAUNCH_CHECK(ctx, "grid.normals");
+    }
+    g->normals_version = c->normals_version;
+    return 0;
+}
+
+extern "C" {
+
+void rtr_default_register_params(rtr_register_params* p) {
+    memset(p, 0, sizeof(*p));
+    p->normal_radius = 0.05f; p->harris_radius = 0.05f; p->harris_threshold = 0.01f; p->harris_nms = 1; p->harris_refine = 1;
+    p->fpfh_radius = 0.10f; p->run_icp = 1;
+    p->ransac.max_iterations = 50000; p->ransac.seed = 20170427ULL; p->ransac.correspondence_k = 5;
+    p->ransac.similarity_threshold = 0.9f; p->ransac.max_correspondence_distance = 0.0365f; p->ransac.inlier_fraction = 0.25f;
+    p->icp.max_iterations = 10; p->icp.mse_threshold_absolute = 1e-12;
+}
+
+int rtr_context_create(int device, rtr_context** out) {
+    if (!out) return rtr_fail("context", "null output pointer", RTR_ERR_INVALID);
+    *out = nullptr;
+    RTR_CHECK(cudaSetDevice(device), "context");
+    rtr_context* ctx = new rtr_context();
+    ctx->device = device;
+    RTR_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "context");
+    cudaDeviceProp prop;
+    RTR_CHECK(cudaGetDeviceProperties(&prop, device), "context");
+    ctx->sm_count = prop.multiProcessorCount;
+    // keep freed blocks in the stream-ordered pool: no cudaMalloc/cudaFree on the hot path (cf. kernel.cu:50-56,101-102)
+    cudaMemPool_t pool;
+    RTR_CHECK(cudaDeviceGetDefaultMemPool(&pool, device), "context");
+    unsigned long long thresh = ~0ULL;
+    RTR_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh), "context");
+    for (int i = 0; i < RTR_NUM_EVENTS; ++i) RTR_CHECK(cudaEventCreate(&ctx->events[i]), "context");
+    ctx->pinned_bytes = 1 << 16;
+    RTR_CHECK(cudaMallocHost(&ctx->pinned, ctx->pinned_bytes), "context");
+    *out = ctx;
+    return 0;
+}
+
+int rtr_context_destroy(rtr_context* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < RTR_NUM_EVENTS; ++i) if (ctx->events[i]) cudaEventDestroy(ctx->events[i]);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+int rtr_context_sync(rtr_context* ctx) {
+    if (!ctx) return rtr_fail("sync", "null context", RTR_ERR_INVALID);
+    RTR_CHECK(cudaStreamSynchronize(ctx->stream), "sync");
+    return 0;
+}
+
+void* rtr_context_stream(rtr_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+long long rtr_context_launches(rtr_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int rtr_event_record(rtr_context* ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= RTR_NUM_EVENTS) return rtr_fail("event", "bad slot", RTR_ERR_INVALID);
+    RTR_CHECK(cudaEventRecord(ctx->events[slot], ctx->stream), "event");
+    return 0;
+}
+int rtr_event_elapsed_ms(rtr_context* ctx, int a, int b, float* ms) {
+    if (!ctx || !ms || a < 0 || b < 0 || a >= RTR_NUM_EVENTS || b >= RTR_NUM_EVENTS) return rtr_fail("event", "bad slot", RTR_ERR_INVALID);
+    RTR_CHECK(cudaEventSynchronize(ctx->events[b]), "event");
+    RTR_CHECK(cudaEventElapsedTime(ms, ctx->events[a], ctx->events[b]), "event");
+    return 0;
+}
+
+static int cloud_new(rtr_context* ctx, int n, rtr_cloud** out) {
+    if (!ctx || !out || n < 0) return rtr_fail("cloud", "bad argument", RTR_ERR_INVALID);
+    *out = nullptr;
+    RTR_CHECK(cudaSetDevice(ctx->device), "cloud");
+    rtr_cloud* c = new rtr_cloud();
+    c->ctx = ctx; c->n = n;
+    if (int e = dev_alloc(ctx, &c->pts, n, "cloud")) { delete c; return e; }
+    *out = c;
+    return 0;
+}
+
+int rtr_cloud_upload(rtr_context* ctx, const float* host_xyz1, int n, rtr_cloud** out) {
+    if (n > 0 && !host_xyz1) return rtr_fail("cloud", "null points", RTR_ERR_INVALID);
+    if (int e = cloud_new(ctx, n, out)) return e;
+    rtr_cloud* c = *out;
+    if (n > 0) RTR_CHECK(cudaMemcpyAsync(c->pts, host_xyz1, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream), "cloud.h2d");
+    // the caller's buffer is host memory: take the bounding box here, so no device round trip is needed later
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    bool any = false;
+    for (int i = 0; i < n; ++i) {
+        const float* p = host_xyz1 + 4 * (size_t)i;
+        if (std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2])) {
+            any = true;
+            for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], p[a]); mx[a] = std::max(mx[a], p[a]); }
+        }
+    }
+    for (int a = 0; a < 3; ++a) { c->bb_min[a] = any ? mn[a] : 0.f; c->bb_max[a] = any ? mx[a] : 0.f; }
+    c->bbox_valid = true;
+    return 0;
+}
+
+int rtr_cloud_from_device(rtr_context* ctx, const float* dev_xyz1, int n, rtr_cloud** out) {
+    if (n > 0 && !dev_xyz1) return rtr_fail("cloud", "null points", RTR_ERR_INVALID);
+    if (int e = cloud_new(ctx, n, out)) return e;
+    if (n > 0) RTR_CHECK(cudaMemcpyAsync((*out)->pts, dev_xyz1, (size_t)n * 16, cudaMemcpyDeviceToDevice, ctx->stream), "cloud.d2d");
+    return 0;
+}
+
+int rtr_cloud_free(rtr_cloud* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->ctx->device);
+    rtr_invalidate(c);
+    dev_free(c->ctx, c->pts);
+    delete c;
+    return 0;
+}
+
+int rtr_cloud_size(const rtr_cloud* c) { return c ? c->n : -1; }
+
+int rtr_cloud_transform(rtr_cloud* c, const float* pose16) {
+    if (!c || !pose16) return rtr_fail("transform", "bad argument", RTR_ERR_INVALID);
+    rtr_context* ctx = c->ctx;
+    RTR_CHECK(cudaSetDevice(ctx->device), "transform");
+    float* d_pose = nullptr;
+    if (int e = dev_alloc(ctx, &d_pose, 16, "transform")) return e;
+    memcpy(ctx->pinned, pose16, 64);
+    RTR_CHECK(cudaMemcpyAsync(d_pose, ctx->pinned, 64, cudaMemcpyHostToDevice, ctx->stream), "transform");
+    if (c->n > 0) {
+        k_transform_inplace<<<nblk(c->n, 256), 256, 0, ctx->stream>>>(c->pts, c->n, d_pose);
+        RTR_LAUNCH_CHECK(ctx, "transform");
+    }
+    RTR_CHECK(cudaStreamSynchronize(ctx->stream), "transform");   // ctx->pinned is reused by the next call
+    dev_free(ctx, d_pose);
+    rtr_invalidate(c);
+    c->bbox_valid = false;
+    return 0;
+}
+
+int rtr_cloud_download(rtr_cloud* c, float* host_xyz1) {
+    if (!c || !host_xyz1) return rtr_fail("download", "bad argument", RTR_ERR_INVALID);
+    RTR_CHECK(cudaSetDevice(c->ctx->device), "download");
+    if (c->n > 0) RTR_CHECK(cudaMemcpyAsync(host_xyz1, c->pts, (size_t)c->n * 16, cudaMemcpyDeviceToHost, c->ctx->stream), "download");
+    RTR_CHECK(cudaStreamSynchronize(c->ctx->stream), "download");
+    return 0;
+}
+
+int rtr_radius_neighbors(rtr_cloud* c, float radius, int* host_counts, long long* host_offsets, int* host_indices,
+                         long long capacity, long long* total) {
+    if (!c || !host_counts || !(radius > 0.f)) return rtr_fail("radius", "bad argument", RTR_ERR_INVALID);
+    rtr_context* ctx = c->ctx;
+    RTR_CHECK(cudaSetDevice(ctx->device), "radius");
+    DevGrid* g;
+    if (int e = rtr_get_grid(c, radius, &g)) return e;
+    int n = c->n;
+    int* d_counts = nullptr;
+    if (int e = dev_alloc(ctx, &d_counts, n, "radius")) return e;
+    float r2 = radius * radius;
+    if (n > 0) {
+        k_radius_count<<<nblk(n, 128), 128, 0, ctx->stream>>>(rtr_view(g), r2, d_counts);
+        RTR_LAUNCH_CHECK(ctx, "radius.count");
+        RTR_CHECK(cudaMemcpyAsync(host_counts, d_counts, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream), "radius");
+    }
+    RTR_CHECK(cudaStreamSynchronize(ctx->stream), "radius");
+    std::vector<long long> off((size_t)n + 1, 0);
+    for (int i = 0; i < n; ++i) off[i + 1] = off[i] + host_counts[i];
+    if (host_offsets) memcpy(host_offsets, off.data(), sizeof(long long) * ((size_t)n + 1));
+    if (total) *total = off[n];
+    int rc = 0;
+    if (host_indices) {
+        if (capacity < off[n]) rc = rtr_fail("radius", "index buffer too small", RTR_ERR_CAPACITY);
+        else if (off[n] > 0) {
+            long long* d_off = nullptr; int* d_idx = nullptr;
+            if (int e = dev_alloc(ctx, &d_off, (size_t)n + 1, "radius")) return e;
+            if (int e = dev_alloc(ctx, &d_idx, (size_t)off[n], "radius")) return e;
+            RTR_CHECK(cudaMemcpyAsync(d_off, off.data(), sizeof(long long) * ((size_t)n + 1), cudaMemcpyHostToDevice, ctx->stream), "radius");
+            k_radius_fill<<<nblk(n, 128), 128, 0, ctx->stream>>>(rtr_view(g), r2, d_off, d_idx);
+            RTR_LAUNCH_CHECK(ctx, "radius.fill");
+            RTR_CHECK(cudaMemcpyAsync(host_indices, d_idx, (size_t)off[n] * 4, cudaMemcpyDeviceToHost, ctx->stream), "radius");
+            RTR_CHECK(cudaStreamSynchronize(ctx->stream), "radius");
+            dev_free(ctx, d_off); dev_free(ctx, d_idx);
+        }
+    }
+    dev_free(ctx, d_counts);
+    return rc;
+}
+
+int rtr_nearest(rtr_cloud* target, const float* host_queries_xyz1, int nq, int* host_idx, float* host_d2) {
+    if (!target || nq < 0 || (nq > 0 && (!host_queries_xyz1 || !host_idx || !host_d2))) return rtr_fail("nearest", "bad argument", RTR_ERR_INVALID);
+    rtr_context* ctx = target->ctx;
+    RTR_CHECK(cudaSetDevice(ctx->device), "nearest");
+    if (nq == 0) return 0;
+    if (int e = rtr_ensure_bbox(target)) return e;
+    DevGrid* g;
+    if (int e = rtr_get_grid(target, rtr_icp_cell(target), &g)) return e;
+    float4* d_q = nullptr; int* d_idx = nullptr; float* d_d2 = nullptr;
+    if (int e = dev_alloc(ctx, &d_q, nq, "nearest")) return e;
+    if (int e = dev_alloc(ctx, &d_idx, nq, "nearest")) return e;
+    if (int e = dev_alloc(ctx, &d_d2, nq, "nearest")) return e;
+    RTR_CHECK(cudaMemcpyAsync(d_q, host_queries_xyz1, (size_t)nq * 16, cudaMemcpyHostToDevice, ctx->stream), "nearest");
+    k_nearest<<<nblk(nq, 128), 128, 0, ctx->stream>>>(rtr_view(g), d_q, nq, d_idx, d_d2);
+    RTR_LAUNCH_CHECK(ctx, "nearest");
+    RTR_CHECK(cudaMemcpyAsync(host_idx, d_idx, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream), "nearest");
+    RTR_CHECK(cudaMemcpyAsync(host_d2, d_d2, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream), "nearest");
+    RTR_CHECK(cudaStreamSynchronize(ctx->stream), "nearest");
+    dev_free(ctx, d_q); dev_free(ctx, d_idx); dev_free(ctx, d_d2);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,517 @@
+// features.cu — per-cloud stages: normals, Harris-3D (response, NMS, refinement), FPFH, feature k-NN.
+//
+// These replace PCL classes the reference instantiates inside ModelPoint::getKeypoint / ScanPoint::getKeypoint
+// (model_point.h:127-136, scan_point.h:85-94: HarrisKeypoint3D with its implicit NormalEstimation) and the FPFH +
+// feature-correspondence stages BASELINE.json's north_star adds.  All gather kernels run one
+// thread (or one warp) per point IN CELL ORDER, so neighbouring threads scan the same 9 contiguous ranges of the
+// cell-sorted array; accumulation is fp64, storage fp32 (common.cuh, arithmetic contract).
+#include "common.cuh"
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <cmath>
+#include <cstring>
+
+static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+
+// ----------------------------------------------------------------------------- normals (App. A.2)
+__global__ void __launch_bounds__(128) k_normals(GridView g, float r2, float4* __restrict__ normals) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= g.n) return;
+    float4 q = __ldg(g.sorted + s);
+    double sx = 0, sy = 0, sz = 0, cxx = 0, cxy = 0, cxz = 0, cyy = 0, cyz = 0, czz = 0;
+    int cnt = 0;
+    for_block27(g, q.x, q.y, q.z, [&](int, float4 p, float d2) {
+        if (d2 < r2) {
+            double dx = (double)p.x - (double)q.x, dy = (double)p.y - (double)q.y, dz = (double)p.z - (double)q.z;
+            sx += dx; sy += dy; sz += dz;
+            cxx += dx * dx; cxy += dx * dy; cxz += dx * dz; cyy += dy * dy; cyz += dy * dz; czz += dz * dz;
+            ++cnt;
+        }
+    });
+    float4 o;
+    if (cnt < 3) {
+        o.x = o.y = o.z = o.w = __int_as_float(0x7fc00000);
+    } else {
+        double k = (double)cnt;
+        double mx = sx / k, my = sy / k, mz = sz / k;
+        double a[3][3], v[3][3];
+        a[0][0] = cxx / k - mx * mx; a[0][1] = cxy / k - mx * my; a[0][2] = cxz / k - mx * mz;
+        a[1][1] = cyy / k - my * my; a[1][2] = cyz / k - my * mz; a[2][2] = czz / k - mz * mz;
+        a[1][0] = a[0][1]; a[2][0] = a[0][2]; a[2][1] = a[1][2];
+        double trace = a[0][0] + a[1][1] + a[2][2];
+        jacobi_eig<3>(a, v);
+        double ev = a[0][0], nx = v[0][0], ny = v[1][0], nz = v[2][0];
+        if (a[1][1] < ev) { ev = a[1][1]; nx = v[0][1]; ny = v[1][1]; nz = v[2][1]; }
+        if (a[2][2] < ev) { ev = a[2][2]; nx = v[0][2]; ny = v[1][2]; nz = v[2][2]; }
+        double curv = (trace > 0) ? fabs(ev / trace) : 0.0;
+        // flipNormalTowardsViewpoint with the default viewpoint (0,0,0)
+        double dot = (nx * -(double)q.x + ny * -(double)q.y) + nz * -(double)q.z;
+        if (dot < 0) { nx = -nx; ny = -ny; nz = -nz; }
+        o.x = (float)nx; o.y = (float)ny; o.z = (float)nz; o.w = (float)curv;
+    }
+    normals[__float_as_int(q.w)] = o;
+}
+
+// ----------------------------------------------------------------------------- Harris 3D (App. A.3)
+__global__ void __launch_bounds__(128) k_harris_response(GridView g, const float4* __restrict__ sn, float r2,
+                                                         float* __restrict__ resp, float* __restrict__ resp_sorted) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= g.n) return;
+    float4 q = __ldg(g.sorted + s);
+    double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
+    int cnt = 0;
+    for_block27(g, q.x, q.y, q.z, [&](int sp, float4, float d2) {
+        if (d2 < r2) {
+            float4 nj = __ldg(sn + sp);
+            if (finite3(nj)) {
+                double x = nj.x, y = nj.y, z = nj.z;
+                c0 += x * x; c1 += x * y; c2 += x * z; c3 += y * y; c4 += y * z; c5 += z * z; ++cnt;
+            }
+        }
+    });
+    float r = 0.f;
+    if (cnt > 0) {
+        double k = (double)cnt;
+        double xx = c0 / k, xy = c1 / k, xz = c2 / k, yy = c3 / k, yz = c4 / k, zz = c5 / k;
+        double trace = xx + yy + zz;
+        if (trace != 0) {
+            double det = xx * yy * zz + 2.0 * xy * xz * yz - xz * xz * yy - xy * xy * zz - yz * yz * xx;
+            r = (float)(0.04 + det - 0.04 * trace * trace);
+        }
+    }
+    resp[__float_as_int(q.w)] = r;
+    resp_sorted[s] = r;
+}
+
+__global__ void __launch_bounds__(128) k_harris_nms(GridView g, const float* __restrict__ resp_sorted, float r2, float thr,
+                                                    int nms, unsigned char* __restrict__ flags) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= g.n) return;
+    float4 q = __ldg(g.sorted + s);
+    float r = resp_sorted[s];
+    bool keep = isfinite(r) && (r >= thr);
+    if (keep && nms) {
+        bool is_max = true;
+        for_block27(g, q.x, q.y, q.z, [&](int sp, float4, float d2) {
+            if (d2 < r2 && __ldg(resp_sorted + sp) > r) is_max = false;
+        });
+        keep = is_max;
+    }
+    flags[__float_as_int(q.w)] = keep ? 1 : 0;
+}
+
+// refineCorners: one thread per corner; neighbours are consumed in ASCENDING ORIGINAL INDEX (27-way merge over the
+// cell runs, each of which is already ascending) so that the fp64 sums are bit-identical to the oracle's.
+__global__ void k_harris_refine(GridView g, const float4* __restrict__ sn, const float4* __restrict__ pts, float r2,
+                                const int* __restrict__ kp_idx, const int* __restrict__ kp_count, int capacity,
+                                float4* __restrict__ kp_xyz, int refine) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int m = min(*kp_count, capacity);
+    if (t >= m) return;
+    float4 c = __ldg(pts + kp_idx[t]);
+    c.w = 1.0f;
+    if (refine) {
+        int it = 0;
+        double diff;
+        do {
+            float4 cur = c;
+            double A0 = 0, A1 = 0, A2 = 0, A3 = 0, A4 = 0, A5 = 0, b0 = 0, b1 = 0, b2 = 0;
+            int cx = cell_coord(cur.x, g.mnx, g.inv_h), cy = cell_coord(cur.y, g.mny, g.inv_h), cz = cell_coord(cur.z, g.mnz, g.inv_h);
+            if (!(cx < -1 || cy < -1 || cz < -1 || cx > g.dx || cy > g.dy || cz > g.dz)) {
+                cx = clampi(cx, 0, g.dx - 1); cy = clampi(cy, 0, g.dy - 1); cz = clampi(cz, 0, g.dz - 1);
+                int cur_s[27], end_s[27], nc = 0;
+                for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
+                    for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y)
+                        for (int x = max(cx - 1, 0); x <= min(cx + 1, g.dx - 1); ++x) {
+                            int key = cell_key(g, x, y, z);
+                            cur_s[nc] = g.cell_begin[key]; end_s[nc] = g.cell_begin[key + 1]; ++nc;
+                        }
+                // advance every cursor to its first in-radius element
+                for (int k = 0; k < nc; ++k) {
+                    while (cur_s[k] < end_s[k]) {
+                        float4 p = g.sorted[cur_s[k]];
+                        if (dist2f(cur.x, cur.y, cur.z, p.x, p.y, p.z) < r2) break;
+                        ++cur_s[k];
+                    }
+                }
+                for (;;) {
+                    int bk = -1, bid = 0x7fffffff;
+                    for (int k = 0; k < nc; ++k)
+                        if (cur_s[k] < end_s[k]) {
+                            int id = __float_as_int(g.sorted[cur_s[k]].w);
+                            if (id < bid) { bid = id; bk = k; }
+                        }
+                    if (bk < 0) break;
+                    int sp = cur_s[bk];
+                    float4 p = g.sorted[sp];
+                    float4 nj = sn[sp];
+                    if (finite3(nj)) {
+                        double x = nj.x, y = nj.y, z = nj.z;
+                        double xx = x * x, xy = x * y, xz = x * z, yy = y * y, yz = y * z, zz = z * z;
+                        A0 += xx; A1 += xy; A2 += xz; A3 += yy; A4 += yz; A5 += zz;
+                        double px = p.x, py = p.y, pz = p.z;
+                        b0 += (xx * px + xy * py) + xz * pz;
+                        b1 += (xy * px + yy * py) + yz * pz;
+                        b2 += (xz * px + yz * py) + zz * pz;
+                    }
+                    ++cur_s[bk];
+                    while (cur_s[bk] < end_s[bk]) {
+                        float4 p2 = g.sorted[cur_s[bk]];
+                        if (dist2f(cur.x, cur.y, cur.z, p2.x, p2.y, p2.z) < r2) break;
+                        ++cur_s[bk];
+                    }
+                }
+            }
+            double c00 = A3 * A5 - A4 * A4, c01 = A2 * A4 - A1 * A5, c02 = A1 * A4 - A2 * A3;
+            double c11 = A0 * A5 - A2 * A2, c12 = A1 * A2 - A0 * A4, c22 = A0 * A3 - A1 * A1;
+            double det = (A0 * c00 + A1 * c01) + A2 * c02;
+            if (det != 0) {
+                c.x = (float)(((c00 * b0 + c01 * b1) + c02 * b2) / det);
+                c.y = (float)(((c01 * b0 + c11 * b1) + c12 * b2) / det);
+                c.z = (float)(((c02 * b0 + c12 * b1) + c22 * b2) / det);
+            }
+            double ddx = (double)c.x - (double)cur.x, ddy = (double)c.y - (double)cur.y, ddz = (double)c.z - (double)cur.z;
+            diff = (ddx * ddx + ddy * ddy) + ddz * ddz;
+        } while (diff > 1e-6 && ++it < 10);
+    }
+    kp_xyz[t] = c;
+}
+
+// ----------------------------------------------------------------------------- FPFH (App. A.4)
+// computePairFeatures in fp64 with the |a1| < |a2| role swap (== acos|a1| > acos|a2|); returns the three bin indices.
+__device__ __forceinline__ bool pair_bins(float4 p1, float4 n1f, float4 p2, float4 n2f, int& b0, int& b1, int& b2) {
+    double d0 = (double)p2.x - (double)p1.x, d1 = (double)p2.y - (double)p1.y, d2 = (double)p2.z - (double)p1.z;
+    double f4 = sqrt((d0 * d0 + d1 * d1) + d2 * d2);
+    if (f4 == 0.0) return false;
+    double n10 = n1f.x, n11 = n1f.y, n12 = n1f.z, n20 = n2f.x, n21 = n2f.y, n22 = n2f.z;
+    double a1 = ((n10 * d0 + n11 * d1) + n12 * d2) / f4;
+    double a2 = ((n20 * d0 + n21 * d1) + n22 * d2) / f4;
+    double f3;
+    if (fabs(a1) < fabs(a2)) {
+        double t;
+        t = n10; n10 = n20; n20 = t; t = n11; n11 = n21; n21 = t; t = n12; n12 = n22; n22 = t;
+        d0 = -d0; d1 = -d1; d2 = -d2;
+        f3 = -a2;
+    } else f3 = a1;
+    double v0 = d1 * n12 - d2 * n11, v1 = d2 * n10 - d0 * n12, v2 = d0 * n11 - d1 * n10;
+    double vn = sqrt((v0 * v0 + v1 * v1) + v2 * v2);
+    if (vn == 0.0) return false;
+    v0 /= vn; v1 /= vn; v2 /= vn;
+    double w0 = n11 * v2 - n12 * v1, w1 = n12 * v0 - n10 * v2, w2 = n10 * v1 - n11 * v0;
+    double f2 = (v0 * n20 + v1 * n21) + v2 * n22;
+    double f1 = atan2((w0 * n20 + w1 * n21) + w2 * n22, (n10 * n20 + n11 * n21) + n12 * n22);
+    const double kPi = 3.14159265358979323846;
+    int i0 = (int)floor(11.0 * ((f1 + kPi) * (1.0 / (2.0 * kPi))));
+    int i1 = (int)floor(11.0 * ((f2 + 1.0) * 0.5));
+    int i2 = (int)floor(11.0 * ((f3 + 1.0) * 0.5));
+    b0 = min(max(i0, 0), 10); b1 = min(max(i1, 0), 10); b2 = min(max(i2, 0), 10);
+    return true;
+}
+
+#define SPFH_THREADS 128
+__global__ void __launch_bounds__(SPFH_THREADS) k_spfh(GridView g, const float4* __restrict__ sn, float r2,
+                                                       float* __restrict__ spfh_sorted) {
+    __shared__ int cnt[33 * SPFH_THREADS];   // bin-major: conflict-free
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 33; ++k) cnt[k * SPFH_THREADS + threadIdx.x] = 0;
+    if (s >= g.n) return;
+    float4 q = __ldg(g.sorted + s);
+    float4 nq = __ldg(sn + s);
+    int qi = __float_as_int(q.w);
+    bool qfin = finite3(nq);
+    int nb = 0;
+    for_block27(g, q.x, q.y, q.z, [&](int sp, float4 p, float d2) {
+        if (d2 < r2) {
+            ++nb;
+            if (qfin && __float_as_int(p.w) != qi) {
+                float4 nj = __ldg(sn + sp);
+                int b0, b1, b2;
+                if (finite3(nj) && pair_bins(q, nq, p, nj, b0, b1, b2)) {
+                    cnt[b0 * SPFH_THREADS + threadIdx.x]++;
+                    cnt[(11 + b1) * SPFH_THREADS + threadIdx.x]++;
+                    cnt[(22 + b2) * SPFH_THREADS + threadIdx.x]++;
+                }
+            }
+        }
+    });
+    float* o = spfh_sorted + (size_t)s * 33;
+    if (nb < 2 || !qfin) {
+#pragma unroll
+        for (int k = 0; k < 33; ++k) o[k] = 0.f;
+    } else {
+        double incr = 100.0 / (double)(nb - 1);
+#pragma unroll
+        for (int k = 0; k < 33; ++k) o[k] = (float)((double)cnt[k * SPFH_THREADS + threadIdx.x] * incr);
+    }
+}
+
+// weightPointSPFHSignature: one warp per point, lane = histogram bin (lane 0 also carries bin 32)
+#define FPFH_WARPS 4
+__global__ void __launch_bounds__(FPFH_WARPS * 32) k_fpfh_weight(GridView g, const float* __restrict__ spfh_sorted, float r2,
+                                                                 float* __restrict__ fpfh) {
+    __shared__ double hs[FPFH_WARPS][36];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int s = blockIdx.x * FPFH_WARPS + warp;
+    if (s >= g.n) return;
+    float4 q = __ldg(g.sorted + s);
+    double acc = 0, acc32 = 0;
+    int nb = 0;
+    for_block27(g, q.x, q.y, q.z, [&](int sp, float4, float d2) {
+        if (d2 < r2) {
+            ++nb;
+            if (d2 != 0.f) {
+                double w = 1.0 / (double)d2;
+                const float* sj = spfh_sorted + (size_t)sp * 33;
+                acc += (double)__ldg(sj + lane) * w;
+                if (lane == 0) acc32 += (double)__ldg(sj + 32) * w;
+            }
+        }
+    });
+    hs[warp][lane] = acc;
+    if (lane == 0) hs[warp][32] = acc32;
+    __syncwarp();
+    if (lane < 3) {
+        double sum = 0;
+        for (int k = 0; k < 11; ++k) sum += hs[warp][lane * 11 + k];
+        hs[warp][33 + lane] = (sum != 0) ? 100.0 / sum : 0.0;
+    }
+    __syncwarp();
+    float* o = fpfh + (size_t)__float_as_int(q.w) * 33;
+    if (nb == 0) {
+        o[lane] = __int_as_float(0x7fc00000);
+        if (lane == 0) o[32] = __int_as_float(0x7fc00000);
+    } else {
+        o[lane] = (float)(hs[warp][lane] * hs[warp][33 + lane / 11]);
+        if (lane == 0) o[32] = (float)(hs[warp][32] * hs[warp][35]);
+    }
+}
+
+// ----------------------------------------------------------------------------- feature k-NN (App. A.5), exact
+// One warp per source feature; targets are staged through shared memory in tiles of 64 rows (row stride 33 floats is
+// conflict-free); each lane keeps a sorted top-K of the rows it scanned; the warp then merges the 32 lists.
+// Distances are the oracle's: sequential fp64 sum of squared fp64 differences, rounded to fp32; ties -> lowest index.
+#define MATCH_WARPS 8
+#define MATCH_TILE 64
+#define MATCH_KMAX 8
+__global__ void __launch_bounds__(MATCH_WARPS * 32) k_match(const float* __restrict__ fa, int na, const float* __restrict__ fb,
+                                                            int nb, int k, int* __restrict__ out_idx, float* __restrict__ out_dist) {
+    __shared__ float tile[MATCH_TILE * 33];
+    __shared__ float src[MATCH_WARPS][33];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int row = blockIdx.x * MATCH_WARPS + warp;
+    bool active = row < na;
+    if (active) {
+        src[warp][lane] = fa[(size_t)row * 33 + lane];
+        if (lane == 0) src[warp][32] = fa[(size_t)row * 33 + 32];
+    }
+    float bd[MATCH_KMAX];
+    int bi[MATCH_KMAX];
+#pragma unroll
+    for (int t = 0; t < MATCH_KMAX; ++t) { bd[t] = FLT_MAX; bi[t] = 0x7fffffff; }
+    for (int base = 0; base < nb; base += MATCH_TILE) {
+        __syncthreads();
+        int rows = min(MATCH_TILE, nb - base);
+        for (int e = threadIdx.x; e < rows * 33; e += blockDim.x) tile[e] = __ldg(fb + (size_t)base * 33 + e);
+        __syncthreads();
+        if (active) {
+#pragma unroll
+            for (int half = 0; half < MATCH_TILE / 32; ++half) {
+                int r = half * 32 + lane;
+                if (r < rows) {
+                    const float* b = tile + r * 33;
+                    double sacc = 0;
+#pragma unroll
+                    for (int c = 0; c < 33; ++c) { double d = (double)src[warp][c] - (double)b[c]; sacc += d * d; }
+                    float df = (float)sacc;
+                    int id = base + r;
+                    if (df == df && (df < bd[MATCH_KMAX - 1] || (df == bd[MATCH_KMAX - 1] && id < bi[MATCH_KMAX - 1]))) {
+                        bd[MATCH_KMAX - 1] = df; bi[MATCH_KMAX - 1] = id;
+#pragma unroll
+                        for (int t = MATCH_KMAX - 1; t > 0; --t) {
+                            bool sw = (bd[t] < bd[t - 1]) || (bd[t] == bd[t - 1] && bi[t] < bi[t - 1]);
+                            if (sw) { float td = bd[t]; bd[t] = bd[t - 1]; bd[t - 1] = td; int ti = bi[t]; bi[t] = bi[t - 1]; bi[t - 1] = ti; }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (!active) return;
+    // merge: k rounds of a warp-wide lexicographic (dist, idx) minimum over the list heads
+    for (int t = 0; t < k; ++t) {
+        float hd = bd[0]; int hi = bi[0];
+        float md = hd; int mi = hi;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float od = __shfl_xor_sync(0xffffffffu, md, o);
+            int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+            if (od < md || (od == md && oi < mi)) { md = od; mi = oi; }
+        }
+        if (mi == hi && md == hd && hi != 0x7fffffff) {   // this lane owned the winner: pop it
+#pragma unroll
+            for (int u = 0; u < MATCH_KMAX - 1; ++u) { bd[u] = bd[u + 1]; bi[u] = bi[u + 1]; }
+            bd[MATCH_KMAX - 1] = FLT_MAX; bi[MATCH_KMAX - 1] = 0x7fffffff;
+        }
+        if (lane == 0) {
+            bool none = (mi == 0x7fffffff);
+            out_idx[(size_t)row * k + t] = none ? -1 : mi;
+            out_dist[(size_t)row * k + t] = none ? __int_as_float(0x7fc00000) : md;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- host drivers
+int rtr_normals_dev(rtr_cloud* c, float radius) {
+    rtr_context* ctx = c->ctx;
+    if (c->normals && c->normals_radius == radius) return 0;
+    DevGrid* g;
+    if (int e = rtr_get_grid(c, radius, &g)) return e;
+    if (!c->normals) if (int e = dev_alloc(ctx, &c->normals, c->n, "normals")) return e;
+    if (c->n > 0) {
+        k_normals<<<nblk(c->n, 128), 128, 0, ctx->stream>>>(rtr_view(g), radius * radius, c->normals);
+        RTR_LAUNCH_CHECK(ctx, "normals");
+    }
+    c->normals_radius = radius;
+    c->normals_version++;
+    return 0;
+}
+
+int rtr_harris_dev(rtr_cloud* c, float radius, float threshold, int nms, int refine, int** d_kp_idx, float4** d_kp_xyz,
+                   int** d_count) {
+    rtr_context* ctx = c->ctx;
+    if (!c->normals) return rtr_fail("harris", "rtr_normals must run first", RTR_ERR_NOT_READY);
+    DevGrid* g;
+    if (int e = rtr_get_grid(c, radius, &g)) return e;
+    if (int e = rtr_grid_normals(c, g)) return e;
+    int n = c->n;
+    float r2 = radius * radius;
+    if (!c->response) if (int e = dev_alloc(ctx, &c->response, n, "harris")) return e;
+    float* resp_sorted = nullptr; unsigned char* flags = nullptr;
+    if (int e = dev_alloc(ctx, &resp_sorted, n, "harris")) return e;
+    if (int e = dev_alloc(ctx, &flags, n, "harris")) return e;
+    if (int e = dev_alloc(ctx, d_kp_idx, n, "harris")) return e;
+    if (int e = dev_alloc(ctx, d_kp_xyz, n, "harris")) return e;
+    if (int e = dev_alloc(ctx, d_count, 1, "harris")) return e;
+    RTR_CHECK(cudaMemsetAsync(*d_count, 0, sizeof(int), ctx->stream), "harris");
+    if (n > 0) {
+        GridView v = rtr_view(g);
+        k_harris_response<<<nblk(n, 128), 128, 0, ctx->stream>>>(v, g->sorted_normals, r2, c->response, resp_sorted);
+        RTR_LAUNCH_CHECK(ctx, "harris.response");
+        k_harris_nms<<<nblk(n, 128), 128, 0, ctx->stream>>>(v, resp_sorted, r2, threshold, nms, flags);
+        RTR_LAUNCH_CHECK(ctx, "harris.nms");
+        size_t tb = 0;
+        thrust::counting_iterator<int> iota(0);
+        cub::DeviceSelect::Flagged(nullptr, tb, iota, flags, *d_kp_idx, *d_count, n, ctx->stream);
+        char* temp = nullptr;
+        if (int e = dev_alloc(ctx, &temp, tb, "harris")) return e;
+        RTR_CHECK(cub::DeviceSelect::Flagged(temp, tb, iota, flags, *d_kp_idx, *d_count, n, ctx->stream), "harris.select");
+        dev_free(ctx, temp);
+        // the corner count lives on the device; launch for the worst case (every point a corner), threads beyond exit
+        k_harris_refine<<<nblk(n, 64), 64, 0, ctx->stream>>>(v, g->sorted_normals, c->pts, r2, *d_kp_idx, *d_count, n, *d_kp_xyz, refine);
+        RTR_LAUNCH_CHECK(ctx, "harris.refine");
+    }
+    dev_free(ctx, resp_sorted); dev_free(ctx, flags);
+    return 0;
+}
+
+int rtr_fpfh_dev(rtr_cloud* c, float radius) {
+    rtr_context* ctx = c->ctx;
+    if (!c->normals) return rtr_fail("fpfh", "rtr_normals must run first", RTR_ERR_NOT_READY);
+    if (c->fpfh && c->fpfh_radius == radius) return 0;
+    DevGrid* g;
+    if (int e = rtr_get_grid(c, radius, &g)) return e;
+    if (int e = rtr_grid_normals(c, g)) return e;
+    int n = c->n;
+    float r2 = radius * radius;
+    if (!c->fpfh) if (int e = dev_alloc(ctx, &c->fpfh, (size_t)n * 33, "fpfh")) return e;
+    float* spfh = nullptr;
+    if (int e = dev_alloc(ctx, &spfh, (size_t)n * 33, "fpfh")) return e;
+    if (n > 0) {
+        GridView v = rtr_view(g);
+        k_spfh<<<nblk(n, SPFH_THREADS), SPFH_THREADS, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh);
+        RTR_LAUNCH_CHECK(ctx, "fpfh.spfh");
+        k_fpfh_weight<<<nblk(n, FPFH_WARPS), FPFH_WARPS * 32, 0, ctx->stream>>>(v, spfh, r2, c->fpfh);
+        RTR_LAUNCH_CHECK(ctx, "fpfh.weight");
+    }
+    dev_free(ctx, spfh);
+    c->fpfh_radius = radius;
+    // features changed: cached correspondences are stale
+    dev_free(ctx, c->knn); c->knn = nullptr; dev_free(ctx, c->knn_dist); c->knn_dist = nullptr; c->knn_k = 0;
+    return 0;
+}
+
+int rtr_match_dev(rtr_cloud* src, rtr_cloud* tgt, int k) {
+    rtr_context* ctx = src->ctx;
+    if (!src->fpfh || !tgt->fpfh) return rtr_fail("match", "rtr_fpfh must run on both clouds first", RTR_ERR_NOT_READY);
+    if (k < 1 || k > MATCH_KMAX) return rtr_fail("match", "k must be in [1, 8]", RTR_ERR_INVALID);
+    dev_free(ctx, src->knn); dev_free(ctx, src->knn_dist);
+    src->knn = nullptr; src->knn_dist = nullptr;
+    if (int e = dev_alloc(ctx, &src->knn, (size_t)src->n * k, "match")) return e;
+    if (int e = dev_alloc(ctx, &src->knn_dist, (size_t)src->n * k, "match")) return e;
+    if (src->n > 0) {
+        k_match<<<nblk(src->n, MATCH_WARPS), MATCH_WARPS * 32, 0, ctx->stream>>>(src->fpfh, src->n, tgt->fpfh, tgt->n, k, src->knn, src->knn_dist);
+        RTR_LAUNCH_CHECK(ctx, "match");
+    }
+    src->knn_k = k; src->knn_target_n = tgt->n;
+    return 0;
+}
+
+extern "C" {
+
+int rtr_normals(rtr_cloud* c, float radius, float* host_normals4) {
+    if (!c || !(radius > 0.f)) return rtr_fail("normals", "bad argument", RTR_ERR_INVALID);
+    RTR_CHECK(cudaSetDevice(c->ctx->device), "normals");
+    if (int e = rtr_normals_dev(c, radius)) return e;
+    if (host_normals4 && c->n > 0) RTR_CHECK(cudaMemcpyAsync(host_normals4, c->normals, (size_t)c->n * 16, cudaMemcpyDeviceToHost, c->ctx->stream), "normals");
+    RTR_CHECK(cudaStreamSynchronize(c->ctx->stream), "normals");
+    return 0;
+}
+
+int rtr_harris3d(rtr_cloud* c, float radius, float threshold, int nms, int refine, float* host_response, int* host_kp_index,
+                 float* host_kp_xyz1, int capacity, int* n_keypoints) {
+    if (!c || !(radius > 0.f) || !n_keypoints || capacity < 0) return rtr_fail("harris", "bad argument", RTR_ERR_INVALID);
+    rtr_context* ctx = c->ctx;
+    RTR_CHECK(cudaSetDevice(ctx->device), "harris");
+    int* d_idx = nullptr; float4* d_xyz = nullptr; int* d_count = nullptr;
+    if (int e = rtr_harris_dev(c, radius, threshold, nms, refine, &d_idx, &d_xyz, &d_count)) return e;
+    int m = 0;
+    RTR_CHECK(cudaMemcpyAsync(&m, d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream), "harris");
+    if (host_response && c->n > 0) RTR_CHECK(cudaMemcpyAsync(host_response, c->response, (size_t)c->n * 4, cudaMemcpyDeviceToHost, ctx->stream), "harris");
+    RTR_CHECK(cudaStreamSynchronize(ctx->stream), "harris");
+    *n_keypoints = m;
+    c->n_keypoints = m;
+    int rc = 0;
+    int take = m < capacity ? m : capacity;
+    if (take > 0) {
+        if (host_kp_index) RTR_CHECK(cudaMemcpyAsync(host_kp_index, d_idx, (size_t)take * 4, cudaMemcpyDeviceToHost, ctx->stream), "harris");
+        if (host_kp_xyz1) RTR_CHECK(cudaMemcpyAsync(host_kp_xyz1, d_xyz, (size_t)take * 16, cudaMemcpyDeviceToHost, ctx->stream), "harris");
+        RTR_CHECK(cudaStreamSynchronize(ctx->stream), "harris");
+    }
+    if (m > capacity && (host_kp_index || host_kp_xyz1)) rc = RTR_ERR_CAPACITY;
+    dev_free(ctx, d_idx); dev_free(ctx, d_xyz); dev_free(ctx, d_count);
+    return rc;
+}
+
+int rtr_fpfh(rtr_cloud* c, float radius, float* host_fpfh) {
+    if (!c || !(radius > 0.f)) return rtr_fail("fpfh", "bad argument", RTR_ERR_INVALID);
+    RTR_CHECK(cudaSetDevice(c->ctx->device), "fpfh");
+    if (int e = rtr_fpfh_dev(c, radius)) return e;
+    if (host_fpfh && c->n > 0) RTR_CHECK(cudaMemcpyAsync(host_fpfh, c->fpfh, (size_t)c->n * 33 * 4, cudaMemcpyDeviceToHost, c->ctx->stream), "fpfh");
+    RTR_CHECK(cudaStreamSynchronize(c->ctx->stream), "fpfh");
+    return 0;
+}
+
+int rtr_match_features(rtr_cloud* source, rtr_cloud* target, int k, int* host_idx, float* host_dist) {
+    if (!source || !target || source->ctx != target->ctx) return rtr_fail("match", "bad argument", RTR_ERR_INVALID);
+    rtr_context* ctx = source->ctx;
+    RTR_CHECK(cudaSetDevice(ctx->device), "match");
+    if (int e = rtr_match_dev(source, target, k)) return e;
+    size_t cnt = (size_t)source->n * k;
+    if (host_idx && cnt) RTR_CHECK(cudaMemcpyAsync(host_idx, source->knn, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream), "match");
+    if (host_dist && cnt) RTR_CHECK(cudaMemcpyAsync(host_dist, source->knn_dist, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream), "match");
+    RTR_CHECK(cudaStreamSynchronize(ctx->stream), "match");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,563 @@
+// pose.cu — pose hypotheses (prerejective RANSAC), ICP refinement, and the whole-registration sequencer.
+//
+// Replaces, for the path BASELINE.json's north_star names: the reference's consensus step (function.h:35-109, an
+// exhaustive loop over keypoint pairs) by pcl::SampleConsensusPrerejective semantics, and
+// keyPointICP (function.h:111-123: pcl::IterativeClosestPoint, all defaults; App. A.6).  rtr_register sequences the
+// stages the way main() does (RealTimeRobot.cpp:39-105) without leaving the device.
+//
+// Work decomposition
+//   RANSAC: K1 one thread per hypothesis (counter-hash draws, polygon prerejection, warp-aggregated append);
+//           K2 one thread per survivor (3-point Horn fit, fp64 Jacobi); K3 one CTA per survivor, persistent over the
+//           survivor list: every thread transforms source points and scans 9 cell ranges of the target grid, inlier
+//           count / error reduced by warp shuffles; K4 one CTA: lexicographic (error, hypothesis) arg-min.
+//   ICP:    per iteration one correspondence kernel (apply previous step, exact 1-NN, 17 fp64 sums per thread ->
+//           warp-shuffle tree -> per-CTA partials) and one solve kernel (fixed-shape reduction, Horn, convergence).
+#include "common.cuh"
+#include <cmath>
+#include <cstring>
+
+static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+
+// ============================================================================= RANSAC
+struct RansacArgs {
+    const float4* src; int ns;
+    const float4* tgt; int nt;
+    const int* knn; int knn_stride; int k;
+    unsigned long long seed;
+    long long h_base; int h_count;
+    float simsq; float dmax2; float inlier_fraction;
+};
+
+__device__ __forceinline__ bool draw_hypothesis(const RansacArgs& a, unsigned long long h, int* s, int* c) {
+    unsigned ns = (unsigned)a.ns;
+    unsigned x = rand_below(a.seed, h, 0, ns);
+    unsigned y = rand_below(a.seed, h, 1, ns - 1); if (y >= x) ++y;
+    unsigned z = rand_below(a.seed, h, 2, ns - 2);
+    unsigned lo = min(x, y), hi = max(x, y);
+    if (z >= lo) ++z;
+    if (z >= hi) ++z;
+    s[0] = (int)x; s[1] = (int)y; s[2] = (int)z;
+    bool ok = true;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        unsigned pick = (a.k > 1) ? rand_below(a.seed, h, 3 + t, (unsigned)a.k) : 0u;
+        c[t] = __ldg(a.knn + (size_t)s[t] * a.knn_stride + pick);
+        if (c[t] < 0) ok = false;
+    }
+    return ok;
+}
+
+// K1: sample + CorrespondenceRejectorPoly::thresholdPolygon (cardinality 3)
+__global__ void __launch_bounds__(256) k_ransac_sample(RansacArgs a, int* __restrict__ survivors, int* __restrict__ count) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    if (t < a.h_count) {
+        int s[3], c[3];
+        ok = draw_hypothesis(a, (unsigned long long)(a.h_base + t), s, c);
+        if (ok) {
+            float4 ps[3], pt[3];
+#pragma unroll
+            for (int e = 0; e < 3; ++e) { ps[e] = __ldg(a.src + s[e]); pt[e] = __ldg(a.tgt + c[e]); }
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                int f = (e + 1) % 3;
+                float ds = dist2f(ps[e].x, ps[e].y, ps[e].z, ps[f].x, ps[f].y, ps[f].z);
+                float dt = dist2f(pt[e].x, pt[e].y, pt[e].z, pt[f].x, pt[f].y, pt[f].z);
+                float sim = ds < dt ? __fdiv_rn(ds, dt) : __fdiv_rn(dt, ds);
+                if (!(sim >= a.simsq)) ok = false;
+            }
+        }
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, ok);
+    if (mask) {
+        int lane = threadIdx.x & 31;
+        int leader = __ffs(mask) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(count, __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (ok) survivors[base + __popc(mask & ((1u << lane) - 1u))] = t;
+    }
+}
+
+// K2: TransformationEstimationSVD on the three sampled pairs (Horn / fp64 Jacobi)
+__global__ void __launch_bounds__(64) k_ransac_pose(RansacArgs a, const int* __restrict__ survivors, const int* __restrict__ count,
+                                                    float* __restrict__ poses) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *count) return;
+    int s[3], c[3];
+    draw_hypothesis(a, (unsigned long long)(a.h_base + survivors[t]), s, c);
+    double ss[3] = {0, 0, 0}, st[3] = {0, 0, 0}, m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        float4 p = __ldg(a.src + s[e]), q = __ldg(a.tgt + c[e]);
+        double sv[3] = {p.x, p.y, p.z}, tv[3] = {q.x, q.y, q.z};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            ss[i] += sv[i]; st[i] += tv[i];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) m[i * 3 + j] += sv[i] * tv[j];
+        }
+    }
+    float pose[16];
+    horn_pose(ss, st, m, 3.0, pose);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) poses[(size_t)t * 16 + i] = pose[i];
+}
+
+// K3: getFitness — one CTA per surviving hypothesis, persistent over the survivor list
+#define EVAL_THREADS 256
+__global__ void __launch_bounds__(EVAL_THREADS) k_ransac_eval(RansacArgs a, GridView g, const int* __restrict__ count,
+                                                              const float* __restrict__ poses, float* __restrict__ err,
+                                                              int* __restrict__ inl) {
+    __shared__ float m[16];
+    __shared__ double wsum[EVAL_THREADS / 32];
+    __shared__ int wcnt[EVAL_THREADS / 32];
+    int n = *count;
+    for (int t = blockIdx.x; t < n; t += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < 16) m[threadIdx.x] = poses[(size_t)t * 16 + threadIdx.x];
+        __syncthreads();
+        int cnt = 0;
+        double sum = 0;
+        for (int i = threadIdx.x; i < a.ns; i += EVAL_THREADS) {
+            float4 q = xform(m, __ldg(a.src + i));
+            float best = FLT_MAX;
+            for_block27(g, q.x, q.y, q.z, [&](int, float4, float d2) { if (d2 < best) best = d2; });
+            if (best < a.dmax2) { ++cnt; sum += (double)best; }
+        }
+        cnt = warp_sum(cnt);
+        sum = warp_sum(sum);
+        if ((threadIdx.x & 31) == 0) { wsum[threadIdx.x >> 5] = sum; wcnt[threadIdx.x >> 5] = cnt; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double S = 0; int C = 0;
+#pragma unroll
+            for (int w = 0; w < EVAL_THREADS / 32; ++w) { S += wsum[w]; C += wcnt[w]; }
+            err[t] = C > 0 ? (float)(S / (double)C) : FLT_MAX;
+            inl[t] = C;
+        }
+    }
+}
+
+// K4: accept iff inlier fraction >= threshold and error < best; parallel form: arg-min over (error, hypothesis),
+// folded into the running best of earlier chunks.
+__global__ void __launch_bounds__(1024) k_ransac_select(RansacArgs a, const int* __restrict__ survivors, const int* __restrict__ count,
+                                                        const float* __restrict__ poses, const float* __restrict__ err,
+                                                        const int* __restrict__ inl, rtr_pose_result* __restrict__ res) {
+    __shared__ float s_err[32];
+    __shared__ long long s_h[32];
+    __shared__ int s_t[32];
+    int n = *count;
+    float be = FLT_MAX; long long bh = -1; int bt = -1;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        int c = inl[t];
+        float frac = __fdiv_rn((float)c, (float)a.ns);
+        if (frac >= a.inlier_fraction) {
+            float e = err[t];
+            long long h = a.h_base + survivors[t];
+            if (e < be || (e == be && (bh < 0 || h < bh))) { be = e; bh = h; bt = t; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float oe = __shfl_xor_sync(0xffffffffu, be, o);
+        long long oh = __shfl_xor_sync(0xffffffffu, bh, o);
+        int ot = __shfl_xor_sync(0xffffffffu, bt, o);
+        if (oh >= 0 && (bh < 0 || oe < be || (oe == be && oh < bh))) { be = oe; bh = oh; bt = ot; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_err[threadIdx.x >> 5] = be; s_h[threadIdx.x >> 5] = bh; s_t[threadIdx.x >> 5] = bt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        be = FLT_MAX; bh = -1; bt = -1;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            float oe = s_err[w]; long long oh = s_h[w]; int ot = s_t[w];
+            if (oh >= 0 && (bh < 0 || oe < be || (oe == be && oh < bh))) { be = oe; bh = oh; bt = ot; }
+        }
+        res->evaluated += n;
+        // strict "error < lowest_error" with lowest_error starting at FLT_MAX, sequential in h == lexicographic min
+        if (bh >= 0 && be < FLT_MAX && (res->hypothesis < 0 || be < res->fitness || (be == res->fitness && bh < res->hypothesis))) {
+            for (int i = 0; i < 16; ++i) res->pose[i] = poses[(size_t)bt * 16 + i];
+            res->fitness = be; res->inliers = inl[bt]; res->hypothesis = bh; res->converged = 1;
+        }
+    }
+}
+
+__global__ void k_result_init(rtr_pose_result* res) {
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 16; ++i) res->pose[i] = (i % 5 == 0) ? 1.f : 0.f;
+        res->fitness = FLT_MAX; res->inliers = 0; res->hypothesis = -1; res->evaluated = 0; res->converged = 0;
+        res->iterations = 0; res->model_id = 0; res->n_keypoints_src = 0; res->n_keypoints_tgt = 0;
+        for (int i = 0; i < 5; ++i) res->pad_[i] = 0;
+    }
+}
+
+int rtr_ransac_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_ransac_params* p, rtr_pose_result* d_result) {
+    rtr_context* ctx = src->ctx;
+    k_result_init<<<1, 32, 0, ctx->stream>>>(d_result);
+    RTR_LAUNCH_CHECK(ctx, "ransac.init");
+    long long h0 = p->hypothesis_begin, h1 = (p->hypothesis_end > 0) ? p->hypothesis_end : p->max_iterations;
+    if (src->n < 3 || tgt->n < 1 || h1 <= h0) return 0;
+    if (!src->knn || src->knn_k < p->correspondence_k || src->knn_target_n != tgt->n)
+        return rtr_fail("ransac", "rtr_match_features(source, target, k >= correspondence_k) must run first", RTR_ERR_NOT_READY);
+    if (!(p->max_correspondence_distance > 0.f)) return rtr_fail("ransac", "max_correspondence_distance must be > 0", RTR_ERR_INVALID);
+    DevGrid* g;
+    if (int e = rtr_get_grid(tgt, p->max_correspondence_distance, &g)) return e;
+    const long long CHUNK = 1 << 20;
+    int cap = (int)std::min<long long>(CHUNK, h1 - h0);
+    int *survivors = nullptr, *count = nullptr, *inl = nullptr; float *poses = nullptr, *err = nullptr;
+    if (int e = dev_alloc(ctx, &survivors, cap, "ransac")) return e;
+    if (int e = dev_alloc(ctx, &count, 1, "ransac")) return e;
+    if (int e = dev_alloc(ctx, &inl, cap, "ransac")) return e;
+    if (int e = dev_alloc(ctx, &err, cap, "ransac")) return e;
+    if (int e = dev_alloc(ctx, &poses, (size_t)cap * 16, "ransac")) return e;
+    RansacArgs a;
+    a.src = src->pts; a.ns = src->n; a.tgt = tgt->pts; a.nt = tgt->n;
+    a.knn = src->knn; a.knn_stride = src->knn_k; a.k = p->correspondence_k; a.seed = p->seed;
+    a.simsq = p->similarity_threshold * p->similarity_threshold;
+    a.dmax2 = p->max_correspondence_distance * p->max_correspondence_distance;
+    a.inlier_fraction = p->inlier_fraction;
+    GridView v = rtr_view(g);
+    for (long long base = h0; base < h1; base += CHUNK) {
+        a.h_base = base; a.h_count = (int)std::min<long long>(CHUNK, h1 - base);
+        RTR_CHECK(cudaMemsetAsync(count, 0, sizeof(int), ctx->stream), "ransac");
+        k_ransac_sample<<<nblk(a.h_count, 256), 256, 0, ctx->stream>>>(a, survivors, count);
+        RTR_LAUNCH_CHECK(ctx, "ransac.sample");
+        k_ransac_pose<<<nblk(a.h_count, 64), 64, 0, ctx->stream>>>(a, survivors, count, poses);
+        RTR_LAUNCH_CHECK(ctx, "ransac.pose");
+        int grid = std::min(a.h_count, ctx->sm_count * 8);
+        k_ransac_eval<<<grid, EVAL_THREADS, 0, ctx->stream>>>(a, v, count, poses, err, inl);
+        RTR_LAUNCH_CHECK(ctx, "ransac.eval");
+        k_ransac_select<<<1, 1024, 0, ctx->stream>>>(a, survivors, count, poses, err, inl, d_result);
+        RTR_LAUNCH_CHECK(ctx, "ransac.select");
+    }
+    dev_free(ctx, survivors); dev_free(ctx, count); dev_free(ctx, inl); dev_free(ctx, err); dev_free(ctx, poses);
+    return 0;
+}
+
+// ============================================================================= ICP
+struct IcpState {
+    float final_[16];
+    float step[16];
+    double prev_mse;
+    int iterations;
+    int done;
+    int state;
+    int corr;
+    int have_step;
+};
+
+#define ICP_THREADS 256
+#define ICP_NSUM 17   // 3 (sum s) + 3 (sum t) + 9 (sum s t^T) + 1 (sum d2) + 1 (count)
+
+__global__ void k_icp_init(const float4* __restrict__ src, int n, const float* __restrict__ init_pose, const rtr_pose_result* __restrict__ init_res,
+                           float4* __restrict__ cur, IcpState* __restrict__ st) {
+    __shared__ float m[16];
+    if (threadIdx.x < 16) {
+        float v = (threadIdx.x % 5 == 0) ? 1.f : 0.f;
+        if (init_res) v = init_res->pose[threadIdx.x];
+        else if (init_pose) v = init_pose[threadIdx.x];
+        m[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x < 16) {
+        st->final_[threadIdx.x] = m[threadIdx.x];
+        st->step[threadIdx.x] = (threadIdx.x % 5 == 0) ? 1.f : 0.f;
+        if (threadIdx.x == 0) { st->prev_mse = DBL_MAX; st->iterations = 0; st->done = 0; st->state = 0; st->corr = 0; st->have_step = 0; }
+    }
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cur[i] = xform(m, __ldg(src + i));
+}
+
+// Exact nearest neighbour that also returns the matched point's coordinates (the grid copy carries them, so the
+// original-order target cloud is never touched during ICP).
+__device__ __forceinline__ void grid_nearest_pt(const GridView& g, float qx, float qy, float qz, int& best, float& best_d2, float4& bp) {
+    best = -1; best_d2 = FLT_MAX; bp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g.n == 0) return;
+    int cx = clampi(cell_coord(qx, g.mnx, g.inv_h), 0, g.dx - 1);
+    int cy = clampi(cell_coord(qy, g.mny, g.inv_h), 0, g.dy - 1);
+    int cz = clampi(cell_coord(qz, g.mnz, g.inv_h), 0, g.dz - 1);
+    {
+        int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
+        for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
+            for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y) {
+                int s0 = __ldg(g.cell_begin + cell_key(g, x0, y, z));
+                int s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
+                for (int s = s0; s < s1; ++s) {
+                    float4 p = __ldg(g.sorted + s);
+                    float d = dist2f(qx, qy, qz, p.x, p.y, p.z);
+                    int id = __float_as_int(p.w);
+                    if (d < best_d2 || (d == best_d2 && id < best)) { best_d2 = d; best = id; bp = p; }
+                }
+            }
+    }
+    int maxr = max(g.dx, max(g.dy, g.dz));
+    for (int R = 1; R <= maxr; ++R) {
+        if (best >= 0) {
+            double lim = (double)R * (double)g.h * 0.999;
+            if ((double)best_d2 <= lim * lim) return;
+        }
+        int Rn = R + 1;
+        for (int z = cz - Rn; z <= cz + Rn; ++z) {
+            if (z < 0 || z >= g.dz) continue;
+            for (int y = cy - Rn; y <= cy + Rn; ++y) {
+                if (y < 0 || y >= g.dy) continue;
+                bool full = (abs(z - cz) == Rn) || (abs(y - cy) == Rn);
+                int nseg = full ? 1 : 2;
+                for (int seg = 0; seg < nseg; ++seg) {
+                    int xa, xb;
+                    if (full) { xa = max(cx - Rn, 0); xb = min(cx + Rn, g.dx - 1); }
+                    else if (seg == 0) { xa = xb = cx - Rn; }
+                    else { xa = xb = cx + Rn; }
+                    if (xa < 0 || xb >= g.dx || xa > xb) continue;
+                    int s0 = __ldg(g.cell_begin + cell_key(g, xa, y, z));
+                    int s1 = __ldg(g.cell_begin + cell_key(g, xb, y, z) + 1);
+                    for (int s = s0; s < s1; ++s) {
+                        float4 p = __ldg(g.sorted + s);
+                        float d = dist2f(qx, qy, qz, p.x, p.y, p.z);
+                        int id = __float_as_int(p.w);
+                        if (d < best_d2 || (d == best_d2 && id < best)) { best_d2 = d; best = id; bp = p; }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// correspondence estimation + accumulation.  Applies the previous iteration's step first (transformCloud in place).
+__global__ void __launch_bounds__(ICP_THREADS) k_icp_corr(GridView g, float4* __restrict__ cur, int n, const IcpState* __restrict__ st,
+                                                           double dmax2, double* __restrict__ partials) {
+    __shared__ float m[16];
+    __shared__ double red[ICP_THREADS / 32][ICP_NSUM];
+    if (st->done) return;
+    int have = st->have_step;
+    if (threadIdx.x < 16) m[threadIdx.x] = st->step[threadIdx.x];
+    __syncthreads();
+    double acc[ICP_NSUM];
+#pragma unroll
+    for (int k = 0; k < ICP_NSUM; ++k) acc[k] = 0.0;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        float4 q = cur[i];
+        if (have) { q = xform(m, q); cur[i] = q; }
+        int b; float d2; float4 t;
+        grid_nearest_pt(g, q.x, q.y, q.z, b, d2, t);
+        if (b >= 0 && (double)d2 <= dmax2) {
+            double sx = q.x, sy = q.y, sz = q.z, tx = t.x, ty = t.y, tz = t.z;
+            acc[0] = sx; acc[1] = sy; acc[2] = sz; acc[3] = tx; acc[4] = ty; acc[5] = tz;
+            acc[6] = sx * tx; acc[7] = sx * ty; acc[8] = sx * tz;
+            acc[9] = sy * tx; acc[10] = sy * ty; acc[11] = sy * tz;
+            acc[12] = sz * tx; acc[13] = sz * ty; acc[14] = sz * tz;
+            acc[15] = (double)d2; acc[16] = 1.0;
+        }
+    }
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < ICP_NSUM; ++k) {
+        double v = warp_sum(acc[k]);
+        if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < ICP_NSUM) {
+        double v = 0;
+#pragma unroll
+        for (int w = 0; w < ICP_THREADS / 32; ++w) v += red[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * ICP_NSUM + threadIdx.x] = v;
+    }
+}
+
+// TransformationEstimationSVD + final = step * final + DefaultConvergenceCriteria.  One CTA of 17 warps: warp k reduces
+// sum k over the per-CTA partials in a fixed order.
+__global__ void __launch_bounds__(ICP_NSUM * 32) k_icp_solve(const double* __restrict__ partials, int nparts, IcpState* __restrict__ st,
+                                                             int max_iterations, int force, double mse_abs) {
+    __shared__ double sums[ICP_NSUM];
+    if (st->done) return;
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double v = 0;
+    for (int b = lane; b < nparts; b += 32) v += partials[(size_t)b * ICP_NSUM + warp];
+    v = warp_sum(v);
+    if (lane == 0) sums[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double cnt = sums[16];
+        st->corr = (int)cnt;
+        if (cnt < 3.0) { st->done = 1; st->state = 0; return; }
+        float step[16], fin[16];
+        horn_pose(&sums[0], &sums[3], &sums[6], cnt, step);
+        for (int i = 0; i < 16; ++i) fin[i] = st->final_[i];
+        matmul4(step, fin, fin);
+        for (int i = 0; i < 16; ++i) { st->final_[i] = fin[i]; st->step[i] = step[i]; }
+        st->have_step = 1;
+        int it = st->iterations + 1;
+        st->iterations = it;
+        if (it >= max_iterations) { st->done = 1; st->state = 1; return; }
+        if (!force) {
+            double cos_angle = 0.5 * ((double)step[0] + (double)step[5] + (double)step[10] - 1.0);
+            double tsq = (double)step[12] * (double)step[12] + (double)step[13] * (double)step[13] + (double)step[14] * (double)step[14];
+            if (cos_angle >= 1.0 && tsq <= 0.0) { st->done = 1; st->state = 2; return; }
+            double mse = sums[15] / cnt;
+            if (fabs(mse - st->prev_mse) < mse_abs) { st->done = 1; st->state = 3; return; }
+            st->prev_mse = mse;
+        }
+    }
+}
+
+// getFitnessScore(): mean squared NN distance of (final o source)
+__global__ void __launch_bounds__(ICP_THREADS) k_icp_fitness(GridView g, const float4* __restrict__ src, int n, const IcpState* __restrict__ st,
+                                                             double* __restrict__ partials) {
+    __shared__ float m[16];
+    __shared__ double red[ICP_THREADS / 32][2];
+    if (threadIdx.x < 16) m[threadIdx.x] = st->final_[threadIdx.x];
+    __syncthreads();
+    double s = 0, c = 0;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        float4 q = xform(m, __ldg(src + i));
+        int b; float d2;
+        grid_nearest(g, q.x, q.y, q.z, b, d2);
+        if (b >= 0) { s = (double)d2; c = 1.0; }
+    }
+    s = warp_sum(s); c = warp_sum(c);
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[warp][0] = s; red[warp][1] = c; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double v = 0;
+#pragma unroll
+        for (int w = 0; w < ICP_THREADS / 32; ++w) v += red[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * 2 + threadIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(64) k_icp_finish(const double* __restrict__ partials, int nparts, const IcpState* __restrict__ st,
+                                                   rtr_pose_result* __restrict__ res, int keep_ransac_fields) {
+    __shared__ double sums[2];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double v = 0;
+    for (int b = lane; b < nparts; b += 32) v += partials[(size_t)b * 2 + warp];
+    v = warp_sum(v);
+    if (lane == 0) sums[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 16; ++i) res->pose[i] = st->final_[i];
+        res->fitness = sums[1] > 0 ? (float)(sums[0] / sums[1]) : FLT_MAX;
+        res->iterations = st->iterations;
+        if (keep_ransac_fields) {
+            res->converged = res->converged ? st->state : 0;
+        } else {
+            res->converged = st->state; res->inliers = st->corr; res->hypothesis = -1; res->evaluated = 0;
+            res->model_id = 0; res->n_keypoints_src = 0; res->n_keypoints_tgt = 0;
+            for (int i = 0; i < 5; ++i) res->pad_[i] = 0;
+        }
+    }
+}
+
+int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const float* d_init_pose16, int init_from_result,
+                rtr_pose_result* d_result) {
+    rtr_context* ctx = src->ctx;
+    int n = src->n;
+    if (int e = rtr_ensure_bbox(tgt)) return e;
+    DevGrid* g;
+    if (int e = rtr_get_grid(tgt, rtr_icp_cell(tgt), &g)) return e;
+    GridView v = rtr_view(g);
+    float4* cur = nullptr; IcpState* st = nullptr; double* partials = nullptr;
+    int nb = std::max(nblk(n, ICP_THREADS), 1);
+    if (int e = dev_alloc(ctx, &cur, n, "icp")) return e;
+    if (int e = dev_alloc(ctx, &st, 1, "icp")) return e;
+    if (int e = dev_alloc(ctx, &partials, (size_t)nb * ICP_NSUM, "icp")) return e;
+    k_icp_init<<<nb, ICP_THREADS, 0, ctx->stream>>>(src->pts, n, d_init_pose16, init_from_result ? d_result : nullptr, cur, st);
+    RTR_LAUNCH_CHECK(ctx, "icp.init");
+    double dmax2 = p->max_correspondence_distance > 0.f ? (double)p->max_correspondence_distance * (double)p->max_correspondence_distance : DBL_MAX;
+    if (n >= 1 && tgt->n >= 1) {
+        for (int it = 0; it < p->max_iterations; ++it) {
+            k_icp_corr<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, cur, n, st, dmax2, partials);
+            RTR_LAUNCH_CHECK(ctx, "icp.corr");
+            k_icp_solve<<<1, ICP_NSUM * 32, 0, ctx->stream>>>(partials, nb, st, p->max_iterations, p->force_iterations, p->mse_threshold_absolute);
+            RTR_LAUNCH_CHECK(ctx, "icp.solve");
+        }
+    }
+    k_icp_fitness<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, src->pts, n, st, partials);
+    RTR_LAUNCH_CHECK(ctx, "icp.fitness");
+    k_icp_finish<<<1, 64, 0, ctx->stream>>>(partials, nb, st, d_result, init_from_result);
+    RTR_LAUNCH_CHECK(ctx, "icp.finish");
+    dev_free(ctx, cur); dev_free(ctx, st); dev_free(ctx, partials);
+    return 0;
+}
+
+// ============================================================================= whole registration
+__global__ void k_set_keypoints(rtr_pose_result* res, const int* n_src, const int* n_tgt) {
+    if (threadIdx.x == 0) { res->n_keypoints_src = *n_src; res->n_keypoints_tgt = *n_tgt; }
+}
+
+static int fetch_result(rtr_context* ctx, rtr_pose_result* d_result, rtr_pose_result* host_result) {
+    RTR_CHECK(cudaMemcpyAsync(ctx->pinned, d_result, sizeof(rtr_pose_result), cudaMemcpyDeviceToHost, ctx->stream), "result");
+    RTR_CHECK(cudaStreamSynchronize(ctx->stream), "result");
+    memcpy(host_result, ctx->pinned, sizeof(rtr_pose_result));
+    return 0;
+}
+
+extern "C" {
+
+int rtr_ransac_prerejective(rtr_cloud* source, rtr_cloud* target, const rtr_ransac_params* p, rtr_pose_result* host_result) {
+    if (!source || !target || !p || !host_result || source->ctx != target->ctx) return rtr_fail("ransac", "bad argument", RTR_ERR_INVALID);
+    rtr_context* ctx = source->ctx;
+    RTR_CHECK(cudaSetDevice(ctx->device), "ransac");
+    rtr_pose_result* d_res = nullptr;
+    if (int e = dev_alloc(ctx, &d_res, 1, "ransac")) return e;
+    if (int e = rtr_ransac_dev(source, target, p, d_res)) return e;
+    int rc = fetch_result(ctx, d_res, host_result);
+    dev_free(ctx, d_res);
+    return rc;
+}
+
+int rtr_icp(rtr_cloud* source, rtr_cloud* target, const rtr_icp_params* p, const float* init_pose16, rtr_pose_result* host_result) {
+    if (!source || !target || !p || !host_result || source->ctx != target->ctx || p->max_iterations < 0) return rtr_fail("icp", "bad argument", RTR_ERR_INVALID);
+    rtr_context* ctx = source->ctx;
+    RTR_CHECK(cudaSetDevice(ctx->device), "icp");
+    rtr_pose_result* d_res = nullptr; float* d_init = nullptr;
+    if (int e = dev_alloc(ctx, &d_res, 1, "icp")) return e;
+    if (init_pose16) {
+        if (int e = dev_alloc(ctx, &d_init, 16, "icp")) return e;
+        RTR_CHECK(cudaMemcpyAsync(d_init, init_pose16, 64, cudaMemcpyHostToDevice, ctx->stream), "icp");
+    }
+    if (int e = rtr_icp_dev(source, target, p, d_init, 0, d_res)) return e;
+    int rc = fetch_result(ctx, d_res, host_result);
+    dev_free(ctx, d_res); dev_free(ctx, d_init);
+    return rc;
+}
+
+int rtr_register(rtr_cloud* model, rtr_cloud* scene, const rtr_register_params* p, rtr_pose_result* host_result) {
+    if (!model || !scene || !p || !host_result || model->ctx != scene->ctx) return rtr_fail("register", "bad argument", RTR_ERR_INVALID);
+    rtr_context* ctx = model->ctx;
+    RTR_CHECK(cudaSetDevice(ctx->device), "register");
+    rtr_cloud* cl[2] = {model, scene};
+    int* d_cnt[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; ++i) {
+        if (int e = rtr_normals_dev(cl[i], p->normal_radius)) return e;
+        int* d_idx = nullptr; float4* d_xyz = nullptr;
+        if (int e = rtr_harris_dev(cl[i], p->harris_radius, p->harris_threshold, p->harris_nms, p->harris_refine, &d_idx, &d_xyz, &d_cnt[i])) return e;
+        dev_free(ctx, d_idx); dev_free(ctx, d_xyz);
+        if (int e = rtr_fpfh_dev(cl[i], p->fpfh_radius)) return e;
+    }
+    if (int e = rtr_match_dev(model, scene, p->ransac.correspondence_k)) return e;
+    rtr_pose_result* d_res = nullptr;
+    if (int e = dev_alloc(ctx, &d_res, 1, "register")) return e;
+    if (int e = rtr_ransac_dev(model, scene, &p->ransac, d_res)) return e;
+    if (p->run_icp) if (int e = rtr_icp_dev(model, scene, &p->icp, nullptr, 1, d_res)) return e;
+    k_set_keypoints<<<1, 32, 0, ctx->stream>>>(d_res, d_cnt[0], d_cnt[1]);
+    RTR_LAUNCH_CHECK(ctx, "register.kp");
+    int rc = fetch_result(ctx, d_res, host_result);
+    dev_free(ctx, d_res); dev_free(ctx, d_cnt[0]); dev_free(ctx, d_cnt[1]);
+    return rc;
+}
+
+int rtr_register_host(rtr_context* ctx, const float* host_model_xyz1, int n_model, const float* host_scene_xyz1, int n_scene,
+                      const rtr_register_params* p, rtr_pose_result* host_result) {
+    rtr_cloud *m = nullptr, *s = nullptr;
+    if (int e = rtr_cloud_upload(ctx, host_model_xyz1, n_model, &m)) return e;
+    if (int e = rtr_cloud_upload(ctx, host_scene_xyz1, n_scene, &s)) { rtr_cloud_free(m); return e; }
+    int rc = rtr_register(m, s, p, host_result);
+    rtr_cloud_free(m); rtr_cloud_free(s);
+    return rc;
+}
+
+}  // extern "C"
