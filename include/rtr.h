@@ -106,6 +106,11 @@ long long rtr_context_launches(rtr_context* ctx);
 int rtr_event_record(rtr_context* ctx, int slot);
 int rtr_event_elapsed_ms(rtr_context* ctx, int slot_a, int slot_b, float* ms);
 
+/* Per-operation device timing (CUDA events after every kernel / CUB pass / memset on the context's stream).
+ * rtr_profile_end writes "tag count total_ms" lines into buf. */
+int rtr_profile_begin(rtr_context* ctx);
+int rtr_profile_end(rtr_context* ctx, char* buf, int capacity);
+
 /* Upload a pcl::PointCloud<pcl::PointXYZ>::points array (n x 16 B, host).  Replaces the cloud hand-off
  * ModelPoint(Ptr) / ScanPoint(Ptr), model_point.h:165-168, scan_point.h:43-54. */
 int rtr_cloud_upload(rtr_context* ctx, const float* host_xyz1, int n, rtr_cloud** out);
@@ -113,6 +118,8 @@ int rtr_cloud_upload(rtr_context* ctx, const float* host_xyz1, int n, rtr_cloud*
 int rtr_cloud_from_device(rtr_context* ctx, const float* dev_xyz1, int n, rtr_cloud** out);
 int rtr_cloud_free(rtr_cloud* c);
 int rtr_cloud_size(const rtr_cloud* c);
+/* Drop all cached stages (grids, normals, features, correspondences); keep the points. */
+int rtr_cloud_reset(rtr_cloud* c);
 /* Apply a 4x4 (column-major) to the cloud in place: pcl::transformPointCloud(*c, *c, m)
  * (model_point.h:111, RealTimeRobot.cpp:105).  Invalidates cached stages. */
 int rtr_cloud_transform(rtr_cloud* c, const float* pose16);

@@ -18,7 +18,7 @@ i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 
 def build():
-    subprocess.check_call(["make", "-s", "-C", _HERE])
+    subprocess.check_call(["make", "-s", "-C", _HERE], stdout=subprocess.DEVNULL)
 
 
 def lib():

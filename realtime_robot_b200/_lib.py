@@ -14,7 +14,7 @@ _LIB = None
 # every symbol include/rtr.h declares (tests check that the library exports each one)
 EXPORTS = [
     "rtr_default_register_params", "rtr_context_create", "rtr_context_destroy", "rtr_context_sync", "rtr_context_stream",
-    "rtr_context_launches", "rtr_event_record", "rtr_event_elapsed_ms", "rtr_cloud_upload", "rtr_cloud_from_device",
+    "rtr_context_launches", "rtr_profile_begin", "rtr_profile_end", "rtr_cloud_reset", "rtr_event_record", "rtr_event_elapsed_ms", "rtr_cloud_upload", "rtr_cloud_from_device",
     "rtr_cloud_free", "rtr_cloud_size", "rtr_cloud_transform", "rtr_cloud_download", "rtr_radius_neighbors", "rtr_nearest",
     "rtr_normals", "rtr_harris3d", "rtr_fpfh", "rtr_match_features", "rtr_ransac_prerejective", "rtr_icp", "rtr_register",
     "rtr_register_host", "ComputeTDFWithCuda", "rtr_tdf_batch", "rtr_tdf_batch_dev",
@@ -44,6 +44,9 @@ def lib():
         L.rtr_context_launches.restype = ll
         L.rtr_event_record.argtypes = [vp, C.c_int]
         L.rtr_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, fp]
+        L.rtr_profile_begin.argtypes = [vp]
+        L.rtr_profile_end.argtypes = [vp, C.c_char_p, C.c_int]
+        L.rtr_cloud_reset.argtypes = [vp]
         L.rtr_cloud_upload.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
         L.rtr_cloud_from_device.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
         L.rtr_cloud_free.argtypes = [vp]

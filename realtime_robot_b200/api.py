@@ -48,6 +48,19 @@ class Context:
         _lib.check("rtr_event_elapsed_ms", _lib.lib().rtr_event_elapsed_ms(self._h, a, b, C.byref(ms)))
         return float(ms.value)
 
+    def profile_begin(self):
+        _lib.check("rtr_profile_begin", _lib.lib().rtr_profile_begin(self._h))
+
+    def profile_end(self) -> dict:
+        """{tag: (count, total_ms)} for every stream operation since profile_begin."""
+        buf = C.create_string_buffer(1 << 16)
+        _lib.check("rtr_profile_end", _lib.lib().rtr_profile_end(self._h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            tag, cnt, ms = line.rsplit(" ", 2)
+            out[tag] = (int(cnt), float(ms))
+        return out
+
     def close(self):
         if self._h:
             _lib.lib().rtr_context_destroy(self._h)
@@ -86,6 +99,10 @@ class Cloud:
         except Exception:
             pass
 
+    def reset(self):
+        """Forget every cached stage (the points stay resident)."""
+        _lib.check("rtr_cloud_reset", _lib.lib().rtr_cloud_reset(self._h))
+
     def download(self) -> np.ndarray:
         out = np.zeros((self.n, 4), dtype=np.float32)
         _lib.check("rtr_cloud_download", _lib.lib().rtr_cloud_download(self._h, _ptr(out)))
@@ -95,11 +112,13 @@ class Cloud:
         m = pose_to_colmajor(pose)
         _lib.check("rtr_cloud_transform", _lib.lib().rtr_cloud_transform(self._h, _ptr(m)))
 
-    def radius_neighbors(self, radius: float):
+    def radius_neighbors(self, radius: float, counts_only: bool = False):
         counts = np.zeros(self.n, dtype=np.int32)
         offsets = np.zeros(self.n + 1, dtype=np.int64)
         total = C.c_longlong()
         _lib.check("rtr_radius_neighbors", _lib.lib().rtr_radius_neighbors(self._h, radius, _ptr(counts), _ptr(offsets), None, 0, C.byref(total)))
+        if counts_only:
+            return counts, offsets, None
         idx = np.zeros(max(total.value, 1), dtype=np.int32)
         _lib.check("rtr_radius_neighbors", _lib.lib().rtr_radius_neighbors(self._h, radius, _ptr(counts), _ptr(offsets), _ptr(idx), total.value, C.byref(total)))
         return counts, offsets, idx[:total.value]

@@ -38,10 +38,15 @@ struct GridView {
     const float4* __restrict__ sorted;
 };
 
+struct ProfMark { const char* tag; cudaEvent_t ev; };
+
 struct rtr_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     long long launches = 0;
+    bool profile = false;                 // when set, every stream operation is followed by an event mark
+    std::vector<ProfMark> marks;
+    std::vector<cudaEvent_t> event_pool;
     int sm_count = 148;
     cudaEvent_t events[RTR_NUM_EVENTS] = {};
     // small pinned staging area for results / counters
@@ -72,9 +77,14 @@ struct rtr_cloud {
         }                                                                                          \
     } while (0)
 
+void rtr_prof_mark(rtr_context* ctx, const char* tag);
+// a non-kernel stream operation (memset / memcpy / CUB pass): only marked when profiling
+#define RTR_MARK(ctx, tag) do { if ((ctx)->profile) rtr_prof_mark((ctx), tag); } while (0)
+
 #define RTR_LAUNCH_CHECK(ctx, tag)                                                                 \
     do {                                                                                           \
         (ctx)->launches++;                                                                         \
+        if ((ctx)->profile) rtr_prof_mark((ctx), tag);                                             \
         cudaError_t e__ = cudaGetLastError();                                                      \
         if (e__ != cudaSuccess) {                                                                  \
             fprintf(stderr, "rtr[%s] kernel launch failed: %s\n", tag, cudaGetErrorString(e__));   \
@@ -193,14 +203,22 @@ __device__ __forceinline__ bool for_block27(const GridView& g, float qx, float q
     return true;
 }
 
-// exact nearest neighbour with expanding Chebyshev rings; ties -> lowest original index.
-__device__ __forceinline__ void grid_nearest(const GridView& g, float qx, float qy, float qz, int& best, float& best_d2) {
-    best = -1; best_d2 = FLT_MAX;
+// Exact nearest neighbour; ties -> lowest original index.  prune2: candidates farther than this (squared) are of no
+// interest to the caller (ICP's max correspondence distance), FLT_MAX for none.
+//   phase 1: the 3x3x3 cell block around the (clamped) query cell — 9 contiguous ranges.  Every point outside that
+//            block is farther than one cell size along some axis, so best_d2 <= (0.999 h)^2 ends the search
+//            (the common case in ICP).
+//   phase 2: otherwise walk slabs (z) and rows (y) outward from the query cell, pruning each slab / row by its exact
+//            box distance to the query and clipping the x range of a row to the current search sphere.  Cost is
+//            proportional to the rows inside the sphere, also for queries far outside the grid.
+// `slack` covers float cell assignment (a point may sit a hair outside its cell's nominal box).
+__device__ __forceinline__ void grid_nearest_ex(const GridView& g, float qx, float qy, float qz, float prune2, int& best,
+                                                float& best_d2, float4& bp) {
+    best = -1; best_d2 = FLT_MAX; bp = make_float4(0.f, 0.f, 0.f, 0.f);
     if (g.n == 0) return;
     int cx = clampi(cell_coord(qx, g.mnx, g.inv_h), 0, g.dx - 1);
     int cy = clampi(cell_coord(qy, g.mny, g.inv_h), 0, g.dy - 1);
     int cz = clampi(cell_coord(qz, g.mnz, g.inv_h), 0, g.dz - 1);
-    // rings 0 and 1 together: 9 contiguous row ranges
     {
         int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
         for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
@@ -211,41 +229,49 @@ __device__ __forceinline__ void grid_nearest(const GridView& g, float qx, float 
                     float4 p = __ldg(g.sorted + s);
                     float d = dist2f(qx, qy, qz, p.x, p.y, p.z);
                     int id = __float_as_int(p.w);
-                    if (d < best_d2 || (d == best_d2 && id < best)) { best_d2 = d; best = id; }
+                    if (d < best_d2 || (d == best_d2 && id < best)) { best_d2 = d; best = id; bp = p; }
                 }
             }
     }
-    int maxr = max(g.dx, max(g.dy, g.dz));
-    for (int R = 1; R <= maxr; ++R) {
-        if (best >= 0) {
-            double lim = (double)R * (double)g.h * 0.999;
-            if ((double)best_d2 <= lim * lim) return;
-        }
-        int Rn = R + 1;   // visit shell Rn: rows whose (y,z) is on the shell take the full x span, others only the two x caps
-        for (int z = cz - Rn; z <= cz + Rn; ++z) {
-            if (z < 0 || z >= g.dz) continue;
-            for (int y = cy - Rn; y <= cy + Rn; ++y) {
-                if (y < 0 || y >= g.dy) continue;
-                bool full = (abs(z - cz) == Rn) || (abs(y - cy) == Rn);
-                int nseg = full ? 1 : 2;
-                for (int seg = 0; seg < nseg; ++seg) {
-                    int xa, xb;
-                    if (full) { xa = max(cx - Rn, 0); xb = min(cx + Rn, g.dx - 1); }
-                    else if (seg == 0) { xa = xb = cx - Rn; }
-                    else { xa = xb = cx + Rn; }
-                    if (xa < 0 || xb >= g.dx || xa > xb) continue;
+    float hh = g.h * 0.999f;
+    if (best >= 0 && best_d2 <= hh * hh) return;
+    float ext = g.h * (float)max(g.dx, max(g.dy, g.dz));
+    float slack = g.h * 1e-3f + 2e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + fabsf(g.mnx) + fabsf(g.mny) + fabsf(g.mnz) + ext);
+    for (int zdir = 0; zdir < 2; ++zdir) {
+        for (int z = zdir == 0 ? cz : cz - 1; z >= 0 && z < g.dz; z += (zdir == 0 ? 1 : -1)) {
+            float lo = g.mnz + (float)z * g.h, hi = lo + g.h;
+            float dzl = qz < lo ? lo - qz : (qz > hi ? qz - hi : 0.f);
+            dzl = fmaxf(dzl - slack, 0.f);
+            float bound = fminf(best_d2, prune2);
+            if (dzl * dzl > bound) break;
+            for (int ydir = 0; ydir < 2; ++ydir) {
+                for (int y = ydir == 0 ? cy : cy - 1; y >= 0 && y < g.dy; y += (ydir == 0 ? 1 : -1)) {
+                    float lo2 = g.mny + (float)y * g.h, hi2 = lo2 + g.h;
+                    float dyl = qy < lo2 ? lo2 - qy : (qy > hi2 ? qy - hi2 : 0.f);
+                    dyl = fmaxf(dyl - slack, 0.f);
+                    bound = fminf(best_d2, prune2);
+                    float rem = bound - (dzl * dzl + dyl * dyl);
+                    if (rem < 0.f) break;
+                    float rx = sqrtf(rem) * 1.000001f + slack;
+                    int xa = clampi(cell_coord(qx - rx, g.mnx, g.inv_h), 0, g.dx - 1);
+                    int xb = clampi(cell_coord(qx + rx, g.mnx, g.inv_h), 0, g.dx - 1);
                     int s0 = __ldg(g.cell_begin + cell_key(g, xa, y, z));
                     int s1 = __ldg(g.cell_begin + cell_key(g, xb, y, z) + 1);
                     for (int s = s0; s < s1; ++s) {
                         float4 p = __ldg(g.sorted + s);
                         float d = dist2f(qx, qy, qz, p.x, p.y, p.z);
                         int id = __float_as_int(p.w);
-                        if (d < best_d2 || (d == best_d2 && id < best)) { best_d2 = d; best = id; }
+                        if (d < best_d2 || (d == best_d2 && id < best)) { best_d2 = d; best = id; bp = p; }
                     }
                 }
             }
         }
     }
+}
+
+__device__ __forceinline__ void grid_nearest(const GridView& g, float qx, float qy, float qz, int& best, float& best_d2) {
+    float4 bp;
+    grid_nearest_ex(g, qx, qy, qz, FLT_MAX, best, best_d2, bp);
 }
 
 // cyclic Jacobi, symmetric NxN, fp64, + - * / sqrt only (same operation sequence as the oracle's restatement)

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <string>
 
 // ----------------------------------------------------------------------------- kernels
 __global__ void k_cell_keys(const float4* __restrict__ pts, int n, float mnx, float mny, float mnz, float inv_h, int dx,
@@ -215,6 +216,7 @@ int rtr_get_grid(rtr_cloud* c, float cell, DevGrid** out) {
     if (int e = dev_alloc(ctx, &g.cell_begin, (size_t)g.ncells + 1, "grid")) return e;
     if (int e = dev_alloc(ctx, &g.sorted, n, "grid")) return e;
     RTR_CHECK(cudaMemsetAsync(counts, 0, ((size_t)g.ncells + 1) * sizeof(int), ctx->stream), "grid");
+    RTR_MARK(ctx, "grid.memset");
     if (n > 0) {
         k_cell_keys<<<nblk(n, 256), 256, 0, ctx->stream>>>(c->pts, n, g.mnx, g.mny, g.mnz, g.inv_h, g.dx, g.dy, g.dz, keys, vals, counts);
         RTR_LAUNCH_CHECK(ctx, "grid.keys");
@@ -228,7 +230,9 @@ int rtr_get_grid(rtr_cloud* c, float cell, DevGrid** out) {
     size_t tb = std::max(tb_sort, tb_scan);
     if (int e = dev_alloc(ctx, (char**)&temp, tb, "grid")) return e;
     if (n > 0) RTR_CHECK(cub::DeviceRadixSort::SortPairs(temp, tb_sort, keys, keys2, vals, vals2, n, 0, end_bit, ctx->stream), "grid.sort");
+    RTR_MARK(ctx, "grid.cub_sort");
     RTR_CHECK(cub::DeviceScan::ExclusiveSum(temp, tb_scan, counts, g.cell_begin, g.ncells + 1, ctx->stream), "grid.scan");
+    RTR_MARK(ctx, "grid.cub_scan");
     if (n > 0) {
         k_gather_sorted<<<nblk(n, 256), 256, 0, ctx->stream>>>(c->pts, vals2, n, g.sorted);
         RTR_LAUNCH_CHECK(ctx, "grid.gather");
@@ -252,7 +256,58 @@ int rtr_grid_normals(rtr_cloud* c, DevGrid* g) {
     return 0;
 }
 
+void rtr_prof_mark(rtr_context* ctx, const char* tag) {
+    cudaEvent_t ev;
+    if (!ctx->event_pool.empty()) { ev = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+    else if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, ctx->stream);
+    ctx->marks.push_back({tag, ev});
+}
+
 extern "C" {
+
+// Per-operation device timing for bench.py's roofline: between begin and end every kernel / CUB pass / memset on the
+// context's stream is followed by a CUDA event; the interval since the previous mark is attributed to that operation.
+int rtr_profile_begin(rtr_context* ctx) {
+    if (!ctx) return rtr_fail("profile", "null context", RTR_ERR_INVALID);
+    RTR_CHECK(cudaSetDevice(ctx->device), "profile");
+    for (auto& m : ctx->marks) ctx->event_pool.push_back(m.ev);
+    ctx->marks.clear();
+    ctx->profile = true;
+    rtr_prof_mark(ctx, "(begin)");
+    return 0;
+}
+
+// Writes "tag count total_ms" lines into buf; returns 0, or RTR_ERR_CAPACITY if buf is too small.
+int rtr_profile_end(rtr_context* ctx, char* buf, int capacity) {
+    if (!ctx || !buf || capacity < 1) return rtr_fail("profile", "bad argument", RTR_ERR_INVALID);
+    ctx->profile = false;
+    RTR_CHECK(cudaStreamSynchronize(ctx->stream), "profile");
+    std::map<std::string, std::pair<long long, double>> agg;
+    for (size_t i = 1; i < ctx->marks.size(); ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->marks[i - 1].ev, ctx->marks[i].ev) != cudaSuccess) continue;
+        auto& a = agg[ctx->marks[i].tag];
+        a.first++; a.second += ms;
+    }
+    for (auto& m : ctx->marks) ctx->event_pool.push_back(m.ev);
+    ctx->marks.clear();
+    std::string out;
+    char line[256];
+    for (auto& kv : agg) { snprintf(line, sizeof(line), "%s %lld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second); out += line; }
+    if ((int)out.size() + 1 > capacity) return RTR_ERR_CAPACITY;
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return 0;
+}
+
+// Drop every cached stage of a cloud (grids, normals, features, correspondences) but keep the points and the bounding
+// box: the next stage call recomputes from the points.  bench.py calls this so no step reuses earlier results.
+int rtr_cloud_reset(rtr_cloud* c) {
+    if (!c) return rtr_fail("reset", "null cloud", RTR_ERR_INVALID);
+    RTR_CHECK(cudaSetDevice(c->ctx->device), "reset");
+    rtr_invalidate(c);
+    return 0;
+}
 
 void rtr_default_register_params(rtr_register_params* p) {
     memset(p, 0, sizeof(*p));
@@ -290,6 +345,8 @@ int rtr_context_destroy(rtr_context* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < RTR_NUM_EVENTS; ++i) if (ctx->events[i]) cudaEventDestroy(ctx->events[i]);
+    for (auto& m : ctx->marks) cudaEventDestroy(m.ev);
+    for (auto& e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -333,6 +390,7 @@ int rtr_cloud_upload(rtr_context* ctx, const float* host_xyz1, int n, rtr_cloud*
     if (int e = cloud_new(ctx, n, out)) return e;
     rtr_cloud* c = *out;
     if (n > 0) RTR_CHECK(cudaMemcpyAsync(c->pts, host_xyz1, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream), "cloud.h2d");
+    RTR_MARK(ctx, "cloud.h2d");
     // the caller's buffer is host memory: take the bounding box here, so no device round trip is needed later
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     bool any = false;

@@ -406,6 +406,7 @@ int rtr_harris_dev(rtr_cloud* c, float radius, float threshold, int nms, int ref
         char* temp = nullptr;
         if (int e = dev_alloc(ctx, &temp, tb, "harris")) return e;
         RTR_CHECK(cub::DeviceSelect::Flagged(temp, tb, iota, flags, *d_kp_idx, *d_count, n, ctx->stream), "harris.select");
+        RTR_MARK(ctx, "harris.cub_select");
         dev_free(ctx, temp);
         // the corner count lives on the device; launch for the worst case (every point a corner), threads beyond exit
         k_harris_refine<<<nblk(n, 64), 64, 0, ctx->stream>>>(v, g->sorted_normals, c->pts, r2, *d_kp_idx, *d_count, n, *d_kp_xyz, refine);

@@ -220,6 +220,7 @@ int rtr_ransac_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_ransac_params* p, r
     for (long long base = h0; base < h1; base += CHUNK) {
         a.h_base = base; a.h_count = (int)std::min<long long>(CHUNK, h1 - base);
         RTR_CHECK(cudaMemsetAsync(count, 0, sizeof(int), ctx->stream), "ransac");
+        RTR_MARK(ctx, "ransac.memset");
         k_ransac_sample<<<nblk(a.h_count, 256), 256, 0, ctx->stream>>>(a, survivors, count);
         RTR_LAUNCH_CHECK(ctx, "ransac.sample");
         k_ransac_pose<<<nblk(a.h_count, 64), 64, 0, ctx->stream>>>(a, survivors, count, poses);
@@ -268,64 +269,9 @@ __global__ void k_icp_init(const float4* __restrict__ src, int n, const float* _
     if (i < n) cur[i] = xform(m, __ldg(src + i));
 }
 
-// Exact nearest neighbour that also returns the matched point's coordinates (the grid copy carries them, so the
-// original-order target cloud is never touched during ICP).
-__device__ __forceinline__ void grid_nearest_pt(const GridView& g, float qx, float qy, float qz, int& best, float& best_d2, float4& bp) {
-    best = -1; best_d2 = FLT_MAX; bp = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g.n == 0) return;
-    int cx = clampi(cell_coord(qx, g.mnx, g.inv_h), 0, g.dx - 1);
-    int cy = clampi(cell_coord(qy, g.mny, g.inv_h), 0, g.dy - 1);
-    int cz = clampi(cell_coord(qz, g.mnz, g.inv_h), 0, g.dz - 1);
-    {
-        int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
-        for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
-            for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y) {
-                int s0 = __ldg(g.cell_begin + cell_key(g, x0, y, z));
-                int s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
-                for (int s = s0; s < s1; ++s) {
-                    float4 p = __ldg(g.sorted + s);
-                    float d = dist2f(qx, qy, qz, p.x, p.y, p.z);
-                    int id = __float_as_int(p.w);
-                    if (d < best_d2 || (d == best_d2 && id < best)) { best_d2 = d; best = id; bp = p; }
-                }
-            }
-    }
-    int maxr = max(g.dx, max(g.dy, g.dz));
-    for (int R = 1; R <= maxr; ++R) {
-        if (best >= 0) {
-            double lim = (double)R * (double)g.h * 0.999;
-            if ((double)best_d2 <= lim * lim) return;
-        }
-        int Rn = R + 1;
-        for (int z = cz - Rn; z <= cz + Rn; ++z) {
-            if (z < 0 || z >= g.dz) continue;
-            for (int y = cy - Rn; y <= cy + Rn; ++y) {
-                if (y < 0 || y >= g.dy) continue;
-                bool full = (abs(z - cz) == Rn) || (abs(y - cy) == Rn);
-                int nseg = full ? 1 : 2;
-                for (int seg = 0; seg < nseg; ++seg) {
-                    int xa, xb;
-                    if (full) { xa = max(cx - Rn, 0); xb = min(cx + Rn, g.dx - 1); }
-                    else if (seg == 0) { xa = xb = cx - Rn; }
-                    else { xa = xb = cx + Rn; }
-                    if (xa < 0 || xb >= g.dx || xa > xb) continue;
-                    int s0 = __ldg(g.cell_begin + cell_key(g, xa, y, z));
-                    int s1 = __ldg(g.cell_begin + cell_key(g, xb, y, z) + 1);
-                    for (int s = s0; s < s1; ++s) {
-                        float4 p = __ldg(g.sorted + s);
-                        float d = dist2f(qx, qy, qz, p.x, p.y, p.z);
-                        int id = __float_as_int(p.w);
-                        if (d < best_d2 || (d == best_d2 && id < best)) { best_d2 = d; best = id; bp = p; }
-                    }
-                }
-            }
-        }
-    }
-}
-
 // correspondence estimation + accumulation.  Applies the previous iteration's step first (transformCloud in place).
 __global__ void __launch_bounds__(ICP_THREADS) k_icp_corr(GridView g, float4* __restrict__ cur, int n, const IcpState* __restrict__ st,
-                                                           double dmax2, double* __restrict__ partials) {
+                                                           double dmax2, float prune2, double* __restrict__ partials) {
     __shared__ float m[16];
     __shared__ double red[ICP_THREADS / 32][ICP_NSUM];
     if (st->done) return;
@@ -340,7 +286,8 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_corr(GridView g, float4* __
         float4 q = cur[i];
         if (have) { q = xform(m, q); cur[i] = q; }
         int b; float d2; float4 t;
-        grid_nearest_pt(g, q.x, q.y, q.z, b, d2, t);
+        // the grid copy carries the matched point's coordinates: the original-order target is never touched
+        grid_nearest_ex(g, q.x, q.y, q.z, prune2, b, d2, t);
         if (b >= 0 && (double)d2 <= dmax2) {
             double sx = q.x, sy = q.y, sz = q.z, tx = t.x, ty = t.y, tz = t.z;
             acc[0] = sx; acc[1] = sy; acc[2] = sz; acc[3] = tx; acc[4] = ty; acc[5] = tz;
@@ -467,9 +414,12 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     k_icp_init<<<nb, ICP_THREADS, 0, ctx->stream>>>(src->pts, n, d_init_pose16, init_from_result ? d_result : nullptr, cur, st);
     RTR_LAUNCH_CHECK(ctx, "icp.init");
     double dmax2 = p->max_correspondence_distance > 0.f ? (double)p->max_correspondence_distance * (double)p->max_correspondence_distance : DBL_MAX;
+    // search radius for pruning: the cap rounded UP in float so no candidate with d2 <= dmax2 is ever skipped
+    float prune2 = FLT_MAX;
+    if (p->max_correspondence_distance > 0.f) { prune2 = (float)dmax2; if ((double)prune2 < dmax2) prune2 = nextafterf(prune2, FLT_MAX); }
     if (n >= 1 && tgt->n >= 1) {
         for (int it = 0; it < p->max_iterations; ++it) {
-            k_icp_corr<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, cur, n, st, dmax2, partials);
+            k_icp_corr<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, cur, n, st, dmax2, prune2, partials);
             RTR_LAUNCH_CHECK(ctx, "icp.corr");
             k_icp_solve<<<1, ICP_NSUM * 32, 0, ctx->stream>>>(partials, nb, st, p->max_iterations, p->force_iterations, p->mse_threshold_absolute);
             RTR_LAUNCH_CHECK(ctx, "icp.solve");
@@ -490,6 +440,7 @@ __global__ void k_set_keypoints(rtr_pose_result* res, const int* n_src, const in
 
 static int fetch_result(rtr_context* ctx, rtr_pose_result* d_result, rtr_pose_result* host_result) {
     RTR_CHECK(cudaMemcpyAsync(ctx->pinned, d_result, sizeof(rtr_pose_result), cudaMemcpyDeviceToHost, ctx->stream), "result");
+    RTR_MARK(ctx, "result.d2h");
     RTR_CHECK(cudaStreamSynchronize(ctx->stream), "result");
     memcpy(host_result, ctx->pinned, sizeof(rtr_pose_result));
     return 0;

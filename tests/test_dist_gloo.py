@@ -1,0 +1,72 @@
+"""N > 1 host logic on CPU: world_size-2 gloo run of the shard planner and the 128-byte record all-gather."""
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+
+from conftest import ROOT
+from realtime_robot_b200 import dist
+from realtime_robot_b200.params import PoseResult
+
+
+def test_shard_planners():
+    assert dist.shard_models(8, 0, 1) == list(range(8))
+    got = sorted(sum((dist.shard_models(8, r, 3) for r in range(3)), []))
+    assert got == list(range(8))
+    for world in (1, 2, 4, 8, 3):
+        spans = [dist.shard_hypotheses(50000, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == 50000
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+
+
+def test_record_roundtrip_and_selection():
+    rs = []
+    for i, (fit, h, conv) in enumerate([(0.5, 7, 1), (0.25, 9, 1), (0.25, 3, 1), (0.1, 1, 0)]):
+        r = PoseResult(); r.fitness = fit; r.hypothesis = h; r.converged = conv; r.model_id = i
+        r.pose[0] = float(i)
+        rs.append(r)
+    back = dist.bytes_to_records(dist.records_to_bytes(rs))
+    assert [bytes(a) == bytes(b) for a, b in zip(rs, back)] == [True] * 4
+    assert dist.select_best_hypothesis(rs).hypothesis == 3          # ties on fitness -> lowest hypothesis id
+    assert dist.select_best_model(rs).model_id == 1
+    assert dist.select_best_hypothesis([rs[3]]) is None
+
+
+WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, %r)
+    import torch.distributed as td
+    from realtime_robot_b200 import dist
+    from realtime_robot_b200.params import PoseResult
+    td.init_process_group("gloo")
+    rank, world = td.get_rank(), td.get_world_size()
+    mine = []
+    for m in dist.shard_models(5, rank, world):
+        r = PoseResult(); r.model_id = m; r.fitness = 1.0 / (1 + m); r.converged = 1; r.hypothesis = 100 + m
+        mine.append(r)
+    per = (5 + world - 1) // world
+    allr = dist.all_gather_records(mine, per)
+    ids = sorted(r.model_id for r in allr)
+    best = dist.select_best_model(allr)
+    b, e = dist.shard_hypotheses(1000, rank, world)
+    print("RANK", rank, ids, best.model_id, b, e, flush=True)
+    td.destroy_process_group()
+""")
+
+
+def test_world_size_2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(WORKER % ROOT)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    lines = sorted(l for o in outs for l in o.splitlines() if l.startswith("RANK"))
+    assert lines[0] == "RANK 0 [0, 1, 2, 3, 4] 4 0 500"
+    assert lines[1] == "RANK 1 [0, 1, 2, 3, 4] 4 500 1000"
