@@ -51,7 +51,7 @@ def workload_config(params):
             "registrations_per_step_per_gpu": len(MODELS),
             "ransac_hypotheses": int(params.ransac.max_iterations),
             "icp_iterations": int(params.icp.max_iterations),
-            "parallelism": "model-sharded, 8 models per rank, one 128 B/record all-gather per step",
+            "parallelism": "model-sharded, 8 models per rank issued concurrently on 8 streams, one 128 B/record all-gather per step",
             "l2": "flushed between timed steps (256 MiB write); inputs are < 1 MB"}
 
 
@@ -179,7 +179,12 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         td.init_process_group("nccl", device_id=dev)
-    ctx = api.Context(local_rank)
+    # one context (stream) per in-flight registration: the step's 8 registrations are issued concurrently from 8 host
+    # threads (ctypes releases the GIL), so small kernels of different registrations share the 148 SMs
+    from concurrent.futures import ThreadPoolExecutor
+    ctxs = [api.Context(local_rank) for _ in MODELS]
+    ctx = ctxs[0]
+    pool = ThreadPoolExecutor(max_workers=len(MODELS))
     p = default_register_params()
     hbm_peak, bf16_peak, peak_src = peaks()
 
@@ -194,8 +199,9 @@ def main():
         t, h = pinned(load_cloud(m))
         keep.append(t)
         models_h.append(h)
-    scene_d = api.Cloud(ctx, scene_h)
-    models_d = [api.Cloud(ctx, h) for h in models_h]
+    scenes_d = [api.Cloud(c, scene_h) for c in ctxs]
+    scene_d = scenes_d[0]
+    models_d = [api.Cloud(c, h) for c, h in zip(ctxs, models_h)]
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def gather(recs):
@@ -205,16 +211,18 @@ def main():
             return recs
         return dist.all_gather_records(recs, len(MODELS), device=dev)
 
+    def reg_resident(i):
+        models_d[i].reset(); scenes_d[i].reset()
+        return api.register(models_d[i], scenes_d[i], p)
+
+    def reg_e2e(i):
+        return api.register_host(ctxs[i], models_h[i], scene_h, p)
+
     def step_resident():
-        recs = []
-        for cm in models_d:
-            cm.reset(); scene_d.reset()
-            recs.append(api.register(cm, scene_d, p))
-        return gather(recs)
+        return gather(list(pool.map(reg_resident, range(len(MODELS)))))
 
     def step_e2e():
-        recs = [api.register_host(ctx, h, scene_h, p) for h in models_h]
-        return gather(recs)
+        return gather(list(pool.map(reg_e2e, range(len(MODELS)))))
 
     def barrier():
         torch.cuda.synchronize()
@@ -253,12 +261,12 @@ def main():
 
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    l0 = ctx.launches
+    l0 = sum(c.launches for c in ctxs)
     wall0 = time.perf_counter()
     ms_res, recs = timed(step_resident, args.steps)
     barrier()
     wall_res = time.perf_counter() - wall0
-    launches = ctx.launches - l0
+    launches = sum(c.launches for c in ctxs) - l0
     ms_e2e, recs_e2e = timed(step_e2e, args.steps)
     barrier()
     clocks = sampler.stop() if sampler else None
@@ -276,10 +284,15 @@ def main():
 
     log(f"timed: resident {ms_res / args.steps:.2f} ms/step, e2e {ms_e2e / args.steps:.2f} ms/step")
     # ---- per-kernel device time of one more step (profiling marks; not part of the timed region)
-    ctx.profile_begin()
-    step_resident()
-    prof = ctx.profile_end()
-    step_ms = sum(v[1] for v in prof.values())
+    # (run one registration at a time here so that the intervals of different streams do not overlap)
+    prof = {}
+    for i in range(len(MODELS)):
+        ctxs[i].profile_begin()
+        reg_resident(i)
+        for k, v in ctxs[i].profile_end().items():
+            a = prof.get(k, (0, 0.0))
+            prof[k] = (a[0] + v[0], a[1] + v[1])
+    step_ms = sum(v[1] for v in prof.values())      # serialised device time of the step's operations
     top = sorted(prof.items(), key=lambda kv: -kv[1][1])
     kernel_share = {k: {"launches": v[0], "ms": round(v[1], 4), "share": round(v[1] / step_ms, 4)} for k, v in top[:8]}
 
@@ -378,7 +391,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps, "entry": "rtr_register_host (pinned host clouds)"},
                 "gpu_launches": int(launches),
-                "clocks": clocks, "roofline": roofline, "kernel_share": kernel_share,
+                "clocks": clocks, "roofline": roofline, "kernel_share": kernel_share, "serialised_device_ms_per_step": round(step_ms, 3),
                 "cpu_baseline": cpu, "icp_1m": icp_out,
                 "wall_ms_per_step_incl_l2_flush": 1e3 * wall_res / args.steps,
                 "results": [{"model": m, "fitness": float(r.fitness), "inliers": int(r.inliers), "hypothesis": int(r.hypothesis),

@@ -174,7 +174,8 @@ int rtr_icp(rtr_cloud* source, rtr_cloud* target, const rtr_icp_params* p, const
             rtr_pose_result* host_result);
 
 /* The whole model-to-scene registration the north star names, device-resident end to end:
- * grid -> normals -> Harris -> FPFH (both clouds) -> feature k-NN -> prerejective RANSAC -> ICP.
+ * grid -> normals -> Harris -> FPFH (both clouds) -> feature k-NN -> prerejective RANSAC -> ICP (skipped when RANSAC
+ * accepted no hypothesis: the result then keeps the identity pose, fitness FLT_MAX, converged 0).
  * Sequencing counterpart of main(), RealTimeRobot.cpp:39-105. */
 int rtr_register(rtr_cloud* model, rtr_cloud* scene, const rtr_register_params* p, rtr_pose_result* host_result);
 

@@ -428,25 +428,33 @@ void harris_response_impl(const P4* pts, int n, const float* nrm4, const RadiusI
     }
 }
 
-// refineCorners (App. A.3): <= 10 Gauss-Newton steps, neighbours of the moving corner in ascending index order
+// refineCorners (App. A.3): <= 10 Gauss-Newton steps  corner <- (sum n n^T)^-1 sum n n^T p  over the r-neighbours of the
+// moving corner.  The two sums are accumulated in 64-bit fixed point (terms rounded to 2^-40 resp. 2^-34) so that the
+// result does not depend on the order of the neighbours — this stage is ill-conditioned, and the CUDA path reduces the
+// same integers with warp shuffles.
 void harris_refine_one(const P4* pts, const float* nrm4, const RadiusIndex& idx, P4& corner) {
+    const double SA = 1099511627776.0, SB = 17179869184.0;   // 2^40, 2^34
     std::vector<int> nb;
     int it = 0; double diff;
     do {
         P4 cur = corner;
         idx.query(cur, nb);
-        double A[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
+        long long q[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         for (int j : nb) {
             const float* nj = nrm4 + 4 * (size_t)j;
             if (!finite3(nj)) continue;
             double x = nj[0], y = nj[1], z = nj[2];
             double xx = x * x, xy = x * y, xz = x * z, yy = y * y, yz = y * z, zz = z * z;
-            A[0] += xx; A[1] += xy; A[2] += xz; A[3] += yy; A[4] += yz; A[5] += zz;
             double px = pts[j].x, py = pts[j].y, pz = pts[j].z;
-            b[0] += (xx * px + xy * py) + xz * pz;
-            b[1] += (xy * px + yy * py) + yz * pz;
-            b[2] += (xz * px + yz * py) + zz * pz;
+            q[0] += std::llrint(xx * SA); q[1] += std::llrint(xy * SA); q[2] += std::llrint(xz * SA);
+            q[3] += std::llrint(yy * SA); q[4] += std::llrint(yz * SA); q[5] += std::llrint(zz * SA);
+            q[6] += std::llrint(((xx * px + xy * py) + xz * pz) * SB);
+            q[7] += std::llrint(((xy * px + yy * py) + yz * pz) * SB);
+            q[8] += std::llrint(((xz * px + yz * py) + zz * pz) * SB);
         }
+        double A[6], b[3];
+        for (int k = 0; k < 6; ++k) A[k] = (double)q[k] / SA;
+        for (int k = 0; k < 3; ++k) b[k] = (double)q[6 + k] / SB;
         // symmetric 3x3 inverse by cofactors
         double c00 = A[3] * A[5] - A[4] * A[4], c01 = A[2] * A[4] - A[1] * A[5], c02 = A[1] * A[4] - A[2] * A[3];
         double c11 = A[0] * A[5] - A[2] * A[2], c12 = A[1] * A[2] - A[0] * A[4], c22 = A[0] * A[3] - A[1] * A[1];
@@ -907,12 +915,12 @@ void orc_register(const float* model_xyz1, int nm, const float* scene_xyz1, int 
     orc_match_features(fm.data(), nm, fs.data(), nsc, k, knn.data(), nullptr);
     rtr_pose_result r;
     orc_ransac_prerejective(model_xyz1, nm, scene_xyz1, nsc, knn.data(), k, &p->ransac, &r);
-    if (p->run_icp) {
+    if (p->run_icp && r.converged) {      // nothing accepted -> no pose to refine (result stays identity / FLT_MAX)
         rtr_pose_result ri;
         orc_icp(model_xyz1, nm, scene_xyz1, nsc, &p->icp, r.pose, &ri);
         std::memcpy(r.pose, ri.pose, sizeof(r.pose));
         r.fitness = ri.fitness; r.iterations = ri.iterations;
-        r.converged = r.converged ? ri.converged : 0;
+        r.converged = ri.converged;
     }
     r.n_keypoints_src = kpm; r.n_keypoints_tgt = kps;
     *res = r;

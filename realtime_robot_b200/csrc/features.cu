@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -100,81 +101,78 @@ __global__ void __launch_bounds__(128) k_harris_nms(GridView g, const float* __r
     flags[__float_as_int(q.w)] = keep ? 1 : 0;
 }
 
-// refineCorners: one thread per corner; neighbours are consumed in ASCENDING ORIGINAL INDEX (27-way merge over the
-// cell runs, each of which is already ascending) so that the fp64 sums are bit-identical to the oracle's.
-__global__ void k_harris_refine(GridView g, const float4* __restrict__ sn, const float4* __restrict__ pts, float r2,
-                                const int* __restrict__ kp_idx, const int* __restrict__ kp_count, int capacity,
-                                float4* __restrict__ kp_xyz, int refine) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
+// refineCorners: one warp per corner, lanes stride over the 9 candidate ranges.  The sums A = sum n n^T and
+// b = sum n n^T p are accumulated in 64-bit FIXED POINT (each fp64 term rounded to 2^-40 resp. 2^-34): integer addition
+// is associative, so the warp-shuffle reduction gives the same bits as the oracle's sequential loop in any order.  This
+// stage is ill-conditioned (corners can move by tens of centimetres), which is why it is made exactly reproducible.
+#define REFINE_SCALE_A 1099511627776.0     /* 2^40 */
+#define REFINE_SCALE_B 17179869184.0       /* 2^34 */
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__global__ void __launch_bounds__(128) k_harris_refine(GridView g, const float4* __restrict__ sn, const float4* __restrict__ pts, float r2,
+                                                       const int* __restrict__ kp_idx, const int* __restrict__ kp_count, int capacity,
+                                                       float4* __restrict__ kp_xyz, int refine) {
+    int lane = threadIdx.x & 31;
+    int nwarps = (gridDim.x * blockDim.x) >> 5;
     int m = min(*kp_count, capacity);
-    if (t >= m) return;
-    float4 c = __ldg(pts + kp_idx[t]);
-    c.w = 1.0f;
-    if (refine) {
-        int it = 0;
-        double diff;
-        do {
-            float4 cur = c;
-            double A0 = 0, A1 = 0, A2 = 0, A3 = 0, A4 = 0, A5 = 0, b0 = 0, b1 = 0, b2 = 0;
-            int cx = cell_coord(cur.x, g.mnx, g.inv_h), cy = cell_coord(cur.y, g.mny, g.inv_h), cz = cell_coord(cur.z, g.mnz, g.inv_h);
-            if (!(cx < -1 || cy < -1 || cz < -1 || cx > g.dx || cy > g.dy || cz > g.dz)) {
-                cx = clampi(cx, 0, g.dx - 1); cy = clampi(cy, 0, g.dy - 1); cz = clampi(cz, 0, g.dz - 1);
-                int cur_s[27], end_s[27], nc = 0;
-                for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
-                    for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y)
-                        for (int x = max(cx - 1, 0); x <= min(cx + 1, g.dx - 1); ++x) {
-                            int key = cell_key(g, x, y, z);
-                            cur_s[nc] = g.cell_begin[key]; end_s[nc] = g.cell_begin[key + 1]; ++nc;
+    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < m; t += nwarps) {
+        float4 c = __ldg(pts + kp_idx[t]);
+        c.w = 1.0f;
+        if (refine) {
+            int it = 0;
+            double diff;
+            do {
+                float4 cur = c;
+                long long q[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                int cx = cell_coord(cur.x, g.mnx, g.inv_h), cy = cell_coord(cur.y, g.mny, g.inv_h), cz = cell_coord(cur.z, g.mnz, g.inv_h);
+                if (!(cx < -1 || cy < -1 || cz < -1 || cx > g.dx || cy > g.dy || cz > g.dz)) {
+                    cx = clampi(cx, 0, g.dx - 1); cy = clampi(cy, 0, g.dy - 1); cz = clampi(cz, 0, g.dz - 1);
+                    int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
+                    for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
+                        for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y) {
+                            int s0 = __ldg(g.cell_begin + cell_key(g, x0, y, z));
+                            int s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
+                            for (int s = s0 + lane; s < s1; s += 32) {
+                                float4 p = __ldg(g.sorted + s);
+                                if (dist2f(cur.x, cur.y, cur.z, p.x, p.y, p.z) < r2) {
+                                    float4 nj = __ldg(sn + s);
+                                    if (finite3(nj)) {
+                                        double x = nj.x, y2 = nj.y, z2 = nj.z;
+                                        double xx = x * x, xy = x * y2, xz = x * z2, yy = y2 * y2, yz = y2 * z2, zz = z2 * z2;
+                                        double px = p.x, py = p.y, pz = p.z;
+                                        q[0] += __double2ll_rn(xx * REFINE_SCALE_A); q[1] += __double2ll_rn(xy * REFINE_SCALE_A);
+                                        q[2] += __double2ll_rn(xz * REFINE_SCALE_A); q[3] += __double2ll_rn(yy * REFINE_SCALE_A);
+                                        q[4] += __double2ll_rn(yz * REFINE_SCALE_A); q[5] += __double2ll_rn(zz * REFINE_SCALE_A);
+                                        q[6] += __double2ll_rn(((xx * px + xy * py) + xz * pz) * REFINE_SCALE_B);
+                                        q[7] += __double2ll_rn(((xy * px + yy * py) + yz * pz) * REFINE_SCALE_B);
+                                        q[8] += __double2ll_rn(((xz * px + yz * py) + zz * pz) * REFINE_SCALE_B);
+                                    }
+                                }
+                            }
                         }
-                // advance every cursor to its first in-radius element
-                for (int k = 0; k < nc; ++k) {
-                    while (cur_s[k] < end_s[k]) {
-                        float4 p = g.sorted[cur_s[k]];
-                        if (dist2f(cur.x, cur.y, cur.z, p.x, p.y, p.z) < r2) break;
-                        ++cur_s[k];
-                    }
                 }
-                for (;;) {
-                    int bk = -1, bid = 0x7fffffff;
-                    for (int k = 0; k < nc; ++k)
-                        if (cur_s[k] < end_s[k]) {
-                            int id = __float_as_int(g.sorted[cur_s[k]].w);
-                            if (id < bid) { bid = id; bk = k; }
-                        }
-                    if (bk < 0) break;
-                    int sp = cur_s[bk];
-                    float4 p = g.sorted[sp];
-                    float4 nj = sn[sp];
-                    if (finite3(nj)) {
-                        double x = nj.x, y = nj.y, z = nj.z;
-                        double xx = x * x, xy = x * y, xz = x * z, yy = y * y, yz = y * z, zz = z * z;
-                        A0 += xx; A1 += xy; A2 += xz; A3 += yy; A4 += yz; A5 += zz;
-                        double px = p.x, py = p.y, pz = p.z;
-                        b0 += (xx * px + xy * py) + xz * pz;
-                        b1 += (xy * px + yy * py) + yz * pz;
-                        b2 += (xz * px + yz * py) + zz * pz;
-                    }
-                    ++cur_s[bk];
-                    while (cur_s[bk] < end_s[bk]) {
-                        float4 p2 = g.sorted[cur_s[bk]];
-                        if (dist2f(cur.x, cur.y, cur.z, p2.x, p2.y, p2.z) < r2) break;
-                        ++cur_s[bk];
-                    }
+#pragma unroll
+                for (int k = 0; k < 9; ++k) q[k] = warp_sum_ll(q[k]);
+                double A0 = (double)q[0] / REFINE_SCALE_A, A1 = (double)q[1] / REFINE_SCALE_A, A2 = (double)q[2] / REFINE_SCALE_A;
+                double A3 = (double)q[3] / REFINE_SCALE_A, A4 = (double)q[4] / REFINE_SCALE_A, A5 = (double)q[5] / REFINE_SCALE_A;
+                double b0 = (double)q[6] / REFINE_SCALE_B, b1 = (double)q[7] / REFINE_SCALE_B, b2 = (double)q[8] / REFINE_SCALE_B;
+                double c00 = A3 * A5 - A4 * A4, c01 = A2 * A4 - A1 * A5, c02 = A1 * A4 - A2 * A3;
+                double c11 = A0 * A5 - A2 * A2, c12 = A1 * A2 - A0 * A4, c22 = A0 * A3 - A1 * A1;
+                double det = (A0 * c00 + A1 * c01) + A2 * c02;
+                if (det != 0) {
+                    c.x = (float)(((c00 * b0 + c01 * b1) + c02 * b2) / det);
+                    c.y = (float)(((c01 * b0 + c11 * b1) + c12 * b2) / det);
+                    c.z = (float)(((c02 * b0 + c12 * b1) + c22 * b2) / det);
                 }
-            }
-            double c00 = A3 * A5 - A4 * A4, c01 = A2 * A4 - A1 * A5, c02 = A1 * A4 - A2 * A3;
-            double c11 = A0 * A5 - A2 * A2, c12 = A1 * A2 - A0 * A4, c22 = A0 * A3 - A1 * A1;
-            double det = (A0 * c00 + A1 * c01) + A2 * c02;
-            if (det != 0) {
-                c.x = (float)(((c00 * b0 + c01 * b1) + c02 * b2) / det);
-                c.y = (float)(((c01 * b0 + c11 * b1) + c12 * b2) / det);
-                c.z = (float)(((c02 * b0 + c12 * b1) + c22 * b2) / det);
-            }
-            double ddx = (double)c.x - (double)cur.x, ddy = (double)c.y - (double)cur.y, ddz = (double)c.z - (double)cur.z;
-            diff = (ddx * ddx + ddy * ddy) + ddz * ddz;
-        } while (diff > 1e-6 && ++it < 10);
+                double ddx = (double)c.x - (double)cur.x, ddy = (double)c.y - (double)cur.y, ddz = (double)c.z - (double)cur.z;
+                diff = (ddx * ddx + ddy * ddy) + ddz * ddz;
+            } while (diff > 1e-6 && ++it < 10);
+        }
+        if (lane == 0) kp_xyz[t] = c;
     }
-    kp_xyz[t] = c;
 }
 
 // ----------------------------------------------------------------------------- FPFH (App. A.4)
@@ -208,41 +206,59 @@ __device__ __forceinline__ bool pair_bins(float4 p1, float4 n1f, float4 p2, floa
     return true;
 }
 
-#define SPFH_THREADS 128
-__global__ void __launch_bounds__(SPFH_THREADS) k_spfh(GridView g, const float4* __restrict__ sn, float r2,
-                                                       float* __restrict__ spfh_sorted) {
-    __shared__ int cnt[33 * SPFH_THREADS];   // bin-major: conflict-free
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-#pragma unroll
-    for (int k = 0; k < 33; ++k) cnt[k * SPFH_THREADS + threadIdx.x] = 0;
-    if (s >= g.n) return;
-    float4 q = __ldg(g.sorted + s);
-    float4 nq = __ldg(sn + s);
-    int qi = __float_as_int(q.w);
-    bool qfin = finite3(nq);
-    int nb = 0;
-    for_block27(g, q.x, q.y, q.z, [&](int sp, float4 p, float d2) {
-        if (d2 < r2) {
-            ++nb;
-            if (qfin && __float_as_int(p.w) != qi) {
-                float4 nj = __ldg(sn + sp);
-                int b0, b1, b2;
-                if (finite3(nj) && pair_bins(q, nq, p, nj, b0, b1, b2)) {
-                    cnt[b0 * SPFH_THREADS + threadIdx.x]++;
-                    cnt[(11 + b1) * SPFH_THREADS + threadIdx.x]++;
-                    cnt[(22 + b2) * SPFH_THREADS + threadIdx.x]++;
+// computePointSPFHSignature: one warp per point, lanes stride over the 9 candidate ranges; the 3 x 11 bins are integer
+// counters in shared memory (integer atomics: order independent), scaled by 100 / (|N| - 1) at the end.
+#define SPFH_WARPS 8
+__global__ void __launch_bounds__(SPFH_WARPS * 32) k_spfh(GridView g, const float4* __restrict__ sn, float r2,
+                                                          float* __restrict__ spfh_sorted) {
+    __shared__ int cnt[SPFH_WARPS][36];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int nwarps = gridDim.x * SPFH_WARPS;
+    for (int s = blockIdx.x * SPFH_WARPS + warp; s < g.n; s += nwarps) {
+        cnt[warp][lane] = 0;
+        if (lane < 4) cnt[warp][32 + lane] = 0;
+        __syncwarp();
+        float4 q = __ldg(g.sorted + s);
+        float4 nq = __ldg(sn + s);
+        int qi = __float_as_int(q.w);
+        bool qfin = finite3(nq);
+        int nb = 0;
+        int cx = clampi(cell_coord(q.x, g.mnx, g.inv_h), 0, g.dx - 1);
+        int cy = clampi(cell_coord(q.y, g.mny, g.inv_h), 0, g.dy - 1);
+        int cz = clampi(cell_coord(q.z, g.mnz, g.inv_h), 0, g.dz - 1);
+        int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
+        for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
+            for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y) {
+                int s0 = __ldg(g.cell_begin + cell_key(g, x0, y, z));
+                int s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
+                for (int sp = s0 + lane; sp < s1; sp += 32) {
+                    float4 p = __ldg(g.sorted + sp);
+                    if (dist2f(q.x, q.y, q.z, p.x, p.y, p.z) < r2) {
+                        ++nb;
+                        if (qfin && __float_as_int(p.w) != qi) {
+                            float4 nj = __ldg(sn + sp);
+                            int b0, b1, b2;
+                            if (finite3(nj) && pair_bins(q, nq, p, nj, b0, b1, b2)) {
+                                atomicAdd(&cnt[warp][b0], 1);
+                                atomicAdd(&cnt[warp][11 + b1], 1);
+                                atomicAdd(&cnt[warp][22 + b2], 1);
+                            }
+                        }
+                    }
                 }
             }
+        nb = warp_sum(nb);
+        __syncwarp();
+        float* o = spfh_sorted + (size_t)s * 33;
+        if (nb < 2 || !qfin) {
+            o[lane] = 0.f;
+            if (lane == 0) o[32] = 0.f;
+        } else {
+            double incr = 100.0 / (double)(nb - 1);
+            o[lane] = (float)((double)cnt[warp][lane] * incr);
+            if (lane == 0) o[32] = (float)((double)cnt[warp][32] * incr);
         }
-    });
-    float* o = spfh_sorted + (size_t)s * 33;
-    if (nb < 2 || !qfin) {
-#pragma unroll
-        for (int k = 0; k < 33; ++k) o[k] = 0.f;
-    } else {
-        double incr = 100.0 / (double)(nb - 1);
-#pragma unroll
-        for (int k = 0; k < 33; ++k) o[k] = (float)((double)cnt[k * SPFH_THREADS + threadIdx.x] * incr);
+        __syncwarp();
     }
 }
 
@@ -408,8 +424,8 @@ int rtr_harris_dev(rtr_cloud* c, float radius, float threshold, int nms, int ref
         RTR_CHECK(cub::DeviceSelect::Flagged(temp, tb, iota, flags, *d_kp_idx, *d_count, n, ctx->stream), "harris.select");
         RTR_MARK(ctx, "harris.cub_select");
         dev_free(ctx, temp);
-        // the corner count lives on the device; launch for the worst case (every point a corner), threads beyond exit
-        k_harris_refine<<<nblk(n, 64), 64, 0, ctx->stream>>>(v, g->sorted_normals, c->pts, r2, *d_kp_idx, *d_count, n, *d_kp_xyz, refine);
+        // the corner count lives on the device: persistent grid of warps striding over the corner list
+        k_harris_refine<<<std::min(nblk((long long)n * 32, 128), ctx->sm_count * 8), 128, 0, ctx->stream>>>(v, g->sorted_normals, c->pts, r2, *d_kp_idx, *d_count, n, *d_kp_xyz, refine);
         RTR_LAUNCH_CHECK(ctx, "harris.refine");
     }
     dev_free(ctx, resp_sorted); dev_free(ctx, flags);
@@ -430,7 +446,7 @@ int rtr_fpfh_dev(rtr_cloud* c, float radius) {
     if (int e = dev_alloc(ctx, &spfh, (size_t)n * 33, "fpfh")) return e;
     if (n > 0) {
         GridView v = rtr_view(g);
-        k_spfh<<<nblk(n, SPFH_THREADS), SPFH_THREADS, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh);
+        k_spfh<<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * 16), SPFH_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh);
         RTR_LAUNCH_CHECK(ctx, "fpfh.spfh");
         k_fpfh_weight<<<nblk(n, FPFH_WARPS), FPFH_WARPS * 32, 0, ctx->stream>>>(v, spfh, r2, c->fpfh);
         RTR_LAUNCH_CHECK(ctx, "fpfh.weight");

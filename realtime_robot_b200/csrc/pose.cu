@@ -13,6 +13,8 @@
 //   ICP:    per iteration one correspondence kernel (apply previous step, exact 1-NN, 17 fp64 sums per thread ->
 //           warp-shuffle tree -> per-CTA partials) and one solve kernel (fixed-shape reduction, Horn, convergence).
 #include "common.cuh"
+#include <cub/cub.cuh>
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -245,6 +247,7 @@ struct IcpState {
     int state;
     int corr;
     int have_step;
+    int skipped;      // registration only: RANSAC accepted nothing, so there is no pose to refine
 };
 
 #define ICP_THREADS 256
@@ -263,10 +266,34 @@ __global__ void k_icp_init(const float4* __restrict__ src, int n, const float* _
     if (blockIdx.x == 0 && threadIdx.x < 16) {
         st->final_[threadIdx.x] = m[threadIdx.x];
         st->step[threadIdx.x] = (threadIdx.x % 5 == 0) ? 1.f : 0.f;
-        if (threadIdx.x == 0) { st->prev_mse = DBL_MAX; st->iterations = 0; st->done = 0; st->state = 0; st->corr = 0; st->have_step = 0; }
+        if (threadIdx.x == 0) {
+            int skip = (init_res && init_res->converged == 0) ? 1 : 0;
+            st->prev_mse = DBL_MAX; st->iterations = 0; st->done = skip; st->state = 0; st->corr = 0; st->have_step = 0; st->skipped = skip;
+        }
     }
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) cur[i] = xform(m, __ldg(src + i));
+}
+
+// Large sources are processed in the TARGET grid's cell order: neighbouring threads then walk the same cell ranges
+// (coalesced, L1-resident) instead of 32 unrelated ones.  The sums are order independent up to fp64 rounding.
+__global__ void k_icp_cell_keys(GridView g, const float4* __restrict__ cur, int n, int* __restrict__ keys, int* __restrict__ vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = cur[i];
+    int cx = clampi(cell_coord(p.x, g.mnx, g.inv_h), 0, g.dx - 1);
+    int cy = clampi(cell_coord(p.y, g.mny, g.inv_h), 0, g.dy - 1);
+    int cz = clampi(cell_coord(p.z, g.mnz, g.inv_h), 0, g.dz - 1);
+    keys[i] = cell_key(g, cx, cy, cz);
+    vals[i] = i;
+}
+__global__ void k_icp_permute(const float4* __restrict__ cur, const float4* __restrict__ src, const int* __restrict__ perm, int n,
+                              float4* __restrict__ cur_out, float4* __restrict__ src_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int j = perm[i];
+    cur_out[i] = cur[j];
+    src_out[i] = __ldg(src + j);
 }
 
 // correspondence estimation + accumulation.  Applies the previous iteration's step first (transformCloud in place).
@@ -353,6 +380,7 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_fitness(GridView g, const f
                                                              double* __restrict__ partials) {
     __shared__ float m[16];
     __shared__ double red[ICP_THREADS / 32][2];
+    if (st->skipped) return;
     if (threadIdx.x < 16) m[threadIdx.x] = st->final_[threadIdx.x];
     __syncthreads();
     double s = 0, c = 0;
@@ -385,6 +413,7 @@ __global__ void __launch_bounds__(64) k_icp_finish(const double* __restrict__ pa
     if (lane == 0) sums[warp] = v;
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (st->skipped) { res->iterations = 0; res->converged = 0; return; }     // pose / fitness stay RANSAC's (identity, FLT_MAX)
         for (int i = 0; i < 16; ++i) res->pose[i] = st->final_[i];
         res->fitness = sums[1] > 0 ? (float)(sums[0] / sums[1]) : FLT_MAX;
         res->iterations = st->iterations;
@@ -413,6 +442,31 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     if (int e = dev_alloc(ctx, &partials, (size_t)nb * ICP_NSUM, "icp")) return e;
     k_icp_init<<<nb, ICP_THREADS, 0, ctx->stream>>>(src->pts, n, d_init_pose16, init_from_result ? d_result : nullptr, cur, st);
     RTR_LAUNCH_CHECK(ctx, "icp.init");
+    const float4* src_pts = src->pts;
+    float4 *cur2 = nullptr, *src2 = nullptr;
+    if (n >= 16384 && tgt->n >= 1) {
+        int *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr; char* temp = nullptr;
+        if (int e = dev_alloc(ctx, &keys, n, "icp")) return e;
+        if (int e = dev_alloc(ctx, &vals, n, "icp")) return e;
+        if (int e = dev_alloc(ctx, &keys2, n, "icp")) return e;
+        if (int e = dev_alloc(ctx, &vals2, n, "icp")) return e;
+        if (int e = dev_alloc(ctx, &cur2, n, "icp")) return e;
+        if (int e = dev_alloc(ctx, &src2, n, "icp")) return e;
+        k_icp_cell_keys<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, cur, n, keys, vals);
+        RTR_LAUNCH_CHECK(ctx, "icp.keys");
+        int end_bit = 1;
+        while ((1LL << end_bit) < (long long)g->ncells) ++end_bit;
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys2, vals, vals2, n, 0, end_bit, ctx->stream);
+        if (int e = dev_alloc(ctx, &temp, tb, "icp")) return e;
+        RTR_CHECK(cub::DeviceRadixSort::SortPairs(temp, tb, keys, keys2, vals, vals2, n, 0, end_bit, ctx->stream), "icp.sort");
+        RTR_MARK(ctx, "icp.cub_sort");
+        k_icp_permute<<<nb, ICP_THREADS, 0, ctx->stream>>>(cur, src->pts, vals2, n, cur2, src2);
+        RTR_LAUNCH_CHECK(ctx, "icp.permute");
+        dev_free(ctx, keys); dev_free(ctx, vals); dev_free(ctx, keys2); dev_free(ctx, vals2); dev_free(ctx, temp);
+        dev_free(ctx, cur);
+        cur = cur2; src_pts = src2;
+    }
     double dmax2 = p->max_correspondence_distance > 0.f ? (double)p->max_correspondence_distance * (double)p->max_correspondence_distance : DBL_MAX;
     // search radius for pruning: the cap rounded UP in float so no candidate with d2 <= dmax2 is ever skipped
     float prune2 = FLT_MAX;
@@ -425,11 +479,11 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
             RTR_LAUNCH_CHECK(ctx, "icp.solve");
         }
     }
-    k_icp_fitness<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, src->pts, n, st, partials);
+    k_icp_fitness<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, src_pts, n, st, partials);
     RTR_LAUNCH_CHECK(ctx, "icp.fitness");
     k_icp_finish<<<1, 64, 0, ctx->stream>>>(partials, nb, st, d_result, init_from_result);
     RTR_LAUNCH_CHECK(ctx, "icp.finish");
-    dev_free(ctx, cur); dev_free(ctx, st); dev_free(ctx, partials);
+    dev_free(ctx, cur); dev_free(ctx, src2); dev_free(ctx, st); dev_free(ctx, partials);
     return 0;
 }
 

@@ -1,0 +1,54 @@
+// realtime_robot.cpp — Linux driver with the shape of the reference's main() (RealTimeRobot.cpp:27-121): load a model
+// and a scan, extract keypoints of both, register the model to the scan, transform, save ASCII PCDs, print the running
+// time.  MSVC-isms, hard-coded file names, the pcl_viewer hand-off and the trailing infinite loop (RealTimeRobot.cpp:114-120)
+// are gone; everything numerical runs in librtr.so on the GPU.
+//
+//   realtime_robot <model.pcd> <scan.pcd> [--scale-model S] [--out transformed_model.pcd] [--hypotheses N] [--icp-only]
+#include <chrono>
+#include <cstdlib>
+#include <iostream>
+#include <string>
+#include "registration.h"
+
+int main(int argc, char** argv) {
+    if (argc < 3) { fprintf(stderr, "usage: %s <model.pcd> <scan.pcd> [--scale-model S] [--out file.pcd] [--hypotheses N] [--icp-only]\n", argv[0]); return 2; }
+    std::string out;
+    float scale = 1.0f; long long hyp = 0; bool icp_only = false;
+    for (int i = 3; i < argc; ++i) {
+        std::string a = argv[i];
+        if (a == "--scale-model" && i + 1 < argc) scale = strtof(argv[++i], nullptr);
+        else if (a == "--out" && i + 1 < argc) out = argv[++i];
+        else if (a == "--hypotheses" && i + 1 < argc) hyp = atoll(argv[++i]);
+        else if (a == "--icp-only") icp_only = true;
+    }
+    pcl::PointCloud<pcl::PointXYZ>::Ptr cloud(new pcl::PointCloud<pcl::PointXYZ>), mcloud(new pcl::PointCloud<pcl::PointXYZ>);
+    if (pcl::io::loadPCDFile(argv[1], *mcloud) != 0 || pcl::io::loadPCDFile(argv[2], *cloud) != 0) return 1;
+    if (scale != 1.0f) {                                    // what model_point.h:106-111 intends for Chair_025.pcd (units x100)
+        Eigen::Matrix4f t = Eigen::Matrix4f::Identity();
+        t(0, 0) = t(1, 1) = t(2, 2) = scale;
+        pcl::transformPointCloud(*mcloud, *mcloud, t);
+    }
+    ModelPoint modelpoint(mcloud);
+    modelpoint.getKeypoint();
+    auto start = std::chrono::steady_clock::now();          // RealTimeRobot.cpp:43
+    ScanPoint scanpoint(cloud);
+    scanpoint.getKeypoint();
+    Eigen::Matrix4f matrix = Eigen::Matrix4f::Identity();
+    pcl::PointCloud<pcl::PointXYZ> moved;
+    if (icp_only) {
+        keyPointICP(nullptr, nullptr, cloud, mcloud, &matrix, &moved);
+    } else {
+        rtr_register_params p;
+        rtr_default_register_params(&p);
+        if (hyp > 0) p.ransac.max_iterations = hyp;
+        rtr_pose_result r = rtr_pose_result();
+        bool ok = registerModelToScene(*mcloud, *cloud, p, matrix, &r);
+        std::cout << "converged " << ok << "  hypothesis " << r.hypothesis << "  inliers " << r.inliers << " / " << mcloud->size()
+                  << "  prerejection survivors " << r.evaluated << "  fitness (mean squared NN distance) " << r.fitness << "\n" << matrix;
+        pcl::transformPointCloud(*mcloud, moved, matrix);
+    }
+    if (!out.empty()) pcl::io::savePCDFileASCII(out, moved);   // RealTimeRobot.cpp:108-109
+    auto ends = std::chrono::steady_clock::now();
+    std::cout << "Running Time : " << std::chrono::duration<double>(ends - start).count() << std::endl;   // RealTimeRobot.cpp:111
+    return 0;
+}
