@@ -262,44 +262,67 @@ __global__ void __launch_bounds__(SPFH_WARPS * 32) k_spfh(GridView g, const floa
     }
 }
 
-// weightPointSPFHSignature: one warp per point, lane = histogram bin (lane 0 also carries bin 32)
-#define FPFH_WARPS 4
+// weightPointSPFHSignature: one warp per point.  Two roles per 32-candidate batch: first lane = candidate (distance
+// test and the fp64 weight 1/d2, computed once per pair instead of once per lane), then lane = histogram bin (lane 0 also
+// carries bin 32) accumulating SPFH_j[bin] * w_j over the batch's in-radius candidates in ascending position order.
+#define FPFH_WARPS 8
 __global__ void __launch_bounds__(FPFH_WARPS * 32) k_fpfh_weight(GridView g, const float* __restrict__ spfh_sorted, float r2,
                                                                  float* __restrict__ fpfh) {
     __shared__ double hs[FPFH_WARPS][36];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int s = blockIdx.x * FPFH_WARPS + warp;
-    if (s >= g.n) return;
-    float4 q = __ldg(g.sorted + s);
-    double acc = 0, acc32 = 0;
-    int nb = 0;
-    for_block27(g, q.x, q.y, q.z, [&](int sp, float4, float d2) {
-        if (d2 < r2) {
-            ++nb;
-            if (d2 != 0.f) {
-                double w = 1.0 / (double)d2;
-                const float* sj = spfh_sorted + (size_t)sp * 33;
-                acc += (double)__ldg(sj + lane) * w;
-                if (lane == 0) acc32 += (double)__ldg(sj + 32) * w;
+    int nwarps = gridDim.x * FPFH_WARPS;
+    for (int s = blockIdx.x * FPFH_WARPS + warp; s < g.n; s += nwarps) {
+        float4 q = __ldg(g.sorted + s);
+        double acc = 0, acc32 = 0;
+        int nb = 0;
+        int cx = clampi(cell_coord(q.x, g.mnx, g.inv_h), 0, g.dx - 1);
+        int cy = clampi(cell_coord(q.y, g.mny, g.inv_h), 0, g.dy - 1);
+        int cz = clampi(cell_coord(q.z, g.mnz, g.inv_h), 0, g.dz - 1);
+        int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
+        for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
+            for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y) {
+                int s0 = __ldg(g.cell_begin + cell_key(g, x0, y, z));
+                int s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
+                for (int base = s0; base < s1; base += 32) {
+                    int sp = base + lane;
+                    double w = 0.0;
+                    bool in = false;
+                    if (sp < s1) {
+                        float4 p = __ldg(g.sorted + sp);
+                        float d2 = dist2f(q.x, q.y, q.z, p.x, p.y, p.z);
+                        in = d2 < r2;
+                        if (in && d2 != 0.f) w = 1.0 / (double)d2;      // "minus the query point itself": dists == 0 skipped
+                    }
+                    nb += __popc(__ballot_sync(0xffffffffu, in));
+                    unsigned mask = __ballot_sync(0xffffffffu, w != 0.0);
+                    while (mask) {
+                        int j = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        double wj = __shfl_sync(0xffffffffu, w, j);
+                        const float* sj = spfh_sorted + (size_t)(base + j) * 33;
+                        acc += (double)__ldg(sj + lane) * wj;
+                        if (lane == 0) acc32 += (double)__ldg(sj + 32) * wj;
+                    }
+                }
             }
+        hs[warp][lane] = acc;
+        if (lane == 0) hs[warp][32] = acc32;
+        __syncwarp();
+        if (lane < 3) {
+            double sum = 0;
+            for (int k = 0; k < 11; ++k) sum += hs[warp][lane * 11 + k];
+            hs[warp][33 + lane] = (sum != 0) ? 100.0 / sum : 0.0;
         }
-    });
-    hs[warp][lane] = acc;
-    if (lane == 0) hs[warp][32] = acc32;
-    __syncwarp();
-    if (lane < 3) {
-        double sum = 0;
-        for (int k = 0; k < 11; ++k) sum += hs[warp][lane * 11 + k];
-        hs[warp][33 + lane] = (sum != 0) ? 100.0 / sum : 0.0;
-    }
-    __syncwarp();
-    float* o = fpfh + (size_t)__float_as_int(q.w) * 33;
-    if (nb == 0) {
-        o[lane] = __int_as_float(0x7fc00000);
-        if (lane == 0) o[32] = __int_as_float(0x7fc00000);
-    } else {
-        o[lane] = (float)(hs[warp][lane] * hs[warp][33 + lane / 11]);
-        if (lane == 0) o[32] = (float)(hs[warp][32] * hs[warp][35]);
+        __syncwarp();
+        float* o = fpfh + (size_t)__float_as_int(q.w) * 33;
+        if (nb == 0) {
+            o[lane] = __int_as_float(0x7fc00000);
+            if (lane == 0) o[32] = __int_as_float(0x7fc00000);
+        } else {
+            o[lane] = (float)(hs[warp][lane] * hs[warp][33 + lane / 11]);
+            if (lane == 0) o[32] = (float)(hs[warp][32] * hs[warp][35]);
+        }
+        __syncwarp();
     }
 }
 
@@ -448,7 +471,7 @@ int rtr_fpfh_dev(rtr_cloud* c, float radius) {
         GridView v = rtr_view(g);
         k_spfh<<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * 16), SPFH_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh);
         RTR_LAUNCH_CHECK(ctx, "fpfh.spfh");
-        k_fpfh_weight<<<nblk(n, FPFH_WARPS), FPFH_WARPS * 32, 0, ctx->stream>>>(v, spfh, r2, c->fpfh);
+        k_fpfh_weight<<<std::min(nblk(n, FPFH_WARPS), ctx->sm_count * 16), FPFH_WARPS * 32, 0, ctx->stream>>>(v, spfh, r2, c->fpfh);
         RTR_LAUNCH_CHECK(ctx, "fpfh.weight");
     }
     dev_free(ctx, spfh);
