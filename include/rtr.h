@@ -161,6 +161,11 @@ int rtr_fpfh(rtr_cloud* c, float radius, float* host_fpfh);
  * (App. A.5).  Both clouds need rtr_fpfh.  Result cached on `source`; host outputs optional (ns x k). */
 int rtr_match_features(rtr_cloud* source, rtr_cloud* target, int k, int* host_idx, float* host_dist);
 
+/* Same search on two bare feature arrays (host, ns x 33 and nt x 33 floats): the descriptor-correspondence stage on its
+ * own, for descriptors computed elsewhere.  *kernel_ms (optional) receives the device time of the search itself. */
+int rtr_match_features_raw(rtr_context* ctx, const float* host_source_feat, int ns, const float* host_target_feat, int nt,
+                           int k, int* host_idx, float* host_dist, float* kernel_ms);
+
 /* ------------------------------------------------------------------ pose stages */
 
 /* SampleConsensusPrerejective::computeTransformation over hypotheses [begin,end) (App. A.5).

@@ -203,3 +203,17 @@ def tdf_batch(ctx: Context, occ_lists, dim: int = 30) -> np.ndarray:
     out = np.zeros((len(occ_lists), dim ** 3), dtype=np.float32)
     _lib.check("rtr_tdf_batch", _lib.lib().rtr_tdf_batch(ctx._h, _ptr(occ) if occ.size else None, _ptr(offs), len(occ_lists), dim, _ptr(out)))
     return out
+
+
+def match_raw(ctx: Context, fa, fb, k: int, reps: int = 1):
+    """Feature k-NN on two bare (n, 33) feature arrays (bench helper): uploads them as the FPFH of two placeholder
+    clouds is not possible through the cloud API, so this goes through rtr_match_features_raw.  Returns (best ms, stats)."""
+    fa, fb = _f32(fa, 33), _f32(fb, 33)
+    idx = np.zeros((len(fa), k), dtype=np.int32)
+    dist = np.zeros((len(fa), k), dtype=np.float32)
+    ms = C.c_float()
+    best = None
+    for _ in range(max(reps, 1)):
+        _lib.check("rtr_match_features_raw", _lib.lib().rtr_match_features_raw(ctx._h, _ptr(fa), len(fa), _ptr(fb), len(fb), k, _ptr(idx), _ptr(dist), C.byref(ms)))
+        best = ms.value if best is None else min(best, ms.value)
+    return best, {"idx0": idx[0].tolist(), "dist0": dist[0].tolist()}

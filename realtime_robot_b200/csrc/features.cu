@@ -542,6 +542,34 @@ int rtr_fpfh(rtr_cloud* c, float radius, float* host_fpfh) {
     return 0;
 }
 
+int rtr_match_features_raw(rtr_context* ctx, const float* host_source_feat, int ns, const float* host_target_feat, int nt,
+                           int k, int* host_idx, float* host_dist, float* kernel_ms) {
+    if (!ctx || ns < 0 || nt < 0 || k < 1 || k > MATCH_KMAX || (ns > 0 && (!host_source_feat || !host_idx)) || (nt > 0 && !host_target_feat))
+        return rtr_fail("match_raw", "bad argument", RTR_ERR_INVALID);
+    RTR_CHECK(cudaSetDevice(ctx->device), "match_raw");
+    float *fa = nullptr, *fb = nullptr, *dd = nullptr; int* di = nullptr;
+    if (int e = dev_alloc(ctx, &fa, (size_t)ns * 33, "match_raw")) return e;
+    if (int e = dev_alloc(ctx, &fb, (size_t)nt * 33, "match_raw")) return e;
+    if (int e = dev_alloc(ctx, &di, (size_t)ns * k, "match_raw")) return e;
+    if (int e = dev_alloc(ctx, &dd, (size_t)ns * k, "match_raw")) return e;
+    if (ns > 0) RTR_CHECK(cudaMemcpyAsync(fa, host_source_feat, (size_t)ns * 132, cudaMemcpyHostToDevice, ctx->stream), "match_raw");
+    if (nt > 0) RTR_CHECK(cudaMemcpyAsync(fb, host_target_feat, (size_t)nt * 132, cudaMemcpyHostToDevice, ctx->stream), "match_raw");
+    RTR_CHECK(cudaEventRecord(ctx->events[RTR_NUM_EVENTS - 2], ctx->stream), "match_raw");
+    if (ns > 0) {
+        k_match<<<nblk(ns, MATCH_WARPS), MATCH_WARPS * 32, 0, ctx->stream>>>(fa, ns, fb, nt, k, di, dd);
+        RTR_LAUNCH_CHECK(ctx, "match");
+    }
+    RTR_CHECK(cudaEventRecord(ctx->events[RTR_NUM_EVENTS - 1], ctx->stream), "match_raw");
+    if (ns > 0) {
+        RTR_CHECK(cudaMemcpyAsync(host_idx, di, (size_t)ns * k * 4, cudaMemcpyDeviceToHost, ctx->stream), "match_raw");
+        if (host_dist) RTR_CHECK(cudaMemcpyAsync(host_dist, dd, (size_t)ns * k * 4, cudaMemcpyDeviceToHost, ctx->stream), "match_raw");
+    }
+    RTR_CHECK(cudaStreamSynchronize(ctx->stream), "match_raw");
+    if (kernel_ms) RTR_CHECK(cudaEventElapsedTime(kernel_ms, ctx->events[RTR_NUM_EVENTS - 2], ctx->events[RTR_NUM_EVENTS - 1]), "match_raw");
+    dev_free(ctx, fa); dev_free(ctx, fb); dev_free(ctx, di); dev_free(ctx, dd);
+    return 0;
+}
+
 int rtr_match_features(rtr_cloud* source, rtr_cloud* target, int k, int* host_idx, float* host_dist) {
     if (!source || !target || source->ctx != target->ctx) return rtr_fail("match", "bad argument", RTR_ERR_INVALID);
     rtr_context* ctx = source->ctx;
