@@ -286,12 +286,20 @@ def main():
     # ---- per-kernel device time of one more step (profiling marks; not part of the timed region)
     # (run one registration at a time here so that the intervals of different streams do not overlap)
     prof = {}
+    per_model_ms = {}
     for i in range(len(MODELS)):
         ctxs[i].profile_begin()
         reg_resident(i)
-        for k, v in ctxs[i].profile_end().items():
+        pi = ctxs[i].profile_end()
+        per_model_ms[MODELS[i]] = round(sum(v[1] for v in pi.values()), 3)
+        for k, v in pi.items():
             a = prof.get(k, (0, 0.0))
             prof[k] = (a[0] + v[0], a[1] + v[1])
+    # one registration at a time, unprofiled: latency of a single registration as a caller sees it
+    lat = {}
+    for i in range(len(MODELS)):
+        reg_resident(i)
+        t0 = time.perf_counter(); reg_resident(i); lat[MODELS[i]] = round(1e3 * (time.perf_counter() - t0), 3)
     step_ms = sum(v[1] for v in prof.values())      # serialised device time of the step's operations
     top = sorted(prof.items(), key=lambda kv: -kv[1][1])
     kernel_share = {k: {"launches": v[0], "ms": round(v[1], 4), "share": round(v[1] / step_ms, 4)} for k, v in top[:8]}
@@ -392,6 +400,7 @@ def main():
                         "ms_per_step": ms_e2e / args.steps, "entry": "rtr_register_host (pinned host clouds)"},
                 "gpu_launches": int(launches),
                 "clocks": clocks, "roofline": roofline, "kernel_share": kernel_share, "serialised_device_ms_per_step": round(step_ms, 3),
+                "per_model_device_ms": per_model_ms, "per_model_latency_ms_alone": lat,
                 "cpu_baseline": cpu, "icp_1m": icp_out,
                 "wall_ms_per_step_incl_l2_flush": 1e3 * wall_res / args.steps,
                 "results": [{"model": m, "fitness": float(r.fitness), "inliers": int(r.inliers), "hypothesis": int(r.hypothesis),

@@ -166,6 +166,10 @@ int rtr_match_features(rtr_cloud* source, rtr_cloud* target, int k, int* host_id
 int rtr_match_features_raw(rtr_context* ctx, const float* host_source_feat, int ns, const float* host_target_feat, int nt,
                            int k, int* host_idx, float* host_dist, float* kernel_ms);
 
+/* stats3[0] = rows the tensor-core prefilter could not certify and the exact kernel redid (-1: the exact kernel did
+ * everything), [1] = target splits, [2] = largest observed prefilter error / (|a||b|) in units of 1e-9, for the last rtr_match_features_raw call on this context. */
+int rtr_match_last_stats(rtr_context* ctx, int* stats3);
+
 /* ------------------------------------------------------------------ pose stages */
 
 /* SampleConsensusPrerejective::computeTransformation over hypotheses [begin,end) (App. A.5).

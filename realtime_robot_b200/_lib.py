@@ -16,7 +16,7 @@ EXPORTS = [
     "rtr_default_register_params", "rtr_context_create", "rtr_context_destroy", "rtr_context_sync", "rtr_context_stream",
     "rtr_context_launches", "rtr_profile_begin", "rtr_profile_end", "rtr_cloud_reset", "rtr_event_record", "rtr_event_elapsed_ms", "rtr_cloud_upload", "rtr_cloud_from_device",
     "rtr_cloud_free", "rtr_cloud_size", "rtr_cloud_transform", "rtr_cloud_download", "rtr_radius_neighbors", "rtr_nearest",
-    "rtr_normals", "rtr_harris3d", "rtr_fpfh", "rtr_match_features", "rtr_match_features_raw", "rtr_ransac_prerejective", "rtr_icp", "rtr_register",
+    "rtr_normals", "rtr_harris3d", "rtr_fpfh", "rtr_match_features", "rtr_match_features_raw", "rtr_match_last_stats", "rtr_ransac_prerejective", "rtr_icp", "rtr_register",
     "rtr_register_host", "ComputeTDFWithCuda", "rtr_tdf_batch", "rtr_tdf_batch_dev",
 ]
 
@@ -60,6 +60,7 @@ def lib():
         L.rtr_fpfh.argtypes = [vp, C.c_float, vp]
         L.rtr_match_features.argtypes = [vp, vp, C.c_int, vp, vp]
         L.rtr_match_features_raw.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, fp]
+        L.rtr_match_last_stats.argtypes = [vp, ip]
         L.rtr_ransac_prerejective.argtypes = [vp, vp, C.POINTER(RansacParams), C.POINTER(PoseResult)]
         L.rtr_icp.argtypes = [vp, vp, C.POINTER(IcpParams), vp, C.POINTER(PoseResult)]
         L.rtr_register.argtypes = [vp, vp, C.POINTER(RegisterParams), C.POINTER(PoseResult)]

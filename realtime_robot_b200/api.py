@@ -216,4 +216,6 @@ def match_raw(ctx: Context, fa, fb, k: int, reps: int = 1):
     for _ in range(max(reps, 1)):
         _lib.check("rtr_match_features_raw", _lib.lib().rtr_match_features_raw(ctx._h, _ptr(fa), len(fa), _ptr(fb), len(fb), k, _ptr(idx), _ptr(dist), C.byref(ms)))
         best = ms.value if best is None else min(best, ms.value)
-    return best, {"idx0": idx[0].tolist(), "dist0": dist[0].tolist()}
+    st = (C.c_int * 3)()
+    _lib.lib().rtr_match_last_stats(ctx._h, st)
+    return best, {"idx": idx, "dist": dist, "redo_rows": int(st[0]), "splits": int(st[1]), "observed_err_over_norms": st[2] * 1e-9}

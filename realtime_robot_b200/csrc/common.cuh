@@ -14,6 +14,8 @@
 #include "../../include/rtr.h"
 
 #define RTR_NUM_EVENTS 16
+// clouds up to this size use one WARP per point in the gather kernels (one thread per point cannot fill 148 SMs)
+#define RTR_WARP_PER_POINT_MAX 262144
 
 // ----------------------------------------------------------------------------- host-side objects
 struct DevGrid {
@@ -48,6 +50,7 @@ struct rtr_context {
     std::vector<ProfMark> marks;
     std::vector<cudaEvent_t> event_pool;
     int sm_count = 148;
+    int match_stats[3] = {-1, 0, 0};
     cudaEvent_t events[RTR_NUM_EVENTS] = {};
     // small pinned staging area for results / counters
     void* pinned = nullptr;
@@ -262,6 +265,79 @@ __device__ __forceinline__ void grid_nearest_ex(const GridView& g, float qx, flo
                         float d = dist2f(qx, qy, qz, p.x, p.y, p.z);
                         int id = __float_as_int(p.w);
                         if (d < best_d2 || (d == best_d2 && id < best)) { best_d2 = d; best = id; bp = p; }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Warp-cooperative form of grid_nearest_ex for small query sets (one warp per query): the lanes stride over the points
+// of every visited range and the (d2, index) minimum is folded with shuffles.  Same visiting rules, same result.
+__device__ __forceinline__ void warp_argmin(float& d, int& id, float4& p) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float od = __shfl_xor_sync(0xffffffffu, d, o);
+        int oi = __shfl_xor_sync(0xffffffffu, id, o);
+        float ox = __shfl_xor_sync(0xffffffffu, p.x, o), oy = __shfl_xor_sync(0xffffffffu, p.y, o), oz = __shfl_xor_sync(0xffffffffu, p.z, o);
+        bool take = (oi >= 0) && (id < 0 || od < d || (od == d && oi < id));
+        if (take) { d = od; id = oi; p.x = ox; p.y = oy; p.z = oz; }
+    }
+}
+__device__ __forceinline__ void grid_nearest_warp(const GridView& g, float qx, float qy, float qz, float prune2, int lane, int& best,
+                                                  float& best_d2, float4& bp) {
+    best = -1; best_d2 = FLT_MAX; bp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g.n == 0) return;
+    int cx = clampi(cell_coord(qx, g.mnx, g.inv_h), 0, g.dx - 1);
+    int cy = clampi(cell_coord(qy, g.mny, g.inv_h), 0, g.dy - 1);
+    int cz = clampi(cell_coord(qz, g.mnz, g.inv_h), 0, g.dz - 1);
+    {
+        int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
+        for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
+            for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y) {
+                int s0 = __ldg(g.cell_begin + cell_key(g, x0, y, z));
+                int s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
+                for (int s = s0 + lane; s < s1; s += 32) {
+                    float4 p = __ldg(g.sorted + s);
+                    float d = dist2f(qx, qy, qz, p.x, p.y, p.z);
+                    int id = __float_as_int(p.w);
+                    if (best < 0 || d < best_d2 || (d == best_d2 && id < best)) { best_d2 = d; best = id; bp = p; }
+                }
+            }
+    }
+    warp_argmin(best_d2, best, bp);
+    float hh = g.h * 0.999f;
+    if (best >= 0 && best_d2 <= hh * hh) return;
+    float ext = g.h * (float)max(g.dx, max(g.dy, g.dz));
+    float slack = g.h * 1e-3f + 2e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + fabsf(g.mnx) + fabsf(g.mny) + fabsf(g.mnz) + ext);
+    for (int zdir = 0; zdir < 2; ++zdir) {
+        for (int z = zdir == 0 ? cz : cz - 1; z >= 0 && z < g.dz; z += (zdir == 0 ? 1 : -1)) {
+            float lo = g.mnz + (float)z * g.h, hi = lo + g.h;
+            float dzl = qz < lo ? lo - qz : (qz > hi ? qz - hi : 0.f);
+            dzl = fmaxf(dzl - slack, 0.f);
+            float bound = fminf(best >= 0 ? best_d2 : FLT_MAX, prune2);      // best is warp-uniform here
+            if (dzl * dzl > bound) break;
+            for (int ydir = 0; ydir < 2; ++ydir) {
+                for (int y = ydir == 0 ? cy : cy - 1; y >= 0 && y < g.dy; y += (ydir == 0 ? 1 : -1)) {
+                    float lo2 = g.mny + (float)y * g.h, hi2 = lo2 + g.h;
+                    float dyl = qy < lo2 ? lo2 - qy : (qy > hi2 ? qy - hi2 : 0.f);
+                    dyl = fmaxf(dyl - slack, 0.f);
+                    bound = fminf(best >= 0 ? best_d2 : FLT_MAX, prune2);
+                    float rem = bound - (dzl * dzl + dyl * dyl);
+                    if (rem < 0.f) break;
+                    float rx = sqrtf(rem) * 1.000001f + slack;
+                    int xa = clampi(cell_coord(qx - rx, g.mnx, g.inv_h), 0, g.dx - 1);
+                    int xb = clampi(cell_coord(qx + rx, g.mnx, g.inv_h), 0, g.dx - 1);
+                    int s0 = __ldg(g.cell_begin + cell_key(g, xa, y, z));
+                    int s1 = __ldg(g.cell_begin + cell_key(g, xb, y, z) + 1);
+                    if (s1 > s0) {
+                        for (int s = s0 + lane; s < s1; s += 32) {
+                            float4 p = __ldg(g.sorted + s);
+                            float d = dist2f(qx, qy, qz, p.x, p.y, p.z);
+                            int id = __float_as_int(p.w);
+                            if (best < 0 || d < best_d2 || (d == best_d2 && id < best)) { best_d2 = d; best = id; bp = p; }
+                        }
+                        warp_argmin(best_d2, best, bp);     // keep the pruning bound uniform across the warp
                     }
                 }
             }

@@ -15,6 +15,33 @@
 static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
 
 // ----------------------------------------------------------------------------- normals (App. A.2)
+// covariance of the offsets from the query (fp64) -> smallest eigenvector (Jacobi) -> flip towards the viewpoint (0,0,0)
+__device__ __forceinline__ float4 normal_from_sums(float4 q, int cnt, double sx, double sy, double sz, double cxx, double cxy,
+                                                   double cxz, double cyy, double cyz, double czz) {
+    float4 o;
+    if (cnt < 3) {
+        o.x = o.y = o.z = o.w = __int_as_float(0x7fc00000);
+        return o;
+    }
+    double k = (double)cnt;
+    double mx = sx / k, my = sy / k, mz = sz / k;
+    double a[3][3], v[3][3];
+    a[0][0] = cxx / k - mx * mx; a[0][1] = cxy / k - mx * my; a[0][2] = cxz / k - mx * mz;
+    a[1][1] = cyy / k - my * my; a[1][2] = cyz / k - my * mz; a[2][2] = czz / k - mz * mz;
+    a[1][0] = a[0][1]; a[2][0] = a[0][2]; a[2][1] = a[1][2];
+    double trace = a[0][0] + a[1][1] + a[2][2];
+    jacobi_eig<3>(a, v);
+    double ev = a[0][0], nx = v[0][0], ny = v[1][0], nz = v[2][0];
+    if (a[1][1] < ev) { ev = a[1][1]; nx = v[0][1]; ny = v[1][1]; nz = v[2][1]; }
+    if (a[2][2] < ev) { ev = a[2][2]; nx = v[0][2]; ny = v[1][2]; nz = v[2][2]; }
+    double curv = (trace > 0) ? fabs(ev / trace) : 0.0;
+    double dot = (nx * -(double)q.x + ny * -(double)q.y) + nz * -(double)q.z;     // flipNormalTowardsViewpoint, vp = 0
+    if (dot < 0) { nx = -nx; ny = -ny; nz = -nz; }
+    o.x = (float)nx; o.y = (float)ny; o.z = (float)nz; o.w = (float)curv;
+    return o;
+}
+
+// large clouds: one thread per point (neighbouring threads walk the same cell ranges)
 __global__ void __launch_bounds__(128) k_normals(GridView g, float r2, float4* __restrict__ normals) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= g.n) return;
@@ -29,31 +56,54 @@ __global__ void __launch_bounds__(128) k_normals(GridView g, float r2, float4* _
             ++cnt;
         }
     });
-    float4 o;
-    if (cnt < 3) {
-        o.x = o.y = o.z = o.w = __int_as_float(0x7fc00000);
-    } else {
-        double k = (double)cnt;
-        double mx = sx / k, my = sy / k, mz = sz / k;
-        double a[3][3], v[3][3];
-        a[0][0] = cxx / k - mx * mx; a[0][1] = cxy / k - mx * my; a[0][2] = cxz / k - mx * mz;
-        a[1][1] = cyy / k - my * my; a[1][2] = cyz / k - my * mz; a[2][2] = czz / k - mz * mz;
-        a[1][0] = a[0][1]; a[2][0] = a[0][2]; a[2][1] = a[1][2];
-        double trace = a[0][0] + a[1][1] + a[2][2];
-        jacobi_eig<3>(a, v);
-        double ev = a[0][0], nx = v[0][0], ny = v[1][0], nz = v[2][0];
-        if (a[1][1] < ev) { ev = a[1][1]; nx = v[0][1]; ny = v[1][1]; nz = v[2][1]; }
-        if (a[2][2] < ev) { ev = a[2][2]; nx = v[0][2]; ny = v[1][2]; nz = v[2][2]; }
-        double curv = (trace > 0) ? fabs(ev / trace) : 0.0;
-        // flipNormalTowardsViewpoint with the default viewpoint (0,0,0)
-        double dot = (nx * -(double)q.x + ny * -(double)q.y) + nz * -(double)q.z;
-        if (dot < 0) { nx = -nx; ny = -ny; nz = -nz; }
-        o.x = (float)nx; o.y = (float)ny; o.z = (float)nz; o.w = (float)curv;
+    normals[__float_as_int(q.w)] = normal_from_sums(q, cnt, sx, sy, sz, cxx, cxy, cxz, cyy, cyz, czz);
+}
+
+// Visit the 27-cell block with the lanes of a warp striding over each of the 9 ranges (all lanes share the query).
+template <typename F>
+__device__ __forceinline__ void for_block27_warp(const GridView& g, float qx, float qy, float qz, int lane, F&& f) {
+    int cx = cell_coord(qx, g.mnx, g.inv_h), cy = cell_coord(qy, g.mny, g.inv_h), cz = cell_coord(qz, g.mnz, g.inv_h);
+    if (cx < -1 || cy < -1 || cz < -1 || cx > g.dx || cy > g.dy || cz > g.dz) return;
+    cx = clampi(cx, 0, g.dx - 1); cy = clampi(cy, 0, g.dy - 1); cz = clampi(cz, 0, g.dz - 1);
+    int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
+    for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
+        for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y) {
+            int s0 = __ldg(g.cell_begin + cell_key(g, x0, y, z));
+            int s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
+            for (int s = s0 + lane; s < s1; s += 32) {
+                float4 p = __ldg(g.sorted + s);
+                f(s, p, dist2f(qx, qy, qz, p.x, p.y, p.z));
+            }
+        }
+}
+
+// repo-sized clouds (a few thousand points) cannot fill the GPU with one thread per point: one WARP per point, lanes
+// stride over the candidates, fp64 partial sums folded with a warp-shuffle tree.
+#define PW_WARPS 8
+__global__ void __launch_bounds__(PW_WARPS * 32) k_normals_warp(GridView g, float r2, float4* __restrict__ normals) {
+    int lane = threadIdx.x & 31;
+    int nwarps = gridDim.x * PW_WARPS;
+    for (int s = blockIdx.x * PW_WARPS + (threadIdx.x >> 5); s < g.n; s += nwarps) {
+        float4 q = __ldg(g.sorted + s);
+        double sx = 0, sy = 0, sz = 0, cxx = 0, cxy = 0, cxz = 0, cyy = 0, cyz = 0, czz = 0;
+        int cnt = 0;
+        for_block27_warp(g, q.x, q.y, q.z, lane, [&](int, float4 p, float d2) {
+            if (d2 < r2) {
+                double dx = (double)p.x - (double)q.x, dy = (double)p.y - (double)q.y, dz = (double)p.z - (double)q.z;
+                sx += dx; sy += dy; sz += dz;
+                cxx += dx * dx; cxy += dx * dy; cxz += dx * dz; cyy += dy * dy; cyz += dy * dz; czz += dz * dz;
+                ++cnt;
+            }
+        });
+        cnt = warp_sum(cnt);
+        sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+        cxx = warp_sum(cxx); cxy = warp_sum(cxy); cxz = warp_sum(cxz); cyy = warp_sum(cyy); cyz = warp_sum(cyz); czz = warp_sum(czz);
+        if (lane == 0) normals[__float_as_int(q.w)] = normal_from_sums(q, cnt, sx, sy, sz, cxx, cxy, cxz, cyy, cyz, czz);
     }
-    normals[__float_as_int(q.w)] = o;
 }
 
 // ----------------------------------------------------------------------------- Harris 3D (App. A.3)
+__device__ __forceinline__ float harris_from_sums(int cnt, double c0, double c1, double c2, double c3, double c4, double c5);
 __global__ void __launch_bounds__(128) k_harris_response(GridView g, const float4* __restrict__ sn, float r2,
                                                          float* __restrict__ resp, float* __restrict__ resp_sorted) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -70,16 +120,7 @@ __global__ void __launch_bounds__(128) k_harris_response(GridView g, const float
             }
         }
     });
-    float r = 0.f;
-    if (cnt > 0) {
-        double k = (double)cnt;
-        double xx = c0 / k, xy = c1 / k, xz = c2 / k, yy = c3 / k, yz = c4 / k, zz = c5 / k;
-        double trace = xx + yy + zz;
-        if (trace != 0) {
-            double det = xx * yy * zz + 2.0 * xy * xz * yz - xz * xz * yy - xy * xy * zz - yz * yz * xx;
-            r = (float)(0.04 + det - 0.04 * trace * trace);
-        }
-    }
+    float r = harris_from_sums(cnt, c0, c1, c2, c3, c4, c5);
     resp[__float_as_int(q.w)] = r;
     resp_sorted[s] = r;
 }
@@ -99,6 +140,66 @@ __global__ void __launch_bounds__(128) k_harris_nms(GridView g, const float* __r
         keep = is_max;
     }
     flags[__float_as_int(q.w)] = keep ? 1 : 0;
+}
+
+__device__ __forceinline__ float harris_from_sums(int cnt, double c0, double c1, double c2, double c3, double c4, double c5) {
+    float r = 0.f;
+    if (cnt > 0) {
+        double k = (double)cnt;
+        double xx = c0 / k, xy = c1 / k, xz = c2 / k, yy = c3 / k, yz = c4 / k, zz = c5 / k;
+        double trace = xx + yy + zz;
+        if (trace != 0) {
+            double det = xx * yy * zz + 2.0 * xy * xz * yz - xz * xz * yy - xy * xy * zz - yz * yz * xx;
+            r = (float)(0.04 + det - 0.04 * trace * trace);
+        }
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(PW_WARPS * 32) k_harris_response_warp(GridView g, const float4* __restrict__ sn, float r2,
+                                                                       float* __restrict__ resp, float* __restrict__ resp_sorted) {
+    int lane = threadIdx.x & 31;
+    int nwarps = gridDim.x * PW_WARPS;
+    for (int s = blockIdx.x * PW_WARPS + (threadIdx.x >> 5); s < g.n; s += nwarps) {
+        float4 q = __ldg(g.sorted + s);
+        double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
+        int cnt = 0;
+        for_block27_warp(g, q.x, q.y, q.z, lane, [&](int sp, float4, float d2) {
+            if (d2 < r2) {
+                float4 nj = __ldg(sn + sp);
+                if (finite3(nj)) {
+                    double x = nj.x, y = nj.y, z = nj.z;
+                    c0 += x * x; c1 += x * y; c2 += x * z; c3 += y * y; c4 += y * z; c5 += z * z; ++cnt;
+                }
+            }
+        });
+        cnt = warp_sum(cnt);
+        c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2); c3 = warp_sum(c3); c4 = warp_sum(c4); c5 = warp_sum(c5);
+        if (lane == 0) {
+            float r = harris_from_sums(cnt, c0, c1, c2, c3, c4, c5);
+            resp[__float_as_int(q.w)] = r;
+            resp_sorted[s] = r;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PW_WARPS * 32) k_harris_nms_warp(GridView g, const float* __restrict__ resp_sorted, float r2, float thr,
+                                                                  int nms, unsigned char* __restrict__ flags) {
+    int lane = threadIdx.x & 31;
+    int nwarps = gridDim.x * PW_WARPS;
+    for (int s = blockIdx.x * PW_WARPS + (threadIdx.x >> 5); s < g.n; s += nwarps) {
+        float4 q = __ldg(g.sorted + s);
+        float r = resp_sorted[s];
+        bool keep = isfinite(r) && (r >= thr);
+        if (keep && nms) {       // warp-uniform branch: all lanes share r
+            bool bigger = false;
+            for_block27_warp(g, q.x, q.y, q.z, lane, [&](int sp, float4, float d2) {
+                if (d2 < r2 && __ldg(resp_sorted + sp) > r) bigger = true;
+            });
+            keep = !__any_sync(0xffffffffu, bigger);
+        }
+        if (lane == 0) flags[__float_as_int(q.w)] = keep ? 1 : 0;
+    }
 }
 
 // refineCorners: one warp per corner, lanes stride over the 9 candidate ranges.  The sums A = sum n n^T and
@@ -334,70 +435,97 @@ __global__ void __launch_bounds__(FPFH_WARPS * 32) k_fpfh_weight(GridView g, con
 #define MATCH_TILE 64
 #define MATCH_KMAX 8
 __global__ void __launch_bounds__(MATCH_WARPS * 32) k_match(const float* __restrict__ fa, int na, const float* __restrict__ fb,
-                                                            int nb, int k, int* __restrict__ out_idx, float* __restrict__ out_dist) {
+                                                            int nb, int k, int* __restrict__ out_idx, float* __restrict__ out_dist,
+                                                            const int* __restrict__ rows, const int* __restrict__ row_count) {
     __shared__ float tile[MATCH_TILE * 33];
     __shared__ float src[MATCH_WARPS][33];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int row = blockIdx.x * MATCH_WARPS + warp;
-    bool active = row < na;
-    if (active) {
-        src[warp][lane] = fa[(size_t)row * 33 + lane];
-        if (lane == 0) src[warp][32] = fa[(size_t)row * 33 + 32];
-    }
-    float bd[MATCH_KMAX];
-    int bi[MATCH_KMAX];
-#pragma unroll
-    for (int t = 0; t < MATCH_KMAX; ++t) { bd[t] = FLT_MAX; bi[t] = 0x7fffffff; }
-    for (int base = 0; base < nb; base += MATCH_TILE) {
-        __syncthreads();
-        int rows = min(MATCH_TILE, nb - base);
-        for (int e = threadIdx.x; e < rows * 33; e += blockDim.x) tile[e] = __ldg(fb + (size_t)base * 33 + e);
-        __syncthreads();
+    // optional row list (rows the tensor-core prefilter could not certify): same kernel, indirect row index
+    int nrows = rows ? *row_count : na;
+    for (int rbase = blockIdx.x * MATCH_WARPS; rbase < nrows; rbase += gridDim.x * MATCH_WARPS) {
+        int li = rbase + warp;
+        bool active = li < nrows;
+        int row = active ? (rows ? rows[li] : li) : 0;
+        __syncwarp();
         if (active) {
+            src[warp][lane] = fa[(size_t)row * 33 + lane];
+            if (lane == 0) src[warp][32] = fa[(size_t)row * 33 + 32];
+        }
+        float bd[MATCH_KMAX];
+        int bi[MATCH_KMAX];
 #pragma unroll
-            for (int half = 0; half < MATCH_TILE / 32; ++half) {
-                int r = half * 32 + lane;
-                if (r < rows) {
-                    const float* b = tile + r * 33;
-                    double sacc = 0;
+        for (int t = 0; t < MATCH_KMAX; ++t) { bd[t] = FLT_MAX; bi[t] = 0x7fffffff; }
+        for (int base = 0; base < nb; base += MATCH_TILE) {
+            __syncthreads();
+            int rows_in_tile = min(MATCH_TILE, nb - base);
+            for (int e = threadIdx.x; e < rows_in_tile * 33; e += blockDim.x) tile[e] = __ldg(fb + (size_t)base * 33 + e);
+            __syncthreads();
+            if (active) {
 #pragma unroll
-                    for (int c = 0; c < 33; ++c) { double d = (double)src[warp][c] - (double)b[c]; sacc += d * d; }
-                    float df = (float)sacc;
-                    int id = base + r;
-                    if (df == df && (df < bd[MATCH_KMAX - 1] || (df == bd[MATCH_KMAX - 1] && id < bi[MATCH_KMAX - 1]))) {
-                        bd[MATCH_KMAX - 1] = df; bi[MATCH_KMAX - 1] = id;
+                for (int half = 0; half < MATCH_TILE / 32; ++half) {
+                    int r = half * 32 + lane;
+                    if (r < rows_in_tile) {
+                        const float* b = tile + r * 33;
+                        double sacc = 0;
 #pragma unroll
-                        for (int t = MATCH_KMAX - 1; t > 0; --t) {
-                            bool sw = (bd[t] < bd[t - 1]) || (bd[t] == bd[t - 1] && bi[t] < bi[t - 1]);
-                            if (sw) { float td = bd[t]; bd[t] = bd[t - 1]; bd[t - 1] = td; int ti = bi[t]; bi[t] = bi[t - 1]; bi[t - 1] = ti; }
+                        for (int c = 0; c < 33; ++c) { double d = (double)src[warp][c] - (double)b[c]; sacc += d * d; }
+                        float df = (float)sacc;
+                        int id = base + r;
+                        if (df == df && (df < bd[MATCH_KMAX - 1] || (df == bd[MATCH_KMAX - 1] && id < bi[MATCH_KMAX - 1]))) {
+                            bd[MATCH_KMAX - 1] = df; bi[MATCH_KMAX - 1] = id;
+#pragma unroll
+                            for (int t = MATCH_KMAX - 1; t > 0; --t) {
+                                bool sw = (bd[t] < bd[t - 1]) || (bd[t] == bd[t - 1] && bi[t] < bi[t - 1]);
+                                if (sw) { float td = bd[t]; bd[t] = bd[t - 1]; bd[t - 1] = td; int ti = bi[t]; bi[t] = bi[t - 1]; bi[t - 1] = ti; }
+                            }
                         }
                     }
                 }
             }
         }
-    }
-    if (!active) return;
-    // merge: k rounds of a warp-wide lexicographic (dist, idx) minimum over the list heads
-    for (int t = 0; t < k; ++t) {
-        float hd = bd[0]; int hi = bi[0];
-        float md = hd; int mi = hi;
+        if (!active) continue;
+        // merge: k rounds of a warp-wide lexicographic (dist, idx) minimum over the list heads
+        for (int t = 0; t < k; ++t) {
+            float hd = bd[0]; int hi = bi[0];
+            float md = hd; int mi = hi;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            float od = __shfl_xor_sync(0xffffffffu, md, o);
-            int oi = __shfl_xor_sync(0xffffffffu, mi, o);
-            if (od < md || (od == md && oi < mi)) { md = od; mi = oi; }
-        }
-        if (mi == hi && md == hd && hi != 0x7fffffff) {   // this lane owned the winner: pop it
+            for (int o = 16; o > 0; o >>= 1) {
+                float od = __shfl_xor_sync(0xffffffffu, md, o);
+                int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+                if (od < md || (od == md && oi < mi)) { md = od; mi = oi; }
+            }
+            if (mi == hi && md == hd && hi != 0x7fffffff) {   // this lane owned the winner: pop it
 #pragma unroll
-            for (int u = 0; u < MATCH_KMAX - 1; ++u) { bd[u] = bd[u + 1]; bi[u] = bi[u + 1]; }
-            bd[MATCH_KMAX - 1] = FLT_MAX; bi[MATCH_KMAX - 1] = 0x7fffffff;
-        }
-        if (lane == 0) {
-            bool none = (mi == 0x7fffffff);
-            out_idx[(size_t)row * k + t] = none ? -1 : mi;
-            out_dist[(size_t)row * k + t] = none ? __int_as_float(0x7fc00000) : md;
+                for (int u = 0; u < MATCH_KMAX - 1; ++u) { bd[u] = bd[u + 1]; bi[u] = bi[u + 1]; }
+                bd[MATCH_KMAX - 1] = FLT_MAX; bi[MATCH_KMAX - 1] = 0x7fffffff;
+            }
+            if (lane == 0) {
+                bool none = (mi == 0x7fffffff);
+                out_idx[(size_t)row * k + t] = none ? -1 : mi;
+                out_dist[(size_t)row * k + t] = none ? __int_as_float(0x7fc00000) : md;
+            }
         }
     }
+}
+
+// exact search for all rows (rows == nullptr) or for a device-side list of rows
+int rtr_match_exact_launch(rtr_context* ctx, const float* fa, int na, const float* fb, int nb, int k, int* out_idx, float* out_dist,
+                           const int* rows, const int* row_count, int max_rows) {
+    if (max_rows <= 0) return 0;
+    int grid = std::min(nblk(max_rows, MATCH_WARPS), ctx->sm_count * 8);
+    k_match<<<grid, MATCH_WARPS * 32, 0, ctx->stream>>>(fa, na, fb, nb, k, out_idx, out_dist, rows, row_count);
+    RTR_LAUNCH_CHECK(ctx, rows ? "match.redo" : "match");
+    return 0;
+}
+
+bool rtr_match_tc_wanted(long long ns, long long nt);
+int rtr_match_tc_dev(rtr_context* ctx, const float* fa, int ns, const float* fb, int nt, int k, int* out_idx, float* out_dist, int* stats);
+
+// feature k-NN dispatcher: tensor-core prefilter + exact re-rank for large problems, exact SIMT kernel otherwise
+static int match_dispatch(rtr_context* ctx, const float* fa, int na, const float* fb, int nb, int k, int* out_idx, float* out_dist, int* stats) {
+    if (stats) { stats[0] = -1; stats[1] = 0; stats[2] = 0; }
+    if (rtr_match_tc_wanted(na, nb)) return rtr_match_tc_dev(ctx, fa, na, fb, nb, k, out_idx, out_dist, stats);
+    return rtr_match_exact_launch(ctx, fa, na, fb, nb, k, out_idx, out_dist, nullptr, nullptr, na);
 }
 
 // ----------------------------------------------------------------------------- host drivers
@@ -408,7 +536,10 @@ int rtr_normals_dev(rtr_cloud* c, float radius) {
     if (int e = rtr_get_grid(c, radius, &g)) return e;
     if (!c->normals) if (int e = dev_alloc(ctx, &c->normals, c->n, "normals")) return e;
     if (c->n > 0) {
-        k_normals<<<nblk(c->n, 128), 128, 0, ctx->stream>>>(rtr_view(g), radius * radius, c->normals);
+        if (c->n <= RTR_WARP_PER_POINT_MAX)
+            k_normals_warp<<<std::min(nblk(c->n, PW_WARPS), ctx->sm_count * 16), PW_WARPS * 32, 0, ctx->stream>>>(rtr_view(g), radius * radius, c->normals);
+        else
+            k_normals<<<nblk(c->n, 128), 128, 0, ctx->stream>>>(rtr_view(g), radius * radius, c->normals);
         RTR_LAUNCH_CHECK(ctx, "normals");
     }
     c->normals_radius = radius;
@@ -435,10 +566,18 @@ int rtr_harris_dev(rtr_cloud* c, float radius, float threshold, int nms, int ref
     RTR_CHECK(cudaMemsetAsync(*d_count, 0, sizeof(int), ctx->stream), "harris");
     if (n > 0) {
         GridView v = rtr_view(g);
-        k_harris_response<<<nblk(n, 128), 128, 0, ctx->stream>>>(v, g->sorted_normals, r2, c->response, resp_sorted);
-        RTR_LAUNCH_CHECK(ctx, "harris.response");
-        k_harris_nms<<<nblk(n, 128), 128, 0, ctx->stream>>>(v, resp_sorted, r2, threshold, nms, flags);
-        RTR_LAUNCH_CHECK(ctx, "harris.nms");
+        if (n <= RTR_WARP_PER_POINT_MAX) {
+            int grid = std::min(nblk(n, PW_WARPS), ctx->sm_count * 16);
+            k_harris_response_warp<<<grid, PW_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, c->response, resp_sorted);
+            RTR_LAUNCH_CHECK(ctx, "harris.response");
+            k_harris_nms_warp<<<grid, PW_WARPS * 32, 0, ctx->stream>>>(v, resp_sorted, r2, threshold, nms, flags);
+            RTR_LAUNCH_CHECK(ctx, "harris.nms");
+        } else {
+            k_harris_response<<<nblk(n, 128), 128, 0, ctx->stream>>>(v, g->sorted_normals, r2, c->response, resp_sorted);
+            RTR_LAUNCH_CHECK(ctx, "harris.response");
+            k_harris_nms<<<nblk(n, 128), 128, 0, ctx->stream>>>(v, resp_sorted, r2, threshold, nms, flags);
+            RTR_LAUNCH_CHECK(ctx, "harris.nms");
+        }
         size_t tb = 0;
         thrust::counting_iterator<int> iota(0);
         cub::DeviceSelect::Flagged(nullptr, tb, iota, flags, *d_kp_idx, *d_count, n, ctx->stream);
@@ -489,10 +628,7 @@ int rtr_match_dev(rtr_cloud* src, rtr_cloud* tgt, int k) {
     src->knn = nullptr; src->knn_dist = nullptr;
     if (int e = dev_alloc(ctx, &src->knn, (size_t)src->n * k, "match")) return e;
     if (int e = dev_alloc(ctx, &src->knn_dist, (size_t)src->n * k, "match")) return e;
-    if (src->n > 0) {
-        k_match<<<nblk(src->n, MATCH_WARPS), MATCH_WARPS * 32, 0, ctx->stream>>>(src->fpfh, src->n, tgt->fpfh, tgt->n, k, src->knn, src->knn_dist);
-        RTR_LAUNCH_CHECK(ctx, "match");
-    }
+    if (src->n > 0) if (int e = match_dispatch(ctx, src->fpfh, src->n, tgt->fpfh, tgt->n, k, src->knn, src->knn_dist, nullptr)) return e;
     src->knn_k = k; src->knn_target_n = tgt->n;
     return 0;
 }
@@ -555,10 +691,7 @@ int rtr_match_features_raw(rtr_context* ctx, const float* host_source_feat, int 
     if (ns > 0) RTR_CHECK(cudaMemcpyAsync(fa, host_source_feat, (size_t)ns * 132, cudaMemcpyHostToDevice, ctx->stream), "match_raw");
     if (nt > 0) RTR_CHECK(cudaMemcpyAsync(fb, host_target_feat, (size_t)nt * 132, cudaMemcpyHostToDevice, ctx->stream), "match_raw");
     RTR_CHECK(cudaEventRecord(ctx->events[RTR_NUM_EVENTS - 2], ctx->stream), "match_raw");
-    if (ns > 0) {
-        k_match<<<nblk(ns, MATCH_WARPS), MATCH_WARPS * 32, 0, ctx->stream>>>(fa, ns, fb, nt, k, di, dd);
-        RTR_LAUNCH_CHECK(ctx, "match");
-    }
+    if (ns > 0) if (int e = match_dispatch(ctx, fa, ns, fb, nt, k, di, dd, ctx->match_stats)) return e;
     RTR_CHECK(cudaEventRecord(ctx->events[RTR_NUM_EVENTS - 1], ctx->stream), "match_raw");
     if (ns > 0) {
         RTR_CHECK(cudaMemcpyAsync(host_idx, di, (size_t)ns * k * 4, cudaMemcpyDeviceToHost, ctx->stream), "match_raw");
@@ -567,6 +700,14 @@ int rtr_match_features_raw(rtr_context* ctx, const float* host_source_feat, int 
     RTR_CHECK(cudaStreamSynchronize(ctx->stream), "match_raw");
     if (kernel_ms) RTR_CHECK(cudaEventElapsedTime(kernel_ms, ctx->events[RTR_NUM_EVENTS - 2], ctx->events[RTR_NUM_EVENTS - 1]), "match_raw");
     dev_free(ctx, fa); dev_free(ctx, fb); dev_free(ctx, di); dev_free(ctx, dd);
+    return 0;
+}
+
+// [0] rows the tensor-core prefilter could not certify and the exact kernel redid (-1: exact kernel used for everything),
+// [1] target splits, [2] observed prefilter error / (|a||b|) in 1e-9 units — of the last rtr_match_features_raw call on this context.
+int rtr_match_last_stats(rtr_context* ctx, int* stats3) {
+    if (!ctx || !stats3) return rtr_fail("match_stats", "bad argument", RTR_ERR_INVALID);
+    for (int i = 0; i < 3; ++i) stats3[i] = ctx->match_stats[i];
     return 0;
 }
 

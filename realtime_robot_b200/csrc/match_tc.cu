@@ -1,0 +1,460 @@
+// match_tc.cu — descriptor correspondence search on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// The step is a dense contraction: d(i,j) = |a_i|^2 + |b_j|^2 - 2 a_i.b_j over 33-D FPFH signatures (KdTreeFLANN<
+// FPFHSignature33>::nearestKSearch inside SampleConsensusPrerejective::findSimilarFeatures).  The
+// result must be EXACT (same indices as the fp64 oracle), so the tensor cores are used as a PREFILTER with a certificate:
+//
+//   1. k_tc_prep   : each fp32 feature value is split into tf32 hi + tf32 lo; operand rows are
+//                    A = [hi | hi | lo | 0], B = [hi | lo | hi | 0] (K = 104), so one TF32 GEMM yields
+//                    hi.hi + hi.lo + lo.hi = a.b to ~2^-22 relative.  Rows are written in the UMMA canonical K-major
+//                    no-swizzle layout (8-row x 16-byte core matrices), 128-row tiles, ready for 1-D bulk copies.
+//   2. k_tc_match  : one CTA per (128 source rows, split of the target tiles).  Warp 0 streams 128-row target tiles into
+//                    a 3-stage shared-memory ring with cp.async.bulk + mbarrier; warp 1 issues tcgen05.mma (M=128,
+//                    N=128, kind::tf32, 13 k-steps) into a 3-stage TMEM accumulator ring; warps 2-5 read the
+//                    accumulators back with tcgen05.ld (thread = source row, 32 columns per load), form
+//                    |b_j|^2 - 2 S_ij and keep the 16 smallest per row in registers.
+//   3. k_tc_rerank : one warp per source row recomputes the kept candidates' distances exactly (the oracle's sequential
+//                    fp64 sum), takes the top k, and certifies the row: every rejected candidate had approximate distance
+//                    >= T (the 16th kept), hence exact distance >= T - E; if the exact k-th best is < T - E nothing
+//                    rejected can enter.  Uncertified rows (rare) are redone by the exact SIMT kernel.
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#define TC_TILE 128                    // rows per operand tile (UMMA M = N = 128)
+#define TC_KF 104                      // floats per operand row: 3 x 33 + 5 pad  (13 k-steps of 8 tf32)
+#define TC_NC 26                       // 16-byte chunks per operand row
+#define TC_TILE_BYTES (TC_TILE * TC_KF * 4)    // 53248
+#define TC_STAGES 3
+#define TC_KEEP_MAX 32                 // candidates kept per (source row, split): 16, or 32 when there is a single split
+#define TC_THREADS 192
+#define TC_MAX_SPLITS 8
+
+// defined in features.cu
+int rtr_match_exact_launch(rtr_context* ctx, const float* fa, int na, const float* fb, int nb, int k, int* out_idx, float* out_dist,
+                           const int* rows, const int* row_count, int max_rows);
+
+// ----------------------------------------------------------------------------- small PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded spin: a protocol bug must end in a trapped kernel (an error status at the C ABI), never in a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (long long spin = 0; spin < 4000000LL; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE ("interleave"): 8-row x 16-byte core matrices;
+// LBO = byte distance between core matrices adjacent in K, SBO = between 8-row groups (both in 16-byte units).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(128 >> 4) << 16;                         // LBO: next core matrix along K is 128 B away
+    d |= (uint64_t)((TC_NC * 128) >> 4) << 32;               // SBO: next 8-row group is 26 core matrices away
+    d |= (uint64_t)1 << 46;                                  // descriptor version (Blackwell)
+    return d;                                                // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+#define TC_IDESC ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_TILE >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24))
+
+// ----------------------------------------------------------------------------- 1. operand preparation
+__device__ __forceinline__ float tf32_hi(float a) { return __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xFFFFE000u); }
+__device__ __forceinline__ float tf32_trunc(float a) { return __uint_as_float(__float_as_uint(a) & 0xFFFFE000u); }
+
+// role 0: source rows A = [hi | hi | lo | 0];  role 1: target rows B = [hi | lo | hi | 0]
+// Features are centred on the targets' mean first (distances are translation invariant): the prefilter's error scales
+// with |a - mu||b - mu| instead of |a||b|, which matters when all signatures are alike (dense scenes).
+__global__ void k_tc_mean(const float* __restrict__ feat, int n, float* __restrict__ mu) {
+    __shared__ double acc[32][33];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double s0 = 0, s1 = 0;
+    for (int r = warp; r < n; r += 32) {
+        float a = __ldg(feat + (size_t)r * 33 + lane), b = (lane == 0) ? __ldg(feat + (size_t)r * 33 + 32) : 0.f;
+        if (isfinite(a)) s0 += a;
+        if (isfinite(b)) s1 += b;
+    }
+    acc[warp][lane] = s0;
+    if (lane == 0) acc[warp][32] = s1;
+    __syncthreads();
+    if (threadIdx.x < 33) {
+        double t = 0;
+        for (int w = 0; w < 32; ++w) t += acc[w][threadIdx.x];
+        mu[threadIdx.x] = n > 0 ? (float)(t / n) : 0.f;
+    }
+}
+
+__global__ void k_tc_prep(const float* __restrict__ feat, int n, int n_pad, int role, const float* __restrict__ mu,
+                          float* __restrict__ tiles, float* __restrict__ norms, float* __restrict__ norm_max) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_pad) return;
+    int tile = r / TC_TILE, rr = r % TC_TILE;
+    char* base = (char*)tiles + (size_t)tile * TC_TILE_BYTES + (size_t)(rr / 8) * TC_NC * 128 + (size_t)(rr % 8) * 16;
+    bool valid = r < n;
+    double nrm = 0;
+    float v[33];
+    if (valid) {
+#pragma unroll
+        for (int c = 0; c < 33; ++c) { v[c] = __ldg(feat + (size_t)r * 33 + c) - __ldg(mu + c); nrm += (double)v[c] * (double)v[c]; if (!isfinite(v[c])) valid = false; }
+    }
+#pragma unroll
+    for (int e = 0; e < TC_KF; ++e) {
+        float x = 0.f;
+        if (valid && e < 99) {
+            int c = e % 33, part = e / 33;
+            float hi = tf32_hi(v[c]);
+            float lo = tf32_trunc(v[c] - hi);
+            bool want_lo = (role == 0) ? (part == 2) : (part == 1);
+            x = want_lo ? lo : hi;
+        }
+        *(float*)(base + (size_t)(e / 4) * 128 + (e % 4) * 4) = x;
+    }
+    norms[r] = valid ? (float)nrm : FLT_MAX;         // FLT_MAX: a padded / non-finite row can never be selected
+    if (valid && norm_max) atomicMax((int*)norm_max, __float_as_int((float)nrm * 1.000001f));   // non-negative floats order like ints
+}
+
+// ----------------------------------------------------------------------------- 2. tcgen05 prefilter
+struct TcSmem {
+    alignas(128) unsigned char a[TC_TILE_BYTES];
+    alignas(128) unsigned char b[TC_STAGES][TC_TILE_BYTES];
+    alignas(16) float nb[TC_STAGES][TC_TILE];
+    alignas(16) float dbuf[32][TC_TILE];         // epilogue scratch: one 32-column chunk of distances, [column][row]
+    alignas(8) unsigned long long bar_a;
+    unsigned long long bar_full[TC_STAGES];      // target tile landed in smem
+    unsigned long long bar_acc[TC_STAGES];       // accumulator complete in TMEM
+    unsigned long long bar_free[TC_STAGES];      // epilogue done with stage (smem norms + TMEM accumulator reusable)
+    unsigned int tmem_base;
+};
+
+template <int TC_KEEP>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_match(const float* __restrict__ a_tiles, const float* __restrict__ b_tiles, const float* __restrict__ b_norms, int ns,
+           int n_tgt_tiles, int tiles_per_split, int n_splits, int* __restrict__ cand_idx, float* __restrict__ cand_val,
+           float* __restrict__ cand_thr) {
+    // (no manual realignment: the pointer must stay visibly derived from the __shared__ array, otherwise every access
+    //  becomes a generic load / store on the long scoreboard)
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int src_tile = blockIdx.x, split = blockIdx.y;
+    const int t0 = split * tiles_per_split;
+    const int nt = max(0, min(tiles_per_split, n_tgt_tiles - t0));
+
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&sm.bar_a), 1);
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(smem_u32(&sm.bar_full[s]), 1);
+            mbar_init(smem_u32(&sm.bar_acc[s]), 1);
+            mbar_init(smem_u32(&sm.bar_free[s]), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM: 3 accumulators x 128 fp32 columns -> 512-column allocation (power of two)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 0) {
+        // ---------------- loader: source tile once, then the ring of target tiles
+        if (lane == 0) {
+            mbar_expect_tx(smem_u32(&sm.bar_a), TC_TILE_BYTES);
+            bulk_g2s(smem_u32(sm.a), (const char*)a_tiles + (size_t)src_tile * TC_TILE_BYTES, TC_TILE_BYTES, smem_u32(&sm.bar_a));
+            for (int t = 0; t < nt; ++t) {
+                int s = t % TC_STAGES;
+                uint32_t ph = (uint32_t)(t / TC_STAGES) & 1u;
+                mbar_wait(smem_u32(&sm.bar_free[s]), ph ^ 1u);
+                uint32_t full = smem_u32(&sm.bar_full[s]);
+                mbar_expect_tx(full, TC_TILE_BYTES + TC_TILE * 4);
+                bulk_g2s(smem_u32(sm.b[s]), (const char*)b_tiles + (size_t)(t0 + t) * TC_TILE_BYTES, TC_TILE_BYTES, full);
+                bulk_g2s(smem_u32(sm.nb[s]), b_norms + (size_t)(t0 + t) * TC_TILE, TC_TILE * 4, full);
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer: one thread issues, accumulators live in TMEM
+        mbar_wait(smem_u32(&sm.bar_a), 0);
+        const uint64_t adesc = umma_desc(smem_u32(sm.a));
+        for (int t = 0; t < nt; ++t) {
+            int s = t % TC_STAGES;
+            uint32_t ph = (uint32_t)(t / TC_STAGES) & 1u;
+            mbar_wait(smem_u32(&sm.bar_full[s]), ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint64_t bdesc = umma_desc(smem_u32(sm.b[s]));
+#pragma unroll
+                for (int k = 0; k < TC_KF / 8; ++k)      // 8 tf32 = 32 B = two 16-byte chunks = 256 B of core matrices per k-step
+                    tc_mma_tf32(tmem + (uint32_t)(s * TC_TILE), adesc + (uint64_t)(k * 16), bdesc + (uint64_t)(k * 16), TC_IDESC, k > 0 ? 1u : 0u);
+                tc_commit(smem_u32(&sm.bar_acc[s]));      // arrives when the MMAs above have completed
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------- epilogue: thread = source row; TMEM lane quarter = warp % 4
+        // Each thread keeps the TC_KEEP smallest values of its row (unsorted, thr = current maximum).  A chunk of 32
+        // columns is turned into distances branch-free (pass mask against thr); only then does each lane walk ITS OWN
+        // set bits — so a warp pays for the longest per-lane list, not for every column in which some lane inserts.
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        float val[TC_KEEP];
+        int idx[TC_KEEP];
+        float thr = FLT_MAX;
+#pragma unroll
+        for (int u = 0; u < TC_KEEP; ++u) { val[u] = FLT_MAX; idx[u] = -1; }
+        for (int t = 0; t < nt; ++t) {
+            int s = t % TC_STAGES;
+            uint32_t ph = (uint32_t)(t / TC_STAGES) & 1u;
+            mbar_wait(smem_u32(&sm.bar_acc[s]), ph);
+            tc_fence_after();
+            const int col0 = (t0 + t) * TC_TILE;
+#pragma unroll 1
+            for (int cc = 0; cc < TC_TILE / 32; ++cc) {
+                uint32_t r[32];
+                tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * TC_TILE + cc * 32), r);
+                tc_ld_wait();
+                unsigned mask = 0;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 nb4 = *reinterpret_cast<const float4*>(&sm.nb[s][cc * 32 + j4 * 4]);     // broadcast
+                    const float nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = j4 * 4 + jj;
+                        float d = fmaf(-2.0f, __uint_as_float(r[j]), nbv[jj]);
+                        sm.dbuf[j][row] = d;
+                        mask |= (d < thr ? 1u : 0u) << j;
+                    }
+                }
+                while (mask) {
+                    int j = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    float d = sm.dbuf[j][row];
+                    if (d < thr) {                 // thr may have tightened since the mask was formed
+                        bool done = false;
+                        float nt_ = -FLT_MAX;
+#pragma unroll
+                        for (int u = 0; u < TC_KEEP; ++u) {
+                            bool hit = (val[u] == thr) && !done;
+                            val[u] = hit ? d : val[u];
+                            idx[u] = hit ? (col0 + cc * 32 + j) : idx[u];
+                            done = done || hit;
+                            nt_ = fmaxf(nt_, val[u]);
+                        }
+                        thr = nt_;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&sm.bar_free[s]));
+        }
+        int grow = src_tile * TC_TILE + row;
+        if (grow < ns) {
+            size_t o = ((size_t)grow * n_splits + split) * TC_KEEP;
+#pragma unroll
+            for (int u = 0; u < TC_KEEP; ++u) { cand_idx[o + u] = idx[u]; cand_val[o + u] = val[u]; }
+            cand_thr[(size_t)grow * n_splits + split] = thr;     // FLT_MAX while the list is not full: nothing was rejected
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// ----------------------------------------------------------------------------- 3. exact re-rank + certificate
+#define RR_WARPS 8
+#define RR_KMAX 8
+__global__ void __launch_bounds__(RR_WARPS * 32)
+k_tc_rerank(const float* __restrict__ fa, int ns, const float* __restrict__ fb, int nt, int k, const int* __restrict__ cand_idx,
+            const float* __restrict__ cand_val, const float* __restrict__ cand_thr, int n_splits, int TC_KEEP, const float* __restrict__ a_norms,
+            const float* __restrict__ b_norms, const float* __restrict__ nb_max_p, int* __restrict__ out_idx, float* __restrict__ out_dist, int* __restrict__ redo_rows, int* __restrict__ redo_count,
+            float* __restrict__ err_ratio_max) {
+    __shared__ float src[RR_WARPS][36];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int row = blockIdx.x * RR_WARPS + warp;
+    if (row >= ns) return;
+    src[warp][lane] = fa[(size_t)row * 33 + lane];
+    if (lane == 0) src[warp][32] = fa[(size_t)row * 33 + 32];
+    __syncwarp();
+    // squared norms of the CENTRED vectors (what the prefilter worked with); a non-finite source row has FLT_MAX here
+    double na = (double)a_norms[row];
+    double nb_max = (double)*nb_max_p;
+    // Error model of the prefilter's distance for a pair with centred norms |a|, |b| (DESIGN.md "tensor-core matching"):
+    // tf32 hi/lo split residue + dropped lo.lo term + fp32 accumulation over 13 MMA k-steps <= 3e-6 |a||b| on the dot
+    // product (x2 in the distance), plus the fp32 roundings of |b|^2 and of the final fma.
+#define TC_ERR(na_, nb_) (6e-6 * sqrt((na_) * (nb_)) + 2e-7 * ((na_) + (nb_)) + 1e-9)
+    float bd[RR_KMAX]; int bi[RR_KMAX];
+#pragma unroll
+    for (int t = 0; t < RR_KMAX; ++t) { bd[t] = FLT_MAX; bi[t] = 0x7fffffff; }
+    int C = n_splits * TC_KEEP;
+    bool sane = true;
+    double T = DBL_MAX;                       // smallest approximate distance any REJECTED candidate can have
+    for (int s = lane; s < n_splits; s += 32) {
+        float last = cand_thr[(size_t)row * n_splits + s];
+        if (last < FLT_MAX) T = fmin(T, (double)last + na);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) T = fmin(T, __shfl_xor_sync(0xffffffffu, T, o));
+    for (int c = lane; c < C; c += 32) {
+        int id = cand_idx[(size_t)row * C + c];
+        if (id < 0 || id >= nt) continue;
+        const float* b = fb + (size_t)id * 33;
+        double sacc = 0;
+#pragma unroll
+        for (int e = 0; e < 33; ++e) { double d = (double)src[warp][e] - (double)__ldg(b + e); sacc += d * d; }
+        float df = (float)sacc;
+        if (!(df == df)) continue;
+        // the error model must hold on everything we can check, with the candidate's own norm
+        double err = fabs(((double)cand_val[(size_t)row * C + c] + na) - sacc);
+        if (err > TC_ERR(na, (double)b_norms[id])) sane = false;
+        // observed error in units of |a||b| (diagnostic: shows how much head-room the 3e-6 model constant has)
+        double scale = sqrt(na * (double)b_norms[id]);
+        if (scale > 0) atomicMax((int*)err_ratio_max, __float_as_int((float)(err / scale)));
+        if (df < bd[RR_KMAX - 1] || (df == bd[RR_KMAX - 1] && id < bi[RR_KMAX - 1])) {
+            bd[RR_KMAX - 1] = df; bi[RR_KMAX - 1] = id;
+#pragma unroll
+            for (int t = RR_KMAX - 1; t > 0; --t) {
+                bool sw = (bd[t] < bd[t - 1]) || (bd[t] == bd[t - 1] && bi[t] < bi[t - 1]);
+                if (sw) { float td = bd[t]; bd[t] = bd[t - 1]; bd[t - 1] = td; int ti = bi[t]; bi[t] = bi[t - 1]; bi[t - 1] = ti; }
+            }
+        }
+    }
+    sane = __all_sync(0xffffffffu, sane);
+    float kth = FLT_MAX;
+    for (int t = 0; t < k; ++t) {
+        float hd = bd[0]; int hi = bi[0];
+        float md = hd; int mi = hi;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float od = __shfl_xor_sync(0xffffffffu, md, o);
+            int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+            if (od < md || (od == md && oi < mi)) { md = od; mi = oi; }
+        }
+        if (mi == hi && md == hd && hi != 0x7fffffff) {
+#pragma unroll
+            for (int u = 0; u < RR_KMAX - 1; ++u) { bd[u] = bd[u + 1]; bi[u] = bi[u + 1]; }
+            bd[RR_KMAX - 1] = FLT_MAX; bi[RR_KMAX - 1] = 0x7fffffff;
+        }
+        kth = md;
+        if (lane == 0) {
+            bool none = (mi == 0x7fffffff);
+            out_idx[(size_t)row * k + t] = none ? -1 : mi;
+            out_dist[(size_t)row * k + t] = none ? __int_as_float(0x7fc00000) : md;
+        }
+    }
+    // Certificate.  A rejected candidate j has approximate distance >= T.  If |b_j| > |a| + sqrt(kth) its exact distance
+    // exceeds kth by the triangle inequality; otherwise its error is at most E = TC_ERR(|a|^2, (|a| + sqrt(kth))^2), so
+    // its exact distance is >= T - E.  The row is final iff the exact k-th best is strictly below that.
+    double reach = sqrt(na) + sqrt(fmax((double)kth, 0.0));
+    double E = TC_ERR(na, fmin(nb_max, reach * reach));
+    bool certified = sane && (T == DBL_MAX || (kth < FLT_MAX && (double)kth < T - E));
+    if (!certified && lane == 0) redo_rows[atomicAdd(redo_count, 1)] = row;
+}
+
+// ----------------------------------------------------------------------------- host driver
+static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+
+bool rtr_match_tc_wanted(long long ns, long long nt) {
+    const char* e = getenv("RTR_MATCH_TC");
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '1') return ns > 0 && nt > 0;
+    return ns * nt >= 2000000LL;          // below ~2 M pairs the exact SIMT kernel is already a few tens of microseconds
+}
+
+// fa, fb: device feature arrays (ns x 33, nt x 33).  out_idx / out_dist: device, ns x k.  stats (host, optional):
+// [0] rows redone by the exact kernel, [1] splits, [2] target tiles.
+int rtr_match_tc_dev(rtr_context* ctx, const float* fa, int ns, const float* fb, int nt, int k, int* out_idx, float* out_dist, int* stats) {
+    if (k > RR_KMAX) return rtr_fail("match.tc", "k must be <= 8", RTR_ERR_INVALID);
+    int src_tiles = nblk(ns, TC_TILE), tgt_tiles = nblk(nt, TC_TILE);
+    int splits = std::min(std::min(TC_MAX_SPLITS, tgt_tiles), std::max(1, (2 * ctx->sm_count + src_tiles - 1) / src_tiles));
+    int tiles_per_split = nblk(tgt_tiles, splits);
+    splits = nblk(tgt_tiles, tiles_per_split);
+    float *a_tiles = nullptr, *b_tiles = nullptr, *a_norms = nullptr, *b_norms = nullptr, *cand_val = nullptr, *cand_thr = nullptr, *d_nbmax = nullptr, *mu = nullptr;
+    int *cand_idx = nullptr, *redo_rows = nullptr, *redo_count = nullptr;
+    if (int e = dev_alloc(ctx, &a_tiles, (size_t)src_tiles * TC_TILE * TC_KF, "match.tc")) return e;
+    if (int e = dev_alloc(ctx, &b_tiles, (size_t)tgt_tiles * TC_TILE * TC_KF, "match.tc")) return e;
+    if (int e = dev_alloc(ctx, &a_norms, (size_t)src_tiles * TC_TILE, "match.tc")) return e;
+    if (int e = dev_alloc(ctx, &b_norms, (size_t)tgt_tiles * TC_TILE, "match.tc")) return e;
+    // more kept candidates make the certificate succeed more often; with one split there is only one list per row
+    const int keep = (splits == 1) ? 32 : 16;
+    if (int e = dev_alloc(ctx, &cand_idx, (size_t)ns * splits * keep, "match.tc")) return e;
+    if (int e = dev_alloc(ctx, &cand_val, (size_t)ns * splits * keep, "match.tc")) return e;
+    if (int e = dev_alloc(ctx, &cand_thr, (size_t)ns * splits, "match.tc")) return e;
+    if (int e = dev_alloc(ctx, &redo_rows, (size_t)ns, "match.tc")) return e;
+    if (int e = dev_alloc(ctx, &redo_count, 1, "match.tc")) return e;
+    if (int e = dev_alloc(ctx, &d_nbmax, 2, "match.tc")) return e;      // [0] max centred |b|^2, [1] observed error ratio
+    if (int e = dev_alloc(ctx, &mu, 33, "match.tc")) return e;
+    RTR_CHECK(cudaMemsetAsync(redo_count, 0, sizeof(int), ctx->stream), "match.tc");
+    RTR_CHECK(cudaMemsetAsync(d_nbmax, 0, 2 * sizeof(float), ctx->stream), "match.tc");
+    k_tc_mean<<<1, 1024, 0, ctx->stream>>>(fb, std::min(nt, 1024), mu);      // any fixed vector works; a sample mean is enough
+    RTR_LAUNCH_CHECK(ctx, "match.tc_mean");
+    k_tc_prep<<<nblk((long long)src_tiles * TC_TILE, 128), 128, 0, ctx->stream>>>(fa, ns, src_tiles * TC_TILE, 0, mu, a_tiles, a_norms, nullptr);
+    RTR_LAUNCH_CHECK(ctx, "match.tc_prep");
+    k_tc_prep<<<nblk((long long)tgt_tiles * TC_TILE, 128), 128, 0, ctx->stream>>>(fb, nt, tgt_tiles * TC_TILE, 1, mu, b_tiles, b_norms, d_nbmax);
+    RTR_LAUNCH_CHECK(ctx, "match.tc_prep");
+    static bool attr_set = false;
+    size_t smem = sizeof(TcSmem);
+    if (!attr_set) {
+        RTR_CHECK(cudaFuncSetAttribute(k_tc_match<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "match.tc");
+        RTR_CHECK(cudaFuncSetAttribute(k_tc_match<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "match.tc");
+        attr_set = true;
+    }
+    if (keep == 32)
+        k_tc_match<32><<<dim3(src_tiles, splits), TC_THREADS, smem, ctx->stream>>>(a_tiles, b_tiles, b_norms, ns, tgt_tiles, tiles_per_split, splits, cand_idx, cand_val, cand_thr);
+    else
+        k_tc_match<16><<<dim3(src_tiles, splits), TC_THREADS, smem, ctx->stream>>>(a_tiles, b_tiles, b_norms, ns, tgt_tiles, tiles_per_split, splits, cand_idx, cand_val, cand_thr);
+    RTR_LAUNCH_CHECK(ctx, "match.tc_mma");
+    k_tc_rerank<<<nblk(ns, RR_WARPS), RR_WARPS * 32, 0, ctx->stream>>>(fa, ns, fb, nt, k, cand_idx, cand_val, cand_thr, splits, keep, a_norms, b_norms, d_nbmax, out_idx, out_dist, redo_rows, redo_count, d_nbmax + 1);
+    RTR_LAUNCH_CHECK(ctx, "match.tc_rerank");
+    if (int e = rtr_match_exact_launch(ctx, fa, ns, fb, nt, k, out_idx, out_dist, redo_rows, redo_count, ns)) return e;
+    if (stats) {
+        float ratio = 0.f;
+        RTR_CHECK(cudaMemcpyAsync(&stats[0], redo_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream), "match.tc");
+        RTR_CHECK(cudaMemcpyAsync(&ratio, d_nbmax + 1, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "match.tc");
+        RTR_CHECK(cudaStreamSynchronize(ctx->stream), "match.tc");
+        stats[1] = splits; stats[2] = (int)(ratio * 1e9f);      // observed max |approx - exact| / (|a||b|), in 1e-9 units
+    }
+    dev_free(ctx, a_tiles); dev_free(ctx, b_tiles); dev_free(ctx, a_norms); dev_free(ctx, b_norms);
+    dev_free(ctx, cand_idx); dev_free(ctx, cand_val); dev_free(ctx, cand_thr); dev_free(ctx, redo_rows); dev_free(ctx, redo_count); dev_free(ctx, d_nbmax); dev_free(ctx, mu);
+    return 0;
+}

@@ -106,22 +106,27 @@ __global__ void __launch_bounds__(64) k_ransac_pose(RansacArgs a, const int* __r
     for (int i = 0; i < 16; ++i) poses[(size_t)t * 16 + i] = pose[i];
 }
 
-// K3: getFitness — one CTA per surviving hypothesis, persistent over the survivor list
+// K3: getFitness — one CTA per (surviving hypothesis, slice of the source cloud), persistent over that work list.
+// With few survivors and a large source a CTA per hypothesis would leave most SMs idle, hence the slices; the per-slice
+// (inlier count, sum d2) partials are folded in slice order by K4.
 #define EVAL_THREADS 256
 __global__ void __launch_bounds__(EVAL_THREADS) k_ransac_eval(RansacArgs a, GridView g, const int* __restrict__ count,
-                                                              const float* __restrict__ poses, float* __restrict__ err,
-                                                              int* __restrict__ inl) {
+                                                              const float* __restrict__ poses, int split,
+                                                              double* __restrict__ psum, int* __restrict__ pcnt) {
     __shared__ float m[16];
     __shared__ double wsum[EVAL_THREADS / 32];
     __shared__ int wcnt[EVAL_THREADS / 32];
     int n = *count;
-    for (int t = blockIdx.x; t < n; t += gridDim.x) {
+    int chunk = (a.ns + split - 1) / split;
+    for (int w = blockIdx.x; w < n * split; w += gridDim.x) {
+        int t = w / split, part = w - t * split;
+        int i0 = part * chunk, i1 = min(a.ns, i0 + chunk);
         __syncthreads();
         if (threadIdx.x < 16) m[threadIdx.x] = poses[(size_t)t * 16 + threadIdx.x];
         __syncthreads();
         int cnt = 0;
         double sum = 0;
-        for (int i = threadIdx.x; i < a.ns; i += EVAL_THREADS) {
+        for (int i = i0 + threadIdx.x; i < i1; i += EVAL_THREADS) {
             float4 q = xform(m, __ldg(a.src + i));
             float best = FLT_MAX;
             for_block27(g, q.x, q.y, q.z, [&](int, float4, float d2) { if (d2 < best) best = d2; });
@@ -134,9 +139,8 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_ransac_eval(RansacArgs a, Grid
         if (threadIdx.x == 0) {
             double S = 0; int C = 0;
 #pragma unroll
-            for (int w = 0; w < EVAL_THREADS / 32; ++w) { S += wsum[w]; C += wcnt[w]; }
-            err[t] = C > 0 ? (float)(S / (double)C) : FLT_MAX;
-            inl[t] = C;
+            for (int ww = 0; ww < EVAL_THREADS / 32; ++ww) { S += wsum[ww]; C += wcnt[ww]; }
+            psum[w] = S; pcnt[w] = C;
         }
     }
 }
@@ -144,18 +148,19 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_ransac_eval(RansacArgs a, Grid
 // K4: accept iff inlier fraction >= threshold and error < best; parallel form: arg-min over (error, hypothesis),
 // folded into the running best of earlier chunks.
 __global__ void __launch_bounds__(1024) k_ransac_select(RansacArgs a, const int* __restrict__ survivors, const int* __restrict__ count,
-                                                        const float* __restrict__ poses, const float* __restrict__ err,
-                                                        const int* __restrict__ inl, rtr_pose_result* __restrict__ res) {
+                                                        const float* __restrict__ poses, int split, const double* __restrict__ psum,
+                                                        const int* __restrict__ pcnt, rtr_pose_result* __restrict__ res) {
     __shared__ float s_err[32];
     __shared__ long long s_h[32];
     __shared__ int s_t[32];
     int n = *count;
     float be = FLT_MAX; long long bh = -1; int bt = -1;
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        int c = inl[t];
+        double S = 0; int c = 0;
+        for (int p = 0; p < split; ++p) { S += psum[(size_t)t * split + p]; c += pcnt[(size_t)t * split + p]; }
         float frac = __fdiv_rn((float)c, (float)a.ns);
         if (frac >= a.inlier_fraction) {
-            float e = err[t];
+            float e = c > 0 ? (float)(S / (double)c) : FLT_MAX;
             long long h = a.h_base + survivors[t];
             if (e < be || (e == be && (bh < 0 || h < bh))) { be = e; bh = h; bt = t; }
         }
@@ -178,8 +183,10 @@ __global__ void __launch_bounds__(1024) k_ransac_select(RansacArgs a, const int*
         res->evaluated += n;
         // strict "error < lowest_error" with lowest_error starting at FLT_MAX, sequential in h == lexicographic min
         if (bh >= 0 && be < FLT_MAX && (res->hypothesis < 0 || be < res->fitness || (be == res->fitness && bh < res->hypothesis))) {
+            int c = 0;
+            for (int p = 0; p < split; ++p) c += pcnt[(size_t)bt * split + p];
             for (int i = 0; i < 16; ++i) res->pose[i] = poses[(size_t)bt * 16 + i];
-            res->fitness = be; res->inliers = inl[bt]; res->hypothesis = bh; res->converged = 1;
+            res->fitness = be; res->inliers = c; res->hypothesis = bh; res->converged = 1;
         }
     }
 }
@@ -206,11 +213,14 @@ int rtr_ransac_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_ransac_params* p, r
     if (int e = rtr_get_grid(tgt, p->max_correspondence_distance, &g)) return e;
     const long long CHUNK = 1 << 20;
     int cap = (int)std::min<long long>(CHUNK, h1 - h0);
-    int *survivors = nullptr, *count = nullptr, *inl = nullptr; float *poses = nullptr, *err = nullptr;
+    // slices of the source per surviving hypothesis: ~2048 points each, fewer when the partial arrays would get large
+    int split = std::max(1, std::min(16, (src->n + 2047) / 2048));
+    while (split > 1 && (long long)cap * split > (1LL << 22)) split /= 2;
+    int *survivors = nullptr, *count = nullptr, *pcnt = nullptr; float* poses = nullptr; double* psum = nullptr;
     if (int e = dev_alloc(ctx, &survivors, cap, "ransac")) return e;
     if (int e = dev_alloc(ctx, &count, 1, "ransac")) return e;
-    if (int e = dev_alloc(ctx, &inl, cap, "ransac")) return e;
-    if (int e = dev_alloc(ctx, &err, cap, "ransac")) return e;
+    if (int e = dev_alloc(ctx, &pcnt, (size_t)cap * split, "ransac")) return e;
+    if (int e = dev_alloc(ctx, &psum, (size_t)cap * split, "ransac")) return e;
     if (int e = dev_alloc(ctx, &poses, (size_t)cap * 16, "ransac")) return e;
     RansacArgs a;
     a.src = src->pts; a.ns = src->n; a.tgt = tgt->pts; a.nt = tgt->n;
@@ -227,13 +237,13 @@ int rtr_ransac_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_ransac_params* p, r
         RTR_LAUNCH_CHECK(ctx, "ransac.sample");
         k_ransac_pose<<<nblk(a.h_count, 64), 64, 0, ctx->stream>>>(a, survivors, count, poses);
         RTR_LAUNCH_CHECK(ctx, "ransac.pose");
-        int grid = std::min(a.h_count, ctx->sm_count * 8);
-        k_ransac_eval<<<grid, EVAL_THREADS, 0, ctx->stream>>>(a, v, count, poses, err, inl);
+        int grid = (int)std::min<long long>((long long)a.h_count * split, ctx->sm_count * 8);
+        k_ransac_eval<<<grid, EVAL_THREADS, 0, ctx->stream>>>(a, v, count, poses, split, psum, pcnt);
         RTR_LAUNCH_CHECK(ctx, "ransac.eval");
-        k_ransac_select<<<1, 1024, 0, ctx->stream>>>(a, survivors, count, poses, err, inl, d_result);
+        k_ransac_select<<<1, 1024, 0, ctx->stream>>>(a, survivors, count, poses, split, psum, pcnt, d_result);
         RTR_LAUNCH_CHECK(ctx, "ransac.select");
     }
-    dev_free(ctx, survivors); dev_free(ctx, count); dev_free(ctx, inl); dev_free(ctx, err); dev_free(ctx, poses);
+    dev_free(ctx, survivors); dev_free(ctx, count); dev_free(ctx, pcnt); dev_free(ctx, psum); dev_free(ctx, poses);
     return 0;
 }
 
@@ -339,6 +349,76 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_corr(GridView g, float4* __
     }
 }
 
+// Small sources (repo clouds): one WARP per source point — the lanes share the candidate scan, so the per-iteration
+// latency is set by ~9 range steps instead of ~50 dependent loads.  Each warp walks a strided list of queries and keeps
+// the 17 sums in lane 0; warps are then folded through shared memory.
+#define ICPW_WARPS 8
+__global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_corr_warp(GridView g, float4* __restrict__ cur, int n, const IcpState* __restrict__ st,
+                                                                   double dmax2, float prune2, double* __restrict__ partials) {
+    __shared__ float m[16];
+    __shared__ double red[ICPW_WARPS][ICP_NSUM];
+    if (st->done) return;
+    int have = st->have_step;
+    if (threadIdx.x < 16) m[threadIdx.x] = st->step[threadIdx.x];
+    __syncthreads();
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int nwarps = gridDim.x * ICPW_WARPS;
+    double acc[ICP_NSUM];
+#pragma unroll
+    for (int k = 0; k < ICP_NSUM; ++k) acc[k] = 0.0;
+    for (int i = blockIdx.x * ICPW_WARPS + warp; i < n; i += nwarps) {
+        float4 q = cur[i];
+        if (have) { q = xform(m, q); if (lane == 0) cur[i] = q; }
+        int b; float d2; float4 t;
+        grid_nearest_warp(g, q.x, q.y, q.z, prune2, lane, b, d2, t);
+        if (lane == 0 && b >= 0 && (double)d2 <= dmax2) {
+            double sx = q.x, sy = q.y, sz = q.z, tx = t.x, ty = t.y, tz = t.z;
+            acc[0] += sx; acc[1] += sy; acc[2] += sz; acc[3] += tx; acc[4] += ty; acc[5] += tz;
+            acc[6] += sx * tx; acc[7] += sx * ty; acc[8] += sx * tz;
+            acc[9] += sy * tx; acc[10] += sy * ty; acc[11] += sy * tz;
+            acc[12] += sz * tx; acc[13] += sz * ty; acc[14] += sz * tz;
+            acc[15] += (double)d2; acc[16] += 1.0;
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < ICP_NSUM; ++k) red[warp][k] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < ICP_NSUM) {
+        double v = 0;
+#pragma unroll
+        for (int w = 0; w < ICPW_WARPS; ++w) v += red[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * ICP_NSUM + threadIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_fitness_warp(GridView g, const float4* __restrict__ src, int n, const IcpState* __restrict__ st,
+                                                                      double* __restrict__ partials) {
+    __shared__ float m[16];
+    __shared__ double red[ICPW_WARPS][2];
+    if (st->skipped) return;
+    if (threadIdx.x < 16) m[threadIdx.x] = st->final_[threadIdx.x];
+    __syncthreads();
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int nwarps = gridDim.x * ICPW_WARPS;
+    double s = 0, c = 0;
+    for (int i = blockIdx.x * ICPW_WARPS + warp; i < n; i += nwarps) {
+        float4 q = xform(m, __ldg(src + i));
+        int b; float d2; float4 t;
+        grid_nearest_warp(g, q.x, q.y, q.z, FLT_MAX, lane, b, d2, t);
+        if (lane == 0 && b >= 0) { s += (double)d2; c += 1.0; }
+    }
+    if (lane == 0) { red[warp][0] = s; red[warp][1] = c; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double v = 0;
+#pragma unroll
+        for (int w = 0; w < ICPW_WARPS; ++w) v += red[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * 2 + threadIdx.x] = v;
+    }
+}
+
 // TransformationEstimationSVD + final = step * final + DefaultConvergenceCriteria.  One CTA of 17 warps: warp k reduces
 // sum k over the per-CTA partials in a fixed order.
 __global__ void __launch_bounds__(ICP_NSUM * 32) k_icp_solve(const double* __restrict__ partials, int nparts, IcpState* __restrict__ st,
@@ -439,7 +519,8 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     int nb = std::max(nblk(n, ICP_THREADS), 1);
     if (int e = dev_alloc(ctx, &cur, n, "icp")) return e;
     if (int e = dev_alloc(ctx, &st, 1, "icp")) return e;
-    if (int e = dev_alloc(ctx, &partials, (size_t)nb * ICP_NSUM, "icp")) return e;
+    const int nbw = std::max(1, std::min(nblk(n, ICPW_WARPS), ctx->sm_count * 8));    // CTAs of the warp-per-query kernels
+    if (int e = dev_alloc(ctx, &partials, (size_t)std::max(nb, nbw) * ICP_NSUM, "icp")) return e;
     k_icp_init<<<nb, ICP_THREADS, 0, ctx->stream>>>(src->pts, n, d_init_pose16, init_from_result ? d_result : nullptr, cur, st);
     RTR_LAUNCH_CHECK(ctx, "icp.init");
     const float4* src_pts = src->pts;
@@ -471,17 +552,22 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     // search radius for pruning: the cap rounded UP in float so no candidate with d2 <= dmax2 is ever skipped
     float prune2 = FLT_MAX;
     if (p->max_correspondence_distance > 0.f) { prune2 = (float)dmax2; if ((double)prune2 < dmax2) prune2 = nextafterf(prune2, FLT_MAX); }
+    // small sources: one warp per query (latency), large ones: one thread per query in cell order (throughput)
+    const bool warp_per_query = n < 65536;
+    const int nparts = warp_per_query ? nbw : nb;
     if (n >= 1 && tgt->n >= 1) {
         for (int it = 0; it < p->max_iterations; ++it) {
-            k_icp_corr<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, cur, n, st, dmax2, prune2, partials);
+            if (warp_per_query) k_icp_corr_warp<<<nbw, ICPW_WARPS * 32, 0, ctx->stream>>>(v, cur, n, st, dmax2, prune2, partials);
+            else k_icp_corr<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, cur, n, st, dmax2, prune2, partials);
             RTR_LAUNCH_CHECK(ctx, "icp.corr");
-            k_icp_solve<<<1, ICP_NSUM * 32, 0, ctx->stream>>>(partials, nb, st, p->max_iterations, p->force_iterations, p->mse_threshold_absolute);
+            k_icp_solve<<<1, ICP_NSUM * 32, 0, ctx->stream>>>(partials, nparts, st, p->max_iterations, p->force_iterations, p->mse_threshold_absolute);
             RTR_LAUNCH_CHECK(ctx, "icp.solve");
         }
     }
-    k_icp_fitness<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, src_pts, n, st, partials);
+    if (warp_per_query) k_icp_fitness_warp<<<nbw, ICPW_WARPS * 32, 0, ctx->stream>>>(v, src_pts, n, st, partials);
+    else k_icp_fitness<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, src_pts, n, st, partials);
     RTR_LAUNCH_CHECK(ctx, "icp.fitness");
-    k_icp_finish<<<1, 64, 0, ctx->stream>>>(partials, nb, st, d_result, init_from_result);
+    k_icp_finish<<<1, 64, 0, ctx->stream>>>(partials, nparts, st, d_result, init_from_result);
     RTR_LAUNCH_CHECK(ctx, "icp.finish");
     dev_free(ctx, cur); dev_free(ctx, src2); dev_free(ctx, st); dev_free(ctx, partials);
     return 0;

@@ -300,3 +300,35 @@ def test_swapped_direction_and_transform(api, gpu_ctx, orc, clouds):
     cm.transform(gt)
     assert np.array_equal(cm.download(), orc.transform(model, gt))
     cm.free(); cs.free()
+
+
+# ------------------------------------------------------------------ tensor-core descriptor matching
+def test_match_tensor_core_path_is_exact(api, gpu_ctx, orc, clouds, monkeypatch):
+    """tcgen05 prefilter + exact re-rank + certificate (csrc/match_tc.cu) must return the oracle's indices and distances."""
+    m, s = clouds("chair1"), clouds("mcloud")
+    fm = orc.fpfh(m, orc.normals(m, 0.05), 0.10)
+    fs = orc.fpfh(s, orc.normals(s, 0.05), 0.10)
+    rng = np.random.default_rng(9)
+    cases = [(fm, fs), (fs, fm),
+             (rng.random((300, 33)).astype(np.float32) * 40, rng.random((1000, 33)).astype(np.float32) * 40),
+             (fm[:130], fs[:129]), (fm[:5], fs[:3])]
+    dup = fs.copy(); dup[100] = dup[7]; dup[900] = dup[7]            # exact ties -> lowest index first
+    cases.append((fs[:64], dup))
+    for fa, fb in cases:
+        oi, od = orc.match_features(fa, fb, 5)
+        monkeypatch.setenv("RTR_MATCH_TC", "1")
+        ms, st = api.match_raw(gpu_ctx, fa, fb, 5)
+        assert st["redo_rows"] >= 0                                   # the tensor-core path ran
+        assert np.array_equal(st["idx"], oi)
+        assert np.array_equal(np.nan_to_num(st["dist"], nan=-1.0), np.nan_to_num(od, nan=-1.0))
+        assert st["redo_rows"] <= max(2, len(fa) // 10), st["redo_rows"]      # the certificate holds for nearly every row
+        monkeypatch.setenv("RTR_MATCH_TC", "0")
+        ms, st0 = api.match_raw(gpu_ctx, fa, fb, 5)
+        assert st0["redo_rows"] == -1 and np.array_equal(st0["idx"], oi)
+    # a NaN signature (point without neighbours) matches nothing and is matched by nothing
+    fa, fb = fm[:200].copy(), fs.copy()
+    fa[3] = np.nan; fb[11] = np.nan
+    monkeypatch.setenv("RTR_MATCH_TC", "1")
+    oi, od = orc.match_features(fa, fb, 5)
+    ms, st = api.match_raw(gpu_ctx, fa, fb, 5)
+    assert np.array_equal(st["idx"], oi) and np.all(st["idx"][3] == -1) and not np.any(st["idx"] == 11)

@@ -98,7 +98,8 @@ def main():
         ms, stats = api.match_raw(ctx, fa, fb, 5, reps=2)
         flop = 2.0 * M * N * 33
         out = {"config": "configs[3] descriptor matching", "M": M, "N": N, "k": 5, "ms": ms, "pairs_per_s": M * N / (ms * 1e-3),
-               "algorithmic_tflops": flop / (ms * 1e-3) / 1e12, "stats": stats}
+               "algorithmic_tflops": flop / (ms * 1e-3) / 1e12,
+               "rows_redone_exactly": stats["redo_rows"], "splits": stats["splits"], "observed_err_over_norms": stats["observed_err_over_norms"], "idx0": stats["idx"][0].tolist(), "dist0": stats["dist"][0].tolist()}
         print(json.dumps(out), flush=True)
 
     if "ransac" not in args.skip:
