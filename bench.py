@@ -170,6 +170,8 @@ def main():
         return
     args.warmup = max(args.warmup, 3)
 
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner there)
     import torch
     import torch.distributed as td
     from realtime_robot_b200 import api, dist, synth

@@ -74,6 +74,21 @@ typedef struct rtr_register_params {
     rtr_icp_params    icp;
 } rtr_register_params;
 
+/* The reference's own descriptor path (key_point.h, matching.h, function.h); literals are the reference's.
+ * The quirk_* flags reproduce as-committed behaviour and default to 0. */
+typedef struct rtr_native_params {
+    float resolution;              /* 0.01  key_point.h:112,251; matching.h:122 */
+    float occ_half;                /* 0.1   KeyPoint::getOccupiedGrid f_adjust, key_point.h:112 */
+    float tdf_half;                /* 0.15  KeyPoint::get_TSDF f_adjust, key_point.h:251 (dim = 30) */
+    float pair_gate;               /* 3     get_Distance(...) < 3, RealTimeRobot.cpp:83 */
+    float consensus_distance;      /* 0.15  function.h:78 */
+    float consensus_score;         /* 100   function.h:78 */
+    int   quirk_skip_first_voxel;  /* B#5:  key_point.h:298 (i = 1), matching.h:179 (p = 1) */
+    int   quirk_running_score;     /* B#4:  distance_temp not reset between angles, matching.h:141,187,189 */
+    int   quirk_integer_screens;   /* B#9, B#10: float(2/3) == 0 and integer division, function.h:161,167,174 */
+    int   pad_;
+} rtr_native_params;
+
 /* fixed 128-byte record: the unit of the multi-GPU all-gather. */
 typedef struct rtr_pose_result {
     float     pose[16];        /* column-major source->target */
@@ -209,6 +224,29 @@ int rtr_tdf_batch(rtr_context* ctx, const int* host_occ, const int* host_occ_off
 /* Same with device pointers, asynchronous on the context stream. */
 int rtr_tdf_batch_dev(rtr_context* ctx, const int* dev_occ, const int* dev_occ_offsets, int n_grids,
                       int dim, float* dev_tdf_out);
+
+/* ---- the reference's own pipeline, batched on the device ---- */
+void rtr_native_default_params(rtr_native_params* p);
+
+/* KeyPoint::getOccupiedGrid + KeyPoint::get_TSDF for every keypoint of a cloud in one go (key_point.h:112-161,251-318;
+ * loops RealTimeRobot.cpp:52-69).  host_kp_xyz1: n_kp x 16 B keypoint coordinates (ModelPoint::key_coordinates).
+ * Outputs (host, each optional): number[n_kp] = Occupiedgrid.Number; occ_count[n_kp] = points in the +-occ_half box;
+ * tdf[n_kp x 27000] = KeyPoint::grid_value; voxel_count[n_kp] = triples handed to the TDF kernel. */
+int rtr_native_keypoint_descriptors(rtr_cloud* c, const float* host_kp_xyz1, int n_kp, const rtr_native_params* p,
+                                    int* host_number, int* host_occ_count, float* host_tdf, int* host_voxel_count);
+
+/* get_Distance (matching.h:122-222) for all Km x Ks pairs: the 36-step yaw sweep of every scan keypoint's occupancy
+ * cloud against every model keypoint's TDF.  Outputs (host, Km x Ks, model-major): score, best step, 4x4 transform. */
+int rtr_native_pair_scores(rtr_cloud* model, const float* host_model_kp_xyz1, int km, rtr_cloud* scan,
+                           const float* host_scan_kp_xyz1, int ks, const rtr_native_params* p, float* host_score,
+                           int* host_best_step, float* host_transform16);
+
+/* main() as the reference intends it (RealTimeRobot.cpp:39-105): Harris corners of both clouds -> occupancy / TDF
+ * descriptors -> all-pairs sweep -> match_by_* screens -> exhaustive Ransac (function.h:35-109).  The pose maps the SCAN
+ * into the model frame (main applies it to `cloud`).  result: inliers = consensus size, hypothesis = winning pair in
+ * screening order (-1 if none: pose = identity, where the reference returns an uninitialised matrix, Appendix B#2),
+ * evaluated = screened pairs, fitness = the winner's sweep score. */
+int rtr_native_register(rtr_cloud* model, rtr_cloud* scan, const rtr_native_params* p, rtr_pose_result* host_result);
 
 #ifdef __cplusplus
 }

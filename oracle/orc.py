@@ -8,7 +8,7 @@ import subprocess
 
 import numpy as np
 
-from realtime_robot_b200.params import IcpParams, PoseResult, RansacParams, RegisterParams
+from realtime_robot_b200.params import IcpParams, NativeParams, PoseResult, RansacParams, RegisterParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -32,6 +32,9 @@ def lib():
         _LIB.orc_harris3d.restype = C.c_int
         _LIB.orc_hypothesis.restype = C.c_int
         _LIB.orc_get_threads.restype = C.c_int
+        _LIB.orc_native_pair_score.restype = C.c_float
+        _LIB.orc_native_occupancy.restype = C.c_int
+        _LIB.orc_native_tdf_voxels.restype = C.c_int
     return _LIB
 
 
@@ -165,4 +168,42 @@ def register(model, scene, params: RegisterParams) -> PoseResult:
     model, scene = _f(model), _f(scene)
     res = PoseResult()
     lib().orc_register(_p(model), len(model), _p(scene), len(scene), C.byref(params), C.byref(res))
+    return res
+
+
+# ------------------------------------------------------------------ reference-native descriptor path (oracle/native.cpp)
+def native_keypoint_descriptors(xyz1, kp_xyz1, params: NativeParams, with_tdf=True):
+    xyz1, kp = _f(xyz1), _f(kp_xyz1)
+    n = len(kp)
+    number, count = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    tdfs = np.zeros((n, 27000), np.float32)
+    vox = np.zeros(n, np.int32)
+    occ = []
+    idx = np.zeros(max(len(xyz1), 1), np.int32)
+    tri = np.zeros((32768, 3), np.int32)
+    for k in range(n):
+        num = C.c_int()
+        c = lib().orc_native_occupancy(_p(xyz1), len(xyz1), _p(kp[k:k + 1]), C.byref(params), _p(idx, C.c_int), len(xyz1), C.byref(num))
+        number[k], count[k] = num.value, c
+        pts = np.ascontiguousarray(xyz1[idx[:c]])
+        occ.append(pts)
+        if with_tdf:
+            nt = lib().orc_native_tdf_voxels(_p(pts), c, _p(kp[k:k + 1]), C.byref(params), _p(tri, C.c_int), 32768)
+            vox[k] = nt
+            tdfs[k] = tdf(tri[:nt], int(params.tdf_half / params.resolution * 2))
+    return number, count, tdfs, vox, occ
+
+
+def native_pair_score(model_kp, model_tdf, scan_occ, scan_kp, params: NativeParams):
+    mk, sk, occ, t = _f(model_kp).reshape(1, 4), _f(scan_kp).reshape(1, 4), _f(scan_occ).reshape(-1, 4), _f(model_tdf)
+    bs = C.c_int()
+    T = np.zeros(16, np.float32)
+    sc = lib().orc_native_pair_score(_p(mk), _p(t), _p(occ), len(occ), _p(sk), C.byref(params), C.byref(bs), _p(T))
+    return float(sc), bs.value, T.reshape(4, 4).T.copy()
+
+
+def native_register(model, model_kp, scan, scan_kp, params: NativeParams) -> PoseResult:
+    model, scan, mk, sk = _f(model), _f(scan), _f(model_kp).reshape(-1, 4), _f(scan_kp).reshape(-1, 4)
+    res = PoseResult()
+    lib().orc_native_register(_p(model), len(model), _p(mk), len(mk), _p(scan), len(scan), _p(sk), len(sk), C.byref(params), C.byref(res))
     return res

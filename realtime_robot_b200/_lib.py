@@ -5,7 +5,7 @@ There is no CPU fallback: if the library is missing or cannot be loaded, importi
 import ctypes as C
 import os
 
-from .params import IcpParams, PoseResult, RansacParams, RegisterParams
+from .params import IcpParams, NativeParams, PoseResult, RansacParams, RegisterParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librtr.so")
@@ -17,7 +17,8 @@ EXPORTS = [
     "rtr_context_launches", "rtr_profile_begin", "rtr_profile_end", "rtr_cloud_reset", "rtr_event_record", "rtr_event_elapsed_ms", "rtr_cloud_upload", "rtr_cloud_from_device",
     "rtr_cloud_free", "rtr_cloud_size", "rtr_cloud_transform", "rtr_cloud_download", "rtr_radius_neighbors", "rtr_nearest",
     "rtr_normals", "rtr_harris3d", "rtr_fpfh", "rtr_match_features", "rtr_match_features_raw", "rtr_match_last_stats", "rtr_ransac_prerejective", "rtr_icp", "rtr_register",
-    "rtr_register_host", "ComputeTDFWithCuda", "rtr_tdf_batch", "rtr_tdf_batch_dev",
+    "rtr_register_host", "ComputeTDFWithCuda", "rtr_tdf_batch", "rtr_tdf_batch_dev", "rtr_native_default_params", "rtr_native_keypoint_descriptors",
+    "rtr_native_pair_scores", "rtr_native_register",
 ]
 
 
@@ -69,6 +70,10 @@ def lib():
         L.rtr_tdf_batch.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
         L.rtr_tdf_batch_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
         L.rtr_default_register_params.argtypes = [C.POINTER(RegisterParams)]
+        L.rtr_native_default_params.argtypes = [C.POINTER(NativeParams)]
+        L.rtr_native_keypoint_descriptors.argtypes = [vp, vp, C.c_int, C.POINTER(NativeParams), vp, vp, vp, vp]
+        L.rtr_native_pair_scores.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, C.POINTER(NativeParams), vp, vp, vp]
+        L.rtr_native_register.argtypes = [vp, vp, C.POINTER(NativeParams), C.POINTER(PoseResult)]
         _LIB = L
     return _LIB
 

@@ -10,8 +10,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .params import (IcpParams, PoseResult, RansacParams, RegisterParams, default_register_params,  # noqa: F401
-                     pose_to_colmajor)
+from .params import (IcpParams, NativeParams, PoseResult, RansacParams, RegisterParams, default_native_params,  # noqa: F401
+                     default_register_params, pose_to_colmajor)
 
 
 def _f32(a, cols=None):
@@ -219,3 +219,36 @@ def match_raw(ctx: Context, fa, fb, k: int, reps: int = 1):
     st = (C.c_int * 3)()
     _lib.lib().rtr_match_last_stats(ctx._h, st)
     return best, {"idx": idx, "dist": dist, "redo_rows": int(st[0]), "splits": int(st[1]), "observed_err_over_norms": st[2] * 1e-9}
+
+
+# ------------------------------------------------------------------ the reference's own descriptor path
+def native_keypoint_descriptors(cloud: Cloud, kp_xyz1, params: NativeParams, with_tdf: bool = True):
+    """KeyPoint::getOccupiedGrid + KeyPoint::get_TSDF for all keypoints: (Number, points in box, TDF [n,27000], voxels)."""
+    kp = _f32(kp_xyz1, 4)
+    n = len(kp)
+    number = np.zeros(n, dtype=np.int32)
+    count = np.zeros(n, dtype=np.int32)
+    tdf = np.zeros((n, 27000), dtype=np.float32) if with_tdf else None
+    vox = np.zeros(n, dtype=np.int32) if with_tdf else None
+    _lib.check("rtr_native_keypoint_descriptors", _lib.lib().rtr_native_keypoint_descriptors(
+        cloud._h, _ptr(kp) if n else None, n, C.byref(params), _ptr(number), _ptr(count), _ptr(tdf), _ptr(vox)))
+    return number, count, tdf, vox
+
+
+def native_pair_scores(model: Cloud, model_kp, scan: Cloud, scan_kp, params: NativeParams):
+    """get_Distance for all pairs: (score [km,ks], best step [km,ks], transforms [km,ks,4,4] row-indexed)."""
+    mk, sk = _f32(model_kp, 4), _f32(scan_kp, 4)
+    km, ks = len(mk), len(sk)
+    score = np.zeros((km, ks), dtype=np.float32)
+    best = np.zeros((km, ks), dtype=np.int32)
+    tr = np.zeros((km, ks, 16), dtype=np.float32)
+    _lib.check("rtr_native_pair_scores", _lib.lib().rtr_native_pair_scores(
+        model._h, _ptr(mk) if km else None, km, scan._h, _ptr(sk) if ks else None, ks, C.byref(params), _ptr(score), _ptr(best), _ptr(tr)))
+    return score, best, tr.reshape(km, ks, 4, 4).transpose(0, 1, 3, 2).copy()
+
+
+def native_register(model: Cloud, scan: Cloud, params: NativeParams) -> PoseResult:
+    """main() of the reference as intended: Harris -> occupancy / TDF -> yaw sweep -> screens -> exhaustive consensus."""
+    res = PoseResult()
+    _lib.check("rtr_native_register", _lib.lib().rtr_native_register(model._h, scan._h, C.byref(params), C.byref(res)))
+    return res

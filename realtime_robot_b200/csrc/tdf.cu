@@ -15,11 +15,12 @@
 
 // `extra`: also write voxel index dim^3 when it is < 27000 — the reference's bound check is `>` not `>=`
 // (kernel.cu:13), so thread dim^3 computes and stores one more element inside the 27000-float buffer.
-__global__ void __launch_bounds__(TDF_THREADS) k_tdf_batch(const int* __restrict__ occ, const int* __restrict__ occ_offsets, int dim,
+__global__ void __launch_bounds__(TDF_THREADS) k_tdf_batch(const int* __restrict__ occ, const int* __restrict__ occ_begin,
+                                                           const int* __restrict__ occ_end, int dim,
                                                            int nvox_write, size_t out_stride, float* __restrict__ out) {
     __shared__ int tile[TDF_TILE * 3];
     int g = blockIdx.y;
-    int o0 = occ_offsets[g], o1 = occ_offsets[g + 1];
+    int o0 = occ_begin[g], o1 = occ_end[g];
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     int d2 = dim * dim;
     int z = v / d2, y = (v - z * d2) / dim, x = v - z * d2 - y * dim;
@@ -41,7 +42,18 @@ __global__ void __launch_bounds__(TDF_THREADS) k_tdf_batch(const int* __restrict
 static int tdf_launch(rtr_context* ctx, const int* d_occ, const int* d_off, int n_grids, int dim, int nvox_write, size_t out_stride, float* d_out) {
     if (n_grids <= 0) return 0;
     dim3 grid((nvox_write + TDF_THREADS - 1) / TDF_THREADS, n_grids);
-    k_tdf_batch<<<grid, TDF_THREADS, 0, ctx->stream>>>(d_occ, d_off, dim, nvox_write, out_stride, d_out);
+    k_tdf_batch<<<grid, TDF_THREADS, 0, ctx->stream>>>(d_occ, d_off, d_off + 1, dim, nvox_write, out_stride, d_out);
+    RTR_LAUNCH_CHECK(ctx, "tdf");
+    return 0;
+}
+
+// per-grid [begin, end) triple ranges instead of a prefix array (native.cu: fixed-stride voxel lists per keypoint);
+// output stride 27000 floats = KeyPoint::grid_value
+int rtr_tdf_launch_ranges(rtr_context* ctx, const int* d_occ, const int* d_begin, const int* d_end, int n_grids, int dim, float* d_out) {
+    if (n_grids <= 0) return 0;
+    int nv = dim * dim * dim;
+    dim3 grid((nv + TDF_THREADS - 1) / TDF_THREADS, n_grids);
+    k_tdf_batch<<<grid, TDF_THREADS, 0, ctx->stream>>>(d_occ, d_begin, d_end, dim, nv, (size_t)RTR_TDF_VOXELS, d_out);
     RTR_LAUNCH_CHECK(ctx, "tdf");
     return 0;
 }

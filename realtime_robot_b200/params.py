@@ -41,6 +41,20 @@ class PoseResult(C.Structure):
 assert C.sizeof(PoseResult) == 128, C.sizeof(PoseResult)
 
 
+class NativeParams(C.Structure):
+    """rtr_native_params: the reference's own descriptor path (key_point.h / matching.h / function.h literals)."""
+    _fields_ = [("resolution", C.c_float), ("occ_half", C.c_float), ("tdf_half", C.c_float), ("pair_gate", C.c_float),
+                ("consensus_distance", C.c_float), ("consensus_score", C.c_float), ("quirk_skip_first_voxel", C.c_int),
+                ("quirk_running_score", C.c_int), ("quirk_integer_screens", C.c_int), ("pad_", C.c_int)]
+
+
+def default_native_params() -> NativeParams:
+    p = NativeParams()
+    p.resolution, p.occ_half, p.tdf_half = 0.01, 0.1, 0.15
+    p.pair_gate, p.consensus_distance, p.consensus_score = 3.0, 0.15, 100.0
+    return p
+
+
 def default_register_params() -> RegisterParams:
     """Defaults of include/rtr.h (reference literals where the reference has the stage, PCL-tutorial values otherwise)."""
     p = RegisterParams()

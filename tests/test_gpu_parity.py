@@ -332,3 +332,65 @@ def test_match_tensor_core_path_is_exact(api, gpu_ctx, orc, clouds, monkeypatch)
     oi, od = orc.match_features(fa, fb, 5)
     ms, st = api.match_raw(gpu_ctx, fa, fb, 5)
     assert np.array_equal(st["idx"], oi) and np.all(st["idx"][3] == -1) and not np.any(st["idx"] == 11)
+
+
+# ------------------------------------------------------------------ the reference's own descriptor path (native.cu)
+def _native_case(orc, clouds, which):
+    if which == "self":
+        model = clouds("chair1")
+        scan = synth.apply(synth.rigid(0, 0, 40, (0.3, -0.2, 0.0), about=(0.2, 0.2, 0.0)), model)
+    else:
+        model, scan = clouds("chair1"), clouds("T0_m8111")           # the pair main() loads (RealTimeRobot.cpp:34-35)
+    return model, scan
+
+
+@pytest.mark.parametrize("which", ["self", "main"])
+def test_native_descriptors_and_pair_scores(api, gpu_ctx, orc, clouds, which):
+    from realtime_robot_b200.params import default_native_params
+    model, scan = _native_case(orc, clouds, which)
+    cm, cs = api.Cloud(gpu_ctx, model), api.Cloud(gpu_ctx, scan)
+    mk = orc.harris3d(model, orc.normals(model, 0.05), 0.05, 0.01)[2]
+    sk = orc.harris3d(scan, orc.normals(scan, 0.05), 0.05, 0.01)[2]
+    for quirks in (0, 1):
+        p = default_native_params()
+        p.quirk_skip_first_voxel = p.quirk_running_score = quirks
+        number, count, tdf, vox = api.native_keypoint_descriptors(cm, mk, p)
+        onum, ocnt, otdf, ovox, oocc = orc.native_keypoint_descriptors(model, mk, p)
+        assert np.array_equal(number, onum) and np.array_equal(count, ocnt) and np.array_equal(vox, ovox)
+        assert np.array_equal(tdf, otdf)                                  # integer voxel work: bit-exact
+        snum, scnt, _, _ = api.native_keypoint_descriptors(cs, sk, p, with_tdf=False)
+        osnum, oscnt, _, _, osocc = orc.native_keypoint_descriptors(scan, sk, p, with_tdf=False)
+        assert np.array_equal(snum, osnum) and np.array_equal(scnt, oscnt)
+        score, best, T = api.native_pair_scores(cm, mk, cs, sk, p)
+        for k in range(len(mk)):
+            for s in range(len(sk)):
+                o = orc.native_pair_score(mk[k], otdf[k], osocc[s], sk[s], p)
+                assert score[k, s] == np.float32(o[0]) and best[k, s] == o[1], (k, s, score[k, s], o[0], best[k, s], o[1])
+                assert np.array_equal(T[k, s], o[2])
+    cm.free(); cs.free()
+
+
+def test_native_register(api, gpu_ctx, orc, clouds):
+    from realtime_robot_b200.params import default_native_params
+    for which, gate in (("self", 30.0), ("main", 3.0), ("self", 3.0)):
+        model, scan = _native_case(orc, clouds, which)
+        cm, cs = api.Cloud(gpu_ctx, model), api.Cloud(gpu_ctx, scan)
+        p = default_native_params()
+        p.pair_gate = gate
+        g = api.native_register(cm, cs, p)
+        # the oracle takes the GPU's own Harris corners (that stage has its own parity test)
+        cm.normals(0.05); cs.normals(0.05)
+        mk, sk = cm.harris3d(0.05, 0.01)[2], cs.harris3d(0.05, 0.01)[2]
+        o = orc.native_register(model, mk, scan, sk, p)
+        assert (g.hypothesis, g.inliers, g.evaluated, g.converged) == (o.hypothesis, o.inliers, o.evaluated, o.converged)
+        assert (g.n_keypoints_src, g.n_keypoints_tgt) == (len(mk), len(sk))
+        assert np.array_equal(g.matrix(), o.matrix()) and (g.fitness == o.fitness)
+        if which == "self" and gate == 30.0:
+            assert g.converged == 1 and g.inliers >= 4
+        cm.free(); cs.free()
+    # degenerate inputs: no keypoints at all -> identity, hypothesis -1 (the reference returns an uninitialised matrix, B#2)
+    flat = np.ones((400, 4), np.float32); flat[:, :2] = np.random.default_rng(0).random((400, 2)).astype(np.float32); flat[:, 2] = 0.5
+    cf = api.Cloud(gpu_ctx, flat)
+    r = api.native_register(cf, cf, default_native_params())
+    assert r.hypothesis == -1 and r.n_keypoints_src == 0 and np.array_equal(r.matrix(), np.eye(4, dtype=np.float32))
+    cf.free()
