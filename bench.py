@@ -189,6 +189,10 @@ def main():
     pool = ThreadPoolExecutor(max_workers=len(MODELS))
     p = default_register_params()
     hbm_peak, bf16_peak, peak_src = peaks()
+    try:
+        ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        ncu_traffic = {}
 
     # host clouds in pinned memory (e2e leg) and resident device clouds (value leg)
     def pinned(a):
@@ -363,15 +367,46 @@ def main():
             ctx.profile_begin(); api.icp(a, b, q.icp, init); pr = ctx.profile_end()
             k_ms = pr["icp.corr"][1] / pr["icp.corr"][0]
             ach = n_src * 32 / (k_ms * 1e-3) / 1e9
+            traffic = ncu_traffic.get("icp.corr@" + label)
             icp_out[label] = {"iters_per_s": 50 * reps / (ms * 1e-3), "ms_per_icp": ms / reps, "n_source": n_src,
                               "pose_err_vs_ground_truth": float(np.abs(res.matrix() - (gt if label == "model_to_scan" else np.linalg.inv(gt))).max()),
                               "fitness": float(res.fitness),
                               "roofline": {"kernel": "icp.corr", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                                           "frac": ach / hbm_peak, "traffic": None, "avg_launch_ms": k_ms,
+                                           "frac": ach / hbm_peak, "traffic": traffic, "avg_launch_ms": k_ms,
                                            "algorithmic_bytes_per_launch": n_src * 32, "peak_source": peak_src},
                               "kernel_ms": {k: round(v[1], 4) for k, v in sorted(pr.items(), key=lambda kv: -kv[1][1])[:6]}}
         cm.free(); cs.free()
 
+    # ---- the reference's own descriptor path (occupancy / TDF / 36-step yaw sweep / exhaustive consensus) on the pair main() loads
+    native_out = None
+    if rank == 0:
+        try:
+            from realtime_robot_b200.params import default_native_params
+            nm_, ns_ = load_cloud("chair1"), to_xyz1(read_pcd_xyz(os.path.join(ROOT, "data", "clouds", "T0_m8111.pcd")))
+            cmn, csn = api.Cloud(ctx, nm_), api.Cloud(ctx, ns_)
+            npar = default_native_params()
+            for _ in range(3):
+                cmn.reset(); csn.reset(); rn = api.native_register(cmn, csn, npar)
+            reps, ms = 20, 0.0
+            for _ in range(reps):
+                cmn.reset(); csn.reset()
+                ctx.record(6); rn = api.native_register(cmn, csn, npar); ctx.record(7)
+                ms += ctx.elapsed_ms(6, 7)
+            native_out = {"workload": "reference-native path, chair1.pcd (model) vs T0_m8111.pcd (scan) as main() loads them: Harris, occupancy, TDF, "
+                                      "7 x 11 pair sweeps x 36 angles, screens, exhaustive consensus", "registrations_per_s": reps / (ms * 1e-3),
+                          "ms_per_registration": ms / reps, "keypoints": [int(rn.n_keypoints_src), int(rn.n_keypoints_tgt)],
+                          "screened_pairs": int(rn.evaluated), "consensus": int(rn.inliers)}
+            if world == 1 and not args.no_cpu_baseline:
+                from oracle import orc
+                orc.build(); orc.set_threads(1)
+                t0 = time.time()
+                mk = orc.harris3d(nm_, orc.normals(nm_, 0.05), 0.05, 0.01)[2]
+                sk = orc.harris3d(ns_, orc.normals(ns_, 0.05), 0.05, 0.01)[2]
+                orc.native_register(nm_, mk, ns_, sk, npar)
+                native_out["cpu_port_1_thread_ms"] = 1e3 * (time.time() - t0)
+            cmn.free(); csn.free()
+        except Exception as e:          # the headline line must survive a failure of an auxiliary section
+            native_out = {"error": repr(e)}
     log("cpu baseline")
     # ---- CPU baseline beside it (rank 0, N = 1): the oracle, one thread, the step's 8 registrations once
     cpu = None
@@ -403,7 +438,7 @@ def main():
                 "gpu_launches": int(launches),
                 "clocks": clocks, "roofline": roofline, "kernel_share": kernel_share, "serialised_device_ms_per_step": round(step_ms, 3),
                 "per_model_device_ms": per_model_ms, "per_model_latency_ms_alone": lat,
-                "cpu_baseline": cpu, "icp_1m": icp_out,
+                "cpu_baseline": cpu, "icp_1m": icp_out, "native_path": native_out,
                 "wall_ms_per_step_incl_l2_flush": 1e3 * wall_res / args.steps,
                 "results": [{"model": m, "fitness": float(r.fitness), "inliers": int(r.inliers), "hypothesis": int(r.hypothesis),
                              "evaluated": int(r.evaluated), "converged": int(r.converged)} for m, r in zip(MODELS, mine)]}

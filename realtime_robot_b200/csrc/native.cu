@@ -21,6 +21,7 @@ int rtr_tdf_launch_ranges(rtr_context* ctx, const int* d_occ, const int* d_begin
 
 #define NAT_THREADS 256
 #define NAT_WORDS 1024          // 32^3 bits
+#define NAT_LIST 4096           // occupied voxels of one sweep angle that fit the shared-memory list
 
 struct NatFrame { double origin[3]; double mn[3]; double res; int depth; unsigned nkeys; };
 
@@ -191,7 +192,9 @@ __global__ void __launch_bounds__(NAT_THREADS) k_native_pair_score(const float4*
     extern __shared__ __align__(16) unsigned char nat_smem[];
     float* tdf = reinterpret_cast<float*>(nat_smem);                         // 27000 floats
     unsigned* bits = reinterpret_cast<unsigned*>(nat_smem + 27000 * 4);     // 1024 words
+    float* list = reinterpret_cast<float*>(nat_smem + 27000 * 4 + NAT_WORDS * 4);   // NAT_LIST floats
     __shared__ float s_step[16];
+    __shared__ int scan[NAT_THREADS];
     int pair = blockIdx.x;
     int k = pair / ks, s = pair - k * ks;
     if (k >= km) return;
@@ -228,26 +231,56 @@ __global__ void __launch_bounds__(NAT_THREADS) k_native_pair_score(const float4*
             if (nat_key(f, p, code)) atomicOr(&bits[code >> 5], 1u << (code & 31u));
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            // float accumulation of grid_value^2 in depth-first voxel order (matching.h:179-189)
-            if (!running) distance_temp = 0.f;
-            int used = 0, seen = 0;
-            for (int w = 0; w < NAT_WORDS; ++w) {
-                unsigned word = bits[w];
+        // All threads enumerate their share of the bitmap (ordered by an exclusive scan of the per-thread bit counts) and
+        // write grid_value^2 of every occupied voxel into a list in depth-first order (-1 marks voxels outside the TDF);
+        // thread 0 then does what must stay sequential: the float accumulation in that order (matching.h:179-189).
+        int total;
+        int pos = nat_prefix(bits, scan, total);
+        const bool fits = total <= NAT_LIST;
+        if (fits) {
+            const int wpt = NAT_WORDS / NAT_THREADS;
+            for (int w = 0; w < wpt; ++w) {
+                unsigned word = bits[threadIdx.x * wpt + w];
                 while (word) {
                     int b = __ffs(word) - 1;
                     word &= word - 1;
-                    if (!(skip_first && seen == 0)) {
-                        unsigned kk[3];
-                        nat_unmorton((unsigned)(w * 32 + b), f.depth, kk);
-                        int cx = nat_index(f, kk[0], 0, resolution), cy = nat_index(f, kk[1], 1, resolution), cz = nat_index(f, kk[2], 2, resolution);
-                        if (cx >= 0 && cy >= 0 && cz >= 0 && cx < 30 && cy < 30 && cz < 30) {
-                            float gv = tdf[cy * 30 + cz * 900 + cx];
-                            distance_temp = __fadd_rn(distance_temp, __fmul_rn(gv, gv));
-                            ++used;
+                    unsigned kk[3];
+                    nat_unmorton((unsigned)((threadIdx.x * wpt + w) * 32 + b), f.depth, kk);
+                    int cx = nat_index(f, kk[0], 0, resolution), cy = nat_index(f, kk[1], 1, resolution), cz = nat_index(f, kk[2], 2, resolution);
+                    float v = -1.f;
+                    if (cx >= 0 && cy >= 0 && cz >= 0 && cx < 30 && cy < 30 && cz < 30) { float gv = tdf[cy * 30 + cz * 900 + cx]; v = __fmul_rn(gv, gv); }
+                    list[pos++] = v;
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (!running) distance_temp = 0.f;
+            int used = 0;
+            if (fits) {
+                for (int i = skip_first ? 1 : 0; i < total; ++i) {
+                    float v = list[i];
+                    if (v >= 0.f) { distance_temp = __fadd_rn(distance_temp, v); ++used; }
+                }
+            } else {                     // more occupied voxels than the list holds: serial enumeration
+                int seen = 0;
+                for (int w = 0; w < NAT_WORDS; ++w) {
+                    unsigned word = bits[w];
+                    while (word) {
+                        int b = __ffs(word) - 1;
+                        word &= word - 1;
+                        if (!(skip_first && seen == 0)) {
+                            unsigned kk[3];
+                            nat_unmorton((unsigned)(w * 32 + b), f.depth, kk);
+                            int cx = nat_index(f, kk[0], 0, resolution), cy = nat_index(f, kk[1], 1, resolution), cz = nat_index(f, kk[2], 2, resolution);
+                            if (cx >= 0 && cy >= 0 && cz >= 0 && cx < 30 && cy < 30 && cz < 30) {
+                                float gv = tdf[cy * 30 + cz * 900 + cx];
+                                distance_temp = __fadd_rn(distance_temp, __fmul_rn(gv, gv));
+                                ++used;
+                            }
                         }
+                        ++seen;
                     }
-                    ++seen;
                 }
             }
             distance_temp = used > 0 ? __fdiv_rn(distance_temp, (float)used) : 100000000.f;
@@ -397,7 +430,7 @@ static int nat_pairs(rtr_context* ctx, const NatDesc& dm, const NatDesc& ds, con
     float4* scratch = nullptr;
     if (int e = dev_alloc(ctx, &scratch, (size_t)npairs * ds.cap, "native")) return e;
     static bool attr = false;
-    size_t smem = 27000 * 4 + NAT_WORDS * 4;
+    size_t smem = 27000 * 4 + NAT_WORDS * 4 + NAT_LIST * 4;
     if (!attr) { RTR_CHECK(cudaFuncSetAttribute(k_native_pair_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "native"); attr = true; }
     NatSweep final_sw = nat_sweep();
     k_native_pair_score<<<npairs, NAT_THREADS, smem, ctx->stream>>>(dm.kps, dm.n_kp, ds.kps, ds.n_kp, dm.tdf, ds.occ, ds.occ_count, ds.cap, scratch,

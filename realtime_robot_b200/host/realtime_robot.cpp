@@ -3,7 +3,9 @@
 // time.  MSVC-isms, hard-coded file names, the pcl_viewer hand-off and the trailing infinite loop (RealTimeRobot.cpp:114-120)
 // are gone; everything numerical runs in librtr.so on the GPU.
 //
-//   realtime_robot <model.pcd> <scan.pcd> [--scale-model S] [--out transformed_model.pcd] [--hypotheses N] [--icp-only]
+//   realtime_robot <model.pcd> <scan.pcd> [--scale-model S] [--out transformed.pcd] [--hypotheses N] [--icp-only] [--native [--gate G]]
+//   --native runs the reference's own descriptor path (occupancy / TDF / yaw sweep / exhaustive consensus) and, like
+//   main(), transforms the SCAN into the model frame.
 #include <chrono>
 #include <cstdlib>
 #include <iostream>
@@ -13,13 +15,15 @@
 int main(int argc, char** argv) {
     if (argc < 3) { fprintf(stderr, "usage: %s <model.pcd> <scan.pcd> [--scale-model S] [--out file.pcd] [--hypotheses N] [--icp-only]\n", argv[0]); return 2; }
     std::string out;
-    float scale = 1.0f; long long hyp = 0; bool icp_only = false;
+    float scale = 1.0f, gate = 3.0f; long long hyp = 0; bool icp_only = false, native = false;
     for (int i = 3; i < argc; ++i) {
         std::string a = argv[i];
         if (a == "--scale-model" && i + 1 < argc) scale = strtof(argv[++i], nullptr);
         else if (a == "--out" && i + 1 < argc) out = argv[++i];
         else if (a == "--hypotheses" && i + 1 < argc) hyp = atoll(argv[++i]);
         else if (a == "--icp-only") icp_only = true;
+        else if (a == "--native") native = true;
+        else if (a == "--gate" && i + 1 < argc) gate = strtof(argv[++i], nullptr);
     }
     pcl::PointCloud<pcl::PointXYZ>::Ptr cloud(new pcl::PointCloud<pcl::PointXYZ>), mcloud(new pcl::PointCloud<pcl::PointXYZ>);
     if (pcl::io::loadPCDFile(argv[1], *mcloud) != 0 || pcl::io::loadPCDFile(argv[2], *cloud) != 0) return 1;
@@ -35,7 +39,14 @@ int main(int argc, char** argv) {
     scanpoint.getKeypoint();
     Eigen::Matrix4f matrix = Eigen::Matrix4f::Identity();
     pcl::PointCloud<pcl::PointXYZ> moved;
-    if (icp_only) {
+    if (native) {
+        rtr_native_params np; rtr_native_default_params(&np);
+        np.pair_gate = gate;
+        rtr_pose_result r = rtr_pose_result();
+        matrix = Ransac(cloud, mcloud, &np, &r);                 // RealTimeRobot.cpp:104
+        std::cout << "consensus " << r.inliers << " of " << r.evaluated << " screened pairs, winner " << r.hypothesis << "\n" << matrix;
+        pcl::transformPointCloud(*cloud, moved, matrix);         // RealTimeRobot.cpp:105
+    } else if (icp_only) {
         keyPointICP(nullptr, nullptr, cloud, mcloud, &matrix, &moved);
     } else {
         rtr_register_params p;

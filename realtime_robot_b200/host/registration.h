@@ -105,6 +105,137 @@ inline void keyPointICP(pcl::PointCloud<pcl::PointXYZ>::Ptr /*SpointCloud*/, pcl
     if (transformed) pcl::transformPointCloud(*mcloud, *transformed, t);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The reference's own descriptor records and pair logic (key_point.h, matching.h, function.h), same names and members.
+// Arithmetic runs in librtr.so (csrc/native.cu); the semantics are the INTENDED ones (matching.h:17-120) with the
+// as-committed quirks behind rtr_native_params flags.
+
+struct Surface {                         // key_point.h:47-51 (Coefficients: a, b, c, d of the plane)
+    double Area = 0;
+    float Coefficients[4] = {0, 0, 0, 0};
+    bool IsVertical = false;
+};
+
+struct OccupiedGrid {                    // key_point.h:53-57
+    pcl::PointCloud<pcl::PointXYZ>::Ptr cloud;
+    float Border[6] = {0, 0, 0, 0, 0, 0};
+    int Number = 0;
+};
+
+inline double getDistance(float v1, float v2, float v3, float v4, pcl::PointXYZ point) {     // key_point.h:38-43 (double abs: Appendix B#14)
+    double d = std::sqrt((double)(v1 * v1 + v2 * v2 + v3 * v3));
+    return std::fabs((double)(v1 * point.x + v2 * point.y + v3 * point.z + v4)) / d;
+}
+
+class KeyPoint {                         // key_point.h:59-76
+public:
+    OccupiedGrid Occupiedgrid;
+    pcl::PointXYZ Key_coordinate;
+    std::vector<double> vector3D;
+    std::vector<float> grid_value;       // 27000 floats (a std::vector instead of float[27000]: KeyPoint is copied by value a lot)
+    float Border[6] = {0, 0, 0, 0, 0, 0};
+    const rtr_cloud* source_ = nullptr;  // device cloud the descriptors were taken from (set by getOccupiedGrid)
+
+    KeyPoint() : vector3D(3, 0.16), grid_value(RTR_TDF_VOXELS, 0.f) {}
+    explicit KeyPoint(pcl::PointXYZ point) : Key_coordinate(point), vector3D(3, 0.16), grid_value(RTR_TDF_VOXELS, 0.f) {
+        Occupiedgrid.cloud.reset(new pcl::PointCloud<pcl::PointXYZ>);
+    }
+
+    // key_point.h:87-111: areas of <= 1 horizontal plane within 5 cm and <= 2 vertical planes within 2 cm, verticals descending
+    void get_Vector3D(std::vector<Surface>& surface) {
+        int vertical = 0, horizontal = 0;
+        for (size_t i = 0; i < surface.size(); i++) {
+            double distance = getDistance(surface[i].Coefficients[0], surface[i].Coefficients[1], surface[i].Coefficients[2], surface[i].Coefficients[3], Key_coordinate);
+            if (surface[i].IsVertical == 0 && horizontal == 0 && distance <= 0.05) { vector3D[0] = surface[i].Area; horizontal++; }
+            else if (surface[i].IsVertical == 1 && vertical <= 1 && distance <= 0.02) { vector3D[1 + vertical] = surface[i].Area; vertical++; }
+        }
+        if (vector3D[1] < vector3D[2]) std::swap(vector3D[1], vector3D[2]);
+    }
+
+    // key_point.h:112-161 and :251-318, one keypoint at a time like the reference (the batched form is
+    // rtr_native_keypoint_descriptors over all keypoints of a cloud)
+    void getOccupiedGrid(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud, float resolution = 0.01f, float f_adjust = 0.1f) {
+        rtr_native_params p; rtr_native_default_params(&p);
+        p.resolution = resolution; p.occ_half = f_adjust;
+        rtr_host::DeviceCloud d(*cloud);
+        if (!d.h) return;
+        int number = 0, count = 0;
+        if (rtr_native_keypoint_descriptors(d.h, &Key_coordinate.x, 1, &p, &number, &count, nullptr, nullptr) != 0) return;
+        Occupiedgrid.Number = number;
+        if (!Occupiedgrid.cloud) Occupiedgrid.cloud.reset(new pcl::PointCloud<pcl::PointXYZ>);
+        Occupiedgrid.cloud->clear();
+        for (const auto& q : cloud->points)     // boxSearch: inclusive float box (key_point.h:118-140)
+            if (q.x >= Key_coordinate.x - f_adjust && q.x <= Key_coordinate.x + f_adjust && q.y >= Key_coordinate.y - f_adjust &&
+                q.y <= Key_coordinate.y + f_adjust && q.z >= Key_coordinate.z - f_adjust && q.z <= Key_coordinate.z + f_adjust)
+                Occupiedgrid.cloud->push_back(q);
+    }
+    void get_TSDF(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud, float resolution = 0.01f, float f_adjust = 0.15f) {
+        rtr_native_params p; rtr_native_default_params(&p);
+        p.resolution = resolution; p.tdf_half = f_adjust;
+        for (int a = 0; a < 3; ++a) { Border[a] = (&Key_coordinate.x)[a] - f_adjust; Border[3 + a] = (&Key_coordinate.x)[a] + f_adjust; }
+        rtr_host::DeviceCloud d(*cloud);
+        if (!d.h) return;
+        std::fill(grid_value.begin(), grid_value.end(), 0.f);
+        if (rtr_native_keypoint_descriptors(d.h, &Key_coordinate.x, 1, &p, nullptr, nullptr, grid_value.data(), nullptr) != 0)
+            fprintf(stderr, "ComputeTDFWithCuda failed!");     // key_point.h:315-318
+    }
+};
+
+struct PairPoint { KeyPoint point_i; KeyPoint point_j; };      // function.h:23-26
+
+inline double pointdistance(pcl::PointXYZ p1, pcl::PointXYZ p2) {   // function.h:27-30
+    return std::sqrt((p1.x - p2.x) * (p1.x - p2.x) + (p1.y - p2.y) * (p1.y - p2.y) + (p1.z - p2.z) * (p1.z - p2.z));
+}
+
+// function.h:158-178 as intended; set quirk = true for the as-committed integer arithmetic (Appendix B#9, B#10)
+inline bool match_by_height(pcl::PointXYZ& key1, pcl::PointXYZ& key2, bool quirk = false) {
+    float temp = key1.z / key2.z;
+    return quirk ? (temp >= float(2 / 3) || temp <= 1.5) : (temp >= 2.0f / 3.0f && temp <= 1.5f);
+}
+inline bool match_by_area(std::vector<double> v1, std::vector<double> v2, bool quirk = false) {
+    double lo = quirk ? (double)float(1 / 3) : 1.0 / 3.0;
+    for (int a = 0; a < 3; ++a) if ((v1[a] / v2[a]) > 3 || (v1[a] / v2[a]) < lo) return false;
+    return true;
+}
+inline bool match_by_occupied(OccupiedGrid& o1, OccupiedGrid& o2, bool quirk = false) {
+    if (o2.Number == 0) return false;
+    float temp = quirk ? (float)(o1.Number / o2.Number) : (float)o1.Number / (float)o2.Number;
+    return !(temp > 2 || temp < 0.5);
+}
+
+// matching.h:122-222 for one pair.  p1_key: a MODEL keypoint with its TDF; p2_scan: a SCAN keypoint with its occupancy cloud.
+// model / scan are the clouds the keypoints came from.  (Batched: rtr_native_pair_scores.)
+inline float get_Distance(Eigen::Matrix4f& key_transform, KeyPoint& p1_key, KeyPoint& p2_scan,
+                          const pcl::PointCloud<pcl::PointXYZ>& model, const pcl::PointCloud<pcl::PointXYZ>& scan, const float resolution = 0.01f) {
+    key_transform = Eigen::Matrix4f::Identity();
+    rtr_native_params p; rtr_native_default_params(&p);
+    p.resolution = resolution;
+    rtr_host::DeviceCloud dm(model), ds(scan);
+    if (!dm.h || !ds.h) return 100000000.f;
+    float score = 100000000.f; int step = 0;
+    if (rtr_native_pair_scores(dm.h, &p1_key.Key_coordinate.x, 1, ds.h, &p2_scan.Key_coordinate.x, 1, &p, &score, &step, key_transform.data()) != 0)
+        return 100000000.f;
+    return score;
+}
+
+// function.h:35-109 + the pair loop of main() (RealTimeRobot.cpp:70-104): the whole reference-native registration on two
+// clouds.  Returns the transform main() applies to `cloud` (the scan); identity when nothing is consistent (the reference
+// returns an uninitialised matrix there, Appendix B#2).
+inline Eigen::Matrix4f Ransac(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud, pcl::PointCloud<pcl::PointXYZ>::Ptr mcloud,
+                              const rtr_native_params* params = nullptr, rtr_pose_result* details = nullptr) {
+    Eigen::Matrix4f m = Eigen::Matrix4f::Identity();
+    rtr_native_params p;
+    if (params) p = *params; else rtr_native_default_params(&p);
+    rtr_host::DeviceCloud dm(*mcloud), ds(*cloud);
+    if (!dm.h || !ds.h) return m;
+    rtr_pose_result r;
+    if (rtr_native_register(dm.h, ds.h, &p, &r) != 0) return m;
+    memcpy(m.data(), r.pose, sizeof(r.pose));
+    std::cout << r.evaluated << "aaaa" << std::endl;                     // RealTimeRobot.cpp:103
+    if (details) *details = r;
+    return m;
+}
+
 // The north-star pipeline on two pcl clouds: model -> scene pose, mean squared fitness, RANSAC bookkeeping.
 inline bool registerModelToScene(const pcl::PointCloud<pcl::PointXYZ>& model, const pcl::PointCloud<pcl::PointXYZ>& scene,
                                  const rtr_register_params& params, Eigen::Matrix4f& pose, rtr_pose_result* details = nullptr) {

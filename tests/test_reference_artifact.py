@@ -1,0 +1,66 @@
+"""Pins the keypoint chain (normals -> Harris response -> NMS -> corner refinement) to an output of the REFERENCE itself.
+
+tests/golden/reference_artifacts.json (tools/fit_reference_artifacts.py) holds the affine map between the reference's
+T0_m8111.pcd and its shipped transformed_cloud1.pcd — the matrix an earlier main() obtained from get_Distance for one
+(model corner, scan corner) pair (matching.h:204-217): yaw 40 degrees (step 4 of the sweep), scale z_m / z_s, translation
+from the two corners.  Those numbers depend only on the Harris corners PCL 1.8.0 found on chair1.pcd and T0_m8111.pcd, so
+one pair of OUR refined corners must reproduce them."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_artifacts.json")))["transformed_cloud1.pcd"]
+TOL = 5e-5
+
+
+def best_pair_error(mk, sk):
+    yaw = np.radians(round(GOLD["yaw_deg"] / 10.0) * 10.0)
+    c, s = np.cos(yaw), np.sin(yaw)
+    best = None
+    for i, a in enumerate(mk.astype(np.float64)):
+        for j, b in enumerate(sk.astype(np.float64)):
+            if b[2] == 0:
+                continue
+            scale = a[2] / b[2]
+            tx = a[0] - c * b[0] + s * b[1]                  # x row of T3 * Rz * T1 * T (unscaled in that code version)
+            ty = (a[1] - s * b[0] - c * b[1]) * scale        # y and z rows carry the scale
+            tz = scale * (a[2] - b[2])
+            err = max(abs(scale - GOLD["scale_z"]), abs(tx - GOLD["t"][0]), abs(ty - GOLD["t"][1]), abs(tz - GOLD["t"][2]))
+            if best is None or err < best[0]:
+                best = (err, i, j)
+    return best
+
+
+def test_artifact_is_a_sweep_transform():
+    assert GOLD["max_residual"] < 1e-6
+    assert abs(GOLD["yaw_deg"] - 40.0) < 1e-3                               # a multiple of the 10 degree step (matching.h:143)
+    assert abs(GOLD["row_scale"][0] - 1.0) < 1e-5 and abs(GOLD["row_scale"][1] - GOLD["scale_z"]) < 1e-5
+
+
+def test_oracle_refined_corners_reproduce_the_reference_artifact(orc, clouds):
+    model, scan = clouds("chair1"), clouds("T0_m8111")
+    mk = orc.harris3d(model, orc.normals(model, 0.05), 0.05, 0.01)[2]
+    sk = orc.harris3d(scan, orc.normals(scan, 0.05), 0.05, 0.01)[2]
+    err, i, j = best_pair_error(mk, sk)
+    assert err < TOL, (err, i, j)
+    # without refineCorners nothing comes close: the refinement step itself is pinned
+    mk0 = orc.harris3d(model, orc.normals(model, 0.05), 0.05, 0.01, 1, 0)[2]
+    sk0 = orc.harris3d(scan, orc.normals(scan, 0.05), 0.05, 0.01, 1, 0)[2]
+    assert best_pair_error(mk0, sk0)[0] > 1e-2
+
+
+@pytest.mark.gpu
+def test_gpu_refined_corners_reproduce_the_reference_artifact(gpu_ctx, clouds):
+    from realtime_robot_b200 import api
+    out = []
+    for name in ("chair1", "T0_m8111"):
+        c = api.Cloud(gpu_ctx, clouds(name))
+        c.normals(0.05)
+        out.append(c.harris3d(0.05, 0.01)[2])
+        c.free()
+    err, i, j = best_pair_error(out[0], out[1])
+    assert err < TOL, (err, i, j)
