@@ -41,6 +41,7 @@ struct GridView {
 };
 
 struct ProfMark { const char* tag; cudaEvent_t ev; };
+struct ArenaSlab { char* base; size_t cap; };
 
 struct rtr_context {
     int device = 0;
@@ -51,6 +52,12 @@ struct rtr_context {
     std::vector<cudaEvent_t> event_pool;
     int sm_count = 148;
     int match_stats[3] = {-1, 0, 0};
+    // bump arena for temporaries of one API call: all work of a context is ordered on one stream, so a temporary's memory
+    // can be handed out again as soon as the call that used it has been ENQUEUED.  Replaces ~100 cudaMallocAsync /
+    // cudaFreeAsync pairs per registration (8 concurrent registrations were partly bound by those driver calls).
+    std::vector<ArenaSlab> slabs;
+    size_t arena_top = 0;
+    int arena_depth = 0;
     cudaEvent_t events[RTR_NUM_EVENTS] = {};
     // small pinned staging area for results / counters
     void* pinned = nullptr;
@@ -107,13 +114,52 @@ static inline int dev_alloc(rtr_context* ctx, T** p, size_t count, const char* t
     RTR_CHECK(cudaMallocAsync((void**)p, count * sizeof(T), ctx->stream), tag);
     return 0;
 }
+static inline bool in_arena(const rtr_context* ctx, const void* p) {
+    for (const ArenaSlab& s : ctx->slabs) if ((const char*)p >= s.base && (const char*)p < s.base + s.cap) return true;
+    return false;
+}
 template <typename T>
 static inline void dev_free(rtr_context* ctx, T* p) {
-    if (p) cudaFreeAsync((void*)p, ctx->stream);
+    if (p && !in_arena(ctx, (const void*)p)) cudaFreeAsync((void*)p, ctx->stream);     // arena memory is released by its scope
 }
+// temporary that does not outlive the current API call (falls back to the pool when no scope is open)
+template <typename T>
+static inline int tmp_alloc(rtr_context* ctx, T** p, size_t count, const char* tag) {
+    if (ctx->arena_depth == 0) return dev_alloc(ctx, p, count, tag);
+    size_t bytes = ((count ? count : 1) * sizeof(T) + 255) & ~(size_t)255;
+    if (ctx->slabs.empty() || ctx->arena_top + bytes > ctx->slabs.back().cap) {
+        size_t cap = ctx->slabs.empty() ? ((size_t)32 << 20) : ctx->slabs.back().cap * 2;
+        if (cap < bytes * 2) cap = bytes * 2;
+        char* base = nullptr;
+        RTR_CHECK(cudaMallocAsync((void**)&base, cap, ctx->stream), tag);
+        ctx->slabs.push_back({base, cap});      // older slabs stay alive until the outermost scope closes
+        ctx->arena_top = 0;
+    }
+    *p = (T*)(ctx->slabs.back().base + ctx->arena_top);
+    ctx->arena_top += bytes;
+    return 0;
+}
+struct TmpScope {
+    rtr_context* ctx; size_t mark; size_t nslabs;
+    explicit TmpScope(rtr_context* c) : ctx(c), mark(c->arena_top), nslabs(c->slabs.size()) { ctx->arena_depth++; }
+    ~TmpScope() {
+        ctx->arena_depth--;
+        if (ctx->slabs.size() == nslabs) { ctx->arena_top = mark; return; }
+        if (ctx->arena_depth == 0) {            // the arena grew during this call: keep only the newest (largest) slab
+            for (size_t i = 0; i + 1 < ctx->slabs.size(); ++i) cudaFreeAsync(ctx->slabs[i].base, ctx->stream);
+            ArenaSlab last = ctx->slabs.back();
+            ctx->slabs.clear(); ctx->slabs.push_back(last);
+            ctx->arena_top = 0;
+        }
+    }
+    TmpScope(const TmpScope&) = delete;
+    TmpScope& operator=(const TmpScope&) = delete;
+};
 
 // internal API between translation units
-int  rtr_get_grid(rtr_cloud* c, float cell, DevGrid** out);          // build-or-fetch a grid with cell size >= `cell`
+int  rtr_get_grid(rtr_cloud* c, float cell, DevGrid** out);          // build-or-fetch the grid that serves radius `cell`
+// a cached grid whose cell size h satisfies lo <= h <= hi (the one closest to `want`), or build one for `want`
+int  rtr_get_grid_any(rtr_cloud* c, float want, float lo, float hi, DevGrid** out);
 int  rtr_grid_normals(rtr_cloud* c, DevGrid* g);                     // make g->sorted_normals current
 GridView rtr_view(const DevGrid* g);
 int  rtr_ensure_bbox(rtr_cloud* c);
@@ -272,6 +318,21 @@ __device__ __forceinline__ void grid_nearest_ex(const GridView& g, float qx, flo
     }
 }
 
+// The 3x3x3 block of a query is 9 contiguous ranges; their 18 bounds are fetched by 18 lanes at once (one round trip
+// instead of a chain of 18 dependent loads) and handed out with shuffles.  Range r = zi * 3 + yi over the clipped block.
+struct BlockRanges { int z0, z1, y0, y1; int bound; };
+__device__ __forceinline__ BlockRanges warp_block_ranges(const GridView& g, int cx, int cy, int cz, int lane) {
+    BlockRanges br;
+    br.z0 = max(cz - 1, 0); br.z1 = min(cz + 1, g.dz - 1); br.y0 = max(cy - 1, 0); br.y1 = min(cy + 1, g.dy - 1);
+    int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
+    int r = lane % 9, zi = r / 3, yi = r - zi * 3;
+    int z = br.z0 + zi, y = br.y0 + yi;
+    br.bound = 0;
+    if (lane < 18 && z <= br.z1 && y <= br.y1)
+        br.bound = (lane < 9) ? __ldg(g.cell_begin + cell_key(g, x0, y, z)) : __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
+    return br;
+}
+
 // Warp-cooperative form of grid_nearest_ex for small query sets (one warp per query): the lanes stride over the points
 // of every visited range and the (d2, index) minimum is folded with shuffles.  Same visiting rules, same result.
 __device__ __forceinline__ void warp_argmin(float& d, int& id, float4& p) {
@@ -292,11 +353,12 @@ __device__ __forceinline__ void grid_nearest_warp(const GridView& g, float qx, f
     int cy = clampi(cell_coord(qy, g.mny, g.inv_h), 0, g.dy - 1);
     int cz = clampi(cell_coord(qz, g.mnz, g.inv_h), 0, g.dz - 1);
     {
-        int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
-        for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
-            for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y) {
-                int s0 = __ldg(g.cell_begin + cell_key(g, x0, y, z));
-                int s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
+        BlockRanges br = warp_block_ranges(g, cx, cy, cz, lane);
+        for (int z = br.z0; z <= br.z1; ++z)
+            for (int y = br.y0; y <= br.y1; ++y) {
+                int r = (z - br.z0) * 3 + (y - br.y0);
+                int s0 = __shfl_sync(0xffffffffu, br.bound, r);
+                int s1 = __shfl_sync(0xffffffffu, br.bound, 9 + r);
                 for (int s = s0 + lane; s < s1; s += 32) {
                     float4 p = __ldg(g.sorted + s);
                     float d = dist2f(qx, qy, qz, p.x, p.y, p.z);

@@ -38,6 +38,59 @@ __global__ void k_gather_sorted(const float4* __restrict__ pts, const int* __res
     sorted[s] = p;
 }
 
+// Grid build for repo-sized clouds in ONE launch (one CTA): histogram -> exclusive scan -> scatter -> in-cell ranking by
+// original index (so the order is the same stable order the radix-sort path produces) -> gather.  Replaces memset + keys
+// + radix sort + scan + gather (7-8 launches, each a few microseconds of pure latency at these sizes).
+#define GB_THREADS 1024
+__global__ void __launch_bounds__(GB_THREADS) k_grid_build_small(const float4* __restrict__ pts, int n, float mnx, float mny, float mnz,
+                                                                float inv_h, int dx, int dy, int dz, int ncells, int* __restrict__ cell_begin,
+                                                                int* __restrict__ keys, int* __restrict__ cursor, int* __restrict__ slot,
+                                                                float4* __restrict__ sorted) {
+    __shared__ int part[GB_THREADS];
+    const int t = threadIdx.x;
+    for (int c = t; c <= ncells; c += GB_THREADS) cell_begin[c] = 0;
+    __syncthreads();
+    for (int i = t; i < n; i += GB_THREADS) {
+        float4 p = __ldg(pts + i);
+        int cx = clampi(cell_coord(p.x, mnx, inv_h), 0, dx - 1);
+        int cy = clampi(cell_coord(p.y, mny, inv_h), 0, dy - 1);
+        int cz = clampi(cell_coord(p.z, mnz, inv_h), 0, dz - 1);
+        int key = (cz * dy + cy) * dx + cx;
+        keys[i] = key;
+        atomicAdd(cell_begin + key, 1);
+    }
+    __syncthreads();
+    // exclusive scan of cell_begin[0 .. ncells] in place: contiguous chunk per thread + block scan of the chunk sums
+    int per = (ncells + 1 + GB_THREADS - 1) / GB_THREADS;
+    int c0 = min(t * per, ncells + 1), c1 = min(c0 + per, ncells + 1);
+    int sum = 0;
+    for (int c = c0; c < c1; ++c) sum += cell_begin[c];
+    part[t] = sum;
+    __syncthreads();
+    for (int off = 1; off < GB_THREADS; off <<= 1) {
+        int v = (t >= off) ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int run = part[t] - sum;
+    for (int c = c0; c < c1; ++c) { int v = cell_begin[c]; cell_begin[c] = run; cursor[c] = run; run += v; }
+    __syncthreads();
+    for (int i = t; i < n; i += GB_THREADS) slot[atomicAdd(cursor + keys[i], 1)] = i;       // unordered inside a cell
+    __syncthreads();
+    // rank inside the cell = number of members with a smaller original index -> deterministic ascending order
+    for (int pos = t; pos < n; pos += GB_THREADS) {
+        int i = slot[pos];
+        int key = keys[i];
+        int b = cell_begin[key], e = cell_begin[key + 1];
+        int rank = 0;
+        for (int q = b; q < e; ++q) rank += (slot[q] < i) ? 1 : 0;
+        float4 p = __ldg(pts + i);
+        p.w = __int_as_float(i);
+        sorted[b + rank] = p;
+    }
+}
+
 __global__ void k_permute4(const float4* __restrict__ src, const float4* __restrict__ sorted, int n, float4* __restrict__ dst) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -134,7 +187,7 @@ int rtr_ensure_bbox(rtr_cloud* c) {
     if (c->bbox_valid) return 0;
     rtr_context* ctx = c->ctx;
     unsigned* d_box = nullptr;
-    if (int e = dev_alloc(ctx, &d_box, 6, "bbox")) return e;
+    if (int e = tmp_alloc(ctx, &d_box, 6, "bbox")) return e;
     unsigned init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
     RTR_CHECK(cudaMemcpyAsync(d_box, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream), "bbox");
     if (c->n > 0) {
@@ -207,12 +260,27 @@ int rtr_get_grid(rtr_cloud* c, float cell, DevGrid** out) {
     g.mnx = c->bb_min[0]; g.mny = c->bb_min[1]; g.mnz = c->bb_min[2];
     g.ncells = g.dx * g.dy * g.dz;
     int n = c->n;
+    if (n > 0 && n <= 32768 && g.ncells <= (1 << 21)) {
+        int *keys = nullptr, *cursor = nullptr, *slot = nullptr;
+        if (int e = tmp_alloc(ctx, &keys, n, "grid")) return e;
+        if (int e = tmp_alloc(ctx, &cursor, (size_t)g.ncells + 1, "grid")) return e;
+        if (int e = tmp_alloc(ctx, &slot, n, "grid")) return e;
+        if (int e = dev_alloc(ctx, &g.cell_begin, (size_t)g.ncells + 1, "grid")) return e;
+        if (int e = dev_alloc(ctx, &g.sorted, n, "grid")) return e;
+        k_grid_build_small<<<1, GB_THREADS, 0, ctx->stream>>>(c->pts, n, g.mnx, g.mny, g.mnz, g.inv_h, g.dx, g.dy, g.dz, g.ncells,
+                                                               g.cell_begin, keys, cursor, slot, g.sorted);
+        RTR_LAUNCH_CHECK(ctx, "grid.build_small");
+        dev_free(ctx, keys); dev_free(ctx, cursor); dev_free(ctx, slot);
+        auto ins = c->grids.emplace(keybits, g);
+        *out = &ins.first->second;
+        return 0;
+    }
     int *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr, *counts = nullptr;
-    if (int e = dev_alloc(ctx, &keys, n, "grid")) return e;
-    if (int e = dev_alloc(ctx, &vals, n, "grid")) return e;
-    if (int e = dev_alloc(ctx, &keys2, n, "grid")) return e;
-    if (int e = dev_alloc(ctx, &vals2, n, "grid")) return e;
-    if (int e = dev_alloc(ctx, &counts, (size_t)g.ncells + 1, "grid")) return e;
+    if (int e = tmp_alloc(ctx, &keys, n, "grid")) return e;
+    if (int e = tmp_alloc(ctx, &vals, n, "grid")) return e;
+    if (int e = tmp_alloc(ctx, &keys2, n, "grid")) return e;
+    if (int e = tmp_alloc(ctx, &vals2, n, "grid")) return e;
+    if (int e = tmp_alloc(ctx, &counts, (size_t)g.ncells + 1, "grid")) return e;
     if (int e = dev_alloc(ctx, &g.cell_begin, (size_t)g.ncells + 1, "grid")) return e;
     if (int e = dev_alloc(ctx, &g.sorted, n, "grid")) return e;
     RTR_CHECK(cudaMemsetAsync(counts, 0, ((size_t)g.ncells + 1) * sizeof(int), ctx->stream), "grid");
@@ -228,7 +296,7 @@ int rtr_get_grid(rtr_cloud* c, float cell, DevGrid** out) {
     cub::DeviceScan::ExclusiveSum(nullptr, tb_scan, counts, g.cell_begin, g.ncells + 1, ctx->stream);
     void* temp = nullptr;
     size_t tb = std::max(tb_sort, tb_scan);
-    if (int e = dev_alloc(ctx, (char**)&temp, tb, "grid")) return e;
+    if (int e = tmp_alloc(ctx, (char**)&temp, tb, "grid")) return e;
     if (n > 0) RTR_CHECK(cub::DeviceRadixSort::SortPairs(temp, tb_sort, keys, keys2, vals, vals2, n, 0, end_bit, ctx->stream), "grid.sort");
     RTR_MARK(ctx, "grid.cub_sort");
     RTR_CHECK(cub::DeviceScan::ExclusiveSum(temp, tb_scan, counts, g.cell_begin, g.ncells + 1, ctx->stream), "grid.scan");
@@ -241,6 +309,16 @@ int rtr_get_grid(rtr_cloud* c, float cell, DevGrid** out) {
     auto ins = c->grids.emplace(keybits, g);
     *out = &ins.first->second;
     return 0;
+}
+
+int rtr_get_grid_any(rtr_cloud* c, float want, float lo, float hi, DevGrid** out) {
+    DevGrid* best = nullptr;
+    for (auto& kv : c->grids) {
+        DevGrid& g = kv.second;
+        if (g.h >= lo && g.h <= hi && (!best || std::fabs(g.h - want) < std::fabs(best->h - want))) best = &g;
+    }
+    if (best) { *out = best; return 0; }
+    return rtr_get_grid(c, want, out);
 }
 
 int rtr_grid_normals(rtr_cloud* c, DevGrid* g) {
@@ -345,6 +423,7 @@ int rtr_context_destroy(rtr_context* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < RTR_NUM_EVENTS; ++i) if (ctx->events[i]) cudaEventDestroy(ctx->events[i]);
+    for (auto& sl : ctx->slabs) cudaFree(sl.base);
     for (auto& m : ctx->marks) cudaEventDestroy(m.ev);
     for (auto& e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

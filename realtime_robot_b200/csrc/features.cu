@@ -65,11 +65,12 @@ __device__ __forceinline__ void for_block27_warp(const GridView& g, float qx, fl
     int cx = cell_coord(qx, g.mnx, g.inv_h), cy = cell_coord(qy, g.mny, g.inv_h), cz = cell_coord(qz, g.mnz, g.inv_h);
     if (cx < -1 || cy < -1 || cz < -1 || cx > g.dx || cy > g.dy || cz > g.dz) return;
     cx = clampi(cx, 0, g.dx - 1); cy = clampi(cy, 0, g.dy - 1); cz = clampi(cz, 0, g.dz - 1);
-    int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
-    for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
-        for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y) {
-            int s0 = __ldg(g.cell_begin + cell_key(g, x0, y, z));
-            int s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
+    BlockRanges br = warp_block_ranges(g, cx, cy, cz, lane);
+    for (int z = br.z0; z <= br.z1; ++z)
+        for (int y = br.y0; y <= br.y1; ++y) {
+            int r = (z - br.z0) * 3 + (y - br.y0);
+            int s0 = __shfl_sync(0xffffffffu, br.bound, r);
+            int s1 = __shfl_sync(0xffffffffu, br.bound, 9 + r);
             for (int s = s0 + lane; s < s1; s += 32) {
                 float4 p = __ldg(g.sorted + s);
                 f(s, p, dist2f(qx, qy, qz, p.x, p.y, p.z));
@@ -427,6 +428,104 @@ __global__ void __launch_bounds__(FPFH_WARPS * 32) k_fpfh_weight(GridView g, con
     }
 }
 
+// Tiled form for larger / denser clouds: all points of a cell share the same 27-cell candidate block, so one CTA per
+// occupied cell stages the candidates' positions and SPFH rows through shared memory ONCE per tile instead of once per
+// query (the untiled kernel moves 132 B x neighbours per query through L2: 2.8 GB for an 18 779-point dense cloud).
+// Every query's 33 running sums live in shared memory between tiles, so the additions happen in exactly the same order
+// (ranges in (z, y) order, positions ascending) as in k_fpfh_weight: the results are bit-identical.
+#define FW_TILE 128
+#define FW_QCHUNK 128
+#define FW_WARPS 8
+struct FwSmem {
+    float4 tpos[FW_TILE];
+    float tsp[FW_TILE * 33];
+    double acc[FW_QCHUNK][33];
+    int nbc[FW_QCHUNK];
+};
+__global__ void k_occupied_cells(const int* __restrict__ cell_begin, int ncells, int* __restrict__ cells, int* __restrict__ count) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ncells && cell_begin[c + 1] > cell_begin[c]) cells[atomicAdd(count, 1)] = c;
+}
+__global__ void __launch_bounds__(FW_WARPS * 32) k_fpfh_weight_tiled(GridView g, const float* __restrict__ spfh_sorted, float r2,
+                                                                     float* __restrict__ fpfh, const int* __restrict__ cells,
+                                                                     const int* __restrict__ n_cells) {
+    extern __shared__ __align__(16) unsigned char fw_raw[];
+    FwSmem& sm = *reinterpret_cast<FwSmem*>(fw_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nc = *n_cells;
+    for (int ci = blockIdx.x; ci < nc; ci += gridDim.x) {
+        const int c = cells[ci];
+        const int cz = c / (g.dx * g.dy), cy = (c - cz * g.dx * g.dy) / g.dx, cx = c - cz * g.dx * g.dy - cy * g.dx;
+        const int qb = __ldg(g.cell_begin + c), qe = __ldg(g.cell_begin + c + 1);
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
+        for (int q0 = qb; q0 < qe; q0 += FW_QCHUNK) {
+            const int nq = min(FW_QCHUNK, qe - q0);
+            __syncthreads();
+            for (int e = threadIdx.x; e < nq * 33; e += blockDim.x) (&sm.acc[0][0])[e] = 0.0;
+            for (int e = threadIdx.x; e < nq; e += blockDim.x) sm.nbc[e] = 0;
+            for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
+                for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y) {
+                    const int s0 = __ldg(g.cell_begin + cell_key(g, x0, y, z));
+                    const int s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
+                    for (int t0 = s0; t0 < s1; t0 += FW_TILE) {
+                        const int nt = min(FW_TILE, s1 - t0);
+                        __syncthreads();
+                        for (int i = threadIdx.x; i < nt; i += blockDim.x) sm.tpos[i] = __ldg(g.sorted + t0 + i);
+                        for (int e = threadIdx.x; e < nt * 33; e += blockDim.x) sm.tsp[e] = __ldg(spfh_sorted + (size_t)t0 * 33 + e);
+                        __syncthreads();
+                        for (int qi = warp; qi < nq; qi += FW_WARPS) {
+                            const float4 q = __ldg(g.sorted + q0 + qi);
+                            double a = sm.acc[qi][lane], a32 = (lane == 0) ? sm.acc[qi][32] : 0.0;
+                            int nb = 0;
+                            for (int base = 0; base < nt; base += 32) {
+                                const int i = base + lane;
+                                double w = 0.0;
+                                bool in = false;
+                                if (i < nt) {
+                                    const float4 p = sm.tpos[i];
+                                    const float d2 = dist2f(q.x, q.y, q.z, p.x, p.y, p.z);
+                                    in = d2 < r2;
+                                    if (in && d2 != 0.f) w = 1.0 / (double)d2;
+                                }
+                                nb += __popc(__ballot_sync(0xffffffffu, in));
+                                unsigned mask = __ballot_sync(0xffffffffu, w != 0.0);
+                                while (mask) {
+                                    const int j = __ffs(mask) - 1;
+                                    mask &= mask - 1;
+                                    const double wj = __shfl_sync(0xffffffffu, w, j);
+                                    a += (double)sm.tsp[(base + j) * 33 + lane] * wj;
+                                    if (lane == 0) a32 += (double)sm.tsp[(base + j) * 33 + 32] * wj;
+                                }
+                            }
+                            sm.acc[qi][lane] = a;
+                            if (lane == 0) { sm.acc[qi][32] = a32; sm.nbc[qi] += nb; }
+                        }
+                    }
+                }
+            __syncthreads();
+            // normalise each third to 100 and store (same arithmetic as k_fpfh_weight)
+            for (int qi = warp; qi < nq; qi += FW_WARPS) {
+                double sc = 0.0;
+                if (lane < 3) {
+                    double sum = 0;
+                    for (int k = 0; k < 11; ++k) sum += sm.acc[qi][lane * 11 + k];
+                    sc = (sum != 0) ? 100.0 / sum : 0.0;
+                }
+                const double s0_ = __shfl_sync(0xffffffffu, sc, 0), s1_ = __shfl_sync(0xffffffffu, sc, 1), s2_ = __shfl_sync(0xffffffffu, sc, 2);
+                const double mine = lane < 11 ? s0_ : (lane < 22 ? s1_ : s2_);
+                float* o = fpfh + (size_t)__float_as_int(__ldg(g.sorted + q0 + qi).w) * 33;
+                if (sm.nbc[qi] == 0) {
+                    o[lane] = __int_as_float(0x7fc00000);
+                    if (lane == 0) o[32] = __int_as_float(0x7fc00000);
+                } else {
+                    o[lane] = (float)(sm.acc[qi][lane] * mine);
+                    if (lane == 0) o[32] = (float)(sm.acc[qi][32] * s2_);
+                }
+            }
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------- feature k-NN (App. A.5), exact
 // One warp per source feature; targets are staged through shared memory in tiles of 64 rows (row stride 33 floats is
 // conflict-free); each lane keeps a sorted top-K of the rows it scanned; the warp then merges the 32 lists.
@@ -558,11 +657,11 @@ int rtr_harris_dev(rtr_cloud* c, float radius, float threshold, int nms, int ref
     float r2 = radius * radius;
     if (!c->response) if (int e = dev_alloc(ctx, &c->response, n, "harris")) return e;
     float* resp_sorted = nullptr; unsigned char* flags = nullptr;
-    if (int e = dev_alloc(ctx, &resp_sorted, n, "harris")) return e;
-    if (int e = dev_alloc(ctx, &flags, n, "harris")) return e;
-    if (int e = dev_alloc(ctx, d_kp_idx, n, "harris")) return e;
-    if (int e = dev_alloc(ctx, d_kp_xyz, n, "harris")) return e;
-    if (int e = dev_alloc(ctx, d_count, 1, "harris")) return e;
+    if (int e = tmp_alloc(ctx, &resp_sorted, n, "harris")) return e;
+    if (int e = tmp_alloc(ctx, &flags, n, "harris")) return e;
+    if (int e = tmp_alloc(ctx, d_kp_idx, n, "harris")) return e;
+    if (int e = tmp_alloc(ctx, d_kp_xyz, n, "harris")) return e;
+    if (int e = tmp_alloc(ctx, d_count, 1, "harris")) return e;
     RTR_CHECK(cudaMemsetAsync(*d_count, 0, sizeof(int), ctx->stream), "harris");
     if (n > 0) {
         GridView v = rtr_view(g);
@@ -582,7 +681,7 @@ int rtr_harris_dev(rtr_cloud* c, float radius, float threshold, int nms, int ref
         thrust::counting_iterator<int> iota(0);
         cub::DeviceSelect::Flagged(nullptr, tb, iota, flags, *d_kp_idx, *d_count, n, ctx->stream);
         char* temp = nullptr;
-        if (int e = dev_alloc(ctx, &temp, tb, "harris")) return e;
+        if (int e = tmp_alloc(ctx, &temp, tb, "harris")) return e;
         RTR_CHECK(cub::DeviceSelect::Flagged(temp, tb, iota, flags, *d_kp_idx, *d_count, n, ctx->stream), "harris.select");
         RTR_MARK(ctx, "harris.cub_select");
         dev_free(ctx, temp);
@@ -605,12 +704,26 @@ int rtr_fpfh_dev(rtr_cloud* c, float radius) {
     float r2 = radius * radius;
     if (!c->fpfh) if (int e = dev_alloc(ctx, &c->fpfh, (size_t)n * 33, "fpfh")) return e;
     float* spfh = nullptr;
-    if (int e = dev_alloc(ctx, &spfh, (size_t)n * 33, "fpfh")) return e;
+    if (int e = tmp_alloc(ctx, &spfh, (size_t)n * 33, "fpfh")) return e;
     if (n > 0) {
         GridView v = rtr_view(g);
         k_spfh<<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * 16), SPFH_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh);
         RTR_LAUNCH_CHECK(ctx, "fpfh.spfh");
-        k_fpfh_weight<<<std::min(nblk(n, FPFH_WARPS), ctx->sm_count * 16), FPFH_WARPS * 32, 0, ctx->stream>>>(v, spfh, r2, c->fpfh);
+        if (n >= (1 << 20)) {
+            // one CTA per occupied cell, candidates staged through shared memory (needs many occupied cells to fill the GPU)
+            int *cells = nullptr, *n_cells = nullptr;
+            if (int e = tmp_alloc(ctx, &cells, (size_t)std::min(g->ncells, n), "fpfh")) return e;
+            if (int e = tmp_alloc(ctx, &n_cells, 1, "fpfh")) return e;
+            RTR_CHECK(cudaMemsetAsync(n_cells, 0, sizeof(int), ctx->stream), "fpfh");
+            k_occupied_cells<<<nblk(g->ncells, 256), 256, 0, ctx->stream>>>(g->cell_begin, g->ncells, cells, n_cells);
+            RTR_LAUNCH_CHECK(ctx, "fpfh.cells");
+            static bool attr = false;
+            if (!attr) { RTR_CHECK(cudaFuncSetAttribute(k_fpfh_weight_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwSmem)), "fpfh"); attr = true; }
+            int grid = std::min(std::min(g->ncells, n), ctx->sm_count * 4);
+            k_fpfh_weight_tiled<<<grid, FW_WARPS * 32, sizeof(FwSmem), ctx->stream>>>(v, spfh, r2, c->fpfh, cells, n_cells);
+        } else {
+            k_fpfh_weight<<<std::min(nblk(n, FPFH_WARPS), ctx->sm_count * 16), FPFH_WARPS * 32, 0, ctx->stream>>>(v, spfh, r2, c->fpfh);
+        }
         RTR_LAUNCH_CHECK(ctx, "fpfh.weight");
     }
     dev_free(ctx, spfh);
@@ -637,6 +750,7 @@ extern "C" {
 
 int rtr_normals(rtr_cloud* c, float radius, float* host_normals4) {
     if (!c || !(radius > 0.f)) return rtr_fail("normals", "bad argument", RTR_ERR_INVALID);
+    TmpScope tmp_scope(c->ctx);
     RTR_CHECK(cudaSetDevice(c->ctx->device), "normals");
     if (int e = rtr_normals_dev(c, radius)) return e;
     if (host_normals4 && c->n > 0) RTR_CHECK(cudaMemcpyAsync(host_normals4, c->normals, (size_t)c->n * 16, cudaMemcpyDeviceToHost, c->ctx->stream), "normals");
@@ -648,6 +762,7 @@ int rtr_harris3d(rtr_cloud* c, float radius, float threshold, int nms, int refin
                  float* host_kp_xyz1, int capacity, int* n_keypoints) {
     if (!c || !(radius > 0.f) || !n_keypoints || capacity < 0) return rtr_fail("harris", "bad argument", RTR_ERR_INVALID);
     rtr_context* ctx = c->ctx;
+    TmpScope tmp_scope(ctx);
     RTR_CHECK(cudaSetDevice(ctx->device), "harris");
     int* d_idx = nullptr; float4* d_xyz = nullptr; int* d_count = nullptr;
     if (int e = rtr_harris_dev(c, radius, threshold, nms, refine, &d_idx, &d_xyz, &d_count)) return e;
@@ -671,6 +786,7 @@ int rtr_harris3d(rtr_cloud* c, float radius, float threshold, int nms, int refin
 
 int rtr_fpfh(rtr_cloud* c, float radius, float* host_fpfh) {
     if (!c || !(radius > 0.f)) return rtr_fail("fpfh", "bad argument", RTR_ERR_INVALID);
+    TmpScope tmp_scope(c->ctx);
     RTR_CHECK(cudaSetDevice(c->ctx->device), "fpfh");
     if (int e = rtr_fpfh_dev(c, radius)) return e;
     if (host_fpfh && c->n > 0) RTR_CHECK(cudaMemcpyAsync(host_fpfh, c->fpfh, (size_t)c->n * 33 * 4, cudaMemcpyDeviceToHost, c->ctx->stream), "fpfh");
@@ -682,12 +798,13 @@ int rtr_match_features_raw(rtr_context* ctx, const float* host_source_feat, int 
                            int k, int* host_idx, float* host_dist, float* kernel_ms) {
     if (!ctx || ns < 0 || nt < 0 || k < 1 || k > MATCH_KMAX || (ns > 0 && (!host_source_feat || !host_idx)) || (nt > 0 && !host_target_feat))
         return rtr_fail("match_raw", "bad argument", RTR_ERR_INVALID);
+    TmpScope tmp_scope(ctx);
     RTR_CHECK(cudaSetDevice(ctx->device), "match_raw");
     float *fa = nullptr, *fb = nullptr, *dd = nullptr; int* di = nullptr;
-    if (int e = dev_alloc(ctx, &fa, (size_t)ns * 33, "match_raw")) return e;
-    if (int e = dev_alloc(ctx, &fb, (size_t)nt * 33, "match_raw")) return e;
-    if (int e = dev_alloc(ctx, &di, (size_t)ns * k, "match_raw")) return e;
-    if (int e = dev_alloc(ctx, &dd, (size_t)ns * k, "match_raw")) return e;
+    if (int e = tmp_alloc(ctx, &fa, (size_t)ns * 33, "match_raw")) return e;
+    if (int e = tmp_alloc(ctx, &fb, (size_t)nt * 33, "match_raw")) return e;
+    if (int e = tmp_alloc(ctx, &di, (size_t)ns * k, "match_raw")) return e;
+    if (int e = tmp_alloc(ctx, &dd, (size_t)ns * k, "match_raw")) return e;
     if (ns > 0) RTR_CHECK(cudaMemcpyAsync(fa, host_source_feat, (size_t)ns * 132, cudaMemcpyHostToDevice, ctx->stream), "match_raw");
     if (nt > 0) RTR_CHECK(cudaMemcpyAsync(fb, host_target_feat, (size_t)nt * 132, cudaMemcpyHostToDevice, ctx->stream), "match_raw");
     RTR_CHECK(cudaEventRecord(ctx->events[RTR_NUM_EVENTS - 2], ctx->stream), "match_raw");
@@ -714,6 +831,7 @@ int rtr_match_last_stats(rtr_context* ctx, int* stats3) {
 int rtr_match_features(rtr_cloud* source, rtr_cloud* target, int k, int* host_idx, float* host_dist) {
     if (!source || !target || source->ctx != target->ctx) return rtr_fail("match", "bad argument", RTR_ERR_INVALID);
     rtr_context* ctx = source->ctx;
+    TmpScope tmp_scope(ctx);
     RTR_CHECK(cudaSetDevice(ctx->device), "match");
     if (int e = rtr_match_dev(source, target, k)) return e;
     size_t cnt = (size_t)source->n * k;

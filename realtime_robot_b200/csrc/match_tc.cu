@@ -411,19 +411,19 @@ int rtr_match_tc_dev(rtr_context* ctx, const float* fa, int ns, const float* fb,
     splits = nblk(tgt_tiles, tiles_per_split);
     float *a_tiles = nullptr, *b_tiles = nullptr, *a_norms = nullptr, *b_norms = nullptr, *cand_val = nullptr, *cand_thr = nullptr, *d_nbmax = nullptr, *mu = nullptr;
     int *cand_idx = nullptr, *redo_rows = nullptr, *redo_count = nullptr;
-    if (int e = dev_alloc(ctx, &a_tiles, (size_t)src_tiles * TC_TILE * TC_KF, "match.tc")) return e;
-    if (int e = dev_alloc(ctx, &b_tiles, (size_t)tgt_tiles * TC_TILE * TC_KF, "match.tc")) return e;
-    if (int e = dev_alloc(ctx, &a_norms, (size_t)src_tiles * TC_TILE, "match.tc")) return e;
-    if (int e = dev_alloc(ctx, &b_norms, (size_t)tgt_tiles * TC_TILE, "match.tc")) return e;
+    if (int e = tmp_alloc(ctx, &a_tiles, (size_t)src_tiles * TC_TILE * TC_KF, "match.tc")) return e;
+    if (int e = tmp_alloc(ctx, &b_tiles, (size_t)tgt_tiles * TC_TILE * TC_KF, "match.tc")) return e;
+    if (int e = tmp_alloc(ctx, &a_norms, (size_t)src_tiles * TC_TILE, "match.tc")) return e;
+    if (int e = tmp_alloc(ctx, &b_norms, (size_t)tgt_tiles * TC_TILE, "match.tc")) return e;
     // more kept candidates make the certificate succeed more often; with one split there is only one list per row
     const int keep = (splits == 1) ? 32 : 16;
-    if (int e = dev_alloc(ctx, &cand_idx, (size_t)ns * splits * keep, "match.tc")) return e;
-    if (int e = dev_alloc(ctx, &cand_val, (size_t)ns * splits * keep, "match.tc")) return e;
-    if (int e = dev_alloc(ctx, &cand_thr, (size_t)ns * splits, "match.tc")) return e;
-    if (int e = dev_alloc(ctx, &redo_rows, (size_t)ns, "match.tc")) return e;
-    if (int e = dev_alloc(ctx, &redo_count, 1, "match.tc")) return e;
-    if (int e = dev_alloc(ctx, &d_nbmax, 2, "match.tc")) return e;      // [0] max centred |b|^2, [1] observed error ratio
-    if (int e = dev_alloc(ctx, &mu, 33, "match.tc")) return e;
+    if (int e = tmp_alloc(ctx, &cand_idx, (size_t)ns * splits * keep, "match.tc")) return e;
+    if (int e = tmp_alloc(ctx, &cand_val, (size_t)ns * splits * keep, "match.tc")) return e;
+    if (int e = tmp_alloc(ctx, &cand_thr, (size_t)ns * splits, "match.tc")) return e;
+    if (int e = tmp_alloc(ctx, &redo_rows, (size_t)ns, "match.tc")) return e;
+    if (int e = tmp_alloc(ctx, &redo_count, 1, "match.tc")) return e;
+    if (int e = tmp_alloc(ctx, &d_nbmax, 2, "match.tc")) return e;      // [0] max centred |b|^2, [1] observed error ratio
+    if (int e = tmp_alloc(ctx, &mu, 33, "match.tc")) return e;
     RTR_CHECK(cudaMemsetAsync(redo_count, 0, sizeof(int), ctx->stream), "match.tc");
     RTR_CHECK(cudaMemsetAsync(d_nbmax, 0, 2 * sizeof(float), ctx->stream), "match.tc");
     k_tc_mean<<<1, 1024, 0, ctx->stream>>>(fb, std::min(nt, 1024), mu);      // any fixed vector works; a sample mean is enough

@@ -383,10 +383,10 @@ static int nat_describe(rtr_cloud* c, const float4* d_kps, int n_kp, const rtr_n
     d.n_kp = n_kp;
     d.cap = std::max(1, std::min(c->n, 16384));
     d.vcap = std::min(d.cap, 32768);
-    if (int e = dev_alloc(ctx, &d.kps, n_kp, "native")) return e;
-    if (int e = dev_alloc(ctx, &d.occ, (size_t)n_kp * d.cap, "native")) return e;
-    if (int e = dev_alloc(ctx, &d.occ_count, n_kp, "native")) return e;
-    if (int e = dev_alloc(ctx, &d.number, n_kp, "native")) return e;
+    if (int e = tmp_alloc(ctx, &d.kps, n_kp, "native")) return e;
+    if (int e = tmp_alloc(ctx, &d.occ, (size_t)n_kp * d.cap, "native")) return e;
+    if (int e = tmp_alloc(ctx, &d.occ_count, n_kp, "native")) return e;
+    if (int e = tmp_alloc(ctx, &d.number, n_kp, "native")) return e;
     if (n_kp == 0) return 0;
     RTR_CHECK(cudaMemcpyAsync(d.kps, d_kps, (size_t)n_kp * 16, cudaMemcpyDeviceToDevice, ctx->stream), "native");
     DevGrid* g;
@@ -394,10 +394,10 @@ static int nat_describe(rtr_cloud* c, const float4* d_kps, int n_kp, const rtr_n
     k_native_occupancy<<<n_kp, NAT_THREADS, 0, ctx->stream>>>(rtr_view(g), d.kps, n_kp, p->occ_half, p->resolution, d.cap, d.occ, d.occ_count, d.number);
     RTR_LAUNCH_CHECK(ctx, "native.occupancy");
     if (with_tdf) {
-        if (int e = dev_alloc(ctx, &d.triples, (size_t)n_kp * d.vcap * 3, "native")) return e;
-        if (int e = dev_alloc(ctx, &d.v_begin, n_kp, "native")) return e;
-        if (int e = dev_alloc(ctx, &d.v_end, n_kp, "native")) return e;
-        if (int e = dev_alloc(ctx, &d.tdf, (size_t)n_kp * 27000, "native")) return e;
+        if (int e = tmp_alloc(ctx, &d.triples, (size_t)n_kp * d.vcap * 3, "native")) return e;
+        if (int e = tmp_alloc(ctx, &d.v_begin, n_kp, "native")) return e;
+        if (int e = tmp_alloc(ctx, &d.v_end, n_kp, "native")) return e;
+        if (int e = tmp_alloc(ctx, &d.tdf, (size_t)n_kp * 27000, "native")) return e;
         k_native_tdf_voxels<<<n_kp, NAT_THREADS, 0, ctx->stream>>>(d.kps, n_kp, p->tdf_half, p->resolution, d.cap, d.occ, d.occ_count,
                                                                     p->quirk_skip_first_voxel, d.vcap, d.triples, d.v_begin, d.v_end);
         RTR_LAUNCH_CHECK(ctx, "native.tdf_voxels");
@@ -428,7 +428,7 @@ static int nat_pairs(rtr_context* ctx, const NatDesc& dm, const NatDesc& ds, con
     if (int e = dev_alloc(ctx, transform, (size_t)npairs * 16, "native")) return e;
     if (npairs == 0) return 0;
     float4* scratch = nullptr;
-    if (int e = dev_alloc(ctx, &scratch, (size_t)npairs * ds.cap, "native")) return e;
+    if (int e = tmp_alloc(ctx, &scratch, (size_t)npairs * ds.cap, "native")) return e;
     static bool attr = false;
     size_t smem = 27000 * 4 + NAT_WORDS * 4 + NAT_LIST * 4;
     if (!attr) { RTR_CHECK(cudaFuncSetAttribute(k_native_pair_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "native"); attr = true; }
@@ -453,9 +453,10 @@ int rtr_native_keypoint_descriptors(rtr_cloud* c, const float* host_kp_xyz1, int
                                     int* host_occ_count, float* host_tdf, int* host_voxel_count) {
     if (!c || !p || n_kp < 0 || (n_kp > 0 && !host_kp_xyz1)) return rtr_fail("native", "bad argument", RTR_ERR_INVALID);
     rtr_context* ctx = c->ctx;
+    TmpScope tmp_scope(ctx);
     RTR_CHECK(cudaSetDevice(ctx->device), "native");
     float4* d_kps = nullptr;
-    if (int e = dev_alloc(ctx, &d_kps, n_kp, "native")) return e;
+    if (int e = tmp_alloc(ctx, &d_kps, n_kp, "native")) return e;
     if (n_kp) RTR_CHECK(cudaMemcpyAsync(d_kps, host_kp_xyz1, (size_t)n_kp * 16, cudaMemcpyHostToDevice, ctx->stream), "native");
     NatDesc d;
     if (int e = nat_describe(c, d_kps, n_kp, p, host_tdf || host_voxel_count, d)) return e;
@@ -484,10 +485,11 @@ int rtr_native_pair_scores(rtr_cloud* model, const float* host_model_kp_xyz1, in
                            int ks, const rtr_native_params* p, float* host_score, int* host_best_step, float* host_transform16) {
     if (!model || !scan || !p || km < 0 || ks < 0 || model->ctx != scan->ctx) return rtr_fail("native", "bad argument", RTR_ERR_INVALID);
     rtr_context* ctx = model->ctx;
+    TmpScope tmp_scope(ctx);
     RTR_CHECK(cudaSetDevice(ctx->device), "native");
     float4 *d_mk = nullptr, *d_sk = nullptr;
-    if (int e = dev_alloc(ctx, &d_mk, km, "native")) return e;
-    if (int e = dev_alloc(ctx, &d_sk, ks, "native")) return e;
+    if (int e = tmp_alloc(ctx, &d_mk, km, "native")) return e;
+    if (int e = tmp_alloc(ctx, &d_sk, ks, "native")) return e;
     if (km) RTR_CHECK(cudaMemcpyAsync(d_mk, host_model_kp_xyz1, (size_t)km * 16, cudaMemcpyHostToDevice, ctx->stream), "native");
     if (ks) RTR_CHECK(cudaMemcpyAsync(d_sk, host_scan_kp_xyz1, (size_t)ks * 16, cudaMemcpyHostToDevice, ctx->stream), "native");
     NatDesc dm, ds;
@@ -510,6 +512,7 @@ int rtr_native_pair_scores(rtr_cloud* model, const float* host_model_kp_xyz1, in
 int rtr_native_register(rtr_cloud* model, rtr_cloud* scan, const rtr_native_params* p, rtr_pose_result* host_result) {
     if (!model || !scan || !p || !host_result || model->ctx != scan->ctx) return rtr_fail("native", "bad argument", RTR_ERR_INVALID);
     rtr_context* ctx = model->ctx;
+    TmpScope tmp_scope(ctx);
     RTR_CHECK(cudaSetDevice(ctx->device), "native");
     // ModelPoint::getKeypoint / ScanPoint::getKeypoint (model_point.h:127-136): Harris r = 0.05, thr = 0.01, NMS, refine
     rtr_cloud* cl[2] = {model, scan};
@@ -528,8 +531,8 @@ int rtr_native_register(rtr_cloud* model, rtr_cloud* scan, const rtr_native_para
     float *score = nullptr, *transform = nullptr; int *best = nullptr, *pair_list = nullptr;
     if (int e = nat_pairs(ctx, dm, ds, p, &score, &best, &transform)) return e;
     rtr_pose_result* d_res = nullptr;
-    if (int e = dev_alloc(ctx, &d_res, 1, "native")) return e;
-    if (int e = dev_alloc(ctx, &pair_list, (size_t)km * ks, "native")) return e;
+    if (int e = tmp_alloc(ctx, &d_res, 1, "native")) return e;
+    if (int e = tmp_alloc(ctx, &pair_list, (size_t)km * ks, "native")) return e;
     k_native_consensus<<<1, 1024, 0, ctx->stream>>>(dm.kps, km, ds.kps, ks, dm.number, ds.number, score, transform, *p, pair_list, d_res);
     RTR_LAUNCH_CHECK(ctx, "native.consensus");
     RTR_CHECK(cudaMemcpyAsync(ctx->pinned, d_res, sizeof(rtr_pose_result), cudaMemcpyDeviceToHost, ctx->stream), "native");

@@ -210,18 +210,19 @@ int rtr_ransac_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_ransac_params* p, r
         return rtr_fail("ransac", "rtr_match_features(source, target, k >= correspondence_k) must run first", RTR_ERR_NOT_READY);
     if (!(p->max_correspondence_distance > 0.f)) return rtr_fail("ransac", "max_correspondence_distance must be > 0", RTR_ERR_INVALID);
     DevGrid* g;
-    if (int e = rtr_get_grid(tgt, p->max_correspondence_distance, &g)) return e;
+    // any cached grid whose cells are at least d_max wide (and not much wider) serves the 27-cell inlier test
+    if (int e = rtr_get_grid_any(tgt, p->max_correspondence_distance, p->max_correspondence_distance * 1.001f, p->max_correspondence_distance * 2.0f, &g)) return e;
     const long long CHUNK = 1 << 20;
     int cap = (int)std::min<long long>(CHUNK, h1 - h0);
     // slices of the source per surviving hypothesis: ~2048 points each, fewer when the partial arrays would get large
     int split = std::max(1, std::min(16, (src->n + 2047) / 2048));
     while (split > 1 && (long long)cap * split > (1LL << 22)) split /= 2;
     int *survivors = nullptr, *count = nullptr, *pcnt = nullptr; float* poses = nullptr; double* psum = nullptr;
-    if (int e = dev_alloc(ctx, &survivors, cap, "ransac")) return e;
-    if (int e = dev_alloc(ctx, &count, 1, "ransac")) return e;
-    if (int e = dev_alloc(ctx, &pcnt, (size_t)cap * split, "ransac")) return e;
-    if (int e = dev_alloc(ctx, &psum, (size_t)cap * split, "ransac")) return e;
-    if (int e = dev_alloc(ctx, &poses, (size_t)cap * 16, "ransac")) return e;
+    if (int e = tmp_alloc(ctx, &survivors, cap, "ransac")) return e;
+    if (int e = tmp_alloc(ctx, &count, 1, "ransac")) return e;
+    if (int e = tmp_alloc(ctx, &pcnt, (size_t)cap * split, "ransac")) return e;
+    if (int e = tmp_alloc(ctx, &psum, (size_t)cap * split, "ransac")) return e;
+    if (int e = tmp_alloc(ctx, &poses, (size_t)cap * 16, "ransac")) return e;
     RansacArgs a;
     a.src = src->pts; a.ns = src->n; a.tgt = tgt->pts; a.nt = tgt->n;
     a.knn = src->knn; a.knn_stride = src->knn_k; a.k = p->correspondence_k; a.seed = p->seed;
@@ -513,33 +514,36 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     int n = src->n;
     if (int e = rtr_ensure_bbox(tgt)) return e;
     DevGrid* g;
-    if (int e = rtr_get_grid(tgt, rtr_icp_cell(tgt), &g)) return e;
+    {   // the exact 1-NN search works on any grid: reuse a cached one of comparable cell size
+        float want = rtr_icp_cell(tgt);
+        if (int e = rtr_get_grid_any(tgt, want, want * 0.6f, want * 1.7f, &g)) return e;
+    }
     GridView v = rtr_view(g);
     float4* cur = nullptr; IcpState* st = nullptr; double* partials = nullptr;
     int nb = std::max(nblk(n, ICP_THREADS), 1);
-    if (int e = dev_alloc(ctx, &cur, n, "icp")) return e;
-    if (int e = dev_alloc(ctx, &st, 1, "icp")) return e;
+    if (int e = tmp_alloc(ctx, &cur, n, "icp")) return e;
+    if (int e = tmp_alloc(ctx, &st, 1, "icp")) return e;
     const int nbw = std::max(1, std::min(nblk(n, ICPW_WARPS), ctx->sm_count * 8));    // CTAs of the warp-per-query kernels
-    if (int e = dev_alloc(ctx, &partials, (size_t)std::max(nb, nbw) * ICP_NSUM, "icp")) return e;
+    if (int e = tmp_alloc(ctx, &partials, (size_t)std::max(nb, nbw) * ICP_NSUM, "icp")) return e;
     k_icp_init<<<nb, ICP_THREADS, 0, ctx->stream>>>(src->pts, n, d_init_pose16, init_from_result ? d_result : nullptr, cur, st);
     RTR_LAUNCH_CHECK(ctx, "icp.init");
     const float4* src_pts = src->pts;
     float4 *cur2 = nullptr, *src2 = nullptr;
     if (n >= 16384 && tgt->n >= 1) {
         int *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr; char* temp = nullptr;
-        if (int e = dev_alloc(ctx, &keys, n, "icp")) return e;
-        if (int e = dev_alloc(ctx, &vals, n, "icp")) return e;
-        if (int e = dev_alloc(ctx, &keys2, n, "icp")) return e;
-        if (int e = dev_alloc(ctx, &vals2, n, "icp")) return e;
-        if (int e = dev_alloc(ctx, &cur2, n, "icp")) return e;
-        if (int e = dev_alloc(ctx, &src2, n, "icp")) return e;
+        if (int e = tmp_alloc(ctx, &keys, n, "icp")) return e;
+        if (int e = tmp_alloc(ctx, &vals, n, "icp")) return e;
+        if (int e = tmp_alloc(ctx, &keys2, n, "icp")) return e;
+        if (int e = tmp_alloc(ctx, &vals2, n, "icp")) return e;
+        if (int e = tmp_alloc(ctx, &cur2, n, "icp")) return e;
+        if (int e = tmp_alloc(ctx, &src2, n, "icp")) return e;
         k_icp_cell_keys<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, cur, n, keys, vals);
         RTR_LAUNCH_CHECK(ctx, "icp.keys");
         int end_bit = 1;
         while ((1LL << end_bit) < (long long)g->ncells) ++end_bit;
         size_t tb = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys2, vals, vals2, n, 0, end_bit, ctx->stream);
-        if (int e = dev_alloc(ctx, &temp, tb, "icp")) return e;
+        if (int e = tmp_alloc(ctx, &temp, tb, "icp")) return e;
         RTR_CHECK(cub::DeviceRadixSort::SortPairs(temp, tb, keys, keys2, vals, vals2, n, 0, end_bit, ctx->stream), "icp.sort");
         RTR_MARK(ctx, "icp.cub_sort");
         k_icp_permute<<<nb, ICP_THREADS, 0, ctx->stream>>>(cur, src->pts, vals2, n, cur2, src2);
@@ -591,9 +595,10 @@ extern "C" {
 int rtr_ransac_prerejective(rtr_cloud* source, rtr_cloud* target, const rtr_ransac_params* p, rtr_pose_result* host_result) {
     if (!source || !target || !p || !host_result || source->ctx != target->ctx) return rtr_fail("ransac", "bad argument", RTR_ERR_INVALID);
     rtr_context* ctx = source->ctx;
+    TmpScope tmp_scope(ctx);
     RTR_CHECK(cudaSetDevice(ctx->device), "ransac");
     rtr_pose_result* d_res = nullptr;
-    if (int e = dev_alloc(ctx, &d_res, 1, "ransac")) return e;
+    if (int e = tmp_alloc(ctx, &d_res, 1, "ransac")) return e;
     if (int e = rtr_ransac_dev(source, target, p, d_res)) return e;
     int rc = fetch_result(ctx, d_res, host_result);
     dev_free(ctx, d_res);
@@ -603,11 +608,12 @@ int rtr_ransac_prerejective(rtr_cloud* source, rtr_cloud* target, const rtr_rans
 int rtr_icp(rtr_cloud* source, rtr_cloud* target, const rtr_icp_params* p, const float* init_pose16, rtr_pose_result* host_result) {
     if (!source || !target || !p || !host_result || source->ctx != target->ctx || p->max_iterations < 0) return rtr_fail("icp", "bad argument", RTR_ERR_INVALID);
     rtr_context* ctx = source->ctx;
+    TmpScope tmp_scope(ctx);
     RTR_CHECK(cudaSetDevice(ctx->device), "icp");
     rtr_pose_result* d_res = nullptr; float* d_init = nullptr;
-    if (int e = dev_alloc(ctx, &d_res, 1, "icp")) return e;
+    if (int e = tmp_alloc(ctx, &d_res, 1, "icp")) return e;
     if (init_pose16) {
-        if (int e = dev_alloc(ctx, &d_init, 16, "icp")) return e;
+        if (int e = tmp_alloc(ctx, &d_init, 16, "icp")) return e;
         RTR_CHECK(cudaMemcpyAsync(d_init, init_pose16, 64, cudaMemcpyHostToDevice, ctx->stream), "icp");
     }
     if (int e = rtr_icp_dev(source, target, p, d_init, 0, d_res)) return e;
@@ -619,6 +625,7 @@ int rtr_icp(rtr_cloud* source, rtr_cloud* target, const rtr_icp_params* p, const
 int rtr_register(rtr_cloud* model, rtr_cloud* scene, const rtr_register_params* p, rtr_pose_result* host_result) {
     if (!model || !scene || !p || !host_result || model->ctx != scene->ctx) return rtr_fail("register", "bad argument", RTR_ERR_INVALID);
     rtr_context* ctx = model->ctx;
+    TmpScope tmp_scope(ctx);
     RTR_CHECK(cudaSetDevice(ctx->device), "register");
     rtr_cloud* cl[2] = {model, scene};
     int* d_cnt[2] = {nullptr, nullptr};
@@ -631,7 +638,7 @@ int rtr_register(rtr_cloud* model, rtr_cloud* scene, const rtr_register_params* 
     }
     if (int e = rtr_match_dev(model, scene, p->ransac.correspondence_k)) return e;
     rtr_pose_result* d_res = nullptr;
-    if (int e = dev_alloc(ctx, &d_res, 1, "register")) return e;
+    if (int e = tmp_alloc(ctx, &d_res, 1, "register")) return e;
     if (int e = rtr_ransac_dev(model, scene, &p->ransac, d_res)) return e;
     if (p->run_icp) if (int e = rtr_icp_dev(model, scene, &p->icp, nullptr, 1, d_res)) return e;
     k_set_keypoints<<<1, 32, 0, ctx->stream>>>(d_res, d_cnt[0], d_cnt[1]);

@@ -86,11 +86,12 @@ int rtr_tdf_batch(rtr_context* ctx, const int* host_occ, const int* host_occ_off
     int total = host_occ_offsets[n_grids];
     if (total > 0 && !host_occ) return rtr_fail("tdf", "null occupied list", RTR_ERR_INVALID);
     RTR_CHECK(cudaSetDevice(ctx->device), "tdf");
+    TmpScope tmp_scope(ctx);
     int nv = dim * dim * dim;
     int *d_occ = nullptr, *d_off = nullptr; float* d_out = nullptr;
-    if (int e = dev_alloc(ctx, &d_occ, (size_t)total * 3, "tdf")) return e;
-    if (int e = dev_alloc(ctx, &d_off, (size_t)n_grids + 1, "tdf")) return e;
-    if (int e = dev_alloc(ctx, &d_out, (size_t)n_grids * nv, "tdf")) return e;
+    if (int e = tmp_alloc(ctx, &d_occ, (size_t)total * 3, "tdf")) return e;
+    if (int e = tmp_alloc(ctx, &d_off, (size_t)n_grids + 1, "tdf")) return e;
+    if (int e = tmp_alloc(ctx, &d_out, (size_t)n_grids * nv, "tdf")) return e;
     if (total > 0) RTR_CHECK(cudaMemcpyAsync(d_occ, host_occ, (size_t)total * 12, cudaMemcpyHostToDevice, ctx->stream), "tdf.h2d");
     RTR_CHECK(cudaMemcpyAsync(d_off, host_occ_offsets, ((size_t)n_grids + 1) * 4, cudaMemcpyHostToDevice, ctx->stream), "tdf.h2d");
     if (int e = tdf_launch(ctx, d_occ, d_off, n_grids, dim, nv, (size_t)nv, d_out)) return e;

@@ -126,7 +126,7 @@ def test_nearest_identical(api, gpu_ctx, orc, clouds):
 
 
 # ------------------------------------------------------------------ per-cloud stages
-@pytest.mark.parametrize("name", ["chair1", "mcloud", "T0_m8111", "desk1", "sofa"])
+@pytest.mark.parametrize("name", ["chair1", "mcloud", "T0_m8111", "desk1", "sofa", "chair4"])
 def test_normals_harris_fpfh(api, gpu_ctx, orc, clouds, name):
     pts = clouds(name)
     c = api.Cloud(gpu_ctx, pts)
