@@ -86,8 +86,21 @@ typedef struct rtr_native_params {
     int   quirk_skip_first_voxel;  /* B#5:  key_point.h:298 (i = 1), matching.h:179 (p = 1) */
     int   quirk_running_score;     /* B#4:  distance_temp not reset between angles, matching.h:141,187,189 */
     int   quirk_integer_screens;   /* B#9, B#10: float(2/3) == 0 and integer division, function.h:161,167,174 */
-    int   pad_;
+    int   use_plane_areas;         /* 1: getArea + get_Vector3D feed match_by_area (RealTimeRobot.cpp:41,47,57,67); 0: KeyPoint defaults 0.16 */
 } rtr_native_params;
+
+/* One peeled plane of ModelPoint::getArea / ScanPoint::get_Area (model_point.h:170-245): the reference's Surface
+ * (key_point.h:47-51: Area, Coefficients, IsVertical) plus bookkeeping. */
+typedef struct rtr_surface {
+    double area;              /* pcl::ConvexHull::getTotalArea of the plane's inliers */
+    float  coefficients[4];   /* refined plane a x + b y + c z + d = 0 */
+    int    is_vertical;       /* Surface::IsVertical (is_v_plane, model_point.h:65-79) */
+    int    inliers;           /* points removed with this plane */
+    int    dimension;         /* 2 or 3: the hull dimension ConvexHull detects */
+    int    iterations;        /* RANSAC iterations run (adaptive, <= 151) */
+    int    kept;              /* 1 if pushed to ModelPoint::surface: horizontal / vertical within 10 degrees and area >= 0.16 */
+    int    pad_;
+} rtr_surface;
 
 /* fixed 128-byte record: the unit of the multi-GPU all-gather. */
 typedef struct rtr_pose_result {
@@ -224,6 +237,11 @@ int rtr_tdf_batch(rtr_context* ctx, const int* host_occ, const int* host_occ_off
 /* Same with device pointers, asynchronous on the context stream. */
 int rtr_tdf_batch_dev(rtr_context* ctx, const int* dev_occ, const int* dev_occ_offsets, int n_grids,
                       int dim, float* dev_tdf_out);
+
+/* ModelPoint::getArea / ScanPoint::get_Area (model_point.h:170-245, scan_point.h:117-188): peel planes with
+ * SACSegmentation(PLANE, RANSAC, 150 it, 5 mm, optimised) until <= 15 % of the points remain, convex-hull area of each.
+ * host_surfaces receives EVERY peeled plane in order (kept = 1 marks those the reference pushes to `surface`). */
+int rtr_plane_areas(rtr_cloud* c, rtr_surface* host_surfaces, int capacity, int* n_planes);
 
 /* ---- the reference's own pipeline, batched on the device ---- */
 void rtr_native_default_params(rtr_native_params* p);

@@ -27,6 +27,7 @@
 #include "../include/rtr.h"
 
 extern "C" void orc_tdf(const int* occ, int num_occ, int dim, float* out);
+extern "C" int orc_plane_areas(const float* xyz1, int n, rtr_surface* out, int capacity);
 
 namespace {
 
@@ -114,6 +115,23 @@ void orc_native_default_params(rtr_native_params* p) {
     std::memset(p, 0, sizeof(*p));
     p->resolution = 0.01f; p->occ_half = 0.1f; p->tdf_half = 0.15f;
     p->pair_gate = 3.0f; p->consensus_distance = 0.15f; p->consensus_score = 100.0f;
+    p->use_plane_areas = 1;
+}
+
+// KeyPoint::get_Vector3D (key_point.h:87-111) with getDistance (key_point.h:38-43): areas of <= 1 horizontal plane within
+// 5 cm and <= 2 vertical planes within 2 cm of the keypoint, verticals in descending order; defaults 0.16 (key_point.h:83-84)
+void orc_native_vector3d(const float* kp_xyz1, const rtr_surface* surfaces, int n_surfaces, double* vector3d) {
+    vector3d[0] = vector3d[1] = vector3d[2] = 0.16;
+    int vertical = 0, horizontal = 0;
+    for (int i = 0; i < n_surfaces; ++i) {
+        if (!surfaces[i].kept) continue;
+        const float* v = surfaces[i].coefficients;
+        double d = (double)std::sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+        double distance = (double)std::fabs(((v[0] * kp_xyz1[0] + v[1] * kp_xyz1[1]) + v[2] * kp_xyz1[2]) + v[3]) / d;
+        if (surfaces[i].is_vertical == 0 && horizontal == 0 && distance <= 0.05) { vector3d[0] = surfaces[i].area; horizontal++; }
+        else if (surfaces[i].is_vertical == 1 && vertical <= 1 && distance <= 0.02) { vector3d[1 + vertical] = surfaces[i].area; vertical++; }
+    }
+    if (vector3d[1] < vector3d[2]) std::swap(vector3d[1], vector3d[2]);
 }
 
 // KeyPoint::getOccupiedGrid: indices (ascending) of the points inside the inclusive float box, and Occupiedgrid.Number
@@ -229,7 +247,13 @@ void orc_native_register(const float* model_xyz1, int nm, const float* model_kp,
     std::memset(res, 0, sizeof(*res));
     identity16(res->pose);
     res->fitness = FLT_MAX; res->hypothesis = -1;
-    const double def_area[3] = {0.16, 0.16, 0.16};
+    std::vector<double> marea((size_t)km * 3, 0.16), sarea((size_t)ks * 3, 0.16);
+    if (p->use_plane_areas) {                                              // modelpoint.getArea(mcloud), scanpoint.get_Area(cloud)
+        std::vector<rtr_surface> ms(256), ss(256);
+        int nms = std::min(orc_plane_areas(model_xyz1, nm, ms.data(), 256), 256), nss = std::min(orc_plane_areas(scan_xyz1, ns, ss.data(), 256), 256);
+        for (int k = 0; k < km; ++k) orc_native_vector3d(model_kp + 4 * k, ms.data(), nms, &marea[3 * k]);
+        for (int s = 0; s < ks; ++s) orc_native_vector3d(scan_kp + 4 * s, ss.data(), nss, &sarea[3 * s]);
+    }
     std::vector<std::vector<P4>> mocc(km), socc(ks);
     std::vector<int> mnum(km), snum(ks);
     std::vector<std::vector<float>> tdf(km, std::vector<float>(27000, 0.f));
@@ -253,7 +277,7 @@ void orc_native_register(const float* model_xyz1, int nm, const float* model_kp,
             Pair pr; pr.k = k; pr.s = s;
             pr.score = orc_native_pair_score(model_kp + 4 * k, tdf[k].data(), (const float*)socc[s].data(), (int)socc[s].size(), scan_kp + 4 * s, p, nullptr, pr.T);
             bool gate = pr.score < p->pair_gate;
-            if (gate && orc_native_screens(model_kp + 4 * k, scan_kp + 4 * s, def_area, def_area, mnum[k], snum[s], p)) pairs.push_back(pr);
+            if (gate && orc_native_screens(model_kp + 4 * k, scan_kp + 4 * s, &marea[3 * k], &sarea[3 * s], mnum[k], snum[s], p)) pairs.push_back(pr);
         }
     res->evaluated = (long long)pairs.size();
     int best_in = 0;

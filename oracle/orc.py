@@ -8,7 +8,7 @@ import subprocess
 
 import numpy as np
 
-from realtime_robot_b200.params import IcpParams, NativeParams, PoseResult, RansacParams, RegisterParams
+from realtime_robot_b200.params import IcpParams, NativeParams, PoseResult, RansacParams, RegisterParams, Surface
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -35,6 +35,10 @@ def lib():
         _LIB.orc_native_pair_score.restype = C.c_float
         _LIB.orc_native_occupancy.restype = C.c_int
         _LIB.orc_native_tdf_voxels.restype = C.c_int
+        _LIB.orc_hull_area.restype = C.c_double
+        _LIB.orc_plane_areas.restype = C.c_int
+        _LIB.orc_plane_segment.restype = C.c_int
+        _LIB.orc_plane_class.restype = C.c_int
     return _LIB
 
 
@@ -207,3 +211,27 @@ def native_register(model, model_kp, scan, scan_kp, params: NativeParams) -> Pos
     res = PoseResult()
     lib().orc_native_register(_p(model), len(model), _p(mk), len(mk), _p(scan), len(scan), _p(sk), len(sk), C.byref(params), C.byref(res))
     return res
+
+
+# ------------------------------------------------------------------ getArea (oracle/planes.cpp)
+def plane_areas(xyz1, capacity=256):
+    xyz1 = _f(xyz1)
+    buf = (Surface * capacity)()
+    n = lib().orc_plane_areas(_p(xyz1), len(xyz1), buf, capacity)
+    return [buf[i] for i in range(min(n, capacity))]
+
+
+def hull_area(xyz1):
+    xyz1 = _f(xyz1)
+    dim = C.c_int()
+    a = lib().orc_hull_area(_p(xyz1), len(xyz1), C.byref(dim))
+    return float(a), dim.value
+
+
+def plane_segment(xyz1, threshold=0.005, max_iterations=150):
+    xyz1 = _f(xyz1)
+    coeff = np.zeros(4, np.float32)
+    idx = np.zeros(max(len(xyz1), 1), np.int32)
+    its = C.c_int()
+    m = lib().orc_plane_segment(_p(xyz1), len(xyz1), C.c_float(threshold), max_iterations, _p(coeff), _p(idx, C.c_int), C.byref(its))
+    return coeff, idx[:m].copy(), its.value

@@ -5,7 +5,7 @@ There is no CPU fallback: if the library is missing or cannot be loaded, importi
 import ctypes as C
 import os
 
-from .params import IcpParams, NativeParams, PoseResult, RansacParams, RegisterParams
+from .params import IcpParams, NativeParams, PoseResult, RansacParams, RegisterParams, Surface
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librtr.so")
@@ -18,7 +18,7 @@ EXPORTS = [
     "rtr_cloud_free", "rtr_cloud_size", "rtr_cloud_transform", "rtr_cloud_download", "rtr_radius_neighbors", "rtr_nearest",
     "rtr_normals", "rtr_harris3d", "rtr_fpfh", "rtr_match_features", "rtr_match_features_raw", "rtr_match_last_stats", "rtr_ransac_prerejective", "rtr_icp", "rtr_register",
     "rtr_register_host", "ComputeTDFWithCuda", "rtr_tdf_batch", "rtr_tdf_batch_dev", "rtr_native_default_params", "rtr_native_keypoint_descriptors",
-    "rtr_native_pair_scores", "rtr_native_register",
+    "rtr_native_pair_scores", "rtr_native_register", "rtr_plane_areas",
 ]
 
 
@@ -73,6 +73,7 @@ def lib():
         L.rtr_native_default_params.argtypes = [C.POINTER(NativeParams)]
         L.rtr_native_keypoint_descriptors.argtypes = [vp, vp, C.c_int, C.POINTER(NativeParams), vp, vp, vp, vp]
         L.rtr_native_pair_scores.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, C.POINTER(NativeParams), vp, vp, vp]
+        L.rtr_plane_areas.argtypes = [vp, C.POINTER(Surface), C.c_int, ip]
         L.rtr_native_register.argtypes = [vp, vp, C.POINTER(NativeParams), C.POINTER(PoseResult)]
         _LIB = L
     return _LIB

@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .params import (IcpParams, NativeParams, PoseResult, RansacParams, RegisterParams, default_native_params,  # noqa: F401
+from .params import (IcpParams, NativeParams, PoseResult, RansacParams, RegisterParams, Surface, default_native_params,  # noqa: F401
                      default_register_params, pose_to_colmajor)
 
 
@@ -252,3 +252,11 @@ def native_register(model: Cloud, scan: Cloud, params: NativeParams) -> PoseResu
     res = PoseResult()
     _lib.check("rtr_native_register", _lib.lib().rtr_native_register(model._h, scan._h, C.byref(params), C.byref(res)))
     return res
+
+
+def plane_areas(cloud: Cloud, capacity: int = 256):
+    """ModelPoint::getArea / ScanPoint::get_Area: every peeled plane, in order (Surface records; .kept marks `surface` entries)."""
+    buf = (Surface * capacity)()
+    n = C.c_int()
+    _lib.check("rtr_plane_areas", _lib.lib().rtr_plane_areas(cloud._h, buf, capacity, C.byref(n)))
+    return [buf[i] for i in range(n.value)]

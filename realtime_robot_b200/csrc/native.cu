@@ -303,11 +303,28 @@ __global__ void __launch_bounds__(NAT_THREADS) k_native_pair_score(const float4*
     }
 }
 
+// KeyPoint::get_Vector3D (key_point.h:87-111) over the kept surfaces of a cloud, with getDistance (key_point.h:38-43)
+struct NatSurface { float c[4]; double area; int is_vertical; int pad; };
+__device__ void nat_vector3d(float4 kp, const NatSurface* __restrict__ surf, int ns, double* v3) {
+    v3[0] = v3[1] = v3[2] = 0.16;
+    int vertical = 0, horizontal = 0;
+    for (int i = 0; i < ns; ++i) {
+        const float* v = surf[i].c;
+        double d = (double)__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(v[0], v[0]), __fmul_rn(v[1], v[1])), __fmul_rn(v[2], v[2])));
+        double distance = (double)fabsf(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v[0], kp.x), __fmul_rn(v[1], kp.y)), __fmul_rn(v[2], kp.z)), v[3])) / d;
+        if (surf[i].is_vertical == 0 && horizontal == 0 && distance <= 0.05) { v3[0] = surf[i].area; horizontal++; }
+        else if (surf[i].is_vertical == 1 && vertical <= 1 && distance <= 0.02) { v3[1 + vertical] = surf[i].area; vertical++; }
+    }
+    if (v3[1] < v3[2]) { double t = v3[1]; v3[1] = v3[2]; v3[2] = t; }
+}
+
 // ---- screens (function.h:158-178), pair list (RealTimeRobot.cpp:70-102) and exhaustive consensus (function.h:35-109)
 __global__ void __launch_bounds__(1024) k_native_consensus(const float4* __restrict__ mkp, int km, const float4* __restrict__ skp, int ks,
                                                            const int* __restrict__ mnum, const int* __restrict__ snum,
                                                            const float* __restrict__ score, const float* __restrict__ transform,
-                                                           rtr_native_params p, int* __restrict__ pair_list, rtr_pose_result* __restrict__ res) {
+                                                           const NatSurface* __restrict__ msurf, int n_msurf, const NatSurface* __restrict__ ssurf,
+                                                           int n_ssurf, rtr_native_params p, int* __restrict__ pair_list,
+                                                           rtr_pose_result* __restrict__ res) {
     __shared__ int s_np;
     __shared__ int s_in[1024];
     int npairs = km * ks;
@@ -325,7 +342,16 @@ __global__ void __launch_bounds__(1024) k_native_consensus(const float4* __restr
                 float t = p.quirk_integer_screens ? (float)(mnum[k] / snum[s]) : __fdiv_rn((float)mnum[k], (float)snum[s]);
                 occ = !(t > 2.f || t < 0.5f);
             }
-            if (gate && height && occ) pair_list[c++] = q;
+            // match_by_area (function.h:165-170) on the keypoints' three plane areas
+            bool area = true;
+            if (gate && height && occ) {
+                double a1[3], a2[3];
+                nat_vector3d(mkp[k], msurf, n_msurf, a1);
+                nat_vector3d(skp[s], ssurf, n_ssurf, a2);
+                double lo = p.quirk_integer_screens ? 0.0 : 1.0 / 3.0;
+                for (int a = 0; a < 3; ++a) { double r = a1[a] / a2[a]; if (r > 3 || r < lo) area = false; }
+            }
+            if (gate && height && occ && area) pair_list[c++] = q;
         }
         s_np = c;
         for (int i = 0; i < 16; ++i) res->pose[i] = (i % 5 == 0) ? 1.f : 0.f;
@@ -447,6 +473,7 @@ void rtr_native_default_params(rtr_native_params* p) {
     memset(p, 0, sizeof(*p));
     p->resolution = 0.01f; p->occ_half = 0.1f; p->tdf_half = 0.15f;
     p->pair_gate = 3.0f; p->consensus_distance = 0.15f; p->consensus_score = 100.0f;
+    p->use_plane_areas = 1;
 }
 
 int rtr_native_keypoint_descriptors(rtr_cloud* c, const float* host_kp_xyz1, int n_kp, const rtr_native_params* p, int* host_number,
@@ -533,7 +560,30 @@ int rtr_native_register(rtr_cloud* model, rtr_cloud* scan, const rtr_native_para
     rtr_pose_result* d_res = nullptr;
     if (int e = tmp_alloc(ctx, &d_res, 1, "native")) return e;
     if (int e = tmp_alloc(ctx, &pair_list, (size_t)km * ks, "native")) return e;
-    k_native_consensus<<<1, 1024, 0, ctx->stream>>>(dm.kps, km, ds.kps, ks, dm.number, ds.number, score, transform, *p, pair_list, d_res);
+    // modelpoint.getArea(mcloud) / scanpoint.get_Area(cloud) (RealTimeRobot.cpp:41,47): the kept surfaces of both clouds
+    NatSurface* d_surf[2] = {nullptr, nullptr};
+    int n_surf[2] = {0, 0};
+    if (p->use_plane_areas) {
+        for (int i = 0; i < 2; ++i) {
+            std::vector<rtr_surface> all(256);
+            int np = 0;
+            int rcp = rtr_plane_areas(cl[i], all.data(), 256, &np);
+            if (rcp != 0 && rcp != RTR_ERR_CAPACITY) return rcp;
+            std::vector<NatSurface> kept;
+            for (int j = 0; j < std::min(np, 256); ++j) if (all[j].kept) {
+                NatSurface sf; memcpy(sf.c, all[j].coefficients, sizeof(sf.c)); sf.area = all[j].area; sf.is_vertical = all[j].is_vertical; sf.pad = 0;
+                kept.push_back(sf);
+            }
+            n_surf[i] = (int)kept.size();
+            if (int e = tmp_alloc(ctx, &d_surf[i], kept.size(), "native")) return e;
+            if (!kept.empty()) {
+                RTR_CHECK(cudaMemcpyAsync(d_surf[i], kept.data(), kept.size() * sizeof(NatSurface), cudaMemcpyHostToDevice, ctx->stream), "native");
+                RTR_CHECK(cudaStreamSynchronize(ctx->stream), "native");      // `kept` is a stack temporary
+            }
+        }
+    }
+    k_native_consensus<<<1, 1024, 0, ctx->stream>>>(dm.kps, km, ds.kps, ks, dm.number, ds.number, score, transform, d_surf[0], n_surf[0],
+                                                     d_surf[1], n_surf[1], *p, pair_list, d_res);
     RTR_LAUNCH_CHECK(ctx, "native.consensus");
     RTR_CHECK(cudaMemcpyAsync(ctx->pinned, d_res, sizeof(rtr_pose_result), cudaMemcpyDeviceToHost, ctx->stream), "native");
     RTR_CHECK(cudaStreamSynchronize(ctx->stream), "native");

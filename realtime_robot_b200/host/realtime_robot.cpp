@@ -34,6 +34,7 @@ int main(int argc, char** argv) {
     }
     ModelPoint modelpoint(mcloud);
     modelpoint.getKeypoint();
+    if (native) { modelpoint.getArea(mcloud); std::cout << "model surfaces kept: " << modelpoint.surface.size() << std::endl; }     // RealTimeRobot.cpp:41
     auto start = std::chrono::steady_clock::now();          // RealTimeRobot.cpp:43
     ScanPoint scanpoint(cloud);
     scanpoint.getKeypoint();

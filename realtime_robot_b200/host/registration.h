@@ -49,10 +49,36 @@ inline void harris_keypoints(const pcl::PointCloud<pcl::PointXYZ>& cloud, pcl::P
 
 }  // namespace rtr_host
 
+struct Surface {                         // key_point.h:47-51 (Coefficients: a, b, c, d of the plane)
+    double Area = 0;
+    float Coefficients[4] = {0, 0, 0, 0};
+    bool IsVertical = false;
+};
+
+namespace rtr_host {
+// shared body of ModelPoint::getArea / ScanPoint::get_Area (model_point.h:170-245, scan_point.h:117-188)
+inline void plane_surfaces(const pcl::PointCloud<pcl::PointXYZ>& cloud, std::vector<Surface>& surface) {
+    DeviceCloud d(cloud);
+    if (!d.h) return;
+    std::vector<rtr_surface> all(256);
+    int n = 0;
+    int rc = rtr_plane_areas(d.h, all.data(), (int)all.size(), &n);
+    if (rc != 0 && rc != RTR_ERR_CAPACITY) { std::cerr << "Could not estimate a planar model for the given dataset." << std::endl; return; }
+    for (int i = 0; i < n && i < (int)all.size(); ++i)
+        if (all[i].kept) {
+            Surface s;
+            s.Area = all[i].area; memcpy(s.Coefficients, all[i].coefficients, sizeof(s.Coefficients)); s.IsVertical = all[i].is_vertical != 0;
+            surface.push_back(s);
+        }
+}
+}  // namespace rtr_host
+
 class ModelPoint {
 public:
     pcl::PointCloud<pcl::PointXYZ>::Ptr Mpoint;
+    std::vector<Surface> surface;
     pcl::PointCloud<pcl::PointXYZ> key_coordinates;
+    void getArea(pcl::PointCloud<pcl::PointXYZ>::Ptr modelPoint) { if (modelPoint) rtr_host::plane_surfaces(*modelPoint, surface); }
     // Appendix B#1: the as-committed getKeypoint() scales the aliased model cloud by 0.01 IN PLACE before Harris runs
     // (model_point.h:105-111), which leaves no corners.  Default off; set to reproduce the shipped behaviour.
     bool quirk_scale_model_in_place = false;
@@ -76,7 +102,9 @@ public:
 class ScanPoint {
 public:
     pcl::PointCloud<pcl::PointXYZ>::Ptr Spoint;
+    std::vector<Surface> surface;
     pcl::PointCloud<pcl::PointXYZ> key_coordinates;
+    void get_Area(pcl::PointCloud<pcl::PointXYZ>::Ptr scanPoint) { if (scanPoint) rtr_host::plane_surfaces(*scanPoint, surface); }
     ScanPoint() {}
     explicit ScanPoint(pcl::PointCloud<pcl::PointXYZ>::Ptr s) : Spoint(s) {}
     void getKeypoint() {
@@ -109,12 +137,6 @@ inline void keyPointICP(pcl::PointCloud<pcl::PointXYZ>::Ptr /*SpointCloud*/, pcl
 // The reference's own descriptor records and pair logic (key_point.h, matching.h, function.h), same names and members.
 // Arithmetic runs in librtr.so (csrc/native.cu); the semantics are the INTENDED ones (matching.h:17-120) with the
 // as-committed quirks behind rtr_native_params flags.
-
-struct Surface {                         // key_point.h:47-51 (Coefficients: a, b, c, d of the plane)
-    double Area = 0;
-    float Coefficients[4] = {0, 0, 0, 0};
-    bool IsVertical = false;
-};
 
 struct OccupiedGrid {                    // key_point.h:53-57
     pcl::PointCloud<pcl::PointXYZ>::Ptr cloud;

@@ -41,17 +41,28 @@ class PoseResult(C.Structure):
 assert C.sizeof(PoseResult) == 128, C.sizeof(PoseResult)
 
 
+class Surface(C.Structure):
+    """rtr_surface: one peeled plane of ModelPoint::getArea (Surface of key_point.h:47-51 plus bookkeeping)."""
+    _fields_ = [("area", C.c_double), ("coefficients", C.c_float * 4), ("is_vertical", C.c_int), ("inliers", C.c_int),
+                ("dimension", C.c_int), ("iterations", C.c_int), ("kept", C.c_int), ("pad_", C.c_int)]
+
+    def as_tuple(self):
+        return (float(self.area), tuple(float(v) for v in self.coefficients), int(self.is_vertical), int(self.inliers),
+                int(self.dimension), int(self.iterations), int(self.kept))
+
+
 class NativeParams(C.Structure):
     """rtr_native_params: the reference's own descriptor path (key_point.h / matching.h / function.h literals)."""
     _fields_ = [("resolution", C.c_float), ("occ_half", C.c_float), ("tdf_half", C.c_float), ("pair_gate", C.c_float),
                 ("consensus_distance", C.c_float), ("consensus_score", C.c_float), ("quirk_skip_first_voxel", C.c_int),
-                ("quirk_running_score", C.c_int), ("quirk_integer_screens", C.c_int), ("pad_", C.c_int)]
+                ("quirk_running_score", C.c_int), ("quirk_integer_screens", C.c_int), ("use_plane_areas", C.c_int)]
 
 
 def default_native_params() -> NativeParams:
     p = NativeParams()
     p.resolution, p.occ_half, p.tdf_half = 0.01, 0.1, 0.15
     p.pair_gate, p.consensus_distance, p.consensus_score = 3.0, 0.15, 100.0
+    p.use_plane_areas = 1
     return p
 
 

@@ -483,3 +483,24 @@ def test_scene_reconstruction_loop(api, gpu_ctx, orc, clouds):
     # the composed scene lies on the segments (every winning model was moved back onto its segment)
     d2 = orc.nearest(np.concatenate(segments), scene, 1)[1]
     assert float(np.sqrt(d2.max())) < 5e-3
+
+
+# ------------------------------------------------------------------ ModelPoint::getArea (planes.cu)
+@pytest.mark.parametrize("name", ["chair1", "mcloud", "T0_m8111", "desk1", "sofa"])
+def test_plane_peel_and_hull_area(api, gpu_ctx, orc, clouds, name):
+    pts = clouds(name)
+    c = api.Cloud(gpu_ctx, pts)
+    g = api.plane_areas(c)
+    o = orc.plane_areas(pts)
+    assert len(g) == len(o) and len(g) > 0
+    for a, b in zip(g, o):
+        assert (a.inliers, a.dimension, a.iterations, a.kept, a.is_vertical) == (b.inliers, b.dimension, b.iterations, b.kept, b.is_vertical)
+        assert np.allclose(np.array(a.coefficients), np.array(b.coefficients), rtol=0, atol=1e-6)
+        assert abs(a.area - b.area) <= 1e-9 * max(1.0, b.area)
+    assert sum(s.inliers for s in g) >= 0.85 * len(pts)          # the loop stops at <= 15 % remaining (model_point.h:193)
+    c.free()
+    # degenerate inputs
+    for few in (np.zeros((0, 4), np.float32), pts[:2]):
+        cf = api.Cloud(gpu_ctx, few)
+        assert api.plane_areas(cf) == []
+        cf.free()
