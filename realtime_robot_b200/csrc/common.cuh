@@ -372,36 +372,60 @@ __device__ __forceinline__ void grid_nearest_warp(const GridView& g, float qx, f
     if (best >= 0 && best_d2 <= hh * hh) return;
     float ext = g.h * (float)max(g.dx, max(g.dy, g.dz));
     float slack = g.h * 1e-3f + 2e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + fabsf(g.mnx) + fabsf(g.mny) + fabsf(g.mnz) + ext);
-    for (int zdir = 0; zdir < 2; ++zdir) {
-        for (int z = zdir == 0 ? cz : cz - 1; z >= 0 && z < g.dz; z += (zdir == 0 ? 1 : -1)) {
-            float lo = g.mnz + (float)z * g.h, hi = lo + g.h;
-            float dzl = qz < lo ? lo - qz : (qz > hi ? qz - hi : 0.f);
-            dzl = fmaxf(dzl - slack, 0.f);
-            float bound = fminf(best >= 0 ? best_d2 : FLT_MAX, prune2);      // best is warp-uniform here
-            if (dzl * dzl > bound) break;
-            for (int ydir = 0; ydir < 2; ++ydir) {
-                for (int y = ydir == 0 ? cy : cy - 1; y >= 0 && y < g.dy; y += (ydir == 0 ? 1 : -1)) {
+    // Phase 2: square rings of x-rows around (cy, cz), 32 rows per step — one row per lane: box-distance test, x range
+    // clipped to the current sphere, the two range bounds.  Surfaces leave most rows empty, so the lanes mostly retire
+    // empty rows in parallel; the few non-empty ones are then scanned by the whole warp.  Ring k lies at least
+    // (k - 1) h away in y or z, which ends the walk.
+    const int kmax = max(max(cy, g.dy - 1 - cy), max(cz, g.dz - 1 - cz));
+    for (int k = 0; k <= kmax; ++k) {
+        float bound = fminf(best >= 0 ? best_d2 : FLT_MAX, prune2);      // best is warp-uniform here
+        float rm = fmaxf((float)(k - 1) * g.h - slack, 0.f);
+        if (rm * rm > bound) break;
+        const int nrows = k == 0 ? 1 : 8 * k;
+        for (int i0 = 0; i0 < nrows; i0 += 32) {
+            int i = i0 + lane, s0 = 0, s1 = 0;
+            if (i < nrows) {
+                int oy = 0, oz = 0;
+                if (k > 0) {
+                    int side = i / (2 * k), o = i - side * 2 * k;
+                    if (side == 0) { oy = -k + o; oz = -k; }
+                    else if (side == 1) { oy = k; oz = -k + o; }
+                    else if (side == 2) { oy = k - o; oz = k; }
+                    else { oy = -k; oz = k - o; }
+                }
+                int y = cy + oy, z = cz + oz;
+                if (y >= 0 && y < g.dy && z >= 0 && z < g.dz) {
+                    float lo = g.mnz + (float)z * g.h, hi = lo + g.h;
+                    float dzl = qz < lo ? lo - qz : (qz > hi ? qz - hi : 0.f);
+                    dzl = fmaxf(dzl - slack, 0.f);
                     float lo2 = g.mny + (float)y * g.h, hi2 = lo2 + g.h;
                     float dyl = qy < lo2 ? lo2 - qy : (qy > hi2 ? qy - hi2 : 0.f);
                     dyl = fmaxf(dyl - slack, 0.f);
-                    bound = fminf(best >= 0 ? best_d2 : FLT_MAX, prune2);
                     float rem = bound - (dzl * dzl + dyl * dyl);
-                    if (rem < 0.f) break;
-                    float rx = sqrtf(rem) * 1.000001f + slack;
-                    int xa = clampi(cell_coord(qx - rx, g.mnx, g.inv_h), 0, g.dx - 1);
-                    int xb = clampi(cell_coord(qx + rx, g.mnx, g.inv_h), 0, g.dx - 1);
-                    int s0 = __ldg(g.cell_begin + cell_key(g, xa, y, z));
-                    int s1 = __ldg(g.cell_begin + cell_key(g, xb, y, z) + 1);
-                    if (s1 > s0) {
-                        for (int s = s0 + lane; s < s1; s += 32) {
-                            float4 p = __ldg(g.sorted + s);
-                            float d = dist2f(qx, qy, qz, p.x, p.y, p.z);
-                            int id = __float_as_int(p.w);
-                            if (best < 0 || d < best_d2 || (d == best_d2 && id < best)) { best_d2 = d; best = id; bp = p; }
-                        }
-                        warp_argmin(best_d2, best, bp);     // keep the pruning bound uniform across the warp
+                    if (rem >= 0.f) {
+                        float rx = sqrtf(rem) * 1.000001f + slack;
+                        int xa = clampi(cell_coord(qx - rx, g.mnx, g.inv_h), 0, g.dx - 1);
+                        int xb = clampi(cell_coord(qx + rx, g.mnx, g.inv_h), 0, g.dx - 1);
+                        s0 = __ldg(g.cell_begin + cell_key(g, xa, y, z));
+                        s1 = __ldg(g.cell_begin + cell_key(g, xb, y, z) + 1);
                     }
                 }
+            }
+            unsigned m = __ballot_sync(0xffffffffu, s1 > s0);
+            if (m) {
+                while (m) {
+                    int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    int ra = __shfl_sync(0xffffffffu, s0, j), rb = __shfl_sync(0xffffffffu, s1, j);
+                    for (int s = ra + lane; s < rb; s += 32) {
+                        float4 p = __ldg(g.sorted + s);
+                        float d = dist2f(qx, qy, qz, p.x, p.y, p.z);
+                        int id = __float_as_int(p.w);
+                        if (best < 0 || d < best_d2 || (d == best_d2 && id < best)) { best_d2 = d; best = id; bp = p; }
+                    }
+                }
+                warp_argmin(best_d2, best, bp);     // keep the pruning bound uniform across the warp
+                bound = fminf(best >= 0 ? best_d2 : FLT_MAX, prune2);
             }
         }
     }

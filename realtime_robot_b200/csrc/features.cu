@@ -308,14 +308,96 @@ __device__ __forceinline__ bool pair_bins(float4 p1, float4 n1f, float4 p2, floa
     return true;
 }
 
+// fp32 screen for the three bin indices.  The bins are integers, so a cheap single-precision evaluation decides them
+// whenever every feature sits safely inside a bin; only pairs within SCREEN_MARGIN of a bin edge, near-degenerate frames
+// (d almost parallel to n1, n2 almost parallel to v) or an undecidable role swap go through the fp64 pair_bins above.
+// Error budget (t = 11 x normalised feature): fp32 rounding of d, the dot / cross products and rsqrtf / atan2f gives
+// |dt| < 1e-4 under the degeneracy guards below (sin^2 > 1e-2); the margin is 20x that.  The result is identical to
+// pair_bins by construction — the tests compare whole histograms with the oracle bit for bit.
+#define SCREEN_MARGIN 2e-3f
+__device__ __forceinline__ float dot3f(float a0, float a1, float a2, float b0, float b1, float b2) {
+    return fmaf(a2, b2, fmaf(a1, b1, a0 * b0));
+}
+__device__ __forceinline__ bool screen_roles(float n10, float n11, float n12, float n20, float n21, float n22, float u0, float u1, float u2,
+                                             float f3, int& b0, int& b1, int& b2) {
+    float v0 = fmaf(u1, n12, -u2 * n11), v1 = fmaf(u2, n10, -u0 * n12), v2 = fmaf(u0, n11, -u1 * n10);
+    float vn2 = dot3f(v0, v1, v2, v0, v1, v2);
+    float iv = rsqrtf(vn2);
+    v0 *= iv; v1 *= iv; v2 *= iv;
+    float w0 = fmaf(n11, v2, -n12 * v1), w1 = fmaf(n12, v0, -n10 * v2), w2 = fmaf(n10, v1, -n11 * v0);
+    float f2 = dot3f(v0, v1, v2, n20, n21, n22);
+    float y = dot3f(w0, w1, w2, n20, n21, n22), x = dot3f(n10, n11, n12, n20, n21, n22);
+    float f1 = atan2f(y, x);
+    float t0 = fmaf(f1, 11.0f * 0.159154943f, 5.5f);
+    float t1 = fmaf(f2, 5.5f, 5.5f);
+    float t2 = fmaf(f3, 5.5f, 5.5f);
+    float l0 = floorf(t0), l1 = floorf(t1), l2 = floorf(t2);
+    float r0 = t0 - l0, r1 = t1 - l1, r2 = t2 - l2;
+    // distance of every t to the nearest bin edge, and t inside (0, 11): one min chain, NaNs fail the comparison
+    float m = fminf(fminf(fminf(r0, 1.0f - r0), fminf(r1, 1.0f - r1)), fminf(r2, 1.0f - r2));
+    float lo = fminf(fminf(t0, t1), t2), hi = fmaxf(fmaxf(t0, t1), t2);
+    bool ok = (m > SCREEN_MARGIN) & (lo > 0.f) & (hi < 11.f) & (vn2 > 1e-2f) & (fmaf(x, x, y * y) > 1e-2f);
+    b0 = (int)l0; b1 = (int)l1; b2 = (int)l2;
+    return ok;
+}
+__device__ __forceinline__ bool pair_bins_screen(float4 p1, float4 n1, float4 p2, float4 n2, int& b0, int& b1, int& b2) {
+    float d0 = p2.x - p1.x, d1 = p2.y - p1.y, d2 = p2.z - p1.z;
+    float ss = dot3f(d0, d1, d2, d0, d1, d2);
+    if (!(ss > 1e-20f)) return false;
+    float inv = rsqrtf(ss);
+    float u0 = d0 * inv, u1 = d1 * inv, u2 = d2 * inv;
+    float a1 = dot3f(n1.x, n1.y, n1.z, u0, u1, u2), a2 = dot3f(n2.x, n2.y, n2.z, u0, u1, u2);
+    float diff = fabsf(a1) - fabsf(a2);
+    if (fabsf(diff) > 1e-5f) {
+        // role swap (|a1| < |a2|) decided: select the operands, one evaluation
+        bool sw = diff < 0.f;
+        float sg = sw ? -1.f : 1.f;
+        return screen_roles(sw ? n2.x : n1.x, sw ? n2.y : n1.y, sw ? n2.z : n1.z, sw ? n1.x : n2.x, sw ? n1.y : n2.y, sw ? n1.z : n2.z,
+                            sg * u0, sg * u1, sg * u2, sw ? -a2 : a1, b0, b1, b2);
+    }
+    // the swap cannot be decided in fp32 (flat neighbourhoods: both ~ 0): accept only if both roles give the same bins
+    int c0, c1, c2;
+    bool ok = screen_roles(n1.x, n1.y, n1.z, n2.x, n2.y, n2.z, u0, u1, u2, a1, b0, b1, b2) &
+              screen_roles(n2.x, n2.y, n2.z, n1.x, n1.y, n1.z, -u0, -u1, -u2, -a2, c0, c1, c2);
+    return ok && b0 == c0 && b1 == c1 && b2 == c2;
+}
+
 // computePointSPFHSignature: one warp per point, lanes stride over the 9 candidate ranges; the 3 x 11 bins are integer
-// counters in shared memory (integer atomics: order independent), scaled by 100 / (|N| - 1) at the end.
+// counters in shared memory (integer atomics: order independent), scaled by 100 / (|N| - 1) at the end.  Pairs the fp32
+// screen cannot decide are queued per warp and evaluated in fp64 32 at a time (dense lanes instead of divergence).
 #define SPFH_WARPS 8
+__device__ __forceinline__ void spfh_exact_one(const GridView& g, const float4* __restrict__ sn, float4 q, float4 nq, int sp, int* cnt) {
+    float4 p = __ldg(g.sorted + sp);
+    float4 nj = __ldg(sn + sp);
+    int b0, b1, b2;
+    if (pair_bins(q, nq, p, nj, b0, b1, b2)) {
+        atomicAdd(&cnt[b0], 1);
+        atomicAdd(&cnt[11 + b1], 1);
+        atomicAdd(&cnt[22 + b2], 1);
+    }
+}
+// one in-radius candidate per lane: fp32 screen -> histogram, or flag it for the fp64 queue
+__device__ __forceinline__ bool spfh_screen_one(const GridView& g, const float4* __restrict__ sn, float4 q, float4 nq, int sp, int use_screen, int* cnt) {
+    float4 p = __ldg(g.sorted + sp);
+    float4 nj = __ldg(sn + sp);
+    if (!finite3(nj)) return false;
+    int b0, b1, b2;
+    if (use_screen && pair_bins_screen(q, nq, p, nj, b0, b1, b2)) {
+        atomicAdd(&cnt[b0], 1);
+        atomicAdd(&cnt[11 + b1], 1);
+        atomicAdd(&cnt[22 + b2], 1);
+        return false;
+    }
+    return true;
+}
 __global__ void __launch_bounds__(SPFH_WARPS * 32) k_spfh(GridView g, const float4* __restrict__ sn, float r2,
-                                                          float* __restrict__ spfh_sorted) {
+                                                          float* __restrict__ spfh_sorted, int use_screen) {
     __shared__ int cnt[SPFH_WARPS][36];
+    __shared__ int cq[SPFH_WARPS][64];      // in-radius candidates waiting for a dense batch of 32
+    __shared__ int fq[SPFH_WARPS][64];      // pairs the screen could not decide
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int nwarps = gridDim.x * SPFH_WARPS;
+    const unsigned lt = (1u << lane) - 1u;
     for (int s = blockIdx.x * SPFH_WARPS + warp; s < g.n; s += nwarps) {
         cnt[warp][lane] = 0;
         if (lane < 4) cnt[warp][32 + lane] = 0;
@@ -324,7 +406,25 @@ __global__ void __launch_bounds__(SPFH_WARPS * 32) k_spfh(GridView g, const floa
         float4 nq = __ldg(sn + s);
         int qi = __float_as_int(q.w);
         bool qfin = finite3(nq);
-        int nb = 0;
+        int nb = 0, n_cand = 0, n_exact = 0;
+        // drains 32 (or the last < 32) queued candidates; uniform control flow across the warp
+        auto drain = [&](int take) {
+            n_cand -= take;
+            bool exact = false;
+            int sp = 0;
+            if (lane < take) { sp = cq[warp][n_cand + lane]; exact = spfh_screen_one(g, sn, q, nq, sp, use_screen, cnt[warp]); }
+            unsigned em = __ballot_sync(0xffffffffu, exact);
+            if (em) {
+                if (exact) fq[warp][n_exact + __popc(em & lt)] = sp;
+                n_exact += __popc(em);
+                __syncwarp();
+                if (n_exact >= 32) {
+                    n_exact -= 32;
+                    spfh_exact_one(g, sn, q, nq, fq[warp][n_exact + lane], cnt[warp]);
+                    __syncwarp();
+                }
+            }
+        };
         int cx = clampi(cell_coord(q.x, g.mnx, g.inv_h), 0, g.dx - 1);
         int cy = clampi(cell_coord(q.y, g.mny, g.inv_h), 0, g.dy - 1);
         int cz = clampi(cell_coord(q.z, g.mnz, g.inv_h), 0, g.dz - 1);
@@ -333,23 +433,28 @@ __global__ void __launch_bounds__(SPFH_WARPS * 32) k_spfh(GridView g, const floa
             for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y) {
                 int s0 = __ldg(g.cell_begin + cell_key(g, x0, y, z));
                 int s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
-                for (int sp = s0 + lane; sp < s1; sp += 32) {
-                    float4 p = __ldg(g.sorted + sp);
-                    if (dist2f(q.x, q.y, q.z, p.x, p.y, p.z) < r2) {
-                        ++nb;
-                        if (qfin && __float_as_int(p.w) != qi) {
-                            float4 nj = __ldg(sn + sp);
-                            int b0, b1, b2;
-                            if (finite3(nj) && pair_bins(q, nq, p, nj, b0, b1, b2)) {
-                                atomicAdd(&cnt[warp][b0], 1);
-                                atomicAdd(&cnt[warp][11 + b1], 1);
-                                atomicAdd(&cnt[warp][22 + b2], 1);
-                            }
-                        }
+                for (int base = s0; base < s1; base += 32) {
+                    int sp = base + lane;
+                    bool in = false, want = false;
+                    if (sp < s1) {
+                        float4 p = __ldg(g.sorted + sp);
+                        in = dist2f(q.x, q.y, q.z, p.x, p.y, p.z) < r2;
+                        want = in && qfin && __float_as_int(p.w) != qi;
+                    }
+                    nb += __popc(__ballot_sync(0xffffffffu, in));          // warp-uniform count
+                    unsigned wm = __ballot_sync(0xffffffffu, want);
+                    if (wm) {
+                        if (want) cq[warp][n_cand + __popc(wm & lt)] = sp;
+                        n_cand += __popc(wm);
+                        __syncwarp();
+                        if (n_cand >= 32) { drain(32); __syncwarp(); }
                     }
                 }
             }
-        nb = warp_sum(nb);
+        if (n_cand > 0) { drain(n_cand); __syncwarp(); }
+        if (n_exact > 0) {
+            if (lane < n_exact) spfh_exact_one(g, sn, q, nq, fq[warp][lane], cnt[warp]);
+        }
         __syncwarp();
         float* o = spfh_sorted + (size_t)s * 33;
         if (nb < 2 || !qfin) {
@@ -387,23 +492,42 @@ __global__ void __launch_bounds__(FPFH_WARPS * 32) k_fpfh_weight(GridView g, con
                 int s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
                 for (int base = s0; base < s1; base += 32) {
                     int sp = base + lane;
-                    double w = 0.0;
+                    double w = 0.0, p32 = 0.0;
                     bool in = false;
                     if (sp < s1) {
                         float4 p = __ldg(g.sorted + sp);
                         float d2 = dist2f(q.x, q.y, q.z, p.x, p.y, p.z);
                         in = d2 < r2;
-                        if (in && d2 != 0.f) w = 1.0 / (double)d2;      // "minus the query point itself": dists == 0 skipped
+                        if (in && d2 != 0.f) {      // "minus the query point itself": dists == 0 skipped
+                            w = 1.0 / (double)d2;
+                            p32 = (double)__ldg(spfh_sorted + (size_t)sp * 33 + 32) * w;    // bin 32's term, by the candidate's lane
+                        }
                     }
                     nb += __popc(__ballot_sync(0xffffffffu, in));
                     unsigned mask = __ballot_sync(0xffffffffu, w != 0.0);
+                    const float* rows = spfh_sorted + (size_t)base * 33 + lane;
+                    // four rows in flight per step; the additions stay in ascending candidate order
+                    while (__popc(mask) >= 4) {
+                        int j0 = __ffs(mask) - 1; mask &= mask - 1;
+                        int j1 = __ffs(mask) - 1; mask &= mask - 1;
+                        int j2 = __ffs(mask) - 1; mask &= mask - 1;
+                        int j3 = __ffs(mask) - 1; mask &= mask - 1;
+                        float v0 = __ldg(rows + j0 * 33), v1 = __ldg(rows + j1 * 33), v2 = __ldg(rows + j2 * 33), v3 = __ldg(rows + j3 * 33);
+                        double w0 = __shfl_sync(0xffffffffu, w, j0), w1 = __shfl_sync(0xffffffffu, w, j1);
+                        double w2 = __shfl_sync(0xffffffffu, w, j2), w3 = __shfl_sync(0xffffffffu, w, j3);
+                        double q0 = __shfl_sync(0xffffffffu, p32, j0), q1 = __shfl_sync(0xffffffffu, p32, j1);
+                        double q2 = __shfl_sync(0xffffffffu, p32, j2), q3 = __shfl_sync(0xffffffffu, p32, j3);
+                        acc += (double)v0 * w0; acc += (double)v1 * w1; acc += (double)v2 * w2; acc += (double)v3 * w3;
+                        acc32 += q0; acc32 += q1; acc32 += q2; acc32 += q3;
+                    }
                     while (mask) {
                         int j = __ffs(mask) - 1;
                         mask &= mask - 1;
+                        float v = __ldg(rows + j * 33);
                         double wj = __shfl_sync(0xffffffffu, w, j);
-                        const float* sj = spfh_sorted + (size_t)(base + j) * 33;
-                        acc += (double)__ldg(sj + lane) * wj;
-                        if (lane == 0) acc32 += (double)__ldg(sj + 32) * wj;
+                        double qj = __shfl_sync(0xffffffffu, p32, j);
+                        acc += (double)v * wj;
+                        acc32 += qj;
                     }
                 }
             }
@@ -707,7 +831,10 @@ int rtr_fpfh_dev(rtr_cloud* c, float radius) {
     if (int e = tmp_alloc(ctx, &spfh, (size_t)n * 33, "fpfh")) return e;
     if (n > 0) {
         GridView v = rtr_view(g);
-        k_spfh<<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * 16), SPFH_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh);
+        // RTR_SPFH_EXACT=1 sends every pair through the fp64 evaluation (the tests use it to show the fp32 screen changes nothing)
+        const char* ex = getenv("RTR_SPFH_EXACT");
+        int use_screen = (ex && ex[0] == '1') ? 0 : 1;
+        k_spfh<<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * 16), SPFH_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh, use_screen);
         RTR_LAUNCH_CHECK(ctx, "fpfh.spfh");
         if (n >= (1 << 20)) {
             // one CTA per occupied cell, candidates staged through shared memory (needs many occupied cells to fill the GPU)

@@ -265,7 +265,7 @@ struct IcpState {
 #define ICP_NSUM 17   // 3 (sum s) + 3 (sum t) + 9 (sum s t^T) + 1 (sum d2) + 1 (count)
 
 __global__ void k_icp_init(const float4* __restrict__ src, int n, const float* __restrict__ init_pose, const rtr_pose_result* __restrict__ init_res,
-                           float4* __restrict__ cur, IcpState* __restrict__ st) {
+                           float4* __restrict__ cur, IcpState* __restrict__ st, unsigned* __restrict__ ticket) {
     __shared__ float m[16];
     if (threadIdx.x < 16) {
         float v = (threadIdx.x % 5 == 0) ? 1.f : 0.f;
@@ -280,6 +280,7 @@ __global__ void k_icp_init(const float4* __restrict__ src, int n, const float* _
         if (threadIdx.x == 0) {
             int skip = (init_res && init_res->converged == 0) ? 1 : 0;
             st->prev_mse = DBL_MAX; st->iterations = 0; st->done = skip; st->state = 0; st->corr = 0; st->have_step = 0; st->skipped = skip;
+            *ticket = 0u;
         }
     }
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -307,11 +308,86 @@ __global__ void k_icp_permute(const float4* __restrict__ cur, const float4* __re
     src_out[i] = __ldg(src + j);
 }
 
+// TransformationEstimationSVD + final = step * final + DefaultConvergenceCriteria, run by the LAST CTA of the
+// correspondence kernel to finish (ticket counter), so an iteration is one launch.  The reduction over the per-CTA
+// partials has a fixed shape (lane-strided, then a shuffle tree) whatever CTA happens to be last.
+struct IcpSolveArgs { int max_iterations, force; double mse_abs; };
+
+__device__ void icp_solve_thread0(const double* sums, IcpState* st, const IcpSolveArgs& sa) {
+    double cnt = sums[16];
+    st->corr = (int)cnt;
+    if (cnt < 3.0) { st->done = 1; st->state = 0; return; }
+    float step[16], fin[16];
+    horn_pose(&sums[0], &sums[3], &sums[6], cnt, step);
+    for (int i = 0; i < 16; ++i) fin[i] = st->final_[i];
+    matmul4(step, fin, fin);
+    for (int i = 0; i < 16; ++i) { st->final_[i] = fin[i]; st->step[i] = step[i]; }
+    st->have_step = 1;
+    int it = st->iterations + 1;
+    st->iterations = it;
+    if (it >= sa.max_iterations) { st->done = 1; st->state = 1; return; }
+    if (!sa.force) {
+        double cos_angle = 0.5 * ((double)step[0] + (double)step[5] + (double)step[10] - 1.0);
+        double tsq = (double)step[12] * (double)step[12] + (double)step[13] * (double)step[13] + (double)step[14] * (double)step[14];
+        if (cos_angle >= 1.0 && tsq <= 0.0) { st->done = 1; st->state = 2; return; }
+        double mse = sums[15] / cnt;
+        if (fabs(mse - st->prev_mse) < sa.mse_abs) { st->done = 1; st->state = 3; return; }
+        st->prev_mse = mse;
+    }
+}
+
+// called by every thread of a CTA after its partials are written; nwarps = warps in the CTA (>= 1)
+__device__ void icp_last_cta_solve(const double* partials, IcpState* st, unsigned* ticket, const IcpSolveArgs& sa, double* sums /* smem[ICP_NSUM] */,
+                                   int* is_last /* smem */) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(ticket, 1u);
+        *is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!*is_last) return;
+    __threadfence();
+    // partials is an [nparts][17] matrix: thread t < 255 owns column t % 17 and the rows t / 17, t / 17 + 15, ... (adjacent
+    // threads read adjacent addresses; eight loads in flight per thread), then 17 threads fold the 15 row groups in order
+    __shared__ double grp[15][ICP_NSUM];
+    const int nparts = (int)gridDim.x, t = threadIdx.x;
+    if (t < 15 * ICP_NSUM) {
+        const int k = t % ICP_NSUM, rg = t / ICP_NSUM;
+        const double* col = partials + k;
+        double v = 0;
+        int b = rg;
+        for (; b + 15 * 7 < nparts; b += 15 * 8) {
+            double x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] = __ldcg(col + (size_t)(b + 15 * u) * ICP_NSUM);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v += x[u];
+        }
+        for (; b < nparts; b += 15) v += __ldcg(col + (size_t)b * ICP_NSUM);
+        grp[rg][k] = v;
+    }
+    __syncthreads();
+    if (t < ICP_NSUM) {
+        double v = 0;
+#pragma unroll
+        for (int rg = 0; rg < 15; ++rg) v += grp[rg][t];
+        sums[t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *ticket = 0u;
+        icp_solve_thread0(sums, st, sa);
+    }
+}
+
 // correspondence estimation + accumulation.  Applies the previous iteration's step first (transformCloud in place).
-__global__ void __launch_bounds__(ICP_THREADS) k_icp_corr(GridView g, float4* __restrict__ cur, int n, const IcpState* __restrict__ st,
-                                                           double dmax2, float prune2, double* __restrict__ partials) {
+__global__ void __launch_bounds__(ICP_THREADS) k_icp_corr(GridView g, float4* __restrict__ cur, int n, IcpState* st,
+                                                           double dmax2, float prune2, double* partials, unsigned* ticket, IcpSolveArgs sa) {
     __shared__ float m[16];
     __shared__ double red[ICP_THREADS / 32][ICP_NSUM];
+    __shared__ double sums[ICP_NSUM];
+    __shared__ int is_last;
     if (st->done) return;
     int have = st->have_step;
     if (threadIdx.x < 16) m[threadIdx.x] = st->step[threadIdx.x];
@@ -348,16 +424,19 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_corr(GridView g, float4* __
         for (int w = 0; w < ICP_THREADS / 32; ++w) v += red[w][threadIdx.x];
         partials[(size_t)blockIdx.x * ICP_NSUM + threadIdx.x] = v;
     }
+    icp_last_cta_solve(partials, st, ticket, sa, sums, &is_last);
 }
 
 // Small sources (repo clouds): one WARP per source point — the lanes share the candidate scan, so the per-iteration
 // latency is set by ~9 range steps instead of ~50 dependent loads.  Each warp walks a strided list of queries and keeps
 // the 17 sums in lane 0; warps are then folded through shared memory.
 #define ICPW_WARPS 8
-__global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_corr_warp(GridView g, float4* __restrict__ cur, int n, const IcpState* __restrict__ st,
-                                                                   double dmax2, float prune2, double* __restrict__ partials) {
+__global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_corr_warp(GridView g, float4* __restrict__ cur, int n, IcpState* st,
+                                                                   double dmax2, float prune2, double* partials, unsigned* ticket, IcpSolveArgs sa) {
     __shared__ float m[16];
     __shared__ double red[ICPW_WARPS][ICP_NSUM];
+    __shared__ double sums[ICP_NSUM];
+    __shared__ int is_last;
     if (st->done) return;
     int have = st->have_step;
     if (threadIdx.x < 16) m[threadIdx.x] = st->step[threadIdx.x];
@@ -392,13 +471,64 @@ __global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_corr_warp(GridView g, f
         for (int w = 0; w < ICPW_WARPS; ++w) v += red[w][threadIdx.x];
         partials[(size_t)blockIdx.x * ICP_NSUM + threadIdx.x] = v;
     }
+    icp_last_cta_solve(partials, st, ticket, sa, sums, &is_last);
+}
+
+// last CTA of the fitness kernel: fold the (sum d2, count) partials in a fixed shape and write the result record
+__device__ void icp_last_cta_finish(const double* partials, const IcpState* st, unsigned* ticket, rtr_pose_result* res, int keep_ransac_fields,
+                                    double* sums /* smem[2] */, int* is_last /* smem */) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(ticket, 1u);
+        *is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!*is_last) return;
+    __threadfence();
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < 2) {
+        const int nparts = (int)gridDim.x;
+        const double* col = partials + warp;
+        double v = 0;
+        int b = lane;
+        for (; b + 32 * 7 < nparts; b += 32 * 8) {
+            double x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] = __ldcg(col + (size_t)(b + 32 * u) * 2);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v += x[u];
+        }
+        for (; b < nparts; b += 32) v += __ldcg(col + (size_t)b * 2);
+        v = warp_sum(v);
+        if (lane == 0) sums[warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *ticket = 0u;
+        for (int i = 0; i < 16; ++i) res->pose[i] = st->final_[i];
+        res->fitness = sums[1] > 0 ? (float)(sums[0] / sums[1]) : FLT_MAX;
+        res->iterations = st->iterations;
+        if (keep_ransac_fields) {
+            res->converged = res->converged ? st->state : 0;
+        } else {
+            res->converged = st->state; res->inliers = st->corr; res->hypothesis = -1; res->evaluated = 0;
+            res->model_id = 0; res->n_keypoints_src = 0; res->n_keypoints_tgt = 0;
+            for (int i = 0; i < 5; ++i) res->pad_[i] = 0;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_fitness_warp(GridView g, const float4* __restrict__ src, int n, const IcpState* __restrict__ st,
-                                                                      double* __restrict__ partials) {
+                                                                      double* partials, unsigned* ticket, rtr_pose_result* res, int keep_ransac_fields) {
     __shared__ float m[16];
     __shared__ double red[ICPW_WARPS][2];
-    if (st->skipped) return;
+    __shared__ double sums[2];
+    __shared__ int is_last;
+    if (st->skipped) {     // pose / fitness stay RANSAC's (identity, FLT_MAX)
+        if (blockIdx.x == 0 && threadIdx.x == 0) { res->iterations = 0; res->converged = 0; }
+        return;
+    }
     if (threadIdx.x < 16) m[threadIdx.x] = st->final_[threadIdx.x];
     __syncthreads();
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -418,50 +548,20 @@ __global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_fitness_warp(GridView g
         for (int w = 0; w < ICPW_WARPS; ++w) v += red[w][threadIdx.x];
         partials[(size_t)blockIdx.x * 2 + threadIdx.x] = v;
     }
-}
-
-// TransformationEstimationSVD + final = step * final + DefaultConvergenceCriteria.  One CTA of 17 warps: warp k reduces
-// sum k over the per-CTA partials in a fixed order.
-__global__ void __launch_bounds__(ICP_NSUM * 32) k_icp_solve(const double* __restrict__ partials, int nparts, IcpState* __restrict__ st,
-                                                             int max_iterations, int force, double mse_abs) {
-    __shared__ double sums[ICP_NSUM];
-    if (st->done) return;
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double v = 0;
-    for (int b = lane; b < nparts; b += 32) v += partials[(size_t)b * ICP_NSUM + warp];
-    v = warp_sum(v);
-    if (lane == 0) sums[warp] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double cnt = sums[16];
-        st->corr = (int)cnt;
-        if (cnt < 3.0) { st->done = 1; st->state = 0; return; }
-        float step[16], fin[16];
-        horn_pose(&sums[0], &sums[3], &sums[6], cnt, step);
-        for (int i = 0; i < 16; ++i) fin[i] = st->final_[i];
-        matmul4(step, fin, fin);
-        for (int i = 0; i < 16; ++i) { st->final_[i] = fin[i]; st->step[i] = step[i]; }
-        st->have_step = 1;
-        int it = st->iterations + 1;
-        st->iterations = it;
-        if (it >= max_iterations) { st->done = 1; st->state = 1; return; }
-        if (!force) {
-            double cos_angle = 0.5 * ((double)step[0] + (double)step[5] + (double)step[10] - 1.0);
-            double tsq = (double)step[12] * (double)step[12] + (double)step[13] * (double)step[13] + (double)step[14] * (double)step[14];
-            if (cos_angle >= 1.0 && tsq <= 0.0) { st->done = 1; st->state = 2; return; }
-            double mse = sums[15] / cnt;
-            if (fabs(mse - st->prev_mse) < mse_abs) { st->done = 1; st->state = 3; return; }
-            st->prev_mse = mse;
-        }
-    }
+    icp_last_cta_finish(partials, st, ticket, res, keep_ransac_fields, sums, &is_last);
 }
 
 // getFitnessScore(): mean squared NN distance of (final o source)
 __global__ void __launch_bounds__(ICP_THREADS) k_icp_fitness(GridView g, const float4* __restrict__ src, int n, const IcpState* __restrict__ st,
-                                                             double* __restrict__ partials) {
+                                                             double* partials, unsigned* ticket, rtr_pose_result* res, int keep_ransac_fields) {
     __shared__ float m[16];
     __shared__ double red[ICP_THREADS / 32][2];
-    if (st->skipped) return;
+    __shared__ double sums[2];
+    __shared__ int is_last;
+    if (st->skipped) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) { res->iterations = 0; res->converged = 0; }
+        return;
+    }
     if (threadIdx.x < 16) m[threadIdx.x] = st->final_[threadIdx.x];
     __syncthreads();
     double s = 0, c = 0;
@@ -482,30 +582,7 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_fitness(GridView g, const f
         for (int w = 0; w < ICP_THREADS / 32; ++w) v += red[w][threadIdx.x];
         partials[(size_t)blockIdx.x * 2 + threadIdx.x] = v;
     }
-}
-
-__global__ void __launch_bounds__(64) k_icp_finish(const double* __restrict__ partials, int nparts, const IcpState* __restrict__ st,
-                                                   rtr_pose_result* __restrict__ res, int keep_ransac_fields) {
-    __shared__ double sums[2];
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double v = 0;
-    for (int b = lane; b < nparts; b += 32) v += partials[(size_t)b * 2 + warp];
-    v = warp_sum(v);
-    if (lane == 0) sums[warp] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (st->skipped) { res->iterations = 0; res->converged = 0; return; }     // pose / fitness stay RANSAC's (identity, FLT_MAX)
-        for (int i = 0; i < 16; ++i) res->pose[i] = st->final_[i];
-        res->fitness = sums[1] > 0 ? (float)(sums[0] / sums[1]) : FLT_MAX;
-        res->iterations = st->iterations;
-        if (keep_ransac_fields) {
-            res->converged = res->converged ? st->state : 0;
-        } else {
-            res->converged = st->state; res->inliers = st->corr; res->hypothesis = -1; res->evaluated = 0;
-            res->model_id = 0; res->n_keypoints_src = 0; res->n_keypoints_tgt = 0;
-            for (int i = 0; i < 5; ++i) res->pad_[i] = 0;
-        }
-    }
+    icp_last_cta_finish(partials, st, ticket, res, keep_ransac_fields, sums, &is_last);
 }
 
 int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const float* d_init_pose16, int init_from_result,
@@ -523,9 +600,12 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     int nb = std::max(nblk(n, ICP_THREADS), 1);
     if (int e = tmp_alloc(ctx, &cur, n, "icp")) return e;
     if (int e = tmp_alloc(ctx, &st, 1, "icp")) return e;
+    unsigned* ticket = nullptr;
+    if (int e = tmp_alloc(ctx, &ticket, 1, "icp")) return e;
+    const IcpSolveArgs sa{p->max_iterations, p->force_iterations, p->mse_threshold_absolute};
     const int nbw = std::max(1, std::min(nblk(n, ICPW_WARPS), ctx->sm_count * 8));    // CTAs of the warp-per-query kernels
     if (int e = tmp_alloc(ctx, &partials, (size_t)std::max(nb, nbw) * ICP_NSUM, "icp")) return e;
-    k_icp_init<<<nb, ICP_THREADS, 0, ctx->stream>>>(src->pts, n, d_init_pose16, init_from_result ? d_result : nullptr, cur, st);
+    k_icp_init<<<nb, ICP_THREADS, 0, ctx->stream>>>(src->pts, n, d_init_pose16, init_from_result ? d_result : nullptr, cur, st, ticket);
     RTR_LAUNCH_CHECK(ctx, "icp.init");
     const float4* src_pts = src->pts;
     float4 *cur2 = nullptr, *src2 = nullptr;
@@ -558,22 +638,17 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     if (p->max_correspondence_distance > 0.f) { prune2 = (float)dmax2; if ((double)prune2 < dmax2) prune2 = nextafterf(prune2, FLT_MAX); }
     // small sources: one warp per query (latency), large ones: one thread per query in cell order (throughput)
     const bool warp_per_query = n < 65536;
-    const int nparts = warp_per_query ? nbw : nb;
     if (n >= 1 && tgt->n >= 1) {
         for (int it = 0; it < p->max_iterations; ++it) {
-            if (warp_per_query) k_icp_corr_warp<<<nbw, ICPW_WARPS * 32, 0, ctx->stream>>>(v, cur, n, st, dmax2, prune2, partials);
-            else k_icp_corr<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, cur, n, st, dmax2, prune2, partials);
+            if (warp_per_query) k_icp_corr_warp<<<nbw, ICPW_WARPS * 32, 0, ctx->stream>>>(v, cur, n, st, dmax2, prune2, partials, ticket, sa);
+            else k_icp_corr<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, cur, n, st, dmax2, prune2, partials, ticket, sa);
             RTR_LAUNCH_CHECK(ctx, "icp.corr");
-            k_icp_solve<<<1, ICP_NSUM * 32, 0, ctx->stream>>>(partials, nparts, st, p->max_iterations, p->force_iterations, p->mse_threshold_absolute);
-            RTR_LAUNCH_CHECK(ctx, "icp.solve");
         }
     }
-    if (warp_per_query) k_icp_fitness_warp<<<nbw, ICPW_WARPS * 32, 0, ctx->stream>>>(v, src_pts, n, st, partials);
-    else k_icp_fitness<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, src_pts, n, st, partials);
+    if (warp_per_query) k_icp_fitness_warp<<<nbw, ICPW_WARPS * 32, 0, ctx->stream>>>(v, src_pts, n, st, partials, ticket, d_result, init_from_result);
+    else k_icp_fitness<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, src_pts, n, st, partials, ticket, d_result, init_from_result);
     RTR_LAUNCH_CHECK(ctx, "icp.fitness");
-    k_icp_finish<<<1, 64, 0, ctx->stream>>>(partials, nparts, st, d_result, init_from_result);
-    RTR_LAUNCH_CHECK(ctx, "icp.finish");
-    dev_free(ctx, cur); dev_free(ctx, src2); dev_free(ctx, st); dev_free(ctx, partials);
+    dev_free(ctx, cur); dev_free(ctx, src2); dev_free(ctx, st); dev_free(ctx, partials); dev_free(ctx, ticket);
     return 0;
 }
 

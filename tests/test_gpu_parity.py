@@ -144,6 +144,34 @@ def test_normals_harris_fpfh(api, gpu_ctx, orc, clouds, name):
     c.free()
 
 
+@pytest.mark.parametrize("name", ["chair1", "chair4", "desk3", "sofa", "room", "noisy_plane"])
+def test_spfh_fp32_screen_changes_nothing(api, gpu_ctx, clouds, name, monkeypatch):
+    """The fp32 bin screen of k_spfh only decides pairs safely inside a bin: FPFH with the screen == FPFH with every pair
+    evaluated in fp64 (RTR_SPFH_EXACT=1), bit for bit, on real clouds, a 200k-point synthetic room and an exactly flat
+    plane with tiny noise (role swap undecidable in fp32 for every pair)."""
+    if name == "room":
+        pts = synth.sample_rects(synth.room_rects((6.0, 6.0, 3.0), n_boxes=6), 200000, 11)
+    elif name == "noisy_plane":
+        rng = np.random.default_rng(4)
+        pts = np.zeros((20000, 4), np.float32)
+        pts[:, :2] = rng.uniform(0, 1.5, (20000, 2))
+        pts[:, 2] = rng.normal(0, 1e-6, 20000)
+        pts[:, 3] = 1
+    else:
+        pts = clouds(name)
+    c = api.Cloud(gpu_ctx, pts)
+    c.normals(0.05)
+    monkeypatch.setenv("RTR_SPFH_EXACT", "0")
+    f_screen = c.fpfh(0.10).copy()
+    c.reset()
+    c.normals(0.05)
+    monkeypatch.setenv("RTR_SPFH_EXACT", "1")
+    f_exact = c.fpfh(0.10).copy()
+    c.free()
+    assert np.array_equal(f_screen.view(np.uint32), f_exact.view(np.uint32))
+    assert np.isfinite(f_exact).any()
+
+
 def test_stage_edge_cases(api, gpu_ctx, orc):
     # fewer than 3 neighbours -> NaN normal (App. A.2); isolated / duplicate points; tiny clouds
     pts = np.array([[0, 0, 0, 1], [0.01, 0, 0, 1], [5, 5, 5, 1], [5, 5, 5, 1]], np.float32)
