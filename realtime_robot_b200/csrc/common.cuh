@@ -431,6 +431,41 @@ __device__ __forceinline__ void grid_nearest_warp(const GridView& g, float qx, f
     }
 }
 
+// Small targets (every scan the reference ships has ~2-3 k points): no search structure at all.  One warp answers TWO
+// queries at once — the lanes stride over all target points (30 KB, L1 resident), each loaded point is tested against
+// both queries — then two shuffle arg-mins.  ~n/32 x 14 instructions per query whatever the alignment of the clouds,
+// against an unbounded ring walk for queries far from the target.  Same distance expression and tie rule: same result.
+#define RTR_BRUTE_NN_MAX 4096
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long ok = __shfl_xor_sync(0xffffffffu, k, o);
+        k = ok < k ? ok : k;
+    }
+    return k;
+}
+// (d2 bits, original index) packed in one 64-bit key: d2 >= +0, so its bit pattern orders like the value, and the
+// unsigned minimum is "smallest distance, then lowest index" — the tie rule — in one compare.  NaN distances (bits above
+// +inf) never count as a match.
+__device__ __forceinline__ void brute_nearest_warp2(const GridView& g, float ax, float ay, float az, float bx, float by, float bz, int lane,
+                                                    int& best_a, float& d2_a, int& best_b, float& d2_b) {
+    unsigned long long ka = ~0ull, kb = ~0ull;
+#pragma unroll 4
+    for (int s = lane; s < g.n; s += 32) {
+        float4 p = __ldg(g.sorted + s);
+        unsigned id = (unsigned)__float_as_int(p.w);
+        unsigned long long ca = ((unsigned long long)__float_as_uint(dist2f(ax, ay, az, p.x, p.y, p.z)) << 32) | id;
+        unsigned long long cb = ((unsigned long long)__float_as_uint(dist2f(bx, by, bz, p.x, p.y, p.z)) << 32) | id;
+        ka = ca < ka ? ca : ka;
+        kb = cb < kb ? cb : kb;
+    }
+    ka = warp_min_u64(ka);
+    kb = warp_min_u64(kb);
+    unsigned ha = (unsigned)(ka >> 32), hb = (unsigned)(kb >> 32);
+    best_a = ha <= 0x7f800000u ? (int)(unsigned)ka : -1; d2_a = __uint_as_float(ha);
+    best_b = hb <= 0x7f800000u ? (int)(unsigned)kb : -1; d2_b = __uint_as_float(hb);
+}
+
 __device__ __forceinline__ void grid_nearest(const GridView& g, float qx, float qy, float qz, int& best, float& best_d2) {
     float4 bp;
     grid_nearest_ex(g, qx, qy, qz, FLT_MAX, best, best_d2, bp);

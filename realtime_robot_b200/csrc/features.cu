@@ -469,19 +469,46 @@ __global__ void __launch_bounds__(SPFH_WARPS * 32) k_spfh(GridView g, const floa
     }
 }
 
-// weightPointSPFHSignature: one warp per point.  Two roles per 32-candidate batch: first lane = candidate (distance
-// test and the fp64 weight 1/d2, computed once per pair instead of once per lane), then lane = histogram bin (lane 0 also
-// carries bin 32) accumulating SPFH_j[bin] * w_j over the batch's in-radius candidates in ascending position order.
+// weightPointSPFHSignature: one warp per point, two roles.  Lane = candidate: distance test, the fp64 weight 1/d2 and
+// bin 32's term, computed once per pair; accepted candidates are appended IN ORDER to a 64-entry ring in shared memory.
+// Lane = histogram bin: whenever 32 entries wait, the warp walks them in order (broadcast reads of (w, term32, row),
+// four SPFH rows in flight), so the additions happen in ascending candidate position exactly as the oracle's loop.
 #define FPFH_WARPS 8
+struct __align__(16) FwEntry { double w, t32; };
 __global__ void __launch_bounds__(FPFH_WARPS * 32) k_fpfh_weight(GridView g, const float* __restrict__ spfh_sorted, float r2,
                                                                  float* __restrict__ fpfh) {
     __shared__ double hs[FPFH_WARPS][36];
+    __shared__ FwEntry wq[FPFH_WARPS][64];
+    __shared__ int rq[FPFH_WARPS][64];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int nwarps = gridDim.x * FPFH_WARPS;
+    const unsigned lt = (1u << lane) - 1u;
+    const float* rows = spfh_sorted + lane;
     for (int s = blockIdx.x * FPFH_WARPS + warp; s < g.n; s += nwarps) {
         float4 q = __ldg(g.sorted + s);
         double acc = 0, acc32 = 0;
-        int nb = 0;
+        int nb = 0, head = 0, nq = 0;
+        auto consume = [&](int cnt) {
+            int k = 0;
+            for (; k + 4 <= cnt; k += 4) {
+                int e = (head + k) & 63;        // head is a multiple of 32 and k of 4: the four entries do not wrap
+                int r0 = rq[warp][e], r1 = rq[warp][e + 1], r2i = rq[warp][e + 2], r3 = rq[warp][e + 3];
+                float v0 = __ldg(rows + (size_t)r0 * 33), v1 = __ldg(rows + (size_t)r1 * 33);
+                float v2 = __ldg(rows + (size_t)r2i * 33), v3 = __ldg(rows + (size_t)r3 * 33);
+                FwEntry a0 = wq[warp][e], a1 = wq[warp][e + 1], a2 = wq[warp][e + 2], a3 = wq[warp][e + 3];
+                acc += (double)v0 * a0.w; acc += (double)v1 * a1.w; acc += (double)v2 * a2.w; acc += (double)v3 * a3.w;
+                acc32 += a0.t32; acc32 += a1.t32; acc32 += a2.t32; acc32 += a3.t32;
+            }
+            for (; k < cnt; ++k) {
+                int e = (head + k) & 63;
+                float v = __ldg(rows + (size_t)rq[warp][e] * 33);
+                FwEntry a = wq[warp][e];
+                acc += (double)v * a.w;
+                acc32 += a.t32;
+            }
+            head = (head + cnt) & 63;
+            nq -= cnt;
+        };
         int cx = clampi(cell_coord(q.x, g.mnx, g.inv_h), 0, g.dx - 1);
         int cy = clampi(cell_coord(q.y, g.mny, g.inv_h), 0, g.dy - 1);
         int cz = clampi(cell_coord(q.z, g.mnz, g.inv_h), 0, g.dz - 1);
@@ -492,45 +519,33 @@ __global__ void __launch_bounds__(FPFH_WARPS * 32) k_fpfh_weight(GridView g, con
                 int s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
                 for (int base = s0; base < s1; base += 32) {
                     int sp = base + lane;
-                    double w = 0.0, p32 = 0.0;
-                    bool in = false;
+                    bool in = false, use = false;
+                    float d2 = 0.f;
                     if (sp < s1) {
                         float4 p = __ldg(g.sorted + sp);
-                        float d2 = dist2f(q.x, q.y, q.z, p.x, p.y, p.z);
+                        d2 = dist2f(q.x, q.y, q.z, p.x, p.y, p.z);
                         in = d2 < r2;
-                        if (in && d2 != 0.f) {      // "minus the query point itself": dists == 0 skipped
-                            w = 1.0 / (double)d2;
-                            p32 = (double)__ldg(spfh_sorted + (size_t)sp * 33 + 32) * w;    // bin 32's term, by the candidate's lane
-                        }
+                        use = in && d2 != 0.f;      // "minus the query point itself": dists == 0 skipped
                     }
                     nb += __popc(__ballot_sync(0xffffffffu, in));
-                    unsigned mask = __ballot_sync(0xffffffffu, w != 0.0);
-                    const float* rows = spfh_sorted + (size_t)base * 33 + lane;
-                    // four rows in flight per step; the additions stay in ascending candidate order
-                    while (__popc(mask) >= 4) {
-                        int j0 = __ffs(mask) - 1; mask &= mask - 1;
-                        int j1 = __ffs(mask) - 1; mask &= mask - 1;
-                        int j2 = __ffs(mask) - 1; mask &= mask - 1;
-                        int j3 = __ffs(mask) - 1; mask &= mask - 1;
-                        float v0 = __ldg(rows + j0 * 33), v1 = __ldg(rows + j1 * 33), v2 = __ldg(rows + j2 * 33), v3 = __ldg(rows + j3 * 33);
-                        double w0 = __shfl_sync(0xffffffffu, w, j0), w1 = __shfl_sync(0xffffffffu, w, j1);
-                        double w2 = __shfl_sync(0xffffffffu, w, j2), w3 = __shfl_sync(0xffffffffu, w, j3);
-                        double q0 = __shfl_sync(0xffffffffu, p32, j0), q1 = __shfl_sync(0xffffffffu, p32, j1);
-                        double q2 = __shfl_sync(0xffffffffu, p32, j2), q3 = __shfl_sync(0xffffffffu, p32, j3);
-                        acc += (double)v0 * w0; acc += (double)v1 * w1; acc += (double)v2 * w2; acc += (double)v3 * w3;
-                        acc32 += q0; acc32 += q1; acc32 += q2; acc32 += q3;
-                    }
-                    while (mask) {
-                        int j = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        float v = __ldg(rows + j * 33);
-                        double wj = __shfl_sync(0xffffffffu, w, j);
-                        double qj = __shfl_sync(0xffffffffu, p32, j);
-                        acc += (double)v * wj;
-                        acc32 += qj;
+                    unsigned mask = __ballot_sync(0xffffffffu, use);
+                    if (mask) {
+                        if (use) {
+                            double w = 1.0 / (double)d2;
+                            int e = (head + nq + __popc(mask & lt)) & 63;
+                            FwEntry en;
+                            en.w = w;
+                            en.t32 = (double)__ldg(spfh_sorted + (size_t)sp * 33 + 32) * w;      // bin 32's term
+                            wq[warp][e] = en;
+                            rq[warp][e] = sp;
+                        }
+                        nq += __popc(mask);
+                        __syncwarp();
+                        if (nq >= 32) { consume(32); __syncwarp(); }
                     }
                 }
             }
+        if (nq > 0) { consume(nq); __syncwarp(); }
         hs[warp][lane] = acc;
         if (lane == 0) hs[warp][32] = acc32;
         __syncwarp();

@@ -431,26 +431,22 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_corr(GridView g, float4* __
 // latency is set by ~9 range steps instead of ~50 dependent loads.  Each warp walks a strided list of queries and keeps
 // the 17 sums in lane 0; warps are then folded through shared memory.
 #define ICPW_WARPS 8
-__global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_corr_warp(GridView g, float4* __restrict__ cur, int n, IcpState* st,
-                                                                   double dmax2, float prune2, double* partials, unsigned* ticket, IcpSolveArgs sa) {
+__global__ void __launch_bounds__(ICPW_WARPS * 32, 4) k_icp_corr_warp(GridView g, const float4* __restrict__ tgt_pts, float4* __restrict__ cur, int n,
+                                                                   IcpState* st, double dmax2, float prune2, double* partials, unsigned* ticket,
+                                                                   IcpSolveArgs sa) {
     __shared__ float m[16];
-    __shared__ double red[ICPW_WARPS][ICP_NSUM];
+    __shared__ double red[ICPW_WARPS][ICP_NSUM];      // lane 0 of every warp accumulates its queries here, in query order
     __shared__ double sums[ICP_NSUM];
     __shared__ int is_last;
     if (st->done) return;
     int have = st->have_step;
     if (threadIdx.x < 16) m[threadIdx.x] = st->step[threadIdx.x];
-    __syncthreads();
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < ICP_NSUM) red[warp][lane] = 0.0;
+    __syncthreads();
     int nwarps = gridDim.x * ICPW_WARPS;
-    double acc[ICP_NSUM];
-#pragma unroll
-    for (int k = 0; k < ICP_NSUM; ++k) acc[k] = 0.0;
-    for (int i = blockIdx.x * ICPW_WARPS + warp; i < n; i += nwarps) {
-        float4 q = cur[i];
-        if (have) { q = xform(m, q); if (lane == 0) cur[i] = q; }
-        int b; float d2; float4 t;
-        grid_nearest_warp(g, q.x, q.y, q.z, prune2, lane, b, d2, t);
+    double* acc = red[warp];
+    auto add = [&](float4 q, int b, float d2, float4 t) {
         if (lane == 0 && b >= 0 && (double)d2 <= dmax2) {
             double sx = q.x, sy = q.y, sz = q.z, tx = t.x, ty = t.y, tz = t.z;
             acc[0] += sx; acc[1] += sy; acc[2] += sz; acc[3] += tx; acc[4] += ty; acc[5] += tz;
@@ -459,10 +455,32 @@ __global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_corr_warp(GridView g, f
             acc[12] += sz * tx; acc[13] += sz * ty; acc[14] += sz * tz;
             acc[15] += (double)d2; acc[16] += 1.0;
         }
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < ICP_NSUM; ++k) red[warp][k] = acc[k];
+    };
+    if (g.n <= RTR_BRUTE_NN_MAX) {
+        // two of this warp's queries per pass (i, i + nwarps): same warp -> query assignment and accumulation order as below
+        for (int i = blockIdx.x * ICPW_WARPS + warp; i < n; i += 2 * nwarps) {
+            int i2 = i + nwarps;
+            bool two = i2 < n;
+            float4 q = cur[i], q2 = two ? cur[i2] : q;
+            if (have) {
+                q = xform(m, q); if (lane == 0) cur[i] = q;
+                if (two) { q2 = xform(m, q2); if (lane == 0) cur[i2] = q2; } else q2 = q;
+            }
+            int b, b2; float d2, d22;
+            brute_nearest_warp2(g, q.x, q.y, q.z, q2.x, q2.y, q2.z, lane, b, d2, b2, d22);
+            if (lane == 0) {
+                if (b >= 0) add(q, b, d2, __ldg(tgt_pts + b));
+                if (two && b2 >= 0) add(q2, b2, d22, __ldg(tgt_pts + b2));
+            }
+        }
+    } else {
+        for (int i = blockIdx.x * ICPW_WARPS + warp; i < n; i += nwarps) {
+            float4 q = cur[i];
+            if (have) { q = xform(m, q); if (lane == 0) cur[i] = q; }
+            int b; float d2; float4 t;
+            grid_nearest_warp(g, q.x, q.y, q.z, prune2, lane, b, d2, t);
+            add(q, b, d2, t);
+        }
     }
     __syncthreads();
     if (threadIdx.x < ICP_NSUM) {
@@ -534,11 +552,24 @@ __global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_fitness_warp(GridView g
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int nwarps = gridDim.x * ICPW_WARPS;
     double s = 0, c = 0;
-    for (int i = blockIdx.x * ICPW_WARPS + warp; i < n; i += nwarps) {
-        float4 q = xform(m, __ldg(src + i));
-        int b; float d2; float4 t;
-        grid_nearest_warp(g, q.x, q.y, q.z, FLT_MAX, lane, b, d2, t);
-        if (lane == 0 && b >= 0) { s += (double)d2; c += 1.0; }
+    if (g.n <= RTR_BRUTE_NN_MAX) {
+        for (int i = blockIdx.x * ICPW_WARPS + warp; i < n; i += 2 * nwarps) {
+            int i2 = i + nwarps;
+            bool two = i2 < n;
+            float4 q = xform(m, __ldg(src + i));
+            float4 q2 = two ? xform(m, __ldg(src + i2)) : q;
+            int b, b2; float d2, d22;
+            brute_nearest_warp2(g, q.x, q.y, q.z, q2.x, q2.y, q2.z, lane, b, d2, b2, d22);
+            if (lane == 0 && b >= 0) { s += (double)d2; c += 1.0; }
+            if (lane == 0 && two && b2 >= 0) { s += (double)d22; c += 1.0; }
+        }
+    } else {
+        for (int i = blockIdx.x * ICPW_WARPS + warp; i < n; i += nwarps) {
+            float4 q = xform(m, __ldg(src + i));
+            int b; float d2; float4 t;
+            grid_nearest_warp(g, q.x, q.y, q.z, FLT_MAX, lane, b, d2, t);
+            if (lane == 0 && b >= 0) { s += (double)d2; c += 1.0; }
+        }
     }
     if (lane == 0) { red[warp][0] = s; red[warp][1] = c; }
     __syncthreads();
@@ -640,7 +671,7 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     const bool warp_per_query = n < 65536;
     if (n >= 1 && tgt->n >= 1) {
         for (int it = 0; it < p->max_iterations; ++it) {
-            if (warp_per_query) k_icp_corr_warp<<<nbw, ICPW_WARPS * 32, 0, ctx->stream>>>(v, cur, n, st, dmax2, prune2, partials, ticket, sa);
+            if (warp_per_query) k_icp_corr_warp<<<nbw, ICPW_WARPS * 32, 0, ctx->stream>>>(v, tgt->pts, cur, n, st, dmax2, prune2, partials, ticket, sa);
             else k_icp_corr<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, cur, n, st, dmax2, prune2, partials, ticket, sa);
             RTR_LAUNCH_CHECK(ctx, "icp.corr");
         }
