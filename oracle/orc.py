@@ -168,6 +168,15 @@ def jacobi(a):
     return ev, vec
 
 
+def horn_top_eigvec(n44):
+    """(ok, q): the characteristic-quartic route of horn_pose for a symmetric 4x4."""
+    a = np.ascontiguousarray(n44, dtype=np.float64)
+    q = np.zeros(4)
+    lib().orc_horn_top_eigvec.restype = C.c_int
+    ok = lib().orc_horn_top_eigvec(a.ctypes.data_as(C.POINTER(C.c_double)), q.ctypes.data_as(C.POINTER(C.c_double)))
+    return bool(ok), q
+
+
 def register(model, scene, params: RegisterParams) -> PoseResult:
     model, scene = _f(model), _f(scene)
     res = PoseResult()

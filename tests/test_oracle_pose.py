@@ -28,6 +28,51 @@ def test_jacobi_matches_eigh(orc):
     assert np.array_equal(ev, [3.0, 1.0, 2.0]) and np.array_equal(vec, np.eye(3))
 
 
+def _horn_matrix(S):
+    N = np.zeros((4, 4))
+    N[0, 0] = S[0, 0] + S[1, 1] + S[2, 2]
+    N[0, 1] = S[1, 2] - S[2, 1]; N[0, 2] = S[2, 0] - S[0, 2]; N[0, 3] = S[0, 1] - S[1, 0]
+    N[1, 1] = S[0, 0] - S[1, 1] - S[2, 2]; N[1, 2] = S[0, 1] + S[1, 0]; N[1, 3] = S[2, 0] + S[0, 2]
+    N[2, 2] = -S[0, 0] + S[1, 1] - S[2, 2]; N[2, 3] = S[1, 2] + S[2, 1]; N[3, 3] = -S[0, 0] - S[1, 1] + S[2, 2]
+    return N + np.triu(N, 1).T
+
+
+def test_horn_quartic_route_matches_eigh(orc):
+    """horn_pose's fast path (top root of the characteristic quartic + adjugate column) against numpy's eigh on random,
+    3-point, near-identity (ICP) and planar cross-covariances; collinear inputs (repeated top eigenvalue) must decline."""
+    rng = np.random.default_rng(0)
+    declined = 0
+    for t in range(4000):
+        kind = t % 5
+        if kind == 0:
+            S = rng.normal(size=(3, 3)) * 10 ** rng.uniform(-4, 6)
+        elif kind == 1:
+            s = rng.normal(size=(3, 3)); R = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+            tt = s @ R.T + rng.normal(size=(3, 3)) * 0.01
+            S = (s - s.mean(0)).T @ (tt - tt.mean(0))
+        elif kind == 2:
+            s = rng.normal(size=(500, 3)); tt = s + rng.normal(size=(500, 3)) * 1e-3
+            S = (s - s.mean(0)).T @ (tt - tt.mean(0))
+        elif kind == 3:
+            s = np.outer(rng.normal(size=50), rng.normal(size=3)) + np.outer(rng.normal(size=50), rng.normal(size=3))
+            S = s.T @ s
+        else:
+            s = np.outer(rng.normal(size=50), rng.normal(size=3))
+            S = s.T @ s
+        N = _horn_matrix(S)
+        ok, q = orc.horn_top_eigvec(N)
+        if kind == 4:
+            assert not ok
+            declined += 1
+            continue
+        assert ok
+        v = np.linalg.eigh(N)[1][:, -1]
+        q = q / np.linalg.norm(q)
+        assert min(np.linalg.norm(q - v), np.linalg.norm(q + v)) < 1e-7
+    assert declined == 800
+    assert orc.horn_top_eigvec(np.zeros((4, 4)))[0] is False
+
+
 def test_horn_matches_kabsch(orc, clouds):
     src = clouds("chair1")[:500]
     gt = synth.rigid(20, -35, 110, (0.3, -0.2, 0.5), about=(0.1, 0.2, 0.3))
