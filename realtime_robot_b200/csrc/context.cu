@@ -38,19 +38,24 @@ __global__ void k_gather_sorted(const float4* __restrict__ pts, const int* __res
     sorted[s] = p;
 }
 
-// Grid build for repo-sized clouds in ONE launch (one CTA): histogram -> exclusive scan -> scatter -> in-cell ranking by
-// original index (so the order is the same stable order the radix-sort path produces) -> gather.  Replaces memset + keys
-// + radix sort + scan + gather (7-8 launches, each a few microseconds of pure latency at these sizes).
+// Grid build for repo-sized clouds in ONE launch: a thread-block CLUSTER of 8 CTAs (8192 threads on 8 SMs) walks the
+// phases histogram -> exclusive scan -> scatter -> in-cell ranking by original index (the same stable order the
+// radix-sort path produces) -> gather, with hardware cluster barriers between them.  Replaces memset + keys + radix
+// sort + scan + gather (7-8 launches, each a few microseconds of pure latency at these sizes).
 #define GB_THREADS 1024
-__global__ void __launch_bounds__(GB_THREADS) k_grid_build_small(const float4* __restrict__ pts, int n, float mnx, float mny, float mnz,
-                                                                float inv_h, int dx, int dy, int dz, int ncells, int* __restrict__ cell_begin,
-                                                                int* __restrict__ keys, int* __restrict__ cursor, int* __restrict__ slot,
-                                                                float4* __restrict__ sorted) {
+#define GB_CLUSTER 8
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__global__ void __cluster_dims__(GB_CLUSTER, 1, 1) __launch_bounds__(GB_THREADS)
+k_grid_build_small(const float4* __restrict__ pts, int n, float mnx, float mny, float mnz, float inv_h, int dx, int dy, int dz, int ncells,
+                   int* cell_begin, int* keys, int* cursor, int* slot, int* cta_total, float4* __restrict__ sorted) {
     __shared__ int part[GB_THREADS];
-    const int t = threadIdx.x;
-    for (int c = t; c <= ncells; c += GB_THREADS) cell_begin[c] = 0;
-    __syncthreads();
-    for (int i = t; i < n; i += GB_THREADS) {
+    const int t = threadIdx.x, cta = blockIdx.x;                 // one cluster per launch: blockIdx.x = rank in the cluster
+    const int gt = cta * GB_THREADS + t, GT = GB_CLUSTER * GB_THREADS;
+    for (int c = gt; c <= ncells; c += GT) cell_begin[c] = 0;
+    cluster_sync_all();
+    for (int i = gt; i < n; i += GT) {
         float4 p = __ldg(pts + i);
         int cx = clampi(cell_coord(p.x, mnx, inv_h), 0, dx - 1);
         int cy = clampi(cell_coord(p.y, mny, inv_h), 0, dy - 1);
@@ -59,10 +64,11 @@ __global__ void __launch_bounds__(GB_THREADS) k_grid_build_small(const float4* _
         keys[i] = key;
         atomicAdd(cell_begin + key, 1);
     }
-    __syncthreads();
-    // exclusive scan of cell_begin[0 .. ncells] in place: contiguous chunk per thread + block scan of the chunk sums
-    int per = (ncells + 1 + GB_THREADS - 1) / GB_THREADS;
-    int c0 = min(t * per, ncells + 1), c1 = min(c0 + per, ncells + 1);
+    cluster_sync_all();
+    // exclusive scan of cell_begin[0 .. ncells] in place: contiguous chunk per thread, block scan of the chunk sums,
+    // then the totals of the lower-ranked CTAs
+    int per = (ncells + 1 + GT - 1) / GT;
+    int c0 = min(gt * per, ncells + 1), c1 = min(c0 + per, ncells + 1);
     int sum = 0;
     for (int c = c0; c < c1; ++c) sum += cell_begin[c];
     part[t] = sum;
@@ -73,13 +79,16 @@ __global__ void __launch_bounds__(GB_THREADS) k_grid_build_small(const float4* _
         part[t] += v;
         __syncthreads();
     }
+    if (t == GB_THREADS - 1) cta_total[cta] = part[t];
+    cluster_sync_all();
     int run = part[t] - sum;
+    for (int k = 0; k < cta; ++k) run += cta_total[k];
     for (int c = c0; c < c1; ++c) { int v = cell_begin[c]; cell_begin[c] = run; cursor[c] = run; run += v; }
-    __syncthreads();
-    for (int i = t; i < n; i += GB_THREADS) slot[atomicAdd(cursor + keys[i], 1)] = i;       // unordered inside a cell
-    __syncthreads();
+    cluster_sync_all();
+    for (int i = gt; i < n; i += GT) slot[atomicAdd(cursor + keys[i], 1)] = i;       // unordered inside a cell
+    cluster_sync_all();
     // rank inside the cell = number of members with a smaller original index -> deterministic ascending order
-    for (int pos = t; pos < n; pos += GB_THREADS) {
+    for (int pos = gt; pos < n; pos += GT) {
         int i = slot[pos];
         int key = keys[i];
         int b = cell_begin[key], e = cell_begin[key + 1];
@@ -260,17 +269,18 @@ int rtr_get_grid(rtr_cloud* c, float cell, DevGrid** out) {
     g.mnx = c->bb_min[0]; g.mny = c->bb_min[1]; g.mnz = c->bb_min[2];
     g.ncells = g.dx * g.dy * g.dz;
     int n = c->n;
-    if (n > 0 && n <= 32768 && g.ncells <= (1 << 21)) {
-        int *keys = nullptr, *cursor = nullptr, *slot = nullptr;
+    if (n > 0 && n <= 65536 && g.ncells <= (1 << 22)) {
+        int *keys = nullptr, *cursor = nullptr, *slot = nullptr, *cta_total = nullptr;
+        if (int e = tmp_alloc(ctx, &cta_total, GB_CLUSTER, "grid")) return e;
         if (int e = tmp_alloc(ctx, &keys, n, "grid")) return e;
         if (int e = tmp_alloc(ctx, &cursor, (size_t)g.ncells + 1, "grid")) return e;
         if (int e = tmp_alloc(ctx, &slot, n, "grid")) return e;
         if (int e = dev_alloc(ctx, &g.cell_begin, (size_t)g.ncells + 1, "grid")) return e;
         if (int e = dev_alloc(ctx, &g.sorted, n, "grid")) return e;
-        k_grid_build_small<<<1, GB_THREADS, 0, ctx->stream>>>(c->pts, n, g.mnx, g.mny, g.mnz, g.inv_h, g.dx, g.dy, g.dz, g.ncells,
-                                                               g.cell_begin, keys, cursor, slot, g.sorted);
+        k_grid_build_small<<<GB_CLUSTER, GB_THREADS, 0, ctx->stream>>>(c->pts, n, g.mnx, g.mny, g.mnz, g.inv_h, g.dx, g.dy, g.dz, g.ncells,
+                                                                        g.cell_begin, keys, cursor, slot, cta_total, g.sorted);
         RTR_LAUNCH_CHECK(ctx, "grid.build_small");
-        dev_free(ctx, keys); dev_free(ctx, cursor); dev_free(ctx, slot);
+        dev_free(ctx, keys); dev_free(ctx, cursor); dev_free(ctx, slot); dev_free(ctx, cta_total);
         auto ins = c->grids.emplace(keybits, g);
         *out = &ins.first->second;
         return 0;

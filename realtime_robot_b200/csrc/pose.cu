@@ -382,7 +382,7 @@ __device__ void icp_last_cta_solve(const double* partials, IcpState* st, unsigne
 }
 
 // correspondence estimation + accumulation.  Applies the previous iteration's step first (transformCloud in place).
-__global__ void __launch_bounds__(ICP_THREADS) k_icp_corr(GridView g, float4* __restrict__ cur, int n, IcpState* st,
+__global__ void __launch_bounds__(ICP_THREADS, 4) k_icp_corr(GridView g, float4* __restrict__ cur, int n, IcpState* st,
                                                            double dmax2, float prune2, double* partials, unsigned* ticket, IcpSolveArgs sa) {
     __shared__ float m[16];
     __shared__ double red[ICP_THREADS / 32][ICP_NSUM];
