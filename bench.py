@@ -329,6 +329,9 @@ def main():
         alg = sum(km * per_k + nm * per_q + ks * per_k + ns * per_q for km, nm, ks, ns in neighbour_sums(r))
     elif dom == "icp.corr":
         alg = sum(cm.n * 32 for cm in models_d) * p.icp.max_iterations
+    elif dom.startswith("grid.build"):
+        # two grids (normals / FPFH radius) per cloud per registration: read 16 B, write 16 B sorted + 4 B key + 4 B slot per point
+        alg = sum(2 * (cm.n + scene_d.n) * 40 for cm in models_d)
     roofline = {"kernel": dom, "bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
                 "peak_source": peak_src, "launches_per_step": prof[dom][0], "ms_per_step": round(prof[dom][1], 4),
                 "share_of_step": round(prof[dom][1] / step_ms, 4),
@@ -392,9 +395,17 @@ def main():
                 cmn.reset(); csn.reset()
                 ctx.record(6); rn = api.native_register(cmn, csn, npar); ctx.record(7)
                 ms += ctx.elapsed_ms(6, 7)
-            native_out = {"workload": "reference-native path, chair1.pcd (model) vs T0_m8111.pcd (scan) as main() loads them: Harris, occupancy, TDF, "
-                                      "7 x 11 pair sweeps x 36 angles, screens, exhaustive consensus", "registrations_per_s": reps / (ms * 1e-3),
-                          "ms_per_registration": ms / reps, "keypoints": [int(rn.n_keypoints_src), int(rn.n_keypoints_tgt)],
+            npar0 = default_native_params(); npar0.use_plane_areas = 0
+            ms0 = 0.0
+            for _ in range(reps + 3):
+                cmn.reset(); csn.reset()
+                ctx.record(6); api.native_register(cmn, csn, npar0); ctx.record(7)
+                ms0 += ctx.elapsed_ms(6, 7) if _ >= 3 else 0.0
+            native_out = {"workload": "reference-native path, chair1.pcd (model) vs T0_m8111.pcd (scan) as main() loads them: getArea plane peel of "
+                                      "both clouds, Harris, occupancy, TDF, 7 x 11 pair sweeps x 36 angles, screens, exhaustive consensus",
+                          "registrations_per_s": reps / (ms * 1e-3),
+                          "ms_per_registration": ms / reps, "ms_per_registration_without_plane_peel": ms0 / reps,
+                          "keypoints": [int(rn.n_keypoints_src), int(rn.n_keypoints_tgt)],
                           "screened_pairs": int(rn.evaluated), "consensus": int(rn.inliers)}
             if world == 1 and not args.no_cpu_baseline:
                 from oracle import orc
@@ -407,6 +418,24 @@ def main():
             cmn.free(); csn.free()
         except Exception as e:          # the headline line must survive a failure of an auxiliary section
             native_out = {"error": repr(e)}
+    # ---- PCD I/O either side of the path: 1 M points, the three DATA modes, file -> device cloud
+    pcd_out = None
+    if rank == 0 and not args.no_icp:
+        try:
+            import tempfile
+            big = synth.icp_config(1000, 1_000_000)[1]
+            pcd_out = {"points": len(big)}
+            with tempfile.TemporaryDirectory() as td:
+                for mode, nm in ((api.PCD_ASCII, "ascii"), (api.PCD_BINARY, "binary"), (api.PCD_BINARY_COMPRESSED, "binary_compressed")):
+                    f = os.path.join(td, nm + ".pcd")
+                    t0 = time.perf_counter(); api.write_pcd(f, big, mode); tw = time.perf_counter() - t0
+                    api.Cloud.from_pcd(ctx, f).free()
+                    t0 = time.perf_counter(); cl = api.Cloud.from_pcd(ctx, f); ctx.sync(); tr = time.perf_counter() - t0
+                    cl.free()
+                    pcd_out[nm] = {"file_MB": round(os.path.getsize(f) / 1e6, 1), "write_ms": round(1e3 * tw, 1),
+                                   "load_to_device_ms": round(1e3 * tr, 1), "load_Mpoints_per_s": round(len(big) / tr / 1e6, 1)}
+        except Exception as e:
+            pcd_out = {"error": repr(e)}
     log("cpu baseline")
     # ---- CPU baseline beside it (rank 0, N = 1): the oracle, one thread, the step's 8 registrations once
     cpu = None
@@ -438,7 +467,7 @@ def main():
                 "gpu_launches": int(launches),
                 "clocks": clocks, "roofline": roofline, "kernel_share": kernel_share, "serialised_device_ms_per_step": round(step_ms, 3),
                 "per_model_device_ms": per_model_ms, "per_model_latency_ms_alone": lat,
-                "cpu_baseline": cpu, "icp_1m": icp_out, "native_path": native_out,
+                "cpu_baseline": cpu, "icp_1m": icp_out, "native_path": native_out, "pcd_io_1m": pcd_out,
                 "wall_ms_per_step_incl_l2_flush": 1e3 * wall_res / args.steps,
                 "results": [{"model": m, "fitness": float(r.fitness), "inliers": int(r.inliers), "hypothesis": int(r.hypothesis),
                              "evaluated": int(r.evaluated), "converged": int(r.converged)} for m, r in zip(MODELS, mine)]}

@@ -154,6 +154,20 @@ int rtr_cloud_transform(rtr_cloud* c, const float* pose16);
 /* Copy points back to host (n x 4 floats). */
 int rtr_cloud_download(rtr_cloud* c, float* host_xyz1);
 
+/* ------------------------------------------------------------------ PCD v0.7 I/O
+ * pcl::io::loadPCDFile (RealTimeRobot.cpp:34-35, scan_point.h:62) and pcl::io::savePCDFileASCII (RealTimeRobot.cpp:108-109,
+ * function.h:126-127), for DATA ascii | binary | binary_compressed; only x y z (float32) are kept, as the reference loads
+ * every file into pcl::PointCloud<pcl::PointXYZ>.  Host-side, multi-threaded; no GPU needed except for rtr_pcd_load /
+ * rtr_cloud_save.  data_mode / mode: 0 ascii (8 significant digits, what savePCDFileASCII prints), 1 binary,
+ * 2 binary_compressed (LZF, field-major). */
+int rtr_pcd_info(const char* path, int* n_points, int* data_mode);
+/* Decode into n x 4 floats (x, y, z, 1).  RTR_ERR_CAPACITY (with *n_points set) when capacity is too small. */
+int rtr_pcd_read(const char* path, float* host_xyz1, int capacity, int* n_points);
+/* File -> pinned staging owned by the context -> device cloud (one asynchronous copy). */
+int rtr_pcd_load(rtr_context* ctx, const char* path, rtr_cloud** out);
+int rtr_pcd_write(const char* path, const float* host_xyz1, int n, int mode);
+int rtr_cloud_save(rtr_cloud* c, const char* path, int mode);
+
 /* ------------------------------------------------------------------ neighbour index */
 
 /* Exact radius neighbour sets over the uniform grid, for queries == the cloud's own points:

@@ -18,7 +18,8 @@ EXPORTS = [
     "rtr_cloud_free", "rtr_cloud_size", "rtr_cloud_transform", "rtr_cloud_download", "rtr_radius_neighbors", "rtr_nearest",
     "rtr_normals", "rtr_harris3d", "rtr_fpfh", "rtr_match_features", "rtr_match_features_raw", "rtr_match_last_stats", "rtr_ransac_prerejective", "rtr_icp", "rtr_register",
     "rtr_register_host", "ComputeTDFWithCuda", "rtr_tdf_batch", "rtr_tdf_batch_dev", "rtr_native_default_params", "rtr_native_keypoint_descriptors",
-    "rtr_native_pair_scores", "rtr_native_register", "rtr_plane_areas",
+    "rtr_native_pair_scores", "rtr_native_register", "rtr_plane_areas", "rtr_pcd_info", "rtr_pcd_read", "rtr_pcd_load", "rtr_pcd_write",
+    "rtr_cloud_save",
 ]
 
 
@@ -75,6 +76,11 @@ def lib():
         L.rtr_native_pair_scores.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, C.POINTER(NativeParams), vp, vp, vp]
         L.rtr_plane_areas.argtypes = [vp, C.POINTER(Surface), C.c_int, ip]
         L.rtr_native_register.argtypes = [vp, vp, C.POINTER(NativeParams), C.POINTER(PoseResult)]
+        L.rtr_pcd_info.argtypes = [C.c_char_p, ip, ip]
+        L.rtr_pcd_read.argtypes = [C.c_char_p, vp, C.c_int, ip]
+        L.rtr_pcd_load.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+        L.rtr_pcd_write.argtypes = [C.c_char_p, vp, C.c_int, C.c_int]
+        L.rtr_cloud_save.argtypes = [vp, C.c_char_p, C.c_int]
         _LIB = L
     return _LIB
 

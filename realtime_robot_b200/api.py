@@ -6,6 +6,7 @@ Ransac -> ransac_prerejective).  Everything here is plumbing: ctypes calls into 
 and there is no CPU fallback.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -73,6 +74,31 @@ class Context:
             pass
 
 
+PCD_ASCII, PCD_BINARY, PCD_BINARY_COMPRESSED = 0, 1, 2
+
+
+def pcd_info(path: str):
+    """(number of points, DATA mode) of a PCD v0.7 file."""
+    n, m = C.c_int(), C.c_int()
+    _lib.check("rtr_pcd_info", _lib.lib().rtr_pcd_info(os.fsencode(path), C.byref(n), C.byref(m)))
+    return n.value, m.value
+
+
+def read_pcd(path: str) -> np.ndarray:
+    """pcl::io::loadPCDFile into host memory: (n, 4) float32 (x, y, z, 1); ascii, binary and binary_compressed."""
+    n, _ = pcd_info(path)
+    out = np.zeros((n, 4), dtype=np.float32)
+    got = C.c_int()
+    _lib.check("rtr_pcd_read", _lib.lib().rtr_pcd_read(os.fsencode(path), _ptr(out), n, C.byref(got)))
+    return out
+
+
+def write_pcd(path: str, xyz1, mode: int = PCD_ASCII):
+    """pcl::io::savePCDFileASCII (mode 0) / savePCDFileBinary (1) / savePCDFileBinaryCompressed (2)."""
+    xyz1 = _f32(xyz1, 4)
+    _lib.check("rtr_pcd_write", _lib.lib().rtr_pcd_write(os.fsencode(path), _ptr(xyz1), len(xyz1), mode))
+
+
 class Cloud:
     """Device-resident pcl::PointCloud<pcl::PointXYZ> (n x 16 B) plus its cached stages."""
 
@@ -98,6 +124,20 @@ class Cloud:
             self.free()
         except Exception:
             pass
+
+    @classmethod
+    def from_pcd(cls, ctx: Context, path: str) -> "Cloud":
+        """pcl::io::loadPCDFile straight to the device: file -> pinned staging -> one async copy (rtr_pcd_load)."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        _lib.check("rtr_pcd_load", _lib.lib().rtr_pcd_load(ctx._h, os.fsencode(path), C.byref(self._h)))
+        self.n = int(_lib.lib().rtr_cloud_size(self._h))
+        return self
+
+    def save_pcd(self, path: str, mode: int = PCD_ASCII):
+        """pcl::io::savePCDFileASCII (mode 0) / binary (1) / binary_compressed (2) of the device cloud."""
+        _lib.check("rtr_cloud_save", _lib.lib().rtr_cloud_save(self._h, os.fsencode(path), mode))
 
     def reset(self):
         """Forget every cached stage (the points stay resident)."""

@@ -62,6 +62,9 @@ struct rtr_context {
     // small pinned staging area for results / counters
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
+    // pinned staging of rtr_pcd_load (decoded points, grown on demand)
+    void* io_pinned = nullptr;
+    size_t io_pinned_cap = 0;
 };
 
 struct rtr_cloud {

@@ -437,6 +437,7 @@ int rtr_context_destroy(rtr_context* ctx) {
     for (auto& m : ctx->marks) cudaEventDestroy(m.ev);
     for (auto& e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->io_pinned) cudaFreeHost(ctx->io_pinned);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;

@@ -96,78 +96,25 @@ inline void getMinMax3D(const PointCloud<PointXYZ>& c, PointXYZ& mn, PointXYZ& m
 
 namespace io {
 
-// pcl::io::loadPCDFile for PCD v0.7, DATA ascii | binary, keeping x y z (RealTimeRobot.cpp:34-35).  0 on success, -1 on error.
+// pcl::io::loadPCDFile for PCD v0.7, DATA ascii | binary | binary_compressed, keeping x y z (RealTimeRobot.cpp:34-35).
+// The decoding (multi-threaded, LZF) lives in librtr.so (csrc/pcd_io.cu); PointXYZ is the 16-byte record it fills.
+// 0 on success, -1 on error, like PCL.
 inline int loadPCDFile(const std::string& path, PointCloud<PointXYZ>& cloud) {
-    std::ifstream f(path, std::ios::binary);
-    if (!f) { fprintf(stderr, "[pcl_compat] cannot open %s\n", path.c_str()); return -1; }
-    std::vector<std::string> fields; std::vector<int> sizes, counts; std::vector<char> types;
-    size_t npts = 0, w = 0, h = 1; std::string mode, line;
-    while (std::getline(f, line)) {
-        if (!line.empty() && line.back() == '\r') line.pop_back();
-        if (line.empty() || line[0] == '#') continue;
-        std::istringstream ss(line); std::string key; ss >> key;
-        if (key == "FIELDS") { std::string v; while (ss >> v) fields.push_back(v); }
-        else if (key == "SIZE") { int v; while (ss >> v) sizes.push_back(v); }
-        else if (key == "TYPE") { char v; while (ss >> v) types.push_back(v); }
-        else if (key == "COUNT") { int v; while (ss >> v) counts.push_back(v); }
-        else if (key == "WIDTH") ss >> w;
-        else if (key == "HEIGHT") ss >> h;
-        else if (key == "POINTS") ss >> npts;
-        else if (key == "DATA") { ss >> mode; break; }
-    }
-    if (npts == 0) npts = w * h;
-    if (counts.empty()) counts.assign(fields.size(), 1);
-    if (fields.size() != sizes.size() || fields.size() != types.size() || fields.size() != counts.size()) return -1;
-    int col[3] = {-1, -1, -1}, off[3] = {-1, -1, -1}, c = 0, o = 0;
-    for (size_t i = 0; i < fields.size(); ++i) {
-        for (int a = 0; a < 3; ++a) if (fields[i] == std::string(1, "xyz"[a])) { col[a] = c; off[a] = o; if (types[i] != 'F' || sizes[i] != 4) return -1; }
-        c += counts[i]; o += sizes[i] * counts[i];
-    }
-    if (col[0] < 0 || col[1] < 0 || col[2] < 0) return -1;
-    cloud.points.assign(npts, PointXYZ());
-    if (mode == "ascii") {
-        for (size_t i = 0; i < npts; ++i) {
-            if (!std::getline(f, line)) return -1;
-            std::istringstream ss(line); std::string tok; int k = 0;
-            while (ss >> tok) {
-                for (int a = 0; a < 3; ++a) if (k == col[a]) (&cloud.points[i].x)[a] = strtof(tok.c_str(), nullptr);
-                ++k;
-            }
-        }
-    } else if (mode == "binary") {
-        std::vector<char> rec(o);
-        for (size_t i = 0; i < npts; ++i) {
-            if (!f.read(rec.data(), o)) return -1;
-            for (int a = 0; a < 3; ++a) memcpy(&(&cloud.points[i].x)[a], rec.data() + off[a], 4);
-        }
-    } else { fprintf(stderr, "[pcl_compat] DATA %s not supported\n", mode.c_str()); return -1; }
-    cloud.width = (uint32_t)npts; cloud.height = 1; cloud.is_dense = true;
+    int n = 0, mode = 0;
+    if (rtr_pcd_info(path.c_str(), &n, &mode) != 0) return -1;
+    cloud.points.assign((size_t)n, PointXYZ());
+    static_assert(sizeof(PointXYZ) == 16, "pcl::PointXYZ is x, y, z + padding");
+    if (rtr_pcd_read(path.c_str(), n ? &cloud.points[0].x : nullptr, n, &n) != 0) return -1;
+    cloud.width = (uint32_t)n; cloud.height = 1; cloud.is_dense = true;
     return 0;
 }
 
-inline std::string pcd_header(size_t n, const char* mode) {
-    std::ostringstream h;
-    h << "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH " << n
-      << "\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS " << n << "\nDATA " << mode << "\n";
-    return h.str();
+inline int save_pcd(const std::string& path, const PointCloud<PointXYZ>& cloud, int mode) {
+    return rtr_pcd_write(path.c_str(), cloud.empty() ? nullptr : &cloud.points[0].x, (int)cloud.size(), mode) == 0 ? 0 : -1;
 }
-
 // pcl::io::savePCDFileASCII (RealTimeRobot.cpp:108-109; 8 significant digits like PCL)
-inline int savePCDFileASCII(const std::string& path, const PointCloud<PointXYZ>& cloud) {
-    FILE* f = fopen(path.c_str(), "w");
-    if (!f) return -1;
-    fputs(pcd_header(cloud.size(), "ascii").c_str(), f);
-    for (const auto& p : cloud.points) fprintf(f, "%.8g %.8g %.8g\n", p.x, p.y, p.z);
-    fclose(f);
-    return 0;
-}
-inline int savePCDFileBinary(const std::string& path, const PointCloud<PointXYZ>& cloud) {
-    FILE* f = fopen(path.c_str(), "wb");
-    if (!f) return -1;
-    fputs(pcd_header(cloud.size(), "binary").c_str(), f);
-    for (const auto& p : cloud.points) fwrite(&p.x, 4, 3, f);
-    fclose(f);
-    return 0;
-}
+inline int savePCDFileASCII(const std::string& path, const PointCloud<PointXYZ>& cloud) { return save_pcd(path, cloud, 0); }
+inline int savePCDFileBinary(const std::string& path, const PointCloud<PointXYZ>& cloud) { return save_pcd(path, cloud, 1); }
+inline int savePCDFileBinaryCompressed(const std::string& path, const PointCloud<PointXYZ>& cloud) { return save_pcd(path, cloud, 2); }
 }  // namespace io
 }  // namespace pcl

@@ -1,4 +1,4 @@
-"""PCD v0.7 reader / writer (ascii + binary), xyz extraction.
+"""PCD v0.7 reader / writer (ascii + binary; binary_compressed through librtr.so), xyz extraction.
 
 Harness-side mirror of the two PCL I/O calls the reference path makes:
 ``pcl::io::loadPCDFile`` (RealTimeRobot/RealTimeRobot.cpp:34-35, scan_point.h:62) and
@@ -60,6 +60,9 @@ def read_pcd_xyz(path) -> np.ndarray:
             rec = np.frombuffer(f.read(npts * dt.itemsize), dtype=dt, count=npts)
             return np.ascontiguousarray(
                 np.stack([rec["x"], rec["y"], rec["z"]], axis=1).astype(np.float32))
+        if mode == "binary_compressed":          # LZF codec lives in the library (csrc/pcd_io.cu); host-only, no GPU needed
+            from . import api
+            return np.ascontiguousarray(api.read_pcd(str(path))[:, :3])
         raise ValueError(f"PCD: DATA {mode} not supported")
 
 

@@ -532,3 +532,29 @@ def test_plane_peel_and_hull_area(api, gpu_ctx, orc, clouds, name):
         cf = api.Cloud(gpu_ctx, few)
         assert api.plane_areas(cf) == []
         cf.free()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_pcd_file_to_device_and_back(api, gpu_ctx, clouds, tmp_path, mode):
+    """rtr_pcd_load (file -> pinned staging -> device) and rtr_cloud_save, all three DATA modes, checked by the CPU
+    restatement of the container (oracle/pcd_ref.py); a registration from files equals the one from arrays."""
+    from oracle import pcd_ref
+    pts = clouds("chair1")
+    src = str(tmp_path / "in.pcd")
+    pcd_ref.write_xyz(src, pts[:, :3], ["ascii", "binary", "binary_compressed"][mode], extra_field=(mode == 1))
+    c = api.Cloud.from_pcd(gpu_ctx, src)
+    assert c.n == len(pts) and np.array_equal(c.download().view(np.uint32), pts.view(np.uint32))
+    dst = str(tmp_path / "out.pcd")
+    c.save_pcd(dst, mode)
+    back = pcd_ref.read_xyz(dst)
+    if mode == 0:
+        assert np.allclose(back, pts[:, :3], rtol=1.3e-7, atol=1e-37)
+    else:
+        assert np.array_equal(back.view(np.uint32), pts[:, :3].view(np.uint32))
+    s = api.Cloud(gpu_ctx, clouds("mcloud"))
+    p = default_register_params(); p.ransac.max_iterations = 5000
+    r_file = api.register(c, s, p)
+    c2 = api.Cloud(gpu_ctx, pts)
+    r_arr = api.register(c2, s, p)
+    assert np.array_equal(r_file.matrix(), r_arr.matrix()) and r_file.hypothesis == r_arr.hypothesis
+    c.free(); c2.free(); s.free()

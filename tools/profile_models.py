@@ -24,5 +24,5 @@ for name in names:
     pr = ctx.profile_end()
     tot = sum(v[1] for v in pr.values())
     print(name, len(m), "points; serialised device ms", round(tot, 3), "inliers", r.inliers)
-    for k, v in sorted(pr.items(), key=lambda kv: -kv[1][1])[:14]:
+    for k, v in sorted(pr.items(), key=lambda kv: -kv[1][1])[:int(os.environ.get("TOP", "14"))]:
         print("   %-22s x%-3d %.3f ms" % (k, v[0], v[1]))
