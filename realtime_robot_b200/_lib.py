@@ -19,7 +19,7 @@ EXPORTS = [
     "rtr_normals", "rtr_harris3d", "rtr_fpfh", "rtr_match_features", "rtr_match_features_raw", "rtr_match_last_stats", "rtr_ransac_prerejective", "rtr_icp", "rtr_register",
     "rtr_register_host", "ComputeTDFWithCuda", "rtr_tdf_batch", "rtr_tdf_batch_dev", "rtr_native_default_params", "rtr_native_keypoint_descriptors",
     "rtr_native_pair_scores", "rtr_native_register", "rtr_plane_areas", "rtr_pcd_info", "rtr_pcd_read", "rtr_pcd_load", "rtr_pcd_write",
-    "rtr_cloud_save",
+    "rtr_cloud_save", "rtr_register_begin", "rtr_register_host_begin", "rtr_register_end",
 ]
 
 
@@ -76,6 +76,9 @@ def lib():
         L.rtr_native_pair_scores.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, C.POINTER(NativeParams), vp, vp, vp]
         L.rtr_plane_areas.argtypes = [vp, C.POINTER(Surface), C.c_int, ip]
         L.rtr_native_register.argtypes = [vp, vp, C.POINTER(NativeParams), C.POINTER(PoseResult)]
+        L.rtr_register_begin.argtypes = [vp, vp, C.POINTER(RegisterParams)]
+        L.rtr_register_host_begin.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.POINTER(RegisterParams)]
+        L.rtr_register_end.argtypes = [vp, C.POINTER(PoseResult)]
         L.rtr_pcd_info.argtypes = [C.c_char_p, ip, ip]
         L.rtr_pcd_read.argtypes = [C.c_char_p, vp, C.c_int, ip]
         L.rtr_pcd_load.argtypes = [vp, C.c_char_p, C.POINTER(vp)]

@@ -224,6 +224,26 @@ def register_host(ctx: Context, model_xyz1, scene_xyz1, params: RegisterParams) 
     return res
 
 
+def register_begin(model: Cloud, scene: Cloud, params: RegisterParams) -> None:
+    """Queue a whole registration on the clouds' context and return (no host synchronisation); see register_end."""
+    _lib.check("rtr_register_begin", _lib.lib().rtr_register_begin(model._h, scene._h, C.byref(params)))
+
+
+def register_host_begin(ctx: Context, model_xyz1, scene_xyz1, params: RegisterParams) -> None:
+    """Same from host clouds (pinned memory keeps the uploads asynchronous).  The arrays must stay alive until register_end."""
+    m, s = _f32(model_xyz1, 4), _f32(scene_xyz1, 4)
+    ctx._inflight = (m, s)
+    _lib.check("rtr_register_host_begin", _lib.lib().rtr_register_host_begin(ctx._h, _ptr(m), len(m), _ptr(s), len(s), C.byref(params)))
+
+
+def register_end(ctx: Context) -> PoseResult:
+    """Wait for the registration in flight on `ctx` and return its record."""
+    res = PoseResult()
+    _lib.check("rtr_register_end", _lib.lib().rtr_register_end(ctx._h, C.byref(res)))
+    ctx._inflight = None
+    return res
+
+
 def compute_tdf_with_cuda(voxel_grid_occ, voxel_grid_tdf, voxel_grid_dim: int, num_occ: int) -> int:
     """The reference FFI, unchanged (key_point.h:35-36).  voxel_grid_tdf: 27000 float32, modified in place."""
     occ = np.ascontiguousarray(voxel_grid_occ, dtype=np.int32)

@@ -62,6 +62,9 @@ struct rtr_context {
     // small pinned staging area for results / counters
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
+    // asynchronous registration (rtr_register_begin / _end): at most one in flight per context
+    int register_pending = 0;
+    struct rtr_cloud* pending_cloud[2] = {nullptr, nullptr};
     // pinned staging of rtr_pcd_load (decoded points, grown on demand)
     void* io_pinned = nullptr;
     size_t io_pinned_cap = 0;
@@ -336,6 +339,32 @@ __device__ __forceinline__ BlockRanges warp_block_ranges(const GridView& g, int 
     return br;
 }
 
+// The 9 ranges of a 27-cell block as ONE candidate list for a warp: candidate j of [0, total) lives at sorted position
+// locate(j), in the same order as walking the ranges one after another.  Walking range by range costs a dependent memory
+// round trip per range and leaves most lanes idle when a range holds 3-5 points (sparse clouds: ~30 neighbours over 9
+// ranges); the flat list needs ceil(total / 32) steps with every lane busy and all loads of a step in flight together.
+struct WarpCand { int total; int pre[9]; int first[9]; };
+__device__ __forceinline__ WarpCand warp_candidates(const GridView& g, int cx, int cy, int cz, int lane) {
+    BlockRanges br = warp_block_ranges(g, cx, cy, cz, lane);
+    int end = __shfl_sync(0xffffffffu, br.bound, (lane + 9) & 31);
+    int len = lane < 9 ? max(end - br.bound, 0) : 0;
+    int incl = len;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    WarpCand w;
+    w.total = __shfl_sync(0xffffffffu, incl, 8);
+    int excl = incl - len;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { w.pre[k] = __shfl_sync(0xffffffffu, excl, k); w.first[k] = __shfl_sync(0xffffffffu, br.bound, k); }
+    return w;
+}
+__device__ __forceinline__ int locate(const WarpCand& w, int j) {
+    int start = 0, first = w.first[0];
+#pragma unroll
+    for (int k = 1; k < 9; ++k) if (j >= w.pre[k]) { start = w.pre[k]; first = w.first[k]; }
+    return first + (j - start);
+}
+
 // Warp-cooperative form of grid_nearest_ex for small query sets (one warp per query): the lanes stride over the points
 // of every visited range and the (d2, index) minimum is folded with shuffles.  Same visiting rules, same result.
 __device__ __forceinline__ void warp_argmin(float& d, int& id, float4& p) {
@@ -356,19 +385,13 @@ __device__ __forceinline__ void grid_nearest_warp(const GridView& g, float qx, f
     int cy = clampi(cell_coord(qy, g.mny, g.inv_h), 0, g.dy - 1);
     int cz = clampi(cell_coord(qz, g.mnz, g.inv_h), 0, g.dz - 1);
     {
-        BlockRanges br = warp_block_ranges(g, cx, cy, cz, lane);
-        for (int z = br.z0; z <= br.z1; ++z)
-            for (int y = br.y0; y <= br.y1; ++y) {
-                int r = (z - br.z0) * 3 + (y - br.y0);
-                int s0 = __shfl_sync(0xffffffffu, br.bound, r);
-                int s1 = __shfl_sync(0xffffffffu, br.bound, 9 + r);
-                for (int s = s0 + lane; s < s1; s += 32) {
-                    float4 p = __ldg(g.sorted + s);
-                    float d = dist2f(qx, qy, qz, p.x, p.y, p.z);
-                    int id = __float_as_int(p.w);
-                    if (best < 0 || d < best_d2 || (d == best_d2 && id < best)) { best_d2 = d; best = id; bp = p; }
-                }
-            }
+        WarpCand w = warp_candidates(g, cx, cy, cz, lane);
+        for (int j = lane; j < w.total; j += 32) {
+            float4 p = __ldg(g.sorted + locate(w, j));
+            float d = dist2f(qx, qy, qz, p.x, p.y, p.z);
+            int id = __float_as_int(p.w);
+            if (best < 0 || d < best_d2 || (d == best_d2 && id < best)) { best_d2 = d; best = id; bp = p; }
+        }
     }
     warp_argmin(best_d2, best, bp);
     float hh = g.h * 0.999f;

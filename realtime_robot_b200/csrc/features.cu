@@ -214,66 +214,94 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__global__ void __launch_bounds__(128) k_harris_refine(GridView g, const float4* __restrict__ sn, const float4* __restrict__ pts, float r2,
-                                                       const int* __restrict__ kp_idx, const int* __restrict__ kp_count, int capacity,
-                                                       float4* __restrict__ kp_xyz, int refine) {
-    int lane = threadIdx.x & 31;
-    int nwarps = (gridDim.x * blockDim.x) >> 5;
+// One CTA (4 warps) per corner: warp 0 fetches the 18 range bounds of the 27-cell block in one round trip, all 128
+// threads stride over the 9 ranges, the nine 64-bit integer sums are folded by shuffles and through shared memory
+// (any order: integer addition), thread 0 solves the 3x3 system and publishes the moved corner.
+#define REFINE_THREADS 128
+__global__ void __launch_bounds__(REFINE_THREADS) k_harris_refine(GridView g, const float4* __restrict__ sn, const float4* __restrict__ pts, float r2,
+                                                                  const int* __restrict__ kp_idx, const int* __restrict__ kp_count, int capacity,
+                                                                  float4* __restrict__ kp_xyz, int refine) {
+    __shared__ int bounds[18];
+    __shared__ long long wsum[REFINE_THREADS / 32][9];
+    __shared__ float4 c_sh;
+    __shared__ int again;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int m = min(*kp_count, capacity);
-    for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < m; t += nwarps) {
+    for (int t = blockIdx.x; t < m; t += gridDim.x) {
         float4 c = __ldg(pts + kp_idx[t]);
         c.w = 1.0f;
         if (refine) {
             int it = 0;
-            double diff;
-            do {
+            for (;;) {
                 float4 cur = c;
                 long long q[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
                 int cx = cell_coord(cur.x, g.mnx, g.inv_h), cy = cell_coord(cur.y, g.mny, g.inv_h), cz = cell_coord(cur.z, g.mnz, g.inv_h);
-                if (!(cx < -1 || cy < -1 || cz < -1 || cx > g.dx || cy > g.dy || cz > g.dz)) {
+                bool near_grid = !(cx < -1 || cy < -1 || cz < -1 || cx > g.dx || cy > g.dy || cz > g.dz);
+                if (near_grid) {
                     cx = clampi(cx, 0, g.dx - 1); cy = clampi(cy, 0, g.dy - 1); cz = clampi(cz, 0, g.dz - 1);
-                    int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
-                    for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
-                        for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y) {
-                            int s0 = __ldg(g.cell_begin + cell_key(g, x0, y, z));
-                            int s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
-                            for (int s = s0 + lane; s < s1; s += 32) {
-                                float4 p = __ldg(g.sorted + s);
-                                if (dist2f(cur.x, cur.y, cur.z, p.x, p.y, p.z) < r2) {
-                                    float4 nj = __ldg(sn + s);
-                                    if (finite3(nj)) {
-                                        double x = nj.x, y2 = nj.y, z2 = nj.z;
-                                        double xx = x * x, xy = x * y2, xz = x * z2, yy = y2 * y2, yz = y2 * z2, zz = z2 * z2;
-                                        double px = p.x, py = p.y, pz = p.z;
-                                        q[0] += __double2ll_rn(xx * REFINE_SCALE_A); q[1] += __double2ll_rn(xy * REFINE_SCALE_A);
-                                        q[2] += __double2ll_rn(xz * REFINE_SCALE_A); q[3] += __double2ll_rn(yy * REFINE_SCALE_A);
-                                        q[4] += __double2ll_rn(yz * REFINE_SCALE_A); q[5] += __double2ll_rn(zz * REFINE_SCALE_A);
-                                        q[6] += __double2ll_rn(((xx * px + xy * py) + xz * pz) * REFINE_SCALE_B);
-                                        q[7] += __double2ll_rn(((xy * px + yy * py) + yz * pz) * REFINE_SCALE_B);
-                                        q[8] += __double2ll_rn(((xz * px + yz * py) + zz * pz) * REFINE_SCALE_B);
-                                    }
-                                }
-                            }
+                    if (warp == 0) {
+                        BlockRanges br = warp_block_ranges(g, cx, cy, cz, lane);
+                        if (lane < 18) bounds[lane] = br.bound;      // slots of rows outside the grid hold 0 / 0: empty ranges
+                    }
+                    __syncthreads();
+                    // the 9 ranges as ONE candidate list: every thread issues all its loads before the first use
+                    int pre[10];
+                    pre[0] = 0;
+#pragma unroll
+                    for (int r = 0; r < 9; ++r) pre[r + 1] = pre[r] + max(bounds[9 + r] - bounds[r], 0);
+                    for (int j = tid; j < pre[9]; j += REFINE_THREADS) {
+                        int start = 0, first = bounds[0];
+#pragma unroll
+                        for (int k = 1; k < 9; ++k) if (j >= pre[k]) { start = pre[k]; first = bounds[k]; }
+                        int s = first + (j - start);
+                        float4 p = __ldg(g.sorted + s);
+                        float4 nj = __ldg(sn + s);          // fetched with the point, not after the distance test
+                        if (dist2f(cur.x, cur.y, cur.z, p.x, p.y, p.z) < r2 && finite3(nj)) {
+                            double x = nj.x, y2 = nj.y, z2 = nj.z;
+                            double xx = x * x, xy = x * y2, xz = x * z2, yy = y2 * y2, yz = y2 * z2, zz = z2 * z2;
+                            double px = p.x, py = p.y, pz = p.z;
+                            q[0] += __double2ll_rn(xx * REFINE_SCALE_A); q[1] += __double2ll_rn(xy * REFINE_SCALE_A);
+                            q[2] += __double2ll_rn(xz * REFINE_SCALE_A); q[3] += __double2ll_rn(yy * REFINE_SCALE_A);
+                            q[4] += __double2ll_rn(yz * REFINE_SCALE_A); q[5] += __double2ll_rn(zz * REFINE_SCALE_A);
+                            q[6] += __double2ll_rn(((xx * px + xy * py) + xz * pz) * REFINE_SCALE_B);
+                            q[7] += __double2ll_rn(((xy * px + yy * py) + yz * pz) * REFINE_SCALE_B);
+                            q[8] += __double2ll_rn(((xz * px + yz * py) + zz * pz) * REFINE_SCALE_B);
                         }
+                    }
                 }
 #pragma unroll
-                for (int k = 0; k < 9; ++k) q[k] = warp_sum_ll(q[k]);
-                double A0 = (double)q[0] / REFINE_SCALE_A, A1 = (double)q[1] / REFINE_SCALE_A, A2 = (double)q[2] / REFINE_SCALE_A;
-                double A3 = (double)q[3] / REFINE_SCALE_A, A4 = (double)q[4] / REFINE_SCALE_A, A5 = (double)q[5] / REFINE_SCALE_A;
-                double b0 = (double)q[6] / REFINE_SCALE_B, b1 = (double)q[7] / REFINE_SCALE_B, b2 = (double)q[8] / REFINE_SCALE_B;
-                double c00 = A3 * A5 - A4 * A4, c01 = A2 * A4 - A1 * A5, c02 = A1 * A4 - A2 * A3;
-                double c11 = A0 * A5 - A2 * A2, c12 = A1 * A2 - A0 * A4, c22 = A0 * A3 - A1 * A1;
-                double det = (A0 * c00 + A1 * c01) + A2 * c02;
-                if (det != 0) {
-                    c.x = (float)(((c00 * b0 + c01 * b1) + c02 * b2) / det);
-                    c.y = (float)(((c01 * b0 + c11 * b1) + c12 * b2) / det);
-                    c.z = (float)(((c02 * b0 + c12 * b1) + c22 * b2) / det);
+                for (int k = 0; k < 9; ++k) { long long v = warp_sum_ll(q[k]); if (lane == 0) wsum[warp][k] = v; }
+                __syncthreads();
+                if (tid == 0) {
+                    long long Q[9];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) Q[k] = ((wsum[0][k] + wsum[1][k]) + wsum[2][k]) + wsum[3][k];
+                    double A0 = (double)Q[0] / REFINE_SCALE_A, A1 = (double)Q[1] / REFINE_SCALE_A, A2 = (double)Q[2] / REFINE_SCALE_A;
+                    double A3 = (double)Q[3] / REFINE_SCALE_A, A4 = (double)Q[4] / REFINE_SCALE_A, A5 = (double)Q[5] / REFINE_SCALE_A;
+                    double b0 = (double)Q[6] / REFINE_SCALE_B, b1 = (double)Q[7] / REFINE_SCALE_B, b2 = (double)Q[8] / REFINE_SCALE_B;
+                    double c00 = A3 * A5 - A4 * A4, c01 = A2 * A4 - A1 * A5, c02 = A1 * A4 - A2 * A3;
+                    double c11 = A0 * A5 - A2 * A2, c12 = A1 * A2 - A0 * A4, c22 = A0 * A3 - A1 * A1;
+                    double det = (A0 * c00 + A1 * c01) + A2 * c02;
+                    float4 nc = cur;
+                    if (det != 0) {
+                        nc.x = (float)(((c00 * b0 + c01 * b1) + c02 * b2) / det);
+                        nc.y = (float)(((c01 * b0 + c11 * b1) + c12 * b2) / det);
+                        nc.z = (float)(((c02 * b0 + c12 * b1) + c22 * b2) / det);
+                    }
+                    double ddx = (double)nc.x - (double)cur.x, ddy = (double)nc.y - (double)cur.y, ddz = (double)nc.z - (double)cur.z;
+                    double diff = (ddx * ddx + ddy * ddy) + ddz * ddz;
+                    c_sh = nc;
+                    again = (diff > 1e-6 && it + 1 < 10) ? 1 : 0;
                 }
-                double ddx = (double)c.x - (double)cur.x, ddy = (double)c.y - (double)cur.y, ddz = (double)c.z - (double)cur.z;
-                diff = (ddx * ddx + ddy * ddy) + ddz * ddz;
-            } while (diff > 1e-6 && ++it < 10);
+                __syncthreads();
+                c = c_sh;
+                ++it;
+                int go = again;
+                __syncthreads();            // c_sh / again / bounds / wsum are rewritten by the next iteration
+                if (!go) break;
+            }
         }
-        if (lane == 0) kp_xyz[t] = c;
+        if (tid == 0) kp_xyz[t] = c;
     }
 }
 
@@ -825,7 +853,7 @@ int rtr_harris_dev(rtr_cloud* c, float radius, float threshold, int nms, int ref
         RTR_MARK(ctx, "harris.cub_select");
         dev_free(ctx, temp);
         // the corner count lives on the device: persistent grid of warps striding over the corner list
-        k_harris_refine<<<std::min(nblk((long long)n * 32, 128), ctx->sm_count * 8), 128, 0, ctx->stream>>>(v, g->sorted_normals, c->pts, r2, *d_kp_idx, *d_count, n, *d_kp_xyz, refine);
+        k_harris_refine<<<std::min(n, ctx->sm_count * 4), REFINE_THREADS, 0, ctx->stream>>>(v, g->sorted_normals, c->pts, r2, *d_kp_idx, *d_count, n, *d_kp_xyz, refine);
         RTR_LAUNCH_CHECK(ctx, "harris.refine");
     }
     dev_free(ctx, resp_sorted); dev_free(ctx, flags);

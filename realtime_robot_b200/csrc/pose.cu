@@ -728,9 +728,13 @@ int rtr_icp(rtr_cloud* source, rtr_cloud* target, const rtr_icp_params* p, const
     return rc;
 }
 
-int rtr_register(rtr_cloud* model, rtr_cloud* scene, const rtr_register_params* p, rtr_pose_result* host_result) {
-    if (!model || !scene || !p || !host_result || model->ctx != scene->ctx) return rtr_fail("register", "bad argument", RTR_ERR_INVALID);
+// Enqueue a whole registration on the context's stream and return: no host synchronisation.  The 128-byte record is copied
+// into the context's pinned result slot by the stream itself; rtr_register_end waits for it.  One registration may be in
+// flight per context; a host thread can keep many contexts (streams) busy this way without one thread per stream.
+int rtr_register_begin(rtr_cloud* model, rtr_cloud* scene, const rtr_register_params* p) {
+    if (!model || !scene || !p || model->ctx != scene->ctx) return rtr_fail("register", "bad argument", RTR_ERR_INVALID);
     rtr_context* ctx = model->ctx;
+    if (ctx->register_pending) return rtr_fail("register", "a registration is already in flight on this context", RTR_ERR_INVALID);
     TmpScope tmp_scope(ctx);
     RTR_CHECK(cudaSetDevice(ctx->device), "register");
     rtr_cloud* cl[2] = {model, scene};
@@ -749,19 +753,48 @@ int rtr_register(rtr_cloud* model, rtr_cloud* scene, const rtr_register_params* 
     if (p->run_icp) if (int e = rtr_icp_dev(model, scene, &p->icp, nullptr, 1, d_res)) return e;
     k_set_keypoints<<<1, 32, 0, ctx->stream>>>(d_res, d_cnt[0], d_cnt[1]);
     RTR_LAUNCH_CHECK(ctx, "register.kp");
-    int rc = fetch_result(ctx, d_res, host_result);
+    RTR_CHECK(cudaMemcpyAsync(ctx->pinned, d_res, sizeof(rtr_pose_result), cudaMemcpyDeviceToHost, ctx->stream), "result");
+    RTR_MARK(ctx, "result.d2h");
     dev_free(ctx, d_res); dev_free(ctx, d_cnt[0]); dev_free(ctx, d_cnt[1]);
-    return rc;
+    ctx->register_pending = 1;
+    return 0;
+}
+
+int rtr_register_end(rtr_context* ctx, rtr_pose_result* host_result) {
+    if (!ctx || !host_result) return rtr_fail("register", "bad argument", RTR_ERR_INVALID);
+    if (!ctx->register_pending) return rtr_fail("register", "no registration in flight on this context", RTR_ERR_INVALID);
+    ctx->register_pending = 0;
+    cudaError_t err = cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 2; ++i) if (ctx->pending_cloud[i]) { rtr_cloud_free(ctx->pending_cloud[i]); ctx->pending_cloud[i] = nullptr; }
+    RTR_CHECK(err, "result");
+    memcpy(host_result, ctx->pinned, sizeof(rtr_pose_result));
+    return 0;
+}
+
+int rtr_register(rtr_cloud* model, rtr_cloud* scene, const rtr_register_params* p, rtr_pose_result* host_result) {
+    if (!host_result) return rtr_fail("register", "bad argument", RTR_ERR_INVALID);
+    if (int e = rtr_register_begin(model, scene, p)) return e;
+    return rtr_register_end(model->ctx, host_result);
+}
+
+// host clouds in (pinned memory makes the two uploads asynchronous), record out; the device clouds live until _end
+int rtr_register_host_begin(rtr_context* ctx, const float* host_model_xyz1, int n_model, const float* host_scene_xyz1, int n_scene,
+                            const rtr_register_params* p) {
+    if (!ctx) return rtr_fail("register", "bad argument", RTR_ERR_INVALID);
+    if (ctx->register_pending) return rtr_fail("register", "a registration is already in flight on this context", RTR_ERR_INVALID);
+    rtr_cloud *m = nullptr, *s = nullptr;
+    if (int e = rtr_cloud_upload(ctx, host_model_xyz1, n_model, &m)) return e;
+    if (int e = rtr_cloud_upload(ctx, host_scene_xyz1, n_scene, &s)) { rtr_cloud_free(m); return e; }
+    if (int e = rtr_register_begin(m, s, p)) { rtr_cloud_free(m); rtr_cloud_free(s); return e; }
+    ctx->pending_cloud[0] = m; ctx->pending_cloud[1] = s;
+    return 0;
 }
 
 int rtr_register_host(rtr_context* ctx, const float* host_model_xyz1, int n_model, const float* host_scene_xyz1, int n_scene,
                       const rtr_register_params* p, rtr_pose_result* host_result) {
-    rtr_cloud *m = nullptr, *s = nullptr;
-    if (int e = rtr_cloud_upload(ctx, host_model_xyz1, n_model, &m)) return e;
-    if (int e = rtr_cloud_upload(ctx, host_scene_xyz1, n_scene, &s)) { rtr_cloud_free(m); return e; }
-    int rc = rtr_register(m, s, p, host_result);
-    rtr_cloud_free(m); rtr_cloud_free(s);
-    return rc;
+    if (!host_result) return rtr_fail("register", "bad argument", RTR_ERR_INVALID);
+    if (int e = rtr_register_host_begin(ctx, host_model_xyz1, n_model, host_scene_xyz1, n_scene, p)) return e;
+    return rtr_register_end(ctx, host_result);
 }
 
 }  // extern "C"

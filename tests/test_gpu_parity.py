@@ -558,3 +558,32 @@ def test_pcd_file_to_device_and_back(api, gpu_ctx, clouds, tmp_path, mode):
     r_arr = api.register(c2, s, p)
     assert np.array_equal(r_file.matrix(), r_arr.matrix()) and r_file.hypothesis == r_arr.hypothesis
     c.free(); c2.free(); s.free()
+
+
+def test_register_begin_end_equals_register(api, clouds):
+    """Four registrations queued on four contexts by one host thread (rtr_register_begin), collected afterwards: same
+    records as the synchronous call; misuse (double begin, end without begin) is reported, not executed."""
+    names = ["chair1", "chair2", "desk1", "Chair_025"]
+    p = default_register_params(); p.ransac.max_iterations = 5000
+    scene_h = clouds("mcloud")
+    ctxs = [api.Context(0) for _ in names]
+    ms = [api.Cloud(c, clouds(n)) for c, n in zip(ctxs, names)]
+    ss = [api.Cloud(c, scene_h) for c in ctxs]
+    sync = [api.register(m, s, p) for m, s in zip(ms, ss)]
+    for m, s in zip(ms, ss):
+        m.reset(); s.reset()
+        api.register_begin(m, s, p)
+    with pytest.raises(Exception):
+        api.register_begin(ms[0], ss[0], p)
+    got = [api.register_end(c) for c in ctxs]
+    with pytest.raises(Exception):
+        api.register_end(ctxs[0])
+    for a, b in zip(sync, got):
+        assert np.array_equal(a.matrix(), b.matrix()) and a.hypothesis == b.hypothesis and a.fitness == b.fitness and a.inliers == b.inliers
+    for m, s, c in zip(ms, ss, ctxs):
+        api.register_host_begin(c, m.download(), scene_h, p)
+    got = [api.register_end(c) for c in ctxs]
+    for a, b in zip(sync, got):
+        assert np.array_equal(a.matrix(), b.matrix()) and a.hypothesis == b.hypothesis
+    for x in ms + ss:
+        x.free()
