@@ -124,6 +124,9 @@ void rtr_default_register_params(rtr_register_params* p);
 /* One context per GPU (device id, one stream, a grow-only workspace arena).  Replaces the
  * cudaSetDevice(0) + cudaMalloc/cudaFree done on EVERY call at kernel.cu:43-56,101-102. */
 int rtr_context_create(int device, rtr_context** out);
+/* Same, with a scheduling hint: urgency 0 = default, larger = served first by the device when several contexts compete
+ * (mapped onto the CUDA stream priority range; longest-job-first for a batch of registrations of unequal size). */
+int rtr_context_create_prio(int device, int urgency, rtr_context** out);
 int rtr_context_destroy(rtr_context* ctx);
 int rtr_context_sync(rtr_context* ctx);
 /* cudaStream_t of the context, as void* (so callers can record CUDA events on it). */

@@ -19,7 +19,7 @@ EXPORTS = [
     "rtr_normals", "rtr_harris3d", "rtr_fpfh", "rtr_match_features", "rtr_match_features_raw", "rtr_match_last_stats", "rtr_ransac_prerejective", "rtr_icp", "rtr_register",
     "rtr_register_host", "ComputeTDFWithCuda", "rtr_tdf_batch", "rtr_tdf_batch_dev", "rtr_native_default_params", "rtr_native_keypoint_descriptors",
     "rtr_native_pair_scores", "rtr_native_register", "rtr_plane_areas", "rtr_pcd_info", "rtr_pcd_read", "rtr_pcd_load", "rtr_pcd_write",
-    "rtr_cloud_save", "rtr_register_begin", "rtr_register_host_begin", "rtr_register_end",
+    "rtr_cloud_save", "rtr_register_begin", "rtr_register_host_begin", "rtr_register_end", "rtr_context_create_prio",
 ]
 
 
@@ -38,6 +38,7 @@ def lib():
         L = C.CDLL(LIB_PATH)
         vp, ip, fp, ll = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_longlong
         L.rtr_context_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.rtr_context_create_prio.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
         L.rtr_context_destroy.argtypes = [vp]
         L.rtr_context_sync.argtypes = [vp]
         L.rtr_context_stream.argtypes = [vp]

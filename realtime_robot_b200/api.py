@@ -5,8 +5,10 @@ Names follow the reference: a cloud object owns the points and its per-cloud sta
 Ransac -> ransac_prerejective).  Everything here is plumbing: ctypes calls into librtr.so.  No compute happens in Python
 and there is no CPU fallback.
 """
+import atexit
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -26,6 +28,22 @@ def _ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
 
+_LIVE = weakref.WeakSet()       # contexts and clouds still holding device resources
+
+
+@atexit.register
+def _release_all():
+    """Free clouds, then contexts, while the CUDA runtime is still loaded (destructors that run during interpreter teardown
+    would call into a runtime that has already shut down)."""
+    live = list(_LIVE)
+    for o in live:
+        if isinstance(o, Cloud):
+            o.free()
+    for o in live:
+        if isinstance(o, Context):
+            o.close()
+
+
 class Context:
     """One per GPU: device id, one stream, stream-ordered memory pool (rtr_context_create)."""
 
@@ -33,6 +51,7 @@ class Context:
         self._h = C.c_void_p()
         _lib.check("rtr_context_create", _lib.lib().rtr_context_create(device, C.byref(self._h)))
         self.device = device
+        _LIVE.add(self)
 
     def sync(self):
         _lib.check("rtr_context_sync", _lib.lib().rtr_context_sync(self._h))
@@ -113,6 +132,7 @@ class Cloud:
             self.n = len(xyz1)
             _lib.check("rtr_cloud_upload", _lib.lib().rtr_cloud_upload(ctx._h, _ptr(xyz1), self.n, C.byref(self._h)))
             ctx.sync()   # the numpy buffer may be released as soon as we return
+        _LIVE.add(self)
 
     def free(self):
         if self._h:
@@ -133,6 +153,7 @@ class Cloud:
         self._h = C.c_void_p()
         _lib.check("rtr_pcd_load", _lib.lib().rtr_pcd_load(ctx._h, os.fsencode(path), C.byref(self._h)))
         self.n = int(_lib.lib().rtr_cloud_size(self._h))
+        _LIVE.add(self)
         return self
 
     def save_pcd(self, path: str, mode: int = PCD_ASCII):

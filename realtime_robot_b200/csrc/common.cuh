@@ -62,6 +62,9 @@ struct rtr_context {
     // small pinned staging area for results / counters
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
+    // this context's own stream-ordered memory pool: blocks freed on this stream are only ever reused on this stream, so the
+    // allocator never makes one context's stream wait for another's (the device's default pool is shared by all streams)
+    cudaMemPool_t pool = nullptr;
     // asynchronous registration (rtr_register_begin / _end): at most one in flight per context
     int register_pending = 0;
     struct rtr_cloud* pending_cloud[2] = {nullptr, nullptr};
@@ -117,7 +120,7 @@ template <typename T>
 static inline int dev_alloc(rtr_context* ctx, T** p, size_t count, const char* tag) {
     *p = nullptr;
     if (count == 0) count = 1;
-    RTR_CHECK(cudaMallocAsync((void**)p, count * sizeof(T), ctx->stream), tag);
+    RTR_CHECK(cudaMallocFromPoolAsync((void**)p, count * sizeof(T), ctx->pool, ctx->stream), tag);
     return 0;
 }
 static inline bool in_arena(const rtr_context* ctx, const void* p) {
@@ -137,7 +140,7 @@ static inline int tmp_alloc(rtr_context* ctx, T** p, size_t count, const char* t
         size_t cap = ctx->slabs.empty() ? ((size_t)32 << 20) : ctx->slabs.back().cap * 2;
         if (cap < bytes * 2) cap = bytes * 2;
         char* base = nullptr;
-        RTR_CHECK(cudaMallocAsync((void**)&base, cap, ctx->stream), tag);
+        RTR_CHECK(cudaMallocFromPoolAsync((void**)&base, cap, ctx->pool, ctx->stream), tag);
         ctx->slabs.push_back({base, cap});      // older slabs stay alive until the outermost scope closes
         ctx->arena_top = 0;
     }

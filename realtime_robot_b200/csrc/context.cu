@@ -406,21 +406,32 @@ void rtr_default_register_params(rtr_register_params* p) {
     p->icp.max_iterations = 10; p->icp.mse_threshold_absolute = 1e-12;
 }
 
-int rtr_context_create(int device, rtr_context** out) {
+int rtr_context_create(int device, rtr_context** out) { return rtr_context_create_prio(device, 0, out); }
+
+int rtr_context_create_prio(int device, int urgency, rtr_context** out) {
     if (!out) return rtr_fail("context", "null output pointer", RTR_ERR_INVALID);
     *out = nullptr;
     RTR_CHECK(cudaSetDevice(device), "context");
     rtr_context* ctx = new rtr_context();
     ctx->device = device;
-    RTR_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "context");
+    // urgency 0 = default; larger = the device scheduler serves this context's stream first when several contexts compete
+    // (longest job first: give the context that registers the largest cloud the highest urgency)
+    int least = 0, greatest = 0;
+    RTR_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest), "context");      // numerically lower = more urgent
+    int prio = std::max(greatest, std::min(least, least - std::max(urgency, 0)));
+    RTR_CHECK(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio), "context");
     cudaDeviceProp prop;
     RTR_CHECK(cudaGetDeviceProperties(&prop, device), "context");
     ctx->sm_count = prop.multiProcessorCount;
-    // keep freed blocks in the stream-ordered pool: no cudaMalloc/cudaFree on the hot path (cf. kernel.cu:50-56,101-102)
-    cudaMemPool_t pool;
-    RTR_CHECK(cudaDeviceGetDefaultMemPool(&pool, device), "context");
+    // keep freed blocks in the context's stream-ordered pool: no cudaMalloc/cudaFree on the hot path (cf. kernel.cu:50-56,101-102)
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    RTR_CHECK(cudaMemPoolCreate(&ctx->pool, &props), "context");
     unsigned long long thresh = ~0ULL;
-    RTR_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh), "context");
+    RTR_CHECK(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thresh), "context");
     for (int i = 0; i < RTR_NUM_EVENTS; ++i) RTR_CHECK(cudaEventCreate(&ctx->events[i]), "context");
     ctx->pinned_bytes = 1 << 16;
     RTR_CHECK(cudaMallocHost(&ctx->pinned, ctx->pinned_bytes), "context");
@@ -439,6 +450,7 @@ int rtr_context_destroy(rtr_context* ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->io_pinned) cudaFreeHost(ctx->io_pinned);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     delete ctx;
     return 0;
 }
