@@ -368,6 +368,10 @@ def main():
                 "share_of_step": round(prof[dom][1] / step_ms, 4),
                 "note": "configs[0..1] are launch-latency / L2 bound (working set < 1 MB, SURVEY 8d): the HBM fraction is reported, "
                         "not the criterion; the bandwidth-bound kernel is icp_1m.roofline"}
+    tkey = "icp.corr@step(chair4 launch)" if dom == "icp.corr" else dom + "@chair4"
+    if tkey in ncu_traffic:
+        roofline["traffic"] = ncu_traffic[tkey]
+        roofline["traffic_note"] = "dram bytes of the step's largest launch of this kernel (chair4), ncu --set full, profiles/r01_ncu_full_summary.md"
     if alg is not None and prof[dom][1] > 0:
         roofline["achieved"] = alg / (prof[dom][1] * 1e-3) / 1e9
         roofline["frac"] = roofline["achieved"] / hbm_peak
