@@ -457,12 +457,11 @@ def main():
     pcd_out = None
     if rank == 0 and not args.no_icp:
         try:
-            import tempfile
             big = synth.icp_config(1000, 1_000_000)[1]
             pcd_out = {"points": len(big)}
-            with tempfile.TemporaryDirectory() as td:
+            with tempfile.TemporaryDirectory() as tmpdir:
                 for mode, nm in ((api.PCD_ASCII, "ascii"), (api.PCD_BINARY, "binary"), (api.PCD_BINARY_COMPRESSED, "binary_compressed")):
-                    f = os.path.join(td, nm + ".pcd")
+                    f = os.path.join(tmpdir, nm + ".pcd")
                     t0 = time.perf_counter(); api.write_pcd(f, big, mode); tw = time.perf_counter() - t0
                     api.Cloud.from_pcd(ctx, f).free()
                     t0 = time.perf_counter(); cl = api.Cloud.from_pcd(ctx, f); ctx.sync(); tr = time.perf_counter() - t0
