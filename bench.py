@@ -69,7 +69,8 @@ def run_reference(args, rank, world):
         return
     from oracle import orc
     orc.build()
-    cores = orc.set_threads(0)
+    # every host core this process may use (torchrun exports OMP_NUM_THREADS=1, which omp_get_max_threads() would obey)
+    cores = orc.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     p = default_register_params()
     scene = load_cloud(SCENE)
     models = [(m, load_cloud(m)) for m in MODELS]
