@@ -27,9 +27,10 @@
 #define TC_KF 104                      // floats per operand row: 3 x 33 + 5 pad  (13 k-steps of 8 tf32)
 #define TC_NC 26                       // 16-byte chunks per operand row
 #define TC_TILE_BYTES (TC_TILE * TC_KF * 4)    // 53248
-#define TC_STAGES 3
+#define TC_STAGES 2
+#define TC_EPI_GROUPS 4                  // epilogue warp groups: group g handles the g-th 32-column chunk of every accumulator
 #define TC_KEEP_MAX 32                 // candidates kept per (source row, split): 16, or 32 when there is a single split
-#define TC_THREADS 192
+#define TC_THREADS (64 + TC_EPI_GROUPS * 128)      // loader warp + MMA warp + 4 x 4 epilogue warps
 #define TC_MAX_SPLITS 8
 
 // defined in features.cu
@@ -61,6 +62,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// half a tile from global into the SAME shared-memory offset of every CTA in ctaMask; each destination CTA's mbarrier (same
+// offset) receives the complete_tx for the bytes that landed in it
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -156,7 +173,7 @@ struct TcSmem {
     alignas(128) unsigned char a[TC_TILE_BYTES];
     alignas(128) unsigned char b[TC_STAGES][TC_TILE_BYTES];
     alignas(16) float nb[TC_STAGES][TC_TILE];
-    alignas(16) float dbuf[32][TC_TILE];         // epilogue scratch: one 32-column chunk of distances, [column][row]
+    alignas(16) float dbuf[TC_EPI_GROUPS][32][TC_TILE];   // epilogue scratch per group: a 32-column chunk of distances, [column][row]
     alignas(8) unsigned long long bar_a;
     unsigned long long bar_full[TC_STAGES];      // target tile landed in smem
     unsigned long long bar_acc[TC_STAGES];       // accumulator complete in TMEM
@@ -164,9 +181,13 @@ struct TcSmem {
     unsigned int tmem_base;
 };
 
-template <int TC_KEEP>
+// CL = 2: two CTAs (two source tiles) form a cluster and share the stream of target tiles — each loads HALF of every tile
+// and multicasts it into both CTAs' shared memory, which halves the L2 -> SM traffic the kernel is bound by.  A stage
+// may be overwritten only when the epilogues of BOTH CTAs are done with it, so every epilogue warp arrives on the
+// stage's free barrier in both CTAs.
+template <int TC_KEEP, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_tc_match(const float* __restrict__ a_tiles, const float* __restrict__ b_tiles, const float* __restrict__ b_norms, int ns,
+k_tc_match(const float* __restrict__ a_tiles, const float* __restrict__ b_tiles, const float* __restrict__ b_norms, int ns, int n_src_tiles,
            int n_tgt_tiles, int tiles_per_split, int n_splits, int* __restrict__ cand_idx, float* __restrict__ cand_val,
            float* __restrict__ cand_thr) {
     // (no manual realignment: the pointer must stay visibly derived from the __shared__ array, otherwise every access
@@ -174,7 +195,9 @@ k_tc_match(const float* __restrict__ a_tiles, const float* __restrict__ b_tiles,
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int src_tile = blockIdx.x, split = blockIdx.y;
+    const bool active = (int)blockIdx.x < n_src_tiles;            // CL = 2 with an odd tile count: the last CTA only helps loading
+    const int src_tile = active ? (int)blockIdx.x : n_src_tiles - 1, split = blockIdx.y;
+    const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
     const int t0 = split * tiles_per_split;
     const int nt = max(0, min(tiles_per_split, n_tgt_tiles - t0));
 
@@ -183,16 +206,17 @@ k_tc_match(const float* __restrict__ a_tiles, const float* __restrict__ b_tiles,
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(smem_u32(&sm.bar_full[s]), 1);
             mbar_init(smem_u32(&sm.bar_acc[s]), 1);
-            mbar_init(smem_u32(&sm.bar_free[s]), 4);
+            mbar_init(smem_u32(&sm.bar_free[s]), 4 * TC_EPI_GROUPS * CL);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {   // TMEM: 3 accumulators x 128 fp32 columns -> 512-column allocation (power of two)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512u) : "memory");
+    if (warp == 1) {   // TMEM: TC_STAGES accumulators x 128 fp32 columns (a power of two >= 32 columns)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"((uint32_t)(TC_STAGES * TC_TILE)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_barrier();          // the peer's barriers exist before anything is multicast to / arrives on them
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
 
@@ -207,7 +231,13 @@ k_tc_match(const float* __restrict__ a_tiles, const float* __restrict__ b_tiles,
                 mbar_wait(smem_u32(&sm.bar_free[s]), ph ^ 1u);
                 uint32_t full = smem_u32(&sm.bar_full[s]);
                 mbar_expect_tx(full, TC_TILE_BYTES + TC_TILE * 4);
-                bulk_g2s(smem_u32(sm.b[s]), (const char*)b_tiles + (size_t)(t0 + t) * TC_TILE_BYTES, TC_TILE_BYTES, full);
+                if (CL > 1) {
+                    const uint32_t half = TC_TILE_BYTES / CL, off = crank * half;
+                    bulk_g2s_multicast(smem_u32(sm.b[s]) + off, (const char*)b_tiles + (size_t)(t0 + t) * TC_TILE_BYTES + off, half, full,
+                                       (uint16_t)((1u << CL) - 1u));
+                } else {
+                    bulk_g2s(smem_u32(sm.b[s]), (const char*)b_tiles + (size_t)(t0 + t) * TC_TILE_BYTES, TC_TILE_BYTES, full);
+                }
                 bulk_g2s(smem_u32(sm.nb[s]), b_norms + (size_t)(t0 + t) * TC_TILE, TC_TILE * 4, full);
             }
         }
@@ -234,8 +264,11 @@ k_tc_match(const float* __restrict__ a_tiles, const float* __restrict__ b_tiles,
         // Each thread keeps the TC_KEEP smallest values of its row (unsorted, thr = current maximum).  A chunk of 32
         // columns is turned into distances branch-free (pass mask against thr); only then does each lane walk ITS OWN
         // set bits — so a warp pays for the longest per-lane list, not for every column in which some lane inserts.
-        const int q = warp & 3;
+        // sixteen epilogue warps: TMEM lane quarter q = warp % 4 (a warp may only touch its own quarter), group g = the
+        // 32-column chunk of every 128-column accumulator this warp scans; each (row, group) keeps its own candidate list
+        const int q = warp & 3, g = (warp - 2) >> 2;
         const int row = q * 32 + lane;
+        float (*dbuf)[TC_TILE] = sm.dbuf[g];
         float val[TC_KEEP];
         int idx[TC_KEEP];
         float thr = FLT_MAX;
@@ -248,7 +281,7 @@ k_tc_match(const float* __restrict__ a_tiles, const float* __restrict__ b_tiles,
             tc_fence_after();
             const int col0 = (t0 + t) * TC_TILE;
 #pragma unroll 1
-            for (int cc = 0; cc < TC_TILE / 32; ++cc) {
+            for (int cc = g; cc < TC_TILE / 32; cc += TC_EPI_GROUPS) {
                 uint32_t r[32];
                 tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * TC_TILE + cc * 32), r);
                 tc_ld_wait();
@@ -261,14 +294,14 @@ k_tc_match(const float* __restrict__ a_tiles, const float* __restrict__ b_tiles,
                     for (int jj = 0; jj < 4; ++jj) {
                         const int j = j4 * 4 + jj;
                         float d = fmaf(-2.0f, __uint_as_float(r[j]), nbv[jj]);
-                        sm.dbuf[j][row] = d;
+                        dbuf[j][row] = d;
                         mask |= (d < thr ? 1u : 0u) << j;
                     }
                 }
                 while (mask) {
                     int j = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    float d = sm.dbuf[j][row];
+                    float d = dbuf[j][row];
                     if (d < thr) {                 // thr may have tightened since the mask was formed
                         bool done = false;
                         float nt_ = -FLT_MAX;
@@ -286,19 +319,26 @@ k_tc_match(const float* __restrict__ a_tiles, const float* __restrict__ b_tiles,
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&sm.bar_free[s]));
+            if (lane == 0) {
+                if (CL > 1) {
+#pragma unroll
+                    for (uint32_t c = 0; c < (uint32_t)CL; ++c) mbar_arrive_cluster(map_to_cta(smem_u32(&sm.bar_free[s]), c));
+                } else mbar_arrive(smem_u32(&sm.bar_free[s]));
+            }
         }
         int grow = src_tile * TC_TILE + row;
-        if (grow < ns) {
-            size_t o = ((size_t)grow * n_splits + split) * TC_KEEP;
+        if (active && grow < ns) {
+            const size_t list = (size_t)grow * (n_splits * TC_EPI_GROUPS) + (size_t)split * TC_EPI_GROUPS + g;
+            size_t o = list * TC_KEEP;
 #pragma unroll
             for (int u = 0; u < TC_KEEP; ++u) { cand_idx[o + u] = idx[u]; cand_val[o + u] = val[u]; }
-            cand_thr[(size_t)grow * n_splits + split] = thr;     // FLT_MAX while the list is not full: nothing was rejected
+            cand_thr[list] = thr;     // FLT_MAX while the list is not full: nothing was rejected
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    if (CL > 1) cluster_barrier();          // no CTA leaves while its peer may still multicast into it or arrive on its barriers
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(TC_STAGES * TC_TILE)) : "memory");
 }
 
 // ----------------------------------------------------------------------------- 3. exact re-rank + certificate
@@ -416,10 +456,10 @@ int rtr_match_tc_dev(rtr_context* ctx, const float* fa, int ns, const float* fb,
     if (int e = tmp_alloc(ctx, &a_norms, (size_t)src_tiles * TC_TILE, "match.tc")) return e;
     if (int e = tmp_alloc(ctx, &b_norms, (size_t)tgt_tiles * TC_TILE, "match.tc")) return e;
     // more kept candidates make the certificate succeed more often; with one split there is only one list per row
-    const int keep = (splits == 1) ? 32 : 16;
-    if (int e = tmp_alloc(ctx, &cand_idx, (size_t)ns * splits * keep, "match.tc")) return e;
-    if (int e = tmp_alloc(ctx, &cand_val, (size_t)ns * splits * keep, "match.tc")) return e;
-    if (int e = tmp_alloc(ctx, &cand_thr, (size_t)ns * splits, "match.tc")) return e;
+    const int keep = 16, lists = splits * TC_EPI_GROUPS;       // one candidate list per (row, split, 32-column chunk class)
+    if (int e = tmp_alloc(ctx, &cand_idx, (size_t)ns * lists * keep, "match.tc")) return e;
+    if (int e = tmp_alloc(ctx, &cand_val, (size_t)ns * lists * keep, "match.tc")) return e;
+    if (int e = tmp_alloc(ctx, &cand_thr, (size_t)ns * lists, "match.tc")) return e;
     if (int e = tmp_alloc(ctx, &redo_rows, (size_t)ns, "match.tc")) return e;
     if (int e = tmp_alloc(ctx, &redo_count, 1, "match.tc")) return e;
     if (int e = tmp_alloc(ctx, &d_nbmax, 2, "match.tc")) return e;      // [0] max centred |b|^2, [1] observed error ratio
@@ -435,16 +475,33 @@ int rtr_match_tc_dev(rtr_context* ctx, const float* fa, int ns, const float* fb,
     static bool attr_set = false;
     size_t smem = sizeof(TcSmem);
     if (!attr_set) {
-        RTR_CHECK(cudaFuncSetAttribute(k_tc_match<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "match.tc");
-        RTR_CHECK(cudaFuncSetAttribute(k_tc_match<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "match.tc");
+        RTR_CHECK(cudaFuncSetAttribute(k_tc_match<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "match.tc");
+        RTR_CHECK(cudaFuncSetAttribute(k_tc_match<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "match.tc");
         attr_set = true;
     }
-    if (keep == 32)
-        k_tc_match<32><<<dim3(src_tiles, splits), TC_THREADS, smem, ctx->stream>>>(a_tiles, b_tiles, b_norms, ns, tgt_tiles, tiles_per_split, splits, cand_idx, cand_val, cand_thr);
-    else
-        k_tc_match<16><<<dim3(src_tiles, splits), TC_THREADS, smem, ctx->stream>>>(a_tiles, b_tiles, b_norms, ns, tgt_tiles, tiles_per_split, splits, cand_idx, cand_val, cand_thr);
+    // pairs of source tiles share the target-tile stream through cluster multicast once there are enough CTAs to fill the
+    // GPU anyway (RTR_MATCH_CLUSTER=0/1 forces the choice); small problems stay on independent CTAs (no gang scheduling)
+    bool use_cluster = (long long)src_tiles * splits >= 2LL * ctx->sm_count;
+    if (const char* e = getenv("RTR_MATCH_CLUSTER")) use_cluster = (e[0] == '1') && src_tiles >= 2;
+    {
+        const int cl = use_cluster ? 2 : 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((src_tiles + cl - 1) / cl * cl), (unsigned)splits, 1);
+        cfg.blockDim = dim3(TC_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const float *ca = a_tiles, *cb = b_tiles, *cn = b_norms;
+        cudaError_t le;
+        le = use_cluster ? cudaLaunchKernelEx(&cfg, k_tc_match<16, 2>, ca, cb, cn, ns, src_tiles, tgt_tiles, tiles_per_split, splits, cand_idx, cand_val, cand_thr)
+                         : cudaLaunchKernelEx(&cfg, k_tc_match<16, 1>, ca, cb, cn, ns, src_tiles, tgt_tiles, tiles_per_split, splits, cand_idx, cand_val, cand_thr);
+        RTR_CHECK(le, "match.tc_mma");
+    }
     RTR_LAUNCH_CHECK(ctx, "match.tc_mma");
-    k_tc_rerank<<<nblk(ns, RR_WARPS), RR_WARPS * 32, 0, ctx->stream>>>(fa, ns, fb, nt, k, cand_idx, cand_val, cand_thr, splits, keep, a_norms, b_norms, d_nbmax, out_idx, out_dist, redo_rows, redo_count, d_nbmax + 1);
+    k_tc_rerank<<<nblk(ns, RR_WARPS), RR_WARPS * 32, 0, ctx->stream>>>(fa, ns, fb, nt, k, cand_idx, cand_val, cand_thr, lists, keep, a_norms, b_norms, d_nbmax, out_idx, out_dist, redo_rows, redo_count, d_nbmax + 1);
     RTR_LAUNCH_CHECK(ctx, "match.tc_rerank");
     if (int e = rtr_match_exact_launch(ctx, fa, ns, fb, nt, k, out_idx, out_dist, redo_rows, redo_count, ns)) return e;
     if (stats) {

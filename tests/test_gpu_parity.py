@@ -456,6 +456,13 @@ def test_match_tensor_core_equals_exact_kernel_at_scale(api, gpu_ctx, clouds, mo
     _, ex = api.match_raw(gpu_ctx, fa, fb, 5)
     assert tc["redo_rows"] >= 0 and ex["redo_rows"] == -1
     assert np.array_equal(tc["idx"], ex["idx"]) and np.array_equal(tc["dist"], ex["dist"])
+    # independent CTAs vs pairs of CTAs sharing the target-tile stream by cluster multicast; odd tile count (127 full + 1)
+    monkeypatch.setenv("RTR_MATCH_TC", "1")
+    for cl in ("0", "1"):
+        monkeypatch.setenv("RTR_MATCH_CLUSTER", cl)
+        _, t2 = api.match_raw(gpu_ctx, fa[:16300], fb, 5)
+        assert np.array_equal(t2["idx"], ex["idx"][:16300]) and np.array_equal(t2["dist"], ex["dist"][:16300]), cl
+    monkeypatch.delenv("RTR_MATCH_CLUSTER")
     assert tc["redo_rows"] < 0.2 * len(fa)
     assert 0 < tc["observed_err_over_norms"] < 6e-6          # the error model's constant (match_tc.cu) has head-room
 
