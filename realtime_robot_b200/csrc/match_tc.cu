@@ -27,7 +27,9 @@
 #define TC_KF 104                      // floats per operand row: 3 x 33 + 5 pad  (13 k-steps of 8 tf32)
 #define TC_NC 26                       // 16-byte chunks per operand row
 #define TC_TILE_BYTES (TC_TILE * TC_KF * 4)    // 53248
-#define TC_STAGES 2
+#define TC_STAGES 2                    // shared-memory ring of target tiles: a stage is free again when its MMAs have completed
+#define TC_ACC 4                       // TMEM ring of 128-column accumulators: free again when the epilogue has scanned it
+#define TC_PEND 16
 #define TC_EPI_GROUPS 4                  // epilogue warp groups: group g handles the g-th 32-column chunk of every accumulator
 #define TC_KEEP_MAX 32                 // candidates kept per (source row, split): 16, or 32 when there is a single split
 #define TC_THREADS (64 + TC_EPI_GROUPS * 128)      // loader warp + MMA warp + 4 x 4 epilogue warps
@@ -59,6 +61,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
     __trap();
 }
+#ifdef RTR_TC_TRACE
+#define TC_TWAIT(acc, bar, ph) do { long long t_ = clock64(); mbar_wait(bar, ph); acc += clock64() - t_; } while (0)
+#else
+#define TC_TWAIT(acc, bar, ph) mbar_wait(bar, ph)
+#endif
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -83,6 +90,9 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask) : "memory");
 }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
@@ -152,6 +162,11 @@ __global__ void k_tc_prep(const float* __restrict__ feat, int n, int n_pad, int 
 #pragma unroll
         for (int c = 0; c < 33; ++c) { v[c] = __ldg(feat + (size_t)r * 33 + c) - __ldg(mu + c); nrm += (double)v[c] * (double)v[c]; if (!isfinite(v[c])) valid = false; }
     }
+    const float nrm_f = valid ? (float)nrm : FLT_MAX;        // FLT_MAX: a padded / non-finite row can never be selected
+    // columns 99..101: the target's -|b|^2 / 2 as three tf32 pieces (11 + 11 + 2 mantissa bits: exact) against ones on the
+    // source side, so the accumulator is S' = a.b - |b|^2 / 2 and the epilogue needs no norm lookup: d = -2 S'
+    const float hx = -0.5f * nrm_f;
+    const float h1 = tf32_trunc(hx), h2 = tf32_trunc(hx - h1), h3 = (hx - h1) - h2;
 #pragma unroll
     for (int e = 0; e < TC_KF; ++e) {
         float x = 0.f;
@@ -162,9 +177,10 @@ __global__ void k_tc_prep(const float* __restrict__ feat, int n, int n_pad, int 
             bool want_lo = (role == 0) ? (part == 2) : (part == 1);
             x = want_lo ? lo : hi;
         }
+        if (e >= 99 && e < 102) x = (role == 0) ? 1.0f : (e == 99 ? h1 : (e == 100 ? h2 : h3));
         *(float*)(base + (size_t)(e / 4) * 128 + (e % 4) * 4) = x;
     }
-    norms[r] = valid ? (float)nrm : FLT_MAX;         // FLT_MAX: a padded / non-finite row can never be selected
+    norms[r] = nrm_f;
     if (valid && norm_max) atomicMax((int*)norm_max, __float_as_int((float)nrm * 1.000001f));   // non-negative floats order like ints
 }
 
@@ -172,12 +188,15 @@ __global__ void k_tc_prep(const float* __restrict__ feat, int n, int n_pad, int 
 struct TcSmem {
     alignas(128) unsigned char a[TC_TILE_BYTES];
     alignas(128) unsigned char b[TC_STAGES][TC_TILE_BYTES];
-    alignas(16) float nb[TC_STAGES][TC_TILE];
-    alignas(16) float dbuf[TC_EPI_GROUPS][32][TC_TILE];   // epilogue scratch per group: a 32-column chunk of distances, [column][row]
+    // per epilogue thread: up to TC_PEND candidates (accumulator value, column) that passed the row's threshold and wait for
+    // insertion into the register-resident list; [entry][thread] so that a warp's accesses to one entry are conflict free
+    alignas(16) float pend_v[TC_PEND][TC_EPI_GROUPS * TC_TILE];
+    alignas(16) int pend_i[TC_PEND][TC_EPI_GROUPS * TC_TILE];
     alignas(8) unsigned long long bar_a;
     unsigned long long bar_full[TC_STAGES];      // target tile landed in smem
-    unsigned long long bar_acc[TC_STAGES];       // accumulator complete in TMEM
-    unsigned long long bar_free[TC_STAGES];      // epilogue done with stage (smem norms + TMEM accumulator reusable)
+    unsigned long long bar_sfree[TC_STAGES];     // the MMAs reading this smem stage have completed (in every CTA of the cluster)
+    unsigned long long bar_acc[TC_ACC];          // accumulator complete in TMEM
+    unsigned long long bar_afree[TC_ACC];        // every epilogue warp is done with this accumulator
     unsigned int tmem_base;
 };
 
@@ -205,13 +224,16 @@ k_tc_match(const float* __restrict__ a_tiles, const float* __restrict__ b_tiles,
         mbar_init(smem_u32(&sm.bar_a), 1);
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(smem_u32(&sm.bar_full[s]), 1);
-            mbar_init(smem_u32(&sm.bar_acc[s]), 1);
-            mbar_init(smem_u32(&sm.bar_free[s]), 4 * TC_EPI_GROUPS * CL);
+            mbar_init(smem_u32(&sm.bar_sfree[s]), CL);
+        }
+        for (int a = 0; a < TC_ACC; ++a) {
+            mbar_init(smem_u32(&sm.bar_acc[a]), 1);
+            mbar_init(smem_u32(&sm.bar_afree[a]), 4 * TC_EPI_GROUPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {   // TMEM: TC_STAGES accumulators x 128 fp32 columns (a power of two >= 32 columns)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"((uint32_t)(TC_STAGES * TC_TILE)) : "memory");
+    if (warp == 1) {   // TMEM: TC_ACC accumulators x 128 fp32 columns = all 512 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"((uint32_t)(TC_ACC * TC_TILE)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -219,6 +241,8 @@ k_tc_match(const float* __restrict__ a_tiles, const float* __restrict__ b_tiles,
     if (CL > 1) cluster_barrier();          // the peer's barriers exist before anything is multicast to / arrives on them
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
+    long long w_free = 0, w_full = 0, w_acc = 0, t_begin = clock64();
+    (void)w_free; (void)w_full; (void)w_acc; (void)t_begin;
 
     if (warp == 0) {
         // ---------------- loader: source tile once, then the ring of target tiles
@@ -228,9 +252,9 @@ k_tc_match(const float* __restrict__ a_tiles, const float* __restrict__ b_tiles,
             for (int t = 0; t < nt; ++t) {
                 int s = t % TC_STAGES;
                 uint32_t ph = (uint32_t)(t / TC_STAGES) & 1u;
-                mbar_wait(smem_u32(&sm.bar_free[s]), ph ^ 1u);
+                TC_TWAIT(w_free, smem_u32(&sm.bar_sfree[s]), ph ^ 1u);
                 uint32_t full = smem_u32(&sm.bar_full[s]);
-                mbar_expect_tx(full, TC_TILE_BYTES + TC_TILE * 4);
+                mbar_expect_tx(full, TC_TILE_BYTES);
                 if (CL > 1) {
                     const uint32_t half = TC_TILE_BYTES / CL, off = crank * half;
                     bulk_g2s_multicast(smem_u32(sm.b[s]) + off, (const char*)b_tiles + (size_t)(t0 + t) * TC_TILE_BYTES + off, half, full,
@@ -238,7 +262,6 @@ k_tc_match(const float* __restrict__ a_tiles, const float* __restrict__ b_tiles,
                 } else {
                     bulk_g2s(smem_u32(sm.b[s]), (const char*)b_tiles + (size_t)(t0 + t) * TC_TILE_BYTES, TC_TILE_BYTES, full);
                 }
-                bulk_g2s(smem_u32(sm.nb[s]), b_norms + (size_t)(t0 + t) * TC_TILE, TC_TILE * 4, full);
             }
         }
     } else if (warp == 1) {
@@ -246,70 +269,54 @@ k_tc_match(const float* __restrict__ a_tiles, const float* __restrict__ b_tiles,
         mbar_wait(smem_u32(&sm.bar_a), 0);
         const uint64_t adesc = umma_desc(smem_u32(sm.a));
         for (int t = 0; t < nt; ++t) {
-            int s = t % TC_STAGES;
-            uint32_t ph = (uint32_t)(t / TC_STAGES) & 1u;
-            mbar_wait(smem_u32(&sm.bar_full[s]), ph);
+            int s = t % TC_STAGES, a = t % TC_ACC;
+            uint32_t ph = (uint32_t)(t / TC_STAGES) & 1u, pa = (uint32_t)(t / TC_ACC) & 1u;
+            TC_TWAIT(w_full, smem_u32(&sm.bar_full[s]), ph);
+            TC_TWAIT(w_acc, smem_u32(&sm.bar_afree[a]), pa ^ 1u);
             tc_fence_after();
             if (lane == 0) {
                 const uint64_t bdesc = umma_desc(smem_u32(sm.b[s]));
 #pragma unroll
                 for (int k = 0; k < TC_KF / 8; ++k)      // 8 tf32 = 32 B = two 16-byte chunks = 256 B of core matrices per k-step
-                    tc_mma_tf32(tmem + (uint32_t)(s * TC_TILE), adesc + (uint64_t)(k * 16), bdesc + (uint64_t)(k * 16), TC_IDESC, k > 0 ? 1u : 0u);
-                tc_commit(smem_u32(&sm.bar_acc[s]));      // arrives when the MMAs above have completed
+                    tc_mma_tf32(tmem + (uint32_t)(a * TC_TILE), adesc + (uint64_t)(k * 16), bdesc + (uint64_t)(k * 16), TC_IDESC, k > 0 ? 1u : 0u);
+                tc_commit(smem_u32(&sm.bar_acc[a]));      // arrives when the MMAs above have completed: accumulator ready ...
+                if (CL > 1) tc_commit_multicast(smem_u32(&sm.bar_sfree[s]), (uint16_t)((1u << CL) - 1u));     // ... and the smem stage
+                else tc_commit(smem_u32(&sm.bar_sfree[s]));                                                     // may be refilled
             }
             __syncwarp();
         }
     } else {
-        // ---------------- epilogue: thread = source row; TMEM lane quarter = warp % 4
-        // Each thread keeps the TC_KEEP smallest values of its row (unsorted, thr = current maximum).  A chunk of 32
-        // columns is turned into distances branch-free (pass mask against thr); only then does each lane walk ITS OWN
-        // set bits — so a warp pays for the longest per-lane list, not for every column in which some lane inserts.
-        // sixteen epilogue warps: TMEM lane quarter q = warp % 4 (a warp may only touch its own quarter), group g = the
-        // 32-column chunk of every 128-column accumulator this warp scans; each (row, group) keeps its own candidate list
+        // ---------------- epilogue: thread = source row.  Sixteen warps: TMEM lane quarter q = warp % 4 (a warp may only
+        // touch its own quarter), group g = which 32-column chunk of every 128-column accumulator this warp scans; each
+        // (row, group) keeps its own list of the TC_KEEP smallest distances (unsorted, in registers, thr = current maximum).
+        // The accumulator already holds S' = a.b - |b|^2 / 2 (the norm rides in three spare K columns), so d = -2 S' and
+        // "d < thr" is "S' > -thr / 2": one compare per element, and a passing element is only APPENDED (two predicated
+        // stores) to the thread's pending buffer.  Insertions — 4 instructions per list slot, executed by the whole warp
+        // whenever any lane inserts — happen in batches when some lane's buffer runs out of room, with the threshold
+        // tightening as they go, instead of once per chunk.
         const int q = warp & 3, g = (warp - 2) >> 2;
         const int row = q * 32 + lane;
-        float (*dbuf)[TC_TILE] = sm.dbuf[g];
+        const int et = g * TC_TILE + row;                     // epilogue thread id 0..511
         float val[TC_KEEP];
         int idx[TC_KEEP];
-        float thr = FLT_MAX;
+        float thr = FLT_MAX, thr_s = -0.5f * FLT_MAX;
+        int cnt = 0;
 #pragma unroll
         for (int u = 0; u < TC_KEEP; ++u) { val[u] = FLT_MAX; idx[u] = -1; }
-        for (int t = 0; t < nt; ++t) {
-            int s = t % TC_STAGES;
-            uint32_t ph = (uint32_t)(t / TC_STAGES) & 1u;
-            mbar_wait(smem_u32(&sm.bar_acc[s]), ph);
-            tc_fence_after();
-            const int col0 = (t0 + t) * TC_TILE;
-#pragma unroll 1
-            for (int cc = g; cc < TC_TILE / 32; cc += TC_EPI_GROUPS) {
-                uint32_t r[32];
-                tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * TC_TILE + cc * 32), r);
-                tc_ld_wait();
-                unsigned mask = 0;
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 nb4 = *reinterpret_cast<const float4*>(&sm.nb[s][cc * 32 + j4 * 4]);     // broadcast
-                    const float nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int j = j4 * 4 + jj;
-                        float d = fmaf(-2.0f, __uint_as_float(r[j]), nbv[jj]);
-                        dbuf[j][row] = d;
-                        mask |= (d < thr ? 1u : 0u) << j;
-                    }
-                }
-                while (mask) {
-                    int j = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    float d = dbuf[j][row];
-                    if (d < thr) {                 // thr may have tightened since the mask was formed
+        auto flush = [&]() {
+            const int mx = __reduce_max_sync(0xffffffffu, cnt);
+            for (int e = 0; e < mx; ++e) {
+                if (e < cnt) {
+                    float d = -2.0f * sm.pend_v[e][et];
+                    if (d < thr) {                 // thr may have tightened since the element was appended
+                        const int col = sm.pend_i[e][et];
                         bool done = false;
                         float nt_ = -FLT_MAX;
 #pragma unroll
                         for (int u = 0; u < TC_KEEP; ++u) {
                             bool hit = (val[u] == thr) && !done;
                             val[u] = hit ? d : val[u];
-                            idx[u] = hit ? (col0 + cc * 32 + j) : idx[u];
+                            idx[u] = hit ? col : idx[u];
                             done = done || hit;
                             nt_ = fmaxf(nt_, val[u]);
                         }
@@ -317,15 +324,44 @@ k_tc_match(const float* __restrict__ a_tiles, const float* __restrict__ b_tiles,
                     }
                 }
             }
+            thr_s = -0.5f * thr;
+            cnt = 0;
+        };
+        for (int t = 0; t < nt; ++t) {
+            int a = t % TC_ACC;
+            uint32_t pa = (uint32_t)(t / TC_ACC) & 1u;
+            TC_TWAIT(w_acc, smem_u32(&sm.bar_acc[a]), pa);
+            tc_fence_after();
+            const int col0 = (t0 + t) * TC_TILE;
+#pragma unroll 1
+            for (int cc = g; cc < TC_TILE / 32; cc += TC_EPI_GROUPS) {
+                uint32_t r[32];
+                tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_TILE + cc * 32), r);
+                tc_ld_wait();
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    if (__any_sync(0xffffffffu, cnt > TC_PEND - 8)) flush();      // room for the next 8 columns
+                    // most 8-column blocks hold nothing below the row's threshold: one 3-input-max tree and one branch
+                    const float* v = reinterpret_cast<const float*>(&r[j8 * 8]);
+                    const float m8 = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+                    if (m8 > thr_s) {
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            const float sp = v[jj];
+                            if (sp > thr_s) {
+                                sm.pend_v[cnt][et] = sp;
+                                sm.pend_i[cnt][et] = col0 + cc * 32 + j8 * 8 + jj;
+                                ++cnt;
+                            }
+                        }
+                    }
+                }
+            }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                if (CL > 1) {
-#pragma unroll
-                    for (uint32_t c = 0; c < (uint32_t)CL; ++c) mbar_arrive_cluster(map_to_cta(smem_u32(&sm.bar_free[s]), c));
-                } else mbar_arrive(smem_u32(&sm.bar_free[s]));
-            }
+            if (lane == 0) mbar_arrive(smem_u32(&sm.bar_afree[a]));
         }
+        flush();
         int grow = src_tile * TC_TILE + row;
         if (active && grow < ns) {
             const size_t list = (size_t)grow * (n_splits * TC_EPI_GROUPS) + (size_t)split * TC_EPI_GROUPS + g;
@@ -335,10 +371,14 @@ k_tc_match(const float* __restrict__ a_tiles, const float* __restrict__ b_tiles,
             cand_thr[list] = thr;     // FLT_MAX while the list is not full: nothing was rejected
         }
     }
+#ifdef RTR_TC_TRACE
+    if (blockIdx.x == 3 && blockIdx.y == 0 && lane == 0 && (warp < 3 || warp == 17))
+        printf("tc trace warp %d: total %lld cycles, %d tiles; waits: free %lld full %lld acc %lld\n", warp, clock64() - t_begin, nt, w_free, w_full, w_acc);
+#endif
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_barrier();          // no CTA leaves while its peer may still multicast into it or arrive on its barriers
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(TC_STAGES * TC_TILE)) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(TC_ACC * TC_TILE)) : "memory");
 }
 
 // ----------------------------------------------------------------------------- 3. exact re-rank + certificate
@@ -362,7 +402,7 @@ k_tc_rerank(const float* __restrict__ fa, int ns, const float* __restrict__ fb, 
     // Error model of the prefilter's distance for a pair with centred norms |a|, |b| (DESIGN.md "tensor-core matching"):
     // tf32 hi/lo split residue + dropped lo.lo term + fp32 accumulation over 13 MMA k-steps <= 3e-6 |a||b| on the dot
     // product (x2 in the distance), plus the fp32 roundings of |b|^2 and of the final fma.
-#define TC_ERR(na_, nb_) (6e-6 * sqrt((na_) * (nb_)) + 2e-7 * ((na_) + (nb_)) + 1e-9)
+#define TC_ERR(na_, nb_) (6e-6 * sqrt((na_) * (nb_)) + 5e-7 * ((na_) + (nb_)) + 1e-9)
     float bd[RR_KMAX]; int bi[RR_KMAX];
 #pragma unroll
     for (int t = 0; t < RR_KMAX; ++t) { bd[t] = FLT_MAX; bi[t] = 0x7fffffff; }
