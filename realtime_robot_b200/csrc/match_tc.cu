@@ -8,15 +8,23 @@
 //                    A = [hi | hi | lo | 0], B = [hi | lo | hi | 0] (K = 104), so one TF32 GEMM yields
 //                    hi.hi + hi.lo + lo.hi = a.b to ~2^-22 relative.  Rows are written in the UMMA canonical K-major
 //                    no-swizzle layout (8-row x 16-byte core matrices), 128-row tiles, ready for 1-D bulk copies.
-//   2. k_tc_match  : one CTA per (128 source rows, split of the target tiles).  Warp 0 streams 128-row target tiles into
-//                    a 3-stage shared-memory ring with cp.async.bulk + mbarrier; warp 1 issues tcgen05.mma (M=128,
-//                    N=128, kind::tf32, 13 k-steps) into a 3-stage TMEM accumulator ring; warps 2-5 read the
-//                    accumulators back with tcgen05.ld (thread = source row, 32 columns per load), form
-//                    |b_j|^2 - 2 S_ij and keep the 16 smallest per row in registers.
+//   2. k_tc_match  : one CTA (18 warps) per (128 source rows, split of the target tiles).  Warp 0 streams 128-row target
+//                    tiles into a 2-stage shared-memory ring with cp.async.bulk + mbarrier (optionally as a cluster of
+//                    two CTAs that each load half a tile and multicast it to both); warp 1 issues tcgen05.mma (M = N =
+//                    128, kind::tf32, 13 k-steps) into a 4-deep ring of TMEM accumulators and commits twice: "accumulator
+//                    ready" for the epilogue and "smem stage free" for the loader, so loads never wait for the epilogue;
+//                    warps 2-17 are the epilogue: TMEM lane quarter = warp % 4, and each of the four groups scans one
+//                    32-column chunk of every accumulator with tcgen05.ld.  The target norm rides in three spare K
+//                    columns, so the accumulator is a.b - |b|^2/2 and "closer than the row's threshold" is one compare;
+//                    passing elements are appended to a per-thread pending buffer and inserted into the register-resident
+//                    16-best list in batches.  Measured per 128x128 tile (clock64 trace, -DRTR_TC_TRACE): MMA ~1180
+//                    cycles (74 % of the tf32 peak while active), epilogue ~1210, period ~1775.
 //   3. k_tc_rerank : one warp per source row recomputes the kept candidates' distances exactly (the oracle's sequential
 //                    fp64 sum), takes the top k, and certifies the row: every rejected candidate had approximate distance
 //                    >= T (the 16th kept), hence exact distance >= T - E; if the exact k-th best is < T - E nothing
 //                    rejected can enter.  Uncertified rows (rare) are redone by the exact SIMT kernel.
+// Tried and dropped: the source tile as a TMEM operand (tcgen05.st, [a_tmem] in the MMA) — correct, but with room for only
+// three accumulators it was 5 % slower: the kernel is not bound by shared-memory operand traffic.
 #include "common.cuh"
 #include <algorithm>
 #include <cmath>
@@ -204,7 +212,7 @@ struct TcSmem {
 // and multicasts it into both CTAs' shared memory, which halves the L2 -> SM traffic the kernel is bound by.  A stage
 // may be overwritten only when the epilogues of BOTH CTAs are done with it, so every epilogue warp arrives on the
 // stage's free barrier in both CTAs.
-template <int TC_KEEP, int CL>
+template <int TC_KEEP, int CL, bool MERGE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_match(const float* __restrict__ a_tiles, const float* __restrict__ b_tiles, const float* __restrict__ b_norms, int ns, int n_src_tiles,
            int n_tgt_tiles, int tiles_per_split, int n_splits, int* __restrict__ cand_idx, float* __restrict__ cand_val,
@@ -363,7 +371,41 @@ k_tc_match(const float* __restrict__ a_tiles, const float* __restrict__ b_tiles,
         }
         flush();
         int grow = src_tile * TC_TILE + row;
-        if (active && grow < ns) {
+        if (MERGE) {
+            // several splits: one list per (row, split) is enough, so the four groups' lists are merged through the (now idle)
+            // pending buffers.  Every element a group rejected was >= that group's threshold >= the merged 16th smallest.
+            static_assert(TC_PEND >= TC_KEEP, "the pending buffer doubles as the merge scratch");
+#pragma unroll
+            for (int u = 0; u < TC_KEEP; ++u) { sm.pend_v[u][et] = val[u]; sm.pend_i[u][et] = idx[u]; }
+            asm volatile("bar.sync 1, %0;" ::"r"(TC_EPI_GROUPS * TC_TILE) : "memory");       // the 16 epilogue warps only
+            if (g == 0) {
+                for (int og = 1; og < TC_EPI_GROUPS; ++og)
+                    for (int e = 0; e < TC_KEEP; ++e) {
+                        float d = sm.pend_v[e][og * TC_TILE + row];
+                        if (d < thr) {
+                            const int col = sm.pend_i[e][og * TC_TILE + row];
+                            bool done = false;
+                            float nt_ = -FLT_MAX;
+#pragma unroll
+                            for (int u = 0; u < TC_KEEP; ++u) {
+                                bool hit = (val[u] == thr) && !done;
+                                val[u] = hit ? d : val[u];
+                                idx[u] = hit ? col : idx[u];
+                                done = done || hit;
+                                nt_ = fmaxf(nt_, val[u]);
+                            }
+                            thr = nt_;
+                        }
+                    }
+                if (active && grow < ns) {
+                    const size_t list = (size_t)grow * n_splits + split;
+                    size_t o = list * TC_KEEP;
+#pragma unroll
+                    for (int u = 0; u < TC_KEEP; ++u) { cand_idx[o + u] = idx[u]; cand_val[o + u] = val[u]; }
+                    cand_thr[list] = thr;
+                }
+            }
+        } else if (active && grow < ns) {
             const size_t list = (size_t)grow * (n_splits * TC_EPI_GROUPS) + (size_t)split * TC_EPI_GROUPS + g;
             size_t o = list * TC_KEEP;
 #pragma unroll
@@ -496,7 +538,10 @@ int rtr_match_tc_dev(rtr_context* ctx, const float* fa, int ns, const float* fb,
     if (int e = tmp_alloc(ctx, &a_norms, (size_t)src_tiles * TC_TILE, "match.tc")) return e;
     if (int e = tmp_alloc(ctx, &b_norms, (size_t)tgt_tiles * TC_TILE, "match.tc")) return e;
     // more kept candidates make the certificate succeed more often; with one split there is only one list per row
-    const int keep = 16, lists = splits * TC_EPI_GROUPS;       // one candidate list per (row, split, 32-column chunk class)
+    // one split: keep the four groups' lists (64 candidates per row make the certificate succeed more often); several splits:
+    // the groups' lists are merged in the kernel, one list of 16 per (row, split)
+    const bool merge = splits > 1;
+    const int keep = 16, lists = merge ? splits : TC_EPI_GROUPS;
     if (int e = tmp_alloc(ctx, &cand_idx, (size_t)ns * lists * keep, "match.tc")) return e;
     if (int e = tmp_alloc(ctx, &cand_val, (size_t)ns * lists * keep, "match.tc")) return e;
     if (int e = tmp_alloc(ctx, &cand_thr, (size_t)ns * lists, "match.tc")) return e;
@@ -515,13 +560,16 @@ int rtr_match_tc_dev(rtr_context* ctx, const float* fa, int ns, const float* fb,
     static bool attr_set = false;
     size_t smem = sizeof(TcSmem);
     if (!attr_set) {
-        RTR_CHECK(cudaFuncSetAttribute(k_tc_match<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "match.tc");
-        RTR_CHECK(cudaFuncSetAttribute(k_tc_match<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "match.tc");
+        RTR_CHECK(cudaFuncSetAttribute(k_tc_match<16, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "match.tc");
+        RTR_CHECK(cudaFuncSetAttribute(k_tc_match<16, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "match.tc");
+        RTR_CHECK(cudaFuncSetAttribute(k_tc_match<16, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "match.tc");
+        RTR_CHECK(cudaFuncSetAttribute(k_tc_match<16, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "match.tc");
         attr_set = true;
     }
-    // pairs of source tiles share the target-tile stream through cluster multicast once there are enough CTAs to fill the
-    // GPU anyway (RTR_MATCH_CLUSTER=0/1 forces the choice); small problems stay on independent CTAs (no gang scheduling)
-    bool use_cluster = (long long)src_tiles * splits >= 2LL * ctx->sm_count;
+    // RTR_MATCH_CLUSTER=1: pairs of source tiles share the target-tile stream through cluster multicast (half the L2 -> SM
+    // traffic).  Off by default: since loads stopped waiting for the epilogue the kernel is bound by MMA + epilogue, the two
+    // variants time the same (7.6 ms at 262144 x 65536), and independent CTAs need no gang scheduling.
+    bool use_cluster = false;
     if (const char* e = getenv("RTR_MATCH_CLUSTER")) use_cluster = (e[0] == '1') && src_tiles >= 2;
     {
         const int cl = use_cluster ? 2 : 1;
@@ -536,8 +584,9 @@ int rtr_match_tc_dev(rtr_context* ctx, const float* fa, int ns, const float* fb,
         cfg.attrs = at; cfg.numAttrs = 1;
         const float *ca = a_tiles, *cb = b_tiles, *cn = b_norms;
         cudaError_t le;
-        le = use_cluster ? cudaLaunchKernelEx(&cfg, k_tc_match<16, 2>, ca, cb, cn, ns, src_tiles, tgt_tiles, tiles_per_split, splits, cand_idx, cand_val, cand_thr)
-                         : cudaLaunchKernelEx(&cfg, k_tc_match<16, 1>, ca, cb, cn, ns, src_tiles, tgt_tiles, tiles_per_split, splits, cand_idx, cand_val, cand_thr);
+#define TC_LAUNCH(CL_, MG_) cudaLaunchKernelEx(&cfg, k_tc_match<16, CL_, MG_>, ca, cb, cn, ns, src_tiles, tgt_tiles, tiles_per_split, splits, cand_idx, cand_val, cand_thr)
+        le = use_cluster ? (merge ? TC_LAUNCH(2, true) : TC_LAUNCH(2, false)) : (merge ? TC_LAUNCH(1, true) : TC_LAUNCH(1, false));
+#undef TC_LAUNCH
         RTR_CHECK(le, "match.tc_mma");
     }
     RTR_LAUNCH_CHECK(ctx, "match.tc_mma");
