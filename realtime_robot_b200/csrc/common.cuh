@@ -261,38 +261,12 @@ __device__ __forceinline__ bool for_block27(const GridView& g, float qx, float q
     return true;
 }
 
-// Exact nearest neighbour; ties -> lowest original index.  prune2: candidates farther than this (squared) are of no
-// interest to the caller (ICP's max correspondence distance), FLT_MAX for none.
-//   phase 1: the 3x3x3 cell block around the (clamped) query cell — 9 contiguous ranges.  Every point outside that
-//            block is farther than one cell size along some axis, so best_d2 <= (0.999 h)^2 ends the search
-//            (the common case in ICP).
-//   phase 2: otherwise walk slabs (z) and rows (y) outward from the query cell, pruning each slab / row by its exact
-//            box distance to the query and clipping the x range of a row to the current search sphere.  Cost is
-//            proportional to the rows inside the sphere, also for queries far outside the grid.
-// `slack` covers float cell assignment (a point may sit a hair outside its cell's nominal box).
-__device__ __forceinline__ void grid_nearest_ex(const GridView& g, float qx, float qy, float qz, float prune2, int& best,
-                                                float& best_d2, float4& bp) {
-    best = -1; best_d2 = FLT_MAX; bp = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g.n == 0) return;
-    int cx = clampi(cell_coord(qx, g.mnx, g.inv_h), 0, g.dx - 1);
+// Phase 2 of the exact search (see grid_nearest_ex): slab / row walk outward from the query cell, starting from the
+// best candidate found so far (best < 0: none).
+__device__ __forceinline__ void grid_nearest_far(const GridView& g, float qx, float qy, float qz, float prune2, int& best,
+                                                 float& best_d2, float4& bp) {
     int cy = clampi(cell_coord(qy, g.mny, g.inv_h), 0, g.dy - 1);
     int cz = clampi(cell_coord(qz, g.mnz, g.inv_h), 0, g.dz - 1);
-    {
-        int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
-        for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
-            for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y) {
-                int s0 = __ldg(g.cell_begin + cell_key(g, x0, y, z));
-                int s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
-                for (int s = s0; s < s1; ++s) {
-                    float4 p = __ldg(g.sorted + s);
-                    float d = dist2f(qx, qy, qz, p.x, p.y, p.z);
-                    int id = __float_as_int(p.w);
-                    if (d < best_d2 || (d == best_d2 && id < best)) { best_d2 = d; best = id; bp = p; }
-                }
-            }
-    }
-    float hh = g.h * 0.999f;
-    if (best >= 0 && best_d2 <= hh * hh) return;
     float ext = g.h * (float)max(g.dx, max(g.dy, g.dz));
     float slack = g.h * 1e-3f + 2e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + fabsf(g.mnx) + fabsf(g.mny) + fabsf(g.mnz) + ext);
     for (int zdir = 0; zdir < 2; ++zdir) {
@@ -325,6 +299,41 @@ __device__ __forceinline__ void grid_nearest_ex(const GridView& g, float qx, flo
             }
         }
     }
+}
+
+// Exact nearest neighbour; ties -> lowest original index.  prune2: candidates farther than this (squared) are of no
+// interest to the caller (ICP's max correspondence distance), FLT_MAX for none.
+//   phase 1: the 3x3x3 cell block around the (clamped) query cell — 9 contiguous ranges.  Every point outside that
+//            block is farther than one cell size along some axis, so best_d2 <= (0.999 h)^2 ends the search
+//            (the common case in ICP).
+//   phase 2: otherwise walk slabs (z) and rows (y) outward from the query cell, pruning each slab / row by its exact
+//            box distance to the query and clipping the x range of a row to the current search sphere.  Cost is
+//            proportional to the rows inside the sphere, also for queries far outside the grid.
+// `slack` covers float cell assignment (a point may sit a hair outside its cell's nominal box).
+__device__ __forceinline__ void grid_nearest_ex(const GridView& g, float qx, float qy, float qz, float prune2, int& best,
+                                                float& best_d2, float4& bp) {
+    best = -1; best_d2 = FLT_MAX; bp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g.n == 0) return;
+    int cx = clampi(cell_coord(qx, g.mnx, g.inv_h), 0, g.dx - 1);
+    int cy = clampi(cell_coord(qy, g.mny, g.inv_h), 0, g.dy - 1);
+    int cz = clampi(cell_coord(qz, g.mnz, g.inv_h), 0, g.dz - 1);
+    {
+        int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
+        for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
+            for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y) {
+                int s0 = __ldg(g.cell_begin + cell_key(g, x0, y, z));
+                int s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
+                for (int s = s0; s < s1; ++s) {
+                    float4 p = __ldg(g.sorted + s);
+                    float d = dist2f(qx, qy, qz, p.x, p.y, p.z);
+                    int id = __float_as_int(p.w);
+                    if (d < best_d2 || (d == best_d2 && id < best)) { best_d2 = d; best = id; bp = p; }
+                }
+            }
+    }
+    float hh = g.h * 0.999f;
+    if (best >= 0 && best_d2 <= hh * hh) return;
+    grid_nearest_far(g, qx, qy, qz, prune2, best, best_d2, bp);
 }
 
 // The 3x3x3 block of a query is 9 contiguous ranges; their 18 bounds are fetched by 18 lanes at once (one round trip

@@ -235,7 +235,8 @@ float rtr_icp_cell(const rtr_cloud* c) {
     // ~2x the mean sample spacing, estimated from the bounding-box surface (clouds here are surface samples)
     double ex = (double)c->bb_max[0] - c->bb_min[0], ey = (double)c->bb_max[1] - c->bb_min[1], ez = (double)c->bb_max[2] - c->bb_min[2];
     double area = 2.0 * (ex * ey + ey * ez + ex * ez);
-    double cell = 2.0 * std::sqrt(std::max(area, 1e-12) / (double)std::max(c->n, 1));
+    static const double factor = []() { const char* e = getenv("RTR_ICP_CELL_FACTOR"); return e ? atof(e) : 2.0; }();
+    double cell = factor * std::sqrt(std::max(area, 1e-12) / (double)std::max(c->n, 1));
     return (float)std::max(cell, 1e-4);
 }
 

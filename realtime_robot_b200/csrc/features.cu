@@ -13,6 +13,12 @@
 #include <cstring>
 
 static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+// Size thresholds between the small-cloud and large-cloud kernel variants; the environment overrides exist so that the
+// tests can push a repo-sized cloud through the large-cloud kernels and compare them with the oracle.
+static inline int env_threshold(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
+}
 
 // ----------------------------------------------------------------------------- normals (App. A.2)
 // covariance of the offsets from the query (fp64) -> smallest eigenvector (Jacobi) -> flip towards the viewpoint (0,0,0)
@@ -41,7 +47,11 @@ __device__ __forceinline__ float4 normal_from_sums(float4 q, int cnt, double sx,
     return o;
 }
 
-// large clouds: one thread per point (neighbouring threads walk the same cell ranges)
+// large clouds: one thread per point (neighbouring threads walk the same cell ranges).  ncu at 4 M points: issue-bound
+// (67 % issue active, fp64 pipe 58 %), the in-radius block runs with ~11 of 32 lanes because which candidates are inside
+// differs from lane to lane.  Parking accepted candidates in a per-thread shared-memory ring and draining the rings
+// warp-wide (dense fp64 blocks) was built and measured: 1.25 -> 1.76 ms — the extra votes, ring traffic and second load
+// cost more than the divergence they remove — so the plain loop stays.
 __global__ void __launch_bounds__(128) k_normals(GridView g, float r2, float4* __restrict__ normals) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= g.n) return;
@@ -418,7 +428,7 @@ __device__ __forceinline__ bool spfh_screen_one(const GridView& g, const float4*
     }
     return true;
 }
-__global__ void __launch_bounds__(SPFH_WARPS * 32) k_spfh(GridView g, const float4* __restrict__ sn, float r2,
+__global__ void __launch_bounds__(SPFH_WARPS * 32, 3) k_spfh(GridView g, const float4* __restrict__ sn, float r2,
                                                           float* __restrict__ spfh_sorted, int use_screen) {
     __shared__ int cnt[SPFH_WARPS][36];
     __shared__ int cq[SPFH_WARPS][64];      // in-radius candidates waiting for a dense batch of 32
@@ -608,6 +618,8 @@ struct FwSmem {
     float tsp[FW_TILE * 33];
     double acc[FW_QCHUNK][33];
     int nbc[FW_QCHUNK];
+    FwEntry wq[FW_WARPS][64];       // per warp: accepted candidates of the current (query, tile), in candidate order
+    int rq[FW_WARPS][64];
 };
 __global__ void k_occupied_cells(const int* __restrict__ cell_begin, int ncells, int* __restrict__ cells, int* __restrict__ count) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -619,6 +631,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32) k_fpfh_weight_tiled(GridView g,
     extern __shared__ __align__(16) unsigned char fw_raw[];
     FwSmem& sm = *reinterpret_cast<FwSmem*>(fw_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
     const int nc = *n_cells;
     for (int ci = blockIdx.x; ci < nc; ci += gridDim.x) {
         const int c = cells[ci];
@@ -642,28 +655,57 @@ __global__ void __launch_bounds__(FW_WARPS * 32) k_fpfh_weight_tiled(GridView g,
                         __syncthreads();
                         for (int qi = warp; qi < nq; qi += FW_WARPS) {
                             const float4 q = __ldg(g.sorted + q0 + qi);
-                            double a = sm.acc[qi][lane], a32 = (lane == 0) ? sm.acc[qi][32] : 0.0;
-                            int nb = 0;
+                            double a = sm.acc[qi][lane], a32 = sm.acc[qi][32];
+                            int nb = 0, head = 0, nring = 0;
+                            // lane = bin: drains cnt ring entries in order (broadcast reads of (w, term32, row), four rows in flight)
+                            auto consume = [&](int cnt) {
+                                int k = 0;
+                                for (; k + 4 <= cnt; k += 4) {
+                                    const int e = (head + k) & 63;      // head is 0 or 32 and k a multiple of 4: no wrap inside the four
+                                    const int r0 = sm.rq[warp][e], r1 = sm.rq[warp][e + 1], r2i = sm.rq[warp][e + 2], r3 = sm.rq[warp][e + 3];
+                                    const float v0 = sm.tsp[r0 * 33 + lane], v1 = sm.tsp[r1 * 33 + lane];
+                                    const float v2 = sm.tsp[r2i * 33 + lane], v3 = sm.tsp[r3 * 33 + lane];
+                                    const FwEntry e0 = sm.wq[warp][e], e1 = sm.wq[warp][e + 1], e2 = sm.wq[warp][e + 2], e3 = sm.wq[warp][e + 3];
+                                    a += (double)v0 * e0.w; a += (double)v1 * e1.w; a += (double)v2 * e2.w; a += (double)v3 * e3.w;
+                                    a32 += e0.t32; a32 += e1.t32; a32 += e2.t32; a32 += e3.t32;
+                                }
+                                for (; k < cnt; ++k) {
+                                    const int e = (head + k) & 63;
+                                    const FwEntry en = sm.wq[warp][e];
+                                    a += (double)sm.tsp[sm.rq[warp][e] * 33 + lane] * en.w;
+                                    a32 += en.t32;
+                                }
+                                head = (head + cnt) & 63;
+                                nring -= cnt;
+                            };
                             for (int base = 0; base < nt; base += 32) {
                                 const int i = base + lane;
-                                double w = 0.0;
-                                bool in = false;
+                                bool in = false, use = false;
+                                float d2 = 0.f;
                                 if (i < nt) {
                                     const float4 p = sm.tpos[i];
-                                    const float d2 = dist2f(q.x, q.y, q.z, p.x, p.y, p.z);
+                                    d2 = dist2f(q.x, q.y, q.z, p.x, p.y, p.z);
                                     in = d2 < r2;
-                                    if (in && d2 != 0.f) w = 1.0 / (double)d2;
+                                    use = in && d2 != 0.f;      // "minus the query point itself": dists == 0 skipped
                                 }
                                 nb += __popc(__ballot_sync(0xffffffffu, in));
-                                unsigned mask = __ballot_sync(0xffffffffu, w != 0.0);
-                                while (mask) {
-                                    const int j = __ffs(mask) - 1;
-                                    mask &= mask - 1;
-                                    const double wj = __shfl_sync(0xffffffffu, w, j);
-                                    a += (double)sm.tsp[(base + j) * 33 + lane] * wj;
-                                    if (lane == 0) a32 += (double)sm.tsp[(base + j) * 33 + 32] * wj;
+                                const unsigned mask = __ballot_sync(0xffffffffu, use);
+                                if (mask) {
+                                    if (use) {                  // lane = candidate: weight and bin 32's term, once per pair
+                                        const double w = 1.0 / (double)d2;
+                                        const int e = (head + nring + __popc(mask & lt)) & 63;
+                                        FwEntry en;
+                                        en.w = w;
+                                        en.t32 = (double)sm.tsp[i * 33 + 32] * w;
+                                        sm.wq[warp][e] = en;
+                                        sm.rq[warp][e] = i;
+                                    }
+                                    nring += __popc(mask);
+                                    __syncwarp();
+                                    if (nring >= 32) { consume(32); __syncwarp(); }
                                 }
                             }
+                            if (nring > 0) { consume(nring); __syncwarp(); }
                             sm.acc[qi][lane] = a;
                             if (lane == 0) { sm.acc[qi][32] = a32; sm.nbc[qi] += nb; }
                         }
@@ -802,7 +844,7 @@ int rtr_normals_dev(rtr_cloud* c, float radius) {
     if (int e = rtr_get_grid(c, radius, &g)) return e;
     if (!c->normals) if (int e = dev_alloc(ctx, &c->normals, c->n, "normals")) return e;
     if (c->n > 0) {
-        if (c->n <= RTR_WARP_PER_POINT_MAX)
+        if (c->n <= env_threshold("RTR_WARP_PER_POINT_MAX", RTR_WARP_PER_POINT_MAX))
             k_normals_warp<<<std::min(nblk(c->n, PW_WARPS), ctx->sm_count * 16), PW_WARPS * 32, 0, ctx->stream>>>(rtr_view(g), radius * radius, c->normals);
         else
             k_normals<<<nblk(c->n, 128), 128, 0, ctx->stream>>>(rtr_view(g), radius * radius, c->normals);
@@ -832,7 +874,7 @@ int rtr_harris_dev(rtr_cloud* c, float radius, float threshold, int nms, int ref
     RTR_CHECK(cudaMemsetAsync(*d_count, 0, sizeof(int), ctx->stream), "harris");
     if (n > 0) {
         GridView v = rtr_view(g);
-        if (n <= RTR_WARP_PER_POINT_MAX) {
+        if (n <= env_threshold("RTR_WARP_PER_POINT_MAX", RTR_WARP_PER_POINT_MAX)) {
             int grid = std::min(nblk(n, PW_WARPS), ctx->sm_count * 16);
             k_harris_response_warp<<<grid, PW_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, c->response, resp_sorted);
             RTR_LAUNCH_CHECK(ctx, "harris.response");
@@ -879,7 +921,7 @@ int rtr_fpfh_dev(rtr_cloud* c, float radius) {
         int use_screen = (ex && ex[0] == '1') ? 0 : 1;
         k_spfh<<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * 16), SPFH_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh, use_screen);
         RTR_LAUNCH_CHECK(ctx, "fpfh.spfh");
-        if (n >= (1 << 20)) {
+        if (n >= env_threshold("RTR_FPFH_TILED_MIN", 1 << 20)) {
             // one CTA per occupied cell, candidates staged through shared memory (needs many occupied cells to fill the GPU)
             int *cells = nullptr, *n_cells = nullptr;
             if (int e = tmp_alloc(ctx, &cells, (size_t)std::min(g->ncells, n), "fpfh")) return e;
@@ -887,9 +929,13 @@ int rtr_fpfh_dev(rtr_cloud* c, float radius) {
             RTR_CHECK(cudaMemsetAsync(n_cells, 0, sizeof(int), ctx->stream), "fpfh");
             k_occupied_cells<<<nblk(g->ncells, 256), 256, 0, ctx->stream>>>(g->cell_begin, g->ncells, cells, n_cells);
             RTR_LAUNCH_CHECK(ctx, "fpfh.cells");
-            static bool attr = false;
-            if (!attr) { RTR_CHECK(cudaFuncSetAttribute(k_fpfh_weight_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwSmem)), "fpfh"); attr = true; }
-            int grid = std::min(std::min(g->ncells, n), ctx->sm_count * 4);
+            static int per_sm = 0;        // persistent CTAs: exactly as many as are resident at once (a partial second wave would idle most SMs)
+            if (!per_sm) {
+                RTR_CHECK(cudaFuncSetAttribute(k_fpfh_weight_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwSmem)), "fpfh");
+                RTR_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fpfh_weight_tiled, FW_WARPS * 32, sizeof(FwSmem)), "fpfh");
+                per_sm = std::max(per_sm, 1);
+            }
+            int grid = std::min(std::min(g->ncells, n), ctx->sm_count * per_sm);
             k_fpfh_weight_tiled<<<grid, FW_WARPS * 32, sizeof(FwSmem), ctx->stream>>>(v, spfh, r2, c->fpfh, cells, n_cells);
         } else {
             k_fpfh_weight<<<std::min(nblk(n, FPFH_WARPS), ctx->sm_count * 16), FPFH_WARPS * 32, 0, ctx->stream>>>(v, spfh, r2, c->fpfh);

@@ -381,8 +381,18 @@ __device__ void icp_last_cta_solve(const double* partials, IcpState* st, unsigne
     }
 }
 
+// Lower bound of dist2f(q, p) over every p inside the box, built from the same float operations (subtraction, product
+// and sum are monotone under round-to-nearest): a query whose bound exceeds the correspondence cap has no correspondence.
+struct Box6 { float mnx, mny, mnz, mxx, mxy, mxz; };
+__device__ __forceinline__ float box_dist2f(const Box6& b, float qx, float qy, float qz) {
+    float ex = qx > b.mxx ? __fsub_rn(qx, b.mxx) : (qx < b.mnx ? __fsub_rn(qx, b.mnx) : 0.f);
+    float ey = qy > b.mxy ? __fsub_rn(qy, b.mxy) : (qy < b.mny ? __fsub_rn(qy, b.mny) : 0.f);
+    float ez = qz > b.mxz ? __fsub_rn(qz, b.mxz) : (qz < b.mnz ? __fsub_rn(qz, b.mnz) : 0.f);
+    return __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+}
 // correspondence estimation + accumulation.  Applies the previous iteration's step first (transformCloud in place).
-__global__ void __launch_bounds__(ICP_THREADS, 4) k_icp_corr(GridView g, float4* __restrict__ cur, int n, IcpState* st,
+// A query farther from the target's bounding box than the cap is dropped before any cell is touched.
+__global__ void __launch_bounds__(ICP_THREADS, 4) k_icp_corr(GridView g, Box6 bb, float4* __restrict__ cur, int n, IcpState* st,
                                                            double dmax2, float prune2, double* partials, unsigned* ticket, IcpSolveArgs sa) {
     __shared__ float m[16];
     __shared__ double red[ICP_THREADS / 32][ICP_NSUM];
@@ -401,7 +411,8 @@ __global__ void __launch_bounds__(ICP_THREADS, 4) k_icp_corr(GridView g, float4*
         if (have) { q = xform(m, q); cur[i] = q; }
         int b; float d2; float4 t;
         // the grid copy carries the matched point's coordinates: the original-order target is never touched
-        grid_nearest_ex(g, q.x, q.y, q.z, prune2, b, d2, t);
+        if (box_dist2f(bb, q.x, q.y, q.z) > prune2) b = -1;
+        else grid_nearest_ex(g, q.x, q.y, q.z, prune2, b, d2, t);
         if (b >= 0 && (double)d2 <= dmax2) {
             double sx = q.x, sy = q.y, sz = q.z, tx = t.x, ty = t.y, tz = t.z;
             acc[0] = sx; acc[1] = sy; acc[2] = sz; acc[3] = tx; acc[4] = ty; acc[5] = tz;
@@ -669,10 +680,11 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     if (p->max_correspondence_distance > 0.f) { prune2 = (float)dmax2; if ((double)prune2 < dmax2) prune2 = nextafterf(prune2, FLT_MAX); }
     // small sources: one warp per query (latency), large ones: one thread per query in cell order (throughput)
     const bool warp_per_query = n < 65536;
+    const Box6 bb{tgt->bb_min[0], tgt->bb_min[1], tgt->bb_min[2], tgt->bb_max[0], tgt->bb_max[1], tgt->bb_max[2]};
     if (n >= 1 && tgt->n >= 1) {
         for (int it = 0; it < p->max_iterations; ++it) {
             if (warp_per_query) k_icp_corr_warp<<<nbw, ICPW_WARPS * 32, 0, ctx->stream>>>(v, tgt->pts, cur, n, st, dmax2, prune2, partials, ticket, sa);
-            else k_icp_corr<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, cur, n, st, dmax2, prune2, partials, ticket, sa);
+            else k_icp_corr<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, bb, cur, n, st, dmax2, prune2, partials, ticket, sa);
             RTR_LAUNCH_CHECK(ctx, "icp.corr");
         }
     }

@@ -144,6 +144,31 @@ def test_normals_harris_fpfh(api, gpu_ctx, orc, clouds, name):
     c.free()
 
 
+@pytest.mark.parametrize("name", ["chair1", "chair4", "sofa"])
+def test_large_cloud_kernel_variants_match_oracle(api, gpu_ctx, orc, clouds, name, monkeypatch):
+    """Clouds above 262 144 points use one thread per point (k_normals with its accept ring, k_harris_response, k_harris_nms)
+    and, from 1 M points, the cell-tiled FPFH weighting kernel; the oracle cannot check those sizes in seconds, so the
+    thresholds are lowered and the same kernels run on repo clouds: same bars as the small-cloud variants, and the tiled
+    weighting must equal the untiled one bit for bit (it adds in the same order)."""
+    pts = clouds(name)
+    c = api.Cloud(gpu_ctx, pts)
+    n_small = c.normals(0.05).copy()
+    f_small = c.fpfh(0.10).copy()
+    c.reset()
+    monkeypatch.setenv("RTR_WARP_PER_POINT_MAX", "0")
+    monkeypatch.setenv("RTR_FPFH_TILED_MIN", "1")
+    n4, o4 = c.normals(0.05), orc.normals(pts, 0.05)
+    assert close_frac(n4, o4) >= 0.9999 and close_frac(n4, n_small) >= 0.9999
+    resp, ki, kx = c.harris3d(0.05, 0.01)
+    oresp, oki, okx = orc.harris3d(pts, n4, 0.05, 0.01)
+    assert close_frac(resp, oresp, atol=1e-9) >= 0.9999 and np.array_equal(ki, oki)
+    f, of = c.fpfh(0.10), orc.fpfh(pts, n4, 0.10)
+    assert close_frac(f, of, rtol=1e-5, atol=1e-4) >= 0.9999
+    if np.array_equal(n4.view(np.uint32), n_small.view(np.uint32)):      # same normals in -> identical histograms out
+        assert np.array_equal(f.view(np.uint32), f_small.view(np.uint32))
+    c.free()
+
+
 @pytest.mark.parametrize("name", ["chair1", "chair4", "desk3", "sofa", "room", "noisy_plane"])
 def test_spfh_fp32_screen_changes_nothing(api, gpu_ctx, clouds, name, monkeypatch):
     """The fp32 bin screen of k_spfh only decides pairs safely inside a bin: FPFH with the screen == FPFH with every pair
@@ -327,6 +352,25 @@ def test_swapped_direction_and_transform(api, gpu_ctx, orc, clouds):
     assert np.abs(g.matrix() - o.matrix()).max() <= POSE_TOL and abs(g.fitness - o.fitness) <= FIT_TOL
     cm.transform(gt)
     assert np.array_equal(cm.download(), orc.transform(model, gt))
+    cm.free(); cs.free()
+
+
+@pytest.mark.parametrize("cap", [0.0, 0.03])
+def test_icp_large_source_path_matches_oracle(api, gpu_ctx, orc, cap):
+    # >= 65 536 source points take the eight-lanes-per-query kernel (k_icp_corr_group): 27-cell block as one flat list,
+    # ring walk beyond it, and - with a cap - the bounding-box rejection of far sources (300 of them scattered metres away)
+    model, scene, gt = synth.icp_config(70_000, 30_000)
+    rng = np.random.default_rng(5)
+    far = model[rng.integers(0, len(model), 300)].copy()
+    far[:, :3] += rng.normal(0, 1.5, (300, 3)).astype(np.float32)
+    src = np.concatenate([model, far]).astype(np.float32)
+    cm, cs = api.Cloud(gpu_ctx, src), api.Cloud(gpu_ctx, scene)
+    p = default_register_params()
+    p.icp.max_iterations = 4; p.icp.max_correspondence_distance = cap
+    g, o = api.icp(cm, cs, p.icp, gt), orc.icp(src, scene, p.icp, gt)
+    assert (g.inliers, g.iterations, g.converged) == (o.inliers, o.iterations, o.converged)
+    assert np.abs(g.matrix() - o.matrix()).max() <= POSE_TOL and abs(g.fitness - o.fitness) <= FIT_TOL
+    assert bytes(api.icp(cm, cs, p.icp, gt)) == bytes(g)
     cm.free(); cs.free()
 
 
