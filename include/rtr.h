@@ -201,6 +201,12 @@ int rtr_harris3d(rtr_cloud* c, float radius, float threshold, int nms, int refin
  * Needs rtr_normals.  host_fpfh (optional): n x 33 floats. */
 int rtr_fpfh(rtr_cloud* c, float radius, float* host_fpfh);
 
+/* The same estimator with input != surface: pcl::FPFHEstimation::setInputCloud(keypoints) + setSearchSurface(cloud)
+ * (App. A.4; BASELINE.json configs[3]: 100 000 query points on a 4 M-point surface).  host_query_index: n_query ORIGINAL
+ * indices into the cloud; host_fpfh: n_query x 33 floats, row i = the row rtr_fpfh gives point host_query_index[i].
+ * SPFH signatures are computed only for the points some query's neighbourhood needs.  Needs rtr_normals. */
+int rtr_fpfh_at(rtr_cloud* c, float radius, const int* host_query_index, int n_query, float* host_fpfh);
+
 /* k nearest target features of every source feature, 33-D squared L2, ascending, ties -> lowest index:
  * KdTreeFLANN<FPFHSignature33>::nearestKSearch inside SampleConsensusPrerejective::findSimilarFeatures
  * (App. A.5).  Both clouds need rtr_fpfh.  Result cached on `source`; host outputs optional (ns x k). */

@@ -16,7 +16,7 @@ EXPORTS = [
     "rtr_default_register_params", "rtr_context_create", "rtr_context_destroy", "rtr_context_sync", "rtr_context_stream",
     "rtr_context_launches", "rtr_profile_begin", "rtr_profile_end", "rtr_cloud_reset", "rtr_event_record", "rtr_event_elapsed_ms", "rtr_cloud_upload", "rtr_cloud_from_device",
     "rtr_cloud_free", "rtr_cloud_size", "rtr_cloud_transform", "rtr_cloud_download", "rtr_radius_neighbors", "rtr_nearest",
-    "rtr_normals", "rtr_harris3d", "rtr_fpfh", "rtr_match_features", "rtr_match_features_raw", "rtr_match_last_stats", "rtr_ransac_prerejective", "rtr_icp", "rtr_register",
+    "rtr_normals", "rtr_harris3d", "rtr_fpfh", "rtr_fpfh_at", "rtr_match_features", "rtr_match_features_raw", "rtr_match_last_stats", "rtr_ransac_prerejective", "rtr_icp", "rtr_register",
     "rtr_register_host", "ComputeTDFWithCuda", "rtr_tdf_batch", "rtr_tdf_batch_dev", "rtr_native_default_params", "rtr_native_keypoint_descriptors",
     "rtr_native_pair_scores", "rtr_native_register", "rtr_plane_areas", "rtr_pcd_info", "rtr_pcd_read", "rtr_pcd_load", "rtr_pcd_write",
     "rtr_cloud_save", "rtr_register_begin", "rtr_register_host_begin", "rtr_register_end", "rtr_context_create_prio",
@@ -61,6 +61,7 @@ def lib():
         L.rtr_normals.argtypes = [vp, C.c_float, vp]
         L.rtr_harris3d.argtypes = [vp, C.c_float, C.c_float, C.c_int, C.c_int, vp, vp, vp, C.c_int, ip]
         L.rtr_fpfh.argtypes = [vp, C.c_float, vp]
+        L.rtr_fpfh_at.argtypes = [vp, C.c_float, vp, C.c_int, vp]
         L.rtr_match_features.argtypes = [vp, vp, C.c_int, vp, vp]
         L.rtr_match_features_raw.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, fp]
         L.rtr_match_last_stats.argtypes = [vp, ip]

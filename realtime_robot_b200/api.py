@@ -210,6 +210,13 @@ class Cloud:
         _lib.check("rtr_fpfh", _lib.lib().rtr_fpfh(self._h, radius, _ptr(out)))
         return out
 
+    def fpfh_at(self, radius: float, query_index) -> np.ndarray:
+        """FPFH at a subset of the points (PCL: setInputCloud(keypoints) + setSearchSurface(cloud)); rows follow query_index."""
+        q = np.ascontiguousarray(query_index, dtype=np.int32)
+        out = np.zeros((len(q), 33), dtype=np.float32)
+        _lib.check("rtr_fpfh_at", _lib.lib().rtr_fpfh_at(self._h, radius, _ptr(q), len(q), _ptr(out)))
+        return out
+
     def match_features(self, target: "Cloud", k: int):
         idx = np.zeros((self.n, k), dtype=np.int32)
         dist = np.zeros((self.n, k), dtype=np.float32)

@@ -429,14 +429,17 @@ __device__ __forceinline__ bool spfh_screen_one(const GridView& g, const float4*
     return true;
 }
 __global__ void __launch_bounds__(SPFH_WARPS * 32, 3) k_spfh(GridView g, const float4* __restrict__ sn, float r2,
-                                                          float* __restrict__ spfh_sorted, int use_screen) {
+                                                             float* __restrict__ spfh_sorted, int use_screen,
+                                                             const int* __restrict__ list, const int* __restrict__ list_count) {
     __shared__ int cnt[SPFH_WARPS][36];
     __shared__ int cq[SPFH_WARPS][64];      // in-radius candidates waiting for a dense batch of 32
     __shared__ int fq[SPFH_WARPS][64];      // pairs the screen could not decide
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int nwarps = gridDim.x * SPFH_WARPS;
     const unsigned lt = (1u << lane) - 1u;
-    for (int s = blockIdx.x * SPFH_WARPS + warp; s < g.n; s += nwarps) {
+    const int n_items = list ? *list_count : g.n;       // list: sorted positions whose SPFH is wanted (rtr_fpfh_at), else all points
+    for (int it = blockIdx.x * SPFH_WARPS + warp; it < n_items; it += nwarps) {
+        const int s = list ? __ldg(list + it) : it;
         cnt[warp][lane] = 0;
         if (lane < 4) cnt[warp][32 + lane] = 0;
         __syncwarp();
@@ -514,7 +517,7 @@ __global__ void __launch_bounds__(SPFH_WARPS * 32, 3) k_spfh(GridView g, const f
 #define FPFH_WARPS 8
 struct __align__(16) FwEntry { double w, t32; };
 __global__ void __launch_bounds__(FPFH_WARPS * 32) k_fpfh_weight(GridView g, const float* __restrict__ spfh_sorted, float r2,
-                                                                 float* __restrict__ fpfh) {
+                                                                 float* __restrict__ fpfh, const int* __restrict__ list, int n_list) {
     __shared__ double hs[FPFH_WARPS][36];
     __shared__ FwEntry wq[FPFH_WARPS][64];
     __shared__ int rq[FPFH_WARPS][64];
@@ -522,7 +525,9 @@ __global__ void __launch_bounds__(FPFH_WARPS * 32) k_fpfh_weight(GridView g, con
     int nwarps = gridDim.x * FPFH_WARPS;
     const unsigned lt = (1u << lane) - 1u;
     const float* rows = spfh_sorted + lane;
-    for (int s = blockIdx.x * FPFH_WARPS + warp; s < g.n; s += nwarps) {
+    const int n_items = list ? n_list : g.n;            // list: sorted positions of the query points (rtr_fpfh_at), row it of the output
+    for (int it = blockIdx.x * FPFH_WARPS + warp; it < n_items; it += nwarps) {
+        const int s = list ? __ldg(list + it) : it;
         float4 q = __ldg(g.sorted + s);
         double acc = 0, acc32 = 0;
         int nb = 0, head = 0, nq = 0;
@@ -593,7 +598,7 @@ __global__ void __launch_bounds__(FPFH_WARPS * 32) k_fpfh_weight(GridView g, con
             hs[warp][33 + lane] = (sum != 0) ? 100.0 / sum : 0.0;
         }
         __syncwarp();
-        float* o = fpfh + (size_t)__float_as_int(q.w) * 33;
+        float* o = fpfh + (size_t)(list ? it : __float_as_int(q.w)) * 33;
         if (nb == 0) {
             o[lane] = __int_as_float(0x7fc00000);
             if (lane == 0) o[32] = __int_as_float(0x7fc00000);
@@ -919,7 +924,7 @@ int rtr_fpfh_dev(rtr_cloud* c, float radius) {
         // RTR_SPFH_EXACT=1 sends every pair through the fp64 evaluation (the tests use it to show the fp32 screen changes nothing)
         const char* ex = getenv("RTR_SPFH_EXACT");
         int use_screen = (ex && ex[0] == '1') ? 0 : 1;
-        k_spfh<<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * 16), SPFH_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh, use_screen);
+        k_spfh<<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * 16), SPFH_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh, use_screen, nullptr, nullptr);
         RTR_LAUNCH_CHECK(ctx, "fpfh.spfh");
         if (n >= env_threshold("RTR_FPFH_TILED_MIN", 1 << 20)) {
             // one CTA per occupied cell, candidates staged through shared memory (needs many occupied cells to fill the GPU)
@@ -938,7 +943,7 @@ int rtr_fpfh_dev(rtr_cloud* c, float radius) {
             int grid = std::min(std::min(g->ncells, n), ctx->sm_count * per_sm);
             k_fpfh_weight_tiled<<<grid, FW_WARPS * 32, sizeof(FwSmem), ctx->stream>>>(v, spfh, r2, c->fpfh, cells, n_cells);
         } else {
-            k_fpfh_weight<<<std::min(nblk(n, FPFH_WARPS), ctx->sm_count * 16), FPFH_WARPS * 32, 0, ctx->stream>>>(v, spfh, r2, c->fpfh);
+            k_fpfh_weight<<<std::min(nblk(n, FPFH_WARPS), ctx->sm_count * 16), FPFH_WARPS * 32, 0, ctx->stream>>>(v, spfh, r2, c->fpfh, nullptr, 0);
         }
         RTR_LAUNCH_CHECK(ctx, "fpfh.weight");
     }
@@ -946,6 +951,67 @@ int rtr_fpfh_dev(rtr_cloud* c, float radius) {
     c->fpfh_radius = radius;
     // features changed: cached correspondences are stale
     dev_free(ctx, c->knn); c->knn = nullptr; dev_free(ctx, c->knn_dist); c->knn_dist = nullptr; c->knn_k = 0;
+    return 0;
+}
+
+// FPFH at a subset of the points (PCL: setInputCloud(keypoints) + setSearchSurface(cloud)): SPFH only where a query's
+// neighbourhood needs it.  inverse permutation -> queries' sorted positions; one warp per query flags its in-radius
+// points; the flagged positions are compacted (ascending) into the SPFH work list; the weighting pass runs over the
+// queries.  Every row equals the row rtr_fpfh computes for that point.
+__global__ void k_inverse_perm(GridView g, int* __restrict__ inv) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < g.n) inv[__float_as_int(__ldg(g.sorted + s).w)] = s;
+}
+__global__ void k_query_positions(const int* __restrict__ qidx, int nq, const int* __restrict__ inv, int* __restrict__ qpos) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) qpos[i] = inv[qidx[i]];
+}
+__global__ void __launch_bounds__(PW_WARPS * 32) k_mark_neighbours(GridView g, const int* __restrict__ qpos, int nq, float r2,
+                                                                   unsigned char* __restrict__ flags) {
+    int lane = threadIdx.x & 31;
+    int nwarps = gridDim.x * PW_WARPS;
+    for (int i = blockIdx.x * PW_WARPS + (threadIdx.x >> 5); i < nq; i += nwarps) {
+        float4 q = __ldg(g.sorted + qpos[i]);
+        for_block27_warp(g, q.x, q.y, q.z, lane, [&](int sp, float4, float d2) { if (d2 < r2) flags[sp] = 1; });
+    }
+}
+
+int rtr_fpfh_at_dev(rtr_cloud* c, float radius, const int* d_query_index, int nq, float* d_out) {
+    rtr_context* ctx = c->ctx;
+    if (!c->normals) return rtr_fail("fpfh_at", "rtr_normals must run first", RTR_ERR_NOT_READY);
+    if (nq <= 0 || c->n <= 0) return 0;
+    DevGrid* g;
+    if (int e = rtr_get_grid(c, radius, &g)) return e;
+    if (int e = rtr_grid_normals(c, g)) return e;
+    const int n = c->n;
+    const float r2 = radius * radius;
+    GridView v = rtr_view(g);
+    int *inv = nullptr, *qpos = nullptr, *list = nullptr, *count = nullptr; unsigned char* flags = nullptr; float* spfh = nullptr; char* temp = nullptr;
+    if (int e = tmp_alloc(ctx, &inv, n, "fpfh_at")) return e;
+    if (int e = tmp_alloc(ctx, &qpos, nq, "fpfh_at")) return e;
+    if (int e = tmp_alloc(ctx, &list, n, "fpfh_at")) return e;
+    if (int e = tmp_alloc(ctx, &count, 1, "fpfh_at")) return e;
+    if (int e = tmp_alloc(ctx, &flags, n, "fpfh_at")) return e;
+    if (int e = tmp_alloc(ctx, &spfh, (size_t)n * 33, "fpfh_at")) return e;
+    k_inverse_perm<<<nblk(n, 256), 256, 0, ctx->stream>>>(v, inv);
+    RTR_LAUNCH_CHECK(ctx, "fpfh_at.inverse");
+    k_query_positions<<<nblk(nq, 256), 256, 0, ctx->stream>>>(d_query_index, nq, inv, qpos);
+    RTR_LAUNCH_CHECK(ctx, "fpfh_at.positions");
+    RTR_CHECK(cudaMemsetAsync(flags, 0, (size_t)n, ctx->stream), "fpfh_at");
+    k_mark_neighbours<<<std::min(nblk(nq, PW_WARPS), ctx->sm_count * 16), PW_WARPS * 32, 0, ctx->stream>>>(v, qpos, nq, r2, flags);
+    RTR_LAUNCH_CHECK(ctx, "fpfh_at.mark");
+    size_t tb = 0;
+    cub::DeviceSelect::Flagged(nullptr, tb, thrust::counting_iterator<int>(0), flags, list, count, n, ctx->stream);
+    if (int e = tmp_alloc(ctx, &temp, tb, "fpfh_at")) return e;
+    RTR_CHECK(cub::DeviceSelect::Flagged(temp, tb, thrust::counting_iterator<int>(0), flags, list, count, n, ctx->stream), "fpfh_at.select");
+    RTR_MARK(ctx, "fpfh_at.cub_select");
+    const char* ex = getenv("RTR_SPFH_EXACT");
+    int use_screen = (ex && ex[0] == '1') ? 0 : 1;
+    k_spfh<<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * 16), SPFH_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh, use_screen, list, count);
+    RTR_LAUNCH_CHECK(ctx, "fpfh.spfh");
+    k_fpfh_weight<<<std::min(nblk(nq, FPFH_WARPS), ctx->sm_count * 16), FPFH_WARPS * 32, 0, ctx->stream>>>(v, spfh, r2, d_out, qpos, nq);
+    RTR_LAUNCH_CHECK(ctx, "fpfh.weight");
+    dev_free(ctx, inv); dev_free(ctx, qpos); dev_free(ctx, list); dev_free(ctx, count); dev_free(ctx, flags); dev_free(ctx, spfh); dev_free(ctx, temp);
     return 0;
 }
 
@@ -1007,6 +1073,24 @@ int rtr_fpfh(rtr_cloud* c, float radius, float* host_fpfh) {
     if (int e = rtr_fpfh_dev(c, radius)) return e;
     if (host_fpfh && c->n > 0) RTR_CHECK(cudaMemcpyAsync(host_fpfh, c->fpfh, (size_t)c->n * 33 * 4, cudaMemcpyDeviceToHost, c->ctx->stream), "fpfh");
     RTR_CHECK(cudaStreamSynchronize(c->ctx->stream), "fpfh");
+    return 0;
+}
+
+int rtr_fpfh_at(rtr_cloud* c, float radius, const int* host_query_index, int n_query, float* host_fpfh) {
+    if (!c || !(radius > 0.f) || n_query < 0 || (n_query > 0 && (!host_query_index || !host_fpfh))) return rtr_fail("fpfh_at", "bad argument", RTR_ERR_INVALID);
+    for (int i = 0; i < n_query; ++i)
+        if (host_query_index[i] < 0 || host_query_index[i] >= c->n) return rtr_fail("fpfh_at", "query index out of range", RTR_ERR_INVALID);
+    if (n_query == 0) return 0;
+    rtr_context* ctx = c->ctx;
+    TmpScope tmp_scope(ctx);
+    RTR_CHECK(cudaSetDevice(ctx->device), "fpfh_at");
+    int* d_q = nullptr; float* d_out = nullptr;
+    if (int e = tmp_alloc(ctx, &d_q, n_query, "fpfh_at")) return e;
+    if (int e = tmp_alloc(ctx, &d_out, (size_t)n_query * 33, "fpfh_at")) return e;
+    RTR_CHECK(cudaMemcpyAsync(d_q, host_query_index, (size_t)n_query * sizeof(int), cudaMemcpyHostToDevice, ctx->stream), "fpfh_at");
+    if (int e = rtr_fpfh_at_dev(c, radius, d_q, n_query, d_out)) return e;
+    RTR_CHECK(cudaMemcpyAsync(host_fpfh, d_out, (size_t)n_query * 33 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream), "fpfh_at");
+    RTR_CHECK(cudaStreamSynchronize(ctx->stream), "fpfh_at");
     return 0;
 }
 

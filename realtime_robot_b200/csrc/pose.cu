@@ -210,8 +210,11 @@ int rtr_ransac_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_ransac_params* p, r
         return rtr_fail("ransac", "rtr_match_features(source, target, k >= correspondence_k) must run first", RTR_ERR_NOT_READY);
     if (!(p->max_correspondence_distance > 0.f)) return rtr_fail("ransac", "max_correspondence_distance must be > 0", RTR_ERR_INVALID);
     DevGrid* g;
-    // any cached grid whose cells are at least d_max wide (and not much wider) serves the 27-cell inlier test
-    if (int e = rtr_get_grid_any(tgt, p->max_correspondence_distance, p->max_correspondence_distance * 1.001f, p->max_correspondence_distance * 2.0f, &g)) return e;
+    // any cached grid whose cells are at least d_max wide (and not much wider) serves the 27-cell inlier test; a large
+    // sweep repays a grid of exactly d_max (the normals grid, 0.05 against d_max = 0.0365, holds 1.9x the candidates per
+    // block: 1e7 hypotheses 8.9 -> 5.9 ms), a single registration's 50 000 hypotheses do not repay the build
+    const float hi_mult = (h1 - h0 >= 200000) ? 1.05f : 2.0f;
+    if (int e = rtr_get_grid_any(tgt, p->max_correspondence_distance, p->max_correspondence_distance * 1.001f, p->max_correspondence_distance * hi_mult, &g)) return e;
     const long long CHUNK = 1 << 20;
     int cap = (int)std::min<long long>(CHUNK, h1 - h0);
     // slices of the source per surviving hypothesis: ~2048 points each, fewer when the partial arrays would get large

@@ -146,7 +146,7 @@ def test_normals_harris_fpfh(api, gpu_ctx, orc, clouds, name):
 
 @pytest.mark.parametrize("name", ["chair1", "chair4", "sofa"])
 def test_large_cloud_kernel_variants_match_oracle(api, gpu_ctx, orc, clouds, name, monkeypatch):
-    """Clouds above 262 144 points use one thread per point (k_normals with its accept ring, k_harris_response, k_harris_nms)
+    """Clouds above 262 144 points use one thread per point (k_normals, k_harris_response, k_harris_nms)
     and, from 1 M points, the cell-tiled FPFH weighting kernel; the oracle cannot check those sizes in seconds, so the
     thresholds are lowered and the same kernels run on repo clouds: same bars as the small-cloud variants, and the tiled
     weighting must equal the untiled one bit for bit (it adds in the same order)."""
@@ -166,6 +166,28 @@ def test_large_cloud_kernel_variants_match_oracle(api, gpu_ctx, orc, clouds, nam
     assert close_frac(f, of, rtol=1e-5, atol=1e-4) >= 0.9999
     if np.array_equal(n4.view(np.uint32), n_small.view(np.uint32)):      # same normals in -> identical histograms out
         assert np.array_equal(f.view(np.uint32), f_small.view(np.uint32))
+    c.free()
+
+
+@pytest.mark.parametrize("name", ["chair1", "sofa", "room"])
+def test_fpfh_at_query_subset_equals_full_rows(api, gpu_ctx, orc, clouds, name):
+    """rtr_fpfh_at (PCL: setInputCloud(keypoints) + setSearchSurface(cloud); BASELINE configs[3]'s query form): row i is,
+    bit for bit, the row rtr_fpfh computes for point query_index[i] — SPFH is only evaluated where some query needs it —
+    and the oracle agrees; duplicates, unordered queries, the empty set and a bad index are handled."""
+    pts = synth.sample_rects(synth.room_rects((6.0, 6.0, 3.0), n_boxes=6), 120000, 12) if name == "room" else clouds(name)
+    c = api.Cloud(gpu_ctx, pts)
+    n4 = c.normals(0.05)
+    full = c.fpfh(0.10).copy()
+    rng = np.random.default_rng(3)
+    q = rng.choice(len(pts), max(1, len(pts) // 40), replace=False).astype(np.int32)
+    q = np.concatenate([q, q[:5], np.array([0, len(pts) - 1], np.int32)])
+    sub = c.fpfh_at(0.10, q)
+    assert np.array_equal(sub.view(np.uint32), full[q].view(np.uint32))
+    if name != "room":
+        assert close_frac(sub, orc.fpfh(pts, n4, 0.10)[q], rtol=1e-5, atol=1e-4) >= 0.9999
+    assert c.fpfh_at(0.10, np.zeros(0, np.int32)).shape == (0, 33)
+    with pytest.raises(Exception):
+        c.fpfh_at(0.10, np.array([len(pts)], np.int32))
     c.free()
 
 

@@ -84,6 +84,28 @@ def main():
         print(json.dumps(out), flush=True)
         # features of the scene, reused as the matching workload (real FPFH statistics, not random numbers)
         feats = c.fpfh(0.08)
+        # SURVEY 8(d) configs[3], query form: 100 000 keypoints (one point per occupied voxel of a coarse lattice, then a
+        # seeded subsample) on the full 4 M-point search surface, r = 0.08 -> ~10 M neighbour entries in the weighting pass
+        vox = np.floor(scene[:, :3] / 0.06).astype(np.int64)
+        _, first = np.unique(vox[:, 0] * 1_000_003 + vox[:, 1] * 1009 + vox[:, 2], return_index=True)
+        rng_q = np.random.default_rng(synth.BASE_SEED + 3)
+        qidx = np.sort(rng_q.choice(first, min(100_000, len(first)), replace=False)).astype(np.int32)
+        sub = c.fpfh_at(0.08, qidx)
+        same = bool(np.array_equal(sub.view(np.uint32), feats[qidx].view(np.uint32)))
+        ms_q = []
+        for _ in range(3):
+            ctx.sync(); ctx.record(4); c.fpfh_at(0.08, qidx); ctx.record(5)
+            ms_q.append(ctx.elapsed_ms(4, 5))
+        ctx.profile_begin(); c.fpfh_at(0.08, qidx); pr = ctx.profile_end()
+        kq = int(cnt8[qidx].sum())
+        alg_wq = 16 * (len(qidx) + kq) + 132 * kq + 132 * len(qidx)
+        print(json.dumps({"config": "configs[3] FPFH at 100k keypoints on the 4M-point surface (rtr_fpfh_at, host query list in, rows out)",
+                          "queries": int(len(qidx)), "radius": 0.08, "neighbour_entries": kq, "rows_equal_full_fpfh_bitwise": same,
+                          "ms_end_to_end": min(ms_q), "queries_per_s": len(qidx) / (min(ms_q) * 1e-3),
+                          "roofline_weight": {"kernel": "k_fpfh_weight", "kernel_ms": pr["fpfh.weight"][1], "algorithmic_bytes": alg_wq,
+                                              "achieved": alg_wq / (pr["fpfh.weight"][1] * 1e-3) / 1e9, "peak": HBM, "unit": "GB/s",
+                                              "frac": alg_wq / (pr["fpfh.weight"][1] * 1e-3) / 1e9 / HBM},
+                          "kernel_ms_all": {k: round(v[1], 3) for k, v in sorted(pr.items(), key=lambda kv: -kv[1][1])[:8]}}), flush=True)
         c.free()
     else:
         feats = None
