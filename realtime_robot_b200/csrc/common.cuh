@@ -333,6 +333,7 @@ __device__ __forceinline__ void grid_nearest_ex(const GridView& g, float qx, flo
     }
     float hh = g.h * 0.999f;
     if (best >= 0 && best_d2 <= hh * hh) return;
+    if (prune2 <= hh * hh) return;        // everything outside the block is farther than the caller cares about
     grid_nearest_far(g, qx, qy, qz, prune2, best, best_d2, bp);
 }
 
@@ -369,6 +370,25 @@ __device__ __forceinline__ WarpCand warp_candidates(const GridView& g, int cx, i
 #pragma unroll
     for (int k = 0; k < 9; ++k) { w.pre[k] = __shfl_sync(0xffffffffu, excl, k); w.first[k] = __shfl_sync(0xffffffffu, br.bound, k); }
     return w;
+}
+// The same list with its tables in shared memory (tab[0..8] = exclusive prefix, tab[9..17] = range begin), for kernels
+// that cannot spare 18 registers; returns the total.  tab is this warp's own; the caller __syncwarp()s before reuse.
+__device__ __forceinline__ int warp_candidates_smem(const GridView& g, int cx, int cy, int cz, int lane, int* tab) {
+    BlockRanges br = warp_block_ranges(g, cx, cy, cz, lane);
+    int end = __shfl_sync(0xffffffffu, br.bound, (lane + 9) & 31);
+    int len = lane < 9 ? max(end - br.bound, 0) : 0;
+    int incl = len;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane < 9) { tab[lane] = incl - len; tab[9 + lane] = br.bound; }
+    __syncwarp();
+    return __shfl_sync(0xffffffffu, incl, 8);
+}
+__device__ __forceinline__ int locate_smem(const int* tab, int j) {
+    int k = 0;
+#pragma unroll
+    for (int r = 1; r < 9; ++r) if (j >= tab[r]) k = r;
+    return tab[9 + k] + (j - tab[k]);
 }
 __device__ __forceinline__ int locate(const WarpCand& w, int j) {
     int start = 0, first = w.first[0];
@@ -408,6 +428,7 @@ __device__ __forceinline__ void grid_nearest_warp(const GridView& g, float qx, f
     warp_argmin(best_d2, best, bp);
     float hh = g.h * 0.999f;
     if (best >= 0 && best_d2 <= hh * hh) return;
+    if (prune2 <= hh * hh) return;        // everything outside the block is farther than the caller cares about
     float ext = g.h * (float)max(g.dx, max(g.dy, g.dz));
     float slack = g.h * 1e-3f + 2e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + fabsf(g.mnx) + fabsf(g.mny) + fabsf(g.mnz) + ext);
     // Phase 2: square rings of x-rows around (cy, cz), 32 rows per step — one row per lane: box-distance test, x range

@@ -434,6 +434,7 @@ __global__ void __launch_bounds__(SPFH_WARPS * 32, 3) k_spfh(GridView g, const f
     __shared__ int cnt[SPFH_WARPS][36];
     __shared__ int cq[SPFH_WARPS][64];      // in-radius candidates waiting for a dense batch of 32
     __shared__ int fq[SPFH_WARPS][64];      // pairs the screen could not decide
+    __shared__ int wtab[SPFH_WARPS][18];    // flat candidate list of the current query (warp_candidates_smem)
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int nwarps = gridDim.x * SPFH_WARPS;
     const unsigned lt = (1u << lane) - 1u;
@@ -469,29 +470,26 @@ __global__ void __launch_bounds__(SPFH_WARPS * 32, 3) k_spfh(GridView g, const f
         int cx = clampi(cell_coord(q.x, g.mnx, g.inv_h), 0, g.dx - 1);
         int cy = clampi(cell_coord(q.y, g.mny, g.inv_h), 0, g.dy - 1);
         int cz = clampi(cell_coord(q.z, g.mnz, g.inv_h), 0, g.dz - 1);
-        int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
-        for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
-            for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y) {
-                int s0 = __ldg(g.cell_begin + cell_key(g, x0, y, z));
-                int s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
-                for (int base = s0; base < s1; base += 32) {
-                    int sp = base + lane;
-                    bool in = false, want = false;
-                    if (sp < s1) {
-                        float4 p = __ldg(g.sorted + sp);
-                        in = dist2f(q.x, q.y, q.z, p.x, p.y, p.z) < r2;
-                        want = in && qfin && __float_as_int(p.w) != qi;
-                    }
-                    nb += __popc(__ballot_sync(0xffffffffu, in));          // warp-uniform count
-                    unsigned wm = __ballot_sync(0xffffffffu, want);
-                    if (wm) {
-                        if (want) cq[warp][n_cand + __popc(wm & lt)] = sp;
-                        n_cand += __popc(wm);
-                        __syncwarp();
-                        if (n_cand >= 32) { drain(32); __syncwarp(); }
-                    }
-                }
+        const int total = warp_candidates_smem(g, cx, cy, cz, lane, wtab[warp]);   // the 9 ranges as one flat list: dense batches of 32
+        for (int j0 = 0; j0 < total; j0 += 32) {
+            const int j = j0 + lane;
+            int sp = 0;
+            bool in = false, want = false;
+            if (j < total) {
+                sp = locate_smem(wtab[warp], j);
+                float4 p = __ldg(g.sorted + sp);
+                in = dist2f(q.x, q.y, q.z, p.x, p.y, p.z) < r2;
+                want = in && qfin && __float_as_int(p.w) != qi;
             }
+            nb += __popc(__ballot_sync(0xffffffffu, in));          // warp-uniform count
+            unsigned wm = __ballot_sync(0xffffffffu, want);
+            if (wm) {
+                if (want) cq[warp][n_cand + __popc(wm & lt)] = sp;
+                n_cand += __popc(wm);
+                __syncwarp();
+                if (n_cand >= 32) { drain(32); __syncwarp(); }
+            }
+        }
         if (n_cand > 0) { drain(n_cand); __syncwarp(); }
         if (n_exact > 0) {
             if (lane < n_exact) spfh_exact_one(g, sn, q, nq, fq[warp][lane], cnt[warp]);

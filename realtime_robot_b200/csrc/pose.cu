@@ -638,7 +638,11 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     DevGrid* g;
     {   // the exact 1-NN search works on any grid: reuse a cached one of comparable cell size
         float want = rtr_icp_cell(tgt);
-        if (int e = rtr_get_grid_any(tgt, want, want * 0.6f, want * 1.7f, &g)) return e;
+        // a cap of the order of the cell: make the cell the cap, so the 27-cell block holds every admissible correspondence
+        // and no query ever needs the walk beyond it (grid_nearest_ex stops after the block when prune2 <= (0.999 h)^2)
+        const float cap = p->max_correspondence_distance;
+        if (cap > want && cap < 3.f * want) want = cap;
+        if (int e = rtr_get_grid_any(tgt, want, want * (cap == want ? 1.0f : 0.6f), want * 1.7f, &g)) return e;
     }
     GridView v = rtr_view(g);
     float4* cur = nullptr; IcpState* st = nullptr; double* partials = nullptr;

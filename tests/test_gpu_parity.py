@@ -396,6 +396,25 @@ def test_icp_large_source_path_matches_oracle(api, gpu_ctx, orc, cap):
     cm.free(); cs.free()
 
 
+def test_icp_cap_sized_cells_match_oracle(api, gpu_ctx, orc):
+    # a correspondence cap between 1x and 3x the default ICP cell makes the cell the cap: the 27-cell block then holds every
+    # admissible correspondence and the search stops after it (large-source kernel, dense 20k-point target)
+    src0 = synth.icp_config(70_000, 1000)[0]
+    tgt = synth.icp_config(20_000, 1000)[0]
+    rng = np.random.default_rng(8)
+    far = src0[rng.integers(0, len(src0), 300)].copy()
+    far[:, :3] += rng.normal(0, 1.0, (300, 3)).astype(np.float32)
+    src = np.concatenate([src0, far]).astype(np.float32)
+    init = synth.rigid(1.5, -1, 2, (0.01, -0.008, 0.006), about=(0.2, 0.2, 0.4))
+    cm, cs = api.Cloud(gpu_ctx, src), api.Cloud(gpu_ctx, tgt)
+    p = default_register_params()
+    p.icp.max_iterations = 4; p.icp.max_correspondence_distance = 0.03
+    g, o = api.icp(cm, cs, p.icp, init), orc.icp(src, tgt, p.icp, init)
+    assert (g.inliers, g.iterations, g.converged) == (o.inliers, o.iterations, o.converged) and 0 < g.inliers < len(src)
+    assert np.abs(g.matrix() - o.matrix()).max() <= POSE_TOL and abs(g.fitness - o.fitness) <= FIT_TOL
+    cm.free(); cs.free()
+
+
 # ------------------------------------------------------------------ tensor-core descriptor matching
 def test_match_tensor_core_path_is_exact(api, gpu_ctx, orc, clouds, monkeypatch):
     """tcgen05 prefilter + exact re-rank + certificate (csrc/match_tc.cu) must return the oracle's indices and distances."""
