@@ -57,7 +57,9 @@ typedef struct rtr_icp_params {
     int    max_iterations;                /* 10 */
     int    force_iterations;              /* 1: ignore convergence tests, always run max_iterations (bench cfg 3) */
     float  max_correspondence_distance;   /* <= 0: unlimited (PCL default sqrt(DBL_MAX)) */
-    float  pad_;
+    int    estimator;                     /* 0: TransformationEstimationSVD, point-to-point (pcl::IterativeClosestPoint, the reference's
+                                           *    keyPointICP, function.h:112); 1: TransformationEstimationPointToPlaneLLS — the 6x6
+                                           *    A^T A / A^T b system of pcl::IterativeClosestPointWithNormals; needs rtr_normals on the TARGET */
     double mse_threshold_absolute;        /* 1e-12 (DefaultConvergenceCriteria) */
 } rtr_icp_params;
 

@@ -771,8 +771,51 @@ float fitness_impl(const P4* src, int ns, const Grid& g, const float pose[16]) {
     return cnt ? (float)(sum / (double)cnt) : FLT_MAX;
 }
 
+// x = A^-1 b by Gaussian elimination with partial pivoting (first largest |pivot|), fp64, fixed operation order
+// (stands in for Eigen's ATA.inverse() * ATb of TransformationEstimationPointToPlaneLLS); false if singular
+bool solve6(double A[6][6], double b[6], double x[6]) {
+    for (int c = 0; c < 6; ++c) {
+        int piv = c; double best = std::fabs(A[c][c]);
+        for (int r = c + 1; r < 6; ++r) { double v = std::fabs(A[r][c]); if (v > best) { best = v; piv = r; } }
+        if (!(best > 0.0)) return false;
+        if (piv != c) {
+            for (int k = 0; k < 6; ++k) { double t = A[c][k]; A[c][k] = A[piv][k]; A[piv][k] = t; }
+            double t = b[c]; b[c] = b[piv]; b[piv] = t;
+        }
+        for (int r = c + 1; r < 6; ++r) {
+            double f = A[r][c] / A[c][c];
+            for (int k = c; k < 6; ++k) A[r][k] = A[r][k] - f * A[c][k];
+            b[r] = b[r] - f * b[c];
+        }
+    }
+    for (int r = 5; r >= 0; --r) {
+        double s = b[r];
+        for (int k = r + 1; k < 6; ++k) s = s - A[r][k] * x[k];
+        x[r] = s / A[r][r];
+    }
+    return true;
+}
+
+// TransformationEstimationPointToPlaneLLS: sums[0..20] = upper triangle of A^T A (row-major), sums[21..26] = A^T b;
+// constructTransformationMatrix(alpha, beta, gamma, tx, ty, tz).  false: singular system (no step)
+bool lls_pose(const double* sums, float pose[16]) {
+    double A[6][6], b[6], x[6];
+    int k = 0;
+    for (int r = 0; r < 6; ++r) for (int c = r; c < 6; ++c) { A[r][c] = sums[k]; A[c][r] = sums[k]; ++k; }
+    for (int r = 0; r < 6; ++r) b[r] = sums[21 + r];
+    if (!solve6(A, b, x)) return false;
+    const double al = x[0], be = x[1], ga = x[2];
+    const double sa = std::sin(al), ca = std::cos(al), sb = std::sin(be), cb = std::cos(be), sg = std::sin(ga), cg = std::cos(ga);
+    identity16(pose);
+    pose[0] = (float)(cg * cb);  pose[4] = (float)(-sg * ca + cg * sb * sa);  pose[8]  = (float)(sg * sa + cg * sb * ca);   pose[12] = (float)x[3];
+    pose[1] = (float)(sg * cb);  pose[5] = (float)(cg * ca + sg * sb * sa);   pose[9]  = (float)(-cg * sa + sg * sb * ca);  pose[13] = (float)x[4];
+    pose[2] = (float)(-sb);      pose[6] = (float)(cb * sa);                  pose[10] = (float)(cb * ca);                  pose[14] = (float)x[5];
+    return true;
+}
+
 // IterativeClosestPoint::computeTransformation + DefaultConvergenceCriteria (App. A.6)
-void icp_impl(const P4* src, int ns, const P4* tgt, int nt, const rtr_icp_params* p, const float* init, rtr_pose_result* res) {
+void icp_impl(const P4* src, int ns, const P4* tgt, int nt, const rtr_icp_params* p, const float* init, rtr_pose_result* res,
+              const P4* tgt_normals = nullptr) {
     std::memset(res, 0, sizeof(*res));
     float final_[16];
     if (init) std::memcpy(final_, init, sizeof(final_)); else identity16(final_);
@@ -807,10 +850,32 @@ void icp_impl(const P4* src, int ns, const P4* tgt, int nt, const rtr_icp_params
         }
         ss[0] = s0; ss[1] = s1; ss[2] = s2; st[0] = t0; st[1] = t1; st[2] = t2;
         m[0][0] = m00; m[0][1] = m01; m[0][2] = m02; m[1][0] = m10; m[1][1] = m11; m[1][2] = m12; m[2][0] = m20; m[2][1] = m21; m[2][2] = m22;
+        float step[16];
+        if (p->estimator == 1) {
+            // point-to-plane (IterativeClosestPointWithNormals / TransformationEstimationPointToPlaneLLS): 6x6 A^T A, A^T b in
+            // fp64 from the fp32 points and target normals; correspondences with a non-finite normal are skipped
+            double S[27]; for (int k = 0; k < 27; ++k) S[k] = 0; sumd = 0; cnt = 0;
+            for (int i = 0; i < ns; ++i) {
+                int b; float d2; g.nearest(cur[i], b, d2);
+                if (b < 0 || (double)d2 > dmax2) continue;
+                const P4 nn = tgt_normals[b];
+                if (!(std::isfinite(nn.x) && std::isfinite(nn.y) && std::isfinite(nn.z))) continue;
+                const double sx = cur[i].x, sy = cur[i].y, sz = cur[i].z, dx = tgt[b].x, dy = tgt[b].y, dz = tgt[b].z, nx = nn.x, ny = nn.y, nz = nn.z;
+                const double v[6] = {nz * sy - ny * sz, nx * sz - nz * sx, ny * sx - nx * sy, nx, ny, nz};
+                const double dd = ((nx * dx + ny * dy) + nz * dz) - ((nx * sx + ny * sy) + nz * sz);
+                int k = 0;
+                for (int r = 0; r < 6; ++r) for (int c = r; c < 6; ++c) S[k++] += v[r] * v[c];
+                for (int r = 0; r < 6; ++r) S[21 + r] += v[r] * dd;
+                sumd += (double)d2; ++cnt;
+            }
+            res->inliers = (int)cnt;
+            if (cnt < 3) { state = 0; break; }
+            if (!lls_pose(S, step)) { state = 0; break; }
+        } else {
         res->inliers = (int)cnt;
         if (cnt < 3) { state = 0; break; }            // CONVERGENCE_CRITERIA_NO_CORRESPONDENCES
-        float step[16];
         horn_pose(ss, st, m, (double)cnt, step);
+        }
         for (int i = 0; i < ns; ++i) cur[i] = xform(step, cur[i]);
         matmul4(step, final_, final_);
         ++it;
@@ -934,6 +999,11 @@ int orc_hypothesis(const float* src_xyz1, int ns, const float* tgt_xyz1, int nt,
 void orc_icp(const float* src_xyz1, int ns, const float* tgt_xyz1, int nt, const rtr_icp_params* p, const float* init16,
              rtr_pose_result* res) {
     icp_impl((const P4*)src_xyz1, ns, (const P4*)tgt_xyz1, nt, p, init16, res);
+}
+// estimator 1 (point-to-plane) needs the target's normals (n x 4 floats, as orc_normals writes them)
+void orc_icp_normals(const float* src_xyz1, int ns, const float* tgt_xyz1, int nt, const float* tgt_normals4, const rtr_icp_params* p,
+                     const float* init16, rtr_pose_result* res) {
+    icp_impl((const P4*)src_xyz1, ns, (const P4*)tgt_xyz1, nt, p, init16, res, (const P4*)tgt_normals4);
 }
 
 // least-squares rigid pose from explicit pairs (for cross-checking Horn against numpy's Kabsch)

@@ -135,11 +135,16 @@ def hypothesis(src, tgt, knn, params: RansacParams, h: int):
     return ok, s6, pose.reshape(4, 4).T.copy()
 
 
-def icp(src, tgt, params: IcpParams, init=None) -> PoseResult:
+def icp(src, tgt, params: IcpParams, init=None, tgt_normals=None) -> PoseResult:
     src, tgt = _f(src), _f(tgt)
     res = PoseResult()
     ini = None if init is None else np.ascontiguousarray(np.asarray(init, dtype=np.float32).reshape(4, 4).T).reshape(16)
-    lib().orc_icp(_p(src), len(src), _p(tgt), len(tgt), C.byref(params), _p(ini), C.byref(res))
+    if params.estimator == 1:
+        nrm = _f(tgt_normals)
+        assert nrm.shape == (len(tgt), 4), "estimator 1 (point-to-plane) needs the target's normals"
+        lib().orc_icp_normals(_p(src), len(src), _p(tgt), len(tgt), _p(nrm), C.byref(params), _p(ini), C.byref(res))
+    else:
+        lib().orc_icp(_p(src), len(src), _p(tgt), len(tgt), C.byref(params), _p(ini), C.byref(res))
     return res
 
 

@@ -384,12 +384,6 @@ __device__ __forceinline__ int warp_candidates_smem(const GridView& g, int cx, i
     __syncwarp();
     return __shfl_sync(0xffffffffu, incl, 8);
 }
-__device__ __forceinline__ int locate_smem(const int* tab, int j) {
-    int k = 0;
-#pragma unroll
-    for (int r = 1; r < 9; ++r) if (j >= tab[r]) k = r;
-    return tab[9 + k] + (j - tab[k]);
-}
 __device__ __forceinline__ int locate(const WarpCand& w, int j) {
     int start = 0, first = w.first[0];
 #pragma unroll

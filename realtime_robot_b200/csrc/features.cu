@@ -428,7 +428,8 @@ __device__ __forceinline__ bool spfh_screen_one(const GridView& g, const float4*
     }
     return true;
 }
-__global__ void __launch_bounds__(SPFH_WARPS * 32, 3) k_spfh(GridView g, const float4* __restrict__ sn, float r2,
+template <int MIN_CTAS>      // 3: 80 registers, 24 warps / SM (4 M points: 2 -> 14.9 ms, 3 -> 12.5 ms, 4 -> spills, no faster)
+__global__ void __launch_bounds__(SPFH_WARPS * 32, MIN_CTAS) k_spfh(GridView g, const float4* __restrict__ sn, float r2,
                                                              float* __restrict__ spfh_sorted, int use_screen,
                                                              const int* __restrict__ list, const int* __restrict__ list_count) {
     __shared__ int cnt[SPFH_WARPS][36];
@@ -471,12 +472,14 @@ __global__ void __launch_bounds__(SPFH_WARPS * 32, 3) k_spfh(GridView g, const f
         int cy = clampi(cell_coord(q.y, g.mny, g.inv_h), 0, g.dy - 1);
         int cz = clampi(cell_coord(q.z, g.mnz, g.inv_h), 0, g.dz - 1);
         const int total = warp_candidates_smem(g, cx, cy, cz, lane, wtab[warp]);   // the 9 ranges as one flat list: dense batches of 32
+        int kr = 0;                          // this lane's current range: its j only grows, so the range only advances
         for (int j0 = 0; j0 < total; j0 += 32) {
             const int j = j0 + lane;
             int sp = 0;
             bool in = false, want = false;
             if (j < total) {
-                sp = locate_smem(wtab[warp], j);
+                while (kr < 8 && j >= wtab[warp][kr + 1]) ++kr;
+                sp = wtab[warp][9 + kr] + (j - wtab[warp][kr]);
                 float4 p = __ldg(g.sorted + sp);
                 in = dist2f(q.x, q.y, q.z, p.x, p.y, p.z) < r2;
                 want = in && qfin && __float_as_int(p.w) != qi;
@@ -623,6 +626,8 @@ struct FwSmem {
     int nbc[FW_QCHUNK];
     FwEntry wq[FW_WARPS][64];       // per warp: accepted candidates of the current (query, tile), in candidate order
     int rq[FW_WARPS][64];
+    int tidx[FW_TILE];              // cell-order position of every tile entry
+    int rb[9], pre[10];             // the cell's 9 candidate ranges: begin, exclusive prefix of the lengths
 };
 __global__ void k_occupied_cells(const int* __restrict__ cell_begin, int ncells, int* __restrict__ cells, int* __restrict__ count) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -641,20 +646,49 @@ __global__ void __launch_bounds__(FW_WARPS * 32) k_fpfh_weight_tiled(GridView g,
         const int cz = c / (g.dx * g.dy), cy = (c - cz * g.dx * g.dy) / g.dx, cx = c - cz * g.dx * g.dy - cy * g.dx;
         const int qb = __ldg(g.cell_begin + c), qe = __ldg(g.cell_begin + c + 1);
         const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dx - 1);
+        // the cell's 27-block as ONE flat candidate list (9 ranges in (z, y) order), cut into tiles of FW_TILE that may span
+        // ranges: at ~35 candidates per range a tile per range meant 9 small loads and 27 barriers per cell instead of 3 and 9
+        __syncthreads();
+        if (threadIdx.x < 9) {
+            const int zi = threadIdx.x / 3, z = cz - 1 + zi, y = cy - 1 + (threadIdx.x - zi * 3);
+            int s0 = 0, s1 = 0;
+            if (z >= 0 && z < g.dz && y >= 0 && y < g.dy) {
+                s0 = __ldg(g.cell_begin + cell_key(g, x0, y, z));
+                s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
+            }
+            sm.rb[threadIdx.x] = s0;
+            sm.pre[threadIdx.x + 1] = s1 - s0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            sm.pre[0] = 0;
+            for (int r = 0; r < 9; ++r) sm.pre[r + 1] += sm.pre[r];
+        }
+        __syncthreads();
+        const int total = sm.pre[9];
         for (int q0 = qb; q0 < qe; q0 += FW_QCHUNK) {
             const int nq = min(FW_QCHUNK, qe - q0);
             __syncthreads();
             for (int e = threadIdx.x; e < nq * 33; e += blockDim.x) (&sm.acc[0][0])[e] = 0.0;
             for (int e = threadIdx.x; e < nq; e += blockDim.x) sm.nbc[e] = 0;
-            for (int z = max(cz - 1, 0); z <= min(cz + 1, g.dz - 1); ++z)
-                for (int y = max(cy - 1, 0); y <= min(cy + 1, g.dy - 1); ++y) {
-                    const int s0 = __ldg(g.cell_begin + cell_key(g, x0, y, z));
-                    const int s1 = __ldg(g.cell_begin + cell_key(g, x1, y, z) + 1);
-                    for (int t0 = s0; t0 < s1; t0 += FW_TILE) {
-                        const int nt = min(FW_TILE, s1 - t0);
+                {
+                    for (int T0 = 0; T0 < total; T0 += FW_TILE) {
+                        const int nt = min(FW_TILE, total - T0);
                         __syncthreads();
-                        for (int i = threadIdx.x; i < nt; i += blockDim.x) sm.tpos[i] = __ldg(g.sorted + t0 + i);
-                        for (int e = threadIdx.x; e < nt * 33; e += blockDim.x) sm.tsp[e] = __ldg(spfh_sorted + (size_t)t0 * 33 + e);
+                        for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+                            const int j = T0 + i;
+                            int k = 0;
+#pragma unroll
+                            for (int r = 1; r < 9; ++r) if (j >= sm.pre[r]) k = r;
+                            const int pos = sm.rb[k] + (j - sm.pre[k]);
+                            sm.tidx[i] = pos;
+                            sm.tpos[i] = __ldg(g.sorted + pos);
+                        }
+                        __syncthreads();
+                        for (int e = threadIdx.x; e < nt * 33; e += blockDim.x) {
+                            const int i = e / 33;
+                            sm.tsp[e] = __ldg(spfh_sorted + (size_t)sm.tidx[i] * 33 + (e - i * 33));
+                        }
                         __syncthreads();
                         for (int qi = warp; qi < nq; qi += FW_WARPS) {
                             const float4 q = __ldg(g.sorted + q0 + qi);
@@ -922,7 +956,7 @@ int rtr_fpfh_dev(rtr_cloud* c, float radius) {
         // RTR_SPFH_EXACT=1 sends every pair through the fp64 evaluation (the tests use it to show the fp32 screen changes nothing)
         const char* ex = getenv("RTR_SPFH_EXACT");
         int use_screen = (ex && ex[0] == '1') ? 0 : 1;
-        k_spfh<<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * 16), SPFH_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh, use_screen, nullptr, nullptr);
+        k_spfh<3><<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * 16), SPFH_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh, use_screen, nullptr, nullptr);
         RTR_LAUNCH_CHECK(ctx, "fpfh.spfh");
         if (n >= env_threshold("RTR_FPFH_TILED_MIN", 1 << 20)) {
             // one CTA per occupied cell, candidates staged through shared memory (needs many occupied cells to fill the GPU)
@@ -1005,7 +1039,7 @@ int rtr_fpfh_at_dev(rtr_cloud* c, float radius, const int* d_query_index, int nq
     RTR_MARK(ctx, "fpfh_at.cub_select");
     const char* ex = getenv("RTR_SPFH_EXACT");
     int use_screen = (ex && ex[0] == '1') ? 0 : 1;
-    k_spfh<<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * 16), SPFH_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh, use_screen, list, count);
+    k_spfh<3><<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * 16), SPFH_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh, use_screen, list, count);
     RTR_LAUNCH_CHECK(ctx, "fpfh.spfh");
     k_fpfh_weight<<<std::min(nblk(nq, FPFH_WARPS), ctx->sm_count * 16), FPFH_WARPS * 32, 0, ctx->stream>>>(v, spfh, r2, d_out, qpos, nq);
     RTR_LAUNCH_CHECK(ctx, "fpfh.weight");

@@ -265,7 +265,69 @@ struct IcpState {
 };
 
 #define ICP_THREADS 256
-#define ICP_NSUM 17   // 3 (sum s) + 3 (sum t) + 9 (sum s t^T) + 1 (sum d2) + 1 (count)
+// Running sums of one ICP iteration.  EST 0 (TransformationEstimationSVD): 3 (sum s) + 3 (sum t) + 9 (sum s t^T);
+// EST 1 (TransformationEstimationPointToPlaneLLS): the 21 upper-triangle entries of the 6x6 A^T A (row-major) + 6 of
+// A^T b, rows [n x s ; n] per correspondence.  Both end with (sum d2, count).
+template <int EST> struct IcpSums { static constexpr int N = EST ? 29 : 17; };
+#define ICP_NSUM_MAX 29
+
+template <int EST>
+__device__ __forceinline__ void icp_accumulate(double* acc, float4 q, float4 t, float4 nrm, float d2) {
+    constexpr int N = IcpSums<EST>::N;
+    const double sx = q.x, sy = q.y, sz = q.z, tx = t.x, ty = t.y, tz = t.z;
+    if (EST == 0) {
+        acc[0] += sx; acc[1] += sy; acc[2] += sz; acc[3] += tx; acc[4] += ty; acc[5] += tz;
+        acc[6] += sx * tx; acc[7] += sx * ty; acc[8] += sx * tz;
+        acc[9] += sy * tx; acc[10] += sy * ty; acc[11] += sy * tz;
+        acc[12] += sz * tx; acc[13] += sz * ty; acc[14] += sz * tz;
+    } else {
+        const double nx = nrm.x, ny = nrm.y, nz = nrm.z;
+        const double v[6] = {nz * sy - ny * sz, nx * sz - nz * sx, ny * sx - nx * sy, nx, ny, nz};
+        const double dd = ((nx * tx + ny * ty) + nz * tz) - ((nx * sx + ny * sy) + nz * sz);
+        int k = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = r; c < 6; ++c) acc[k++] += v[r] * v[c];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) acc[21 + r] += v[r] * dd;
+    }
+    acc[N - 2] += (double)d2; acc[N - 1] += 1.0;
+}
+
+// x = A^-1 b: Gaussian elimination with partial pivoting (first largest |pivot|), fp64, the oracle's operation order
+// (stands in for Eigen's ATA.inverse() * ATb); then pcl's constructTransformationMatrix(alpha, beta, gamma, tx, ty, tz)
+__device__ bool lls_pose(const double* sums, float* pose) {
+    double A[6][6], b[6], x[6];
+    int k = 0;
+    for (int r = 0; r < 6; ++r) for (int c = r; c < 6; ++c) { A[r][c] = sums[k]; A[c][r] = sums[k]; ++k; }
+    for (int r = 0; r < 6; ++r) b[r] = sums[21 + r];
+    for (int c = 0; c < 6; ++c) {
+        int piv = c; double best = fabs(A[c][c]);
+        for (int r = c + 1; r < 6; ++r) { double v = fabs(A[r][c]); if (v > best) { best = v; piv = r; } }
+        if (!(best > 0.0)) return false;
+        if (piv != c) {
+            for (int kk = 0; kk < 6; ++kk) { double t = A[c][kk]; A[c][kk] = A[piv][kk]; A[piv][kk] = t; }
+            double t = b[c]; b[c] = b[piv]; b[piv] = t;
+        }
+        for (int r = c + 1; r < 6; ++r) {
+            double f = A[r][c] / A[c][c];
+            for (int kk = c; kk < 6; ++kk) A[r][kk] = A[r][kk] - f * A[c][kk];
+            b[r] = b[r] - f * b[c];
+        }
+    }
+    for (int r = 5; r >= 0; --r) {
+        double sacc = b[r];
+        for (int kk = r + 1; kk < 6; ++kk) sacc = sacc - A[r][kk] * x[kk];
+        x[r] = sacc / A[r][r];
+    }
+    const double sa = sin(x[0]), ca = cos(x[0]), sb = sin(x[1]), cb = cos(x[1]), sg = sin(x[2]), cg = cos(x[2]);
+    for (int i = 0; i < 16; ++i) pose[i] = (i % 5 == 0) ? 1.f : 0.f;
+    pose[0] = (float)(cg * cb);  pose[4] = (float)(-sg * ca + cg * sb * sa);  pose[8]  = (float)(sg * sa + cg * sb * ca);   pose[12] = (float)x[3];
+    pose[1] = (float)(sg * cb);  pose[5] = (float)(cg * ca + sg * sb * sa);   pose[9]  = (float)(-cg * sa + sg * sb * ca);  pose[13] = (float)x[4];
+    pose[2] = (float)(-sb);      pose[6] = (float)(cb * sa);                  pose[10] = (float)(cb * ca);                  pose[14] = (float)x[5];
+    return true;
+}
 
 __global__ void k_icp_init(const float4* __restrict__ src, int n, const float* __restrict__ init_pose, const rtr_pose_result* __restrict__ init_res,
                            float4* __restrict__ cur, IcpState* __restrict__ st, unsigned* __restrict__ ticket) {
@@ -316,12 +378,15 @@ __global__ void k_icp_permute(const float4* __restrict__ cur, const float4* __re
 // partials has a fixed shape (lane-strided, then a shuffle tree) whatever CTA happens to be last.
 struct IcpSolveArgs { int max_iterations, force; double mse_abs; };
 
+template <int EST>
 __device__ void icp_solve_thread0(const double* sums, IcpState* st, const IcpSolveArgs& sa) {
-    double cnt = sums[16];
+    constexpr int N = IcpSums<EST>::N;
+    double cnt = sums[N - 1];
     st->corr = (int)cnt;
     if (cnt < 3.0) { st->done = 1; st->state = 0; return; }
     float step[16], fin[16];
-    horn_pose(&sums[0], &sums[3], &sums[6], cnt, step);
+    if (EST == 0) horn_pose(&sums[0], &sums[3], &sums[6], cnt, step);
+    else if (!lls_pose(sums, step)) { st->done = 1; st->state = 0; return; }
     for (int i = 0; i < 16; ++i) fin[i] = st->final_[i];
     matmul4(step, fin, fin);
     for (int i = 0; i < 16; ++i) { st->final_[i] = fin[i]; st->step[i] = step[i]; }
@@ -333,15 +398,18 @@ __device__ void icp_solve_thread0(const double* sums, IcpState* st, const IcpSol
         double cos_angle = 0.5 * ((double)step[0] + (double)step[5] + (double)step[10] - 1.0);
         double tsq = (double)step[12] * (double)step[12] + (double)step[13] * (double)step[13] + (double)step[14] * (double)step[14];
         if (cos_angle >= 1.0 && tsq <= 0.0) { st->done = 1; st->state = 2; return; }
-        double mse = sums[15] / cnt;
+        double mse = sums[N - 2] / cnt;
         if (fabs(mse - st->prev_mse) < sa.mse_abs) { st->done = 1; st->state = 3; return; }
         st->prev_mse = mse;
     }
 }
 
-// called by every thread of a CTA after its partials are written; nwarps = warps in the CTA (>= 1)
-__device__ void icp_last_cta_solve(const double* partials, IcpState* st, unsigned* ticket, const IcpSolveArgs& sa, double* sums /* smem[ICP_NSUM] */,
+// called by every thread of a CTA (256 threads) after its partials are written
+template <int EST>
+__device__ void icp_last_cta_solve(const double* partials, IcpState* st, unsigned* ticket, const IcpSolveArgs& sa, double* sums /* smem[N] */,
                                    int* is_last /* smem */) {
+    constexpr int N = IcpSums<EST>::N;
+    constexpr int G = 255 / N;          // row groups: 15 for 17 sums, 8 for 29
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -351,36 +419,36 @@ __device__ void icp_last_cta_solve(const double* partials, IcpState* st, unsigne
     __syncthreads();
     if (!*is_last) return;
     __threadfence();
-    // partials is an [nparts][17] matrix: thread t < 255 owns column t % 17 and the rows t / 17, t / 17 + 15, ... (adjacent
-    // threads read adjacent addresses; eight loads in flight per thread), then 17 threads fold the 15 row groups in order
-    __shared__ double grp[15][ICP_NSUM];
+    // partials is an [nparts][N] matrix: thread t < G * N owns column t % N and the rows t / N, t / N + G, ... (adjacent
+    // threads read adjacent addresses; eight loads in flight per thread), then N threads fold the G row groups in order
+    __shared__ double grp[G][N];
     const int nparts = (int)gridDim.x, t = threadIdx.x;
-    if (t < 15 * ICP_NSUM) {
-        const int k = t % ICP_NSUM, rg = t / ICP_NSUM;
+    if (t < G * N) {
+        const int k = t % N, rg = t / N;
         const double* col = partials + k;
         double v = 0;
         int b = rg;
-        for (; b + 15 * 7 < nparts; b += 15 * 8) {
+        for (; b + G * 7 < nparts; b += G * 8) {
             double x[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) x[u] = __ldcg(col + (size_t)(b + 15 * u) * ICP_NSUM);
+            for (int u = 0; u < 8; ++u) x[u] = __ldcg(col + (size_t)(b + G * u) * N);
 #pragma unroll
             for (int u = 0; u < 8; ++u) v += x[u];
         }
-        for (; b < nparts; b += 15) v += __ldcg(col + (size_t)b * ICP_NSUM);
+        for (; b < nparts; b += G) v += __ldcg(col + (size_t)b * N);
         grp[rg][k] = v;
     }
     __syncthreads();
-    if (t < ICP_NSUM) {
+    if (t < N) {
         double v = 0;
 #pragma unroll
-        for (int rg = 0; rg < 15; ++rg) v += grp[rg][t];
+        for (int rg = 0; rg < G; ++rg) v += grp[rg][t];
         sums[t] = v;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         *ticket = 0u;
-        icp_solve_thread0(sums, st, sa);
+        icp_solve_thread0<EST>(sums, st, sa);
     }
 }
 
@@ -395,19 +463,22 @@ __device__ __forceinline__ float box_dist2f(const Box6& b, float qx, float qy, f
 }
 // correspondence estimation + accumulation.  Applies the previous iteration's step first (transformCloud in place).
 // A query farther from the target's bounding box than the cap is dropped before any cell is touched.
-__global__ void __launch_bounds__(ICP_THREADS, 4) k_icp_corr(GridView g, Box6 bb, float4* __restrict__ cur, int n, IcpState* st,
-                                                           double dmax2, float prune2, double* partials, unsigned* ticket, IcpSolveArgs sa) {
+template <int EST>
+__global__ void __launch_bounds__(ICP_THREADS, 4) k_icp_corr(GridView g, Box6 bb, const float4* __restrict__ tgt_normals, float4* __restrict__ cur, int n,
+                                                           IcpState* st, double dmax2, float prune2, double* partials, unsigned* ticket,
+                                                           IcpSolveArgs sa) {
+    constexpr int N = IcpSums<EST>::N;
     __shared__ float m[16];
-    __shared__ double red[ICP_THREADS / 32][ICP_NSUM];
-    __shared__ double sums[ICP_NSUM];
+    __shared__ double red[ICP_THREADS / 32][N];
+    __shared__ double sums[N];
     __shared__ int is_last;
     if (st->done) return;
     int have = st->have_step;
     if (threadIdx.x < 16) m[threadIdx.x] = st->step[threadIdx.x];
     __syncthreads();
-    double acc[ICP_NSUM];
+    double acc[N];
 #pragma unroll
-    for (int k = 0; k < ICP_NSUM; ++k) acc[k] = 0.0;
+    for (int k = 0; k < N; ++k) acc[k] = 0.0;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         float4 q = cur[i];
@@ -417,57 +488,53 @@ __global__ void __launch_bounds__(ICP_THREADS, 4) k_icp_corr(GridView g, Box6 bb
         if (box_dist2f(bb, q.x, q.y, q.z) > prune2) b = -1;
         else grid_nearest_ex(g, q.x, q.y, q.z, prune2, b, d2, t);
         if (b >= 0 && (double)d2 <= dmax2) {
-            double sx = q.x, sy = q.y, sz = q.z, tx = t.x, ty = t.y, tz = t.z;
-            acc[0] = sx; acc[1] = sy; acc[2] = sz; acc[3] = tx; acc[4] = ty; acc[5] = tz;
-            acc[6] = sx * tx; acc[7] = sx * ty; acc[8] = sx * tz;
-            acc[9] = sy * tx; acc[10] = sy * ty; acc[11] = sy * tz;
-            acc[12] = sz * tx; acc[13] = sz * ty; acc[14] = sz * tz;
-            acc[15] = (double)d2; acc[16] = 1.0;
+            float4 nrm = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (EST == 1) nrm = __ldg(tgt_normals + b);
+            if (EST == 0 || finite3(nrm)) icp_accumulate<EST>(acc, q, t, nrm, d2);
         }
     }
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int k = 0; k < ICP_NSUM; ++k) {
+    for (int k = 0; k < N; ++k) {
         double v = warp_sum(acc[k]);
         if (lane == 0) red[warp][k] = v;
     }
     __syncthreads();
-    if (threadIdx.x < ICP_NSUM) {
+    if (threadIdx.x < N) {
         double v = 0;
 #pragma unroll
         for (int w = 0; w < ICP_THREADS / 32; ++w) v += red[w][threadIdx.x];
-        partials[(size_t)blockIdx.x * ICP_NSUM + threadIdx.x] = v;
+        partials[(size_t)blockIdx.x * N + threadIdx.x] = v;
     }
-    icp_last_cta_solve(partials, st, ticket, sa, sums, &is_last);
+    icp_last_cta_solve<EST>(partials, st, ticket, sa, sums, &is_last);
 }
 
 // Small sources (repo clouds): one WARP per source point — the lanes share the candidate scan, so the per-iteration
 // latency is set by ~9 range steps instead of ~50 dependent loads.  Each warp walks a strided list of queries and keeps
 // the 17 sums in lane 0; warps are then folded through shared memory.
 #define ICPW_WARPS 8
-__global__ void __launch_bounds__(ICPW_WARPS * 32, 4) k_icp_corr_warp(GridView g, const float4* __restrict__ tgt_pts, float4* __restrict__ cur, int n,
-                                                                   IcpState* st, double dmax2, float prune2, double* partials, unsigned* ticket,
-                                                                   IcpSolveArgs sa) {
+template <int EST>
+__global__ void __launch_bounds__(ICPW_WARPS * 32, 4) k_icp_corr_warp(GridView g, const float4* __restrict__ tgt_pts, const float4* __restrict__ tgt_normals,
+                                                                   float4* __restrict__ cur, int n, IcpState* st, double dmax2, float prune2,
+                                                                   double* partials, unsigned* ticket, IcpSolveArgs sa) {
+    constexpr int N = IcpSums<EST>::N;
     __shared__ float m[16];
-    __shared__ double red[ICPW_WARPS][ICP_NSUM];      // lane 0 of every warp accumulates its queries here, in query order
-    __shared__ double sums[ICP_NSUM];
+    __shared__ double red[ICPW_WARPS][N];      // lane 0 of every warp accumulates its queries here, in query order
+    __shared__ double sums[N];
     __shared__ int is_last;
     if (st->done) return;
     int have = st->have_step;
     if (threadIdx.x < 16) m[threadIdx.x] = st->step[threadIdx.x];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane < ICP_NSUM) red[warp][lane] = 0.0;
+    if (lane < N) red[warp][lane] = 0.0;
     __syncthreads();
     int nwarps = gridDim.x * ICPW_WARPS;
     double* acc = red[warp];
     auto add = [&](float4 q, int b, float d2, float4 t) {
         if (lane == 0 && b >= 0 && (double)d2 <= dmax2) {
-            double sx = q.x, sy = q.y, sz = q.z, tx = t.x, ty = t.y, tz = t.z;
-            acc[0] += sx; acc[1] += sy; acc[2] += sz; acc[3] += tx; acc[4] += ty; acc[5] += tz;
-            acc[6] += sx * tx; acc[7] += sx * ty; acc[8] += sx * tz;
-            acc[9] += sy * tx; acc[10] += sy * ty; acc[11] += sy * tz;
-            acc[12] += sz * tx; acc[13] += sz * ty; acc[14] += sz * tz;
-            acc[15] += (double)d2; acc[16] += 1.0;
+            float4 nrm = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (EST == 1) nrm = __ldg(tgt_normals + b);
+            if (EST == 0 || finite3(nrm)) icp_accumulate<EST>(acc, q, t, nrm, d2);
         }
     };
     if (g.n <= RTR_BRUTE_NN_MAX) {
@@ -497,13 +564,13 @@ __global__ void __launch_bounds__(ICPW_WARPS * 32, 4) k_icp_corr_warp(GridView g
         }
     }
     __syncthreads();
-    if (threadIdx.x < ICP_NSUM) {
+    if (threadIdx.x < N) {
         double v = 0;
 #pragma unroll
         for (int w = 0; w < ICPW_WARPS; ++w) v += red[w][threadIdx.x];
-        partials[(size_t)blockIdx.x * ICP_NSUM + threadIdx.x] = v;
+        partials[(size_t)blockIdx.x * N + threadIdx.x] = v;
     }
-    icp_last_cta_solve(partials, st, ticket, sa, sums, &is_last);
+    icp_last_cta_solve<EST>(partials, st, ticket, sa, sums, &is_last);
 }
 
 // last CTA of the fitness kernel: fold the (sum d2, count) partials in a fixed shape and write the result record
@@ -634,6 +701,8 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
                 rtr_pose_result* d_result) {
     rtr_context* ctx = src->ctx;
     int n = src->n;
+    if (p->estimator != 0 && p->estimator != 1) return rtr_fail("icp", "estimator must be 0 (SVD) or 1 (point-to-plane LLS)", RTR_ERR_INVALID);
+    if (p->estimator == 1 && !tgt->normals) return rtr_fail("icp", "estimator 1 (point-to-plane) needs rtr_normals on the target", RTR_ERR_NOT_READY);
     if (int e = rtr_ensure_bbox(tgt)) return e;
     DevGrid* g;
     {   // the exact 1-NN search works on any grid: reuse a cached one of comparable cell size
@@ -653,7 +722,7 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     if (int e = tmp_alloc(ctx, &ticket, 1, "icp")) return e;
     const IcpSolveArgs sa{p->max_iterations, p->force_iterations, p->mse_threshold_absolute};
     const int nbw = std::max(1, std::min(nblk(n, ICPW_WARPS), ctx->sm_count * 8));    // CTAs of the warp-per-query kernels
-    if (int e = tmp_alloc(ctx, &partials, (size_t)std::max(nb, nbw) * ICP_NSUM, "icp")) return e;
+    if (int e = tmp_alloc(ctx, &partials, (size_t)std::max(nb, nbw) * ICP_NSUM_MAX, "icp")) return e;
     k_icp_init<<<nb, ICP_THREADS, 0, ctx->stream>>>(src->pts, n, d_init_pose16, init_from_result ? d_result : nullptr, cur, st, ticket);
     RTR_LAUNCH_CHECK(ctx, "icp.init");
     const float4* src_pts = src->pts;
@@ -687,11 +756,17 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     if (p->max_correspondence_distance > 0.f) { prune2 = (float)dmax2; if ((double)prune2 < dmax2) prune2 = nextafterf(prune2, FLT_MAX); }
     // small sources: one warp per query (latency), large ones: one thread per query in cell order (throughput)
     const bool warp_per_query = n < 65536;
+    const bool plane = p->estimator == 1;
     const Box6 bb{tgt->bb_min[0], tgt->bb_min[1], tgt->bb_min[2], tgt->bb_max[0], tgt->bb_max[1], tgt->bb_max[2]};
     if (n >= 1 && tgt->n >= 1) {
         for (int it = 0; it < p->max_iterations; ++it) {
-            if (warp_per_query) k_icp_corr_warp<<<nbw, ICPW_WARPS * 32, 0, ctx->stream>>>(v, tgt->pts, cur, n, st, dmax2, prune2, partials, ticket, sa);
-            else k_icp_corr<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, bb, cur, n, st, dmax2, prune2, partials, ticket, sa);
+            if (warp_per_query) {
+                if (plane) k_icp_corr_warp<1><<<nbw, ICPW_WARPS * 32, 0, ctx->stream>>>(v, tgt->pts, tgt->normals, cur, n, st, dmax2, prune2, partials, ticket, sa);
+                else k_icp_corr_warp<0><<<nbw, ICPW_WARPS * 32, 0, ctx->stream>>>(v, tgt->pts, nullptr, cur, n, st, dmax2, prune2, partials, ticket, sa);
+            } else {
+                if (plane) k_icp_corr<1><<<nb, ICP_THREADS, 0, ctx->stream>>>(v, bb, tgt->normals, cur, n, st, dmax2, prune2, partials, ticket, sa);
+                else k_icp_corr<0><<<nb, ICP_THREADS, 0, ctx->stream>>>(v, bb, nullptr, cur, n, st, dmax2, prune2, partials, ticket, sa);
+            }
             RTR_LAUNCH_CHECK(ctx, "icp.corr");
         }
     }

@@ -13,7 +13,7 @@ class RansacParams(C.Structure):
 
 class IcpParams(C.Structure):
     _fields_ = [("max_iterations", C.c_int), ("force_iterations", C.c_int), ("max_correspondence_distance", C.c_float),
-                ("pad_", C.c_float), ("mse_threshold_absolute", C.c_double)]
+                ("estimator", C.c_int), ("mse_threshold_absolute", C.c_double)]
 
 
 class RegisterParams(C.Structure):

@@ -396,6 +396,39 @@ def test_icp_large_source_path_matches_oracle(api, gpu_ctx, orc, cap):
     cm.free(); cs.free()
 
 
+@pytest.mark.parametrize("case", ["chair1_brute", "sofa_grid", "large_source"])
+def test_icp_point_to_plane_matches_oracle(api, gpu_ctx, orc, clouds, case):
+    """estimator 1: the 6x6 A^T A / A^T b system of TransformationEstimationPointToPlaneLLS (north_star's "6x6 JtJ/Jtr"),
+    accumulated by the same warp-shuffle tree and solved by the last CTA; all three correspondence kernels (brute-force
+    warp, grid warp, thread per query), against the oracle, and it must recover a known pose in fewer iterations than SVD."""
+    if case == "large_source":
+        tgt = synth.icp_config(20_000, 1000)[0]
+        src0 = synth.icp_config(70_000, 1000)[0]
+        gt = synth.rigid(1.5, -1, 2, (0.01, -0.008, 0.006), about=(0.2, 0.2, 0.4))
+        src = synth.apply(np.linalg.inv(gt), src0)
+    else:
+        tgt = clouds("chair1" if case == "chair1_brute" else "sofa")
+        gt = synth.rigid(3, -2, 4, (0.02, -0.015, 0.01), about=(0.2, 0.2, 0.4))
+        src = synth.apply(np.linalg.inv(gt), tgt)[::2].copy()
+    cs, ct = api.Cloud(gpu_ctx, src), api.Cloud(gpu_ctx, tgt)
+    n4 = ct.normals(0.05)
+    p = default_register_params()
+    p.icp.max_iterations = 30
+    out = {}
+    for est in (0, 1):
+        p.icp.estimator = est
+        g, o = api.icp(cs, ct, p.icp), orc.icp(src, tgt, p.icp, None, n4)
+        assert (g.iterations, g.converged, g.inliers) == (o.iterations, o.converged, o.inliers), (case, est)
+        assert np.abs(g.matrix() - o.matrix()).max() <= POSE_TOL and abs(g.fitness - o.fitness) <= FIT_TOL
+        out[est] = g
+    if case != "large_source":
+        assert np.abs(out[1].matrix() - gt).max() < 1e-4 and out[1].iterations < out[0].iterations
+    ct.reset()                                               # no normals on the target: refused, not computed silently
+    with pytest.raises(Exception):
+        api.icp(cs, ct, p.icp)
+    cs.free(); ct.free()
+
+
 def test_icp_cap_sized_cells_match_oracle(api, gpu_ctx, orc):
     # a correspondence cap between 1x and 3x the default ICP cell makes the cell the cap: the 27-cell block then holds every
     # admissible correspondence and the search stops after it (large-source kernel, dense 20k-point target)

@@ -171,3 +171,21 @@ def test_icp_defaults_and_states(orc, clouds):
     far = tgt.copy(); far[:, :3] += 3
     r = orc.icp(src, far, p.icp)
     assert r.converged == 0 and r.iterations == 0 and np.array_equal(r.matrix(), np.eye(4, dtype=np.float32))
+
+
+def test_point_to_plane_icp_recovers_pose_in_fewer_iterations(orc, clouds):
+    """estimator 1 (TransformationEstimationPointToPlaneLLS restated: 6x6 normal equations, Gaussian elimination,
+    constructTransformationMatrix): on an exact rigid copy it converges to the ground truth, faster than the SVD estimator."""
+    from realtime_robot_b200.params import default_register_params
+    m = clouds("chair1")
+    gt = synth.rigid(3, -2, 4, (0.02, -0.015, 0.01), about=(0.2, 0.2, 0.4))
+    s = synth.apply(gt, m)
+    n4 = orc.normals(s, 0.05)
+    p = default_register_params()
+    p.icp.max_iterations = 30
+    res = {}
+    for est in (0, 1):
+        p.icp.estimator = est
+        res[est] = orc.icp(m, s, p.icp, None, n4)
+        assert res[est].converged and np.abs(res[est].matrix() - gt).max() < 1e-5
+    assert res[1].iterations < res[0].iterations
