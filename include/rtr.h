@@ -249,7 +249,9 @@ int rtr_register_host(rtr_context* ctx, const float* host_model_xyz1, int n_mode
 
 /* The same two calls split in an enqueue half and a wait half: _begin returns as soon as the whole registration is
  * queued on the context's stream (no host synchronisation); _end waits and returns the record.  One registration may be in
- * flight per context, so ONE host thread can keep many contexts (streams) busy: begin on each, then end on each. */
+ * flight per context, so ONE host thread can keep many contexts (streams) busy: begin on each, then end on each.
+ * The synchronous forms above (one registration, latency) queue the scene's stages on the context's second stream so they
+ * overlap the model's; the split forms (many in flight, throughput) keep one stream per registration. */
 int rtr_register_begin(rtr_cloud* model, rtr_cloud* scene, const rtr_register_params* p);
 int rtr_register_host_begin(rtr_context* ctx, const float* host_model_xyz1, int n_model, const float* host_scene_xyz1, int n_scene,
                             const rtr_register_params* p);

@@ -46,6 +46,10 @@ struct ArenaSlab { char* base; size_t cap; };
 struct rtr_context {
     int device = 0;
     cudaStream_t stream = nullptr;
+    // second stream of a registration: the scene's stages (grid, normals, Harris, FPFH) run here while the model's run on
+    // `stream`; forked and joined with the two events below inside rtr_register_begin, idle otherwise
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t fork_event = nullptr, join_event = nullptr;
     long long launches = 0;
     bool profile = false;                 // when set, every stream operation is followed by an event mark
     std::vector<ProfMark> marks;

@@ -421,6 +421,9 @@ int rtr_context_create_prio(int device, int urgency, rtr_context** out) {
     RTR_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest), "context");      // numerically lower = more urgent
     int prio = std::max(greatest, std::min(least, least - std::max(urgency, 0)));
     RTR_CHECK(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio), "context");
+    RTR_CHECK(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio), "context");
+    RTR_CHECK(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming), "context");
+    RTR_CHECK(cudaEventCreateWithFlags(&ctx->join_event, cudaEventDisableTiming), "context");
     cudaDeviceProp prop;
     RTR_CHECK(cudaGetDeviceProperties(&prop, device), "context");
     ctx->sm_count = prop.multiProcessorCount;
@@ -450,6 +453,9 @@ int rtr_context_destroy(rtr_context* ctx) {
     for (auto& e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->io_pinned) cudaFreeHost(ctx->io_pinned);
+    if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
+    if (ctx->join_event) cudaEventDestroy(ctx->join_event);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     cudaStreamDestroy(ctx->stream);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     delete ctx;

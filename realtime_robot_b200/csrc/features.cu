@@ -15,6 +15,11 @@
 static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
 // Size thresholds between the small-cloud and large-cloud kernel variants; the environment overrides exist so that the
 // tests can push a repo-sized cloud through the large-cloud kernels and compare them with the oracle.
+// persistent-grid width of the warp-per-point kernels in CTAs per SM (RTR_GRID_MULT: scheduling experiment knob)
+static inline int wide_grid_mult() {
+    static const int m = []() { const char* e = getenv("RTR_GRID_MULT"); int v = e ? atoi(e) : 16; return v > 0 ? v : 16; }();
+    return m;
+}
 static inline int env_threshold(const char* name, int dflt) {
     const char* e = getenv(name);
     return (e && e[0]) ? atoi(e) : dflt;
@@ -882,7 +887,7 @@ int rtr_normals_dev(rtr_cloud* c, float radius) {
     if (!c->normals) if (int e = dev_alloc(ctx, &c->normals, c->n, "normals")) return e;
     if (c->n > 0) {
         if (c->n <= env_threshold("RTR_WARP_PER_POINT_MAX", RTR_WARP_PER_POINT_MAX))
-            k_normals_warp<<<std::min(nblk(c->n, PW_WARPS), ctx->sm_count * 16), PW_WARPS * 32, 0, ctx->stream>>>(rtr_view(g), radius * radius, c->normals);
+            k_normals_warp<<<std::min(nblk(c->n, PW_WARPS), ctx->sm_count * wide_grid_mult()), PW_WARPS * 32, 0, ctx->stream>>>(rtr_view(g), radius * radius, c->normals);
         else
             k_normals<<<nblk(c->n, 128), 128, 0, ctx->stream>>>(rtr_view(g), radius * radius, c->normals);
         RTR_LAUNCH_CHECK(ctx, "normals");
@@ -912,7 +917,7 @@ int rtr_harris_dev(rtr_cloud* c, float radius, float threshold, int nms, int ref
     if (n > 0) {
         GridView v = rtr_view(g);
         if (n <= env_threshold("RTR_WARP_PER_POINT_MAX", RTR_WARP_PER_POINT_MAX)) {
-            int grid = std::min(nblk(n, PW_WARPS), ctx->sm_count * 16);
+            int grid = std::min(nblk(n, PW_WARPS), ctx->sm_count * wide_grid_mult());
             k_harris_response_warp<<<grid, PW_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, c->response, resp_sorted);
             RTR_LAUNCH_CHECK(ctx, "harris.response");
             k_harris_nms_warp<<<grid, PW_WARPS * 32, 0, ctx->stream>>>(v, resp_sorted, r2, threshold, nms, flags);
@@ -956,7 +961,7 @@ int rtr_fpfh_dev(rtr_cloud* c, float radius) {
         // RTR_SPFH_EXACT=1 sends every pair through the fp64 evaluation (the tests use it to show the fp32 screen changes nothing)
         const char* ex = getenv("RTR_SPFH_EXACT");
         int use_screen = (ex && ex[0] == '1') ? 0 : 1;
-        k_spfh<3><<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * 16), SPFH_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh, use_screen, nullptr, nullptr);
+        k_spfh<3><<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * wide_grid_mult()), SPFH_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh, use_screen, nullptr, nullptr);
         RTR_LAUNCH_CHECK(ctx, "fpfh.spfh");
         if (n >= env_threshold("RTR_FPFH_TILED_MIN", 1 << 20)) {
             // one CTA per occupied cell, candidates staged through shared memory (needs many occupied cells to fill the GPU)
@@ -975,7 +980,7 @@ int rtr_fpfh_dev(rtr_cloud* c, float radius) {
             int grid = std::min(std::min(g->ncells, n), ctx->sm_count * per_sm);
             k_fpfh_weight_tiled<<<grid, FW_WARPS * 32, sizeof(FwSmem), ctx->stream>>>(v, spfh, r2, c->fpfh, cells, n_cells);
         } else {
-            k_fpfh_weight<<<std::min(nblk(n, FPFH_WARPS), ctx->sm_count * 16), FPFH_WARPS * 32, 0, ctx->stream>>>(v, spfh, r2, c->fpfh, nullptr, 0);
+            k_fpfh_weight<<<std::min(nblk(n, FPFH_WARPS), ctx->sm_count * wide_grid_mult()), FPFH_WARPS * 32, 0, ctx->stream>>>(v, spfh, r2, c->fpfh, nullptr, 0);
         }
         RTR_LAUNCH_CHECK(ctx, "fpfh.weight");
     }
@@ -1030,7 +1035,7 @@ int rtr_fpfh_at_dev(rtr_cloud* c, float radius, const int* d_query_index, int nq
     k_query_positions<<<nblk(nq, 256), 256, 0, ctx->stream>>>(d_query_index, nq, inv, qpos);
     RTR_LAUNCH_CHECK(ctx, "fpfh_at.positions");
     RTR_CHECK(cudaMemsetAsync(flags, 0, (size_t)n, ctx->stream), "fpfh_at");
-    k_mark_neighbours<<<std::min(nblk(nq, PW_WARPS), ctx->sm_count * 16), PW_WARPS * 32, 0, ctx->stream>>>(v, qpos, nq, r2, flags);
+    k_mark_neighbours<<<std::min(nblk(nq, PW_WARPS), ctx->sm_count * wide_grid_mult()), PW_WARPS * 32, 0, ctx->stream>>>(v, qpos, nq, r2, flags);
     RTR_LAUNCH_CHECK(ctx, "fpfh_at.mark");
     size_t tb = 0;
     cub::DeviceSelect::Flagged(nullptr, tb, thrust::counting_iterator<int>(0), flags, list, count, n, ctx->stream);
@@ -1039,9 +1044,9 @@ int rtr_fpfh_at_dev(rtr_cloud* c, float radius, const int* d_query_index, int nq
     RTR_MARK(ctx, "fpfh_at.cub_select");
     const char* ex = getenv("RTR_SPFH_EXACT");
     int use_screen = (ex && ex[0] == '1') ? 0 : 1;
-    k_spfh<3><<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * 16), SPFH_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh, use_screen, list, count);
+    k_spfh<3><<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * wide_grid_mult()), SPFH_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh, use_screen, list, count);
     RTR_LAUNCH_CHECK(ctx, "fpfh.spfh");
-    k_fpfh_weight<<<std::min(nblk(nq, FPFH_WARPS), ctx->sm_count * 16), FPFH_WARPS * 32, 0, ctx->stream>>>(v, spfh, r2, d_out, qpos, nq);
+    k_fpfh_weight<<<std::min(nblk(nq, FPFH_WARPS), ctx->sm_count * wide_grid_mult()), FPFH_WARPS * 32, 0, ctx->stream>>>(v, spfh, r2, d_out, qpos, nq);
     RTR_LAUNCH_CHECK(ctx, "fpfh.weight");
     dev_free(ctx, inv); dev_free(ctx, qpos); dev_free(ctx, list); dev_free(ctx, count); dev_free(ctx, flags); dev_free(ctx, spfh); dev_free(ctx, temp);
     return 0;

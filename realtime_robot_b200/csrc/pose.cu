@@ -825,7 +825,10 @@ int rtr_icp(rtr_cloud* source, rtr_cloud* target, const rtr_icp_params* p, const
 // Enqueue a whole registration on the context's stream and return: no host synchronisation.  The 128-byte record is copied
 // into the context's pinned result slot by the stream itself; rtr_register_end waits for it.  One registration may be in
 // flight per context; a host thread can keep many contexts (streams) busy this way without one thread per stream.
-int rtr_register_begin(rtr_cloud* model, rtr_cloud* scene, const rtr_register_params* p) {
+// want_fork: the synchronous entry points (one registration, latency matters: 0.66 -> 0.58 ms for chair1) fork the scene's
+// stages onto the second stream; rtr_register_begin (many registrations in flight on many contexts, throughput matters:
+// 16 streams instead of 8 cost 6 % of the 8-registration step) does not.  RTR_REGISTER_FORK=0 / 1 forces either.
+static int register_begin_impl(rtr_cloud* model, rtr_cloud* scene, const rtr_register_params* p, bool want_fork) {
     if (!model || !scene || !p || model->ctx != scene->ctx) return rtr_fail("register", "bad argument", RTR_ERR_INVALID);
     rtr_context* ctx = model->ctx;
     if (ctx->register_pending) return rtr_fail("register", "a registration is already in flight on this context", RTR_ERR_INVALID);
@@ -833,12 +836,34 @@ int rtr_register_begin(rtr_cloud* model, rtr_cloud* scene, const rtr_register_pa
     RTR_CHECK(cudaSetDevice(ctx->device), "register");
     rtr_cloud* cl[2] = {model, scene};
     int* d_cnt[2] = {nullptr, nullptr};
+    // The model's and the scene's stages are independent until the descriptor matching: the scene's are enqueued on the
+    // context's second stream (fork after whatever the caller queued, e.g. the uploads; join before matching).  Every
+    // stage function launches on ctx->stream, so the stream is swapped while the scene's stages are queued.  Temporaries
+    // come from the bump arena, which hands nothing out twice inside one entry point, and the next entry point starts on
+    // `stream` after the join: no buffer is shared by the two streams.  Profiling keeps one stream (its marks time a
+    // single queue).
+    static const int fork_env = []() { const char* e = getenv("RTR_REGISTER_FORK"); return (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : -1; }();
+    const bool fork = (fork_env < 0 ? want_fork : fork_env == 1) && !ctx->profile && ctx->aux_stream;
+    cudaStream_t main_stream = ctx->stream;
+    if (fork) {
+        RTR_CHECK(cudaEventRecord(ctx->fork_event, main_stream), "register.fork");
+        RTR_CHECK(cudaStreamWaitEvent(ctx->aux_stream, ctx->fork_event, 0), "register.fork");
+    }
     for (int i = 0; i < 2; ++i) {
-        if (int e = rtr_normals_dev(cl[i], p->normal_radius)) return e;
+        if (fork && i == 1) ctx->stream = ctx->aux_stream;
+        int e = rtr_normals_dev(cl[i], p->normal_radius);
         int* d_idx = nullptr; float4* d_xyz = nullptr;
-        if (int e = rtr_harris_dev(cl[i], p->harris_radius, p->harris_threshold, p->harris_nms, p->harris_refine, &d_idx, &d_xyz, &d_cnt[i])) return e;
-        dev_free(ctx, d_idx); dev_free(ctx, d_xyz);
-        if (int e = rtr_fpfh_dev(cl[i], p->fpfh_radius)) return e;
+        if (!e) e = rtr_harris_dev(cl[i], p->harris_radius, p->harris_threshold, p->harris_nms, p->harris_refine, &d_idx, &d_xyz, &d_cnt[i]);
+        if (!e) { dev_free(ctx, d_idx); dev_free(ctx, d_xyz); e = rtr_fpfh_dev(cl[i], p->fpfh_radius); }
+        ctx->stream = main_stream;
+        if (e) {
+            if (fork) { cudaEventRecord(ctx->join_event, ctx->aux_stream); cudaStreamWaitEvent(main_stream, ctx->join_event, 0); }
+            return e;
+        }
+    }
+    if (fork) {
+        RTR_CHECK(cudaEventRecord(ctx->join_event, ctx->aux_stream), "register.join");
+        RTR_CHECK(cudaStreamWaitEvent(main_stream, ctx->join_event, 0), "register.join");
     }
     if (int e = rtr_match_dev(model, scene, p->ransac.correspondence_k)) return e;
     rtr_pose_result* d_res = nullptr;
@@ -854,6 +879,8 @@ int rtr_register_begin(rtr_cloud* model, rtr_cloud* scene, const rtr_register_pa
     return 0;
 }
 
+int rtr_register_begin(rtr_cloud* model, rtr_cloud* scene, const rtr_register_params* p) { return register_begin_impl(model, scene, p, false); }
+
 int rtr_register_end(rtr_context* ctx, rtr_pose_result* host_result) {
     if (!ctx || !host_result) return rtr_fail("register", "bad argument", RTR_ERR_INVALID);
     if (!ctx->register_pending) return rtr_fail("register", "no registration in flight on this context", RTR_ERR_INVALID);
@@ -867,27 +894,31 @@ int rtr_register_end(rtr_context* ctx, rtr_pose_result* host_result) {
 
 int rtr_register(rtr_cloud* model, rtr_cloud* scene, const rtr_register_params* p, rtr_pose_result* host_result) {
     if (!host_result) return rtr_fail("register", "bad argument", RTR_ERR_INVALID);
-    if (int e = rtr_register_begin(model, scene, p)) return e;
+    if (int e = register_begin_impl(model, scene, p, true)) return e;
     return rtr_register_end(model->ctx, host_result);
 }
 
 // host clouds in (pinned memory makes the two uploads asynchronous), record out; the device clouds live until _end
-int rtr_register_host_begin(rtr_context* ctx, const float* host_model_xyz1, int n_model, const float* host_scene_xyz1, int n_scene,
-                            const rtr_register_params* p) {
+static int register_host_begin_impl(rtr_context* ctx, const float* host_model_xyz1, int n_model, const float* host_scene_xyz1, int n_scene,
+                                    const rtr_register_params* p, bool want_fork) {
     if (!ctx) return rtr_fail("register", "bad argument", RTR_ERR_INVALID);
     if (ctx->register_pending) return rtr_fail("register", "a registration is already in flight on this context", RTR_ERR_INVALID);
     rtr_cloud *m = nullptr, *s = nullptr;
     if (int e = rtr_cloud_upload(ctx, host_model_xyz1, n_model, &m)) return e;
     if (int e = rtr_cloud_upload(ctx, host_scene_xyz1, n_scene, &s)) { rtr_cloud_free(m); return e; }
-    if (int e = rtr_register_begin(m, s, p)) { rtr_cloud_free(m); rtr_cloud_free(s); return e; }
+    if (int e = register_begin_impl(m, s, p, want_fork)) { rtr_cloud_free(m); rtr_cloud_free(s); return e; }
     ctx->pending_cloud[0] = m; ctx->pending_cloud[1] = s;
     return 0;
+}
+int rtr_register_host_begin(rtr_context* ctx, const float* host_model_xyz1, int n_model, const float* host_scene_xyz1, int n_scene,
+                            const rtr_register_params* p) {
+    return register_host_begin_impl(ctx, host_model_xyz1, n_model, host_scene_xyz1, n_scene, p, false);
 }
 
 int rtr_register_host(rtr_context* ctx, const float* host_model_xyz1, int n_model, const float* host_scene_xyz1, int n_scene,
                       const rtr_register_params* p, rtr_pose_result* host_result) {
     if (!host_result) return rtr_fail("register", "bad argument", RTR_ERR_INVALID);
-    if (int e = rtr_register_host_begin(ctx, host_model_xyz1, n_model, host_scene_xyz1, n_scene, p)) return e;
+    if (int e = register_host_begin_impl(ctx, host_model_xyz1, n_model, host_scene_xyz1, n_scene, p, true)) return e;
     return rtr_register_end(ctx, host_result);
 }
 

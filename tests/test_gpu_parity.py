@@ -712,3 +712,29 @@ def test_register_begin_end_equals_register(api, clouds):
         assert np.array_equal(a.matrix(), b.matrix()) and a.hypothesis == b.hypothesis
     for x in ms + ss:
         x.free()
+
+
+def test_cpp_host_driver_matches_ctypes_path(api, gpu_ctx, clouds, tmp_path):
+    """The C++ host mirror (realtime_robot_b200/host: pcl_compat.h + registration.h + the driver with the shape of the
+    reference's main()) goes through the same C ABI: same hypothesis / inliers as the ctypes path, and the ASCII PCD it
+    saves (RealTimeRobot.cpp:108-109) is the model under the reported pose."""
+    import re
+    import subprocess
+    from realtime_robot_b200.pcd import read_pcd_xyz
+    exe = os.path.join(ROOT, "realtime_robot_b200", "realtime_robot")
+    assert os.path.exists(exe), "build() must have produced the C++ driver"
+    out = str(tmp_path / "moved.pcd")
+    data = os.path.join(ROOT, "data", "clouds")
+    r = subprocess.run([exe, os.path.join(data, "chair1.pcd"), os.path.join(data, "mcloud.pcd"), "--out", out, "--hypotheses", "20000"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    m = re.search(r"converged (\d+)\s+hypothesis (-?\d+)\s+inliers (\d+)", r.stdout)
+    assert m, r.stdout
+    p = default_register_params()
+    p.ransac.max_iterations = 20000
+    model = clouds("chair1")
+    g = api.register_host(gpu_ctx, model, clouds("mcloud"), p)
+    assert (int(m.group(1)) != 0, int(m.group(2)), int(m.group(3))) == (g.converged != 0, g.hypothesis, g.inliers)
+    moved = read_pcd_xyz(out)
+    want = synth.apply(g.matrix().astype(np.float64), model)[:, :3]
+    assert moved.shape == want.shape and np.abs(moved - want).max() < 1e-5
