@@ -417,6 +417,7 @@ __device__ void icp_last_cta_solve(const double* partials, IcpState* st, unsigne
         *is_last = (t == gridDim.x - 1);
     }
     __syncthreads();
+    pdl_launch_dependents();    // this CTA's part is done: the next iteration's CTAs may take their places and wait while the last CTA solves
     if (!*is_last) return;
     __threadfence();
     // partials is an [nparts][N] matrix: thread t < G * N owns column t % N and the rows t / N, t / N + G, ... (adjacent
@@ -472,6 +473,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 4) k_icp_corr(GridView g, Box6 bb
     __shared__ double red[ICP_THREADS / 32][N];
     __shared__ double sums[N];
     __shared__ int is_last;
+    pdl_wait();                 // the previous iteration (or k_icp_init) has completed: st, cur, ticket are current
     if (st->done) return;
     int have = st->have_step;
     if (threadIdx.x < 16) m[threadIdx.x] = st->step[threadIdx.x];
@@ -522,6 +524,7 @@ __global__ void __launch_bounds__(ICPW_WARPS * 32, 4) k_icp_corr_warp(GridView g
     __shared__ double red[ICPW_WARPS][N];      // lane 0 of every warp accumulates its queries here, in query order
     __shared__ double sums[N];
     __shared__ int is_last;
+    pdl_wait();                 // the previous iteration (or k_icp_init) has completed: st, cur, ticket are current
     if (st->done) return;
     int have = st->have_step;
     if (threadIdx.x < 16) m[threadIdx.x] = st->step[threadIdx.x];
@@ -624,6 +627,7 @@ __global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_fitness_warp(GridView g
     __shared__ double red[ICPW_WARPS][2];
     __shared__ double sums[2];
     __shared__ int is_last;
+    pdl_wait();
     if (st->skipped) {     // pose / fitness stay RANSAC's (identity, FLT_MAX)
         if (blockIdx.x == 0 && threadIdx.x == 0) { res->iterations = 0; res->converged = 0; }
         return;
@@ -670,6 +674,7 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_fitness(GridView g, const f
     __shared__ double red[ICP_THREADS / 32][2];
     __shared__ double sums[2];
     __shared__ int is_last;
+    pdl_wait();
     if (st->skipped) {
         if (blockIdx.x == 0 && threadIdx.x == 0) { res->iterations = 0; res->converged = 0; }
         return;
@@ -761,17 +766,17 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     if (n >= 1 && tgt->n >= 1) {
         for (int it = 0; it < p->max_iterations; ++it) {
             if (warp_per_query) {
-                if (plane) k_icp_corr_warp<1><<<nbw, ICPW_WARPS * 32, 0, ctx->stream>>>(v, tgt->pts, tgt->normals, cur, n, st, dmax2, prune2, partials, ticket, sa);
-                else k_icp_corr_warp<0><<<nbw, ICPW_WARPS * 32, 0, ctx->stream>>>(v, tgt->pts, nullptr, cur, n, st, dmax2, prune2, partials, ticket, sa);
+                if (plane) launch_pdl(k_icp_corr_warp<1>, nbw, ICPW_WARPS * 32, 0, ctx->stream, v, (const float4*)tgt->pts, (const float4*)tgt->normals, cur, n, st, dmax2, prune2, partials, ticket, sa);
+                else launch_pdl(k_icp_corr_warp<0>, nbw, ICPW_WARPS * 32, 0, ctx->stream, v, (const float4*)tgt->pts, (const float4*)nullptr, cur, n, st, dmax2, prune2, partials, ticket, sa);
             } else {
-                if (plane) k_icp_corr<1><<<nb, ICP_THREADS, 0, ctx->stream>>>(v, bb, tgt->normals, cur, n, st, dmax2, prune2, partials, ticket, sa);
-                else k_icp_corr<0><<<nb, ICP_THREADS, 0, ctx->stream>>>(v, bb, nullptr, cur, n, st, dmax2, prune2, partials, ticket, sa);
+                if (plane) launch_pdl(k_icp_corr<1>, nb, ICP_THREADS, 0, ctx->stream, v, bb, (const float4*)tgt->normals, cur, n, st, dmax2, prune2, partials, ticket, sa);
+                else launch_pdl(k_icp_corr<0>, nb, ICP_THREADS, 0, ctx->stream, v, bb, (const float4*)nullptr, cur, n, st, dmax2, prune2, partials, ticket, sa);
             }
             RTR_LAUNCH_CHECK(ctx, "icp.corr");
         }
     }
-    if (warp_per_query) k_icp_fitness_warp<<<nbw, ICPW_WARPS * 32, 0, ctx->stream>>>(v, src_pts, n, st, partials, ticket, d_result, init_from_result);
-    else k_icp_fitness<<<nb, ICP_THREADS, 0, ctx->stream>>>(v, src_pts, n, st, partials, ticket, d_result, init_from_result);
+    if (warp_per_query) launch_pdl(k_icp_fitness_warp, nbw, ICPW_WARPS * 32, 0, ctx->stream, v, src_pts, n, (const IcpState*)st, partials, ticket, d_result, init_from_result);
+    else launch_pdl(k_icp_fitness, nb, ICP_THREADS, 0, ctx->stream, v, src_pts, n, (const IcpState*)st, partials, ticket, d_result, init_from_result);
     RTR_LAUNCH_CHECK(ctx, "icp.fitness");
     dev_free(ctx, cur); dev_free(ctx, src2); dev_free(ctx, st); dev_free(ctx, partials); dev_free(ctx, ticket);
     return 0;
