@@ -421,13 +421,15 @@ __device__ void icp_last_cta_solve(const double* partials, IcpState* st, unsigne
     if (!*is_last) return;
     __threadfence();
     // partials is an [nparts][N] matrix: thread t < G * N owns column t % N and the rows t / N, t / N + G, ... (adjacent
-    // threads read adjacent addresses; eight loads in flight per thread), then N threads fold the G row groups in order
+    // threads read adjacent addresses), then N threads fold the G row groups in order
     __shared__ double grp[G][N];
     const int nparts = (int)gridDim.x, t = threadIdx.x;
     if (t < G * N) {
         const int k = t % N, rg = t / N;
         const double* col = partials + k;
         double v = 0;
+        // eight loads in flight per thread, missing rows read as +0.0 (x + 0.0 == x): no tail loop of single loads, each of
+        // which would be a full round trip to L2 behind the previous add
         int b = rg;
         for (; b + G * 7 < nparts; b += G * 8) {
             double x[8];
@@ -436,7 +438,14 @@ __device__ void icp_last_cta_solve(const double* partials, IcpState* st, unsigne
 #pragma unroll
             for (int u = 0; u < 8; ++u) v += x[u];
         }
-        for (; b < nparts; b += G) v += __ldcg(col + (size_t)b * N);
+        {   // the last, partial batch: rows past the end are re-reads of the last valid row, masked to +0.0
+            double x[8];
+            const int last = nparts - 1;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] = __ldcg(col + (size_t)min(b + G * u, last) * N);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v += (b + G * u < nparts) ? x[u] : 0.0;
+        }
         grp[rg][k] = v;
     }
     __syncthreads();
@@ -726,7 +735,7 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     unsigned* ticket = nullptr;
     if (int e = tmp_alloc(ctx, &ticket, 1, "icp")) return e;
     const IcpSolveArgs sa{p->max_iterations, p->force_iterations, p->mse_threshold_absolute};
-    const int nbw = std::max(1, std::min(nblk(n, ICPW_WARPS), ctx->sm_count * 8));    // CTAs of the warp-per-query kernels
+    const int nbw = std::max(1, std::min(nblk(n, ICPW_WARPS), ctx->sm_count * 8));    // CTAs of the warp-per-query kernels (2 / 4 / 8 per SM time the same)
     if (int e = tmp_alloc(ctx, &partials, (size_t)std::max(nb, nbw) * ICP_NSUM_MAX, "icp")) return e;
     k_icp_init<<<nb, ICP_THREADS, 0, ctx->stream>>>(src->pts, n, d_init_pose16, init_from_result ? d_result : nullptr, cur, st, ticket);
     RTR_LAUNCH_CHECK(ctx, "icp.init");
