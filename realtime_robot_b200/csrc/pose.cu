@@ -10,8 +10,10 @@
 //           K2 one thread per survivor (3-point Horn fit, fp64 Jacobi); K3 one CTA per survivor, persistent over the
 //           survivor list: every thread transforms source points and scans 9 cell ranges of the target grid, inlier
 //           count / error reduced by warp shuffles; K4 one CTA: lexicographic (error, hypothesis) arg-min.
-//   ICP:    per iteration one correspondence kernel (apply previous step, exact 1-NN, 17 fp64 sums per thread ->
-//           warp-shuffle tree -> per-CTA partials) and one solve kernel (fixed-shape reduction, Horn, convergence).
+//   ICP:    per iteration ONE kernel: apply the previous step, exact 1-NN, 17 (SVD estimator) or 29 (point-to-plane 6x6
+//           A^T A / A^T b) fp64 sums per thread -> warp-shuffle tree -> per-CTA partials; the last CTA to finish folds the
+//           partials in a fixed shape, solves (Horn / 6x6 elimination) and runs the convergence tests.  Iterations are
+//           chained with programmatic dependent launch.
 #include "common.cuh"
 #include <cub/cub.cuh>
 #include <algorithm>
