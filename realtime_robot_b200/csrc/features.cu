@@ -747,7 +747,8 @@ __global__ void __launch_bounds__(FW_WARPS * 32) k_fpfh_weight_tiled(GridView g,
                                     if (nring >= 32) { consume(32); __syncwarp(); }
                                 }
                             }
-                            if (nring > 0) { consume(nring); __syncwarp(); }
+                            if (nring > 0) consume(nring);
+                            __syncwarp();               // every lane has read acc[qi][32] before lane 0 rewrites it
                             sm.acc[qi][lane] = a;
                             if (lane == 0) { sm.acc[qi][32] = a32; sm.nbc[qi] += nb; }
                         }
