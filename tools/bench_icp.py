@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """ICP @ 1 M points (BASELINE.json configs[2]) on its own: both directions, per-kernel times, result bytes.
-Development A/B aid (RTR_ICP_GROUP=0|1|2|3 selects the thread-per-query / eight-lanes-per-query kernels); the graded
+Development A/B aid (the RTR_* environment switches of DESIGN.md select variants); the graded
 numbers are bench.py's icp_1m section.  usage: bench_icp.py [--model 100000] [--scan 1000000] [--iters 50]"""
 import argparse
 import json
@@ -28,7 +28,7 @@ def main():
     q = default_register_params()
     q.icp.max_iterations = args.iters
     q.icp.force_iterations = 1
-    out = {"RTR_ICP_GROUP": os.environ.get("RTR_ICP_GROUP", "(default)")}
+    out = {"env": {k: v for k, v in os.environ.items() if k.startswith("RTR_")}}
     for label, a, b, cap in (("model_to_scan", cm, cs, 0.0), ("scan_to_model", cs, cm, 0.05), ("scan_to_model_uncapped", cs, cm, 0.0)):
         q.icp.max_correspondence_distance = cap
         for _ in range(2):
