@@ -219,10 +219,12 @@ int rtr_ransac_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_ransac_params* p, r
     if (int e = rtr_get_grid_any(tgt, p->max_correspondence_distance, p->max_correspondence_distance * 1.001f, p->max_correspondence_distance * hi_mult, &g)) return e;
     const long long CHUNK = 1 << 20;
     int cap = (int)std::min<long long>(CHUNK, h1 - h0);
-    // slices of the source per surviving hypothesis: ~512 points each, fewer when the partial arrays would get large
+    // slices of the source per surviving hypothesis, fewer when the partial arrays would get large
     // (512-point slices: two source points per thread; 2048 -> 512 took the evaluation of a 50 000-hypothesis registration
-    //  from 72 to 54 us on the repo clouds — the chain of dependent cell loads per thread is what it costs)
-    int split = std::max(1, std::min(16, (src->n + 511) / 512));
+    //  from 72 to 54 us on the repo clouds — the chain of dependent cell loads per thread is what it costs;
+    //  a 1e7 sweep keeps every SM busy with whole-cloud CTAs and prefers 2048: 5.9 ms against 6.9 ms)
+    const int slice = (h1 - h0 >= 200000) ? 2048 : 512;
+    int split = std::max(1, std::min(16, (src->n + slice - 1) / slice));
     while (split > 1 && (long long)cap * split > (1LL << 22)) split /= 2;
     int *survivors = nullptr, *count = nullptr, *pcnt = nullptr; float* poses = nullptr; double* psum = nullptr;
     if (int e = tmp_alloc(ctx, &survivors, cap, "ransac")) return e;
