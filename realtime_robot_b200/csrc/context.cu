@@ -47,6 +47,70 @@ __global__ void k_gather_sorted(const float4* __restrict__ pts, const int* __res
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Tiny clouds (<= 4096 points, <= 8192 cells: chair1, chair2, Chair_025 and every scan the reference ships): the whole
+// build in ONE CTA with keys, cell table and slots in shared memory — __syncthreads instead of six cluster barriers and no
+// trips through L2 between the phases.  Same result as the kernels below: points ordered by (cell, original index).
+//   counts -> inclusive scan (cell ends) -> scatter by atomicSub from the cell end (the table ends up holding the cell
+//   BEGINS) -> rank inside the cell by original index -> write.
+#define GB1_MAXN 4096
+#define GB1_MAXC 8192
+__global__ void __launch_bounds__(GB_THREADS)
+k_grid_build_tiny(const float4* __restrict__ pts, int n, float mnx, float mny, float mnz, float inv_h, int dx, int dy, int dz, int ncells,
+                  int* __restrict__ cell_begin, float4* __restrict__ sorted) {
+    extern __shared__ int gb1_smem[];
+    int* s_key = gb1_smem;                 // n
+    int* s_slot = gb1_smem + n;            // n
+    int* s_cell = gb1_smem + 2 * n;        // ncells + 1
+    __shared__ int warp_tot[GB_THREADS / 32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int c = t; c <= ncells; c += GB_THREADS) s_cell[c] = 0;
+    __syncthreads();
+    for (int i = t; i < n; i += GB_THREADS) {
+        float4 p = __ldg(pts + i);
+        int cx = clampi(cell_coord(p.x, mnx, inv_h), 0, dx - 1);
+        int cy = clampi(cell_coord(p.y, mny, inv_h), 0, dy - 1);
+        int cz = clampi(cell_coord(p.z, mnz, inv_h), 0, dz - 1);
+        int key = (cz * dy + cy) * dx + cx;
+        s_key[i] = key;
+        atomicAdd(s_cell + key, 1);
+    }
+    __syncthreads();
+    // inclusive scan of the counts: contiguous chunk per thread, shuffle scan of the chunk sums, warp totals through smem
+    const int per = (ncells + GB_THREADS - 1) / GB_THREADS;
+    const int c0 = min(t * per, ncells), c1 = min(c0 + per, ncells);
+    int sum = 0;
+    for (int c = c0; c < c1; ++c) sum += s_cell[c];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += v; }
+        warp_tot[lane] = w;
+    }
+    __syncthreads();
+    int run = incl - sum + (warp > 0 ? warp_tot[warp - 1] : 0);
+    for (int c = c0; c < c1; ++c) { run += s_cell[c]; s_cell[c] = run; }       // s_cell[c] = end of cell c
+    if (t == 0) s_cell[ncells] = n;
+    __syncthreads();
+    for (int i = t; i < n; i += GB_THREADS) s_slot[atomicSub(s_cell + s_key[i], 1) - 1] = i;     // unordered inside a cell; s_cell -> begins
+    __syncthreads();
+    for (int c = t; c <= ncells; c += GB_THREADS) cell_begin[c] = s_cell[c];
+    for (int pos = t; pos < n; pos += GB_THREADS) {
+        const int i = s_slot[pos];
+        const int key = s_key[i];
+        const int b = s_cell[key], e = s_cell[key + 1];
+        int rank = 0;
+        for (int q = b; q < e; ++q) rank += (s_slot[q] < i) ? 1 : 0;
+        float4 p = __ldg(pts + i);
+        p.w = __int_as_float(i);
+        sorted[b + rank] = p;
+    }
+}
+
 __global__ void __cluster_dims__(GB_CLUSTER, 1, 1) __launch_bounds__(GB_THREADS)
 k_grid_build_small(const float4* __restrict__ pts, int n, float mnx, float mny, float mnz, float inv_h, int dx, int dy, int dz, int ncells,
                    int* cell_begin, int* keys, int* cursor, int* slot, int* cta_total, float4* __restrict__ sorted) {
@@ -270,6 +334,18 @@ int rtr_get_grid(rtr_cloud* c, float cell, DevGrid** out) {
     g.mnx = c->bb_min[0]; g.mny = c->bb_min[1]; g.mnz = c->bb_min[2];
     g.ncells = g.dx * g.dy * g.dz;
     int n = c->n;
+    if (n > 0 && n <= GB1_MAXN && g.ncells <= GB1_MAXC) {
+        static bool attr = false;
+        if (!attr) { RTR_CHECK(cudaFuncSetAttribute(k_grid_build_tiny, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * GB1_MAXN + GB1_MAXC + 1) * (int)sizeof(int)), "grid"); attr = true; }
+        if (int e = dev_alloc(ctx, &g.cell_begin, (size_t)g.ncells + 1, "grid")) return e;
+        if (int e = dev_alloc(ctx, &g.sorted, n, "grid")) return e;
+        k_grid_build_tiny<<<1, GB_THREADS, (2 * (size_t)n + g.ncells + 1) * sizeof(int), ctx->stream>>>(c->pts, n, g.mnx, g.mny, g.mnz, g.inv_h, g.dx, g.dy, g.dz,
+                                                                                                     g.ncells, g.cell_begin, g.sorted);
+        RTR_LAUNCH_CHECK(ctx, "grid.build_small");
+        auto ins = c->grids.emplace(keybits, g);
+        *out = &ins.first->second;
+        return 0;
+    }
     if (n > 0 && n <= 65536 && g.ncells <= (1 << 22)) {
         int *keys = nullptr, *cursor = nullptr, *slot = nullptr, *cta_total = nullptr;
         if (int e = tmp_alloc(ctx, &cta_total, GB_CLUSTER, "grid")) return e;
