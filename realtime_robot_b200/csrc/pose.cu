@@ -273,7 +273,7 @@ struct IcpState {
 #define ICP_THREADS 256
 // Running sums of one ICP iteration.  EST 0 (TransformationEstimationSVD): 3 (sum s) + 3 (sum t) + 9 (sum s t^T);
 // EST 1 (TransformationEstimationPointToPlaneLLS): the 21 upper-triangle entries of the 6x6 A^T A (row-major) + 6 of
-// A^T b, rows [n x s ; n] per correspondence.  Both end with (sum d2, count).
+// A^T b, rows [s x n ; n] per correspondence (the linearised (R s + t - d) . n).  Both end with (sum d2, count).
 template <int EST> struct IcpSums { static constexpr int N = EST ? 29 : 17; };
 #define ICP_NSUM_MAX 29
 

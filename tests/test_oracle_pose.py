@@ -189,3 +189,30 @@ def test_point_to_plane_icp_recovers_pose_in_fewer_iterations(orc, clouds):
         res[est] = orc.icp(m, s, p.icp, None, n4)
         assert res[est].converged and np.abs(res[est].matrix() - gt).max() < 1e-5
     assert res[1].iterations < res[0].iterations
+
+
+def test_point_to_plane_step_matches_numpy_normal_equations(orc, clouds):
+    """One estimator-1 iteration == numpy: exact 1-NN pairs (cKDTree), rows [s x n ; n], right-hand sides n.(t - s),
+    numpy.linalg.solve of the 6x6 normal equations, R = Rz(gamma) Ry(beta) Rx(alpha) (constructTransformationMatrix)."""
+    from scipy.spatial import cKDTree
+    tgt = clouds("chair1")
+    gt = synth.rigid(2, -1, 3, (0.01, -0.008, 0.006), about=(0.2, 0.2, 0.4))
+    src = synth.apply(np.linalg.inv(gt), tgt)[::3].copy()
+    n4 = orc.normals(tgt, 0.05)
+    p = default_register_params()
+    p.icp.max_iterations = 1; p.icp.estimator = 1
+    r = orc.icp(src, tgt, p.icp, None, n4)
+    assert r.iterations == 1
+    _, nn = cKDTree(tgt[:, :3].astype(np.float64)).query(src[:, :3].astype(np.float64))
+    s, t, n = src[:, :3].astype(np.float64), tgt[nn, :3].astype(np.float64), n4[nn, :3].astype(np.float64)
+    ok = np.isfinite(n).all(1)
+    s, t, n = s[ok], t[ok], n[ok]
+    A = np.hstack([np.cross(s, n), n])                     # linearised (R s + t - d) . n: omega . (s x n) + t . n = (d - s) . n
+    b = (n * (t - s)).sum(1)
+    x = np.linalg.solve(A.T @ A, A.T @ b)
+    ca, sa, cb, sb, cg, sg = np.cos(x[0]), np.sin(x[0]), np.cos(x[1]), np.sin(x[1]), np.cos(x[2]), np.sin(x[2])
+    Rx = np.array([[1, 0, 0], [0, ca, -sa], [0, sa, ca]]); Ry = np.array([[cb, 0, sb], [0, 1, 0], [-sb, 0, cb]]); Rz = np.array([[cg, -sg, 0], [sg, cg, 0], [0, 0, 1]])
+    M = np.eye(4); M[:3, :3] = Rz @ Ry @ Rx; M[:3, 3] = x[3:]
+    assert np.abs(r.matrix() - M).max() < 1e-6
+    R = r.matrix()[:3, :3].astype(np.float64)
+    assert np.abs(R @ R.T - np.eye(3)).max() < 1e-6 and abs(np.linalg.det(R) - 1.0) < 1e-6
