@@ -1055,7 +1055,7 @@ void orc_register(const float* model_xyz1, int nm, const float* scene_xyz1, int 
     orc_ransac_prerejective(model_xyz1, nm, scene_xyz1, nsc, knn.data(), k, &p->ransac, &r);
     if (p->run_icp && r.converged) {      // nothing accepted -> no pose to refine (result stays identity / FLT_MAX)
         rtr_pose_result ri;
-        orc_icp(model_xyz1, nm, scene_xyz1, nsc, &p->icp, r.pose, &ri);
+        orc_icp_normals(model_xyz1, nm, scene_xyz1, nsc, ns4.data(), &p->icp, r.pose, &ri);     // the scene's normals serve estimator 1
         std::memcpy(r.pose, ri.pose, sizeof(r.pose));
         r.fitness = ri.fitness; r.iterations = ri.iterations;
         r.converged = ri.converged;

@@ -332,6 +332,19 @@ def test_register_matches_oracle(api, gpu_ctx, orc, clouds, model, iters):
     cm.free(); cs.free()
 
 
+def test_register_with_point_to_plane_refinement(api, gpu_ctx, orc, clouds):
+    # the whole registration with estimator 1: the scene's normals (computed anyway) serve the 6x6 refinement
+    m, s = clouds("chair2"), clouds("mcloud")
+    p = default_register_params()
+    p.ransac.max_iterations = 20000
+    p.icp.estimator = 1
+    g, o = api.register_host(gpu_ctx, m, s, p), orc.register(m, s, p)
+    assert (g.hypothesis, g.inliers, g.iterations, g.converged) == (o.hypothesis, o.inliers, o.iterations, o.converged)
+    assert np.abs(g.matrix() - o.matrix()).max() <= POSE_TOL and abs(g.fitness - o.fitness) <= FIT_TOL
+    p.icp.estimator = 0
+    assert bytes(api.register_host(gpu_ctx, m, s, p)) != bytes(g)
+
+
 def test_known_pose_recovery(api, gpu_ctx, clouds):
     model = clouds("T0_m8111")
     gt = synth.rigid(6, -4, 75, (0.5, -0.2, 0.1), about=(0.2, 0.2, 0.4))
