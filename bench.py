@@ -168,6 +168,7 @@ def main():
                     "(rtr_register_begin / _end); 8 = one thread per registration")
     ap.add_argument("--verbose", action="store_true", help="per-step event / wall times on stderr")
     ap.add_argument("--no-native", action="store_true", help="skip the reference-native descriptor path section")
+    ap.add_argument("--no-scene", action="store_true", help="skip the 4M-point scene section (configs[3]: normals + FPFH)")
     args = ap.parse_args()
     rank, local_rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
@@ -454,6 +455,60 @@ def main():
             cmn.free(); csn.free()
         except Exception as e:          # the headline line must survive a failure of an auxiliary section
             native_out = {"error": repr(e)}
+    # ---- configs[3]: synthetic 4 M-point scene, normals (r = .05) + FPFH (r = .08) of every point and at 100 000 keypoints.
+    #      These are the HBM-scale gather kernels; their roofline uses SURVEY 8(d)'s algorithmic bytes (16 B per point and
+    #      neighbour read, + 16 B per neighbour normal / 132 B per neighbour SPFH row, + the output row).
+    scene_out = None
+    if rank == 0 and not args.no_scene:
+        try:
+            n4m = 4_000_000
+            side = max(4.0, (-12.0 + np.sqrt(144.0 + 4.0 * (n4m / 4700.0 * 0.8))) / 2.0)
+            scene = synth.sample_rects(synth.room_rects((side, side, 3.0), n_boxes=max(4, int(side)), seed=synth.BASE_SEED), n4m, synth.BASE_SEED + 7)
+            c4 = api.Cloud(ctx, scene)
+            from realtime_robot_b200 import _lib
+            L = _lib.lib()
+
+            def run_normals():
+                c4.reset(); L.rtr_normals(c4._h, 0.05, None)
+
+            def run_fpfh():
+                c4.reset(); L.rtr_normals(c4._h, 0.05, None); L.rtr_fpfh(c4._h, 0.08, None)
+
+            def best_of(fn, reps):
+                fn(); ms = []
+                for _ in range(reps):
+                    flush_buf.fill_(1); torch.cuda.synchronize()
+                    ctx.record(2); fn(); ctx.record(3)
+                    ms.append(ctx.elapsed_ms(2, 3))
+                return min(ms)
+            ms_n, ms_f = best_of(run_normals, 3), best_of(run_fpfh, 2)
+            k5 = int(c4.radius_neighbors(0.05, counts_only=True)[0].sum())
+            cnt8 = c4.radius_neighbors(0.08, counts_only=True)[0]
+            k8 = int(cnt8.sum())
+            ctx.profile_begin(); run_fpfh(); pr = ctx.profile_end()
+
+            def roof(kernel, ms, alg):
+                ach = alg / (ms * 1e-3) / 1e9
+                return {"kernel": kernel, "bound": "hbm", "kernel_ms": round(ms, 3), "algorithmic_bytes": alg, "achieved": ach,
+                        "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": peak_src}
+            vox = np.floor(scene[:, :3] / 0.06).astype(np.int64)
+            _, first = np.unique(vox[:, 0] * 1_000_003 + vox[:, 1] * 1009 + vox[:, 2], return_index=True)
+            qidx = np.sort(np.random.default_rng(synth.BASE_SEED + 3).choice(first, min(100_000, len(first)), replace=False)).astype(np.int32)
+            c4.fpfh_at(0.08, qidx)
+            ctx.sync(); ctx.record(2); c4.fpfh_at(0.08, qidx); ctx.record(3)
+            scene_out = {"workload": "configs[3]: synthetic 4M-point room (4700 pts/m2, 1 mm noise); grid build + normals r=.05; + FPFH r=.08 of every "
+                                     "point; FPFH at 100 000 keypoints on the full surface (rtr_fpfh_at, host indices in, rows out)",
+                         "points": n4m, "normals_ms_incl_grid": round(ms_n, 3), "normals_plus_fpfh_ms": round(ms_f, 3),
+                         "neighbour_entries_r05": k5, "neighbour_entries_r08": k8,
+                         "fpfh_at_100k_ms": round(ctx.elapsed_ms(2, 3), 3), "fpfh_at_neighbour_entries": int(cnt8[qidx].sum()),
+                         "roofline_normals": roof("k_normals", pr["normals"][1], 16 * (n4m + k5) + 16 * n4m),
+                         "roofline_spfh": roof("k_spfh", pr["fpfh.spfh"][1], 16 * (n4m + k8) + 16 * k8 + 132 * n4m),
+                         "roofline_fpfh_weight": roof("k_fpfh_weight_tiled", pr["fpfh.weight"][1], 16 * (n4m + k8) + 132 * k8 + 132 * n4m)}
+            c4.free()
+            del scene
+        except Exception as e:          # the headline line must survive a failure of an auxiliary section
+            scene_out = {"error": repr(e)}
+
     # ---- PCD I/O either side of the path: 1 M points, the three DATA modes, file -> device cloud
     pcd_out = None
     if rank == 0 and not args.no_icp:
@@ -502,7 +557,7 @@ def main():
                 "gpu_launches": int(launches),
                 "clocks": clocks, "roofline": roofline, "kernel_share": kernel_share, "serialised_device_ms_per_step": round(step_ms, 3),
                 "per_model_device_ms": per_model_ms, "per_model_latency_ms_alone": lat,
-                "cpu_baseline": cpu, "icp_1m": icp_out, "native_path": native_out, "pcd_io_1m": pcd_out,
+                "cpu_baseline": cpu, "icp_1m": icp_out, "scene_4m": scene_out, "native_path": native_out, "pcd_io_1m": pcd_out,
                 "wall_ms_per_step_incl_l2_flush": 1e3 * wall_res / args.steps,
                 "results": [{"model": m, "fitness": float(r.fitness), "inliers": int(r.inliers), "hypothesis": int(r.hypothesis),
                              "evaluated": int(r.evaluated), "converged": int(r.converged)} for m, r in zip(MODELS, mine)]}
