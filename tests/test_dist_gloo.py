@@ -70,3 +70,49 @@ def test_world_size_2_gloo(tmp_path):
     lines = sorted(l for o in outs for l in o.splitlines() if l.startswith("RANK"))
     assert lines[0] == "RANK 0 [0, 1, 2, 3, 4] 4 0 500"
     assert lines[1] == "RANK 1 [0, 1, 2, 3, 4] 4 500 1000"
+
+
+SHARD_WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, %r)
+    import numpy as np
+    import torch.distributed as td
+    from oracle import orc
+    from realtime_robot_b200 import dist
+    from realtime_robot_b200.params import default_register_params
+    from realtime_robot_b200.pcd import read_pcd_xyz, to_xyz1
+    td.init_process_group("gloo")
+    rank, world = td.get_rank(), td.get_world_size()
+    orc.set_threads(2)
+    m = to_xyz1(read_pcd_xyz(os.path.join(%r, "data", "clouds", "chair1.pcd")))
+    s = to_xyz1(read_pcd_xyz(os.path.join(%r, "data", "clouds", "mcloud.pcd")))
+    p = default_register_params()
+    fm, fs = orc.fpfh(m, orc.normals(m, 0.05), 0.10), orc.fpfh(s, orc.normals(s, 0.05), 0.10)
+    knn, _ = orc.match_features(fm, fs, 5)
+    H = 4000
+    p.ransac.max_iterations = H
+    full = orc.ransac(m, s, knn, p.ransac)
+    p.ransac.hypothesis_begin, p.ransac.hypothesis_end = dist.shard_hypotheses(H, rank, world)
+    mine = orc.ransac(m, s, knn, p.ransac)
+    best = dist.select_best_hypothesis(dist.all_gather_records([mine], 1))
+    same = (best.hypothesis, best.inliers) == (full.hypothesis, full.inliers) and bytes(best.pose) == bytes(full.pose) and best.fitness == full.fitness
+    print("RANK", rank, int(best.hypothesis), int(same), flush=True)
+    td.destroy_process_group()
+""")
+
+
+def test_world_size_2_gloo_hypothesis_sharded_ransac(tmp_path):
+    """The multi-GPU RANSAC algorithm end to end on CPU: each rank evaluates its hypothesis range (the oracle stands in for
+    the GPU), one all-gather of the 128-byte records, arg-min over (fitness, hypothesis) -> the unsharded winner on every rank."""
+    script = tmp_path / "w2.py"
+    script.write_text(SHARD_WORKER % (ROOT, ROOT, ROOT))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    lines = sorted(l for o in outs for l in o.splitlines() if l.startswith("RANK"))
+    assert len(lines) == 2 and lines[0].split()[2] == lines[1].split()[2] and int(lines[0].split()[2]) >= 0
+    assert lines[0].split()[3] == "1" and lines[1].split()[3] == "1", lines
