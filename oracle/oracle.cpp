@@ -23,7 +23,8 @@
 //   * point transforms are float: ((m00*x + m01*y) + m02*z) + m03, no FMA (pcl::transformPointCloud).
 //   * RANSAC draws come from a counter hash of (seed, hypothesis, draw) — PCL uses C rand(), which is not portable.
 //
-// Build: see oracle/Makefile (g++ -O2 -ffp-contract=off -fopenmp).
+// Build: see oracle/Makefile (g++ -O3 -march=native -ffp-contract=off -fno-fast-math -fopenmp; `make oracle_asan` for the
+// AddressSanitizer / UBSan build that tests/test_oracle_sanitizers.py runs).
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -1033,35 +1034,64 @@ void orc_jacobi(const double* a_in, int n, double* evals, double* evecs) {
 
 // The whole registration (rtr_register's CPU counterpart): normals -> Harris -> FPFH (both clouds) -> k-NN features
 // -> prerejective RANSAC -> ICP.  Sequencing of main(), RealTimeRobot.cpp:39-105, with the north-star stages.
-void orc_register(const float* model_xyz1, int nm, const float* scene_xyz1, int nsc, const rtr_register_params* p,
-                  rtr_pose_result* res) {
-    std::vector<float> nm4((size_t)nm * 4), ns4((size_t)nsc * 4), fm((size_t)nm * 33), fs((size_t)nsc * 33);
+// The scan side (ScanPoint: keypoints + descriptors) is built ONCE per scan and reused for every database model, as the
+// reference does (RealTimeRobot.cpp:45-60 before the loops at :62-102): orc_register_many is rtr_register_many's
+// counterpart, orc_register the one-model case of it.
+struct SceneStages { std::vector<float> normals4, fpfh; int n_keypoints = 0; };
+
+static void scene_stages(const float* scene_xyz1, int nsc, const rtr_register_params* p, SceneStages& sc) {
+    sc.normals4.assign((size_t)nsc * 4, 0.f); sc.fpfh.assign((size_t)nsc * 33, 0.f);
+    orc_normals(scene_xyz1, nsc, p->normal_radius, 0, sc.normals4.data());
+    int kps = orc_harris3d(scene_xyz1, nsc, sc.normals4.data(), p->harris_radius, p->harris_threshold, p->harris_nms, p->harris_refine, nullptr, nullptr, nullptr, 0);
+    // refinement of the counted corners (capacity 0 above skips it); run it for real so the CPU baseline pays for it
+    std::vector<int> ki(kps + 1); std::vector<float> kx((size_t)(kps + 1) * 4);
+    orc_harris3d(scene_xyz1, nsc, sc.normals4.data(), p->harris_radius, p->harris_threshold, p->harris_nms, p->harris_refine, nullptr, ki.data(), kx.data(), kps);
+    sc.n_keypoints = kps;
+    orc_fpfh(scene_xyz1, nsc, sc.normals4.data(), p->fpfh_radius, sc.fpfh.data());
+}
+
+static void register_against(const float* model_xyz1, int nm, const float* scene_xyz1, int nsc, const SceneStages& sc,
+                             const rtr_register_params* p, rtr_pose_result* res) {
+    std::vector<float> nm4((size_t)nm * 4), fm((size_t)nm * 33);
     orc_normals(model_xyz1, nm, p->normal_radius, 0, nm4.data());
-    orc_normals(scene_xyz1, nsc, p->normal_radius, 0, ns4.data());
     int kpm = orc_harris3d(model_xyz1, nm, nm4.data(), p->harris_radius, p->harris_threshold, p->harris_nms, p->harris_refine, nullptr, nullptr, nullptr, 0);
-    int kps = orc_harris3d(scene_xyz1, nsc, ns4.data(), p->harris_radius, p->harris_threshold, p->harris_nms, p->harris_refine, nullptr, nullptr, nullptr, 0);
-    // refinement of the counted corners (cap 0 above skips it); run it for real so the CPU baseline pays for it
     {
-        std::vector<int> ki(std::max(kpm, kps) + 1); std::vector<float> kx((size_t)(std::max(kpm, kps) + 1) * 4);
+        std::vector<int> ki(kpm + 1); std::vector<float> kx((size_t)(kpm + 1) * 4);
         orc_harris3d(model_xyz1, nm, nm4.data(), p->harris_radius, p->harris_threshold, p->harris_nms, p->harris_refine, nullptr, ki.data(), kx.data(), kpm);
-        orc_harris3d(scene_xyz1, nsc, ns4.data(), p->harris_radius, p->harris_threshold, p->harris_nms, p->harris_refine, nullptr, ki.data(), kx.data(), kps);
     }
     orc_fpfh(model_xyz1, nm, nm4.data(), p->fpfh_radius, fm.data());
-    orc_fpfh(scene_xyz1, nsc, ns4.data(), p->fpfh_radius, fs.data());
     int k = p->ransac.correspondence_k;
     std::vector<int> knn((size_t)nm * k);
-    orc_match_features(fm.data(), nm, fs.data(), nsc, k, knn.data(), nullptr);
+    orc_match_features(fm.data(), nm, sc.fpfh.data(), nsc, k, knn.data(), nullptr);
     rtr_pose_result r;
     orc_ransac_prerejective(model_xyz1, nm, scene_xyz1, nsc, knn.data(), k, &p->ransac, &r);
     if (p->run_icp && r.converged) {      // nothing accepted -> no pose to refine (result stays identity / FLT_MAX)
         rtr_pose_result ri;
-        orc_icp_normals(model_xyz1, nm, scene_xyz1, nsc, ns4.data(), &p->icp, r.pose, &ri);     // the scene's normals serve estimator 1
+        orc_icp_normals(model_xyz1, nm, scene_xyz1, nsc, sc.normals4.data(), &p->icp, r.pose, &ri);     // the scene's normals serve estimator 1
         std::memcpy(r.pose, ri.pose, sizeof(r.pose));
         r.fitness = ri.fitness; r.iterations = ri.iterations;
         r.converged = ri.converged;
     }
-    r.n_keypoints_src = kpm; r.n_keypoints_tgt = kps;
+    r.n_keypoints_src = kpm; r.n_keypoints_tgt = sc.n_keypoints;
     *res = r;
+}
+
+void orc_register(const float* model_xyz1, int nm, const float* scene_xyz1, int nsc, const rtr_register_params* p,
+                  rtr_pose_result* res) {
+    SceneStages sc;
+    scene_stages(scene_xyz1, nsc, p, sc);
+    register_against(model_xyz1, nm, scene_xyz1, nsc, sc, p, res);
+}
+
+// n_models database models (model_xyz1[m], model_n[m]) against one scan; res[m].model_id = m
+void orc_register_many(const float* const* model_xyz1, const int* model_n, int n_models, const float* scene_xyz1, int nsc,
+                       const rtr_register_params* p, rtr_pose_result* res) {
+    SceneStages sc;
+    scene_stages(scene_xyz1, nsc, p, sc);
+    for (int m = 0; m < n_models; ++m) {
+        register_against(model_xyz1[m], model_n[m], scene_xyz1, nsc, sc, p, &res[m]);
+        res[m].model_id = m;
+    }
 }
 
 void orc_default_register_params(rtr_register_params* p) {

@@ -189,6 +189,18 @@ def register(model, scene, params: RegisterParams) -> PoseResult:
     return res
 
 
+def register_many(models, scene, params: RegisterParams):
+    """rtr_register_many's counterpart: the scan's stages once (RealTimeRobot.cpp:45-60), then every model against it."""
+    models = [_f(m) for m in models]
+    scene = _f(scene)
+    k = len(models)
+    ptrs = (C.POINTER(C.c_float) * k)(*[_p(m) for m in models])
+    ns = (C.c_int * k)(*[len(m) for m in models])
+    res = (PoseResult * k)()
+    lib().orc_register_many(ptrs, ns, k, _p(scene), len(scene), C.byref(params), res)
+    return [PoseResult.from_buffer_copy(bytes(res[i])) for i in range(k)]
+
+
 # ------------------------------------------------------------------ reference-native descriptor path (oracle/native.cpp)
 def native_keypoint_descriptors(xyz1, kp_xyz1, params: NativeParams, with_tdf=True):
     xyz1, kp = _f(xyz1), _f(kp_xyz1)

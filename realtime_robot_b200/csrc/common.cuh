@@ -88,7 +88,10 @@ struct rtr_cloud {
     float4* normals = nullptr;   float normals_radius = -1.f;  int normals_version = 0;
     float*  response = nullptr;
     float*  fpfh = nullptr;      float fpfh_radius = -1.f;
-    int*    knn = nullptr;       float* knn_dist = nullptr;    int knn_k = 0;   int knn_target_n = 0;
+    // the k-NN correspondences name their target by identity: the handle plus the generation of its features at that time
+    int*    knn = nullptr;       float* knn_dist = nullptr;    int knn_k = 0;
+    const rtr_cloud* knn_target = nullptr;   long long knn_target_gen = -1;
+    long long feature_gen = 0;                // process-wide unique stamp, renewed whenever this cloud's FPFH rows are recomputed or dropped
     int n_keypoints = -1;
 };
 
@@ -170,6 +173,15 @@ struct TmpScope {
     TmpScope& operator=(const TmpScope&) = delete;
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: set it once per (device, kernel), under a mutex
+// (contexts may live on any device and on any host thread; ComputeTDFWithCuda always uses device 0).
+int  rtr_func_smem(const void* func, int device, int bytes);
+template <typename K> static inline int rtr_kernel_smem(K kernel, const rtr_context* ctx, size_t bytes) {
+    return rtr_func_smem((const void*)kernel, ctx->device, (int)bytes);
+}
+// cached cudaOccupancyMaxActiveBlocksPerMultiprocessor per (device, kernel, block, smem); >= 1
+int  rtr_func_occupancy(const void* func, int device, int block, size_t smem, int* per_sm);
+
 // internal API between translation units
 int  rtr_get_grid(rtr_cloud* c, float cell, DevGrid** out);          // build-or-fetch the grid that serves radius `cell`
 // a cached grid whose cell size h satisfies lo <= h <= hi (the one closest to `want`), or build one for `want`
@@ -187,6 +199,8 @@ int  rtr_match_dev(rtr_cloud* src, rtr_cloud* tgt, int k);
 int  rtr_ransac_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_ransac_params* p, rtr_pose_result* d_result);
 int  rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const float* d_init_pose16, int init_from_result,
                  rtr_pose_result* d_result);
+int  rtr_validate_register_params(const rtr_register_params* p);
+long long rtr_next_generation();          // process-wide, never repeats (a freed handle's address may be reused, its stamps are not)
 
 // launch with programmatic stream serialization (see pdl_wait below); RTR_PDL=0 falls back to ordinary launches
 template <typename... KArgs, typename... Args>

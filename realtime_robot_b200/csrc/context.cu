@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <string>
 
@@ -249,6 +250,33 @@ __global__ void k_nearest(GridView g, const float4* __restrict__ q, int nq, int*
 // ----------------------------------------------------------------------------- host
 static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
 
+long long rtr_next_generation() { static std::atomic<long long> g{0}; return ++g; }
+
+static std::mutex g_attr_mu;
+static std::map<std::pair<int, const void*>, int> g_attr_smem;            // (device, kernel) -> bytes already granted
+static std::map<std::pair<int, const void*>, int> g_attr_occ;             // (device, kernel) -> resident CTAs per SM
+int rtr_func_smem(const void* func, int device, int bytes) {
+    std::lock_guard<std::mutex> lock(g_attr_mu);
+    auto key = std::make_pair(device, func);
+    auto it = g_attr_smem.find(key);
+    if (it != g_attr_smem.end() && it->second >= bytes) return 0;
+    RTR_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), "smem.attr");
+    g_attr_smem[key] = bytes;
+    return 0;
+}
+int rtr_func_occupancy(const void* func, int device, int block, size_t smem, int* per_sm) {
+    std::lock_guard<std::mutex> lock(g_attr_mu);
+    auto key = std::make_pair(device, func);
+    auto it = g_attr_occ.find(key);
+    if (it != g_attr_occ.end()) { *per_sm = it->second; return 0; }
+    int v = 0;
+    RTR_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, func, block, smem), "occupancy");
+    v = std::max(v, 1);
+    g_attr_occ[key] = v;
+    *per_sm = v;
+    return 0;
+}
+
 GridView rtr_view(const DevGrid* g) {
     GridView v;
     v.inv_h = g->inv_h; v.h = g->h; v.mnx = g->mnx; v.mny = g->mny; v.mnz = g->mnz;
@@ -290,8 +318,8 @@ void rtr_invalidate(rtr_cloud* c) {
     c->grids.clear();
     dev_free(ctx, c->normals); c->normals = nullptr; c->normals_radius = -1.f; c->normals_version++;
     dev_free(ctx, c->response); c->response = nullptr;
-    dev_free(ctx, c->fpfh); c->fpfh = nullptr; c->fpfh_radius = -1.f;
-    dev_free(ctx, c->knn); c->knn = nullptr; dev_free(ctx, c->knn_dist); c->knn_dist = nullptr; c->knn_k = 0;
+    dev_free(ctx, c->fpfh); c->fpfh = nullptr; c->fpfh_radius = -1.f; c->feature_gen = rtr_next_generation();
+    dev_free(ctx, c->knn); c->knn = nullptr; dev_free(ctx, c->knn_dist); c->knn_dist = nullptr; c->knn_k = 0; c->knn_target = nullptr;
     c->n_keypoints = -1;
 }
 
@@ -305,6 +333,8 @@ float rtr_icp_cell(const rtr_cloud* c) {
 }
 
 int rtr_get_grid(rtr_cloud* c, float cell, DevGrid** out) {
+    // a zero / negative / non-finite cell would never satisfy the dimension caps below (h *= 1.25 keeps 0 at 0)
+    if (!(cell > 0.f) || !std::isfinite(cell)) return rtr_fail("grid", "cell size (search radius) must be finite and > 0", RTR_ERR_INVALID);
     int keybits;
     memcpy(&keybits, &cell, 4);
     auto it = c->grids.find(keybits);
@@ -335,8 +365,7 @@ int rtr_get_grid(rtr_cloud* c, float cell, DevGrid** out) {
     g.ncells = g.dx * g.dy * g.dz;
     int n = c->n;
     if (n > 0 && n <= GB1_MAXN && g.ncells <= GB1_MAXC) {
-        static bool attr = false;
-        if (!attr) { RTR_CHECK(cudaFuncSetAttribute(k_grid_build_tiny, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * GB1_MAXN + GB1_MAXC + 1) * (int)sizeof(int)), "grid"); attr = true; }
+        if (int e = rtr_kernel_smem(k_grid_build_tiny, ctx, (2 * GB1_MAXN + GB1_MAXC + 1) * sizeof(int))) return e;
         if (int e = dev_alloc(ctx, &g.cell_begin, (size_t)g.ncells + 1, "grid")) return e;
         if (int e = dev_alloc(ctx, &g.sorted, n, "grid")) return e;
         k_grid_build_tiny<<<1, GB_THREADS, (2 * (size_t)n + g.ncells + 1) * sizeof(int), ctx->stream>>>(c->pts, n, g.mnx, g.mny, g.mnz, g.inv_h, g.dx, g.dy, g.dz,

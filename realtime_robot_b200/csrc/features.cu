@@ -972,12 +972,9 @@ int rtr_fpfh_dev(rtr_cloud* c, float radius) {
             RTR_CHECK(cudaMemsetAsync(n_cells, 0, sizeof(int), ctx->stream), "fpfh");
             k_occupied_cells<<<nblk(g->ncells, 256), 256, 0, ctx->stream>>>(g->cell_begin, g->ncells, cells, n_cells);
             RTR_LAUNCH_CHECK(ctx, "fpfh.cells");
-            static int per_sm = 0;        // persistent CTAs: exactly as many as are resident at once (a partial second wave would idle most SMs)
-            if (!per_sm) {
-                RTR_CHECK(cudaFuncSetAttribute(k_fpfh_weight_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwSmem)), "fpfh");
-                RTR_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fpfh_weight_tiled, FW_WARPS * 32, sizeof(FwSmem)), "fpfh");
-                per_sm = std::max(per_sm, 1);
-            }
+            int per_sm = 1;               // persistent CTAs: exactly as many as are resident at once (a partial second wave would idle most SMs)
+            if (int e = rtr_kernel_smem(k_fpfh_weight_tiled, ctx, sizeof(FwSmem))) return e;
+            if (int e = rtr_func_occupancy((const void*)k_fpfh_weight_tiled, ctx->device, FW_WARPS * 32, sizeof(FwSmem), &per_sm)) return e;
             int grid = std::min(std::min(g->ncells, n), ctx->sm_count * per_sm);
             k_fpfh_weight_tiled<<<grid, FW_WARPS * 32, sizeof(FwSmem), ctx->stream>>>(v, spfh, r2, c->fpfh, cells, n_cells);
         } else {
@@ -987,6 +984,7 @@ int rtr_fpfh_dev(rtr_cloud* c, float radius) {
     }
     dev_free(ctx, spfh);
     c->fpfh_radius = radius;
+    c->feature_gen = rtr_next_generation();
     // features changed: cached correspondences are stale
     dev_free(ctx, c->knn); c->knn = nullptr; dev_free(ctx, c->knn_dist); c->knn_dist = nullptr; c->knn_k = 0;
     return 0;
@@ -1062,7 +1060,7 @@ int rtr_match_dev(rtr_cloud* src, rtr_cloud* tgt, int k) {
     if (int e = dev_alloc(ctx, &src->knn, (size_t)src->n * k, "match")) return e;
     if (int e = dev_alloc(ctx, &src->knn_dist, (size_t)src->n * k, "match")) return e;
     if (src->n > 0) if (int e = match_dispatch(ctx, src->fpfh, src->n, tgt->fpfh, tgt->n, k, src->knn, src->knn_dist, nullptr)) return e;
-    src->knn_k = k; src->knn_target_n = tgt->n;
+    src->knn_k = k; src->knn_target = tgt; src->knn_target_gen = tgt->feature_gen;
     return 0;
 }
 

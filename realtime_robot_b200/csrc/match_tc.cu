@@ -557,15 +557,11 @@ int rtr_match_tc_dev(rtr_context* ctx, const float* fa, int ns, const float* fb,
     RTR_LAUNCH_CHECK(ctx, "match.tc_prep");
     k_tc_prep<<<nblk((long long)tgt_tiles * TC_TILE, 128), 128, 0, ctx->stream>>>(fb, nt, tgt_tiles * TC_TILE, 1, mu, b_tiles, b_norms, d_nbmax);
     RTR_LAUNCH_CHECK(ctx, "match.tc_prep");
-    static bool attr_set = false;
     size_t smem = sizeof(TcSmem);
-    if (!attr_set) {
-        RTR_CHECK(cudaFuncSetAttribute(k_tc_match<16, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "match.tc");
-        RTR_CHECK(cudaFuncSetAttribute(k_tc_match<16, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "match.tc");
-        RTR_CHECK(cudaFuncSetAttribute(k_tc_match<16, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "match.tc");
-        RTR_CHECK(cudaFuncSetAttribute(k_tc_match<16, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "match.tc");
-        attr_set = true;
-    }
+    if (int e = rtr_kernel_smem(k_tc_match<16, 1, false>, ctx, smem)) return e;
+    if (int e = rtr_kernel_smem(k_tc_match<16, 2, false>, ctx, smem)) return e;
+    if (int e = rtr_kernel_smem(k_tc_match<16, 1, true>, ctx, smem)) return e;
+    if (int e = rtr_kernel_smem(k_tc_match<16, 2, true>, ctx, smem)) return e;
     // RTR_MATCH_CLUSTER=1: pairs of source tiles share the target-tile stream through cluster multicast (half the L2 -> SM
     // traffic).  Off by default: since loads stopped waiting for the epilogue the kernel is bound by MMA + epilogue, the two
     // variants time the same (7.6 ms at 262144 x 65536), and independent CTAs need no gang scheduling.

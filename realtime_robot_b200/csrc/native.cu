@@ -455,15 +455,26 @@ static int nat_pairs(rtr_context* ctx, const NatDesc& dm, const NatDesc& ds, con
     if (npairs == 0) return 0;
     float4* scratch = nullptr;
     if (int e = tmp_alloc(ctx, &scratch, (size_t)npairs * ds.cap, "native")) return e;
-    static bool attr = false;
     size_t smem = 27000 * 4 + NAT_WORDS * 4 + NAT_LIST * 4;
-    if (!attr) { RTR_CHECK(cudaFuncSetAttribute(k_native_pair_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "native"); attr = true; }
+    if (int e = rtr_kernel_smem(k_native_pair_score, ctx, smem)) return e;
     NatSweep final_sw = nat_sweep();
     k_native_pair_score<<<npairs, NAT_THREADS, smem, ctx->stream>>>(dm.kps, dm.n_kp, ds.kps, ds.n_kp, dm.tdf, ds.occ, ds.occ_count, ds.cap, scratch,
                                                                      final_sw, p->tdf_half, p->resolution, p->quirk_skip_first_voxel,
                                                                      p->quirk_running_score, *score, *best, *transform);
     RTR_LAUNCH_CHECK(ctx, "native.pair_score");
     dev_free(ctx, scratch);
+    return 0;
+}
+
+// A zero / negative / NaN half-width or resolution would hang the grid sizing or index outside the TDF; the pair sweep
+// (k_native_pair_score) and the consensus are written for the reference's 30^3 TDF (KeyPoint::grid_value[27000]).
+static int nat_validate(const rtr_native_params* p, bool need_dim30) {
+    if (!(p->resolution > 0.f) || !std::isfinite(p->resolution) || !(p->occ_half > 0.f) || !std::isfinite(p->occ_half) ||
+        !(p->tdf_half > 0.f) || !std::isfinite(p->tdf_half))
+        return rtr_fail("native", "resolution, occ_half and tdf_half must be finite and > 0", RTR_ERR_INVALID);
+    int dim = (int)(p->tdf_half / p->resolution * 2);
+    if (dim < 1 || dim > RTR_TDF_DIM) return rtr_fail("native", "tdf_half / resolution * 2 must be in 1..30", RTR_ERR_INVALID);
+    if (need_dim30 && dim != RTR_TDF_DIM) return rtr_fail("native", "the pair sweep needs tdf_half / resolution * 2 == 30 (KeyPoint::grid_value[27000])", RTR_ERR_INVALID);
     return 0;
 }
 
@@ -479,6 +490,7 @@ void rtr_native_default_params(rtr_native_params* p) {
 int rtr_native_keypoint_descriptors(rtr_cloud* c, const float* host_kp_xyz1, int n_kp, const rtr_native_params* p, int* host_number,
                                     int* host_occ_count, float* host_tdf, int* host_voxel_count) {
     if (!c || !p || n_kp < 0 || (n_kp > 0 && !host_kp_xyz1)) return rtr_fail("native", "bad argument", RTR_ERR_INVALID);
+    if (int e = nat_validate(p, false)) return e;
     rtr_context* ctx = c->ctx;
     TmpScope tmp_scope(ctx);
     RTR_CHECK(cudaSetDevice(ctx->device), "native");
@@ -511,6 +523,7 @@ int rtr_native_keypoint_descriptors(rtr_cloud* c, const float* host_kp_xyz1, int
 int rtr_native_pair_scores(rtr_cloud* model, const float* host_model_kp_xyz1, int km, rtr_cloud* scan, const float* host_scan_kp_xyz1,
                            int ks, const rtr_native_params* p, float* host_score, int* host_best_step, float* host_transform16) {
     if (!model || !scan || !p || km < 0 || ks < 0 || model->ctx != scan->ctx) return rtr_fail("native", "bad argument", RTR_ERR_INVALID);
+    if (int e = nat_validate(p, true)) return e;
     rtr_context* ctx = model->ctx;
     TmpScope tmp_scope(ctx);
     RTR_CHECK(cudaSetDevice(ctx->device), "native");
@@ -538,6 +551,7 @@ int rtr_native_pair_scores(rtr_cloud* model, const float* host_model_kp_xyz1, in
 
 int rtr_native_register(rtr_cloud* model, rtr_cloud* scan, const rtr_native_params* p, rtr_pose_result* host_result) {
     if (!model || !scan || !p || !host_result || model->ctx != scan->ctx) return rtr_fail("native", "bad argument", RTR_ERR_INVALID);
+    if (int e = nat_validate(p, true)) return e;
     rtr_context* ctx = model->ctx;
     TmpScope tmp_scope(ctx);
     RTR_CHECK(cudaSetDevice(ctx->device), "native");

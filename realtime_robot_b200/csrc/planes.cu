@@ -532,11 +532,7 @@ extern "C" int rtr_plane_areas(rtr_cloud* c, rtr_surface* host_surfaces, int cap
         int m = 0;
         if (n_cur <= PL_SMALL_MAX) {
             // one single-CTA launch for the rest of this plane, one host round trip
-            static bool attr_set = false;
-            if (!attr_set) {
-                RTR_CHECK(cudaFuncSetAttribute(k_plane_step_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PlaneSmall)), "planes");
-                attr_set = true;
-            }
+            if (int e = rtr_kernel_smem(k_plane_step_small, ctx, sizeof(PlaneSmall))) return e;
             k_plane_step_small<<<1, PL_FT, sizeof(PlaneSmall), ctx->stream>>>(cur, n_cur, coeffs, counts, bad, threshold, max_iterations, idx_in,
                                                                               plane_pts, next, n_in, n_rest, st);
             RTR_LAUNCH_CHECK(ctx, "planes.step_small");

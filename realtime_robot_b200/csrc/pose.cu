@@ -208,8 +208,8 @@ int rtr_ransac_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_ransac_params* p, r
     RTR_LAUNCH_CHECK(ctx, "ransac.init");
     long long h0 = p->hypothesis_begin, h1 = (p->hypothesis_end > 0) ? p->hypothesis_end : p->max_iterations;
     if (src->n < 3 || tgt->n < 1 || h1 <= h0) return 0;
-    if (!src->knn || src->knn_k < p->correspondence_k || src->knn_target_n != tgt->n)
-        return rtr_fail("ransac", "rtr_match_features(source, target, k >= correspondence_k) must run first", RTR_ERR_NOT_READY);
+    if (!src->knn || src->knn_k < p->correspondence_k || src->knn_target != tgt || src->knn_target_gen != tgt->feature_gen)
+        return rtr_fail("ransac", "rtr_match_features(source, target, k >= correspondence_k) must run first (on THIS target, after its last rtr_fpfh)", RTR_ERR_NOT_READY);
     if (!(p->max_correspondence_distance > 0.f)) return rtr_fail("ransac", "max_correspondence_distance must be > 0", RTR_ERR_INVALID);
     DevGrid* g;
     // any cached grid whose cells are at least d_max wide (and not much wider) serves the 27-cell inlier test; a large
@@ -827,6 +827,17 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
 }
 
 // ============================================================================= whole registration
+// a zero-initialised or partly filled params struct must come back as RTR_ERR_INVALID, not hang the grid sizing
+int rtr_validate_register_params(const rtr_register_params* p) {
+    auto bad = [](float v) { return !(v > 0.f) || !std::isfinite(v); };
+    if (bad(p->normal_radius) || bad(p->harris_radius) || bad(p->fpfh_radius))
+        return rtr_fail("register", "normal_radius, harris_radius and fpfh_radius must be finite and > 0", RTR_ERR_INVALID);
+    if (bad(p->ransac.max_correspondence_distance)) return rtr_fail("register", "ransac.max_correspondence_distance must be finite and > 0", RTR_ERR_INVALID);
+    if (p->ransac.correspondence_k < 1 || p->ransac.correspondence_k > 8) return rtr_fail("register", "ransac.correspondence_k must be in [1, 8]", RTR_ERR_INVALID);
+    if (p->run_icp && (p->icp.max_iterations < 0 || (p->icp.estimator != 0 && p->icp.estimator != 1)))
+        return rtr_fail("register", "icp.max_iterations must be >= 0 and icp.estimator 0 or 1", RTR_ERR_INVALID);
+    return 0;
+}
 __global__ void k_set_keypoints(rtr_pose_result* res, const int* n_src, const int* n_tgt) {
     if (threadIdx.x == 0) { res->n_keypoints_src = *n_src; res->n_keypoints_tgt = *n_tgt; }
 }
@@ -879,6 +890,7 @@ int rtr_icp(rtr_cloud* source, rtr_cloud* target, const rtr_icp_params* p, const
 // 16 streams instead of 8 cost 6 % of the 8-registration step) does not.  RTR_REGISTER_FORK=0 / 1 forces either.
 static int register_begin_impl(rtr_cloud* model, rtr_cloud* scene, const rtr_register_params* p, bool want_fork) {
     if (!model || !scene || !p || model->ctx != scene->ctx) return rtr_fail("register", "bad argument", RTR_ERR_INVALID);
+    if (int e = rtr_validate_register_params(p)) return e;
     rtr_context* ctx = model->ctx;
     if (ctx->register_pending) return rtr_fail("register", "a registration is already in flight on this context", RTR_ERR_INVALID);
     TmpScope tmp_scope(ctx);

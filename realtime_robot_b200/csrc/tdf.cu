@@ -39,23 +39,27 @@ __global__ void __launch_bounds__(TDF_THREADS) k_tdf_batch(const int* __restrict
     if (v < nvox_write) out[(size_t)g * out_stride + v] = (float)best;
 }
 
-static int tdf_launch(rtr_context* ctx, const int* d_occ, const int* d_off, int n_grids, int dim, int nvox_write, size_t out_stride, float* d_out) {
-    if (n_grids <= 0) return 0;
-    dim3 grid((nvox_write + TDF_THREADS - 1) / TDF_THREADS, n_grids);
-    k_tdf_batch<<<grid, TDF_THREADS, 0, ctx->stream>>>(d_occ, d_off, d_off + 1, dim, nvox_write, out_stride, d_out);
-    RTR_LAUNCH_CHECK(ctx, "tdf");
+// gridDim.y carries the keypoint and is limited to 65535: larger batches go in chunks
+#define TDF_MAX_GRID_Y 65535
+static int tdf_launch_chunks(rtr_context* ctx, const int* d_occ, const int* d_begin, const int* d_end, int n_grids, int dim, int nvox_write,
+                             size_t out_stride, float* d_out) {
+    for (int g0 = 0; g0 < n_grids; g0 += TDF_MAX_GRID_Y) {
+        int ng = n_grids - g0 < TDF_MAX_GRID_Y ? n_grids - g0 : TDF_MAX_GRID_Y;
+        dim3 grid((nvox_write + TDF_THREADS - 1) / TDF_THREADS, ng);
+        k_tdf_batch<<<grid, TDF_THREADS, 0, ctx->stream>>>(d_occ, d_begin + g0, d_end + g0, dim, nvox_write, out_stride, d_out + (size_t)g0 * out_stride);
+        RTR_LAUNCH_CHECK(ctx, "tdf");
+    }
     return 0;
+}
+static int tdf_launch(rtr_context* ctx, const int* d_occ, const int* d_off, int n_grids, int dim, int nvox_write, size_t out_stride, float* d_out) {
+    return tdf_launch_chunks(ctx, d_occ, d_off, d_off + 1, n_grids, dim, nvox_write, out_stride, d_out);
 }
 
 // per-grid [begin, end) triple ranges instead of a prefix array (native.cu: fixed-stride voxel lists per keypoint);
 // output stride 27000 floats = KeyPoint::grid_value
 int rtr_tdf_launch_ranges(rtr_context* ctx, const int* d_occ, const int* d_begin, const int* d_end, int n_grids, int dim, float* d_out) {
-    if (n_grids <= 0) return 0;
     int nv = dim * dim * dim;
-    dim3 grid((nv + TDF_THREADS - 1) / TDF_THREADS, n_grids);
-    k_tdf_batch<<<grid, TDF_THREADS, 0, ctx->stream>>>(d_occ, d_begin, d_end, dim, nv, (size_t)RTR_TDF_VOXELS, d_out);
-    RTR_LAUNCH_CHECK(ctx, "tdf");
-    return 0;
+    return tdf_launch_chunks(ctx, d_occ, d_begin, d_end, n_grids, dim, nv, (size_t)RTR_TDF_VOXELS, d_out);
 }
 
 // process-wide state behind the legacy entry point: device 0 (kernel.cu:43), persistent buffers, pinned staging
@@ -115,10 +119,23 @@ int ComputeTDFWithCuda(const int* voxel_grid_occ, float* voxel_grid_TDF, int vox
         return RTR_ERR_INVALID;
     }
     if (!g_legacy_ctx) {
-        if (int e = rtr_context_create(0, &g_legacy_ctx)) return e;
-        RTR_CHECK(cudaMalloc(&g_legacy_tdf, RTR_TDF_VOXELS * sizeof(float)), "ComputeTDFWithCuda");
-        RTR_CHECK(cudaMalloc(&g_legacy_off, 2 * sizeof(int)), "ComputeTDFWithCuda");
-        RTR_CHECK(cudaMallocHost(&g_legacy_pin_tdf, RTR_TDF_VOXELS * sizeof(float)), "ComputeTDFWithCuda");
+        // the context is published only once every persistent buffer exists: a failed first call leaves nothing half
+        // initialised behind (the next call starts over)
+        rtr_context* c0 = nullptr;
+        float *tdf0 = nullptr, *pin0 = nullptr; int* off0 = nullptr;
+        int e = rtr_context_create(0, &c0);
+        if (!e) e = (int)cudaMalloc(&tdf0, RTR_TDF_VOXELS * sizeof(float));
+        if (!e) e = (int)cudaMalloc(&off0, 2 * sizeof(int));
+        if (!e) e = (int)cudaMallocHost(&pin0, RTR_TDF_VOXELS * sizeof(float));
+        if (e) {
+            fprintf(stderr, "rtr[ComputeTDFWithCuda] initialisation failed (status %d)\n", e);
+            if (pin0) cudaFreeHost(pin0);
+            if (off0) cudaFree(off0);
+            if (tdf0) cudaFree(tdf0);
+            if (c0) rtr_context_destroy(c0);
+            return e;
+        }
+        g_legacy_tdf = tdf0; g_legacy_off = off0; g_legacy_pin_tdf = pin0; g_legacy_ctx = c0;
     }
     rtr_context* ctx = g_legacy_ctx;
     RTR_CHECK(cudaSetDevice(0), "ComputeTDFWithCuda");

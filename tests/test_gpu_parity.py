@@ -311,13 +311,16 @@ def test_icp_parity_and_known_translation(api, gpu_ctx, orc, clouds):
         c.free()
 
 
-@pytest.mark.parametrize("model,iters", [("chair1", 50000), ("chair2", 20000), ("Chair_025", 20000), ("desk1", 4000)])
-def test_register_matches_oracle(api, gpu_ctx, orc, clouds, model, iters):
-    m, s = clouds(model).copy(), clouds("mcloud")
+# every member of BASELINE.json configs[1], at the benched settings (50 000 hypotheses, 10 ICP iterations); desk2.pcd is
+# byte-identical to desk1.pcd in the reference
+@pytest.mark.parametrize("model", ["chair1", "chair2", "chair4", "desk1", "desk2", "desk3", "sofa", "Chair_025"])
+def test_register_matches_oracle(api, gpu_ctx, orc, clouds, model):
+    m, s = clouds("desk1" if model == "desk2" else model).copy(), clouds("mcloud")
     if model == "Chair_025":
         m[:, :3] *= np.float32(0.01)                     # units x100 (model_point.h:106-111 intends this scale)
     p = default_register_params()
-    p.ransac.max_iterations = iters
+    assert p.ransac.max_iterations == 50000 and p.icp.max_iterations == 10
+    orc.set_threads(0)                                   # all host threads: the oracle's result does not depend on the count
     g = api.register_host(gpu_ctx, m, s, p)
     o = orc.register(m, s, p)
     assert (g.hypothesis, g.inliers, g.evaluated, g.iterations, g.converged) == (o.hypothesis, o.inliers, o.evaluated, o.iterations, o.converged)
@@ -751,3 +754,76 @@ def test_cpp_host_driver_matches_ctypes_path(api, gpu_ctx, clouds, tmp_path):
     moved = read_pcd_xyz(out)
     want = synth.apply(g.matrix().astype(np.float64), model)[:, :3]
     assert moved.shape == want.shape and np.abs(moved - want).max() < 1e-5
+
+
+# ------------------------------------------------------------------ argument validation
+@pytest.mark.gpu
+def test_invalid_radii_are_rejected_not_hung(api, gpu_ctx, clouds):
+    """A zero-initialised / partly filled params struct must return RTR_ERR_INVALID (1): with a zero cell size the grid sizing
+    loop of round 1 never terminated."""
+    from realtime_robot_b200 import _lib
+    from realtime_robot_b200.params import RegisterParams, default_native_params
+    m, s = clouds("chair1"), clouds("mcloud")
+    cm, cs = api.Cloud(gpu_ctx, m), api.Cloud(gpu_ctx, s)
+    zero = RegisterParams()                                   # all fields 0
+    with pytest.raises(_lib.RtrError) as e:
+        api.register(cm, cs, zero)
+    assert e.value.code == 1
+    for field, bad in (("normal_radius", 0.0), ("harris_radius", -0.05), ("fpfh_radius", float("nan")), ("normal_radius", float("inf"))):
+        p = default_register_params()
+        setattr(p, field, bad)
+        with pytest.raises(_lib.RtrError) as e:
+            api.register(cm, cs, p)
+        assert e.value.code == 1, field
+        with pytest.raises(_lib.RtrError):
+            api.register_host(gpu_ctx, m, s, p)
+    for field, bad in (("occ_half", 0.0), ("tdf_half", -1.0), ("resolution", 0.0), ("resolution", float("nan")), ("tdf_half", 0.10)):
+        q = default_native_params()
+        setattr(q, field, bad)                                # tdf_half 0.10 -> dim 20: the pair sweep is written for 30^3
+        with pytest.raises(_lib.RtrError) as e:
+            api.native_register(cm, cs, q)
+        assert e.value.code == 1, field
+    q = default_native_params()
+    q.tdf_half = 0.10                                         # a 20^3 TDF alone is fine (KeyPoint::get_TSDF takes any f_adjust)
+    api.native_keypoint_descriptors(cm, m[:3], q)
+    # the clouds are still usable afterwards
+    assert api.register(cm, cs, default_register_params()).converged in (0, 1)
+    cm.free(); cs.free()
+
+
+@pytest.mark.gpu
+def test_ransac_rejects_correspondences_of_another_target(api, gpu_ctx, clouds):
+    """rtr_match_features(src, A) followed by rtr_ransac_prerejective(src, B) with |B| == |A| used A's correspondences in
+    round 1 (the cache was keyed by the target's size only)."""
+    from realtime_robot_b200 import _lib
+    p = default_register_params()
+    src, a = clouds("chair1"), clouds("mcloud")
+    b = a.copy(); b[:, 0] += np.float32(0.25)                 # same size, different cloud
+    cs, ca, cb = api.Cloud(gpu_ctx, src), api.Cloud(gpu_ctx, a), api.Cloud(gpu_ctx, b)
+    for c in (cs, ca, cb):
+        c.normals(p.normal_radius); c.fpfh(p.fpfh_radius)
+    cs.match_features(ca, p.ransac.correspondence_k)
+    p.ransac.max_iterations = 2000
+    ok = api.ransac_prerejective(cs, ca, p.ransac)
+    with pytest.raises(_lib.RtrError) as e:
+        api.ransac_prerejective(cs, cb, p.ransac)
+    assert e.value.code == 4                                  # RTR_ERR_NOT_READY
+    ca.fpfh(0.09)                                             # the target's features changed: correspondences are stale
+    with pytest.raises(_lib.RtrError):
+        api.ransac_prerejective(cs, ca, p.ransac)
+    cs.match_features(cb, p.ransac.correspondence_k)
+    assert api.ransac_prerejective(cs, cb, p.ransac).evaluated >= 0 and ok.evaluated >= 0
+    for c in (cs, ca, cb):
+        c.free()
+
+
+@pytest.mark.gpu
+def test_tdf_batch_beyond_65535_keypoints(api, gpu_ctx, orc):
+    """gridDim.y carries the keypoint: batches above 65535 grids go in chunks."""
+    rng = np.random.default_rng(5)
+    n = 66000
+    dim = 6
+    lists = [rng.integers(0, dim, (int(k), 3)).astype(np.int32) for k in rng.integers(0, 4, n)]
+    out = api.tdf_batch(gpu_ctx, lists, dim)
+    for g in (0, 1, 65534, 65535, 65536, n - 1):
+        assert np.array_equal(out[g], orc.tdf(lists[g], dim)[:dim ** 3]), g
