@@ -257,6 +257,31 @@ int rtr_register_host_begin(rtr_context* ctx, const float* host_model_xyz1, int 
                             const rtr_register_params* p);
 int rtr_register_end(rtr_context* ctx, rtr_pose_result* host_result);
 
+/* One scan against MANY database models (README.md:10: "match the segmented objects against the model database").  The reference
+ * builds the scan side once — ScanPoint keypoints and descriptors, RealTimeRobot.cpp:45-60 — and then loops over the model's
+ * keypoints (:62-102); the per-model work is the offline side (:124-165).  These entry points do the same for a batch: the
+ * scan's grid / normals / Harris / FPFH run once, every per-cloud stage of the models and the scan is ONE launch over all of
+ * them (a "model set": clouds concatenated, one uniform grid per cloud), descriptor matching is one search of all model
+ * features against the scan's, and the models' RANSAC hypotheses and ICP iterations share their launches.
+ * host_results[m] is what rtr_register(models[m], scene) returns (bit for bit), with model_id = m.
+ * Batches of up to 31 models go through the model-set path; clouds of 65536 points or more, sweeps above 2^20 hypotheses
+ * and degenerate clouds (< 3 points) fall back to one rtr_register per model inside the same call. */
+int rtr_register_many(rtr_cloud* const* models, int n_models, rtr_cloud* scene, const rtr_register_params* p,
+                      rtr_pose_result* host_results);
+/* HOST clouds in (n_models pointers + sizes, and the scan), HOST records out: uploads + batch + free in one call. */
+int rtr_register_many_host(rtr_context* ctx, const float* const* host_models_xyz1, const int* n_points, int n_models,
+                           const float* host_scene_xyz1, int n_scene, const rtr_register_params* p, rtr_pose_result* host_results);
+/* Enqueue / wait halves (at most 31 models, model-set shapes only; RTR_ERR_INVALID otherwise).  Host buffers must stay
+ * valid until _end. */
+int rtr_register_many_begin(rtr_cloud* const* models, int n_models, rtr_cloud* scene, const rtr_register_params* p);
+int rtr_register_many_host_begin(rtr_context* ctx, const float* const* host_models_xyz1, const int* n_points, int n_models,
+                                 const float* host_scene_xyz1, int n_scene, const rtr_register_params* p);
+int rtr_register_many_end(rtr_context* ctx, rtr_pose_result* host_results, int capacity);
+/* The Harris corners the last batch found — ModelPoint::key_coordinates / ScanPoint::key_coordinates (model_point.h:146-152,
+ * scan_point.h:104-110), refined xyz1 — of member `member` (0 .. n_models-1: the models, n_models: the scan).  They travel
+ * back with the records (up to 64 per cloud; *n_keypoints is the full count, RTR_ERR_CAPACITY if not all fit). */
+int rtr_register_many_keypoints(rtr_context* ctx, int member, float* host_kp_xyz1, int capacity, int* n_keypoints);
+
 /* ------------------------------------------------------------------ reference-native descriptor path */
 
 /* THE reference FFI, exported unchanged (key_point.h:35-36, kernel.cu:34-35).  Host pointers;

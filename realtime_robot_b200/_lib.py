@@ -20,6 +20,8 @@ EXPORTS = [
     "rtr_register_host", "ComputeTDFWithCuda", "rtr_tdf_batch", "rtr_tdf_batch_dev", "rtr_native_default_params", "rtr_native_keypoint_descriptors",
     "rtr_native_pair_scores", "rtr_native_register", "rtr_plane_areas", "rtr_pcd_info", "rtr_pcd_read", "rtr_pcd_load", "rtr_pcd_write",
     "rtr_cloud_save", "rtr_register_begin", "rtr_register_host_begin", "rtr_register_end", "rtr_context_create_prio",
+    "rtr_register_many", "rtr_register_many_host", "rtr_register_many_begin", "rtr_register_many_host_begin", "rtr_register_many_end",
+    "rtr_register_many_keypoints",
 ]
 
 
@@ -81,6 +83,12 @@ def lib():
         L.rtr_register_begin.argtypes = [vp, vp, C.POINTER(RegisterParams)]
         L.rtr_register_host_begin.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.POINTER(RegisterParams)]
         L.rtr_register_end.argtypes = [vp, C.POINTER(PoseResult)]
+        L.rtr_register_many.argtypes = [C.POINTER(vp), C.c_int, vp, C.POINTER(RegisterParams), C.POINTER(PoseResult)]
+        L.rtr_register_many_host.argtypes = [vp, C.POINTER(vp), ip, C.c_int, vp, C.c_int, C.POINTER(RegisterParams), C.POINTER(PoseResult)]
+        L.rtr_register_many_begin.argtypes = [C.POINTER(vp), C.c_int, vp, C.POINTER(RegisterParams)]
+        L.rtr_register_many_host_begin.argtypes = [vp, C.POINTER(vp), ip, C.c_int, vp, C.c_int, C.POINTER(RegisterParams)]
+        L.rtr_register_many_end.argtypes = [vp, C.POINTER(PoseResult), C.c_int]
+        L.rtr_register_many_keypoints.argtypes = [vp, C.c_int, vp, C.c_int, ip]
         L.rtr_pcd_info.argtypes = [C.c_char_p, ip, ip]
         L.rtr_pcd_read.argtypes = [C.c_char_p, vp, C.c_int, ip]
         L.rtr_pcd_load.argtypes = [vp, C.c_char_p, C.POINTER(vp)]

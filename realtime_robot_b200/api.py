@@ -272,6 +272,70 @@ def register_end(ctx: Context) -> PoseResult:
     return res
 
 
+def _records(buf, n):
+    return [PoseResult.from_buffer_copy(bytes(buf[i])) for i in range(n)]
+
+
+def register_many(models, scene: Cloud, params: RegisterParams):
+    """One scan against many database models (RealTimeRobot.cpp:45-104 once per model, README.md:10): the scan's stages run
+    once, the models' stages share their launches.  Returns one PoseResult per model, equal to register(model, scene)."""
+    k = len(models)
+    handles = (C.c_void_p * k)(*[m._h for m in models])
+    res = (PoseResult * k)()
+    _lib.check("rtr_register_many", _lib.lib().rtr_register_many(handles, k, scene._h, C.byref(params), res))
+    return _records(res, k)
+
+
+def _host_batch(models_xyz1, scene_xyz1):
+    ms = [_f32(m, 4) for m in models_xyz1]
+    s = _f32(scene_xyz1, 4)
+    k = len(ms)
+    ptrs = (C.c_void_p * k)(*[m.ctypes.data for m in ms])
+    ns = (C.c_int * k)(*[len(m) for m in ms])
+    return ms, s, ptrs, ns, k
+
+
+def register_many_host(ctx: Context, models_xyz1, scene_xyz1, params: RegisterParams):
+    """Host clouds in, host records out: uploads + batch + free inside one C-ABI call."""
+    ms, s, ptrs, ns, k = _host_batch(models_xyz1, scene_xyz1)
+    res = (PoseResult * k)()
+    _lib.check("rtr_register_many_host", _lib.lib().rtr_register_many_host(ctx._h, ptrs, ns, k, _ptr(s), len(s), C.byref(params), res))
+    return _records(res, k)
+
+
+def register_many_begin(models, scene: Cloud, params: RegisterParams) -> None:
+    k = len(models)
+    handles = (C.c_void_p * k)(*[m._h for m in models])
+    scene.ctx._inflight_many = k
+    _lib.check("rtr_register_many_begin", _lib.lib().rtr_register_many_begin(handles, k, scene._h, C.byref(params)))
+
+
+def register_many_host_begin(ctx: Context, models_xyz1, scene_xyz1, params: RegisterParams) -> None:
+    """The arrays must stay alive until register_many_end (pinned memory keeps the uploads asynchronous)."""
+    ms, s, ptrs, ns, k = _host_batch(models_xyz1, scene_xyz1)
+    ctx._inflight = (ms, s, ptrs, ns)
+    ctx._inflight_many = k
+    _lib.check("rtr_register_many_host_begin", _lib.lib().rtr_register_many_host_begin(ctx._h, ptrs, ns, k, _ptr(s), len(s), C.byref(params)))
+
+
+def register_many_end(ctx: Context):
+    k = ctx._inflight_many
+    res = (PoseResult * k)()
+    _lib.check("rtr_register_many_end", _lib.lib().rtr_register_many_end(ctx._h, res, k))
+    ctx._inflight = None
+    return _records(res, k)
+
+
+def register_many_keypoints(ctx: Context, member: int, capacity: int = 64):
+    """Refined Harris corners (xyz1) of one member of the last batch: 0..k-1 the models, k the scan; (corners, full count)."""
+    out = np.zeros((capacity, 4), dtype=np.float32)
+    n = C.c_int()
+    rc = _lib.lib().rtr_register_many_keypoints(ctx._h, member, _ptr(out), capacity, C.byref(n))
+    if rc not in (0, 3):
+        _lib.check("rtr_register_many_keypoints", rc)
+    return out[:min(n.value, capacity)].copy(), n.value
+
+
 def compute_tdf_with_cuda(voxel_grid_occ, voxel_grid_tdf, voxel_grid_dim: int, num_occ: int) -> int:
     """The reference FFI, unchanged (key_point.h:35-36).  voxel_grid_tdf: 27000 float32, modified in place."""
     occ = np.ascontiguousarray(voxel_grid_occ, dtype=np.int32)

@@ -29,6 +29,18 @@ struct DevGrid {
     float4* sorted = nullptr;        // points in cell order; .w carries the ORIGINAL index (int bits)
     float4* sorted_normals = nullptr;  // optional: normals4 permuted into this grid's order
     int normals_version = -1;
+    // Segmented grid of a model set (see rtr_cloud::seg_begin): one independent uniform grid per segment.  cell_begin is
+    // the concatenation of the segments' cell tables (segment k at cell_off, ncells_k entries, values are GLOBAL positions
+    // into `sorted`, so the table of segment k+1 closes segment k), sorted[.].w carries the GLOBAL original index.
+    std::vector<struct SegHdr> segs;
+};
+
+// one segment of a segmented grid
+struct SegHdr {
+    float inv_h, h;
+    float mnx, mny, mnz;
+    int dx, dy, dz;
+    int cell_off;      // first entry of this segment's cell table inside the concatenated cell_begin
 };
 
 // what the kernels see (passed by value)
@@ -39,6 +51,52 @@ struct GridView {
     int n;
     const int* __restrict__ cell_begin;
     const float4* __restrict__ sorted;
+};
+
+// Grid source of the per-point kernels: the grid a work item (a position in cell order) belongs to.
+//   OneGrid   — an ordinary cloud: every position is in the one grid (compiles to the plain GridView kernels).
+//   ManyGrids — a model set: up to RTR_MAX_SEGMENTS clouds concatenated, each with its own grid; positions are global
+//               (segment k owns [begin[k], begin[k+1])), so ONE launch serves every cloud of the set and a point only
+//               ever sees neighbours of its own cloud.
+#define RTR_MAX_SEGMENTS 32
+struct OneGrid {
+    GridView g;
+    __host__ __device__ int total() const { return g.n; }
+#ifdef __CUDACC__
+    __device__ __forceinline__ GridView at(int) const { return g; }
+    __device__ __forceinline__ GridView view(int) const { return g; }
+    __device__ __forceinline__ int segment_of(int) const { return 0; }
+    __device__ __forceinline__ int seg_start(int) const { return 0; }
+    __device__ __forceinline__ int seg_size(int) const { return g.n; }
+#endif
+};
+struct ManyGrids {
+    int nseg;
+    int begin[RTR_MAX_SEGMENTS + 1];        // unused tail = total
+    SegHdr seg[RTR_MAX_SEGMENTS];
+    const int* __restrict__ cell_begin;
+    const float4* __restrict__ sorted;
+    __host__ __device__ int total() const { return begin[RTR_MAX_SEGMENTS]; }
+#ifdef __CUDACC__
+    // binary search over the 32 segment starts (positions past the end fall into the last slot)
+    __device__ __forceinline__ int segment_of(int s) const {
+        int k = 0;
+#pragma unroll
+        for (int step = RTR_MAX_SEGMENTS / 2; step > 0; step >>= 1) if (s >= begin[k + step]) k += step;
+        return k;
+    }
+    __device__ __forceinline__ GridView view(int k) const {
+        GridView g;
+        const SegHdr& h = seg[k];
+        g.inv_h = h.inv_h; g.h = h.h; g.mnx = h.mnx; g.mny = h.mny; g.mnz = h.mnz; g.dx = h.dx; g.dy = h.dy; g.dz = h.dz;
+        g.n = begin[k + 1] - begin[k];
+        g.cell_begin = cell_begin + h.cell_off; g.sorted = sorted;
+        return g;
+    }
+    __device__ __forceinline__ GridView at(int s) const { return view(segment_of(s)); }
+    __device__ __forceinline__ int seg_start(int k) const { return begin[k]; }
+    __device__ __forceinline__ int seg_size(int k) const { return begin[k + 1] - begin[k]; }
+#endif
 };
 
 struct ProfMark { const char* tag; cudaEvent_t ev; };
@@ -73,6 +131,9 @@ struct rtr_context {
     // asynchronous registration (rtr_register_begin / _end): at most one in flight per context
     int register_pending = 0;
     struct rtr_cloud* pending_cloud[2] = {nullptr, nullptr};
+    int many_models = 0;                  // > 0: the registration in flight is a batch of that many models (rtr_register_many_begin)
+    std::vector<char> kp_preview;         // corner previews of the last batch (rtr_register_many_keypoints)
+    int kp_members = 0;
     // pinned staging of rtr_pcd_load (decoded points, grown on demand)
     void* io_pinned = nullptr;
     size_t io_pinned_cap = 0;
@@ -93,6 +154,12 @@ struct rtr_cloud {
     const rtr_cloud* knn_target = nullptr;   long long knn_target_gen = -1;
     long long feature_gen = 0;                // process-wide unique stamp, renewed whenever this cloud's FPFH rows are recomputed or dropped
     int n_keypoints = -1;
+    // A model set (rtr_register_many): the points of several clouds concatenated, seg_begin[k] .. seg_begin[k+1] is cloud k
+    // (size nseg + 1; empty for an ordinary cloud).  Every per-point stage then runs on all member clouds in one launch,
+    // through segmented grids; outputs (normals, response, FPFH) are concatenated in the same order.
+    std::vector<int> seg_begin;
+    std::vector<float> seg_bb;                // 6 floats per segment: min x, y, z, max x, y, z
+    int nseg() const { return seg_begin.empty() ? 0 : (int)seg_begin.size() - 1; }
 };
 
 #define RTR_CHECK(call, tag)                                                                       \
@@ -188,6 +255,13 @@ int  rtr_get_grid(rtr_cloud* c, float cell, DevGrid** out);          // build-or
 int  rtr_get_grid_any(rtr_cloud* c, float want, float lo, float hi, DevGrid** out);
 int  rtr_grid_normals(rtr_cloud* c, DevGrid* g);                     // make g->sorted_normals current
 GridView rtr_view(const DevGrid* g);
+OneGrid  rtr_one(const DevGrid* g);
+ManyGrids rtr_many(const DevGrid* g, const rtr_cloud* c);
+// one segment of a segmented grid as an ordinary view: sorted / cell_begin are offset so that positions are LOCAL to the
+// segment (0 .. n_k), while sorted[.].w still carries the global original index
+GridView rtr_segment_view(const DevGrid* g, const rtr_cloud* c, int k);
+// build-or-fetch several grids of a model set in as few launches as possible (one per cell size)
+int  rtr_get_grids(rtr_cloud* c, const float* cells, int n_cells, DevGrid** out);
 int  rtr_ensure_bbox(rtr_cloud* c);
 void rtr_invalidate(rtr_cloud* c);
 float rtr_icp_cell(const rtr_cloud* c);
@@ -200,6 +274,10 @@ int  rtr_ransac_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_ransac_params* p, 
 int  rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const float* d_init_pose16, int init_from_result,
                  rtr_pose_result* d_result);
 int  rtr_validate_register_params(const rtr_register_params* p);
+// model sets: member clouds (device handles / host buffers) concatenated into one segmented rtr_cloud; free with rtr_cloud_free
+int  rtr_model_set_from_clouds(rtr_context* ctx, rtr_cloud* const* members, int nseg, rtr_cloud** out);
+int  rtr_model_set_from_host(rtr_context* ctx, const float* const* host_xyz1, const int* ns, int nseg, rtr_cloud** out);
+int  rtr_match_features_dev(rtr_context* ctx, const float* fa, int na, const float* fb, int nb, int k, int* out_idx, float* out_dist);
 long long rtr_next_generation();          // process-wide, never repeats (a freed handle's address may be reused, its stamps are not)
 
 // launch with programmatic stream serialization (see pdl_wait below); RTR_PDL=0 falls back to ordinary launches

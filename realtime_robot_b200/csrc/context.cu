@@ -165,6 +165,86 @@ k_grid_build_small(const float4* __restrict__ pts, int n, float mnx, float mny, 
     }
 }
 
+// The same build for every cloud of a model set in ONE launch: cluster j builds segment j (blockIdx.x = 8 j + rank).
+// Positions written to the cell table and the index in sorted[.].w are GLOBAL (segment start + local), so the segment
+// tables concatenate into one array (see DevGrid::segs).  keys / slot are per point, cursor mirrors the cell table.
+__global__ void __cluster_dims__(GB_CLUSTER, 1, 1) __launch_bounds__(GB_THREADS)
+k_grid_build_multi(const __grid_constant__ ManyGrids mg, const float4* __restrict__ pts, int* cell_table, int* keys_all, int* cursor_all,
+                   int* slot_all, int* cta_total_all, float4* __restrict__ sorted) {
+    __shared__ int part[GB_THREADS];
+    const int job = blockIdx.x / GB_CLUSTER, cta = blockIdx.x % GB_CLUSTER;
+    const SegHdr hd = mg.seg[job];
+    const int p0 = mg.begin[job], n = mg.begin[job + 1] - p0;
+    const int ncells = hd.dx * hd.dy * hd.dz;
+    int* cell_begin = cell_table + hd.cell_off;
+    int* cursor = cursor_all + hd.cell_off;
+    int* keys = keys_all + p0;
+    int* cta_total = cta_total_all + job * GB_CLUSTER;
+    const int t = threadIdx.x;
+    const int gt = cta * GB_THREADS + t, GT = GB_CLUSTER * GB_THREADS;
+    // local counts first; the last segment also owns the closing entry of the whole table
+    const int last = (job == mg.nseg - 1) ? 1 : 0;
+    for (int c = gt; c < ncells + last; c += GT) cell_begin[c] = 0;
+    cluster_sync_all();
+    for (int i = gt; i < n; i += GT) {
+        float4 p = __ldg(pts + p0 + i);
+        int cx = clampi(cell_coord(p.x, hd.mnx, hd.inv_h), 0, hd.dx - 1);
+        int cy = clampi(cell_coord(p.y, hd.mny, hd.inv_h), 0, hd.dy - 1);
+        int cz = clampi(cell_coord(p.z, hd.mnz, hd.inv_h), 0, hd.dz - 1);
+        int key = (cz * hd.dy + cy) * hd.dx + cx;
+        keys[i] = key;
+        atomicAdd(cell_begin + key, 1);
+    }
+    cluster_sync_all();
+    // exclusive scan of the ncells counts (+ the closing entry of the last segment), offset by the segment start
+    const int nscan = ncells + last;
+    int per = (nscan + GT - 1) / GT;
+    int c0 = min(gt * per, nscan), c1 = min(c0 + per, nscan);
+    int sum = 0;
+    for (int c = c0; c < c1; ++c) sum += cell_begin[c];
+    part[t] = sum;
+    __syncthreads();
+    for (int off = 1; off < GB_THREADS; off <<= 1) {
+        int v = (t >= off) ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    if (t == GB_THREADS - 1) cta_total[cta] = part[t];
+    cluster_sync_all();
+    int run = p0 + part[t] - sum;
+    for (int k = 0; k < cta; ++k) run += cta_total[k];
+    for (int c = c0; c < c1; ++c) { int v = cell_begin[c]; cell_begin[c] = run; if (c < ncells) cursor[c] = run; run += v; }
+    cluster_sync_all();
+    for (int i = gt; i < n; i += GT) slot_all[atomicAdd(cursor + keys[i], 1)] = i;       // unordered inside a cell; slot_all is indexed by GLOBAL position
+    cluster_sync_all();
+    // rank inside the cell = number of members with a smaller original index -> deterministic ascending order.
+    // The end of a cell is the next table entry; for the last cell of a segment that is the next segment's first entry
+    // (= this segment's end), written by another cluster: use the segment end directly there.
+    for (int pos = gt; pos < n; pos += GT) {
+        int i = slot_all[p0 + pos];
+        int key = keys[i];
+        int b = cell_begin[key], e = (key + 1 < ncells) ? cell_begin[key + 1] : p0 + n;
+        int rank = 0;
+        for (int q = b; q < e; ++q) rank += (slot_all[q] < i) ? 1 : 0;
+        float4 p = __ldg(pts + p0 + i);
+        p.w = __int_as_float(p0 + i);
+        sorted[b + rank] = p;
+    }
+}
+
+// model set from device clouds: one gather over a pointer table (RTR_MAX_SEGMENTS members at most)
+struct ConcatTable { int nseg; int begin[RTR_MAX_SEGMENTS + 1]; const float4* src[RTR_MAX_SEGMENTS]; };
+__global__ void k_concat_clouds(const __grid_constant__ ConcatTable t, float4* __restrict__ out) {
+    const int total = t.begin[RTR_MAX_SEGMENTS];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int k = 0;
+#pragma unroll
+        for (int step = RTR_MAX_SEGMENTS / 2; step > 0; step >>= 1) if (i >= t.begin[k + step]) k += step;
+        out[i] = __ldg(t.src[k] + (i - t.begin[k]));
+    }
+}
+
 __global__ void k_permute4(const float4* __restrict__ src, const float4* __restrict__ sorted, int n, float4* __restrict__ dst) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -284,6 +364,27 @@ GridView rtr_view(const DevGrid* g) {
     return v;
 }
 
+OneGrid rtr_one(const DevGrid* g) { OneGrid o; o.g = rtr_view(g); return o; }
+
+ManyGrids rtr_many(const DevGrid* g, const rtr_cloud* c) {
+    ManyGrids m;
+    memset(&m, 0, sizeof(m));
+    m.nseg = c->nseg();
+    for (int k = 0; k <= RTR_MAX_SEGMENTS; ++k) m.begin[k] = k < m.nseg ? c->seg_begin[k] : c->n;
+    for (int k = 0; k < m.nseg; ++k) m.seg[k] = g->segs[k];
+    m.cell_begin = g->cell_begin; m.sorted = g->sorted;
+    return m;
+}
+
+GridView rtr_segment_view(const DevGrid* g, const rtr_cloud* c, int k) {
+    GridView v;
+    const SegHdr& h = g->segs[k];
+    v.inv_h = h.inv_h; v.h = h.h; v.mnx = h.mnx; v.mny = h.mny; v.mnz = h.mnz; v.dx = h.dx; v.dy = h.dy; v.dz = h.dz;
+    v.n = c->seg_begin[k + 1] - c->seg_begin[k];
+    v.cell_begin = g->cell_begin + h.cell_off; v.sorted = g->sorted;
+    return v;
+}
+
 int rtr_ensure_bbox(rtr_cloud* c) {
     if (c->bbox_valid) return 0;
     rtr_context* ctx = c->ctx;
@@ -332,7 +433,74 @@ float rtr_icp_cell(const rtr_cloud* c) {
     return (float)std::max(cell, 1e-4);
 }
 
+// cell size and dimensions of the grid that serves radius `cell` over a bounding box.  The cell is 0.1 % wider than the
+// radius so that float cell assignment can never put two points that are within the radius more than one cell apart
+// (DESIGN.md "grid exactness"); dims are capped (2048 per axis, 2^26 cells) by widening the cell.
+static void grid_dims(const float* bb_min, const float* bb_max, float cell, double max_cells, float* h_out, int* d) {
+    double h = (double)cell * 1.001;
+    for (;;) {
+        double cells = 1;
+        bool ok = true;
+        for (int a = 0; a < 3; ++a) {
+            double ext = (double)bb_max[a] - (double)bb_min[a];
+            double da = std::floor(ext / h) + 2;     // +1 for the floor, +1 slack for float rounding at the upper face
+            if (da > 2048) ok = false;
+            d[a] = (int)std::min(da, 4096.0);
+            cells *= d[a];
+        }
+        if (ok && cells <= max_cells) break;
+        h *= 1.25;
+    }
+    *h_out = (float)h;
+}
+
+// Model sets: one launch builds the grids of every member cloud for one cell size (clusters of 8 CTAs, one per segment).
+int rtr_get_grids(rtr_cloud* c, const float* cells, int n_cells, DevGrid** out) {
+    rtr_context* ctx = c->ctx;
+    const int nseg = c->nseg();
+    if (nseg <= 0 || nseg > RTR_MAX_SEGMENTS) return rtr_fail("grid", "rtr_get_grids needs a model set of 1..32 clouds", RTR_ERR_INVALID);
+    for (int j = 0; j < n_cells; ++j) {
+        const float cell = cells[j];
+        if (!(cell > 0.f) || !std::isfinite(cell)) return rtr_fail("grid", "cell size (search radius) must be finite and > 0", RTR_ERR_INVALID);
+        int keybits;
+        memcpy(&keybits, &cell, 4);
+        auto it = c->grids.find(keybits);
+        if (it != c->grids.end()) { out[j] = &it->second; continue; }
+        DevGrid g;
+        g.n = c->n;
+        g.segs.resize(nseg);
+        long long cell_total = 0;
+        for (int k = 0; k < nseg; ++k) {
+            SegHdr& hd = g.segs[k];
+            int d[3];
+            const float* bb = &c->seg_bb[6 * k];
+            grid_dims(bb, bb + 3, cell, 4194304.0, &hd.h, d);
+            hd.inv_h = 1.0f / hd.h; hd.mnx = bb[0]; hd.mny = bb[1]; hd.mnz = bb[2];
+            hd.dx = d[0]; hd.dy = d[1]; hd.dz = d[2];
+            hd.cell_off = (int)cell_total;
+            cell_total += (long long)d[0] * d[1] * d[2];
+        }
+        if (cell_total > (1LL << 28)) return rtr_fail("grid", "model set needs too many grid cells", RTR_ERR_INVALID);
+        g.h = g.segs[0].h; g.inv_h = g.segs[0].inv_h; g.ncells = (int)cell_total;
+        int *keys = nullptr, *cursor = nullptr, *slot = nullptr, *cta_total = nullptr;
+        if (int e = tmp_alloc(ctx, &cta_total, (size_t)GB_CLUSTER * nseg, "grid")) return e;
+        if (int e = tmp_alloc(ctx, &keys, c->n, "grid")) return e;
+        if (int e = tmp_alloc(ctx, &cursor, (size_t)cell_total + 1, "grid")) return e;
+        if (int e = tmp_alloc(ctx, &slot, c->n, "grid")) return e;
+        if (int e = dev_alloc(ctx, &g.cell_begin, (size_t)cell_total + 1, "grid")) return e;
+        if (int e = dev_alloc(ctx, &g.sorted, c->n, "grid")) return e;
+        ManyGrids mg = rtr_many(&g, c);
+        k_grid_build_multi<<<GB_CLUSTER * nseg, GB_THREADS, 0, ctx->stream>>>(mg, c->pts, g.cell_begin, keys, cursor, slot, cta_total, g.sorted);
+        RTR_LAUNCH_CHECK(ctx, "grid.build_multi");
+        dev_free(ctx, keys); dev_free(ctx, cursor); dev_free(ctx, slot); dev_free(ctx, cta_total);
+        auto ins = c->grids.emplace(keybits, g);
+        out[j] = &ins.first->second;
+    }
+    return 0;
+}
+
 int rtr_get_grid(rtr_cloud* c, float cell, DevGrid** out) {
+    if (c->nseg() > 0) return rtr_get_grids(c, &cell, 1, out);
     // a zero / negative / non-finite cell would never satisfy the dimension caps below (h *= 1.25 keeps 0 at 0)
     if (!(cell > 0.f) || !std::isfinite(cell)) return rtr_fail("grid", "cell size (search radius) must be finite and > 0", RTR_ERR_INVALID);
     int keybits;
@@ -343,24 +511,12 @@ int rtr_get_grid(rtr_cloud* c, float cell, DevGrid** out) {
     if (int e = rtr_ensure_bbox(c)) return e;
     DevGrid g;
     g.n = c->n;
-    // the cell is 0.1 % wider than the radius it serves so that float cell assignment can never put two points that
-    // are within the radius more than one cell apart (DESIGN.md "grid exactness")
-    double h = (double)cell * 1.001;
-    for (;;) {
-        double cells = 1;
-        bool ok = true;
+    {
         int d[3];
-        for (int a = 0; a < 3; ++a) {
-            double ext = (double)c->bb_max[a] - (double)c->bb_min[a];
-            double da = std::floor(ext / h) + 2;     // +1 for the floor, +1 slack for float rounding at the upper face
-            if (da > 2048) ok = false;
-            d[a] = (int)std::min(da, 4096.0);
-            cells *= d[a];
-        }
-        if (ok && cells <= 67108864.0) { g.dx = d[0]; g.dy = d[1]; g.dz = d[2]; break; }
-        h *= 1.25;
+        grid_dims(c->bb_min, c->bb_max, cell, 67108864.0, &g.h, d);
+        g.dx = d[0]; g.dy = d[1]; g.dz = d[2];
     }
-    g.h = (float)h; g.inv_h = 1.0f / g.h;
+    g.inv_h = 1.0f / g.h;
     g.mnx = c->bb_min[0]; g.mny = c->bb_min[1]; g.mnz = c->bb_min[2];
     g.ncells = g.dx * g.dy * g.dz;
     int n = c->n;
@@ -424,6 +580,81 @@ int rtr_get_grid(rtr_cloud* c, float cell, DevGrid** out) {
     dev_free(ctx, (char*)temp); dev_free(ctx, keys); dev_free(ctx, vals); dev_free(ctx, keys2); dev_free(ctx, vals2); dev_free(ctx, counts);
     auto ins = c->grids.emplace(keybits, g);
     *out = &ins.first->second;
+    return 0;
+}
+
+// ---- model sets (rtr_register_many): several clouds concatenated into one rtr_cloud with a segment table ----
+static int set_new(rtr_context* ctx, const int* ns, int nseg, rtr_cloud** out) {
+    if (!ctx || !out || nseg < 1 || nseg > RTR_MAX_SEGMENTS) return rtr_fail("model_set", "1..32 member clouds", RTR_ERR_INVALID);
+    long long total = 0;
+    for (int k = 0; k < nseg; ++k) { if (ns[k] < 0) return rtr_fail("model_set", "negative size", RTR_ERR_INVALID); total += ns[k]; }
+    if (total > 0x7fffffffLL) return rtr_fail("model_set", "too many points", RTR_ERR_INVALID);
+    rtr_cloud* c = new rtr_cloud();
+    c->ctx = ctx; c->n = (int)total;
+    c->seg_begin.resize(nseg + 1);
+    c->seg_begin[0] = 0;
+    for (int k = 0; k < nseg; ++k) c->seg_begin[k + 1] = c->seg_begin[k] + ns[k];
+    c->seg_bb.assign((size_t)6 * nseg, 0.f);
+    if (int e = dev_alloc(ctx, &c->pts, (size_t)total, "model_set")) { delete c; return e; }
+    *out = c;
+    return 0;
+}
+static void set_finish_bbox(rtr_cloud* c) {
+    const int nseg = c->nseg();
+    for (int a = 0; a < 3; ++a) { c->bb_min[a] = FLT_MAX; c->bb_max[a] = -FLT_MAX; }
+    for (int k = 0; k < nseg; ++k)
+        for (int a = 0; a < 3; ++a) { c->bb_min[a] = std::min(c->bb_min[a], c->seg_bb[6 * k + a]); c->bb_max[a] = std::max(c->bb_max[a], c->seg_bb[6 * k + 3 + a]); }
+    c->bbox_valid = true;
+}
+
+int rtr_model_set_from_clouds(rtr_context* ctx, rtr_cloud* const* members, int nseg, rtr_cloud** out) {
+    if (!members || nseg < 1 || nseg > RTR_MAX_SEGMENTS) return rtr_fail("model_set", "1..32 member clouds", RTR_ERR_INVALID);
+    int ns[RTR_MAX_SEGMENTS];
+    for (int k = 0; k < nseg; ++k) {
+        if (!members[k] || members[k]->ctx != ctx || members[k]->nseg() > 0) return rtr_fail("model_set", "members must be ordinary clouds of this context", RTR_ERR_INVALID);
+        ns[k] = members[k]->n;
+        if (int e = rtr_ensure_bbox(members[k])) return e;
+    }
+    if (int e = set_new(ctx, ns, nseg, out)) return e;
+    rtr_cloud* c = *out;
+    ConcatTable t;
+    memset(&t, 0, sizeof(t));
+    t.nseg = nseg;
+    for (int k = 0; k <= RTR_MAX_SEGMENTS; ++k) t.begin[k] = k < nseg ? c->seg_begin[k] : c->n;
+    for (int k = 0; k < nseg; ++k) {
+        t.src[k] = members[k]->pts;
+        for (int a = 0; a < 3; ++a) { c->seg_bb[6 * k + a] = members[k]->bb_min[a]; c->seg_bb[6 * k + 3 + a] = members[k]->bb_max[a]; }
+    }
+    if (c->n > 0) {
+        k_concat_clouds<<<std::min(nblk(c->n, 256), 8 * ctx->sm_count), 256, 0, ctx->stream>>>(t, c->pts);
+        RTR_LAUNCH_CHECK(ctx, "set.concat");
+    }
+    set_finish_bbox(c);
+    return 0;
+}
+
+int rtr_model_set_from_host(rtr_context* ctx, const float* const* host_xyz1, const int* ns, int nseg, rtr_cloud** out) {
+    if (!host_xyz1 || !ns) return rtr_fail("model_set", "bad argument", RTR_ERR_INVALID);
+    for (int k = 0; k < nseg; ++k) if (ns[k] > 0 && !host_xyz1[k]) return rtr_fail("model_set", "null points", RTR_ERR_INVALID);
+    if (int e = set_new(ctx, ns, nseg, out)) return e;
+    rtr_cloud* c = *out;
+    for (int k = 0; k < nseg; ++k) {
+        const int n = ns[k];
+        if (n > 0) RTR_CHECK(cudaMemcpyAsync(c->pts + c->seg_begin[k], host_xyz1[k], (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream), "set.h2d");
+        RTR_MARK(ctx, "cloud.h2d");
+        // the caller's buffer is host memory: take the bounding box here, so no device round trip is needed later
+        float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        bool any = false;
+        for (int i = 0; i < n; ++i) {
+            const float* p = host_xyz1[k] + 4 * (size_t)i;
+            if (std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2])) {
+                any = true;
+                for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], p[a]); mx[a] = std::max(mx[a], p[a]); }
+            }
+        }
+        for (int a = 0; a < 3; ++a) { c->seg_bb[6 * k + a] = any ? mn[a] : 0.f; c->seg_bb[6 * k + 3 + a] = any ? mx[a] : 0.f; }
+    }
+    set_finish_bbox(c);
     return 0;
 }
 

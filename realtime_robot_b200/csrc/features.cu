@@ -96,10 +96,13 @@ __device__ __forceinline__ void for_block27_warp(const GridView& g, float qx, fl
 // repo-sized clouds (a few thousand points) cannot fill the GPU with one thread per point: one WARP per point, lanes
 // stride over the candidates, fp64 partial sums folded with a warp-shuffle tree.
 #define PW_WARPS 8
-__global__ void __launch_bounds__(PW_WARPS * 32) k_normals_warp(GridView g, float r2, float4* __restrict__ normals) {
+template <class GS>
+__global__ void __launch_bounds__(PW_WARPS * 32) k_normals_warp(const __grid_constant__ GS gs, float r2, float4* __restrict__ normals) {
     int lane = threadIdx.x & 31;
     int nwarps = gridDim.x * PW_WARPS;
-    for (int s = blockIdx.x * PW_WARPS + (threadIdx.x >> 5); s < g.n; s += nwarps) {
+    const int total = gs.total();
+    for (int s = blockIdx.x * PW_WARPS + (threadIdx.x >> 5); s < total; s += nwarps) {
+        const GridView g = gs.at(s);
         float4 q = __ldg(g.sorted + s);
         double sx = 0, sy = 0, sz = 0, cxx = 0, cxy = 0, cxz = 0, cyy = 0, cyz = 0, czz = 0;
         int cnt = 0;
@@ -172,11 +175,14 @@ __device__ __forceinline__ float harris_from_sums(int cnt, double c0, double c1,
     return r;
 }
 
-__global__ void __launch_bounds__(PW_WARPS * 32) k_harris_response_warp(GridView g, const float4* __restrict__ sn, float r2,
+template <class GS>
+__global__ void __launch_bounds__(PW_WARPS * 32) k_harris_response_warp(const __grid_constant__ GS gs, const float4* __restrict__ sn, float r2,
                                                                        float* __restrict__ resp, float* __restrict__ resp_sorted) {
     int lane = threadIdx.x & 31;
     int nwarps = gridDim.x * PW_WARPS;
-    for (int s = blockIdx.x * PW_WARPS + (threadIdx.x >> 5); s < g.n; s += nwarps) {
+    const int total = gs.total();
+    for (int s = blockIdx.x * PW_WARPS + (threadIdx.x >> 5); s < total; s += nwarps) {
+        const GridView g = gs.at(s);
         float4 q = __ldg(g.sorted + s);
         double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
         int cnt = 0;
@@ -199,11 +205,14 @@ __global__ void __launch_bounds__(PW_WARPS * 32) k_harris_response_warp(GridView
     }
 }
 
-__global__ void __launch_bounds__(PW_WARPS * 32) k_harris_nms_warp(GridView g, const float* __restrict__ resp_sorted, float r2, float thr,
+template <class GS>
+__global__ void __launch_bounds__(PW_WARPS * 32) k_harris_nms_warp(const __grid_constant__ GS gs, const float* __restrict__ resp_sorted, float r2, float thr,
                                                                   int nms, unsigned char* __restrict__ flags) {
     int lane = threadIdx.x & 31;
     int nwarps = gridDim.x * PW_WARPS;
-    for (int s = blockIdx.x * PW_WARPS + (threadIdx.x >> 5); s < g.n; s += nwarps) {
+    const int total = gs.total();
+    for (int s = blockIdx.x * PW_WARPS + (threadIdx.x >> 5); s < total; s += nwarps) {
+        const GridView g = gs.at(s);
         float4 q = __ldg(g.sorted + s);
         float r = resp_sorted[s];
         bool keep = isfinite(r) && (r >= thr);
@@ -233,15 +242,21 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 // threads stride over the 9 ranges, the nine 64-bit integer sums are folded by shuffles and through shared memory
 // (any order: integer addition), thread 0 solves the 3x3 system and publishes the moved corner.
 #define REFINE_THREADS 128
-__global__ void __launch_bounds__(REFINE_THREADS) k_harris_refine(GridView g, const float4* __restrict__ sn, const float4* __restrict__ pts, float r2,
-                                                                  const int* __restrict__ kp_idx, const int* __restrict__ kp_count, int capacity,
-                                                                  float4* __restrict__ kp_xyz, int refine) {
+// Model sets: blockIdx.y = member cloud; its corner list starts at the cloud's first point index (capacity = its size).
+template <class GS>
+__global__ void __launch_bounds__(REFINE_THREADS) k_harris_refine(const __grid_constant__ GS gs, const float4* __restrict__ sn, const float4* __restrict__ pts, float r2,
+                                                                  const int* __restrict__ kp_idx_all, const int* __restrict__ kp_count, int capacity,
+                                                                  float4* __restrict__ kp_xyz_all, int refine) {
     __shared__ int bounds[18];
     __shared__ long long wsum[REFINE_THREADS / 32][9];
     __shared__ float4 c_sh;
     __shared__ int again;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int m = min(*kp_count, capacity);
+    const int seg = blockIdx.y;
+    const GridView g = gs.view(seg);
+    const int* kp_idx = kp_idx_all + gs.seg_start(seg);
+    float4* kp_xyz = kp_xyz_all + gs.seg_start(seg);
+    int m = min(kp_count[seg], min(capacity, gs.seg_size(seg)));
     for (int t = blockIdx.x; t < m; t += gridDim.x) {
         float4 c = __ldg(pts + kp_idx[t]);
         c.w = 1.0f;
@@ -433,8 +448,9 @@ __device__ __forceinline__ bool spfh_screen_one(const GridView& g, const float4*
     }
     return true;
 }
-template <int MIN_CTAS>      // 3: 80 registers, 24 warps / SM (4 M points: 2 -> 14.9 ms, 3 -> 12.5 ms, 4 -> spills, no faster)
-__global__ void __launch_bounds__(SPFH_WARPS * 32, MIN_CTAS) k_spfh(GridView g, const float4* __restrict__ sn, float r2,
+// MIN_CTAS 3: 80 registers, 24 warps / SM (4 M points: 2 -> 14.9 ms, 3 -> 12.5 ms, 4 -> spills, no faster)
+template <int MIN_CTAS, class GS>
+__global__ void __launch_bounds__(SPFH_WARPS * 32, MIN_CTAS) k_spfh(const __grid_constant__ GS gs, const float4* __restrict__ sn, float r2,
                                                              float* __restrict__ spfh_sorted, int use_screen,
                                                              const int* __restrict__ list, const int* __restrict__ list_count) {
     __shared__ int cnt[SPFH_WARPS][36];
@@ -444,9 +460,10 @@ __global__ void __launch_bounds__(SPFH_WARPS * 32, MIN_CTAS) k_spfh(GridView g, 
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int nwarps = gridDim.x * SPFH_WARPS;
     const unsigned lt = (1u << lane) - 1u;
-    const int n_items = list ? *list_count : g.n;       // list: sorted positions whose SPFH is wanted (rtr_fpfh_at), else all points
+    const int n_items = list ? *list_count : gs.total();       // list: sorted positions whose SPFH is wanted (rtr_fpfh_at), else all points
     for (int it = blockIdx.x * SPFH_WARPS + warp; it < n_items; it += nwarps) {
         const int s = list ? __ldg(list + it) : it;
+        const GridView g = gs.at(s);
         cnt[warp][lane] = 0;
         if (lane < 4) cnt[warp][32 + lane] = 0;
         __syncwarp();
@@ -522,7 +539,8 @@ __global__ void __launch_bounds__(SPFH_WARPS * 32, MIN_CTAS) k_spfh(GridView g, 
 // four SPFH rows in flight), so the additions happen in ascending candidate position exactly as the oracle's loop.
 #define FPFH_WARPS 8
 struct __align__(16) FwEntry { double w, t32; };
-__global__ void __launch_bounds__(FPFH_WARPS * 32) k_fpfh_weight(GridView g, const float* __restrict__ spfh_sorted, float r2,
+template <class GS>
+__global__ void __launch_bounds__(FPFH_WARPS * 32) k_fpfh_weight(const __grid_constant__ GS gs, const float* __restrict__ spfh_sorted, float r2,
                                                                  float* __restrict__ fpfh, const int* __restrict__ list, int n_list) {
     __shared__ double hs[FPFH_WARPS][36];
     __shared__ FwEntry wq[FPFH_WARPS][64];
@@ -531,9 +549,10 @@ __global__ void __launch_bounds__(FPFH_WARPS * 32) k_fpfh_weight(GridView g, con
     int nwarps = gridDim.x * FPFH_WARPS;
     const unsigned lt = (1u << lane) - 1u;
     const float* rows = spfh_sorted + lane;
-    const int n_items = list ? n_list : g.n;            // list: sorted positions of the query points (rtr_fpfh_at), row it of the output
+    const int n_items = list ? n_list : gs.total();            // list: sorted positions of the query points (rtr_fpfh_at), row it of the output
     for (int it = blockIdx.x * FPFH_WARPS + warp; it < n_items; it += nwarps) {
         const int s = list ? __ldg(list + it) : it;
+        const GridView g = gs.at(s);
         float4 q = __ldg(g.sorted + s);
         double acc = 0, acc32 = 0;
         int nb = 0, head = 0, nq = 0;
@@ -879,6 +898,36 @@ static int match_dispatch(rtr_context* ctx, const float* fa, int na, const float
     return rtr_match_exact_launch(ctx, fa, na, fb, nb, k, out_idx, out_dist, nullptr, nullptr, na);
 }
 
+// Model sets: stable compaction of the corner flags (original order) per member cloud, one CTA per cloud — the ascending
+// index lists cub::DeviceSelect::Flagged gives a single cloud, for all clouds in one launch.  The list of cloud k starts at
+// out_idx[begin[k]]; counts[k] receives its length.
+__global__ void __launch_bounds__(1024) k_select_segments(const __grid_constant__ ManyGrids mg, const unsigned char* __restrict__ flags,
+                                                          int* __restrict__ out_idx, int* __restrict__ counts) {
+    __shared__ int warp_tot[32];
+    const int seg = blockIdx.x, p0 = mg.begin[seg], p1 = mg.begin[seg + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int base = 0;
+    for (int c0 = p0; c0 < p1; c0 += 1024) {
+        const int i = c0 + tid;
+        const bool f = i < p1 && flags[i] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) warp_tot[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, all = 0;
+        for (int w = 0; w < 32; ++w) { const int v = warp_tot[w]; all += v; if (w < warp) before += v; }
+        if (f) out_idx[p0 + base + before + __popc(m & ((1u << lane) - 1u))] = i;
+        base += all;
+        __syncthreads();
+    }
+    if (tid == 0) counts[seg] = base;
+}
+
+int rtr_match_features_dev(rtr_context* ctx, const float* fa, int na, const float* fb, int nb, int k, int* out_idx, float* out_dist) {
+    if (k < 1 || k > MATCH_KMAX) return rtr_fail("match", "k must be in [1, 8]", RTR_ERR_INVALID);
+    if (na <= 0) return 0;
+    return match_dispatch(ctx, fa, na, fb, nb, k, out_idx, out_dist, nullptr);
+}
+
 // ----------------------------------------------------------------------------- host drivers
 int rtr_normals_dev(rtr_cloud* c, float radius) {
     rtr_context* ctx = c->ctx;
@@ -887,8 +936,10 @@ int rtr_normals_dev(rtr_cloud* c, float radius) {
     if (int e = rtr_get_grid(c, radius, &g)) return e;
     if (!c->normals) if (int e = dev_alloc(ctx, &c->normals, c->n, "normals")) return e;
     if (c->n > 0) {
-        if (c->n <= env_threshold("RTR_WARP_PER_POINT_MAX", RTR_WARP_PER_POINT_MAX))
-            k_normals_warp<<<std::min(nblk(c->n, PW_WARPS), ctx->sm_count * wide_grid_mult()), PW_WARPS * 32, 0, ctx->stream>>>(rtr_view(g), radius * radius, c->normals);
+        if (c->nseg() > 0)
+            k_normals_warp<ManyGrids><<<std::min(nblk(c->n, PW_WARPS), ctx->sm_count * wide_grid_mult()), PW_WARPS * 32, 0, ctx->stream>>>(rtr_many(g, c), radius * radius, c->normals);
+        else if (c->n <= env_threshold("RTR_WARP_PER_POINT_MAX", RTR_WARP_PER_POINT_MAX))
+            k_normals_warp<OneGrid><<<std::min(nblk(c->n, PW_WARPS), ctx->sm_count * wide_grid_mult()), PW_WARPS * 32, 0, ctx->stream>>>(rtr_one(g), radius * radius, c->normals);
         else
             k_normals<<<nblk(c->n, 128), 128, 0, ctx->stream>>>(rtr_view(g), radius * radius, c->normals);
         RTR_LAUNCH_CHECK(ctx, "normals");
@@ -914,14 +965,37 @@ int rtr_harris_dev(rtr_cloud* c, float radius, float threshold, int nms, int ref
     if (int e = tmp_alloc(ctx, d_kp_idx, n, "harris")) return e;
     if (int e = tmp_alloc(ctx, d_kp_xyz, n, "harris")) return e;
     if (int e = tmp_alloc(ctx, d_count, 1, "harris")) return e;
+    const int nseg = c->nseg();
+    if (nseg > 0) {
+        // model set: per-cloud corner lists (list k starts at the cloud's first point index), counts[nseg]
+        dev_free(ctx, *d_count);
+        if (int e = tmp_alloc(ctx, d_count, nseg, "harris")) return e;
+        if (n > 0) {
+            const ManyGrids mg = rtr_many(g, c);
+            int grid = std::min(nblk(n, PW_WARPS), ctx->sm_count * wide_grid_mult());
+            k_harris_response_warp<ManyGrids><<<grid, PW_WARPS * 32, 0, ctx->stream>>>(mg, g->sorted_normals, r2, c->response, resp_sorted);
+            RTR_LAUNCH_CHECK(ctx, "harris.response");
+            k_harris_nms_warp<ManyGrids><<<grid, PW_WARPS * 32, 0, ctx->stream>>>(mg, resp_sorted, r2, threshold, nms, flags);
+            RTR_LAUNCH_CHECK(ctx, "harris.nms");
+            k_select_segments<<<nseg, 1024, 0, ctx->stream>>>(mg, flags, *d_kp_idx, *d_count);
+            RTR_LAUNCH_CHECK(ctx, "harris.select");
+            k_harris_refine<ManyGrids><<<dim3(32, nseg), REFINE_THREADS, 0, ctx->stream>>>(mg, g->sorted_normals, c->pts, r2, *d_kp_idx, *d_count, n, *d_kp_xyz, refine);
+            RTR_LAUNCH_CHECK(ctx, "harris.refine");
+        } else {
+            RTR_CHECK(cudaMemsetAsync(*d_count, 0, sizeof(int) * nseg, ctx->stream), "harris");
+        }
+        dev_free(ctx, resp_sorted); dev_free(ctx, flags);
+        return 0;
+    }
     RTR_CHECK(cudaMemsetAsync(*d_count, 0, sizeof(int), ctx->stream), "harris");
     if (n > 0) {
         GridView v = rtr_view(g);
+        const OneGrid ov = rtr_one(g);
         if (n <= env_threshold("RTR_WARP_PER_POINT_MAX", RTR_WARP_PER_POINT_MAX)) {
             int grid = std::min(nblk(n, PW_WARPS), ctx->sm_count * wide_grid_mult());
-            k_harris_response_warp<<<grid, PW_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, c->response, resp_sorted);
+            k_harris_response_warp<OneGrid><<<grid, PW_WARPS * 32, 0, ctx->stream>>>(ov, g->sorted_normals, r2, c->response, resp_sorted);
             RTR_LAUNCH_CHECK(ctx, "harris.response");
-            k_harris_nms_warp<<<grid, PW_WARPS * 32, 0, ctx->stream>>>(v, resp_sorted, r2, threshold, nms, flags);
+            k_harris_nms_warp<OneGrid><<<grid, PW_WARPS * 32, 0, ctx->stream>>>(ov, resp_sorted, r2, threshold, nms, flags);
             RTR_LAUNCH_CHECK(ctx, "harris.nms");
         } else {
             k_harris_response<<<nblk(n, 128), 128, 0, ctx->stream>>>(v, g->sorted_normals, r2, c->response, resp_sorted);
@@ -938,7 +1012,7 @@ int rtr_harris_dev(rtr_cloud* c, float radius, float threshold, int nms, int ref
         RTR_MARK(ctx, "harris.cub_select");
         dev_free(ctx, temp);
         // the corner count lives on the device: persistent grid of warps striding over the corner list
-        k_harris_refine<<<std::min(n, ctx->sm_count * 4), REFINE_THREADS, 0, ctx->stream>>>(v, g->sorted_normals, c->pts, r2, *d_kp_idx, *d_count, n, *d_kp_xyz, refine);
+        k_harris_refine<OneGrid><<<std::min(n, ctx->sm_count * 4), REFINE_THREADS, 0, ctx->stream>>>(ov, g->sorted_normals, c->pts, r2, *d_kp_idx, *d_count, n, *d_kp_xyz, refine);
         RTR_LAUNCH_CHECK(ctx, "harris.refine");
     }
     dev_free(ctx, resp_sorted); dev_free(ctx, flags);
@@ -962,7 +1036,20 @@ int rtr_fpfh_dev(rtr_cloud* c, float radius) {
         // RTR_SPFH_EXACT=1 sends every pair through the fp64 evaluation (the tests use it to show the fp32 screen changes nothing)
         const char* ex = getenv("RTR_SPFH_EXACT");
         int use_screen = (ex && ex[0] == '1') ? 0 : 1;
-        k_spfh<3><<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * wide_grid_mult()), SPFH_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh, use_screen, nullptr, nullptr);
+        if (c->nseg() > 0) {
+            const ManyGrids mg = rtr_many(g, c);
+            k_spfh<3, ManyGrids><<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * wide_grid_mult()), SPFH_WARPS * 32, 0, ctx->stream>>>(mg, g->sorted_normals, r2, spfh, use_screen, nullptr, nullptr);
+            RTR_LAUNCH_CHECK(ctx, "fpfh.spfh");
+            k_fpfh_weight<ManyGrids><<<std::min(nblk(n, FPFH_WARPS), ctx->sm_count * wide_grid_mult()), FPFH_WARPS * 32, 0, ctx->stream>>>(mg, spfh, r2, c->fpfh, nullptr, 0);
+            RTR_LAUNCH_CHECK(ctx, "fpfh.weight");
+            dev_free(ctx, spfh);
+            c->fpfh_radius = radius;
+            c->feature_gen = rtr_next_generation();
+            dev_free(ctx, c->knn); c->knn = nullptr; dev_free(ctx, c->knn_dist); c->knn_dist = nullptr; c->knn_k = 0;
+            return 0;
+        }
+        const OneGrid ov = rtr_one(g);
+        k_spfh<3, OneGrid><<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * wide_grid_mult()), SPFH_WARPS * 32, 0, ctx->stream>>>(ov, g->sorted_normals, r2, spfh, use_screen, nullptr, nullptr);
         RTR_LAUNCH_CHECK(ctx, "fpfh.spfh");
         if (n >= env_threshold("RTR_FPFH_TILED_MIN", 1 << 20)) {
             // one CTA per occupied cell, candidates staged through shared memory (needs many occupied cells to fill the GPU)
@@ -978,7 +1065,7 @@ int rtr_fpfh_dev(rtr_cloud* c, float radius) {
             int grid = std::min(std::min(g->ncells, n), ctx->sm_count * per_sm);
             k_fpfh_weight_tiled<<<grid, FW_WARPS * 32, sizeof(FwSmem), ctx->stream>>>(v, spfh, r2, c->fpfh, cells, n_cells);
         } else {
-            k_fpfh_weight<<<std::min(nblk(n, FPFH_WARPS), ctx->sm_count * wide_grid_mult()), FPFH_WARPS * 32, 0, ctx->stream>>>(v, spfh, r2, c->fpfh, nullptr, 0);
+            k_fpfh_weight<OneGrid><<<std::min(nblk(n, FPFH_WARPS), ctx->sm_count * wide_grid_mult()), FPFH_WARPS * 32, 0, ctx->stream>>>(ov, spfh, r2, c->fpfh, nullptr, 0);
         }
         RTR_LAUNCH_CHECK(ctx, "fpfh.weight");
     }
@@ -1015,6 +1102,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32) k_mark_neighbours(GridView g, c
 int rtr_fpfh_at_dev(rtr_cloud* c, float radius, const int* d_query_index, int nq, float* d_out) {
     rtr_context* ctx = c->ctx;
     if (!c->normals) return rtr_fail("fpfh_at", "rtr_normals must run first", RTR_ERR_NOT_READY);
+    if (c->nseg() > 0) return rtr_fail("fpfh_at", "not available on a model set", RTR_ERR_INVALID);
     if (nq <= 0 || c->n <= 0) return 0;
     DevGrid* g;
     if (int e = rtr_get_grid(c, radius, &g)) return e;
@@ -1043,9 +1131,10 @@ int rtr_fpfh_at_dev(rtr_cloud* c, float radius, const int* d_query_index, int nq
     RTR_MARK(ctx, "fpfh_at.cub_select");
     const char* ex = getenv("RTR_SPFH_EXACT");
     int use_screen = (ex && ex[0] == '1') ? 0 : 1;
-    k_spfh<3><<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * wide_grid_mult()), SPFH_WARPS * 32, 0, ctx->stream>>>(v, g->sorted_normals, r2, spfh, use_screen, list, count);
+    const OneGrid ov = rtr_one(g);
+    k_spfh<3, OneGrid><<<std::min(nblk(n, SPFH_WARPS), ctx->sm_count * wide_grid_mult()), SPFH_WARPS * 32, 0, ctx->stream>>>(ov, g->sorted_normals, r2, spfh, use_screen, list, count);
     RTR_LAUNCH_CHECK(ctx, "fpfh.spfh");
-    k_fpfh_weight<<<std::min(nblk(nq, FPFH_WARPS), ctx->sm_count * wide_grid_mult()), FPFH_WARPS * 32, 0, ctx->stream>>>(v, spfh, r2, d_out, qpos, nq);
+    k_fpfh_weight<OneGrid><<<std::min(nblk(nq, FPFH_WARPS), ctx->sm_count * wide_grid_mult()), FPFH_WARPS * 32, 0, ctx->stream>>>(ov, spfh, r2, d_out, qpos, nq);
     RTR_LAUNCH_CHECK(ctx, "fpfh.weight");
     dev_free(ctx, inv); dev_free(ctx, qpos); dev_free(ctx, list); dev_free(ctx, count); dev_free(ctx, flags); dev_free(ctx, spfh); dev_free(ctx, temp);
     return 0;

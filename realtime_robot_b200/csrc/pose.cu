@@ -257,6 +257,266 @@ int rtr_ransac_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_ransac_params* p, r
     return 0;
 }
 
+// ============================================================================= RANSAC over a model set
+// Every member cloud's hypotheses in the same launches: slot t of [0, nseg * H) is hypothesis h_base + t % H of member
+// t / H, evaluated against the one target (the scan).  Draws, prerejection, pose fit, the slice shape of the inlier sums and
+// the acceptance rule are the single-cloud kernels', so each member's record equals what rtr_ransac_prerejective returns
+// for it alone.
+struct RansacMany {
+    int nseg;
+    int pt_begin[RTR_MAX_SEGMENTS + 1];       // member k = source points [pt_begin[k], pt_begin[k+1]) of src_all / knn_all
+    int split[RTR_MAX_SEGMENTS];              // slices of member k's cloud per surviving hypothesis (as rtr_ransac_dev sizes them)
+    const float4* src_all;
+    const int* knn_all;
+    int H;                                    // hypotheses per member in this pass
+};
+__device__ __forceinline__ RansacArgs ransac_member(const RansacArgs& common, const RansacMany& rm, int k) {
+    RansacArgs a = common;
+    a.src = rm.src_all + rm.pt_begin[k];
+    a.ns = rm.pt_begin[k + 1] - rm.pt_begin[k];
+    a.knn = rm.knn_all + (size_t)rm.pt_begin[k] * common.knn_stride;
+    return a;
+}
+
+__global__ void __launch_bounds__(256) k_ransac_sample_many(const __grid_constant__ RansacMany rm, RansacArgs common, int* __restrict__ survivors,
+                                                            int* __restrict__ count) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    if (t < (long long)rm.nseg * rm.H) {
+        const int k = (int)(t / rm.H), hl = (int)(t - (long long)k * rm.H);
+        const RansacArgs a = ransac_member(common, rm, k);
+        if (a.ns >= 3 && a.nt >= 1) {
+            int s[3], c[3];
+            ok = draw_hypothesis(a, (unsigned long long)(a.h_base + hl), s, c);
+            if (ok) {
+                float4 ps[3], pt[3];
+#pragma unroll
+                for (int e = 0; e < 3; ++e) { ps[e] = __ldg(a.src + s[e]); pt[e] = __ldg(a.tgt + c[e]); }
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                    int f = (e + 1) % 3;
+                    float ds = dist2f(ps[e].x, ps[e].y, ps[e].z, ps[f].x, ps[f].y, ps[f].z);
+                    float dt = dist2f(pt[e].x, pt[e].y, pt[e].z, pt[f].x, pt[f].y, pt[f].z);
+                    float sim = ds < dt ? __fdiv_rn(ds, dt) : __fdiv_rn(dt, ds);
+                    if (!(sim >= a.simsq)) ok = false;
+                }
+            }
+        }
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, ok);
+    if (mask) {
+        int lane = threadIdx.x & 31;
+        int leader = __ffs(mask) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(count, __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (ok) survivors[base + __popc(mask & ((1u << lane) - 1u))] = (int)t;
+    }
+}
+
+// pose of every survivor + its evaluation work items: split[k] consecutive entries of `items` ((survivor << 5) | slice)
+__global__ void __launch_bounds__(64) k_ransac_pose_many(const __grid_constant__ RansacMany rm, RansacArgs common, const int* __restrict__ survivors,
+                                                         const int* __restrict__ count, float* __restrict__ poses, int* __restrict__ item_first,
+                                                         int* __restrict__ items, int* __restrict__ n_items) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *count) return;
+    const int slot = survivors[t];
+    const int k = slot / rm.H, hl = slot - k * rm.H;
+    const RansacArgs a = ransac_member(common, rm, k);
+    int s[3], c[3];
+    draw_hypothesis(a, (unsigned long long)(a.h_base + hl), s, c);
+    double ss[3] = {0, 0, 0}, st[3] = {0, 0, 0}, m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        float4 p = __ldg(a.src + s[e]), q = __ldg(a.tgt + c[e]);
+        double sv[3] = {p.x, p.y, p.z}, tv[3] = {q.x, q.y, q.z};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            ss[i] += sv[i]; st[i] += tv[i];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) m[i * 3 + j] += sv[i] * tv[j];
+        }
+    }
+    float pose[16];
+    horn_pose(ss, st, m, 3.0, pose);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) poses[(size_t)t * 16 + i] = pose[i];
+    const int split = rm.split[k];
+    const int first = atomicAdd(n_items, split);
+    item_first[t] = first;
+    for (int j = 0; j < split; ++j) items[first + j] = (t << 5) | j;
+}
+
+__global__ void __launch_bounds__(EVAL_THREADS) k_ransac_eval_many(const __grid_constant__ RansacMany rm, RansacArgs common, GridView g,
+                                                                   const int* __restrict__ survivors, const float* __restrict__ poses,
+                                                                   const int* __restrict__ items, const int* __restrict__ n_items,
+                                                                   double* __restrict__ psum, int* __restrict__ pcnt) {
+    __shared__ float m[16];
+    __shared__ double wsum[EVAL_THREADS / 32];
+    __shared__ int wcnt[EVAL_THREADS / 32];
+    const int n = *n_items;
+    for (int w = blockIdx.x; w < n; w += gridDim.x) {
+        const int item = items[w];
+        const int t = item >> 5, part = item & 31;
+        const int k = survivors[t] / rm.H;
+        const float4* src = rm.src_all + rm.pt_begin[k];
+        const int ns = rm.pt_begin[k + 1] - rm.pt_begin[k];
+        const int split = rm.split[k];
+        const int chunk = (ns + split - 1) / split;
+        const int i0 = part * chunk, i1 = min(ns, i0 + chunk);
+        __syncthreads();
+        if (threadIdx.x < 16) m[threadIdx.x] = poses[(size_t)t * 16 + threadIdx.x];
+        __syncthreads();
+        int cnt = 0;
+        double sum = 0;
+        for (int i = i0 + threadIdx.x; i < i1; i += EVAL_THREADS) {
+            float4 q = xform(m, __ldg(src + i));
+            float best = FLT_MAX;
+            for_block27(g, q.x, q.y, q.z, [&](int, float4, float d2) { if (d2 < best) best = d2; });
+            if (best < common.dmax2) { ++cnt; sum += (double)best; }
+        }
+        cnt = warp_sum(cnt);
+        sum = warp_sum(sum);
+        if ((threadIdx.x & 31) == 0) { wsum[threadIdx.x >> 5] = sum; wcnt[threadIdx.x >> 5] = cnt; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double S = 0; int C = 0;
+#pragma unroll
+            for (int ww = 0; ww < EVAL_THREADS / 32; ++ww) { S += wsum[ww]; C += wcnt[ww]; }
+            psum[w] = S; pcnt[w] = C;
+        }
+    }
+}
+
+// one CTA per member: its record (initialised here), the arg-min over its survivors
+__global__ void __launch_bounds__(1024) k_ransac_select_many(const __grid_constant__ RansacMany rm, RansacArgs common, const int* __restrict__ survivors,
+                                                             const int* __restrict__ count, const float* __restrict__ poses,
+                                                             const int* __restrict__ item_first, const double* __restrict__ psum,
+                                                             const int* __restrict__ pcnt, rtr_pose_result* __restrict__ res_all) {
+    __shared__ float s_err[32];
+    __shared__ long long s_h[32];
+    __shared__ int s_t[32];
+    __shared__ int s_n[32];
+    const int k = blockIdx.x;
+    const int ns = rm.pt_begin[k + 1] - rm.pt_begin[k];
+    const int split = rm.split[k];
+    rtr_pose_result* res = res_all + k;
+    const int n = *count;
+    float be = FLT_MAX; long long bh = -1; int bt = -1; int mine = 0;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int slot = survivors[t];
+        if (slot / rm.H != k) continue;
+        ++mine;
+        const int first = item_first[t];
+        double S = 0; int c = 0;
+        for (int p = 0; p < split; ++p) { S += psum[first + p]; c += pcnt[first + p]; }
+        float frac = __fdiv_rn((float)c, (float)ns);
+        if (frac >= common.inlier_fraction) {
+            float e = c > 0 ? (float)(S / (double)c) : FLT_MAX;
+            long long h = common.h_base + (slot - k * rm.H);
+            if (e < be || (e == be && (bh < 0 || h < bh))) { be = e; bh = h; bt = t; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float oe = __shfl_xor_sync(0xffffffffu, be, o);
+        long long oh = __shfl_xor_sync(0xffffffffu, bh, o);
+        int ot = __shfl_xor_sync(0xffffffffu, bt, o);
+        mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if (oh >= 0 && (bh < 0 || oe < be || (oe == be && oh < bh))) { be = oe; bh = oh; bt = ot; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_err[threadIdx.x >> 5] = be; s_h[threadIdx.x >> 5] = bh; s_t[threadIdx.x >> 5] = bt; s_n[threadIdx.x >> 5] = mine; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        be = FLT_MAX; bh = -1; bt = -1; mine = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            float oe = s_err[w]; long long oh = s_h[w]; int ot = s_t[w];
+            mine += s_n[w];
+            if (oh >= 0 && (bh < 0 || oe < be || (oe == be && oh < bh))) { be = oe; bh = oh; bt = ot; }
+        }
+        for (int i = 0; i < 16; ++i) res->pose[i] = (i % 5 == 0) ? 1.f : 0.f;
+        res->fitness = FLT_MAX; res->inliers = 0; res->hypothesis = -1; res->evaluated = mine; res->converged = 0;
+        res->iterations = 0; res->model_id = k; res->n_keypoints_src = 0; res->n_keypoints_tgt = 0;
+        for (int i = 0; i < 5; ++i) res->pad_[i] = 0;
+        if (bh >= 0 && be < FLT_MAX) {
+            const int first = item_first[bt];
+            int c = 0;
+            for (int p = 0; p < split; ++p) c += pcnt[first + p];
+            for (int i = 0; i < 16; ++i) res->pose[i] = poses[(size_t)bt * 16 + i];
+            res->fitness = be; res->inliers = c; res->hypothesis = bh; res->converged = 1;
+        }
+    }
+}
+
+__global__ void k_result_init_many(rtr_pose_result* res, int n) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    rtr_pose_result* r = res + k;
+    for (int i = 0; i < 16; ++i) r->pose[i] = (i % 5 == 0) ? 1.f : 0.f;
+    r->fitness = FLT_MAX; r->inliers = 0; r->hypothesis = -1; r->evaluated = 0; r->converged = 0;
+    r->iterations = 0; r->model_id = k; r->n_keypoints_src = 0; r->n_keypoints_tgt = 0;
+    for (int i = 0; i < 5; ++i) r->pad_[i] = 0;
+}
+
+// set = model set whose members [0, n_models) are the sources; the target is member `tgt_seg` (the scan).  knn_all: the
+// members' correspondences (target-local indices), n_source_points x k.  d_results: n_models records.
+static int ransac_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const int* knn_all, int knn_k, const rtr_ransac_params* p,
+                           rtr_pose_result* d_results) {
+    rtr_context* ctx = set->ctx;
+    const long long h0 = p->hypothesis_begin, h1 = (p->hypothesis_end > 0) ? p->hypothesis_end : p->max_iterations;
+    const int nt = set->seg_begin[tgt_seg + 1] - set->seg_begin[tgt_seg];
+    const long long H = h1 - h0;
+    if (H <= 0 || nt < 1) {
+        k_result_init_many<<<1, 32, 0, ctx->stream>>>(d_results, n_models);
+        RTR_LAUNCH_CHECK(ctx, "ransac.init");
+        return 0;
+    }
+    if (!(p->max_correspondence_distance > 0.f)) return rtr_fail("ransac", "max_correspondence_distance must be > 0", RTR_ERR_INVALID);
+    if (H > (1 << 20) || (long long)n_models * H > (1LL << 24)) return rtr_fail("ransac", "model-set RANSAC takes at most 2^20 hypotheses per model", RTR_ERR_INVALID);
+    // target grid for the inlier test: any cached grid of the set whose cells are >= d_max (and < 2 d_max), else one of d_max
+    DevGrid* g;
+    if (int e = rtr_get_grid_any(set, p->max_correspondence_distance, p->max_correspondence_distance * 1.001f, p->max_correspondence_distance * 2.0f, &g)) return e;
+    const GridView v = rtr_segment_view(g, set, tgt_seg);
+    RansacMany rm;
+    memset(&rm, 0, sizeof(rm));
+    rm.nseg = n_models;
+    for (int k = 0; k <= RTR_MAX_SEGMENTS; ++k) rm.pt_begin[k] = set->seg_begin[std::min(k, n_models)];
+    long long max_items = 0;
+    for (int k = 0; k < n_models; ++k) {
+        const int ns = set->seg_begin[k + 1] - set->seg_begin[k];
+        rm.split[k] = std::max(1, std::min(16, (ns + 511) / 512));        // 512-point slices, as rtr_ransac_dev
+        max_items += (long long)H * rm.split[k];
+    }
+    rm.src_all = set->pts; rm.knn_all = knn_all; rm.H = (int)H;
+    RansacArgs a;
+    a.src = nullptr; a.ns = 0; a.tgt = set->pts + set->seg_begin[tgt_seg]; a.nt = nt;
+    a.knn = nullptr; a.knn_stride = knn_k; a.k = p->correspondence_k; a.seed = p->seed;
+    a.simsq = p->similarity_threshold * p->similarity_threshold;
+    a.dmax2 = p->max_correspondence_distance * p->max_correspondence_distance;
+    a.inlier_fraction = p->inlier_fraction;
+    a.h_base = h0; a.h_count = (int)H;
+    const long long slots = (long long)n_models * H;
+    int *survivors = nullptr, *counters = nullptr, *item_first = nullptr, *items = nullptr, *pcnt = nullptr; float* poses = nullptr; double* psum = nullptr;
+    if (int e = tmp_alloc(ctx, &survivors, (size_t)slots, "ransac")) return e;
+    if (int e = tmp_alloc(ctx, &counters, 2, "ransac")) return e;
+    if (int e = tmp_alloc(ctx, &item_first, (size_t)slots, "ransac")) return e;
+    if (int e = tmp_alloc(ctx, &items, (size_t)max_items, "ransac")) return e;
+    if (int e = tmp_alloc(ctx, &pcnt, (size_t)max_items, "ransac")) return e;
+    if (int e = tmp_alloc(ctx, &psum, (size_t)max_items, "ransac")) return e;
+    if (int e = tmp_alloc(ctx, &poses, (size_t)slots * 16, "ransac")) return e;
+    RTR_CHECK(cudaMemsetAsync(counters, 0, 2 * sizeof(int), ctx->stream), "ransac");
+    RTR_MARK(ctx, "ransac.memset");
+    k_ransac_sample_many<<<nblk(slots, 256), 256, 0, ctx->stream>>>(rm, a, survivors, counters);
+    RTR_LAUNCH_CHECK(ctx, "ransac.sample");
+    k_ransac_pose_many<<<nblk(slots, 64), 64, 0, ctx->stream>>>(rm, a, survivors, counters, poses, item_first, items, counters + 1);
+    RTR_LAUNCH_CHECK(ctx, "ransac.pose");
+    k_ransac_eval_many<<<ctx->sm_count * 8, EVAL_THREADS, 0, ctx->stream>>>(rm, a, v, survivors, poses, items, counters + 1, psum, pcnt);
+    RTR_LAUNCH_CHECK(ctx, "ransac.eval");
+    k_ransac_select_many<<<n_models, 1024, 0, ctx->stream>>>(rm, a, survivors, counters, poses, item_first, psum, pcnt, d_results);
+    RTR_LAUNCH_CHECK(ctx, "ransac.select");
+    return 0;
+}
+
 // ============================================================================= ICP
 struct IcpState {
     float final_[16];
@@ -413,14 +673,14 @@ __device__ void icp_solve_thread0(const double* sums, IcpState* st, const IcpSol
 // called by every thread of a CTA (256 threads) after its partials are written
 template <int EST>
 __device__ void icp_last_cta_solve(const double* partials, IcpState* st, unsigned* ticket, const IcpSolveArgs& sa, double* sums /* smem[N] */,
-                                   int* is_last /* smem */) {
+                                   int* is_last /* smem */, const int nparts /* CTAs that share this ticket */) {
     constexpr int N = IcpSums<EST>::N;
     constexpr int G = 255 / N;          // row groups: 15 for 17 sums, 8 for 29
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned t = atomicAdd(ticket, 1u);
-        *is_last = (t == gridDim.x - 1);
+        *is_last = (t == (unsigned)nparts - 1u);
     }
     __syncthreads();
     pdl_launch_dependents();    // this CTA's part is done: the next iteration's CTAs may take their places and wait while the last CTA solves
@@ -429,7 +689,7 @@ __device__ void icp_last_cta_solve(const double* partials, IcpState* st, unsigne
     // partials is an [nparts][N] matrix: thread t < G * N owns column t % N and the rows t / N, t / N + G, ... (adjacent
     // threads read adjacent addresses), then N threads fold the G row groups in order
     __shared__ double grp[G][N];
-    const int nparts = (int)gridDim.x, t = threadIdx.x;
+    const int t = threadIdx.x;
     if (t < G * N) {
         const int k = t % N, rg = t / N;
         const double* col = partials + k;
@@ -527,30 +787,31 @@ __global__ void __launch_bounds__(ICP_THREADS, 4) k_icp_corr(GridView g, GridVie
         for (int w = 0; w < ICP_THREADS / 32; ++w) v += red[w][threadIdx.x];
         partials[(size_t)blockIdx.x * N + threadIdx.x] = v;
     }
-    icp_last_cta_solve<EST>(partials, st, ticket, sa, sums, &is_last);
+    icp_last_cta_solve<EST>(partials, st, ticket, sa, sums, &is_last, (int)gridDim.x);
 }
 
 // Small sources (repo clouds): one WARP per source point — the lanes share the candidate scan, so the per-iteration
 // latency is set by ~9 range steps instead of ~50 dependent loads.  Each warp walks a strided list of queries and keeps
 // the 17 sums in lane 0; warps are then folded through shared memory.
 #define ICPW_WARPS 8
+// bid / nblocks: this CTA's place among the CTAs that work on this source cloud (== blockIdx.x / gridDim.x for one cloud; a
+// model set gives every member cloud its own range of CTAs, state, ticket and partials — see k_icp_corr_warp_many)
 template <int EST>
-__global__ void __launch_bounds__(ICPW_WARPS * 32, 4) k_icp_corr_warp(GridView g, const float4* __restrict__ tgt_pts, const float4* __restrict__ tgt_normals,
-                                                                   float4* __restrict__ cur, int n, IcpState* st, double dmax2, float prune2,
-                                                                   double* partials, unsigned* ticket, IcpSolveArgs sa) {
+__device__ __forceinline__ void icp_corr_warp_body(const GridView& g, const float4* __restrict__ tgt_pts, const float4* __restrict__ tgt_normals,
+                                                   float4* __restrict__ cur, int n, IcpState* st, double dmax2, float prune2,
+                                                   double* partials, unsigned* ticket, const IcpSolveArgs& sa, const int bid, const int nblocks) {
     constexpr int N = IcpSums<EST>::N;
     __shared__ float m[16];
     __shared__ double red[ICPW_WARPS][N];      // lane 0 of every warp accumulates its queries here, in query order
     __shared__ double sums[N];
     __shared__ int is_last;
-    pdl_wait();                 // the previous iteration (or k_icp_init) has completed: st, cur, ticket are current
     if (st->done) return;
     int have = st->have_step;
     if (threadIdx.x < 16) m[threadIdx.x] = st->step[threadIdx.x];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane < N) red[warp][lane] = 0.0;
     __syncthreads();
-    int nwarps = gridDim.x * ICPW_WARPS;
+    int nwarps = nblocks * ICPW_WARPS;
     double* acc = red[warp];
     auto add = [&](float4 q, int b, float d2, float4 t) {
         if (lane == 0 && b >= 0 && (double)d2 <= dmax2) {
@@ -561,7 +822,7 @@ __global__ void __launch_bounds__(ICPW_WARPS * 32, 4) k_icp_corr_warp(GridView g
     };
     if (g.n <= RTR_BRUTE_NN_MAX) {
         // two of this warp's queries per pass (i, i + nwarps): same warp -> query assignment and accumulation order as below
-        for (int i = blockIdx.x * ICPW_WARPS + warp; i < n; i += 2 * nwarps) {
+        for (int i = bid * ICPW_WARPS + warp; i < n; i += 2 * nwarps) {
             int i2 = i + nwarps;
             bool two = i2 < n;
             float4 q = cur[i], q2 = two ? cur[i2] : q;
@@ -577,7 +838,7 @@ __global__ void __launch_bounds__(ICPW_WARPS * 32, 4) k_icp_corr_warp(GridView g
             }
         }
     } else {
-        for (int i = blockIdx.x * ICPW_WARPS + warp; i < n; i += nwarps) {
+        for (int i = bid * ICPW_WARPS + warp; i < n; i += nwarps) {
             float4 q = cur[i];
             if (have) { q = xform(m, q); if (lane == 0) cur[i] = q; }
             int b; float d2; float4 t;
@@ -590,26 +851,57 @@ __global__ void __launch_bounds__(ICPW_WARPS * 32, 4) k_icp_corr_warp(GridView g
         double v = 0;
 #pragma unroll
         for (int w = 0; w < ICPW_WARPS; ++w) v += red[w][threadIdx.x];
-        partials[(size_t)blockIdx.x * N + threadIdx.x] = v;
+        partials[(size_t)bid * N + threadIdx.x] = v;
     }
-    icp_last_cta_solve<EST>(partials, st, ticket, sa, sums, &is_last);
+    icp_last_cta_solve<EST>(partials, st, ticket, sa, sums, &is_last, nblocks);
+}
+
+template <int EST>
+__global__ void __launch_bounds__(ICPW_WARPS * 32, 4) k_icp_corr_warp(GridView g, const float4* __restrict__ tgt_pts, const float4* __restrict__ tgt_normals,
+                                                                   float4* __restrict__ cur, int n, IcpState* st, double dmax2, float prune2,
+                                                                   double* partials, unsigned* ticket, IcpSolveArgs sa) {
+    pdl_wait();                 // the previous iteration (or k_icp_init) has completed: st, cur, ticket are current
+    icp_corr_warp_body<EST>(g, tgt_pts, tgt_normals, cur, n, st, dmax2, prune2, partials, ticket, sa, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// Model set: the CTAs of every member cloud in one launch.  cta_begin[k] .. cta_begin[k+1] work on member k with the CTA
+// count the single-cloud launch would use, so the summation shape — and with it every bit of the pose — is the same.
+struct IcpMany {
+    int nseg;
+    int pt_begin[RTR_MAX_SEGMENTS + 1];
+    int cta_begin[RTR_MAX_SEGMENTS + 1];      // unused tail = total CTAs
+};
+__device__ __forceinline__ int icp_many_segment(const IcpMany& im, int b) {
+    int k = 0;
+#pragma unroll
+    for (int step = RTR_MAX_SEGMENTS / 2; step > 0; step >>= 1) if (b >= im.cta_begin[k + step]) k += step;
+    return k;
+}
+template <int EST>
+__global__ void __launch_bounds__(ICPW_WARPS * 32, 4) k_icp_corr_warp_many(const __grid_constant__ IcpMany im, GridView g, const float4* __restrict__ tgt_pts,
+                                                                        const float4* __restrict__ tgt_normals, float4* __restrict__ cur_all, IcpState* st_all,
+                                                                        double dmax2, float prune2, double* partials_all, unsigned* ticket_all, IcpSolveArgs sa) {
+    pdl_wait();
+    const int k = icp_many_segment(im, (int)blockIdx.x);
+    const int b0 = im.cta_begin[k];
+    icp_corr_warp_body<EST>(g, tgt_pts, tgt_normals, cur_all + im.pt_begin[k], im.pt_begin[k + 1] - im.pt_begin[k], st_all + k, dmax2, prune2,
+                            partials_all + (size_t)b0 * ICP_NSUM_MAX, ticket_all + k, sa, (int)blockIdx.x - b0, im.cta_begin[k + 1] - b0);
 }
 
 // last CTA of the fitness kernel: fold the (sum d2, count) partials in a fixed shape and write the result record
 __device__ void icp_last_cta_finish(const double* partials, const IcpState* st, unsigned* ticket, rtr_pose_result* res, int keep_ransac_fields,
-                                    double* sums /* smem[2] */, int* is_last /* smem */) {
+                                    double* sums /* smem[2] */, int* is_last /* smem */, const int nparts) {
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned t = atomicAdd(ticket, 1u);
-        *is_last = (t == gridDim.x - 1);
+        *is_last = (t == (unsigned)nparts - 1u);
     }
     __syncthreads();
     if (!*is_last) return;
     __threadfence();
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp < 2) {
-        const int nparts = (int)gridDim.x;
         const double* col = partials + warp;
         double v = 0;
         int b = lane;
@@ -640,24 +932,24 @@ __device__ void icp_last_cta_finish(const double* partials, const IcpState* st, 
     }
 }
 
-__global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_fitness_warp(GridView g, const float4* __restrict__ src, int n, const IcpState* __restrict__ st,
-                                                                      double* partials, unsigned* ticket, rtr_pose_result* res, int keep_ransac_fields) {
+__device__ __forceinline__ void icp_fitness_warp_body(const GridView& g, const float4* __restrict__ src, int n, const IcpState* __restrict__ st,
+                                                      double* partials, unsigned* ticket, rtr_pose_result* res, int keep_ransac_fields,
+                                                      const int bid, const int nblocks) {
     __shared__ float m[16];
     __shared__ double red[ICPW_WARPS][2];
     __shared__ double sums[2];
     __shared__ int is_last;
-    pdl_wait();
     if (st->skipped) {     // pose / fitness stay RANSAC's (identity, FLT_MAX)
-        if (blockIdx.x == 0 && threadIdx.x == 0) { res->iterations = 0; res->converged = 0; }
+        if (bid == 0 && threadIdx.x == 0) { res->iterations = 0; res->converged = 0; }
         return;
     }
     if (threadIdx.x < 16) m[threadIdx.x] = st->final_[threadIdx.x];
     __syncthreads();
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int nwarps = gridDim.x * ICPW_WARPS;
+    int nwarps = nblocks * ICPW_WARPS;
     double s = 0, c = 0;
     if (g.n <= RTR_BRUTE_NN_MAX) {
-        for (int i = blockIdx.x * ICPW_WARPS + warp; i < n; i += 2 * nwarps) {
+        for (int i = bid * ICPW_WARPS + warp; i < n; i += 2 * nwarps) {
             int i2 = i + nwarps;
             bool two = i2 < n;
             float4 q = xform(m, __ldg(src + i));
@@ -668,7 +960,7 @@ __global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_fitness_warp(GridView g
             if (lane == 0 && two && b2 >= 0) { s += (double)d22; c += 1.0; }
         }
     } else {
-        for (int i = blockIdx.x * ICPW_WARPS + warp; i < n; i += nwarps) {
+        for (int i = bid * ICPW_WARPS + warp; i < n; i += nwarps) {
             float4 q = xform(m, __ldg(src + i));
             int b; float d2; float4 t;
             grid_nearest_warp(g, q.x, q.y, q.z, FLT_MAX, lane, b, d2, t);
@@ -681,9 +973,25 @@ __global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_fitness_warp(GridView g
         double v = 0;
 #pragma unroll
         for (int w = 0; w < ICPW_WARPS; ++w) v += red[w][threadIdx.x];
-        partials[(size_t)blockIdx.x * 2 + threadIdx.x] = v;
+        partials[(size_t)bid * 2 + threadIdx.x] = v;
     }
-    icp_last_cta_finish(partials, st, ticket, res, keep_ransac_fields, sums, &is_last);
+    icp_last_cta_finish(partials, st, ticket, res, keep_ransac_fields, sums, &is_last, nblocks);
+}
+
+__global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_fitness_warp(GridView g, const float4* __restrict__ src, int n, const IcpState* __restrict__ st,
+                                                                      double* partials, unsigned* ticket, rtr_pose_result* res, int keep_ransac_fields) {
+    pdl_wait();
+    icp_fitness_warp_body(g, src, n, st, partials, ticket, res, keep_ransac_fields, (int)blockIdx.x, (int)gridDim.x);
+}
+
+__global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_fitness_warp_many(const __grid_constant__ IcpMany im, GridView g, const float4* __restrict__ src_all,
+                                                                           const IcpState* __restrict__ st_all, double* partials_all, unsigned* ticket_all,
+                                                                           rtr_pose_result* res_all) {
+    pdl_wait();
+    const int k = icp_many_segment(im, (int)blockIdx.x);
+    const int b0 = im.cta_begin[k];
+    icp_fitness_warp_body(g, src_all + im.pt_begin[k], im.pt_begin[k + 1] - im.pt_begin[k], st_all + k, partials_all + (size_t)b0 * ICP_NSUM_MAX, ticket_all + k,
+                          res_all + k, 1, (int)blockIdx.x - b0, im.cta_begin[k + 1] - b0);
 }
 
 // getFitnessScore(): mean squared NN distance of (final o source)
@@ -723,7 +1031,7 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_fitness(GridView g, GridVie
         for (int w = 0; w < ICP_THREADS / 32; ++w) v += red[w][threadIdx.x];
         partials[(size_t)blockIdx.x * 2 + threadIdx.x] = v;
     }
-    icp_last_cta_finish(partials, st, ticket, res, keep_ransac_fields, sums, &is_last);
+    icp_last_cta_finish(partials, st, ticket, res, keep_ransac_fields, sums, &is_last, (int)gridDim.x);
 }
 
 int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const float* d_init_pose16, int init_from_result,
@@ -826,6 +1134,84 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     return 0;
 }
 
+// ---- ICP over a model set: every member's refinement in the same launches (one per iteration) --------------------------
+__global__ void k_icp_init_many(const __grid_constant__ IcpMany im, const float4* __restrict__ src_all, const rtr_pose_result* __restrict__ res_all,
+                                float4* __restrict__ cur_all, IcpState* __restrict__ st_all, unsigned* __restrict__ ticket_all) {
+    const int total = im.pt_begin[RTR_MAX_SEGMENTS];
+    if (blockIdx.x == 0 && threadIdx.x < im.nseg) {
+        const int k = threadIdx.x;
+        IcpState* st = st_all + k;
+        for (int i = 0; i < 16; ++i) { st->final_[i] = res_all[k].pose[i]; st->step[i] = (i % 5 == 0) ? 1.f : 0.f; }
+        const int skip = res_all[k].converged == 0 ? 1 : 0;
+        st->prev_mse = DBL_MAX; st->iterations = 0; st->done = skip; st->state = 0; st->corr = 0; st->have_step = 0; st->skipped = skip;
+        ticket_all[k] = 0u;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int k = 0;
+#pragma unroll
+        for (int step = RTR_MAX_SEGMENTS / 2; step > 0; step >>= 1) if (i >= im.pt_begin[k + step]) k += step;
+        cur_all[i] = xform(res_all[k].pose, __ldg(src_all + i));
+    }
+}
+
+static int icp_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const rtr_icp_params* p, rtr_pose_result* d_results) {
+    rtr_context* ctx = set->ctx;
+    if (p->estimator != 0 && p->estimator != 1) return rtr_fail("icp", "estimator must be 0 (SVD) or 1 (point-to-plane LLS)", RTR_ERR_INVALID);
+    if (p->estimator == 1 && !set->normals) return rtr_fail("icp", "estimator 1 (point-to-plane) needs normals on the target", RTR_ERR_NOT_READY);
+    const int t0 = set->seg_begin[tgt_seg], nt = set->seg_begin[tgt_seg + 1] - t0;
+    const int n_src = set->seg_begin[n_models];
+    // target search structure: scans up to RTR_BRUTE_NN_MAX points are searched without one (the kernels only stride over the
+    // target's points: any grid's copy serves); larger scans use the cached grid closest to the ICP cell, as rtr_icp_dev does.
+    // Either way the neighbour is the exact one.
+    GridView v;
+    if (nt <= RTR_BRUTE_NN_MAX) {
+        if (set->grids.empty()) return rtr_fail("icp", "model set has no grid", RTR_ERR_NOT_READY);
+        v = rtr_segment_view(&set->grids.begin()->second, set, tgt_seg);
+        v.sorted += t0;            // the brute-force scan reads sorted[0 .. n)
+    } else {
+        rtr_cloud box;             // a bounding box + size only, for the cell heuristic
+        box.n = nt;
+        for (int a = 0; a < 3; ++a) { box.bb_min[a] = set->seg_bb[6 * tgt_seg + a]; box.bb_max[a] = set->seg_bb[6 * tgt_seg + 3 + a]; }
+        float want = rtr_icp_cell(&box);
+        const float cap = p->max_correspondence_distance;
+        if (cap > want && cap < 3.f * want) want = cap;
+        DevGrid* g;
+        if (int e = rtr_get_grid_any(set, want, want * (cap == want ? 1.0f : 0.6f), want * 1.7f, &g)) return e;
+        v = rtr_segment_view(g, set, tgt_seg);
+    }
+    IcpMany im;
+    memset(&im, 0, sizeof(im));
+    im.nseg = n_models;
+    int ctas = 0;
+    for (int k = 0; k <= RTR_MAX_SEGMENTS; ++k) {
+        im.pt_begin[k] = set->seg_begin[std::min(k, n_models)];
+        im.cta_begin[k] = ctas;
+        if (k < n_models) ctas += std::max(1, std::min(nblk(set->seg_begin[k + 1] - set->seg_begin[k], ICPW_WARPS), ctx->sm_count * 8));
+    }
+    float4* cur = nullptr; IcpState* st = nullptr; double* partials = nullptr; unsigned* ticket = nullptr;
+    if (int e = tmp_alloc(ctx, &cur, n_src, "icp")) return e;
+    if (int e = tmp_alloc(ctx, &st, n_models, "icp")) return e;
+    if (int e = tmp_alloc(ctx, &ticket, n_models, "icp")) return e;
+    if (int e = tmp_alloc(ctx, &partials, (size_t)ctas * ICP_NSUM_MAX, "icp")) return e;
+    const IcpSolveArgs sa{p->max_iterations, p->force_iterations, p->mse_threshold_absolute};
+    k_icp_init_many<<<std::max(1, std::min(nblk(n_src, 256), 4 * ctx->sm_count)), 256, 0, ctx->stream>>>(im, set->pts, d_results, cur, st, ticket);
+    RTR_LAUNCH_CHECK(ctx, "icp.init");
+    double dmax2 = p->max_correspondence_distance > 0.f ? (double)p->max_correspondence_distance * (double)p->max_correspondence_distance : DBL_MAX;
+    float prune2 = FLT_MAX;
+    if (p->max_correspondence_distance > 0.f) { prune2 = (float)dmax2; if ((double)prune2 < dmax2) prune2 = nextafterf(prune2, FLT_MAX); }
+    const bool plane = p->estimator == 1;
+    if (nt >= 1) {
+        for (int it = 0; it < p->max_iterations; ++it) {
+            if (plane) launch_pdl(k_icp_corr_warp_many<1>, ctas, ICPW_WARPS * 32, 0, ctx->stream, im, v, (const float4*)set->pts, (const float4*)set->normals, cur, st, dmax2, prune2, partials, ticket, sa);
+            else launch_pdl(k_icp_corr_warp_many<0>, ctas, ICPW_WARPS * 32, 0, ctx->stream, im, v, (const float4*)set->pts, (const float4*)nullptr, cur, st, dmax2, prune2, partials, ticket, sa);
+            RTR_LAUNCH_CHECK(ctx, "icp.corr");
+        }
+    }
+    launch_pdl(k_icp_fitness_warp_many, ctas, ICPW_WARPS * 32, 0, ctx->stream, im, v, (const float4*)set->pts, (const IcpState*)st, partials, ticket, d_results);
+    RTR_LAUNCH_CHECK(ctx, "icp.fitness");
+    return 0;
+}
+
 // ============================================================================= whole registration
 // a zero-initialised or partly filled params struct must come back as RTR_ERR_INVALID, not hang the grid sizing
 int rtr_validate_register_params(const rtr_register_params* p) {
@@ -850,7 +1236,195 @@ static int fetch_result(rtr_context* ctx, rtr_pose_result* d_result, rtr_pose_re
     return 0;
 }
 
+// ---- one scan against many database models ------------------------------------------------------------------------------
+// The reference builds the scan side once (ScanPoint keypoints + descriptors, RealTimeRobot.cpp:45-60) and then loops over
+// model keypoints (:62-102); its database holds many candidate models (README.md:10).  Here the scan and up to 31 models
+// form one model set (the scan is the last member): every per-cloud stage is ONE launch over all of them, descriptor
+// matching is one search of all model features against the scan's, and RANSAC / ICP run all models' hypotheses / iterations
+// in shared launches.  About 35 launches for the whole batch instead of ~45 per registration, and the scan's stages run once.
+#define RTR_KP_PREVIEW 64       // corners per cloud returned with the results (rtr_register_many_keypoints)
+struct KpPreview { int count; int pad_[3]; float4 xyz[RTR_KP_PREVIEW]; };
+
+__global__ void k_register_finish_many(const __grid_constant__ IcpMany im, rtr_pose_result* __restrict__ res, const int* __restrict__ kp_count,
+                                       const float4* __restrict__ kp_xyz_all, int n_members, KpPreview* __restrict__ preview) {
+    const int k = blockIdx.x;       // member (models first, the scan last)
+    const int n_models = n_members - 1;
+    if (threadIdx.x == 0 && k < n_models) { res[k].n_keypoints_src = kp_count[k]; res[k].n_keypoints_tgt = kp_count[n_models]; }
+    const int cnt = kp_count[k];
+    if (threadIdx.x == 0) preview[k].count = cnt;
+    // corner list of member k starts at its first point index (im.pt_begin covers the models; the scan follows them)
+    const int first = k < n_models ? im.pt_begin[k] : im.pt_begin[RTR_MAX_SEGMENTS];
+    for (int i = threadIdx.x; i < min(cnt, RTR_KP_PREVIEW); i += blockDim.x) preview[k].xyz[i] = kp_xyz_all[first + i];
+}
+
+// set: n_models + 1 members, the scan last.  Queues everything on the context's stream, ends with the D2H of the records
+// (and the corner previews) into the context's pinned area.
+static int register_many_enqueue(rtr_cloud* set, int n_models, const rtr_register_params* p) {
+    rtr_context* ctx = set->ctx;
+    const int tgt = n_models, nseg = n_models + 1;
+    for (int k = 0; k < nseg; ++k)
+        if (set->seg_begin[k + 1] - set->seg_begin[k] >= 65536) return rtr_fail("register_many", "member clouds of a model set hold fewer than 65536 points", RTR_ERR_INVALID);
+    const int n_src = set->seg_begin[n_models], nt = set->n - n_src;
+    float cells[3] = {p->normal_radius, p->fpfh_radius, p->harris_radius};
+    DevGrid* gs[3];
+    if (int e = rtr_get_grids(set, cells, p->harris_radius == p->normal_radius ? 2 : 3, gs)) return e;
+    if (int e = rtr_normals_dev(set, p->normal_radius)) return e;
+    int* d_idx = nullptr; float4* d_xyz = nullptr; int* d_cnt = nullptr;
+    if (int e = rtr_harris_dev(set, p->harris_radius, p->harris_threshold, p->harris_nms, p->harris_refine, &d_idx, &d_xyz, &d_cnt)) return e;
+    if (int e = rtr_fpfh_dev(set, p->fpfh_radius)) return e;
+    const int k = p->ransac.correspondence_k;
+    int* knn = nullptr; float* knn_dist = nullptr;
+    if (int e = tmp_alloc(ctx, &knn, (size_t)n_src * k, "register_many")) return e;
+    if (int e = tmp_alloc(ctx, &knn_dist, (size_t)n_src * k, "register_many")) return e;
+    if (int e = rtr_match_features_dev(ctx, set->fpfh, n_src, set->fpfh + (size_t)n_src * 33, nt, k, knn, knn_dist)) return e;
+    rtr_pose_result* d_res = nullptr; KpPreview* d_prev = nullptr;
+    if (int e = tmp_alloc(ctx, &d_res, n_models, "register_many")) return e;
+    if (int e = tmp_alloc(ctx, &d_prev, nseg, "register_many")) return e;
+    if (int e = ransac_many_dev(set, n_models, tgt, knn, k, &p->ransac, d_res)) return e;
+    if (p->run_icp) if (int e = icp_many_dev(set, n_models, tgt, &p->icp, d_res)) return e;
+    IcpMany im;
+    memset(&im, 0, sizeof(im));
+    im.nseg = n_models;
+    for (int kk = 0; kk <= RTR_MAX_SEGMENTS; ++kk) im.pt_begin[kk] = set->seg_begin[std::min(kk, n_models)];
+    k_register_finish_many<<<nseg, 64, 0, ctx->stream>>>(im, d_res, d_cnt, d_xyz, nseg, d_prev);
+    RTR_LAUNCH_CHECK(ctx, "register.kp");
+    const size_t res_bytes = sizeof(rtr_pose_result) * (size_t)n_models, prev_bytes = sizeof(KpPreview) * (size_t)nseg;
+    if (res_bytes + prev_bytes > ctx->pinned_bytes) return rtr_fail("register_many", "pinned result area too small", RTR_ERR_CAPACITY);
+    RTR_CHECK(cudaMemcpyAsync(ctx->pinned, d_res, res_bytes, cudaMemcpyDeviceToHost, ctx->stream), "result");
+    RTR_CHECK(cudaMemcpyAsync((char*)ctx->pinned + res_bytes, d_prev, prev_bytes, cudaMemcpyDeviceToHost, ctx->stream), "result");
+    RTR_MARK(ctx, "result.d2h");
+    return 0;
+}
+
+static bool many_shape_ok(const int* ns, int n_models, int n_scene, const rtr_register_params* p) {
+    if (n_models < 1 || n_models > RTR_MAX_SEGMENTS - 1 || n_scene >= 65536) return false;
+    for (int k = 0; k < n_models; ++k) if (ns[k] >= 65536) return false;
+    const long long H = (p->ransac.hypothesis_end > 0 ? p->ransac.hypothesis_end : p->ransac.max_iterations) - p->ransac.hypothesis_begin;
+    return H <= (1 << 20) && (long long)n_models * std::max(H, 0LL) <= (1LL << 24);
+}
+
+static int register_many_begin_set(rtr_context* ctx, rtr_cloud* set, int n_models, const rtr_register_params* p) {
+    int e;
+    {
+        TmpScope tmp_scope(ctx);
+        e = register_many_enqueue(set, n_models, p);
+    }
+    if (e) { cudaStreamSynchronize(ctx->stream); rtr_cloud_free(set); return e; }
+    ctx->pending_cloud[0] = set;
+    ctx->register_pending = n_models;
+    ctx->many_models = n_models;
+    return 0;
+}
+
 extern "C" {
+
+int rtr_register_many_begin(rtr_cloud* const* models, int n_models, rtr_cloud* scene, const rtr_register_params* p) {
+    if (!models || !scene || !p || n_models < 1) return rtr_fail("register_many", "bad argument", RTR_ERR_INVALID);
+    if (int e = rtr_validate_register_params(p)) return e;
+    rtr_context* ctx = scene->ctx;
+    if (ctx->register_pending) return rtr_fail("register_many", "a registration is already in flight on this context", RTR_ERR_INVALID);
+    if (n_models > RTR_MAX_SEGMENTS - 1) return rtr_fail("register_many", "at most 31 models per batch in the asynchronous form", RTR_ERR_INVALID);
+    int ns[RTR_MAX_SEGMENTS];
+    rtr_cloud* members[RTR_MAX_SEGMENTS];
+    for (int k = 0; k < n_models; ++k) {
+        if (!models[k] || models[k]->ctx != ctx) return rtr_fail("register_many", "models and scene must belong to one context", RTR_ERR_INVALID);
+        ns[k] = models[k]->n; members[k] = models[k];
+    }
+    members[n_models] = scene;
+    if (!many_shape_ok(ns, n_models, scene->n, p)) return rtr_fail("register_many", "batch shape not supported asynchronously (clouds >= 65536 points or > 2^20 hypotheses): use rtr_register_many", RTR_ERR_INVALID);
+    RTR_CHECK(cudaSetDevice(ctx->device), "register_many");
+    rtr_cloud* set = nullptr;
+    if (int e = rtr_model_set_from_clouds(ctx, members, n_models + 1, &set)) return e;
+    return register_many_begin_set(ctx, set, n_models, p);
+}
+
+int rtr_register_many_host_begin(rtr_context* ctx, const float* const* host_models_xyz1, const int* n_points, int n_models,
+                                 const float* host_scene_xyz1, int n_scene, const rtr_register_params* p) {
+    if (!ctx || !host_models_xyz1 || !n_points || !p || n_models < 1 || n_scene < 0 || (n_scene > 0 && !host_scene_xyz1))
+        return rtr_fail("register_many", "bad argument", RTR_ERR_INVALID);
+    if (int e = rtr_validate_register_params(p)) return e;
+    if (ctx->register_pending) return rtr_fail("register_many", "a registration is already in flight on this context", RTR_ERR_INVALID);
+    if (n_models > RTR_MAX_SEGMENTS - 1 || !many_shape_ok(n_points, n_models, n_scene, p))
+        return rtr_fail("register_many", "batch shape not supported asynchronously (> 31 models, clouds >= 65536 points or > 2^20 hypotheses): use rtr_register_many_host", RTR_ERR_INVALID);
+    RTR_CHECK(cudaSetDevice(ctx->device), "register_many");
+    const float* ptrs[RTR_MAX_SEGMENTS]; int ns[RTR_MAX_SEGMENTS];
+    for (int k = 0; k < n_models; ++k) { ptrs[k] = host_models_xyz1[k]; ns[k] = n_points[k]; }
+    ptrs[n_models] = host_scene_xyz1; ns[n_models] = n_scene;
+    rtr_cloud* set = nullptr;
+    if (int e = rtr_model_set_from_host(ctx, ptrs, ns, n_models + 1, &set)) return e;
+    return register_many_begin_set(ctx, set, n_models, p);
+}
+
+int rtr_register_many_end(rtr_context* ctx, rtr_pose_result* host_results, int capacity) {
+    if (!ctx || !host_results) return rtr_fail("register_many", "bad argument", RTR_ERR_INVALID);
+    if (!ctx->register_pending || ctx->many_models <= 0) return rtr_fail("register_many", "no batch in flight on this context", RTR_ERR_INVALID);
+    const int n = ctx->many_models;
+    if (capacity < n) return rtr_fail("register_many", "result buffer too small", RTR_ERR_CAPACITY);
+    ctx->register_pending = 0; ctx->many_models = 0;
+    cudaError_t err = cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 2; ++i) if (ctx->pending_cloud[i]) { rtr_cloud_free(ctx->pending_cloud[i]); ctx->pending_cloud[i] = nullptr; }
+    RTR_CHECK(err, "result");
+    memcpy(host_results, ctx->pinned, sizeof(rtr_pose_result) * (size_t)n);
+    // keep the corner previews for rtr_register_many_keypoints
+    ctx->kp_preview.assign((const char*)ctx->pinned + sizeof(rtr_pose_result) * (size_t)n,
+                           (const char*)ctx->pinned + sizeof(rtr_pose_result) * (size_t)n + sizeof(KpPreview) * (size_t)(n + 1));
+    ctx->kp_members = n + 1;
+    return 0;
+}
+
+int rtr_register_many_keypoints(rtr_context* ctx, int member, float* host_kp_xyz1, int capacity, int* n_keypoints) {
+    if (!ctx || !n_keypoints || capacity < 0 || (capacity > 0 && !host_kp_xyz1)) return rtr_fail("register_many", "bad argument", RTR_ERR_INVALID);
+    if (member < 0 || member >= ctx->kp_members) return rtr_fail("register_many", "no such member in the last batch", RTR_ERR_INVALID);
+    const KpPreview* pv = reinterpret_cast<const KpPreview*>(ctx->kp_preview.data()) + member;
+    *n_keypoints = pv->count;
+    const int take = std::min(std::min(pv->count, RTR_KP_PREVIEW), capacity);
+    if (take > 0) memcpy(host_kp_xyz1, pv->xyz, (size_t)take * 16);
+    return (pv->count > take) ? RTR_ERR_CAPACITY : 0;
+}
+
+int rtr_register_many(rtr_cloud* const* models, int n_models, rtr_cloud* scene, const rtr_register_params* p, rtr_pose_result* host_results) {
+    if (!models || !scene || !p || !host_results || n_models < 1) return rtr_fail("register_many", "bad argument", RTR_ERR_INVALID);
+    if (int e = rtr_validate_register_params(p)) return e;
+    // batches of up to 31 models; shapes the set path does not take (huge clouds, huge sweeps) go one model at a time
+    for (int m0 = 0; m0 < n_models; m0 += RTR_MAX_SEGMENTS - 1) {
+        const int nb = std::min(n_models - m0, RTR_MAX_SEGMENTS - 1);
+        int ns[RTR_MAX_SEGMENTS];
+        bool ok = true;
+        for (int k = 0; k < nb; ++k) { if (!models[m0 + k]) return rtr_fail("register_many", "null model", RTR_ERR_INVALID); ns[k] = models[m0 + k]->n; ok &= ns[k] >= 3; }
+        ok = ok && scene->n >= 1 && many_shape_ok(ns, nb, scene->n, p);
+        if (ok) {
+            if (int e = rtr_register_many_begin(models + m0, nb, scene, p)) return e;
+            if (int e = rtr_register_many_end(scene->ctx, host_results + m0, nb)) return e;
+        } else {
+            for (int k = 0; k < nb; ++k) {
+                if (int e = rtr_register(models[m0 + k], scene, p, host_results + m0 + k)) return e;
+                host_results[m0 + k].model_id = k;
+            }
+        }
+        for (int k = 0; k < nb; ++k) host_results[m0 + k].model_id = m0 + k;
+    }
+    return 0;
+}
+
+int rtr_register_many_host(rtr_context* ctx, const float* const* host_models_xyz1, const int* n_points, int n_models,
+                           const float* host_scene_xyz1, int n_scene, const rtr_register_params* p, rtr_pose_result* host_results) {
+    if (!ctx || !host_models_xyz1 || !n_points || !p || !host_results || n_models < 1) return rtr_fail("register_many", "bad argument", RTR_ERR_INVALID);
+    if (int e = rtr_validate_register_params(p)) return e;
+    for (int m0 = 0; m0 < n_models; m0 += RTR_MAX_SEGMENTS - 1) {
+        const int nb = std::min(n_models - m0, RTR_MAX_SEGMENTS - 1);
+        bool ok = n_scene >= 1 && many_shape_ok(n_points + m0, nb, n_scene, p);
+        for (int k = 0; k < nb; ++k) ok &= n_points[m0 + k] >= 3;
+        if (ok) {
+            if (int e = rtr_register_many_host_begin(ctx, host_models_xyz1 + m0, n_points + m0, nb, host_scene_xyz1, n_scene, p)) return e;
+            if (int e = rtr_register_many_end(ctx, host_results + m0, nb)) return e;
+        } else {
+            for (int k = 0; k < nb; ++k)
+                if (int e = rtr_register_host(ctx, host_models_xyz1[m0 + k], n_points[m0 + k], host_scene_xyz1, n_scene, p, host_results + m0 + k)) return e;
+        }
+        for (int k = 0; k < nb; ++k) host_results[m0 + k].model_id = m0 + k;
+    }
+    return 0;
+}
 
 int rtr_ransac_prerejective(rtr_cloud* source, rtr_cloud* target, const rtr_ransac_params* p, rtr_pose_result* host_result) {
     if (!source || !target || !p || !host_result || source->ctx != target->ctx) return rtr_fail("ransac", "bad argument", RTR_ERR_INVALID);
@@ -945,6 +1519,7 @@ int rtr_register_begin(rtr_cloud* model, rtr_cloud* scene, const rtr_register_pa
 int rtr_register_end(rtr_context* ctx, rtr_pose_result* host_result) {
     if (!ctx || !host_result) return rtr_fail("register", "bad argument", RTR_ERR_INVALID);
     if (!ctx->register_pending) return rtr_fail("register", "no registration in flight on this context", RTR_ERR_INVALID);
+    if (ctx->many_models > 0) return rtr_fail("register", "the registration in flight is a batch: call rtr_register_many_end", RTR_ERR_INVALID);
     ctx->register_pending = 0;
     cudaError_t err = cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 2; ++i) if (ctx->pending_cloud[i]) { rtr_cloud_free(ctx->pending_cloud[i]); ctx->pending_cloud[i] = nullptr; }

@@ -1,0 +1,136 @@
+"""rtr_register_many — one scan against many database models (RealTimeRobot.cpp:45-104 per model, README.md:10) through the
+model-set path (segmented grids, shared launches): every record must equal rtr_register's for that model BIT FOR BIT, and
+with it the CPU oracle's (tests/test_gpu_parity.py::test_register_matches_oracle pins rtr_register against the oracle)."""
+import numpy as np
+import pytest
+
+from realtime_robot_b200.params import default_register_params
+
+pytestmark = pytest.mark.gpu
+
+MODELS = ["chair1", "chair2", "chair4", "desk1", "desk2", "desk3", "sofa", "Chair_025"]
+
+
+@pytest.fixture(scope="module")
+def api(gpu_ctx):
+    from realtime_robot_b200 import api as a
+    return a
+
+
+def load(clouds, name):
+    m = clouds("desk1" if name == "desk2" else name).copy()
+    if name == "Chair_025":
+        m[:, :3] *= np.float32(0.01)
+    return m
+
+
+def core(r):
+    """every field of the record except model_id, bit-exact (pose and fitness as raw bytes)"""
+    return (r.hypothesis, r.inliers, r.evaluated, r.iterations, r.converged, r.n_keypoints_src, r.n_keypoints_tgt,
+            np.array(r.pose, dtype=np.float32).tobytes(), np.float32(r.fitness).tobytes())
+
+
+def test_register_many_equals_register_and_oracle_on_configs1(api, gpu_ctx, orc, clouds):
+    """BASELINE.json configs[1] at the benched settings: 8 models vs mcloud, 50 000 hypotheses, 10 ICP iterations."""
+    p = default_register_params()
+    scene = clouds("mcloud")
+    hosts = [load(clouds, m) for m in MODELS]
+    cs = api.Cloud(gpu_ctx, scene)
+    cms = [api.Cloud(gpu_ctx, h) for h in hosts]
+    l0 = gpu_ctx.launches
+    many = api.register_many(cms, cs, p)
+    launches_many = gpu_ctx.launches - l0
+    assert [r.model_id for r in many] == list(range(len(MODELS)))
+    l0 = gpu_ctx.launches
+    singles = []
+    for c in cms:
+        c.reset(); cs.reset()
+        singles.append(api.register(c, cs, p))
+    launches_single = gpu_ctx.launches - l0
+    for name, a, b in zip(MODELS, many, singles):
+        assert core(a) == core(b), name
+    # the batch shares its launches: the scan's stages once, every stage of the 8 models in one launch
+    assert launches_many * 5 < launches_single, (launches_many, launches_single)
+    # host-buffer form, asynchronous halves, repeatability
+    many_h = api.register_many_host(gpu_ctx, hosts, scene, p)
+    api.register_many_host_begin(gpu_ctx, hosts, scene, p)
+    many_a = api.register_many_end(gpu_ctx)
+    for a, b, c in zip(many, many_h, many_a):
+        assert bytes(a) == bytes(b) == bytes(c)
+    # and the oracle, scan-side stages once (orc_register_many)
+    orc.set_threads(0)
+    want = orc.register_many(hosts, scene, p)
+    for name, g, o in zip(MODELS, many, want):
+        assert (g.hypothesis, g.inliers, g.evaluated, g.iterations, g.converged) == (o.hypothesis, o.inliers, o.evaluated, o.iterations, o.converged), name
+        assert (g.n_keypoints_src, g.n_keypoints_tgt) == (o.n_keypoints_src, o.n_keypoints_tgt), name
+        assert np.abs(g.matrix() - o.matrix()).max() <= 1e-4 and abs(g.fitness - o.fitness) <= 1e-5, name
+    for c in cms + [cs]:
+        c.free()
+
+
+def test_register_many_keypoints_are_the_harris_corners(api, gpu_ctx, clouds):
+    p = default_register_params()
+    p.ransac.max_iterations = 2000
+    names = ["chair1", "T0_m8111", "desk1"]
+    hosts = [load(clouds, m) for m in names]
+    scene = clouds("mcloud")
+    api.register_many_host(gpu_ctx, hosts, scene, p)
+    for member, pts in enumerate(hosts + [scene]):
+        c = api.Cloud(gpu_ctx, pts)
+        c.normals(p.normal_radius)
+        _, _, kx = c.harris3d(p.harris_radius, p.harris_threshold, p.harris_nms, p.harris_refine)
+        got, n = api.register_many_keypoints(gpu_ctx, member)
+        assert n == len(kx) and np.array_equal(got, kx[:64]), member
+        c.free()
+
+
+def test_register_many_point_to_plane_and_hypothesis_shards(api, gpu_ctx, clouds):
+    """estimator 1 (6x6 LLS on the scan's normals) and a hypothesis shard [begin, end) through the batch."""
+    p = default_register_params()
+    p.icp.estimator = 1
+    p.ransac.max_iterations = 20000
+    p.ransac.hypothesis_begin, p.ransac.hypothesis_end = 5000, 17000
+    hosts = [load(clouds, m) for m in ("chair2", "chair1", "Chair_025")]
+    scene = clouds("mcloud")
+    many = api.register_many_host(gpu_ctx, hosts, scene, p)
+    for h, r in zip(hosts, many):
+        s = api.register_host(gpu_ctx, h, scene, p)
+        s.model_id = r.model_id
+        assert bytes(s) == bytes(r)
+    assert any(r.converged for r in many)
+
+
+def test_register_many_edge_cases(api, gpu_ctx, clouds):
+    """a single model; duplicates; degenerate members (empty / 2 points: per-model fallback inside the call); > 31 models."""
+    p = default_register_params()
+    p.ransac.max_iterations = 3000
+    scene = clouds("mcloud")
+    c1 = load(clouds, "chair1")
+    ref = api.register_host(gpu_ctx, c1, scene, p)
+    one = api.register_many_host(gpu_ctx, [c1], scene, p)
+    assert len(one) == 1 and bytes(one[0]) == bytes(ref)
+    tiny = np.array([[0, 0, 0, 1], [0.01, 0, 0, 1]], np.float32)
+    mixed = api.register_many_host(gpu_ctx, [c1, tiny, c1], scene, p)
+    assert [r.model_id for r in mixed] == [0, 1, 2]
+    assert mixed[1].converged == 0 and mixed[1].hypothesis == -1
+    for r in (mixed[0], mixed[2]):
+        r.model_id = 0
+        assert bytes(r) == bytes(ref)
+    many = api.register_many_host(gpu_ctx, [c1] * 33, scene, p)          # two batches: 31 + 2
+    assert [r.model_id for r in many] == list(range(33))
+    for r in many:
+        r.model_id = 0
+        assert bytes(r) == bytes(ref)
+    # a scan that matches nothing: every record is the "nothing accepted" record
+    far = scene.copy(); far[:, :3] *= np.float32(0.01)
+    none = api.register_many_host(gpu_ctx, [c1, load(clouds, "desk1")], far, p)
+    for h, r in zip([c1, load(clouds, "desk1")], none):
+        s = api.register_host(gpu_ctx, h, far, p)
+        s.model_id = r.model_id
+        assert bytes(s) == bytes(r)
+    # invalid parameters come back as RTR_ERR_INVALID
+    from realtime_robot_b200 import _lib
+    q = default_register_params(); q.fpfh_radius = 0.0
+    with pytest.raises(_lib.RtrError) as e:
+        api.register_many_host(gpu_ctx, [c1], scene, q)
+    assert e.value.code == 1
