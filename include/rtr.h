@@ -282,6 +282,23 @@ int rtr_register_many_end(rtr_context* ctx, rtr_pose_result* host_results, int c
  * back with the records (up to 64 per cloud; *n_keypoints is the full count, RTR_ERR_CAPACITY if not all fit). */
 int rtr_register_many_keypoints(rtr_context* ctx, int member, float* host_kp_xyz1, int capacity, int* n_keypoints);
 
+/* ------------------------------------------------------------------ multi-GPU: one small all-gather
+ * The path shards by candidate model cloud (rank r registers its models against the replicated scan) and by RANSAC hypothesis
+ * range [hypothesis_begin, hypothesis_end); the only exchange is ONE ncclAllGather of the 128-byte records.  One process per
+ * GPU; rank 0 calls rtr_comm_unique_id and ships the 128 bytes to the others by any means (MPI, a file, torch.distributed),
+ * then every rank calls rtr_comm_init on its context.  NCCL is bound at run time (the copy already in the process, else
+ * libnccl.so.2); a host without NCCL gets RTR_ERR_NOT_READY here and nothing else changes. */
+int rtr_comm_unique_id(char* id128);
+int rtr_comm_init(rtr_context* ctx, int world, int rank, const char* id128);
+int rtr_comm_destroy(rtr_context* ctx);
+int rtr_comm_world(rtr_context* ctx, int* world, int* rank);
+/* Every rank contributes n_local (<= 64, the same everywhere) records; host_all receives world x n_local in rank order.
+ * Without a communicator it is a copy.  Cost: one H2D, one ncclAllGather on the context's stream, one D2H, one sync. */
+int rtr_allgather_results(rtr_context* ctx, const rtr_pose_result* host_local, int n_local, rtr_pose_result* host_all);
+/* Winner of a hypothesis-sharded registration: arg-min over (fitness, hypothesis id) among the accepted shard records —
+ * identical on every rank and for every world size; `evaluated` is the sum over shards. */
+int rtr_select_best_hypothesis(const rtr_pose_result* records, int n, rtr_pose_result* best);
+
 /* ------------------------------------------------------------------ reference-native descriptor path */
 
 /* THE reference FFI, exported unchanged (key_point.h:35-36, kernel.cu:34-35).  Host pointers;

@@ -21,7 +21,8 @@ EXPORTS = [
     "rtr_native_pair_scores", "rtr_native_register", "rtr_plane_areas", "rtr_pcd_info", "rtr_pcd_read", "rtr_pcd_load", "rtr_pcd_write",
     "rtr_cloud_save", "rtr_register_begin", "rtr_register_host_begin", "rtr_register_end", "rtr_context_create_prio",
     "rtr_register_many", "rtr_register_many_host", "rtr_register_many_begin", "rtr_register_many_host_begin", "rtr_register_many_end",
-    "rtr_register_many_keypoints",
+    "rtr_register_many_keypoints", "rtr_comm_unique_id", "rtr_comm_init", "rtr_comm_destroy", "rtr_comm_world", "rtr_allgather_results",
+    "rtr_select_best_hypothesis",
 ]
 
 
@@ -89,6 +90,12 @@ def lib():
         L.rtr_register_many_host_begin.argtypes = [vp, C.POINTER(vp), ip, C.c_int, vp, C.c_int, C.POINTER(RegisterParams)]
         L.rtr_register_many_end.argtypes = [vp, C.POINTER(PoseResult), C.c_int]
         L.rtr_register_many_keypoints.argtypes = [vp, C.c_int, vp, C.c_int, ip]
+        L.rtr_comm_unique_id.argtypes = [C.c_char_p]
+        L.rtr_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+        L.rtr_comm_destroy.argtypes = [vp]
+        L.rtr_comm_world.argtypes = [vp, ip, ip]
+        L.rtr_allgather_results.argtypes = [vp, C.POINTER(PoseResult), C.c_int, C.POINTER(PoseResult)]
+        L.rtr_select_best_hypothesis.argtypes = [C.POINTER(PoseResult), C.c_int, C.POINTER(PoseResult)]
         L.rtr_pcd_info.argtypes = [C.c_char_p, ip, ip]
         L.rtr_pcd_read.argtypes = [C.c_char_p, vp, C.c_int, ip]
         L.rtr_pcd_load.argtypes = [vp, C.c_char_p, C.POINTER(vp)]

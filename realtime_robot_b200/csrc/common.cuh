@@ -134,6 +134,9 @@ struct rtr_context {
     int many_models = 0;                  // > 0: the registration in flight is a batch of that many models (rtr_register_many_begin)
     std::vector<char> kp_preview;         // corner previews of the last batch (rtr_register_many_keypoints)
     int kp_members = 0;
+    // multi-GPU (comm.cu): an NCCL communicator on this context's stream + pre-allocated staging for the record all-gather
+    void* comm = nullptr; int comm_world = 0, comm_rank = 0;
+    void* comm_dev = nullptr; void* comm_pinned = nullptr;
     // pinned staging of rtr_pcd_load (decoded points, grown on demand)
     void* io_pinned = nullptr;
     size_t io_pinned_cap = 0;

@@ -779,10 +779,13 @@ int rtr_context_create_prio(int device, int urgency, rtr_context** out) {
     return 0;
 }
 
+int rtr_comm_destroy(rtr_context* ctx);
+
 int rtr_context_destroy(rtr_context* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    rtr_comm_destroy(ctx);
     for (int i = 0; i < RTR_NUM_EVENTS; ++i) if (ctx->events[i]) cudaEventDestroy(ctx->events[i]);
     for (auto& sl : ctx->slabs) cudaFree(sl.base);
     for (auto& m : ctx->marks) cudaEventDestroy(m.ev);

@@ -96,8 +96,12 @@ __device__ __forceinline__ void for_block27_warp(const GridView& g, float qx, fl
 // repo-sized clouds (a few thousand points) cannot fill the GPU with one thread per point: one WARP per point, lanes
 // stride over the candidates, fp64 partial sums folded with a warp-shuffle tree.
 #define PW_WARPS 8
+// The eigen-solve is serial fp64 (cyclic Jacobi: divisions, square roots) — run by lane 0 of a warp it costs the whole warp
+// ~1500 issue slots per point, half of this kernel's instructions on the bench batch (ncu: 221 M warp instructions for 75 k
+// points).  So the warps only gather and reduce (the ten sums go to global memory, 80 B per point), and k_normals_solve
+// runs the solve with one THREAD per point: every lane busy, same sums, same operations, same bits.
 template <class GS>
-__global__ void __launch_bounds__(PW_WARPS * 32) k_normals_warp(const __grid_constant__ GS gs, float r2, float4* __restrict__ normals) {
+__global__ void __launch_bounds__(PW_WARPS * 32) k_normals_warp(const __grid_constant__ GS gs, float r2, double* __restrict__ sums /* [10][total] */) {
     int lane = threadIdx.x & 31;
     int nwarps = gridDim.x * PW_WARPS;
     const int total = gs.total();
@@ -117,8 +121,20 @@ __global__ void __launch_bounds__(PW_WARPS * 32) k_normals_warp(const __grid_con
         cnt = warp_sum(cnt);
         sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
         cxx = warp_sum(cxx); cxy = warp_sum(cxy); cxz = warp_sum(cxz); cyy = warp_sum(cyy); cyz = warp_sum(cyz); czz = warp_sum(czz);
-        if (lane == 0) normals[__float_as_int(q.w)] = normal_from_sums(q, cnt, sx, sy, sz, cxx, cxy, cxz, cyy, cyz, czz);
+        // lane k stores sum k (one coalescing-friendly store per lane instead of ten by lane 0)
+        double v = lane == 0 ? sx : lane == 1 ? sy : lane == 2 ? sz : lane == 3 ? cxx : lane == 4 ? cxy : lane == 5 ? cxz : lane == 6 ? cyy
+                 : lane == 7 ? cyz : lane == 8 ? czz : (double)cnt;
+        if (lane < 10) sums[(size_t)lane * total + s] = v;
     }
+}
+__global__ void __launch_bounds__(128) k_normals_solve(const float4* __restrict__ sorted, int total, const double* __restrict__ sums,
+                                                       float4* __restrict__ normals) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= total) return;
+    const float4 q = __ldg(sorted + s);
+    const size_t t = (size_t)total;
+    normals[__float_as_int(q.w)] = normal_from_sums(q, (int)sums[9 * t + s], sums[s], sums[t + s], sums[2 * t + s], sums[3 * t + s], sums[4 * t + s],
+                                                    sums[5 * t + s], sums[6 * t + s], sums[7 * t + s], sums[8 * t + s]);
 }
 
 // ----------------------------------------------------------------------------- Harris 3D (App. A.3)
@@ -936,13 +952,21 @@ int rtr_normals_dev(rtr_cloud* c, float radius) {
     if (int e = rtr_get_grid(c, radius, &g)) return e;
     if (!c->normals) if (int e = dev_alloc(ctx, &c->normals, c->n, "normals")) return e;
     if (c->n > 0) {
-        if (c->nseg() > 0)
-            k_normals_warp<ManyGrids><<<std::min(nblk(c->n, PW_WARPS), ctx->sm_count * wide_grid_mult()), PW_WARPS * 32, 0, ctx->stream>>>(rtr_many(g, c), radius * radius, c->normals);
-        else if (c->n <= env_threshold("RTR_WARP_PER_POINT_MAX", RTR_WARP_PER_POINT_MAX))
-            k_normals_warp<OneGrid><<<std::min(nblk(c->n, PW_WARPS), ctx->sm_count * wide_grid_mult()), PW_WARPS * 32, 0, ctx->stream>>>(rtr_one(g), radius * radius, c->normals);
-        else
+        const bool many = c->nseg() > 0;
+        if (many || c->n <= env_threshold("RTR_WARP_PER_POINT_MAX", RTR_WARP_PER_POINT_MAX)) {
+            double* sums = nullptr;
+            if (int e = tmp_alloc(ctx, &sums, (size_t)c->n * 10, "normals")) return e;
+            const int grid = std::min(nblk(c->n, PW_WARPS), ctx->sm_count * wide_grid_mult());
+            if (many) k_normals_warp<ManyGrids><<<grid, PW_WARPS * 32, 0, ctx->stream>>>(rtr_many(g, c), radius * radius, sums);
+            else k_normals_warp<OneGrid><<<grid, PW_WARPS * 32, 0, ctx->stream>>>(rtr_one(g), radius * radius, sums);
+            RTR_LAUNCH_CHECK(ctx, "normals");
+            k_normals_solve<<<nblk(c->n, 128), 128, 0, ctx->stream>>>(g->sorted, c->n, sums, c->normals);
+            RTR_LAUNCH_CHECK(ctx, "normals.solve");
+            dev_free(ctx, sums);
+        } else {
             k_normals<<<nblk(c->n, 128), 128, 0, ctx->stream>>>(rtr_view(g), radius * radius, c->normals);
-        RTR_LAUNCH_CHECK(ctx, "normals");
+            RTR_LAUNCH_CHECK(ctx, "normals");
+        }
     }
     c->normals_radius = radius;
     c->normals_version++;

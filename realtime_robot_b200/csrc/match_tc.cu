@@ -541,7 +541,15 @@ int rtr_match_tc_dev(rtr_context* ctx, const float* fa, int ns, const float* fb,
     // one split: keep the four groups' lists (64 candidates per row make the certificate succeed more often); several splits:
     // the groups' lists are merged in the kernel, one list of 16 per (row, split)
     const bool merge = splits > 1;
-    const int keep = 16, lists = merge ? splits : TC_EPI_GROUPS;
+    // Short target lists (a scan of a few thousand points against a whole model database: 15 target tiles per source row) never
+    // tighten the threshold enough for the one-compare fast path: the epilogue is bound by list insertions (~6 instructions per
+    // list slot each, warp-wide).  Shorter lists make an insertion cheaper and rarer (6 ln(n/6) against 16 ln(n/16) per 480
+    // columns); the certificate decides as before whether a row is final, uncertified rows are redone exactly.  Measured on the
+    // bench batch (74 786 model rows x 1909 scan rows, k = 5): lists of 16 / 8 / 6 / 4 -> 659 / 398 / 338 / 819 us with
+    // 0 / 0 / 0 / 15 139 rows redone (4 < k cannot hold the answer of one group).
+    static const int keep_env = []() { const char* e = getenv("RTR_MATCH_KEEP"); return e ? atoi(e) : 0; }();
+    const int keep = (keep_env == 4 || keep_env == 6 || keep_env == 8 || keep_env == 16) ? keep_env : ((!merge && tgt_tiles <= 64 && k <= 5) ? 6 : 16);
+    const int lists = merge ? splits : TC_EPI_GROUPS;
     if (int e = tmp_alloc(ctx, &cand_idx, (size_t)ns * lists * keep, "match.tc")) return e;
     if (int e = tmp_alloc(ctx, &cand_val, (size_t)ns * lists * keep, "match.tc")) return e;
     if (int e = tmp_alloc(ctx, &cand_thr, (size_t)ns * lists, "match.tc")) return e;
@@ -562,6 +570,16 @@ int rtr_match_tc_dev(rtr_context* ctx, const float* fa, int ns, const float* fb,
     if (int e = rtr_kernel_smem(k_tc_match<16, 2, false>, ctx, smem)) return e;
     if (int e = rtr_kernel_smem(k_tc_match<16, 1, true>, ctx, smem)) return e;
     if (int e = rtr_kernel_smem(k_tc_match<16, 2, true>, ctx, smem)) return e;
+    if (int e = rtr_kernel_smem(k_tc_match<4, 1, false>, ctx, smem)) return e;
+    if (int e = rtr_kernel_smem(k_tc_match<4, 2, false>, ctx, smem)) return e;
+    if (int e = rtr_kernel_smem(k_tc_match<4, 1, true>, ctx, smem)) return e;
+    if (int e = rtr_kernel_smem(k_tc_match<4, 2, true>, ctx, smem)) return e;
+    if (int e = rtr_kernel_smem(k_tc_match<6, 1, false>, ctx, smem)) return e;
+    if (int e = rtr_kernel_smem(k_tc_match<6, 1, true>, ctx, smem)) return e;
+    if (int e = rtr_kernel_smem(k_tc_match<8, 1, false>, ctx, smem)) return e;
+    if (int e = rtr_kernel_smem(k_tc_match<8, 2, false>, ctx, smem)) return e;
+    if (int e = rtr_kernel_smem(k_tc_match<8, 1, true>, ctx, smem)) return e;
+    if (int e = rtr_kernel_smem(k_tc_match<8, 2, true>, ctx, smem)) return e;
     // RTR_MATCH_CLUSTER=1: pairs of source tiles share the target-tile stream through cluster multicast (half the L2 -> SM
     // traffic).  Off by default: since loads stopped waiting for the epilogue the kernel is bound by MMA + epilogue, the two
     // variants time the same (7.6 ms at 262144 x 65536), and independent CTAs need no gang scheduling.
@@ -580,8 +598,11 @@ int rtr_match_tc_dev(rtr_context* ctx, const float* fa, int ns, const float* fb,
         cfg.attrs = at; cfg.numAttrs = 1;
         const float *ca = a_tiles, *cb = b_tiles, *cn = b_norms;
         cudaError_t le;
-#define TC_LAUNCH(CL_, MG_) cudaLaunchKernelEx(&cfg, k_tc_match<16, CL_, MG_>, ca, cb, cn, ns, src_tiles, tgt_tiles, tiles_per_split, splits, cand_idx, cand_val, cand_thr)
-        le = use_cluster ? (merge ? TC_LAUNCH(2, true) : TC_LAUNCH(2, false)) : (merge ? TC_LAUNCH(1, true) : TC_LAUNCH(1, false));
+#define TC_LAUNCH(KP_, CL_, MG_) cudaLaunchKernelEx(&cfg, k_tc_match<KP_, CL_, MG_>, ca, cb, cn, ns, src_tiles, tgt_tiles, tiles_per_split, splits, cand_idx, cand_val, cand_thr)
+        if (keep == 4) le = use_cluster ? (merge ? TC_LAUNCH(4, 2, true) : TC_LAUNCH(4, 2, false)) : (merge ? TC_LAUNCH(4, 1, true) : TC_LAUNCH(4, 1, false));
+        else if (keep == 6) le = merge ? TC_LAUNCH(6, 1, true) : TC_LAUNCH(6, 1, false);
+        else if (keep == 8) le = use_cluster ? (merge ? TC_LAUNCH(8, 2, true) : TC_LAUNCH(8, 2, false)) : (merge ? TC_LAUNCH(8, 1, true) : TC_LAUNCH(8, 1, false));
+        else le = use_cluster ? (merge ? TC_LAUNCH(16, 2, true) : TC_LAUNCH(16, 2, false)) : (merge ? TC_LAUNCH(16, 1, true) : TC_LAUNCH(16, 1, false));
 #undef TC_LAUNCH
         RTR_CHECK(le, "match.tc_mma");
     }

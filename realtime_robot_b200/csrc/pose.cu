@@ -473,10 +473,21 @@ static int ransac_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const int*
     }
     if (!(p->max_correspondence_distance > 0.f)) return rtr_fail("ransac", "max_correspondence_distance must be > 0", RTR_ERR_INVALID);
     if (H > (1 << 20) || (long long)n_models * H > (1LL << 24)) return rtr_fail("ransac", "model-set RANSAC takes at most 2^20 hypotheses per model", RTR_ERR_INVALID);
-    // target grid for the inlier test: any cached grid of the set whose cells are >= d_max (and < 2 d_max), else one of d_max
+    // target grid for the inlier test: the scan alone, gridded at exactly d_max (one small single-cloud build on an alias of
+    // the scan's slice of the set).  Every surviving hypothesis of every model walks this grid for every source point, so the
+    // 1.9x fewer candidates per 27-cell block than the normals grid (cells of 0.05 against d_max = 0.0365) repay the build;
+    // the inlier test itself is exact on any grid with cells >= d_max.
+    rtr_cloud scan_alias;
+    scan_alias.ctx = ctx; scan_alias.n = nt; scan_alias.pts = set->pts + set->seg_begin[tgt_seg];
+    for (int a = 0; a < 3; ++a) { scan_alias.bb_min[a] = set->seg_bb[6 * tgt_seg + a]; scan_alias.bb_max[a] = set->seg_bb[6 * tgt_seg + 3 + a]; }
+    scan_alias.bbox_valid = true;
+    struct AliasGuard {            // the points are borrowed from the set; the grid is the alias' own (released stream-ordered)
+        rtr_cloud* c;
+        ~AliasGuard() { c->pts = nullptr; rtr_invalidate(c); }
+    } alias_guard{&scan_alias};
     DevGrid* g;
-    if (int e = rtr_get_grid_any(set, p->max_correspondence_distance, p->max_correspondence_distance * 1.001f, p->max_correspondence_distance * 2.0f, &g)) return e;
-    const GridView v = rtr_segment_view(g, set, tgt_seg);
+    if (int e = rtr_get_grid(&scan_alias, p->max_correspondence_distance, &g)) return e;
+    const GridView v = rtr_view(g);
     RansacMany rm;
     memset(&rm, 0, sizeof(rm));
     rm.nseg = n_models;
@@ -796,10 +807,28 @@ __global__ void __launch_bounds__(ICP_THREADS, 4) k_icp_corr(GridView g, GridVie
 #define ICPW_WARPS 8
 // bid / nblocks: this CTA's place among the CTAs that work on this source cloud (== blockIdx.x / gridDim.x for one cloud; a
 // model set gives every member cloud its own range of CTAs, state, ticket and partials — see k_icp_corr_warp_many)
+// Target search of the warp-per-query kernels.
+//   Scans up to RTR_BRUTE_NN_MAX points (every scan the reference ships) are searched WITHOUT a structure: the lanes stride
+//   over all target points, two queries per pass.  That pass is instruction-bound (~30 instructions per 64 point pairs: the
+//   step's ICP executes 36.6 M warp instructions per iteration for 26 k queries x 1909 targets).  Measured and dropped in
+//   round 2, all exact, none faster, because most of a model's points have NO scan point nearby (chair4: 26 % inliers):
+//   (a) the uniform grid with the previous neighbour's distance as prune radius — the ring walks of the far queries cost as
+//   much as the scan (43.7 -> 32.8 M instructions over the ten iterations against 36.1 M); (b) "neighbour provably unchanged"
+//   from the second smallest distance and the distance moved (dist(q', p) >= dist(q, p) - delta) — for a far query the second
+//   nearest scan point is within a fraction of a millimetre of the nearest, the bound never holds (711 us against 640).
+//   Larger scans use the exact grid search (block, then rings of rows), warm-started with the previous neighbour's distance
+//   as its prune radius (the nearest distance cannot exceed it).
+struct IcpTarget {
+    GridView g;                       // grid over the target (positions as stored in g.cell_begin)
+    const float4* brute;              // the target's points in any order with the original index in .w (brute_n of them; 0: none)
+    int brute_n;
+    const float4* pts;                // target points by original index (the index .w / the search returns)
+    const float4* normals;            // target normals by original index (estimator 1)
+};
 template <int EST>
-__device__ __forceinline__ void icp_corr_warp_body(const GridView& g, const float4* __restrict__ tgt_pts, const float4* __restrict__ tgt_normals,
-                                                   float4* __restrict__ cur, int n, IcpState* st, double dmax2, float prune2,
-                                                   double* partials, unsigned* ticket, const IcpSolveArgs& sa, const int bid, const int nblocks) {
+__device__ __forceinline__ void icp_corr_warp_body(const IcpTarget& T, float4* __restrict__ cur, int* __restrict__ nn_prev, int n, IcpState* st,
+                                                   double dmax2, float prune2, double* partials, unsigned* ticket, const IcpSolveArgs& sa,
+                                                   const int bid, const int nblocks) {
     constexpr int N = IcpSums<EST>::N;
     __shared__ float m[16];
     __shared__ double red[ICPW_WARPS][N];      // lane 0 of every warp accumulates its queries here, in query order
@@ -813,14 +842,18 @@ __device__ __forceinline__ void icp_corr_warp_body(const GridView& g, const floa
     __syncthreads();
     int nwarps = nblocks * ICPW_WARPS;
     double* acc = red[warp];
+    const float4* __restrict__ tgt_pts = T.pts;
     auto add = [&](float4 q, int b, float d2, float4 t) {
         if (lane == 0 && b >= 0 && (double)d2 <= dmax2) {
             float4 nrm = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (EST == 1) nrm = __ldg(tgt_normals + b);
+            if (EST == 1) nrm = __ldg(T.normals + b);
             if (EST == 0 || finite3(nrm)) icp_accumulate<EST>(acc, q, t, nrm, d2);
         }
     };
-    if (g.n <= RTR_BRUTE_NN_MAX) {
+    const bool warm = have && nn_prev != nullptr;
+    if (T.brute_n > 0) {
+        GridView gb = T.g;
+        gb.sorted = T.brute; gb.n = T.brute_n;
         // two of this warp's queries per pass (i, i + nwarps): same warp -> query assignment and accumulation order as below
         for (int i = bid * ICPW_WARPS + warp; i < n; i += 2 * nwarps) {
             int i2 = i + nwarps;
@@ -831,7 +864,7 @@ __device__ __forceinline__ void icp_corr_warp_body(const GridView& g, const floa
                 if (two) { q2 = xform(m, q2); if (lane == 0) cur[i2] = q2; } else q2 = q;
             }
             int b, b2; float d2, d22;
-            brute_nearest_warp2(g, q.x, q.y, q.z, q2.x, q2.y, q2.z, lane, b, d2, b2, d22);
+            brute_nearest_warp2(gb, q.x, q.y, q.z, q2.x, q2.y, q2.z, lane, b, d2, b2, d22);
             if (lane == 0) {
                 if (b >= 0) add(q, b, d2, __ldg(tgt_pts + b));
                 if (two && b2 >= 0) add(q2, b2, d22, __ldg(tgt_pts + b2));
@@ -841,8 +874,18 @@ __device__ __forceinline__ void icp_corr_warp_body(const GridView& g, const floa
         for (int i = bid * ICPW_WARPS + warp; i < n; i += nwarps) {
             float4 q = cur[i];
             if (have) { q = xform(m, q); if (lane == 0) cur[i] = q; }
+            float pr2 = prune2;
+            if (warm) {
+                const int pb = nn_prev[i];
+                if (pb >= 0) {
+                    const float4 tp = __ldg(tgt_pts + pb);
+                    // the previous neighbour is a candidate: the nearest distance cannot exceed this (a hair of slack keeps it inside)
+                    pr2 = fminf(prune2, __fmul_rn(dist2f(q.x, q.y, q.z, tp.x, tp.y, tp.z), 1.000001f));
+                }
+            }
             int b; float d2; float4 t;
-            grid_nearest_warp(g, q.x, q.y, q.z, prune2, lane, b, d2, t);
+            grid_nearest_warp(T.g, q.x, q.y, q.z, pr2, lane, b, d2, t);
+            if (lane == 0 && nn_prev) nn_prev[i] = b;
             add(q, b, d2, t);
         }
     }
@@ -857,11 +900,10 @@ __device__ __forceinline__ void icp_corr_warp_body(const GridView& g, const floa
 }
 
 template <int EST>
-__global__ void __launch_bounds__(ICPW_WARPS * 32, 4) k_icp_corr_warp(GridView g, const float4* __restrict__ tgt_pts, const float4* __restrict__ tgt_normals,
-                                                                   float4* __restrict__ cur, int n, IcpState* st, double dmax2, float prune2,
-                                                                   double* partials, unsigned* ticket, IcpSolveArgs sa) {
+__global__ void __launch_bounds__(ICPW_WARPS * 32, 4) k_icp_corr_warp(IcpTarget T, float4* __restrict__ cur, int* __restrict__ nn_prev, int n, IcpState* st,
+                                                                   double dmax2, float prune2, double* partials, unsigned* ticket, IcpSolveArgs sa) {
     pdl_wait();                 // the previous iteration (or k_icp_init) has completed: st, cur, ticket are current
-    icp_corr_warp_body<EST>(g, tgt_pts, tgt_normals, cur, n, st, dmax2, prune2, partials, ticket, sa, (int)blockIdx.x, (int)gridDim.x);
+    icp_corr_warp_body<EST>(T, cur, nn_prev, n, st, dmax2, prune2, partials, ticket, sa, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // Model set: the CTAs of every member cloud in one launch.  cta_begin[k] .. cta_begin[k+1] work on member k with the CTA
@@ -878,13 +920,13 @@ __device__ __forceinline__ int icp_many_segment(const IcpMany& im, int b) {
     return k;
 }
 template <int EST>
-__global__ void __launch_bounds__(ICPW_WARPS * 32, 4) k_icp_corr_warp_many(const __grid_constant__ IcpMany im, GridView g, const float4* __restrict__ tgt_pts,
-                                                                        const float4* __restrict__ tgt_normals, float4* __restrict__ cur_all, IcpState* st_all,
-                                                                        double dmax2, float prune2, double* partials_all, unsigned* ticket_all, IcpSolveArgs sa) {
+__global__ void __launch_bounds__(ICPW_WARPS * 32, 4) k_icp_corr_warp_many(const __grid_constant__ IcpMany im, IcpTarget T, float4* __restrict__ cur_all,
+                                                                        int* __restrict__ nn_prev_all, IcpState* st_all, double dmax2, float prune2,
+                                                                        double* partials_all, unsigned* ticket_all, IcpSolveArgs sa) {
     pdl_wait();
     const int k = icp_many_segment(im, (int)blockIdx.x);
     const int b0 = im.cta_begin[k];
-    icp_corr_warp_body<EST>(g, tgt_pts, tgt_normals, cur_all + im.pt_begin[k], im.pt_begin[k + 1] - im.pt_begin[k], st_all + k, dmax2, prune2,
+    icp_corr_warp_body<EST>(T, cur_all + im.pt_begin[k], nn_prev_all + im.pt_begin[k], im.pt_begin[k + 1] - im.pt_begin[k], st_all + k, dmax2, prune2,
                             partials_all + (size_t)b0 * ICP_NSUM_MAX, ticket_all + k, sa, (int)blockIdx.x - b0, im.cta_begin[k + 1] - b0);
 }
 
@@ -932,9 +974,11 @@ __device__ void icp_last_cta_finish(const double* partials, const IcpState* st, 
     }
 }
 
-__device__ __forceinline__ void icp_fitness_warp_body(const GridView& g, const float4* __restrict__ src, int n, const IcpState* __restrict__ st,
-                                                      double* partials, unsigned* ticket, rtr_pose_result* res, int keep_ransac_fields,
-                                                      const int bid, const int nblocks) {
+// nn_prev: every query's neighbour at its last search (warm start of the grid search on large scans)
+__device__ __forceinline__ void icp_fitness_warp_body(const IcpTarget& T, const float4* __restrict__ src, const float4* __restrict__ cur,
+                                                      const int* __restrict__ nn_prev, int n,
+                                                      const IcpState* __restrict__ st, double* partials, unsigned* ticket, rtr_pose_result* res,
+                                                      int keep_ransac_fields, const int bid, const int nblocks) {
     __shared__ float m[16];
     __shared__ double red[ICPW_WARPS][2];
     __shared__ double sums[2];
@@ -948,22 +992,34 @@ __device__ __forceinline__ void icp_fitness_warp_body(const GridView& g, const f
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int nwarps = nblocks * ICPW_WARPS;
     double s = 0, c = 0;
-    if (g.n <= RTR_BRUTE_NN_MAX) {
+    // valid once at least one iteration has stored every query's neighbour
+    const bool warm = nn_prev != nullptr && st->iterations > 0;
+    if (T.brute_n > 0) {
+        GridView gb = T.g;
+        gb.sorted = T.brute; gb.n = T.brute_n;
         for (int i = bid * ICPW_WARPS + warp; i < n; i += 2 * nwarps) {
             int i2 = i + nwarps;
             bool two = i2 < n;
             float4 q = xform(m, __ldg(src + i));
             float4 q2 = two ? xform(m, __ldg(src + i2)) : q;
             int b, b2; float d2, d22;
-            brute_nearest_warp2(g, q.x, q.y, q.z, q2.x, q2.y, q2.z, lane, b, d2, b2, d22);
+            brute_nearest_warp2(gb, q.x, q.y, q.z, q2.x, q2.y, q2.z, lane, b, d2, b2, d22);
             if (lane == 0 && b >= 0) { s += (double)d2; c += 1.0; }
             if (lane == 0 && two && b2 >= 0) { s += (double)d22; c += 1.0; }
         }
     } else {
         for (int i = bid * ICPW_WARPS + warp; i < n; i += nwarps) {
             float4 q = xform(m, __ldg(src + i));
+            float pr2 = FLT_MAX;
+            if (warm) {
+                const int pb = nn_prev[i];
+                if (pb >= 0) {
+                    const float4 tp = __ldg(T.pts + pb);
+                    pr2 = __fmul_rn(dist2f(q.x, q.y, q.z, tp.x, tp.y, tp.z), 1.000001f);
+                }
+            }
             int b; float d2; float4 t;
-            grid_nearest_warp(g, q.x, q.y, q.z, FLT_MAX, lane, b, d2, t);
+            grid_nearest_warp(T.g, q.x, q.y, q.z, pr2, lane, b, d2, t);
             if (lane == 0 && b >= 0) { s += (double)d2; c += 1.0; }
         }
     }
@@ -978,20 +1034,23 @@ __device__ __forceinline__ void icp_fitness_warp_body(const GridView& g, const f
     icp_last_cta_finish(partials, st, ticket, res, keep_ransac_fields, sums, &is_last, nblocks);
 }
 
-__global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_fitness_warp(GridView g, const float4* __restrict__ src, int n, const IcpState* __restrict__ st,
-                                                                      double* partials, unsigned* ticket, rtr_pose_result* res, int keep_ransac_fields) {
+__global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_fitness_warp(IcpTarget T, const float4* __restrict__ src, const float4* __restrict__ cur,
+                                                                      const int* __restrict__ nn_prev, int n,
+                                                                      const IcpState* __restrict__ st, double* partials, unsigned* ticket,
+                                                                      rtr_pose_result* res, int keep_ransac_fields) {
     pdl_wait();
-    icp_fitness_warp_body(g, src, n, st, partials, ticket, res, keep_ransac_fields, (int)blockIdx.x, (int)gridDim.x);
+    icp_fitness_warp_body(T, src, cur, nn_prev, n, st, partials, ticket, res, keep_ransac_fields, (int)blockIdx.x, (int)gridDim.x);
 }
 
-__global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_fitness_warp_many(const __grid_constant__ IcpMany im, GridView g, const float4* __restrict__ src_all,
-                                                                           const IcpState* __restrict__ st_all, double* partials_all, unsigned* ticket_all,
-                                                                           rtr_pose_result* res_all) {
+__global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_fitness_warp_many(const __grid_constant__ IcpMany im, IcpTarget T, const float4* __restrict__ src_all,
+                                                                           const float4* __restrict__ cur_all, const int* __restrict__ nn_prev_all,
+                                                                           const IcpState* __restrict__ st_all,
+                                                                           double* partials_all, unsigned* ticket_all, rtr_pose_result* res_all) {
     pdl_wait();
     const int k = icp_many_segment(im, (int)blockIdx.x);
-    const int b0 = im.cta_begin[k];
-    icp_fitness_warp_body(g, src_all + im.pt_begin[k], im.pt_begin[k + 1] - im.pt_begin[k], st_all + k, partials_all + (size_t)b0 * ICP_NSUM_MAX, ticket_all + k,
-                          res_all + k, 1, (int)blockIdx.x - b0, im.cta_begin[k + 1] - b0);
+    const int b0 = im.cta_begin[k], p0 = im.pt_begin[k];
+    icp_fitness_warp_body(T, src_all + p0, cur_all + p0, nn_prev_all + p0, im.pt_begin[k + 1] - p0, st_all + k,
+                          partials_all + (size_t)b0 * ICP_NSUM_MAX, ticket_all + k, res_all + k, 1, (int)blockIdx.x - b0, im.cta_begin[k + 1] - b0);
 }
 
 // getFitnessScore(): mean squared NN distance of (final o source)
@@ -1048,7 +1107,13 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
         // and no query ever needs the walk beyond it (grid_nearest_ex stops after the block when prune2 <= (0.999 h)^2)
         const float cap = p->max_correspondence_distance;
         if (cap > want && cap < 3.f * want) want = cap;
-        if (int e = rtr_get_grid_any(tgt, want, want * (cap == want ? 1.0f : 0.6f), want * 1.7f, &g)) return e;
+        if (n < 65536) {
+            // warp-per-query kernels warm-start every search from the previous neighbour: prefer the finest cached grid in range
+            g = nullptr;
+            const float lo = want * (cap == want ? 1.0f : 0.4f), hi = want * 1.7f;
+            for (auto& kv : tgt->grids) { DevGrid& c = kv.second; if (c.h >= lo && c.h <= hi && (!g || c.h < g->h)) g = &c; }
+            if (!g) if (int e = rtr_get_grid(tgt, want, &g)) return e;
+        } else if (int e = rtr_get_grid_any(tgt, want, want * (cap == want ? 1.0f : 0.6f), want * 1.7f, &g)) return e;
     }
     GridView v = rtr_view(g);
     // large sources: a second, coarser grid for the queries far from the target (k_icp_fitness).  1M scan points onto a 100k-point
@@ -1114,12 +1179,17 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     // small sources: one warp per query (latency), large ones: one thread per query in cell order (throughput)
     const bool warp_per_query = n < 65536;
     const bool plane = p->estimator == 1;
+    // warp-per-query kernels: the target as they see it, and each query's previous neighbour (warm start of the next search)
+    IcpTarget T;
+    T.g = v; T.brute = v.sorted; T.brute_n = (tgt->n <= RTR_BRUTE_NN_MAX) ? tgt->n : 0; T.pts = tgt->pts; T.normals = plane ? tgt->normals : nullptr;
+    int* nn_prev = nullptr;
+    if (warp_per_query) if (int e = tmp_alloc(ctx, &nn_prev, n, "icp")) return e;
     const Box6 bb{tgt->bb_min[0], tgt->bb_min[1], tgt->bb_min[2], tgt->bb_max[0], tgt->bb_max[1], tgt->bb_max[2]};
     if (n >= 1 && tgt->n >= 1) {
         for (int it = 0; it < p->max_iterations; ++it) {
             if (warp_per_query) {
-                if (plane) launch_pdl(k_icp_corr_warp<1>, nbw, ICPW_WARPS * 32, 0, ctx->stream, v, (const float4*)tgt->pts, (const float4*)tgt->normals, cur, n, st, dmax2, prune2, partials, ticket, sa);
-                else launch_pdl(k_icp_corr_warp<0>, nbw, ICPW_WARPS * 32, 0, ctx->stream, v, (const float4*)tgt->pts, (const float4*)nullptr, cur, n, st, dmax2, prune2, partials, ticket, sa);
+                if (plane) launch_pdl(k_icp_corr_warp<1>, nbw, ICPW_WARPS * 32, 0, ctx->stream, T, cur, nn_prev, n, st, dmax2, prune2, partials, ticket, sa);
+                else launch_pdl(k_icp_corr_warp<0>, nbw, ICPW_WARPS * 32, 0, ctx->stream, T, cur, nn_prev, n, st, dmax2, prune2, partials, ticket, sa);
             } else {
                 if (plane) launch_pdl(k_icp_corr<1>, nb, ICP_THREADS, 0, ctx->stream, v, vc, bb, far2, (const float4*)tgt->normals, cur, n, st, dmax2, prune2, partials, ticket, sa);
                 else launch_pdl(k_icp_corr<0>, nb, ICP_THREADS, 0, ctx->stream, v, vc, bb, far2, (const float4*)nullptr, cur, n, st, dmax2, prune2, partials, ticket, sa);
@@ -1127,10 +1197,10 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
             RTR_LAUNCH_CHECK(ctx, "icp.corr");
         }
     }
-    if (warp_per_query) launch_pdl(k_icp_fitness_warp, nbw, ICPW_WARPS * 32, 0, ctx->stream, v, src_pts, n, (const IcpState*)st, partials, ticket, d_result, init_from_result);
+    if (warp_per_query) launch_pdl(k_icp_fitness_warp, nbw, ICPW_WARPS * 32, 0, ctx->stream, T, src_pts, (const float4*)cur, (const int*)nn_prev, n, (const IcpState*)st, partials, ticket, d_result, init_from_result);
     else launch_pdl(k_icp_fitness, nb, ICP_THREADS, 0, ctx->stream, v, vc, bb, far2, src_pts, n, (const IcpState*)st, partials, ticket, d_result, init_from_result);
     RTR_LAUNCH_CHECK(ctx, "icp.fitness");
-    dev_free(ctx, cur); dev_free(ctx, src2); dev_free(ctx, st); dev_free(ctx, partials); dev_free(ctx, ticket);
+    dev_free(ctx, cur); dev_free(ctx, src2); dev_free(ctx, st); dev_free(ctx, partials); dev_free(ctx, ticket); dev_free(ctx, nn_prev);
     return 0;
 }
 
@@ -1164,21 +1234,25 @@ static int icp_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const rtr_icp
     // target's points: any grid's copy serves); larger scans use the cached grid closest to the ICP cell, as rtr_icp_dev does.
     // Either way the neighbour is the exact one.
     GridView v;
-    if (nt <= RTR_BRUTE_NN_MAX) {
-        if (set->grids.empty()) return rtr_fail("icp", "model set has no grid", RTR_ERR_NOT_READY);
-        v = rtr_segment_view(&set->grids.begin()->second, set, tgt_seg);
-        v.sorted += t0;            // the brute-force scan reads sorted[0 .. n)
-    } else {
+    {
         rtr_cloud box;             // a bounding box + size only, for the cell heuristic
         box.n = nt;
         for (int a = 0; a < 3; ++a) { box.bb_min[a] = set->seg_bb[6 * tgt_seg + a]; box.bb_max[a] = set->seg_bb[6 * tgt_seg + 3 + a]; }
         float want = rtr_icp_cell(&box);
         const float cap = p->max_correspondence_distance;
         if (cap > want && cap < 3.f * want) want = cap;
-        DevGrid* g;
-        if (int e = rtr_get_grid_any(set, want, want * (cap == want ? 1.0f : 0.6f), want * 1.7f, &g)) return e;
+        // warm-started searches are bounded by the previous neighbour's distance, usually far below the point spacing: the
+        // FINEST cached grid in range keeps the 27-cell block small (the 0.05 normals grid holds ~80 candidates per block on
+        // the repo scans against ~400 for the 0.10 FPFH grid, which made the warm start no faster than the brute-force pass)
+        DevGrid* g = nullptr;
+        const float lo = want * (cap == want ? 1.0f : 0.4f), hi = want * 1.7f;
+        for (auto& kv : set->grids) { DevGrid& c = kv.second; if (c.h >= lo && c.h <= hi && (!g || c.h < g->h)) g = &c; }
+        if (!g) if (int e = rtr_get_grid(set, want, &g)) return e;
         v = rtr_segment_view(g, set, tgt_seg);
     }
+    IcpTarget T;
+    T.g = v; T.brute = v.sorted + t0; T.brute_n = (nt <= RTR_BRUTE_NN_MAX) ? nt : 0;     // the scan's slice of the cell-ordered copy
+    T.pts = set->pts; T.normals = (p->estimator == 1) ? set->normals : nullptr;
     IcpMany im;
     memset(&im, 0, sizeof(im));
     im.nseg = n_models;
@@ -1188,8 +1262,9 @@ static int icp_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const rtr_icp
         im.cta_begin[k] = ctas;
         if (k < n_models) ctas += std::max(1, std::min(nblk(set->seg_begin[k + 1] - set->seg_begin[k], ICPW_WARPS), ctx->sm_count * 8));
     }
-    float4* cur = nullptr; IcpState* st = nullptr; double* partials = nullptr; unsigned* ticket = nullptr;
+    float4* cur = nullptr; IcpState* st = nullptr; double* partials = nullptr; unsigned* ticket = nullptr; int* nn_prev = nullptr;
     if (int e = tmp_alloc(ctx, &cur, n_src, "icp")) return e;
+    if (int e = tmp_alloc(ctx, &nn_prev, n_src, "icp")) return e;
     if (int e = tmp_alloc(ctx, &st, n_models, "icp")) return e;
     if (int e = tmp_alloc(ctx, &ticket, n_models, "icp")) return e;
     if (int e = tmp_alloc(ctx, &partials, (size_t)ctas * ICP_NSUM_MAX, "icp")) return e;
@@ -1202,12 +1277,12 @@ static int icp_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const rtr_icp
     const bool plane = p->estimator == 1;
     if (nt >= 1) {
         for (int it = 0; it < p->max_iterations; ++it) {
-            if (plane) launch_pdl(k_icp_corr_warp_many<1>, ctas, ICPW_WARPS * 32, 0, ctx->stream, im, v, (const float4*)set->pts, (const float4*)set->normals, cur, st, dmax2, prune2, partials, ticket, sa);
-            else launch_pdl(k_icp_corr_warp_many<0>, ctas, ICPW_WARPS * 32, 0, ctx->stream, im, v, (const float4*)set->pts, (const float4*)nullptr, cur, st, dmax2, prune2, partials, ticket, sa);
+            if (plane) launch_pdl(k_icp_corr_warp_many<1>, ctas, ICPW_WARPS * 32, 0, ctx->stream, im, T, cur, nn_prev, st, dmax2, prune2, partials, ticket, sa);
+            else launch_pdl(k_icp_corr_warp_many<0>, ctas, ICPW_WARPS * 32, 0, ctx->stream, im, T, cur, nn_prev, st, dmax2, prune2, partials, ticket, sa);
             RTR_LAUNCH_CHECK(ctx, "icp.corr");
         }
     }
-    launch_pdl(k_icp_fitness_warp_many, ctas, ICPW_WARPS * 32, 0, ctx->stream, im, v, (const float4*)set->pts, (const IcpState*)st, partials, ticket, d_results);
+    launch_pdl(k_icp_fitness_warp_many, ctas, ICPW_WARPS * 32, 0, ctx->stream, im, T, (const float4*)set->pts, (const float4*)cur, (const int*)nn_prev, (const IcpState*)st, partials, ticket, d_results);
     RTR_LAUNCH_CHECK(ctx, "icp.fitness");
     return 0;
 }
@@ -1269,8 +1344,29 @@ static int register_many_enqueue(rtr_cloud* set, int n_models, const rtr_registe
     DevGrid* gs[3];
     if (int e = rtr_get_grids(set, cells, p->harris_radius == p->normal_radius ? 2 : 3, gs)) return e;
     if (int e = rtr_normals_dev(set, p->normal_radius)) return e;
+    // Harris (response, NMS, corner lists, refinement) needs only the normals and feeds nothing but the records' corner
+    // counts and previews: it runs on the context's second stream beside FPFH / matching / RANSAC / ICP and is joined before
+    // the finishing kernel.  Temporaries come from the bump arena, which hands nothing out twice inside one entry point.
     int* d_idx = nullptr; float4* d_xyz = nullptr; int* d_cnt = nullptr;
-    if (int e = rtr_harris_dev(set, p->harris_radius, p->harris_threshold, p->harris_nms, p->harris_refine, &d_idx, &d_xyz, &d_cnt)) return e;
+    const bool fork = !ctx->profile && ctx->aux_stream;
+    cudaStream_t main_stream = ctx->stream;
+    if (fork) {
+        RTR_CHECK(cudaEventRecord(ctx->fork_event, main_stream), "register_many.fork");
+        RTR_CHECK(cudaStreamWaitEvent(ctx->aux_stream, ctx->fork_event, 0), "register_many.fork");
+        ctx->stream = ctx->aux_stream;
+    }
+    int eh = rtr_harris_dev(set, p->harris_radius, p->harris_threshold, p->harris_nms, p->harris_refine, &d_idx, &d_xyz, &d_cnt);
+    ctx->stream = main_stream;
+    if (fork) {
+        cudaEventRecord(ctx->join_event, ctx->aux_stream);
+        // error paths below must not leave the second stream running behind a freed set: every return waits for the join
+    }
+    struct JoinGuard {
+        rtr_context* ctx; bool fork; bool joined;
+        void join() { if (fork && !joined) { cudaStreamWaitEvent(ctx->stream, ctx->join_event, 0); joined = true; } }
+        ~JoinGuard() { join(); }
+    } join_guard{ctx, fork, false};
+    if (eh) return eh;
     if (int e = rtr_fpfh_dev(set, p->fpfh_radius)) return e;
     const int k = p->ransac.correspondence_k;
     int* knn = nullptr; float* knn_dist = nullptr;
@@ -1286,6 +1382,7 @@ static int register_many_enqueue(rtr_cloud* set, int n_models, const rtr_registe
     memset(&im, 0, sizeof(im));
     im.nseg = n_models;
     for (int kk = 0; kk <= RTR_MAX_SEGMENTS; ++kk) im.pt_begin[kk] = set->seg_begin[std::min(kk, n_models)];
+    join_guard.join();
     k_register_finish_many<<<nseg, 64, 0, ctx->stream>>>(im, d_res, d_cnt, d_xyz, nseg, d_prev);
     RTR_LAUNCH_CHECK(ctx, "register.kp");
     const size_t res_bytes = sizeof(rtr_pose_result) * (size_t)n_models, prev_bytes = sizeof(KpPreview) * (size_t)nseg;

@@ -65,6 +65,56 @@ def all_gather_records(records, per_rank: int, device=None):
     return [r for r in out if not (r.hypothesis == -2 and r.model_id == -1)]
 
 
+# ------------------------------------------------------------------ in-library collective (csrc/comm.cu, NCCL)
+def comm_init(ctx, rank: int, world: int, exchange=None):
+    """Give `ctx` an NCCL communicator on its own stream (rtr_comm_init).  Rank 0 draws the 128-byte NCCL id
+    (rtr_comm_unique_id); `exchange(id_bytes_or_None) -> id_bytes` ships it to the other ranks — default:
+    torch.distributed.broadcast_object_list over the already initialised process group (any backend)."""
+    from . import _lib
+    L = _lib.lib()
+    if world <= 1:
+        return
+    ident = None
+    if rank == 0:
+        buf = C.create_string_buffer(128)
+        _lib.check("rtr_comm_unique_id", L.rtr_comm_unique_id(buf))
+        ident = buf.raw
+    if exchange is None:
+        import torch.distributed as td
+        box = [ident]
+        td.broadcast_object_list(box, src=0)
+        ident = box[0]
+    else:
+        ident = exchange(ident)
+    _lib.check("rtr_comm_init", L.rtr_comm_init(ctx._h, world, rank, ident))
+
+
+def allgather_results(ctx, records, world: int = None):
+    """ONE ncclAllGather of the 128-byte records on the context's stream (rtr_allgather_results): every rank passes the same
+    number of records and receives world x that many, in rank order."""
+    from . import _lib
+    L = _lib.lib()
+    n = len(records)
+    if world is None:
+        w, r = C.c_int(), C.c_int()
+        L.rtr_comm_world(ctx._h, C.byref(w), C.byref(r))
+        world = w.value
+    local = (PoseResult * max(n, 1))(*records)
+    out = (PoseResult * max(n * world, 1))()
+    _lib.check("rtr_allgather_results", L.rtr_allgather_results(ctx._h, local, n, out))
+    return [PoseResult.from_buffer_copy(bytes(out[i])) for i in range(n * world)]
+
+
+def select_best_hypothesis_native(records):
+    """rtr_select_best_hypothesis: the library's own arg-min over (fitness, hypothesis id) — what the C++ host calls."""
+    from . import _lib
+    n = len(records)
+    arr = (PoseResult * n)(*records)
+    best = PoseResult()
+    _lib.check("rtr_select_best_hypothesis", _lib.lib().rtr_select_best_hypothesis(arr, n, C.byref(best)))
+    return best
+
+
 def select_best_hypothesis(records):
     """Deterministic arg-min over (fitness, hypothesis id) among accepted shards: identical on every rank and for
     every world size (the sequential PCL rule 'error < lowest_error' keeps the first lowest)."""

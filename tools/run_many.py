@@ -1,0 +1,54 @@
+#!/usr/bin/env python3
+"""One bench step (rtr_register_many: mcloud vs the 8 repo models) for profilers: warm-up steps, then `--steps` steps between
+cudaProfilerStart / cudaProfilerStop (run ncu with --profile-from-start off).  Prints the unprofiled step time first."""
+import argparse
+import ctypes
+import os
+import sys
+import time
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+from realtime_robot_b200 import api  # noqa: E402
+from realtime_robot_b200.pcd import read_pcd_xyz, to_xyz1  # noqa: E402
+
+MODELS = ["chair1", "chair2", "chair4", "desk1", "desk1", "desk3", "sofa", "Chair_025"]
+
+
+def load(name):
+    pts = to_xyz1(read_pcd_xyz(os.path.join(ROOT, "data", "clouds", name + ".pcd")))
+    if name == "Chair_025":
+        pts[:, :3] *= np.float32(0.01)
+    return pts
+
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--steps", type=int, default=1)
+ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--models", default=",".join(MODELS))
+ap.add_argument("--marks", action="store_true", help="print the per-operation device times of one step (profiling marks)")
+args = ap.parse_args()
+names = args.models.split(",")
+ctx = api.Context(0)
+scene = api.Cloud(ctx, load("mcloud"))
+models = [api.Cloud(ctx, load(m)) for m in names]
+p = api.default_register_params()
+for _ in range(args.warmup):
+    api.register_many(models, scene, p)
+ts = []
+for _ in range(10):
+    ctx.sync(); t0 = time.perf_counter(); api.register_many(models, scene, p); ts.append(1e3 * (time.perf_counter() - t0))
+print("step %.3f ms (min of 10, wall), launches/step %d" % (min(ts), 0), flush=True)
+if args.marks:
+    ctx.profile_begin(); api.register_many(models, scene, p); pr = ctx.profile_end()
+    tot = sum(v[1] for v in pr.values())
+    for k, v in sorted(pr.items(), key=lambda kv: -kv[1][1]):
+        print("  %-22s x%-3d %8.1f us  %5.1f %%" % (k, v[0], 1e3 * v[1], 100 * v[1] / tot))
+    print("  serialised %.3f ms" % tot)
+rt = ctypes.CDLL("libcudart.so")
+rt.cudaProfilerStart()
+for _ in range(args.steps):
+    api.register_many(models, scene, p)
+ctx.sync()
+rt.cudaProfilerStop()
