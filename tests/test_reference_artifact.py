@@ -64,3 +64,47 @@ def test_gpu_refined_corners_reproduce_the_reference_artifact(gpu_ctx, clouds):
         c.free()
     err, i, j = best_pair_error(out[0], out[1])
     assert err < TOL, (err, i, j)
+
+
+ALL = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_artifacts.json")))
+
+
+@pytest.mark.parametrize("name", ["mcloudYasuo.pcd", "transformed_cloud2.pcd"])
+def test_more_artifacts_have_the_form_of_a_sweep_transform(name):
+    """mcloudYasuo.pcd / transformed_cloud2.pcd: T0_m8111.pcd through get_Distance transforms of an earlier main() whose model
+    cloud the reference does not ship — they pin the FORM (matching.h:143,204-217): yaw a multiple of the 10 degree step, one xy
+    row unscaled, the other xy row and the z row scaled by the same z_model / z_scan, an exact affine image (residual ~1e-7)."""
+    g = ALL[name]
+    assert g["max_residual"] < 1e-6
+    assert abs(g["yaw_deg"] / 10.0 - round(g["yaw_deg"] / 10.0)) < 1e-4
+    rows = g["row_scale"]
+    assert abs(rows[g["unscaled_row"]] - 1.0) < 1e-5 and abs(rows[1 - g["unscaled_row"]] - g["scale_z"]) < 1e-5
+    assert abs(g["scale_z"] - ALL["mcloudYasuo.pcd"]["scale_z"]) < 1e-6          # both runs used the same corner pair
+    m = np.array(g["affine_3x4"])
+    assert np.abs(m[2, :2]).max() < 1e-6 and np.abs(m[:2, 2]).max() < 1e-6       # yaw only: z decoupled (matching.h:147-167)
+
+
+def test_oracle_sweep_transform_has_the_artifact_form(orc, clouds):
+    """The oracle's get_Distance (matching.h:122-222 as intended): for every corner pair the returned transform is a yaw by a
+    multiple of 10 degrees about the model corner composed with the similarity scale z_model / z_scan — the structure all three
+    shipped artefacts show."""
+    from realtime_robot_b200.params import default_native_params
+    model, scan = clouds("chair1"), clouds("T0_m8111")
+    mk = orc.harris3d(model, orc.normals(model, 0.05), 0.05, 0.01)[2]
+    sk = orc.harris3d(scan, orc.normals(scan, 0.05), 0.05, 0.01)[2]
+    p = default_native_params()
+    _, _, tdfs, _, _ = orc.native_keypoint_descriptors(model, mk, p)
+    _, _, _, _, occ = orc.native_keypoint_descriptors(scan, sk, p, with_tdf=False)
+    checked = 0
+    for i in range(min(len(mk), 3)):
+        for j in range(min(len(sk), 4)):
+            if sk[j][2] == 0 or len(occ[j]) == 0:
+                continue
+            _, step, T = orc.native_pair_score(mk[i], tdfs[i], occ[j], sk[j], p)
+            s = float(mk[i][2]) / float(sk[j][2])
+            R = T[:3, :3] / s
+            yaw = np.degrees(np.arctan2(R[1, 0], R[0, 0])) % 360.0
+            assert abs(yaw - (step * 10.0) % 360.0) < 1e-2, (i, j, yaw, step)
+            assert abs(R[2, 2] - 1.0) < 1e-4 and np.abs(R[2, :2]).max() < 1e-5
+            checked += 1
+    assert checked >= 6
