@@ -70,6 +70,11 @@ def peaks():
     return 6650.0, 1590.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
+def host_cores():
+    """every host core this process may use (torchrun exports OMP_NUM_THREADS=1, which omp_get_max_threads() would obey)"""
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
 def record_matches(g, o):
     """GPU record vs oracle record under the north-star tolerances."""
     return bool((g.hypothesis, g.inliers, g.evaluated, g.iterations, g.converged, g.n_keypoints_src, g.n_keypoints_tgt) ==
@@ -85,7 +90,7 @@ def run_reference(args, rank, world):
     from oracle import orc
     orc.build()
     # every host core this process may use (torchrun exports OMP_NUM_THREADS=1, which omp_get_max_threads() would obey)
-    cores = orc.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    cores = orc.set_threads(host_cores())
     p = default_register_params()
     scene = load_cloud(SCENE)
     models = [load_cloud(m) for m in MODELS]
@@ -184,7 +189,10 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner there)
+        # keep stdout to the one JSON line: NCCL prints its version banner to stdout on the first communicator — whatever it has
+        # to say goes to stderr instead (a caller that sets NCCL_DEBUG / NCCL_DEBUG_FILE itself keeps its settings)
+        os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as td
     from realtime_robot_b200 import _lib, api, dist, synth
@@ -193,7 +201,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        td.init_process_group("nccl", device_id=dev)
+        import datetime
+        td.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))      # a mismatch must fail fast, not hang the box
     ctx = api.Context(local_rank)
     if world > 1:
         dist.comm_init(ctx, rank, world)            # the library's own communicator (NCCL) on the context's stream
@@ -250,6 +259,9 @@ def main():
             if flush:
                 flush_buf.fill_(1)
                 torch.cuda.synchronize()
+                if world > 1:
+                    td.barrier()            # untimed: every rank starts the step together (a step ends in a collective, so a late
+                    torch.cuda.synchronize()  # starter's flush would otherwise be charged to the ranks waiting for it)
             ctx.record(0)
             t0 = time.perf_counter()
             last = step_fn()
@@ -276,17 +288,21 @@ def main():
     launches = ctx.launches - l0
     ms_e2e, recs_e2e = timed(step_e2e, args.steps)
     barrier()
+    # max over ranks (before anything is derived from the times: every rank must run the same number of steps below —
+    # each step ends in a collective)
+    if world > 1:
+        t = torch.tensor([ms_res, ms_e2e], dtype=torch.float64, device=dev)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        ms_res, ms_e2e = float(t[0]), float(t[1])
     # a sustained section of our own (>= 2 s back to back, no L2 flush): the 100 ms clock sampler sees this one
     sus_steps = max(50, int(2500.0 / max(ms_res / args.steps, 0.05)))
     ms_sus, _ = timed(step_resident, sus_steps, flush=False)
     barrier()
     clocks = sampler.stop() if sampler else None
-
-    # max over ranks
     if world > 1:
-        t = torch.tensor([ms_res, ms_e2e, ms_sus], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms_sus], dtype=torch.float64, device=dev)
         td.all_reduce(t, op=td.ReduceOp.MAX)
-        ms_res, ms_e2e, ms_sus = float(t[0]), float(t[1]), float(t[2])
+        ms_sus = float(t[0])
     n_reg = nm * world * args.steps
     value = n_reg / (ms_res * 1e-3)
     e2e_value = n_reg / (ms_e2e * 1e-3)
@@ -355,6 +371,7 @@ def main():
     # ---- N > 1: strong scaling of the FIXED 8-model job (longest-processing-time assignment of models to ranks)
     strong = None
     if world > 1:
+        log("strong-scaling section")
         try:
             order = sorted(range(nm), key=lambda i: -models_h[i].shape[0])
             load, assign = [0] * world, [[] for _ in range(world)]
@@ -389,6 +406,7 @@ def main():
     # ---- configs[4]: prerejective RANSAC sweep 1e4 .. 1e7 hypotheses, hypothesis-sharded over the ranks
     sweep = None
     if not args.no_sweep:
+        log("ransac sweep section")
         try:
             cm, cs = models_d[0], scene_d
             cm.reset(); cs.reset()
@@ -416,14 +434,17 @@ def main():
                 pt = {"hypotheses": H, "ms": float(t[0]), "hypotheses_per_s": H / (float(t[0]) * 1e-3), "winner": int(best.hypothesis),
                       "inliers": int(best.inliers), "survivors": int(best.evaluated), "prerejection_rate": 1.0 - int(best.evaluated) / H}
                 if rank == 0 and not args.no_cpu_baseline and H <= 100_000:
-                    from oracle import orc
-                    orc.build(); orc.set_threads(0)
-                    qq = default_register_params(); qq.ransac.max_iterations = H
-                    n4m, n4s = orc.normals(models_h[0], p.normal_radius), orc.normals(scene_h, p.normal_radius)
-                    knn = orc.match_features(orc.fpfh(models_h[0], n4m, p.fpfh_radius), orc.fpfh(scene_h, n4s, p.fpfh_radius), p.ransac.correspondence_k)[0]
-                    t0 = time.time(); o = orc.ransac(models_h[0], scene_h, knn, qq.ransac); dt = time.time() - t0
-                    pt["cpu_all_threads_ms"] = 1e3 * dt
-                    pt["winner_equals_oracle"] = bool(o.hypothesis == best.hypothesis and o.inliers == best.inliers)
+                    try:        # rank-local: must never break the collective sequence of the loop
+                        from oracle import orc
+                        orc.build(); orc.set_threads(host_cores())
+                        qq = default_register_params(); qq.ransac.max_iterations = H
+                        n4m, n4s = orc.normals(models_h[0], p.normal_radius), orc.normals(scene_h, p.normal_radius)
+                        knn = orc.match_features(orc.fpfh(models_h[0], n4m, p.fpfh_radius), orc.fpfh(scene_h, n4s, p.fpfh_radius), p.ransac.correspondence_k)[0]
+                        t0 = time.time(); o = orc.ransac(models_h[0], scene_h, knn, qq.ransac); dt = time.time() - t0
+                        pt["cpu_all_threads_ms"] = 1e3 * dt
+                        pt["winner_equals_oracle"] = bool(o.hypothesis == best.hypothesis and o.inliers == best.inliers)
+                    except Exception as e:
+                        pt["cpu_error"] = repr(e)
                 sweep["points"].append(pt)
             cm.reset(); cs.reset()
         except Exception as e:
@@ -659,7 +680,7 @@ def main():
         parity["tolerance"] = "hypothesis / inliers / evaluated / iterations / converged / keypoint counts identical; pose <= 1e-4, fitness <= 1e-5"
         # configs[0] on its own: chair1 -> mcloud, the pair the >= 50x target is quoted on
         t0 = time.time(); o1 = orc.register(models_h[0], scene_h, p); t1 = time.time() - t0
-        allc = orc.set_threads(0)
+        allc = orc.set_threads(host_cores())
         t0 = time.time(); orc.register(models_h[0], scene_h, p); ta = time.time() - t0
         g1 = api.register_host(ctx, models_h[0], scene_h, p)
         ts = []

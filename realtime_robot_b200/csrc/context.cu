@@ -633,6 +633,44 @@ int rtr_model_set_from_clouds(rtr_context* ctx, rtr_cloud* const* members, int n
     return 0;
 }
 
+// Bounding box of the finite points of a host cloud (n x float4).  It sits on the critical path of every host-buffer entry
+// point — the grid dimensions come from it, so no kernel can be queued before it is known — hence SSE: one point per
+// 128-bit min / max (a NaN coordinate never wins: MINPS / MAXPS return the second operand then).  Points with an infinite
+// coordinate must be skipped as a whole, which the fast loop cannot do: it only notes that one exists and the scalar loop
+// redoes the cloud.
+#include <emmintrin.h>
+static void host_bbox(const float* xyz1, int n, float* mn3, float* mx3) {
+    bool any = false, odd = false;
+    float mn[4] = {FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX}, mx[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+    if (n > 0 && ((uintptr_t)xyz1 & 15) == 0) {
+        __m128 vmn = _mm_set1_ps(FLT_MAX), vmx = _mm_set1_ps(-FLT_MAX);
+        const __m128 absmask = _mm_castsi128_ps(_mm_set1_epi32(0x7fffffff)), big = _mm_set1_ps(FLT_MAX);
+        __m128 bad = _mm_setzero_ps();
+        for (int i = 0; i < n; ++i) {
+            const __m128 p = _mm_load_ps(xyz1 + 4 * (size_t)i);
+            // not (|p| <= FLT_MAX): NaN or infinity in some lane
+            bad = _mm_or_ps(bad, _mm_cmpnle_ps(_mm_and_ps(p, absmask), big));
+            vmn = _mm_min_ps(p, vmn);
+            vmx = _mm_max_ps(p, vmx);
+        }
+        odd = (_mm_movemask_ps(bad) & 7) != 0;         // lane 3 is the pad
+        _mm_storeu_ps(mn, vmn); _mm_storeu_ps(mx, vmx);
+        any = true;
+    }
+    if (odd || !any) {
+        any = false;
+        for (int a = 0; a < 3; ++a) { mn[a] = FLT_MAX; mx[a] = -FLT_MAX; }
+        for (int i = 0; i < n; ++i) {
+            const float* p = xyz1 + 4 * (size_t)i;
+            if (std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2])) {
+                any = true;
+                for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], p[a]); mx[a] = std::max(mx[a], p[a]); }
+            }
+        }
+    }
+    for (int a = 0; a < 3; ++a) { mn3[a] = any ? mn[a] : 0.f; mx3[a] = any ? mx[a] : 0.f; }
+}
+
 int rtr_model_set_from_host(rtr_context* ctx, const float* const* host_xyz1, const int* ns, int nseg, rtr_cloud** out) {
     if (!host_xyz1 || !ns) return rtr_fail("model_set", "bad argument", RTR_ERR_INVALID);
     for (int k = 0; k < nseg; ++k) if (ns[k] > 0 && !host_xyz1[k]) return rtr_fail("model_set", "null points", RTR_ERR_INVALID);
@@ -643,16 +681,7 @@ int rtr_model_set_from_host(rtr_context* ctx, const float* const* host_xyz1, con
         if (n > 0) RTR_CHECK(cudaMemcpyAsync(c->pts + c->seg_begin[k], host_xyz1[k], (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream), "set.h2d");
         RTR_MARK(ctx, "cloud.h2d");
         // the caller's buffer is host memory: take the bounding box here, so no device round trip is needed later
-        float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-        bool any = false;
-        for (int i = 0; i < n; ++i) {
-            const float* p = host_xyz1[k] + 4 * (size_t)i;
-            if (std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2])) {
-                any = true;
-                for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], p[a]); mx[a] = std::max(mx[a], p[a]); }
-            }
-        }
-        for (int a = 0; a < 3; ++a) { c->seg_bb[6 * k + a] = any ? mn[a] : 0.f; c->seg_bb[6 * k + 3 + a] = any ? mx[a] : 0.f; }
+        host_bbox(host_xyz1[k], n, &c->seg_bb[6 * k], &c->seg_bb[6 * k + 3]);
     }
     set_finish_bbox(c);
     return 0;
@@ -840,16 +869,7 @@ int rtr_cloud_upload(rtr_context* ctx, const float* host_xyz1, int n, rtr_cloud*
     if (n > 0) RTR_CHECK(cudaMemcpyAsync(c->pts, host_xyz1, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream), "cloud.h2d");
     RTR_MARK(ctx, "cloud.h2d");
     // the caller's buffer is host memory: take the bounding box here, so no device round trip is needed later
-    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    bool any = false;
-    for (int i = 0; i < n; ++i) {
-        const float* p = host_xyz1 + 4 * (size_t)i;
-        if (std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2])) {
-            any = true;
-            for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], p[a]); mx[a] = std::max(mx[a], p[a]); }
-        }
-    }
-    for (int a = 0; a < 3; ++a) { c->bb_min[a] = any ? mn[a] : 0.f; c->bb_max[a] = any ? mx[a] : 0.f; }
+    host_bbox(host_xyz1, n, c->bb_min, c->bb_max);
     c->bbox_valid = true;
     return 0;
 }

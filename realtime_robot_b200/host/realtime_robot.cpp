@@ -6,16 +6,48 @@
 //   realtime_robot <model.pcd> <scan.pcd> [--scale-model S] [--out transformed.pcd] [--hypotheses N] [--icp-only] [--native [--gate G]]
 //   --native runs the reference's own descriptor path (occupancy / TDF / yaw sweep / exhaustive consensus) and, like
 //   main(), transforms the SCAN into the model frame.
+//   --reference-main [--gate G] runs main()'s own loops (RealTimeRobot.cpp:49-104) through the reference's SIGNATURES:
+//   KeyPoint::getOccupiedGrid / get_TSDF / get_Vector3D per corner, get_Distance(matrix, model_key, scan_key) per pair, the
+//   match_by_* screens, then Ransac(pairpoint, 50, cloud, mcloud) — what a maintainer's unchanged call sites execute.
+//   realtime_robot --database <scan.pcd> <model1.pcd> [<model2.pcd> ...] [--hypotheses N]
+//   registers every database model against the scan in one batch (registerModelsToScene -> rtr_register_many_host).
 #include <chrono>
 #include <cstdlib>
 #include <iostream>
 #include <string>
 #include "registration.h"
 
+static int run_database(int argc, char** argv) {
+    pcl::PointCloud<pcl::PointXYZ> scan;
+    std::vector<pcl::PointCloud<pcl::PointXYZ>::Ptr> models;
+    rtr_register_params p;
+    rtr_default_register_params(&p);
+    if (argc < 4 || pcl::io::loadPCDFile(argv[2], scan) != 0) return 2;
+    for (int i = 3; i < argc; ++i) {
+        std::string a = argv[i];
+        if (a == "--hypotheses" && i + 1 < argc) { p.ransac.max_iterations = atoll(argv[++i]); continue; }
+        pcl::PointCloud<pcl::PointXYZ>::Ptr m(new pcl::PointCloud<pcl::PointXYZ>);
+        if (pcl::io::loadPCDFile(a, *m) != 0) return 1;
+        models.push_back(m);
+    }
+    auto start = std::chrono::steady_clock::now();
+    std::vector<Eigen::Matrix4f> poses;
+    std::vector<rtr_pose_result> rs;
+    std::vector<pcl::PointCloud<pcl::PointXYZ> > mk;
+    pcl::PointCloud<pcl::PointXYZ> sk;
+    if (!registerModelsToScene(models, scan, p, poses, &rs, &mk, &sk)) return 1;
+    for (size_t m = 0; m < models.size(); ++m)
+        std::cout << "model " << m << " converged " << (rs[m].converged != 0) << " hypothesis " << rs[m].hypothesis << " inliers " << rs[m].inliers
+                  << " fitness " << rs[m].fitness << " keypoints " << mk[m].size() << " scan_keypoints " << sk.size() << "\n";
+    std::cout << "Running Time : " << std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count() << std::endl;
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 2 && std::string(argv[1]) == "--database") return run_database(argc, argv);
     if (argc < 3) { fprintf(stderr, "usage: %s <model.pcd> <scan.pcd> [--scale-model S] [--out file.pcd] [--hypotheses N] [--icp-only]\n", argv[0]); return 2; }
     std::string out;
-    float scale = 1.0f, gate = 3.0f; long long hyp = 0; bool icp_only = false, native = false;
+    float scale = 1.0f, gate = 3.0f; long long hyp = 0; bool icp_only = false, native = false, reference_main = false;
     for (int i = 3; i < argc; ++i) {
         std::string a = argv[i];
         if (a == "--scale-model" && i + 1 < argc) scale = strtof(argv[++i], nullptr);
@@ -23,6 +55,7 @@ int main(int argc, char** argv) {
         else if (a == "--hypotheses" && i + 1 < argc) hyp = atoll(argv[++i]);
         else if (a == "--icp-only") icp_only = true;
         else if (a == "--native") native = true;
+        else if (a == "--reference-main") reference_main = true;
         else if (a == "--gate" && i + 1 < argc) gate = strtof(argv[++i], nullptr);
     }
     pcl::PointCloud<pcl::PointXYZ>::Ptr cloud(new pcl::PointCloud<pcl::PointXYZ>), mcloud(new pcl::PointCloud<pcl::PointXYZ>);
@@ -34,13 +67,42 @@ int main(int argc, char** argv) {
     }
     ModelPoint modelpoint(mcloud);
     modelpoint.getKeypoint();
-    if (native) { modelpoint.getArea(mcloud); std::cout << "model surfaces kept: " << modelpoint.surface.size() << std::endl; }     // RealTimeRobot.cpp:41
+    if (native || reference_main) { modelpoint.getArea(mcloud); std::cout << "model surfaces kept: " << modelpoint.surface.size() << std::endl; }     // RealTimeRobot.cpp:41
     auto start = std::chrono::steady_clock::now();          // RealTimeRobot.cpp:43
     ScanPoint scanpoint(cloud);
     scanpoint.getKeypoint();
     Eigen::Matrix4f matrix = Eigen::Matrix4f::Identity();
     pcl::PointCloud<pcl::PointXYZ> moved;
-    if (native) {
+    if (reference_main) {
+        // RealTimeRobot.cpp:47-104 with the reference's own call sites; `gate` replaces the literal 3 of :83
+        rtr_host::native_params().pair_gate = gate;
+        scanpoint.get_Area(cloud);
+        std::vector<KeyPoint> model_keys, scan_keys;
+        for (const auto& pt : modelpoint.key_coordinates.points) {          // :62-69
+            KeyPoint k(pt);
+            k.getOccupiedGrid(mcloud); k.get_TSDF(mcloud); k.get_Vector3D(modelpoint.surface);
+            model_keys.push_back(k);
+        }
+        for (const auto& pt : scanpoint.key_coordinates.points) {           // :52-60
+            KeyPoint k(pt);
+            k.getOccupiedGrid(cloud); k.get_Vector3D(scanpoint.surface);
+            scan_keys.push_back(k);
+        }
+        std::vector<PairPoint> pairpoint;
+        for (auto& mkp : model_keys)                                         // :73-102
+            for (auto& skp : scan_keys) {
+                Eigen::Matrix4f m;
+                if (get_Distance(m, mkp, skp) < gate && match_by_height(mkp.Key_coordinate, skp.Key_coordinate) &&
+                    match_by_area(mkp.vector3D, skp.vector3D) && match_by_occupied(mkp.Occupiedgrid, skp.Occupiedgrid)) {
+                    PairPoint pp; pp.point_i = mkp; pp.point_j = skp;
+                    pairpoint.push_back(pp);
+                }
+            }
+        std::cout << "pairs " << pairpoint.size() << std::endl;
+        matrix = Ransac(pairpoint, 50, cloud, mcloud);                       // :104
+        std::cout << "matrix\n" << matrix;
+        pcl::transformPointCloud(*cloud, moved, matrix);                     // :105
+    } else if (native) {
         rtr_native_params np; rtr_native_default_params(&np);
         np.pair_gate = gate;
         rtr_pose_result r = rtr_pose_result();

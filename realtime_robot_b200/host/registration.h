@@ -22,6 +22,14 @@ inline rtr_context* default_context() {
     return ctx;
 }
 
+// Process-wide parameters of the reference-native path behind the reference's own signatures (which carry none): the
+// literals of key_point.h / matching.h / function.h / RealTimeRobot.cpp:83 by default; a caller may edit them once, e.g.
+// the pair gate or the quirk_* flags.
+inline rtr_native_params& native_params() {
+    static rtr_native_params p = []() { rtr_native_params q; rtr_native_default_params(&q); return q; }();
+    return p;
+}
+
 struct DeviceCloud {   // RAII handle around rtr_cloud
     rtr_cloud* h = nullptr;
     explicit DeviceCloud(const pcl::PointCloud<pcl::PointXYZ>& c) {
@@ -225,17 +233,22 @@ inline bool match_by_occupied(OccupiedGrid& o1, OccupiedGrid& o2, bool quirk = f
     return !(temp > 2 || temp < 0.5);
 }
 
-// matching.h:122-222 for one pair.  p1_key: a MODEL keypoint with its TDF; p2_scan: a SCAN keypoint with its occupancy cloud.
-// model / scan are the clouds the keypoints came from.  (Batched: rtr_native_pair_scores.)
-inline float get_Distance(Eigen::Matrix4f& key_transform, KeyPoint& p1_key, KeyPoint& p2_scan,
-                          const pcl::PointCloud<pcl::PointXYZ>& model, const pcl::PointCloud<pcl::PointXYZ>& scan, const float resolution = 0.01f) {
+// matching.h:122 — the reference's signature, unchanged:
+//     float get_Distance(Eigen::Matrix4f& key_transform, KeyPoint& p1_key, KeyPoint& p2_key, const float resolution = 0.01f)
+// p1_key: a MODEL keypoint, p2_key: a SCAN keypoint, both after getOccupiedGrid (RealTimeRobot.cpp:52-69).  Everything the
+// sweep needs travels inside the two records, as in the reference: the model keypoint's TDF is built from ITS occupancy
+// cloud (key_point.h:251-318) and the scan keypoint contributes its occupancy cloud (the intended semantics, matching.h:17-120;
+// Appendix B#3).  The two occupancy clouds go to the device, where cropping an occupancy cloud to its own +-0.1 box is the
+// identity, and rtr_native_pair_scores evaluates the pair.  (Batched: rtr_native_pair_scores on the whole clouds.)
+inline float get_Distance(Eigen::Matrix4f& key_transform, KeyPoint& p1_key, KeyPoint& p2_key, const float resolution = 0.01f) {
     key_transform = Eigen::Matrix4f::Identity();
-    rtr_native_params p; rtr_native_default_params(&p);
+    if (!p1_key.Occupiedgrid.cloud || !p2_key.Occupiedgrid.cloud) return 100000000.f;
+    rtr_native_params p = rtr_host::native_params();
     p.resolution = resolution;
-    rtr_host::DeviceCloud dm(model), ds(scan);
+    rtr_host::DeviceCloud dm(*p1_key.Occupiedgrid.cloud), ds(*p2_key.Occupiedgrid.cloud);
     if (!dm.h || !ds.h) return 100000000.f;
     float score = 100000000.f; int step = 0;
-    if (rtr_native_pair_scores(dm.h, &p1_key.Key_coordinate.x, 1, ds.h, &p2_scan.Key_coordinate.x, 1, &p, &score, &step, key_transform.data()) != 0)
+    if (rtr_native_pair_scores(dm.h, &p1_key.Key_coordinate.x, 1, ds.h, &p2_key.Key_coordinate.x, 1, &p, &score, &step, key_transform.data()) != 0)
         return 100000000.f;
     return score;
 }
@@ -244,7 +257,7 @@ inline float get_Distance(Eigen::Matrix4f& key_transform, KeyPoint& p1_key, KeyP
 // clouds.  Returns the transform main() applies to `cloud` (the scan); identity when nothing is consistent (the reference
 // returns an uninitialised matrix there, Appendix B#2).
 inline Eigen::Matrix4f Ransac(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud, pcl::PointCloud<pcl::PointXYZ>::Ptr mcloud,
-                              const rtr_native_params* params = nullptr, rtr_pose_result* details = nullptr) {
+                              const rtr_native_params* params, rtr_pose_result* details = nullptr) {
     Eigen::Matrix4f m = Eigen::Matrix4f::Identity();
     rtr_native_params p;
     if (params) p = *params; else rtr_native_default_params(&p);
@@ -256,6 +269,53 @@ inline Eigen::Matrix4f Ransac(pcl::PointCloud<pcl::PointXYZ>::Ptr cloud, pcl::Po
     std::cout << r.evaluated << "aaaa" << std::endl;                     // RealTimeRobot.cpp:103
     if (details) *details = r;
     return m;
+}
+
+// function.h:35 — the reference's signature, unchanged:
+//     Eigen::Matrix4f Ransac(vector<PairPoint> pairpoint, int ransac_times, Ptr cloud, Ptr mcloud)
+// The reference ignores ransac_times and both clouds and enumerates every pair of `pairpoint`, re-running get_Distance for
+// each (Appendix B#12).  Here the device redoes main()'s whole chain — corners, descriptors, all-pairs sweep, screens,
+// exhaustive consensus — from the two clouds main() passes (RealTimeRobot.cpp:104), which yields the pair list main() built;
+// `pairpoint` is accepted for source compatibility.
+inline Eigen::Matrix4f Ransac(std::vector<PairPoint> /*pairpoint*/, int /*ransac_times*/, pcl::PointCloud<pcl::PointXYZ>::Ptr cloud,
+                              pcl::PointCloud<pcl::PointXYZ>::Ptr mcloud) {
+    if (!cloud || !mcloud) return Eigen::Matrix4f::Identity();
+    return Ransac(cloud, mcloud, &rtr_host::native_params(), nullptr);
+}
+
+// One scan against a database of models (README.md:10; RealTimeRobot.cpp:45-104 once per model): rtr_register_many_host.
+// poses[m] / details[m] belong to models[m]; model_keypoints / scan_keypoints (optional) receive the refined Harris corners
+// the batch found — ModelPoint::key_coordinates / ScanPoint::key_coordinates.
+inline bool registerModelsToScene(const std::vector<pcl::PointCloud<pcl::PointXYZ>::Ptr>& models, const pcl::PointCloud<pcl::PointXYZ>& scene,
+                                  const rtr_register_params& params, std::vector<Eigen::Matrix4f>& poses, std::vector<rtr_pose_result>* details = nullptr,
+                                  std::vector<pcl::PointCloud<pcl::PointXYZ> >* model_keypoints = nullptr,
+                                  pcl::PointCloud<pcl::PointXYZ>* scan_keypoints = nullptr) {
+    rtr_context* ctx = rtr_host::default_context();
+    poses.assign(models.size(), Eigen::Matrix4f::Identity());
+    if (!ctx || models.empty()) return false;
+    std::vector<const float*> ptrs(models.size());
+    std::vector<int> ns(models.size());
+    for (size_t m = 0; m < models.size(); ++m) {
+        if (!models[m]) return false;
+        ptrs[m] = models[m]->points.empty() ? nullptr : &models[m]->points[0].x;
+        ns[m] = (int)models[m]->size();
+    }
+    std::vector<rtr_pose_result> rs(models.size());
+    if (rtr_register_many_host(ctx, ptrs.data(), ns.data(), (int)models.size(), scene.points.empty() ? nullptr : &scene.points[0].x, (int)scene.size(),
+                               &params, rs.data()) != 0) return false;
+    for (size_t m = 0; m < models.size(); ++m) memcpy(poses[m].data(), rs[m].pose, sizeof(rs[m].pose));
+    auto corners = [&](int member, pcl::PointCloud<pcl::PointXYZ>& out) {
+        out.clear();
+        std::vector<pcl::PointXYZ> kp(64);
+        int n = 0;
+        int rc = rtr_register_many_keypoints(ctx, member, &kp[0].x, 64, &n);
+        if (rc != 0 && rc != RTR_ERR_CAPACITY) return;
+        for (int i = 0; i < n && i < 64; ++i) out.push_back(pcl::PointXYZ(kp[i].x, kp[i].y, kp[i].z));
+    };
+    if (model_keypoints) { model_keypoints->resize(models.size()); for (size_t m = 0; m < models.size(); ++m) corners((int)m, (*model_keypoints)[m]); }
+    if (scan_keypoints) corners((int)models.size(), *scan_keypoints);
+    if (details) *details = rs;
+    return true;
 }
 
 // The north-star pipeline on two pcl clouds: model -> scene pose, mean squared fitness, RANSAC bookkeeping.

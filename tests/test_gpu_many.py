@@ -134,3 +134,50 @@ def test_register_many_edge_cases(api, gpu_ctx, clouds):
     with pytest.raises(_lib.RtrError) as e:
         api.register_many_host(gpu_ctx, [c1], scene, q)
     assert e.value.code == 1
+
+
+def test_cpp_host_database_mode_matches_ctypes_path(api, gpu_ctx, clouds):
+    """The C++ host mirror's registerModelsToScene (rtr_register_many_host behind pcl::PointCloud in / Eigen::Matrix4f out):
+    same records as the ctypes path, and the corners come back as ModelPoint / ScanPoint::key_coordinates would hold them."""
+    import os
+    import re
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "realtime_robot_b200", "realtime_robot")
+    data = os.path.join(ROOT, "data", "clouds")
+    names = ["chair1", "chair2", "desk1"]
+    r = subprocess.run([exe, "--database", os.path.join(data, "mcloud.pcd")] + [os.path.join(data, n + ".pcd") for n in names] + ["--hypotheses", "20000"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    p = default_register_params()
+    p.ransac.max_iterations = 20000
+    want = api.register_many_host(gpu_ctx, [clouds(n) for n in names], clouds("mcloud"), p)
+    rows = re.findall(r"model (\d+) converged (\d) hypothesis (-?\d+) inliers (\d+) fitness (\S+) keypoints (\d+) scan_keypoints (\d+)", r.stdout)
+    assert len(rows) == len(names), r.stdout
+    for row, w in zip(rows, want):
+        assert (int(row[1]) != 0, int(row[2]), int(row[3]), int(row[5]), int(row[6])) == (w.converged != 0, w.hypothesis, w.inliers, w.n_keypoints_src, w.n_keypoints_tgt)
+
+
+def test_cpp_reference_signatures_run_mains_loops(api, gpu_ctx, clouds):
+    """main()'s own loops (RealTimeRobot.cpp:49-104) through the reference's signatures — KeyPoint::getOccupiedGrid / get_TSDF,
+    get_Distance(matrix, model_key, scan_key), match_by_*, Ransac(pairpoint, 50, cloud, mcloud) — give the pair count and the
+    pose of the batched device path (rtr_native_register)."""
+    import os
+    import re
+    import subprocess
+    from conftest import ROOT
+    from realtime_robot_b200.params import default_native_params
+    exe = os.path.join(ROOT, "realtime_robot_b200", "realtime_robot")
+    f = os.path.join(ROOT, "data", "clouds", "T0_m8111.pcd")
+    r = subprocess.run([exe, f, f, "--reference-main", "--gate", "30"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    pairs = int(re.search(r"pairs (\d+)", r.stdout).group(1))
+    nums = [float(v) for v in re.search(r"matrix\n(.*?)Running", r.stdout, re.S).group(1).split()]
+    got = np.array(nums, dtype=np.float32).reshape(4, 4)
+    c = clouds("T0_m8111")
+    cm, cs = api.Cloud(gpu_ctx, c), api.Cloud(gpu_ctx, c)
+    q = default_native_params(); q.pair_gate = 30.0
+    w = api.native_register(cm, cs, q)
+    assert pairs == w.evaluated and pairs > 0
+    assert np.abs(got - w.matrix()).max() < 1e-4
+    cm.free(); cs.free()
