@@ -12,7 +12,17 @@
 #include <cfloat>
 #include <map>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/rtr.h"
+
+// NVTX range around the host-side enqueue of a stage (SURVEY section 5 "tracing"): shows up as rtr.<stage> rows in Nsight
+// Systems / ncu --nvtx; header-only NVTX v3, a pointer test when no tool is attached.
+struct RtrRange {
+    explicit RtrRange(const char* name) { nvtxRangePushA(name); }
+    ~RtrRange() { nvtxRangePop(); }
+    RtrRange(const RtrRange&) = delete;
+    RtrRange& operator=(const RtrRange&) = delete;
+};
 
 #define RTR_NUM_EVENTS 16
 // clouds up to this size use one WARP per point in the gather kernels (one thread per point cannot fill 148 SMs)

@@ -456,6 +456,7 @@ static void grid_dims(const float* bb_min, const float* bb_max, float cell, doub
 
 // Model sets: one launch builds the grids of every member cloud for one cell size (clusters of 8 CTAs, one per segment).
 int rtr_get_grids(rtr_cloud* c, const float* cells, int n_cells, DevGrid** out) {
+    RtrRange nvtx_range("rtr.grid_build.many");
     rtr_context* ctx = c->ctx;
     const int nseg = c->nseg();
     if (nseg <= 0 || nseg > RTR_MAX_SEGMENTS) return rtr_fail("grid", "rtr_get_grids needs a model set of 1..32 clouds", RTR_ERR_INVALID);
@@ -500,6 +501,7 @@ int rtr_get_grids(rtr_cloud* c, const float* cells, int n_cells, DevGrid** out) 
 }
 
 int rtr_get_grid(rtr_cloud* c, float cell, DevGrid** out) {
+    RtrRange nvtx_range("rtr.grid");
     if (c->nseg() > 0) return rtr_get_grids(c, &cell, 1, out);
     // a zero / negative / non-finite cell would never satisfy the dimension caps below (h *= 1.25 keeps 0 at 0)
     if (!(cell > 0.f) || !std::isfinite(cell)) return rtr_fail("grid", "cell size (search radius) must be finite and > 0", RTR_ERR_INVALID);

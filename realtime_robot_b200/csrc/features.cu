@@ -825,13 +825,13 @@ __global__ void __launch_bounds__(FW_WARPS * 32) k_fpfh_weight_tiled(GridView g,
 #define MATCH_KMAX 8
 __global__ void __launch_bounds__(MATCH_WARPS * 32) k_match(const float* __restrict__ fa, int na, const float* __restrict__ fb,
                                                             int nb, int k, int* __restrict__ out_idx, float* __restrict__ out_dist,
-                                                            const int* __restrict__ rows, const int* __restrict__ row_count) {
+                                                            const int* __restrict__ rows, const int* __restrict__ row_count, int row_offset) {
     __shared__ float tile[MATCH_TILE * 33];
     __shared__ float src[MATCH_WARPS][33];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // optional row list (rows the tensor-core prefilter could not certify): same kernel, indirect row index
     int nrows = rows ? *row_count : na;
-    for (int rbase = blockIdx.x * MATCH_WARPS; rbase < nrows; rbase += gridDim.x * MATCH_WARPS) {
+    for (int rbase = row_offset + blockIdx.x * MATCH_WARPS; rbase < nrows; rbase += gridDim.x * MATCH_WARPS) {
         int li = rbase + warp;
         bool active = li < nrows;
         int row = active ? (rows ? rows[li] : li) : 0;
@@ -897,12 +897,134 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_match(const float* __restr
     }
 }
 
+// Redo of the few rows the tensor-core prefilter could not certify.  k_match gives a row to ONE warp, fine when every row is
+// searched (thousands of warps), but 240 uncertified rows of the 262 144 x 65 536 search were 240 warps scanning 65 536
+// targets each: 5.0 ms of the 12.0 ms search with 12 % of the warp slots filled (ncu, profiles/r02).  Here a row goes to
+// MS_SPLITS CTAs of 8 warps, every warp scanning its own slice of the targets (same sequential fp64 distance, same
+// per-lane top-8), the CTA's 256 lists are merged by block-wide lexicographic (distance, index) minima, and the last CTA of
+// a row to finish (ticket) merges the MS_SPLITS partial lists.  Same distances, same tie rule: same result.
+#define MS_SPLITS 16
+__global__ void __launch_bounds__(MATCH_WARPS * 32) k_match_rows_split(const float* __restrict__ fa, const float* __restrict__ fb, int nb, int k,
+                                                                       int* __restrict__ out_idx, float* __restrict__ out_dist,
+                                                                       const int* __restrict__ rows, const int* __restrict__ row_count,
+                                                                       float* __restrict__ part_d, int* __restrict__ part_i, unsigned* __restrict__ tickets,
+                                                                       int max_rows) {
+    __shared__ float src[33];
+    __shared__ float red_d[MATCH_WARPS];
+    __shared__ int red_i[MATCH_WARPS];
+    __shared__ int is_last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nrows = min(*row_count, max_rows);      // rows beyond the partial-list capacity are left to k_match
+    for (int li = blockIdx.x; li < nrows; li += gridDim.x) {
+        const int row = rows[li], split = blockIdx.y;
+        __syncthreads();
+        if (threadIdx.x < 33) src[threadIdx.x] = fa[(size_t)row * 33 + threadIdx.x];
+        __syncthreads();
+        float bd[MATCH_KMAX]; int bi[MATCH_KMAX];
+#pragma unroll
+        for (int t = 0; t < MATCH_KMAX; ++t) { bd[t] = FLT_MAX; bi[t] = 0x7fffffff; }
+        // slice of the targets of this CTA, strided over its 256 threads
+        const int per = (nb + MS_SPLITS - 1) / MS_SPLITS, j0 = split * per, j1 = min(nb, j0 + per);
+        for (int j = j0 + (int)threadIdx.x; j < j1; j += MATCH_WARPS * 32) {
+            const float* b = fb + (size_t)j * 33;
+            double sacc = 0;
+#pragma unroll
+            for (int c = 0; c < 33; ++c) { double d = (double)src[c] - (double)__ldg(b + c); sacc += d * d; }
+            const float df = (float)sacc;
+            if (df == df && (df < bd[MATCH_KMAX - 1] || (df == bd[MATCH_KMAX - 1] && j < bi[MATCH_KMAX - 1]))) {
+                bd[MATCH_KMAX - 1] = df; bi[MATCH_KMAX - 1] = j;
+#pragma unroll
+                for (int t = MATCH_KMAX - 1; t > 0; --t) {
+                    bool sw = (bd[t] < bd[t - 1]) || (bd[t] == bd[t - 1] && bi[t] < bi[t - 1]);
+                    if (sw) { float td = bd[t]; bd[t] = bd[t - 1]; bd[t - 1] = td; int ti = bi[t]; bi[t] = bi[t - 1]; bi[t - 1] = ti; }
+                }
+            }
+        }
+        // k rounds of a block-wide lexicographic minimum over the 256 list heads; the owner of the winner pops it
+        float* pd = part_d + ((size_t)li * MS_SPLITS + split) * MATCH_KMAX;
+        int* pi = part_i + ((size_t)li * MS_SPLITS + split) * MATCH_KMAX;
+        for (int t = 0; t < k; ++t) {
+            float md = bd[0]; int mi = bi[0];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                float od = __shfl_xor_sync(0xffffffffu, md, o);
+                int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+                if (od < md || (od == md && oi < mi)) { md = od; mi = oi; }
+            }
+            if (lane == 0) { red_d[warp] = md; red_i[warp] = mi; }
+            __syncthreads();
+            float gd = red_d[0]; int gi = red_i[0];
+#pragma unroll
+            for (int w = 1; w < MATCH_WARPS; ++w) if (red_d[w] < gd || (red_d[w] == gd && red_i[w] < gi)) { gd = red_d[w]; gi = red_i[w]; }
+            if (gi != 0x7fffffff && bi[0] == gi && bd[0] == gd) {      // target indices are unique: exactly one thread owns the winner
+#pragma unroll
+                for (int u = 0; u < MATCH_KMAX - 1; ++u) { bd[u] = bd[u + 1]; bi[u] = bi[u + 1]; }
+                bd[MATCH_KMAX - 1] = FLT_MAX; bi[MATCH_KMAX - 1] = 0x7fffffff;
+            }
+            if (threadIdx.x == 0) { pd[t] = gd; pi[t] = gi; }
+            __syncthreads();
+        }
+        // the last CTA of this row merges the MS_SPLITS sorted partial lists (k entries each)
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned tk = atomicAdd(tickets + li, 1u);
+            is_last = (tk == MS_SPLITS - 1);
+        }
+        __syncthreads();
+        if (is_last && warp == 0) {
+            __threadfence();
+            const float* rd = part_d + (size_t)li * MS_SPLITS * MATCH_KMAX;
+            const int* ri = part_i + (size_t)li * MS_SPLITS * MATCH_KMAX;
+            int head = 0;                           // lane s < MS_SPLITS walks the sorted list of split s
+            for (int t = 0; t < k; ++t) {
+                float md = FLT_MAX; int mi = 0x7fffffff;
+                if (lane < MS_SPLITS && head < k) { md = __ldcg(rd + lane * MATCH_KMAX + head); mi = __ldcg(ri + lane * MATCH_KMAX + head); }
+                float gd = md; int gi = mi;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    float od = __shfl_xor_sync(0xffffffffu, gd, o);
+                    int oi = __shfl_xor_sync(0xffffffffu, gi, o);
+                    if (od < gd || (od == gd && oi < gi)) { gd = od; gi = oi; }
+                }
+                if (gi != 0x7fffffff && mi == gi && md == gd) ++head;
+                if (lane == 0) {
+                    const bool none = (gi == 0x7fffffff);
+                    out_idx[(size_t)row * k + t] = none ? -1 : gi;
+                    out_dist[(size_t)row * k + t] = none ? __int_as_float(0x7fc00000) : gd;
+                }
+            }
+            if (lane == 0) tickets[li] = 0u;
+        }
+    }
+}
+
 // exact search for all rows (rows == nullptr) or for a device-side list of rows
 int rtr_match_exact_launch(rtr_context* ctx, const float* fa, int na, const float* fb, int nb, int k, int* out_idx, float* out_dist,
                            const int* rows, const int* row_count, int max_rows) {
     if (max_rows <= 0) return 0;
+    if (rows && nb >= 4096) {
+        // a (short) row list against many targets: MS_SPLITS CTAs per row, for the first `cap` rows of the list (the partial
+        // lists are sized for that many; a longer list — the certificate failing wholesale — finishes in k_match below)
+        const int cap = std::min(max_rows, 16384);
+        float* part_d = nullptr; int* part_i = nullptr; unsigned* tickets = nullptr;
+        if (int e = tmp_alloc(ctx, &part_d, (size_t)cap * MS_SPLITS * MATCH_KMAX, "match")) return e;
+        if (int e = tmp_alloc(ctx, &part_i, (size_t)cap * MS_SPLITS * MATCH_KMAX, "match")) return e;
+        if (int e = tmp_alloc(ctx, &tickets, (size_t)cap, "match")) return e;
+        RTR_CHECK(cudaMemsetAsync(tickets, 0, sizeof(unsigned) * (size_t)cap, ctx->stream), "match");
+        k_match_rows_split<<<dim3(std::min(cap, ctx->sm_count * 2), MS_SPLITS), MATCH_WARPS * 32, 0, ctx->stream>>>(fa, fb, nb, k, out_idx, out_dist, rows, row_count,
+                                                                                                              part_d, part_i, tickets, cap);
+        RTR_LAUNCH_CHECK(ctx, "match.redo");
+        dev_free(ctx, part_d); dev_free(ctx, part_i); dev_free(ctx, tickets);
+        if (max_rows > cap) {
+            int grid = std::min(nblk(max_rows - cap, MATCH_WARPS), ctx->sm_count * 8);
+            k_match<<<grid, MATCH_WARPS * 32, 0, ctx->stream>>>(fa, na, fb, nb, k, out_idx, out_dist, rows, row_count, cap);
+            RTR_LAUNCH_CHECK(ctx, "match.redo");
+        }
+        return 0;
+    }
     int grid = std::min(nblk(max_rows, MATCH_WARPS), ctx->sm_count * 8);
-    k_match<<<grid, MATCH_WARPS * 32, 0, ctx->stream>>>(fa, na, fb, nb, k, out_idx, out_dist, rows, row_count);
+    k_match<<<grid, MATCH_WARPS * 32, 0, ctx->stream>>>(fa, na, fb, nb, k, out_idx, out_dist, rows, row_count, 0);
     RTR_LAUNCH_CHECK(ctx, rows ? "match.redo" : "match");
     return 0;
 }
@@ -912,6 +1034,7 @@ int rtr_match_tc_dev(rtr_context* ctx, const float* fa, int ns, const float* fb,
 
 // feature k-NN dispatcher: tensor-core prefilter + exact re-rank for large problems, exact SIMT kernel otherwise
 static int match_dispatch(rtr_context* ctx, const float* fa, int na, const float* fb, int nb, int k, int* out_idx, float* out_dist, int* stats) {
+    RtrRange nvtx_range("rtr.match_features");
     if (stats) { stats[0] = -1; stats[1] = 0; stats[2] = 0; }
     if (rtr_match_tc_wanted(na, nb)) return rtr_match_tc_dev(ctx, fa, na, fb, nb, k, out_idx, out_dist, stats);
     return rtr_match_exact_launch(ctx, fa, na, fb, nb, k, out_idx, out_dist, nullptr, nullptr, na);
@@ -949,6 +1072,7 @@ int rtr_match_features_dev(rtr_context* ctx, const float* fa, int na, const floa
 
 // ----------------------------------------------------------------------------- host drivers
 int rtr_normals_dev(rtr_cloud* c, float radius) {
+    RtrRange nvtx_range("rtr.normals");
     rtr_context* ctx = c->ctx;
     if (c->normals && c->normals_radius == radius) return 0;
     DevGrid* g;
@@ -978,6 +1102,7 @@ int rtr_normals_dev(rtr_cloud* c, float radius) {
 
 int rtr_harris_dev(rtr_cloud* c, float radius, float threshold, int nms, int refine, int** d_kp_idx, float4** d_kp_xyz,
                    int** d_count) {
+    RtrRange nvtx_range("rtr.harris3d");
     rtr_context* ctx = c->ctx;
     if (!c->normals) return rtr_fail("harris", "rtr_normals must run first", RTR_ERR_NOT_READY);
     DevGrid* g;
@@ -1047,6 +1172,7 @@ int rtr_harris_dev(rtr_cloud* c, float radius, float threshold, int nms, int ref
 }
 
 int rtr_fpfh_dev(rtr_cloud* c, float radius) {
+    RtrRange nvtx_range("rtr.fpfh");
     rtr_context* ctx = c->ctx;
     if (!c->normals) return rtr_fail("fpfh", "rtr_normals must run first", RTR_ERR_NOT_READY);
     if (c->fpfh && c->fpfh_radius == radius) return 0;

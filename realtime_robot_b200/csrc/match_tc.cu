@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(RR_WARPS * 32)
 k_tc_rerank(const float* __restrict__ fa, int ns, const float* __restrict__ fb, int nt, int k, const int* __restrict__ cand_idx,
             const float* __restrict__ cand_val, const float* __restrict__ cand_thr, int n_splits, int TC_KEEP, const float* __restrict__ a_norms,
             const float* __restrict__ b_norms, const float* __restrict__ nb_max_p, int* __restrict__ out_idx, float* __restrict__ out_dist, int* __restrict__ redo_rows, int* __restrict__ redo_count,
-            float* __restrict__ err_ratio_max) {
+            float* __restrict__ err_ratio_max, int force_redo) {
     __shared__ float src[RR_WARPS][36];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int row = blockIdx.x * RR_WARPS + warp;
@@ -509,7 +509,7 @@ k_tc_rerank(const float* __restrict__ fa, int ns, const float* __restrict__ fb, 
     // its exact distance is >= T - E.  The row is final iff the exact k-th best is strictly below that.
     double reach = sqrt(na) + sqrt(fmax((double)kth, 0.0));
     double E = TC_ERR(na, fmin(nb_max, reach * reach));
-    bool certified = sane && (T == DBL_MAX || (kth < FLT_MAX && (double)kth < T - E));
+    bool certified = !force_redo && sane && (T == DBL_MAX || (kth < FLT_MAX && (double)kth < T - E));
     if (!certified && lane == 0) redo_rows[atomicAdd(redo_count, 1)] = row;
 }
 
@@ -607,7 +607,10 @@ int rtr_match_tc_dev(rtr_context* ctx, const float* fa, int ns, const float* fb,
         RTR_CHECK(le, "match.tc_mma");
     }
     RTR_LAUNCH_CHECK(ctx, "match.tc_mma");
-    k_tc_rerank<<<nblk(ns, RR_WARPS), RR_WARPS * 32, 0, ctx->stream>>>(fa, ns, fb, nt, k, cand_idx, cand_val, cand_thr, lists, keep, a_norms, b_norms, d_nbmax, out_idx, out_dist, redo_rows, redo_count, d_nbmax + 1);
+    // RTR_MATCH_FORCE_REDO=1 (tests): treat every row as uncertified, so the exact redo kernels answer all of them
+    const char* fr = getenv("RTR_MATCH_FORCE_REDO");
+    const int force_redo = (fr && fr[0] == '1') ? 1 : 0;
+    k_tc_rerank<<<nblk(ns, RR_WARPS), RR_WARPS * 32, 0, ctx->stream>>>(fa, ns, fb, nt, k, cand_idx, cand_val, cand_thr, lists, keep, a_norms, b_norms, d_nbmax, out_idx, out_dist, redo_rows, redo_count, d_nbmax + 1, force_redo);
     RTR_LAUNCH_CHECK(ctx, "match.tc_rerank");
     if (int e = rtr_match_exact_launch(ctx, fa, ns, fb, nt, k, out_idx, out_dist, redo_rows, redo_count, ns)) return e;
     if (stats) {

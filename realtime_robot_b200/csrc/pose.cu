@@ -203,6 +203,7 @@ __global__ void k_result_init(rtr_pose_result* res) {
 }
 
 int rtr_ransac_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_ransac_params* p, rtr_pose_result* d_result) {
+    RtrRange nvtx_range("rtr.ransac_prerejective");
     rtr_context* ctx = src->ctx;
     k_result_init<<<1, 32, 0, ctx->stream>>>(d_result);
     RTR_LAUNCH_CHECK(ctx, "ransac.init");
@@ -462,6 +463,7 @@ __global__ void k_result_init_many(rtr_pose_result* res, int n) {
 // members' correspondences (target-local indices), n_source_points x k.  d_results: n_models records.
 static int ransac_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const int* knn_all, int knn_k, const rtr_ransac_params* p,
                            rtr_pose_result* d_results) {
+    RtrRange nvtx_range("rtr.ransac_prerejective.many");
     rtr_context* ctx = set->ctx;
     const long long h0 = p->hypothesis_begin, h1 = (p->hypothesis_end > 0) ? p->hypothesis_end : p->max_iterations;
     const int nt = set->seg_begin[tgt_seg + 1] - set->seg_begin[tgt_seg];
@@ -1095,6 +1097,7 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_fitness(GridView g, GridVie
 
 int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const float* d_init_pose16, int init_from_result,
                 rtr_pose_result* d_result) {
+    RtrRange nvtx_range("rtr.icp");
     rtr_context* ctx = src->ctx;
     int n = src->n;
     if (p->estimator != 0 && p->estimator != 1) return rtr_fail("icp", "estimator must be 0 (SVD) or 1 (point-to-plane LLS)", RTR_ERR_INVALID);
@@ -1225,6 +1228,7 @@ __global__ void k_icp_init_many(const __grid_constant__ IcpMany im, const float4
 }
 
 static int icp_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const rtr_icp_params* p, rtr_pose_result* d_results) {
+    RtrRange nvtx_range("rtr.icp.many");
     rtr_context* ctx = set->ctx;
     if (p->estimator != 0 && p->estimator != 1) return rtr_fail("icp", "estimator must be 0 (SVD) or 1 (point-to-plane LLS)", RTR_ERR_INVALID);
     if (p->estimator == 1 && !set->normals) return rtr_fail("icp", "estimator 1 (point-to-plane) needs normals on the target", RTR_ERR_NOT_READY);
@@ -1335,6 +1339,7 @@ __global__ void k_register_finish_many(const __grid_constant__ IcpMany im, rtr_p
 // set: n_models + 1 members, the scan last.  Queues everything on the context's stream, ends with the D2H of the records
 // (and the corner previews) into the context's pinned area.
 static int register_many_enqueue(rtr_cloud* set, int n_models, const rtr_register_params* p) {
+    RtrRange nvtx_range("rtr.register_many");
     rtr_context* ctx = set->ctx;
     const int tgt = n_models, nseg = n_models + 1;
     for (int k = 0; k < nseg; ++k)
@@ -1560,6 +1565,7 @@ int rtr_icp(rtr_cloud* source, rtr_cloud* target, const rtr_icp_params* p, const
 // stages onto the second stream; rtr_register_begin (many registrations in flight on many contexts, throughput matters:
 // 16 streams instead of 8 cost 6 % of the 8-registration step) does not.  RTR_REGISTER_FORK=0 / 1 forces either.
 static int register_begin_impl(rtr_cloud* model, rtr_cloud* scene, const rtr_register_params* p, bool want_fork) {
+    RtrRange nvtx_range("rtr.register");
     if (!model || !scene || !p || model->ctx != scene->ctx) return rtr_fail("register", "bad argument", RTR_ERR_INVALID);
     if (int e = rtr_validate_register_params(p)) return e;
     rtr_context* ctx = model->ctx;

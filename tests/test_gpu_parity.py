@@ -599,6 +599,16 @@ def test_match_tensor_core_equals_exact_kernel_at_scale(api, gpu_ctx, clouds, mo
     monkeypatch.delenv("RTR_MATCH_CLUSTER")
     assert tc["redo_rows"] < 0.2 * len(fa)
     assert 0 < tc["observed_err_over_norms"] < 6e-6          # the error model's constant (match_tc.cu) has head-room
+    # the exact redo of uncertified rows (16 CTAs per row, k_match_rows_split; rows beyond its 16384-row capacity in k_match):
+    # every row forced through it must still give the exact kernel's answer, incl. ties and rows with < k finite targets
+    monkeypatch.setenv("RTR_MATCH_FORCE_REDO", "1")
+    fa2 = np.concatenate([fa, fa[:4000]])
+    fb2 = fb.copy(); fb2[4000] = fb2[17]; fb2[8000] = fb2[17]
+    _, t3 = api.match_raw(gpu_ctx, fa2, fb2, 5)
+    monkeypatch.delenv("RTR_MATCH_FORCE_REDO")
+    monkeypatch.setenv("RTR_MATCH_TC", "0")
+    _, e3 = api.match_raw(gpu_ctx, fa2, fb2, 5)
+    assert t3["redo_rows"] == len(fa2) and np.array_equal(t3["idx"], e3["idx"]) and np.array_equal(t3["dist"], e3["dist"])
 
 
 def test_ransac_million_hypotheses_shard_invariance(api, gpu_ctx, clouds):

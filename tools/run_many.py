@@ -46,6 +46,19 @@ if args.marks:
     for k, v in sorted(pr.items(), key=lambda kv: -kv[1][1]):
         print("  %-22s x%-3d %8.1f us  %5.1f %%" % (k, v[0], 1e3 * v[1], 100 * v[1] / tot))
     print("  serialised %.3f ms" % tot)
+# host-side issue time of the two entry points (begin = everything queued, end = wait + records)
+hosts = [load(m) for m in names]
+scene_h = load("mcloud")
+import torch  # noqa: E402
+pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+hosts_p, scene_p = [pin(h) for h in hosts], pin(scene_h)
+for label, begin, end in (("resident", lambda: api.register_many_begin(models, scene, p), lambda: api.register_many_end(ctx)),
+                          ("host    ", lambda: api.register_many_host_begin(ctx, hosts_p, scene_p, p), lambda: api.register_many_end(ctx))):
+    tb, tt = [], []
+    for _ in range(12):
+        ctx.sync(); t0 = time.perf_counter(); begin(); t1 = time.perf_counter(); end(); t2 = time.perf_counter()
+        tb.append(1e3 * (t1 - t0)); tt.append(1e3 * (t2 - t0))
+    print("%s: begin (enqueue) %.3f ms, begin+end %.3f ms (min of 12)" % (label, min(tb), min(tt)), flush=True)
 rt = ctypes.CDLL("libcudart.so")
 rt.cudaProfilerStart()
 for _ in range(args.steps):
