@@ -584,6 +584,9 @@ def main():
             def run_fpfh():
                 c4.reset(); L.rtr_normals(c4._h, 0.05, None); L.rtr_fpfh(c4._h, 0.08, None)
 
+            def run_normals_f32():
+                c4.reset(); L.rtr_normals_mode(c4._h, 0.05, 1, None)
+
             def best_of(fn, reps):
                 fn(); ms = []
                 for _ in range(reps):
@@ -592,6 +595,8 @@ def main():
                     ms.append(ctx.elapsed_ms(2, 3))
                 return min(ms)
             ms_n, ms_f = best_of(run_normals, 3), best_of(run_fpfh, 2)
+            ms_n32 = best_of(run_normals_f32, 3)
+            ctx.profile_begin(); run_normals_f32(); pr32 = ctx.profile_end()
             k5 = int(c4.radius_neighbors(0.05, counts_only=True)[0].sum())
             cnt8 = c4.radius_neighbors(0.08, counts_only=True)[0]
             k8 = int(cnt8.sum())
@@ -614,6 +619,9 @@ def main():
                          "neighbour_entries_r05": k5, "neighbour_entries_r08": k8,
                          "fpfh_at_100k_ms": round(ctx.elapsed_ms(2, 3), 3), "fpfh_at_neighbour_entries": int(cnt8[qidx].sum()),
                          "roofline_normals": roof("k_normals", "normals", pr["normals"][1], 16 * (n4m + k5) + 16 * n4m),
+                         "normals_pcl_float_ms_incl_grid": round(ms_n32, 3),
+                         "roofline_normals_pcl_float": roof("k_normals_pcl_float (rtr_normals_mode 1: PCL's own float arithmetic)", "normals.pcl_float",
+                                                            pr32["normals.pcl_float"][1], 16 * (n4m + k5) + 16 * n4m),
                          "roofline_spfh": roof("k_spfh", "fpfh.spfh", pr["fpfh.spfh"][1], 16 * (n4m + k8) + 16 * k8 + 132 * n4m),
                          "roofline_fpfh_weight": roof("k_fpfh_weight_tiled", "fpfh.weight", pr["fpfh.weight"][1], 16 * (n4m + k8) + 132 * k8 + 132 * n4m)}
             # matching: 262 144 scene features x 65 536 model features, real FPFH rows of this scene

@@ -192,6 +192,14 @@ int rtr_nearest(rtr_cloud* target, const float* host_queries_xyz1, int nq, int* 
 /* pcl::NormalEstimation (run implicitly by HarrisKeypoint3D, model_point.h:127-136; App. A.2).
  * host_normals4 (optional): n x {nx, ny, nz, curvature}. */
 int rtr_normals(rtr_cloud* c, float radius, float* host_normals4);
+/* The same stage with the arithmetic selectable:
+ *   mode 0  exact — fp64 sums of the offsets from the query point, cyclic Jacobi; what rtr_normals and rtr_register run and
+ *           what every parity test is pinned to (GPU == oracle mode 0 bit for bit);
+ *   mode 1  PCL-float-faithful — what pcl::NormalEstimation::computePointNormal itself does (App. A.2): nine single-pass FLOAT
+ *           accumulators over the raw coordinates (no de-meaning), pcl::eigen33's closed-form roots in float.  Agrees with the
+ *           oracle's mode 1 to float summation order (tolerance parity), runs off the fp64 pipe.
+ * The normals cached on the cloud are those of the last call; later stages (Harris, FPFH) use whatever is cached. */
+int rtr_normals_mode(rtr_cloud* c, float radius, int mode, float* host_normals4);
 
 /* pcl::HarrisKeypoint3D<PointXYZ,PointXYZI,Normal>::compute — ModelPoint::getKeypoint (model_point.h:99-156),
  * ScanPoint::getKeypoint (scan_point.h:57-113).  Needs rtr_normals first (same radius in the reference).

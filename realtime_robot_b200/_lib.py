@@ -22,7 +22,7 @@ EXPORTS = [
     "rtr_cloud_save", "rtr_register_begin", "rtr_register_host_begin", "rtr_register_end", "rtr_context_create_prio",
     "rtr_register_many", "rtr_register_many_host", "rtr_register_many_begin", "rtr_register_many_host_begin", "rtr_register_many_end",
     "rtr_register_many_keypoints", "rtr_comm_unique_id", "rtr_comm_init", "rtr_comm_destroy", "rtr_comm_world", "rtr_allgather_results",
-    "rtr_select_best_hypothesis",
+    "rtr_select_best_hypothesis", "rtr_normals_mode",
 ]
 
 
@@ -62,6 +62,7 @@ def lib():
         L.rtr_radius_neighbors.argtypes = [vp, C.c_float, vp, vp, vp, ll, C.POINTER(ll)]
         L.rtr_nearest.argtypes = [vp, vp, C.c_int, vp, vp]
         L.rtr_normals.argtypes = [vp, C.c_float, vp]
+        L.rtr_normals_mode.argtypes = [vp, C.c_float, C.c_int, vp]
         L.rtr_harris3d.argtypes = [vp, C.c_float, C.c_float, C.c_int, C.c_int, vp, vp, vp, C.c_int, ip]
         L.rtr_fpfh.argtypes = [vp, C.c_float, vp]
         L.rtr_fpfh_at.argtypes = [vp, C.c_float, vp, C.c_int, vp]

@@ -191,9 +191,13 @@ class Cloud:
         _lib.check("rtr_nearest", _lib.lib().rtr_nearest(self._h, _ptr(q), len(q), _ptr(idx), _ptr(d2)))
         return idx, d2
 
-    def normals(self, radius: float) -> np.ndarray:
+    def normals(self, radius: float, mode: int = 0) -> np.ndarray:
+        """pcl::NormalEstimation; mode 0: exact (fp64, the parity mode), mode 1: PCL-float-faithful (rtr_normals_mode)."""
         out = np.zeros((self.n, 4), dtype=np.float32)
-        _lib.check("rtr_normals", _lib.lib().rtr_normals(self._h, radius, _ptr(out)))
+        if mode == 0:
+            _lib.check("rtr_normals", _lib.lib().rtr_normals(self._h, radius, _ptr(out)))
+        else:
+            _lib.check("rtr_normals_mode", _lib.lib().rtr_normals_mode(self._h, radius, mode, _ptr(out)))
         return out
 
     def harris3d(self, radius: float, threshold: float, nms: int = 1, refine: int = 1):

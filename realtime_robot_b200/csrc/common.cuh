@@ -159,7 +159,7 @@ struct rtr_cloud {
     float bb_min[3] = {0, 0, 0}, bb_max[3] = {0, 0, 0};
     bool bbox_valid = false;
     std::map<int, DevGrid> grids;             // keyed by float bits of the requested cell size
-    float4* normals = nullptr;   float normals_radius = -1.f;  int normals_version = 0;
+    float4* normals = nullptr;   float normals_radius = -1.f;  int normals_version = 0;  int normals_mode = 0;
     float*  response = nullptr;
     float*  fpfh = nullptr;      float fpfh_radius = -1.f;
     // the k-NN correspondences name their target by identity: the handle plus the generation of its features at that time
@@ -279,6 +279,7 @@ int  rtr_ensure_bbox(rtr_cloud* c);
 void rtr_invalidate(rtr_cloud* c);
 float rtr_icp_cell(const rtr_cloud* c);
 int  rtr_normals_dev(rtr_cloud* c, float radius);
+int  rtr_normals_mode_dev(rtr_cloud* c, float radius, int mode);
 int  rtr_harris_dev(rtr_cloud* c, float radius, float threshold, int nms, int refine, int** d_kp_idx, float4** d_kp_xyz,
                     int** d_count);
 int  rtr_fpfh_dev(rtr_cloud* c, float radius);

@@ -137,6 +137,102 @@ __global__ void __launch_bounds__(128) k_normals_solve(const float4* __restrict_
                                                     sums[5 * t + s], sums[6 * t + s], sums[7 * t + s], sums[8 * t + s]);
 }
 
+// ---- PCL-float-faithful normals (mode 1) ------------------------------------------------
+// What pcl::NormalEstimation itself does: nine SINGLE-PASS float accumulators over the raw coordinates (sum xx, xy, xz, yy,
+// yz, zz, x, y, z — no de-meaning pass, so cancellation grows with the distance from the origin), C = E[pp^T] - mu mu^T,
+// smallest eigenpair by pcl::eigen33's closed-form trigonometric roots in float.  Closer to the reference than the exact
+// mode (fp64 sums of offsets + Jacobi) and off the fp64 pipe, which bounds k_normals at 58 % (ncu, 4 M points).  One thread
+// per point in cell order; each thread adds its neighbours in the grid's candidate order, so the result is run-to-run
+// reproducible.  It differs from the oracle's mode 1 by float summation order (the oracle adds in ascending index) and by
+// the device's atan2f / sincosf — parity is by tolerance (tests/test_gpu_parity.py::test_normals_pcl_float_mode).
+__device__ __forceinline__ void pcl_eigen33_smallest_dev(const float* cov, float& eval, float* evec) {
+    float scale = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) scale = fmaxf(scale, fabsf(cov[i]));
+    if (scale <= FLT_MIN) scale = 1.0f;
+    float m[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) m[i] = cov[i] / scale;
+    const float c0 = m[0] * m[4] * m[8] + 2.f * m[1] * m[2] * m[5] - m[0] * m[5] * m[5] - m[4] * m[2] * m[2] - m[8] * m[1] * m[1];
+    const float c1 = m[0] * m[4] - m[1] * m[1] + m[0] * m[8] - m[2] * m[2] + m[4] * m[8] - m[5] * m[5];
+    const float c2 = m[0] + m[4] + m[8];
+    float r0, r1, r2;
+    auto quad = [&](float b, float c) {        // roots of x^2 - b x + c, with root 0 = 0
+        r0 = 0.f;
+        float d = b * b - 4.f * c; if (d < 0.f) d = 0.f;
+        const float sd = sqrtf(d);
+        r2 = 0.5f * (b + sd); r1 = 0.5f * (b - sd);
+    };
+    if (fabsf(c0) < FLT_EPSILON) quad(c2, c1);
+    else {
+        const float s_inv3 = 1.0f / 3.0f, s_sqrt3 = sqrtf(3.0f);
+        const float c2_over_3 = c2 * s_inv3;
+        float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3; if (a_over_3 > 0.f) a_over_3 = 0.f;
+        const float half_b = 0.5f * (c0 + c2_over_3 * (2.f * c2_over_3 * c2_over_3 - c1));
+        float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3; if (q > 0.f) q = 0.f;
+        const float rho = sqrtf(-a_over_3);
+        const float theta = atan2f(sqrtf(-q), half_b) * s_inv3;
+        float st, ct;
+        sincosf(theta, &st, &ct);
+        r0 = c2_over_3 + 2.f * rho * ct;
+        r1 = c2_over_3 - rho * (ct + s_sqrt3 * st);
+        r2 = c2_over_3 - rho * (ct - s_sqrt3 * st);
+        float t;
+        if (r0 >= r1) { t = r0; r0 = r1; r1 = t; }
+        if (r1 >= r2) { t = r1; r1 = r2; r2 = t; if (r0 >= r1) { t = r0; r0 = r1; r1 = t; } }
+        if (r0 <= 0.f) quad(c2, c1);
+    }
+    eval = r0 * scale;
+    const float d0 = m[0] - r0, d1 = m[4] - r0, d2 = m[8] - r0;
+    // rows of (C / scale - lambda I): (d0, m1, m2), (m1, d1, m5), (m2, m5, d2); the largest of the three cross products
+    const float v0x = m[1] * m[5] - m[2] * d1, v0y = m[2] * m[1] - d0 * m[5], v0z = d0 * d1 - m[1] * m[1];
+    const float v1x = m[1] * d2 - m[2] * m[5], v1y = m[2] * m[2] - d0 * d2, v1z = d0 * m[5] - m[1] * m[2];
+    const float v2x = d1 * d2 - m[5] * m[5], v2y = m[5] * m[2] - m[1] * d2, v2z = m[1] * m[5] - d1 * m[2];
+    const float l0 = v0x * v0x + v0y * v0y + v0z * v0z, l1 = v1x * v1x + v1y * v1y + v1z * v1z, l2 = v2x * v2x + v2y * v2y + v2z * v2z;
+    float vx, vy, vz, l;
+    if (l0 >= l1 && l0 >= l2) { vx = v0x; vy = v0y; vz = v0z; l = l0; }
+    else if (l1 >= l0 && l1 >= l2) { vx = v1x; vy = v1y; vz = v1z; l = l1; }
+    else { vx = v2x; vy = v2y; vz = v2z; l = l2; }
+    const float inv = 1.0f / sqrtf(l);
+    evec[0] = vx * inv; evec[1] = vy * inv; evec[2] = vz * inv;
+}
+
+template <class GS>
+__global__ void __launch_bounds__(128) k_normals_pcl_float(const __grid_constant__ GS gs, float r2, float4* __restrict__ normals) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= gs.total()) return;
+    const GridView g = gs.at(s);
+    const float4 q = __ldg(g.sorted + s);
+    float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;
+    int cnt = 0;
+    for_block27(g, q.x, q.y, q.z, [&](int, float4 p, float d2) {
+        if (d2 < r2) {
+            a0 += p.x * p.x; a1 += p.x * p.y; a2 += p.x * p.z; a3 += p.y * p.y; a4 += p.y * p.z; a5 += p.z * p.z;
+            a6 += p.x; a7 += p.y; a8 += p.z;
+            ++cnt;
+        }
+    });
+    float4 o;
+    if (cnt < 3) o.x = o.y = o.z = o.w = __int_as_float(0x7fc00000);
+    else {
+        const float k = (float)cnt;
+        a0 /= k; a1 /= k; a2 /= k; a3 /= k; a4 /= k; a5 /= k; a6 /= k; a7 /= k; a8 /= k;
+        float cov[9];
+        cov[0] = a0 - a6 * a6; cov[1] = a1 - a6 * a7; cov[2] = a2 - a6 * a8;
+        cov[4] = a3 - a7 * a7; cov[5] = a4 - a7 * a8; cov[8] = a5 - a8 * a8;
+        cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+        float ev, e[3];
+        pcl_eigen33_smallest_dev(cov, ev, e);
+        const float tr = cov[0] + cov[4] + cov[8];
+        const double curv = (tr != 0.f) ? fabs((double)(ev / tr)) : 0.0;
+        double nx = e[0], ny = e[1], nz = e[2];
+        const double dot = (nx * -(double)q.x + ny * -(double)q.y) + nz * -(double)q.z;     // flipNormalTowardsViewpoint, vp = 0
+        if (dot < 0) { nx = -nx; ny = -ny; nz = -nz; }
+        o.x = (float)nx; o.y = (float)ny; o.z = (float)nz; o.w = (float)curv;
+    }
+    normals[__float_as_int(q.w)] = o;
+}
+
 // ----------------------------------------------------------------------------- Harris 3D (App. A.3)
 __device__ __forceinline__ float harris_from_sums(int cnt, double c0, double c1, double c2, double c3, double c4, double c5);
 __global__ void __launch_bounds__(128) k_harris_response(GridView g, const float4* __restrict__ sn, float r2,
@@ -1071,10 +1167,26 @@ int rtr_match_features_dev(rtr_context* ctx, const float* fa, int na, const floa
 }
 
 // ----------------------------------------------------------------------------- host drivers
-int rtr_normals_dev(rtr_cloud* c, float radius) {
+int rtr_normals_dev(rtr_cloud* c, float radius) { return rtr_normals_mode_dev(c, radius, 0); }
+
+// mode 0: exact (fp64 sums of offsets, Jacobi) — the parity mode every downstream test is pinned to; mode 1: PCL-float-faithful
+int rtr_normals_mode_dev(rtr_cloud* c, float radius, int mode) {
     RtrRange nvtx_range("rtr.normals");
     rtr_context* ctx = c->ctx;
-    if (c->normals && c->normals_radius == radius) return 0;
+    if (c->normals && c->normals_radius == radius && c->normals_mode == mode) return 0;
+    if (mode == 1) {
+        DevGrid* g1;
+        if (int e = rtr_get_grid(c, radius, &g1)) return e;
+        if (!c->normals) if (int e = dev_alloc(ctx, &c->normals, c->n, "normals")) return e;
+        if (c->n > 0) {
+            if (c->nseg() > 0) k_normals_pcl_float<ManyGrids><<<nblk(c->n, 128), 128, 0, ctx->stream>>>(rtr_many(g1, c), radius * radius, c->normals);
+            else k_normals_pcl_float<OneGrid><<<nblk(c->n, 128), 128, 0, ctx->stream>>>(rtr_one(g1), radius * radius, c->normals);
+            RTR_LAUNCH_CHECK(ctx, "normals.pcl_float");
+        }
+        c->normals_radius = radius; c->normals_mode = 1;
+        c->normals_version++;
+        return 0;
+    }
     DevGrid* g;
     if (int e = rtr_get_grid(c, radius, &g)) return e;
     if (!c->normals) if (int e = dev_alloc(ctx, &c->normals, c->n, "normals")) return e;
@@ -1095,7 +1207,7 @@ int rtr_normals_dev(rtr_cloud* c, float radius) {
             RTR_LAUNCH_CHECK(ctx, "normals");
         }
     }
-    c->normals_radius = radius;
+    c->normals_radius = radius; c->normals_mode = 0;
     c->normals_version++;
     return 0;
 }
@@ -1313,6 +1425,16 @@ int rtr_normals(rtr_cloud* c, float radius, float* host_normals4) {
     TmpScope tmp_scope(c->ctx);
     RTR_CHECK(cudaSetDevice(c->ctx->device), "normals");
     if (int e = rtr_normals_dev(c, radius)) return e;
+    if (host_normals4 && c->n > 0) RTR_CHECK(cudaMemcpyAsync(host_normals4, c->normals, (size_t)c->n * 16, cudaMemcpyDeviceToHost, c->ctx->stream), "normals");
+    RTR_CHECK(cudaStreamSynchronize(c->ctx->stream), "normals");
+    return 0;
+}
+
+int rtr_normals_mode(rtr_cloud* c, float radius, int mode, float* host_normals4) {
+    if (!c || !(radius > 0.f) || (mode != 0 && mode != 1)) return rtr_fail("normals", "bad argument (mode 0: exact, 1: PCL-float)", RTR_ERR_INVALID);
+    TmpScope tmp_scope(c->ctx);
+    RTR_CHECK(cudaSetDevice(c->ctx->device), "normals");
+    if (int e = rtr_normals_mode_dev(c, radius, mode)) return e;
     if (host_normals4 && c->n > 0) RTR_CHECK(cudaMemcpyAsync(host_normals4, c->normals, (size_t)c->n * 16, cudaMemcpyDeviceToHost, c->ctx->stream), "normals");
     RTR_CHECK(cudaStreamSynchronize(c->ctx->stream), "normals");
     return 0;
