@@ -288,6 +288,7 @@ int  rtr_ransac_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_ransac_params* p, 
 int  rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const float* d_init_pose16, int init_from_result,
                  rtr_pose_result* d_result);
 int  rtr_validate_register_params(const rtr_register_params* p);
+int  rtr_nearest_bvh_dev(rtr_cloud* tgt, const float4* d_q, int nq, int* d_idx, float* d_d2);
 // model sets: member clouds (device handles / host buffers) concatenated into one segmented rtr_cloud; free with rtr_cloud_free
 int  rtr_model_set_from_clouds(rtr_context* ctx, rtr_cloud* const* members, int nseg, rtr_cloud** out);
 int  rtr_model_set_from_host(rtr_context* ctx, const float* const* host_xyz1, const int* ns, int nseg, rtr_cloud** out);

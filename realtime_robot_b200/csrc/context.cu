@@ -974,8 +974,14 @@ int rtr_nearest(rtr_cloud* target, const float* host_queries_xyz1, int nq, int* 
     if (int e = dev_alloc(ctx, &d_idx, nq, "nearest")) return e;
     if (int e = dev_alloc(ctx, &d_d2, nq, "nearest")) return e;
     RTR_CHECK(cudaMemcpyAsync(d_q, host_queries_xyz1, (size_t)nq * 16, cudaMemcpyHostToDevice, ctx->stream), "nearest");
-    k_nearest<<<nblk(nq, 128), 128, 0, ctx->stream>>>(rtr_view(g), d_q, nq, d_idx, d_d2);
-    RTR_LAUNCH_CHECK(ctx, "nearest");
+    const char* use_bvh = getenv("RTR_NEAREST_BVH");       // tests: answer from the small-target hierarchy of the ICP kernels (bvh.cuh)
+    if (use_bvh && use_bvh[0] == '1' && target->n <= 4096) {
+        TmpScope tmp_scope(ctx);
+        if (int e = rtr_nearest_bvh_dev(target, d_q, nq, d_idx, d_d2)) return e;
+    } else {
+        k_nearest<<<nblk(nq, 128), 128, 0, ctx->stream>>>(rtr_view(g), d_q, nq, d_idx, d_d2);
+        RTR_LAUNCH_CHECK(ctx, "nearest");
+    }
     RTR_CHECK(cudaMemcpyAsync(host_idx, d_idx, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream), "nearest");
     RTR_CHECK(cudaMemcpyAsync(host_d2, d_d2, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream), "nearest");
     RTR_CHECK(cudaStreamSynchronize(ctx->stream), "nearest");

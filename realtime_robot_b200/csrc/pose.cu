@@ -15,6 +15,7 @@
 //           partials in a fixed shape, solves (Horn / 6x6 elimination) and runs the convergence tests.  Iterations are
 //           chained with programmatic dependent launch.
 #include "common.cuh"
+#include "bvh.cuh"
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <cmath>
@@ -686,7 +687,8 @@ __device__ void icp_solve_thread0(const double* sums, IcpState* st, const IcpSol
 // called by every thread of a CTA (256 threads) after its partials are written
 template <int EST>
 __device__ void icp_last_cta_solve(const double* partials, IcpState* st, unsigned* ticket, const IcpSolveArgs& sa, double* sums /* smem[N] */,
-                                   int* is_last /* smem */, const int nparts /* CTAs that share this ticket */) {
+                                   int* is_last /* smem */, const int nparts /* CTAs that share this ticket */,
+                                   unsigned* publish = nullptr, unsigned publish_value = 0u /* persistent kernel: iteration counter */) {
     constexpr int N = IcpSums<EST>::N;
     constexpr int G = 255 / N;          // row groups: 15 for 17 sums, 8 for 29
     __threadfence();
@@ -738,6 +740,7 @@ __device__ void icp_last_cta_solve(const double* partials, IcpState* st, unsigne
     if (threadIdx.x == 0) {
         *ticket = 0u;
         icp_solve_thread0<EST>(sums, st, sa);
+        if (publish) { __threadfence(); atomicExch(publish, publish_value); }      // state, step and ticket are visible before the counter moves
     }
 }
 
@@ -826,11 +829,12 @@ struct IcpTarget {
     int brute_n;
     const float4* pts;                // target points by original index (the index .w / the search returns)
     const float4* normals;            // target normals by original index (estimator 1)
+    WbvhView bvh;                     // small targets: two-level 32-wide hierarchy for the warp-per-query kernels (bvh.n == 0: plain scan)
 };
 template <int EST>
 __device__ __forceinline__ void icp_corr_warp_body(const IcpTarget& T, float4* __restrict__ cur, int* __restrict__ nn_prev, int n, IcpState* st,
                                                    double dmax2, float prune2, double* partials, unsigned* ticket, const IcpSolveArgs& sa,
-                                                   const int bid, const int nblocks) {
+                                                   const int bid, const int nblocks, unsigned* publish = nullptr, unsigned publish_value = 0u) {
     constexpr int N = IcpSums<EST>::N;
     __shared__ float m[16];
     __shared__ double red[ICPW_WARPS][N];      // lane 0 of every warp accumulates its queries here, in query order
@@ -853,7 +857,29 @@ __device__ __forceinline__ void icp_corr_warp_body(const IcpTarget& T, float4* _
         }
     };
     const bool warm = have && nn_prev != nullptr;
-    if (T.brute_n > 0) {
+    if (T.bvh.n > 0) {
+        // small target: two-level 32-wide hierarchy (bvh.cuh), started from the query's previous neighbour.  Same warp -> query
+        // assignment and accumulation order as the plain scan below (i, i + nwarps, i + 2 nwarps, ...): same sums, same bits.
+        for (int i = bid * ICPW_WARPS + warp; i < n; i += nwarps) {
+            float4 q = cur[i];
+            if (have) { q = xform(m, q); if (lane == 0) cur[i] = q; }
+            unsigned long long key = ~0ull;
+            if (warm) {
+                const int pb = nn_prev[i];
+                if (pb >= 0) {
+                    const float4 tp = __ldg(tgt_pts + pb);
+                    key = ((unsigned long long)__float_as_uint(dist2f(q.x, q.y, q.z, tp.x, tp.y, tp.z)) << 32) | (unsigned)pb;
+                }
+            }
+            key = wbvh_nearest_warp(T.bvh, q.x, q.y, q.z, lane, key);
+            const unsigned h = (unsigned)(key >> 32);
+            const int b = h <= 0x7f800000u ? (int)(unsigned)key : -1;
+            if (lane == 0) {
+                if (nn_prev) nn_prev[i] = b;
+                if (b >= 0) add(q, b, __uint_as_float(h), __ldg(tgt_pts + b));
+            }
+        }
+    } else if (T.brute_n > 0) {
         GridView gb = T.g;
         gb.sorted = T.brute; gb.n = T.brute_n;
         // two of this warp's queries per pass (i, i + nwarps): same warp -> query assignment and accumulation order as below
@@ -898,7 +924,7 @@ __device__ __forceinline__ void icp_corr_warp_body(const IcpTarget& T, float4* _
         for (int w = 0; w < ICPW_WARPS; ++w) v += red[w][threadIdx.x];
         partials[(size_t)bid * N + threadIdx.x] = v;
     }
-    icp_last_cta_solve<EST>(partials, st, ticket, sa, sums, &is_last, nblocks);
+    icp_last_cta_solve<EST>(partials, st, ticket, sa, sums, &is_last, nblocks, publish, publish_value);
 }
 
 template <int EST>
@@ -996,7 +1022,22 @@ __device__ __forceinline__ void icp_fitness_warp_body(const IcpTarget& T, const 
     double s = 0, c = 0;
     // valid once at least one iteration has stored every query's neighbour
     const bool warm = nn_prev != nullptr && st->iterations > 0;
-    if (T.brute_n > 0) {
+    if (T.bvh.n > 0) {
+        for (int i = bid * ICPW_WARPS + warp; i < n; i += nwarps) {
+            const float4 q = xform(m, __ldg(src + i));
+            unsigned long long key = ~0ull;
+            if (warm) {
+                const int pb = nn_prev[i];
+                if (pb >= 0) {
+                    const float4 tp = __ldg(T.pts + pb);
+                    key = ((unsigned long long)__float_as_uint(dist2f(q.x, q.y, q.z, tp.x, tp.y, tp.z)) << 32) | (unsigned)pb;
+                }
+            }
+            key = wbvh_nearest_warp(T.bvh, q.x, q.y, q.z, lane, key);
+            const unsigned h = (unsigned)(key >> 32);
+            if (lane == 0 && h <= 0x7f800000u) { s += (double)__uint_as_float(h); c += 1.0; }
+        }
+    } else if (T.brute_n > 0) {
         GridView gb = T.g;
         gb.sorted = T.brute; gb.n = T.brute_n;
         for (int i = bid * ICPW_WARPS + warp; i < n; i += 2 * nwarps) {
@@ -1055,6 +1096,94 @@ __global__ void __launch_bounds__(ICPW_WARPS * 32) k_icp_fitness_warp_many(const
                           partials_all + (size_t)b0 * ICP_NSUM_MAX, ticket_all + k, res_all + k, 1, (int)blockIdx.x - b0, im.cta_begin[k + 1] - b0);
 }
 
+// ---- all iterations of every member cloud in ONE launch ----------------------------------------------------------------------
+// With the hierarchy the search is a few hundred instructions per query, and an iteration launched on its own is bound by
+// everything around it: ~6000 CTAs (10 waves of 4 per SM) that mostly do one or two queries each, the launch itself, the
+// tail until the last CTA has solved (ncu / marks: 52 us per iteration for the bench batch, of which the searches need < 10).
+// The persistent form keeps the same VIRTUAL CTAs — the same queries per warp, the same partial sums, the same fixed-shape
+// fold by the member's last virtual CTA, hence the same bits — but runs them on a resident grid (cooperative launch: every
+// CTA is on an SM, so waiting for another CTA cannot deadlock), iteration after iteration.  A member's next iteration starts
+// as soon as ITS solve has been published (a per-member counter written behind a fence), independent of the other members;
+// the fitness pass of a member follows its last iteration the same way.
+__device__ __forceinline__ void icp_wait_member(const unsigned* gen, const IcpState* st, unsigned need) {
+    if (threadIdx.x == 0) {
+        const volatile unsigned* g = gen;
+        const volatile int* done = &st->done;
+        for (long long spin = 0; *g < need && !*done; ++spin) {
+            if (spin > (1LL << 26)) __trap();          // a protocol bug must end in an error status, never in a hung GPU
+            __nanosleep(40);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+template <int EST>
+__global__ void __launch_bounds__(ICPW_WARPS * 32, 4) k_icp_persistent(const __grid_constant__ IcpMany im, IcpTarget T, const float4* __restrict__ src_all,
+                                                                    float4* __restrict__ cur_all, int* __restrict__ nn_prev_all, IcpState* st_all,
+                                                                    double dmax2, float prune2, double* partials_all, unsigned* ticket_all,
+                                                                    unsigned* gen_all, IcpSolveArgs sa, int iterations, rtr_pose_result* res_all,
+                                                                    int keep_ransac_fields) {
+    const int total = im.cta_begin[RTR_MAX_SEGMENTS];
+    for (int it = 0; it < iterations; ++it)
+        for (int vb = blockIdx.x; vb < total; vb += gridDim.x) {
+            const int k = icp_many_segment(im, vb);
+            const int b0 = im.cta_begin[k], p0 = im.pt_begin[k];
+            __syncthreads();                                                   // shared memory of the previous virtual CTA is free
+            if (it > 0) icp_wait_member(gen_all + k, st_all + k, (unsigned)it);
+            icp_corr_warp_body<EST>(T, cur_all + p0, nn_prev_all + p0, im.pt_begin[k + 1] - p0, st_all + k, dmax2, prune2,
+                                    partials_all + (size_t)b0 * ICP_NSUM_MAX, ticket_all + k, sa, vb - b0, im.cta_begin[k + 1] - b0,
+                                    gen_all + k, (unsigned)(it + 1));
+        }
+    for (int vb = blockIdx.x; vb < total; vb += gridDim.x) {
+        const int k = icp_many_segment(im, vb);
+        const int b0 = im.cta_begin[k], p0 = im.pt_begin[k];
+        __syncthreads();
+        if (iterations > 0) icp_wait_member(gen_all + k, st_all + k, (unsigned)iterations);
+        icp_fitness_warp_body(T, src_all + p0, cur_all + p0, nn_prev_all + p0, im.pt_begin[k + 1] - p0, st_all + k,
+                              partials_all + (size_t)b0 * ICP_NSUM_MAX, ticket_all + k, res_all + k, keep_ransac_fields, vb - b0, im.cta_begin[k + 1] - b0);
+    }
+}
+
+// Build the two-level hierarchy of a small target (one launch, one CTA).  pts: the target's points by local index; idx_base:
+// added to the reported indices.
+static int wbvh_build_dev(rtr_context* ctx, const float4* pts, int n, int idx_base, const float* bb_min, const float* bb_max, WbvhView* out) {
+    out->n = 0; out->nleaf = 0; out->boxes = nullptr; out->pts = nullptr;
+    if (n <= 0 || n > WBVH_MAX_POINTS) return 0;
+    const int nleaf = (n + WBVH_LEAF - 1) / WBVH_LEAF;
+    float4 *boxes = nullptr, *mpts = nullptr;
+    if (int e = tmp_alloc(ctx, &boxes, (size_t)2 * nleaf, "icp.bvh")) return e;
+    if (int e = tmp_alloc(ctx, &mpts, n, "icp.bvh")) return e;
+    k_wbvh_build<<<1, WBVH_BUILD_THREADS, 0, ctx->stream>>>(pts, n, idx_base, bb_min[0], bb_min[1], bb_min[2], bb_max[0], bb_max[1], bb_max[2], boxes, mpts);
+    RTR_LAUNCH_CHECK(ctx, "icp.bvh_build");
+    out->boxes = boxes; out->pts = mpts; out->nleaf = nleaf; out->n = n;
+    return 0;
+}
+// the hierarchy on its own (rtr_nearest with RTR_NEAREST_BVH=1: the tests compare it with the oracle's brute-force search)
+__global__ void k_nearest_wbvh(WbvhView B, const float4* __restrict__ q, int nq, int* __restrict__ idx, float* __restrict__ d2) {
+    const int lane = threadIdx.x & 31;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= nq) return;
+    const float4 p = __ldg(q + i);
+    const unsigned long long key = wbvh_nearest_warp(B, p.x, p.y, p.z, lane, ~0ull);
+    const unsigned h = (unsigned)(key >> 32);
+    if (lane == 0) { idx[i] = h <= 0x7f800000u ? (int)(unsigned)key : -1; d2[i] = __uint_as_float(h); }
+}
+int rtr_nearest_bvh_dev(rtr_cloud* tgt, const float4* d_q, int nq, int* d_idx, float* d_d2) {
+    rtr_context* ctx = tgt->ctx;
+    if (int e = rtr_ensure_bbox(tgt)) return e;
+    WbvhView B;
+    if (int e = wbvh_build_dev(ctx, tgt->pts, tgt->n, 0, tgt->bb_min, tgt->bb_max, &B)) return e;
+    if (B.n == 0) return rtr_fail("nearest", "the hierarchy serves clouds of 1..4096 points", RTR_ERR_INVALID);
+    k_nearest_wbvh<<<nblk((long long)nq * 32, 128), 128, 0, ctx->stream>>>(B, d_q, nq, d_idx, d_d2);
+    RTR_LAUNCH_CHECK(ctx, "nearest.bvh");
+    return 0;
+}
+// RTR_ICP_BVH=0: keep the plain brute-force scan for small targets (A/B runs, tests)
+static bool icp_bvh_wanted() {
+    const char* e = getenv("RTR_ICP_BVH");
+    return !(e && e[0] == '0');
+}
+
 // getFitnessScore(): mean squared NN distance of (final o source)
 // Queries farther than sqrt(far2) from the target's bounding box search the COARSE grid gc: the walk beyond the 27-cell
 // block visits every row inside the search sphere, and for a query metres away from a finely gridded target that is all
@@ -1093,6 +1222,36 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_fitness(GridView g, GridVie
         partials[(size_t)blockIdx.x * 2 + threadIdx.x] = v;
     }
     icp_last_cta_finish(partials, st, ticket, res, keep_ransac_fields, sums, &is_last, (int)gridDim.x);
+}
+
+// one cooperative launch for all iterations + the fitness pass (k_icp_persistent).  Built for SURVEY section 7 step 6, exact
+// (bit-identical records, tests/test_gpu_parity.py), and MEASURED SLOWER than one launch per iteration on the bench batch:
+// 715 us against 562 us for the ten iterations + fitness of the 8-model batch.  A resident CTA walks ~10 virtual CTAs per
+// iteration one after the other (each a dependent chain of a few global round trips), where separate launches let the
+// hardware scheduler run the same ~10 waves back to back with programmatic dependent launch hiding the hand-over; the
+// per-member barrier adds its own round trips.  So it is opt-in: RTR_ICP_PERSISTENT=1.
+static bool icp_persistent_wanted() {
+    const char* e = getenv("RTR_ICP_PERSISTENT");
+    return e && e[0] == '1';
+}
+static int icp_persistent_launch(rtr_context* ctx, const IcpMany& im, const IcpTarget& T, const float4* src_all, float4* cur, int* nn_prev, IcpState* st,
+                                 double dmax2, float prune2, double* partials, unsigned* ticket, unsigned* gen, const IcpSolveArgs& sa, int iterations,
+                                 rtr_pose_result* d_results, int keep_ransac_fields, bool plane) {
+    const void* fn = plane ? (const void*)k_icp_persistent<1> : (const void*)k_icp_persistent<0>;
+    int per_sm = 1;
+    if (int e = rtr_func_occupancy(fn, ctx->device, ICPW_WARPS * 32, 0, &per_sm)) return e;
+    const int total = im.cta_begin[RTR_MAX_SEGMENTS];
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)std::max(1, std::min(total, ctx->sm_count * per_sm)));
+    cfg.blockDim = dim3(ICPW_WARPS * 32); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t le = plane ? cudaLaunchKernelEx(&cfg, k_icp_persistent<1>, im, T, src_all, cur, nn_prev, st, dmax2, prune2, partials, ticket, gen, sa, iterations, d_results, keep_ransac_fields)
+                           : cudaLaunchKernelEx(&cfg, k_icp_persistent<0>, im, T, src_all, cur, nn_prev, st, dmax2, prune2, partials, ticket, gen, sa, iterations, d_results, keep_ransac_fields);
+    RTR_CHECK(le, "icp.persistent");
+    return 0;
 }
 
 int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const float* d_init_pose16, int init_from_result,
@@ -1185,9 +1344,27 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     // warp-per-query kernels: the target as they see it, and each query's previous neighbour (warm start of the next search)
     IcpTarget T;
     T.g = v; T.brute = v.sorted; T.brute_n = (tgt->n <= RTR_BRUTE_NN_MAX) ? tgt->n : 0; T.pts = tgt->pts; T.normals = plane ? tgt->normals : nullptr;
+    T.bvh.n = 0; T.bvh.nleaf = 0; T.bvh.boxes = nullptr; T.bvh.pts = nullptr;
     int* nn_prev = nullptr;
     if (warp_per_query) if (int e = tmp_alloc(ctx, &nn_prev, n, "icp")) return e;
+    // small targets (every scan the reference ships): the warp-per-query kernels search a two-level hierarchy of the target
+    if (warp_per_query && tgt->n >= 1 && tgt->n <= WBVH_MAX_POINTS && icp_bvh_wanted())
+        if (int e = wbvh_build_dev(ctx, tgt->pts, tgt->n, 0, tgt->bb_min, tgt->bb_max, &T.bvh)) return e;
     const Box6 bb{tgt->bb_min[0], tgt->bb_min[1], tgt->bb_min[2], tgt->bb_max[0], tgt->bb_max[1], tgt->bb_max[2]};
+    if (warp_per_query && n >= 1 && tgt->n >= 1 && icp_persistent_wanted()) {
+        // all iterations and the fitness pass in one cooperative launch (k_icp_persistent), as a model set of one member
+        IcpMany im;
+        memset(&im, 0, sizeof(im));
+        im.nseg = 1;
+        for (int k = 1; k <= RTR_MAX_SEGMENTS; ++k) { im.pt_begin[k] = n; im.cta_begin[k] = nbw; }
+        unsigned* gen = nullptr;
+        if (int e = tmp_alloc(ctx, &gen, 1, "icp")) return e;
+        RTR_CHECK(cudaMemsetAsync(gen, 0, sizeof(unsigned), ctx->stream), "icp");
+        if (int e = icp_persistent_launch(ctx, im, T, src_pts, cur, nn_prev, st, dmax2, prune2, partials, ticket, gen, sa, p->max_iterations, d_result, init_from_result, plane)) return e;
+        RTR_LAUNCH_CHECK(ctx, "icp.corr");
+        dev_free(ctx, cur); dev_free(ctx, src2); dev_free(ctx, st); dev_free(ctx, partials); dev_free(ctx, ticket); dev_free(ctx, nn_prev); dev_free(ctx, gen);
+        return 0;
+    }
     if (n >= 1 && tgt->n >= 1) {
         for (int it = 0; it < p->max_iterations; ++it) {
             if (warp_per_query) {
@@ -1257,6 +1434,10 @@ static int icp_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const rtr_icp
     IcpTarget T;
     T.g = v; T.brute = v.sorted + t0; T.brute_n = (nt <= RTR_BRUTE_NN_MAX) ? nt : 0;     // the scan's slice of the cell-ordered copy
     T.pts = set->pts; T.normals = (p->estimator == 1) ? set->normals : nullptr;
+    T.bvh.n = 0; T.bvh.nleaf = 0; T.bvh.boxes = nullptr; T.bvh.pts = nullptr;
+    // small scans: the warp-per-query kernels search a two-level hierarchy of the scan (indices reported set-wide: + t0)
+    if (nt >= 1 && nt <= WBVH_MAX_POINTS && icp_bvh_wanted())
+        if (int e = wbvh_build_dev(ctx, set->pts + t0, nt, t0, &set->seg_bb[6 * tgt_seg], &set->seg_bb[6 * tgt_seg + 3], &T.bvh)) return e;
     IcpMany im;
     memset(&im, 0, sizeof(im));
     im.nseg = n_models;
@@ -1264,6 +1445,7 @@ static int icp_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const rtr_icp
     for (int k = 0; k <= RTR_MAX_SEGMENTS; ++k) {
         im.pt_begin[k] = set->seg_begin[std::min(k, n_models)];
         im.cta_begin[k] = ctas;
+        // the CTA count the single-cloud launch of the same kernel would use (rtr_icp_dev): same summation shape, same bits
         if (k < n_models) ctas += std::max(1, std::min(nblk(set->seg_begin[k + 1] - set->seg_begin[k], ICPW_WARPS), ctx->sm_count * 8));
     }
     float4* cur = nullptr; IcpState* st = nullptr; double* partials = nullptr; unsigned* ticket = nullptr; int* nn_prev = nullptr;
@@ -1279,6 +1461,14 @@ static int icp_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const rtr_icp
     float prune2 = FLT_MAX;
     if (p->max_correspondence_distance > 0.f) { prune2 = (float)dmax2; if ((double)prune2 < dmax2) prune2 = nextafterf(prune2, FLT_MAX); }
     const bool plane = p->estimator == 1;
+    if (icp_persistent_wanted() && nt >= 1) {
+        unsigned* gen = nullptr;
+        if (int e = tmp_alloc(ctx, &gen, n_models, "icp")) return e;
+        RTR_CHECK(cudaMemsetAsync(gen, 0, sizeof(unsigned) * (size_t)n_models, ctx->stream), "icp");
+        if (int e = icp_persistent_launch(ctx, im, T, set->pts, cur, nn_prev, st, dmax2, prune2, partials, ticket, gen, sa, p->max_iterations, d_results, 1, plane)) return e;
+        RTR_LAUNCH_CHECK(ctx, "icp.corr");
+        return 0;
+    }
     if (nt >= 1) {
         for (int it = 0; it < p->max_iterations; ++it) {
             if (plane) launch_pdl(k_icp_corr_warp_many<1>, ctas, ICPW_WARPS * 32, 0, ctx->stream, im, T, cur, nn_prev, st, dmax2, prune2, partials, ticket, sa);

@@ -872,3 +872,53 @@ def test_normals_pcl_float_mode(api, gpu_ctx, orc, clouds, name):
     c.reset()
     assert np.array_equal(c.normals(0.05, mode=1), g1, equal_nan=True)
     c.free()
+
+
+@pytest.mark.gpu
+def test_bvh_nearest_is_the_brute_force_answer(api, gpu_ctx, orc, clouds, monkeypatch):
+    """bvh.cuh — the small-target two-level hierarchy of the warp-per-query ICP kernels — against the oracle's exact search: near and
+    far queries, queries ON target points, a lattice full of exact distance ties (ties -> lowest index), duplicates, clouds of
+    1 .. 4096 points (partial leaves, a single leaf), a degenerate flat cloud."""
+    monkeypatch.setenv("RTR_NEAREST_BVH", "1")
+    rng = np.random.default_rng(3)
+    lattice = np.ones((1000, 4), np.float32)
+    lattice[:, :3] = np.stack(np.meshgrid(np.arange(10), np.arange(10), np.arange(10), indexing="ij"), -1).reshape(-1, 3) * np.float32(0.25)
+    lattice = lattice[rng.permutation(1000)]
+    dup = clouds("mcloud").copy(); dup[1500:] = dup[:409]
+    flat = random_cloud(300, 4); flat[:, 2] = 0.5
+    cases = [clouds("mcloud"), clouds("T0_m8111"), lattice, dup, flat, random_cloud(1, 1), random_cloud(3, 2), random_cloud(5, 3), random_cloud(4096, 5, 2.0)]
+    for tgt in cases:
+        c = api.Cloud(gpu_ctx, tgt)
+        lo, hi = tgt[:, :3].min(0), tgt[:, :3].max(0)
+        q = np.ones((3000, 4), np.float32)
+        q[:1000, :3] = (lo + (hi - lo) * rng.random((1000, 3))).astype(np.float32)                       # inside the box
+        q[1000:2000, :3] = (lo - 2.0 + (hi - lo + 4.0) * rng.random((1000, 3))).astype(np.float32)       # far outside
+        q[2000:2500] = tgt[rng.integers(0, len(tgt), 500)]                                               # on target points
+        q[2500:, :3] = (np.round((lo + (hi - lo) * rng.random((500, 3))) * 8) / 8).astype(np.float32)    # ties on the lattice
+        gi, gd = c.nearest(q)
+        oi, od = orc.nearest(tgt, q)
+        assert np.array_equal(gi, oi) and np.array_equal(gd, od), len(tgt)
+        c.free()
+
+
+@pytest.mark.gpu
+def test_icp_bvh_and_brute_force_kernels_give_the_same_records(api, gpu_ctx, clouds):
+    """RTR_ICP_BVH=0 keeps the plain brute-force scan of the target: both searches are exact and the kernels add their
+    correspondences in the same order, so the records agree bit for bit."""
+    import subprocess, sys, json
+    code = ("import sys, json; sys.path.insert(0, %r)\n"
+            "from realtime_robot_b200 import api\n"
+            "from realtime_robot_b200.pcd import read_pcd_xyz, to_xyz1\n"
+            "import os\n"
+            "L = lambda n: to_xyz1(read_pcd_xyz(os.path.join(%r, 'data', 'clouds', n + '.pcd')))\n"
+            "ctx = api.Context(0); p = api.default_register_params(); p.ransac.max_iterations = 20000\n"
+            "rs = api.register_many_host(ctx, [L('chair1'), L('chair2'), L('chair4')], L('mcloud'), p)\n"
+            "one = api.register_host(ctx, L('chair2'), L('mcloud'), p)\n"
+            "print(json.dumps([[r.hypothesis, r.inliers, r.iterations, r.converged, float(r.fitness)] + r.matrix().ravel().tolist() for r in rs + [one]]))\n") % (ROOT, ROOT)
+    outs = []
+    # the hierarchy, the plain scan, and the opt-in persistent kernel (all iterations + fitness in one cooperative launch)
+    for env in ({"RTR_ICP_BVH": "1"}, {"RTR_ICP_BVH": "0"}, {"RTR_ICP_PERSISTENT": "1"}, {"RTR_ICP_PERSISTENT": "1", "RTR_ICP_BVH": "0"}):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, **env), timeout=300)
+        assert r.returncode == 0, r.stderr
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert outs[0] == outs[1] == outs[2] == outs[3]
