@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--no-scene", action="store_true", help="skip the 4M-point scene section (configs[3]: normals + FPFH + matching)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the configs[4] RANSAC sweep section")
     ap.add_argument("--quick", action="store_true", help="headline only: skip every auxiliary section")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s sustained section (runs under a profiler)")
     args = ap.parse_args()
     if args.quick:
         args.no_icp = args.no_native = args.no_scene = args.no_sweep = True
@@ -295,7 +296,7 @@ def main():
         td.all_reduce(t, op=td.ReduceOp.MAX)
         ms_res, ms_e2e = float(t[0]), float(t[1])
     # a sustained section of our own (>= 2 s back to back, no L2 flush): the 100 ms clock sampler sees this one
-    sus_steps = max(50, int(2500.0 / max(ms_res / args.steps, 0.05)))
+    sus_steps = 2 if args.no_sustained else max(50, int(2500.0 / max(ms_res / args.steps, 0.05)))
     ms_sus, _ = timed(step_resident, sus_steps, flush=False)
     barrier()
     clocks = sampler.stop() if sampler else None

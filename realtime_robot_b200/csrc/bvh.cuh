@@ -120,15 +120,24 @@ __device__ __forceinline__ unsigned long long wbvh_nearest_warp(const WbvhView& 
         bnd[r] = inf;
         if (l < B.nleaf) bnd[r] = wbvh_box_d2(__ldg(B.boxes + 2 * l), __ldg(B.boxes + 2 * l + 1), qx, qy, qz);
     }
+    // best so far as two words: d2 bits (their unsigned order is the order of the non-negative distances, NaN bits above
+    // +inf) and the original index; the warp-wide minimum of a leaf is two redux.sync instructions (min of the distance
+    // bits, then min of the indices among the lanes that hold it) instead of a five-step 64-bit shuffle butterfly
+    unsigned kd = (unsigned)(key >> 32), ki = (unsigned)key;
     auto scan_leaf = [&](int l) {
         const int s = l * WBVH_LEAF + lane;
-        unsigned long long c = ~0ull;
+        unsigned db = 0xffffffffu, id = 0xffffffffu;
         if (s < B.n) {
             const float4 p = __ldg(B.pts + s);
-            c = ((unsigned long long)__float_as_uint(dist2f(qx, qy, qz, p.x, p.y, p.z)) << 32) | (unsigned)__float_as_int(p.w);
+            db = __float_as_uint(dist2f(qx, qy, qz, p.x, p.y, p.z));
+            id = (unsigned)__float_as_int(p.w);
         }
-        c = warp_min_u64(c);
-        key = c < key ? c : key;
+        const unsigned mdb = __reduce_min_sync(0xffffffffu, db);
+        if (mdb <= kd) {                       // warp-uniform
+            const unsigned mid = __reduce_min_sync(0xffffffffu, db == mdb ? id : 0xffffffffu);
+            if (mdb < kd || mid < ki) { kd = mdb; ki = mid; }
+        }
+        key = ((unsigned long long)kd << 32) | ki;
     };
     if (key == ~0ull) {
         // no candidate yet: the leaf with the nearest box first (its best point is usually the answer or close to it)

@@ -1224,6 +1224,17 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_fitness(GridView g, GridVie
     icp_last_cta_finish(partials, st, ticket, res, keep_ransac_fields, sums, &is_last, (int)gridDim.x);
 }
 
+// CTAs of the warp-per-query kernels for a source of n points (the same for a cloud on its own and as a member of a model set:
+// it fixes the summation shape).  The plain scan is instruction-bound and wants every warp it can get (one or two queries per
+// warp); with the hierarchy a search is a short chain of dependent loads and an iteration is bound by the number of CTA waves
+// (~6000 CTAs = 10 waves of 4 per SM for the bench batch: 52 us per iteration, of which the searches need < 10), so a warp
+// takes RTR_ICP_QPW queries one after the other and the launch shrinks to two or three waves.
+static int icp_warp_ctas(int n, int sm_count, bool hierarchy) {
+    static const int qpw = []() { const char* e = getenv("RTR_ICP_QPW"); int v = e ? atoi(e) : 4; return v >= 1 && v <= 64 ? v : 4; }();
+    const int per_cta = ICPW_WARPS * (hierarchy ? qpw : 1);
+    return std::max(1, std::min(nblk(n, per_cta), sm_count * 8));
+}
+
 // one cooperative launch for all iterations + the fitness pass (k_icp_persistent).  Built for SURVEY section 7 step 6, exact
 // (bit-identical records, tests/test_gpu_parity.py), and MEASURED SLOWER than one launch per iteration on the bench batch:
 // 715 us against 562 us for the ten iterations + fitness of the 8-model batch.  A resident CTA walks ~10 virtual CTAs per
@@ -1305,7 +1316,8 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     unsigned* ticket = nullptr;
     if (int e = tmp_alloc(ctx, &ticket, 1, "icp")) return e;
     const IcpSolveArgs sa{p->max_iterations, p->force_iterations, p->mse_threshold_absolute};
-    const int nbw = std::max(1, std::min(nblk(n, ICPW_WARPS), ctx->sm_count * 8));    // CTAs of the warp-per-query kernels (2 / 4 / 8 per SM time the same)
+    const bool hierarchy = n < 65536 && tgt->n >= 1 && tgt->n <= WBVH_MAX_POINTS && icp_bvh_wanted();
+    const int nbw = icp_warp_ctas(n, ctx->sm_count, hierarchy);    // CTAs of the warp-per-query kernels
     if (int e = tmp_alloc(ctx, &partials, (size_t)std::max(nb, nbw) * ICP_NSUM_MAX, "icp")) return e;
     k_icp_init<<<nb, ICP_THREADS, 0, ctx->stream>>>(src->pts, n, d_init_pose16, init_from_result ? d_result : nullptr, cur, st, ticket);
     RTR_LAUNCH_CHECK(ctx, "icp.init");
@@ -1446,7 +1458,7 @@ static int icp_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const rtr_icp
         im.pt_begin[k] = set->seg_begin[std::min(k, n_models)];
         im.cta_begin[k] = ctas;
         // the CTA count the single-cloud launch of the same kernel would use (rtr_icp_dev): same summation shape, same bits
-        if (k < n_models) ctas += std::max(1, std::min(nblk(set->seg_begin[k + 1] - set->seg_begin[k], ICPW_WARPS), ctx->sm_count * 8));
+        if (k < n_models) ctas += icp_warp_ctas(set->seg_begin[k + 1] - set->seg_begin[k], ctx->sm_count, T.bvh.n > 0);
     }
     float4* cur = nullptr; IcpState* st = nullptr; double* partials = nullptr; unsigned* ticket = nullptr; int* nn_prev = nullptr;
     if (int e = tmp_alloc(ctx, &cur, n_src, "icp")) return e;
