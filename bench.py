@@ -234,16 +234,27 @@ def main():
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     nm = len(MODELS)
 
-    def gather(recs):
-        for i, r in enumerate(recs):
-            r.model_id = rank * nm + i
-        return dist.allgather_results(ctx, recs, world) if world > 1 else recs
+    # N > 1: every batch ends with the in-stream ncclAllGather of its records (rtr_comm_gather_batches); a step returns the
+    # world x 8 records every rank now holds.  Switched on only around the main loops: the other sections run batches of
+    # different sizes per rank.
+    from realtime_robot_b200.params import PoseResult
+    gathered = (PoseResult * (nm * world))()
 
     def step_resident():
-        return gather(api.register_many(models_d, scene_d, p))
+        recs = api.register_many(models_d, scene_d, p)
+        if world == 1:
+            return recs
+        allr, n_all = dist.gathered_results(ctx, out=gathered)
+        assert n_all == nm * world
+        return allr
 
     def step_e2e():
-        return gather(api.register_many_host(ctx, models_h, scene_h, p))
+        recs = api.register_many_host(ctx, models_h, scene_h, p)
+        if world == 1:
+            return recs
+        allr, n_all = dist.gathered_results(ctx, out=gathered)
+        assert n_all == nm * world
+        return allr
 
     def barrier():
         torch.cuda.synchronize()
@@ -274,6 +285,8 @@ def main():
                 print(f"[bench] step: events {ev:.3f} ms, host wall {wall:.3f} ms", file=sys.stderr, flush=True)
         return total_ms, last
 
+    if world > 1:
+        dist.gather_batches(ctx, True, rank * nm)
     log("warm-up")
     for _ in range(args.warmup):
         t0 = time.perf_counter(); step_resident(); t1 = time.perf_counter(); step_e2e()
@@ -300,6 +313,20 @@ def main():
     ms_sus, _ = timed(step_resident, sus_steps, flush=False)
     barrier()
     clocks = sampler.stop() if sampler else None
+    # the exchange on its own: rtr_allgather_results of 8 host records per rank (H2D + ncclAllGather + D2H + sync), wall clock
+    allgather_us = None
+    if world > 1:
+        mine_now = [PoseResult.from_buffer_copy(bytes(recs[rank * nm + i])) for i in range(nm)]
+        recs_e2e = [PoseResult.from_buffer_copy(bytes(recs_e2e[rank * nm + i])) for i in range(nm)]
+        recs = [PoseResult.from_buffer_copy(bytes(recs[i])) for i in range(nm * world)]
+        dist.gather_batches(ctx, False)
+        for _ in range(5):
+            dist.allgather_results(ctx, mine_now, world)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            dist.allgather_results(ctx, mine_now, world)
+        allgather_us = 1e6 * (time.perf_counter() - t0) / 50
     if world > 1:
         t = torch.tensor([ms_sus], dtype=torch.float64, device=dev)
         td.all_reduce(t, op=td.ReduceOp.MAX)
@@ -451,49 +478,6 @@ def main():
         except Exception as e:
             sweep = {"error": repr(e)}
 
-    # ---- ICP iterations/s @ 1 M points (configs[2]), both directions
-    icp_out = None
-    if not args.no_icp and rank == 0:
-        try:
-            model, scan, gt = synth.icp_config(100_000, 1_000_000)
-            cm, cs = api.Cloud(ctx, model), api.Cloud(ctx, scan)
-            q = default_register_params()
-            q.icp.max_iterations = 50
-            q.icp.force_iterations = 1
-            icp_out = {"workload": "configs[2]: synthetic 100k-point model vs 1M-point scan, 50 forced iterations, grid build included; "
-                                   "model_to_scan is the reference's direction (function.h:113-114) with PCL's unlimited correspondence distance; "
-                                   "scan_to_model (1M source points) is given capped at 0.05 m AND uncapped (PCL default)"}
-            for label, a, b, n_src, cap, its in (("model_to_scan", cm, cs, len(model), 0.0, 50), ("scan_to_model", cs, cm, len(scan), 0.05, 50),
-                                                 ("scan_to_model_uncapped", cs, cm, len(scan), 0.0, 10)):
-                q.icp.max_correspondence_distance = cap
-                q.icp.max_iterations = its
-                for _ in range(2):
-                    a.reset(); b.reset(); api.icp(a, b, q.icp, None)
-                ms, reps = 0.0, 3
-                for _ in range(reps):
-                    a.reset(); b.reset()
-                    flush_buf.fill_(1); torch.cuda.synchronize()
-                    ctx.record(2); res = api.icp(a, b, q.icp, None); ctx.record(3)
-                    ms += ctx.elapsed_ms(2, 3)
-                log(f"icp {label}: {ms / reps:.2f} ms per {its}-iteration ICP")
-                a.reset(); b.reset()
-                ctx.profile_begin(); api.icp(a, b, q.icp, None); pr = ctx.profile_end()
-                k_ms = pr["icp.corr"][1] / pr["icp.corr"][0]
-                ach = n_src * 32 / (k_ms * 1e-3) / 1e9
-                traffic = ncu_traffic.get("icp.corr@" + label)
-                icp_out[label] = {"iters_per_s": its * reps / (ms * 1e-3), "ms_per_icp": ms / reps, "iterations": its, "n_source": n_src,
-                                  "max_correspondence_distance": cap,
-                                  "pose_err_vs_ground_truth": float(np.abs(res.matrix() - (gt if label == "model_to_scan" else np.linalg.inv(gt))).max()),
-                                  "fitness": float(res.fitness),
-                                  "roofline": {"kernel": "icp.corr", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                                               "frac": ach / hbm_peak, "traffic": traffic, "avg_launch_ms": k_ms,
-                                               "frac_on_dram_traffic": (traffic / (k_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None,
-                                               "algorithmic_bytes_per_launch": n_src * 32, "peak_source": peak_src},
-                                  "kernel_ms": {k: round(v[1], 4) for k, v in sorted(pr.items(), key=lambda kv: -kv[1][1])[:6]}}
-            cm.free(); cs.free()
-        except Exception as e:
-            icp_out = {"error": repr(e)}
-
     # ---- the reference's own descriptor path (occupancy / TDF / 36-step yaw sweep / exhaustive consensus)
     native_out, tdf_out = None, None
     if rank == 0 and not args.no_native:
@@ -539,6 +523,8 @@ def main():
             ref = C.CDLL(ref_path)
             ref.ComputeTDFWithCuda.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
             rng = np.random.default_rng(7)
+            # (runs before the sections that allocate 1 M / 4 M-point clouds: the reference wrapper's cudaMalloc / cudaFree per keypoint
+            #  get several times slower in a process that holds large pools — measured 0.6 ms against 6.6 ms per call)
             tdf_out = {"workload": "per-keypoint TDF of 191 occupied voxels in a 30^3 grid (KeyPoint::get_TSDF, key_point.h:251-318): the reference's "
                                    "ComputeTDFWithCuda (2 cudaMalloc, 2 H2D, <<<72,512>>>, cudaDeviceSynchronize, D2H, 2 cudaFree per keypoint, "
                                    "kernel.cu:34-106) called once per keypoint, vs librtr.so's same symbol, vs rtr_tdf_batch (all keypoints, one launch); "
@@ -568,6 +554,49 @@ def main():
                                               "speedup_same_symbol": t_ref / t_leg, "speedup_batched": t_ref / t_bat, "bit_equal": True}
         except Exception as e:
             tdf_out = {"error": repr(e)}
+
+    # ---- ICP iterations/s @ 1 M points (configs[2]), both directions
+    icp_out = None
+    if not args.no_icp and rank == 0:
+        try:
+            model, scan, gt = synth.icp_config(100_000, 1_000_000)
+            cm, cs = api.Cloud(ctx, model), api.Cloud(ctx, scan)
+            q = default_register_params()
+            q.icp.max_iterations = 50
+            q.icp.force_iterations = 1
+            icp_out = {"workload": "configs[2]: synthetic 100k-point model vs 1M-point scan, 50 forced iterations, grid build included; "
+                                   "model_to_scan is the reference's direction (function.h:113-114) with PCL's unlimited correspondence distance; "
+                                   "scan_to_model (1M source points) is given capped at 0.05 m AND uncapped (PCL default)"}
+            for label, a, b, n_src, cap, its in (("model_to_scan", cm, cs, len(model), 0.0, 50), ("scan_to_model", cs, cm, len(scan), 0.05, 50),
+                                                 ("scan_to_model_uncapped", cs, cm, len(scan), 0.0, 10)):
+                q.icp.max_correspondence_distance = cap
+                q.icp.max_iterations = its
+                for _ in range(2):
+                    a.reset(); b.reset(); api.icp(a, b, q.icp, None)
+                ms, reps = 0.0, 3
+                for _ in range(reps):
+                    a.reset(); b.reset()
+                    flush_buf.fill_(1); torch.cuda.synchronize()
+                    ctx.record(2); res = api.icp(a, b, q.icp, None); ctx.record(3)
+                    ms += ctx.elapsed_ms(2, 3)
+                log(f"icp {label}: {ms / reps:.2f} ms per {its}-iteration ICP")
+                a.reset(); b.reset()
+                ctx.profile_begin(); api.icp(a, b, q.icp, None); pr = ctx.profile_end()
+                k_ms = pr["icp.corr"][1] / pr["icp.corr"][0]
+                ach = n_src * 32 / (k_ms * 1e-3) / 1e9
+                traffic = ncu_traffic.get("icp.corr@" + label)
+                icp_out[label] = {"iters_per_s": its * reps / (ms * 1e-3), "ms_per_icp": ms / reps, "iterations": its, "n_source": n_src,
+                                  "max_correspondence_distance": cap,
+                                  "pose_err_vs_ground_truth": float(np.abs(res.matrix() - (gt if label == "model_to_scan" else np.linalg.inv(gt))).max()),
+                                  "fitness": float(res.fitness),
+                                  "roofline": {"kernel": "icp.corr", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                                               "frac": ach / hbm_peak, "traffic": traffic, "avg_launch_ms": k_ms,
+                                               "frac_on_dram_traffic": (traffic / (k_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None,
+                                               "algorithmic_bytes_per_launch": n_src * 32, "peak_source": peak_src},
+                                  "kernel_ms": {k: round(v[1], 4) for k, v in sorted(pr.items(), key=lambda kv: -kv[1][1])[:6]}}
+            cm.free(); cs.free()
+        except Exception as e:
+            icp_out = {"error": repr(e)}
 
     # ---- configs[3]: synthetic 4 M-point scene, normals (r = .05) + FPFH (r = .08) of every point and at 100 000 keypoints,
     #      and brute-force tensor-core matching of 262 144 x 65 536 real FPFH rows.
@@ -713,7 +742,7 @@ def main():
                 "kernel_share": kernel_share, "serialised_device_ms_per_step": round(step_ms, 3),
                 "launches_per_registration": launches / max(n_reg / world, 1),
                 "single_registration_latency_ms": lat, "configs0_chair1_mcloud": cfg0,
-                "strong_scaling": strong, "ransac_sweep": sweep,
+                "strong_scaling": strong, "ransac_sweep": sweep, "allgather_results_us": allgather_us,
                 "icp_1m": icp_out, "scene_4m": scene_out, "matching_262k_x_65k": match_out, "native_path": native_out, "tdf_ab": tdf_out,
                 "pcd_io_1m": pcd_out,
                 "wall_ms_per_step_incl_l2_flush": 1e3 * wall_res / args.steps,

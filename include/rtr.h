@@ -303,6 +303,12 @@ int rtr_comm_world(rtr_context* ctx, int* world, int* rank);
 /* Every rank contributes n_local (<= 64, the same everywhere) records; host_all receives world x n_local in rank order.
  * Without a communicator it is a copy.  Cost: one H2D, one ncclAllGather on the context's stream, one D2H, one sync. */
 int rtr_allgather_results(rtr_context* ctx, const rtr_pose_result* host_local, int n_local, rtr_pose_result* host_all);
+/* In-stream form for batches: after rtr_comm_gather_batches(ctx, 1, base) every rtr_register_many* on this context ends with the
+ * all-gather of its records queued on the stream right behind the batch (no extra host round trip or synchronisation);
+ * model_id of local record k becomes base + k; every rank must run batches of the same size (<= 64 models).
+ * rtr_gathered_results returns the world x n_models records (rank order) after rtr_register_many_end. */
+int rtr_comm_gather_batches(rtr_context* ctx, int on, int model_id_base);
+int rtr_gathered_results(rtr_context* ctx, rtr_pose_result* host_all, int capacity, int* n_records);
 /* Winner of a hypothesis-sharded registration: arg-min over (fitness, hypothesis id) among the accepted shard records —
  * identical on every rank and for every world size; `evaluated` is the sum over shards. */
 int rtr_select_best_hypothesis(const rtr_pose_result* records, int n, rtr_pose_result* best);

@@ -22,7 +22,7 @@ EXPORTS = [
     "rtr_cloud_save", "rtr_register_begin", "rtr_register_host_begin", "rtr_register_end", "rtr_context_create_prio",
     "rtr_register_many", "rtr_register_many_host", "rtr_register_many_begin", "rtr_register_many_host_begin", "rtr_register_many_end",
     "rtr_register_many_keypoints", "rtr_comm_unique_id", "rtr_comm_init", "rtr_comm_destroy", "rtr_comm_world", "rtr_allgather_results",
-    "rtr_select_best_hypothesis", "rtr_normals_mode",
+    "rtr_select_best_hypothesis", "rtr_normals_mode", "rtr_comm_gather_batches", "rtr_gathered_results",
 ]
 
 
@@ -95,6 +95,8 @@ def lib():
         L.rtr_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
         L.rtr_comm_destroy.argtypes = [vp]
         L.rtr_comm_world.argtypes = [vp, ip, ip]
+        L.rtr_comm_gather_batches.argtypes = [vp, C.c_int, C.c_int]
+        L.rtr_gathered_results.argtypes = [vp, C.POINTER(PoseResult), C.c_int, ip]
         L.rtr_allgather_results.argtypes = [vp, C.POINTER(PoseResult), C.c_int, C.POINTER(PoseResult)]
         L.rtr_select_best_hypothesis.argtypes = [C.POINTER(PoseResult), C.c_int, C.POINTER(PoseResult)]
         L.rtr_pcd_info.argtypes = [C.c_char_p, ip, ip]

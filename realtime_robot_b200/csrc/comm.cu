@@ -63,6 +63,18 @@ static int nccl_bind() {
 // records every rank may contribute per gather (device staging: world x this x 128 B)
 #define RTR_COMM_MAX_LOCAL 64
 
+// queue the all-gather of n_local device records on the context's stream (register_many_enqueue); d_local must stay valid
+// until the stream has passed it
+int rtr_comm_allgather_dev(rtr_context* ctx, const rtr_pose_result* d_local, int n_local) {
+    if (!ctx->comm) return 0;
+    if (n_local > RTR_COMM_MAX_LOCAL) return rtr_fail("allgather", "at most 64 records per rank and batch", RTR_ERR_CAPACITY);
+    const size_t lb = sizeof(rtr_pose_result) * (size_t)n_local;
+    RTR_NCCL(g_nccl.AllGather(d_local, ctx->comm_dev, lb, RTR_NCCL_UINT8, (ncclComm_t)ctx->comm, ctx->stream), "allgather");
+    RTR_MARK(ctx, "comm.allgather");
+    RTR_CHECK(cudaMemcpyAsync(ctx->comm_pinned, ctx->comm_dev, lb * (size_t)ctx->comm_world, cudaMemcpyDeviceToHost, ctx->stream), "allgather");
+    return 0;
+}
+
 extern "C" {
 
 int rtr_comm_unique_id(char* id128) {
@@ -130,6 +142,27 @@ int rtr_allgather_results(rtr_context* ctx, const rtr_pose_result* host_local, i
     RTR_CHECK(cudaMemcpyAsync(pin_all, dev_all, ab, cudaMemcpyDeviceToHost, ctx->stream), "allgather");
     RTR_CHECK(cudaStreamSynchronize(ctx->stream), "allgather");
     memcpy(host_all, pin_all, ab);
+    return 0;
+}
+
+// In-stream form for batches: with rtr_comm_gather_batches(ctx, 1, base) every rtr_register_many* on this context ends with the
+// all-gather of its records queued on the context's stream right behind the batch — device buffer to device buffer, then one
+// D2H next to the local records — so the exchange costs no extra host round trip or synchronisation; rtr_gathered_results
+// hands out the world x n_models records after rtr_register_many_end.  model_id of local record k is base + k.  Every rank
+// must run batches of the same size.
+int rtr_comm_gather_batches(rtr_context* ctx, int on, int model_id_base) {
+    if (!ctx) return rtr_fail("comm", "bad argument", RTR_ERR_INVALID);
+    ctx->gather_batches = on ? 1 : 0;
+    ctx->model_id_base = model_id_base;
+    return 0;
+}
+int rtr_gathered_results(rtr_context* ctx, rtr_pose_result* host_all, int capacity, int* n_records) {
+    if (!ctx || !host_all || !n_records) return rtr_fail("comm", "bad argument", RTR_ERR_INVALID);
+    const int n = ctx->gathered_records;
+    *n_records = n;
+    if (n <= 0) return rtr_fail("comm", "no gathered batch on this context (rtr_comm_gather_batches + rtr_register_many_end first)", RTR_ERR_NOT_READY);
+    if (capacity < n) return rtr_fail("comm", "result buffer too small", RTR_ERR_CAPACITY);
+    memcpy(host_all, ctx->comm ? ctx->comm_pinned : ctx->pinned, sizeof(rtr_pose_result) * (size_t)n);
     return 0;
 }
 

@@ -147,6 +147,9 @@ struct rtr_context {
     // multi-GPU (comm.cu): an NCCL communicator on this context's stream + pre-allocated staging for the record all-gather
     void* comm = nullptr; int comm_world = 0, comm_rank = 0;
     void* comm_dev = nullptr; void* comm_pinned = nullptr;
+    int gather_batches = 0;               // rtr_comm_gather_batches: every batch ends with the in-stream all-gather of its records
+    int model_id_base = 0;                // model_id of a batch's record k = base + k
+    int gathered_records = 0;             // records of the last gathered batch (world x n_models; n_models without a communicator)
     // pinned staging of rtr_pcd_load (decoded points, grown on demand)
     void* io_pinned = nullptr;
     size_t io_pinned_cap = 0;
@@ -288,6 +291,7 @@ int  rtr_ransac_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_ransac_params* p, 
 int  rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const float* d_init_pose16, int init_from_result,
                  rtr_pose_result* d_result);
 int  rtr_validate_register_params(const rtr_register_params* p);
+int  rtr_comm_allgather_dev(rtr_context* ctx, const rtr_pose_result* d_local, int n_local);
 int  rtr_nearest_bvh_dev(rtr_cloud* tgt, const float4* d_q, int nq, int* d_idx, float* d_d2);
 // model sets: member clouds (device handles / host buffers) concatenated into one segmented rtr_cloud; free with rtr_cloud_free
 int  rtr_model_set_from_clouds(rtr_context* ctx, rtr_cloud* const* members, int nseg, rtr_cloud** out);

@@ -1527,10 +1527,10 @@ static int fetch_result(rtr_context* ctx, rtr_pose_result* d_result, rtr_pose_re
 struct KpPreview { int count; int pad_[3]; float4 xyz[RTR_KP_PREVIEW]; };
 
 __global__ void k_register_finish_many(const __grid_constant__ IcpMany im, rtr_pose_result* __restrict__ res, const int* __restrict__ kp_count,
-                                       const float4* __restrict__ kp_xyz_all, int n_members, KpPreview* __restrict__ preview) {
+                                       const float4* __restrict__ kp_xyz_all, int n_members, KpPreview* __restrict__ preview, int model_id_base) {
     const int k = blockIdx.x;       // member (models first, the scan last)
     const int n_models = n_members - 1;
-    if (threadIdx.x == 0 && k < n_models) { res[k].n_keypoints_src = kp_count[k]; res[k].n_keypoints_tgt = kp_count[n_models]; }
+    if (threadIdx.x == 0 && k < n_models) { res[k].n_keypoints_src = kp_count[k]; res[k].n_keypoints_tgt = kp_count[n_models]; res[k].model_id = model_id_base + k; }
     const int cnt = kp_count[k];
     if (threadIdx.x == 0) preview[k].count = cnt;
     // corner list of member k starts at its first point index (im.pt_begin covers the models; the scan follows them)
@@ -1590,13 +1590,19 @@ static int register_many_enqueue(rtr_cloud* set, int n_models, const rtr_registe
     im.nseg = n_models;
     for (int kk = 0; kk <= RTR_MAX_SEGMENTS; ++kk) im.pt_begin[kk] = set->seg_begin[std::min(kk, n_models)];
     join_guard.join();
-    k_register_finish_many<<<nseg, 64, 0, ctx->stream>>>(im, d_res, d_cnt, d_xyz, nseg, d_prev);
+    k_register_finish_many<<<nseg, 64, 0, ctx->stream>>>(im, d_res, d_cnt, d_xyz, nseg, d_prev, ctx->gather_batches ? ctx->model_id_base : 0);
     RTR_LAUNCH_CHECK(ctx, "register.kp");
     const size_t res_bytes = sizeof(rtr_pose_result) * (size_t)n_models, prev_bytes = sizeof(KpPreview) * (size_t)nseg;
     if (res_bytes + prev_bytes > ctx->pinned_bytes) return rtr_fail("register_many", "pinned result area too small", RTR_ERR_CAPACITY);
     RTR_CHECK(cudaMemcpyAsync(ctx->pinned, d_res, res_bytes, cudaMemcpyDeviceToHost, ctx->stream), "result");
     RTR_CHECK(cudaMemcpyAsync((char*)ctx->pinned + res_bytes, d_prev, prev_bytes, cudaMemcpyDeviceToHost, ctx->stream), "result");
     RTR_MARK(ctx, "result.d2h");
+    // multi-GPU: the one collective of the path, queued right behind the batch (rtr_comm_gather_batches)
+    ctx->gathered_records = 0;
+    if (ctx->gather_batches) {
+        if (int e = rtr_comm_allgather_dev(ctx, d_res, n_models)) return e;
+        ctx->gathered_records = n_models * (ctx->comm ? ctx->comm_world : 1);
+    }
     return 0;
 }
 

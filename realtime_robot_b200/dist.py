@@ -105,6 +105,23 @@ def allgather_results(ctx, records, world: int = None):
     return [PoseResult.from_buffer_copy(bytes(out[i])) for i in range(n * world)]
 
 
+def gather_batches(ctx, on: bool, model_id_base: int = 0):
+    """Every rtr_register_many* on `ctx` ends with the in-stream ncclAllGather of its records (rtr_comm_gather_batches)."""
+    from . import _lib
+    _lib.check("rtr_comm_gather_batches", _lib.lib().rtr_comm_gather_batches(ctx._h, 1 if on else 0, model_id_base))
+
+
+def gathered_results(ctx, capacity: int = 2048, out=None):
+    """The world x n_models records of the last gathered batch, in rank order (rtr_gathered_results), as a ctypes array of
+    PoseResult (index it like a list; pass `out` to reuse a buffer)."""
+    from . import _lib
+    if out is None:
+        out = (PoseResult * capacity)()
+    n = C.c_int()
+    _lib.check("rtr_gathered_results", _lib.lib().rtr_gathered_results(ctx._h, out, len(out), C.byref(n)))
+    return out, n.value
+
+
 def select_best_hypothesis_native(records):
     """rtr_select_best_hypothesis: the library's own arg-min over (fitness, hypothesis id) — what the C++ host calls."""
     from . import _lib
