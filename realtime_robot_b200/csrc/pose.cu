@@ -1224,15 +1224,21 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_fitness(GridView g, GridVie
     icp_last_cta_finish(partials, st, ticket, res, keep_ransac_fields, sums, &is_last, (int)gridDim.x);
 }
 
-// CTAs of the warp-per-query kernels for a source of n points (the same for a cloud on its own and as a member of a model set:
-// it fixes the summation shape).  The plain scan is instruction-bound and wants every warp it can get (one or two queries per
-// warp); with the hierarchy a search is a short chain of dependent loads and an iteration is bound by the number of CTA waves
-// (~6000 CTAs = 10 waves of 4 per SM for the bench batch: 52 us per iteration, of which the searches need < 10), so a warp
-// takes RTR_ICP_QPW queries one after the other and the launch shrinks to two or three waves.
-static int icp_warp_ctas(int n, int sm_count, bool hierarchy) {
-    static const int qpw = []() { const char* e = getenv("RTR_ICP_QPW"); int v = e ? atoi(e) : 4; return v >= 1 && v <= 64 ? v : 4; }();
-    const int per_cta = ICPW_WARPS * (hierarchy ? qpw : 1);
-    return std::max(1, std::min(nblk(n, per_cta), sm_count * 8));
+// CTAs of the warp-per-query kernels for a source of n points — a function of n alone, the same for a cloud on its own and
+// as a member of a model set: it fixes the summation shape, hence the bits of the pose.  A warp takes 1 .. 4 queries one after
+// the other (RTR_ICP_QPW caps it): small sources keep every warp they can get; for large ones an iteration is bound by the
+// number of CTA waves (the bench batch: ~6000 CTAs = 10 waves of 4 per SM, 52 us per iteration at one query per warp, 44 us
+// at four), not by the searches.
+static int icp_warp_ctas(int n, int sm_count) {
+    static const int qpw_max = []() { const char* e = getenv("RTR_ICP_QPW"); int v = e ? atoi(e) : 4; return v >= 1 && v <= 64 ? v : 4; }();
+    const int qpw = std::max(1, std::min(qpw_max, n / (ICPW_WARPS * 2 * sm_count)));
+    return std::max(1, std::min(nblk(n, ICPW_WARPS * qpw), sm_count * 8));
+}
+// The two-level hierarchy costs one 25 us build launch and pays per query and iteration: worth it from ~60 k query-iterations
+// (a batch, a dense model); a single small model keeps the plain scan.  Either search is exact and the kernels add their
+// correspondences in the same order, so the choice never changes a bit of the result.
+static bool icp_hierarchy_pays(long long n_queries, int iterations) {
+    return icp_bvh_wanted() && n_queries * (long long)std::max(iterations, 1) >= 60000;
 }
 
 // one cooperative launch for all iterations + the fitness pass (k_icp_persistent).  Built for SURVEY section 7 step 6, exact
@@ -1316,8 +1322,7 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     unsigned* ticket = nullptr;
     if (int e = tmp_alloc(ctx, &ticket, 1, "icp")) return e;
     const IcpSolveArgs sa{p->max_iterations, p->force_iterations, p->mse_threshold_absolute};
-    const bool hierarchy = n < 65536 && tgt->n >= 1 && tgt->n <= WBVH_MAX_POINTS && icp_bvh_wanted();
-    const int nbw = icp_warp_ctas(n, ctx->sm_count, hierarchy);    // CTAs of the warp-per-query kernels
+    const int nbw = icp_warp_ctas(n, ctx->sm_count);    // CTAs of the warp-per-query kernels
     if (int e = tmp_alloc(ctx, &partials, (size_t)std::max(nb, nbw) * ICP_NSUM_MAX, "icp")) return e;
     k_icp_init<<<nb, ICP_THREADS, 0, ctx->stream>>>(src->pts, n, d_init_pose16, init_from_result ? d_result : nullptr, cur, st, ticket);
     RTR_LAUNCH_CHECK(ctx, "icp.init");
@@ -1360,7 +1365,7 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     int* nn_prev = nullptr;
     if (warp_per_query) if (int e = tmp_alloc(ctx, &nn_prev, n, "icp")) return e;
     // small targets (every scan the reference ships): the warp-per-query kernels search a two-level hierarchy of the target
-    if (warp_per_query && tgt->n >= 1 && tgt->n <= WBVH_MAX_POINTS && icp_bvh_wanted())
+    if (warp_per_query && tgt->n >= 1 && tgt->n <= WBVH_MAX_POINTS && icp_hierarchy_pays(n, p->max_iterations))
         if (int e = wbvh_build_dev(ctx, tgt->pts, tgt->n, 0, tgt->bb_min, tgt->bb_max, &T.bvh)) return e;
     const Box6 bb{tgt->bb_min[0], tgt->bb_min[1], tgt->bb_min[2], tgt->bb_max[0], tgt->bb_max[1], tgt->bb_max[2]};
     if (warp_per_query && n >= 1 && tgt->n >= 1 && icp_persistent_wanted()) {
@@ -1448,7 +1453,7 @@ static int icp_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const rtr_icp
     T.pts = set->pts; T.normals = (p->estimator == 1) ? set->normals : nullptr;
     T.bvh.n = 0; T.bvh.nleaf = 0; T.bvh.boxes = nullptr; T.bvh.pts = nullptr;
     // small scans: the warp-per-query kernels search a two-level hierarchy of the scan (indices reported set-wide: + t0)
-    if (nt >= 1 && nt <= WBVH_MAX_POINTS && icp_bvh_wanted())
+    if (nt >= 1 && nt <= WBVH_MAX_POINTS && icp_hierarchy_pays(n_src, p->max_iterations))
         if (int e = wbvh_build_dev(ctx, set->pts + t0, nt, t0, &set->seg_bb[6 * tgt_seg], &set->seg_bb[6 * tgt_seg + 3], &T.bvh)) return e;
     IcpMany im;
     memset(&im, 0, sizeof(im));
@@ -1458,7 +1463,7 @@ static int icp_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const rtr_icp
         im.pt_begin[k] = set->seg_begin[std::min(k, n_models)];
         im.cta_begin[k] = ctas;
         // the CTA count the single-cloud launch of the same kernel would use (rtr_icp_dev): same summation shape, same bits
-        if (k < n_models) ctas += icp_warp_ctas(set->seg_begin[k + 1] - set->seg_begin[k], ctx->sm_count, T.bvh.n > 0);
+        if (k < n_models) ctas += icp_warp_ctas(set->seg_begin[k + 1] - set->seg_begin[k], ctx->sm_count);
     }
     float4* cur = nullptr; IcpState* st = nullptr; double* partials = nullptr; unsigned* ticket = nullptr; int* nn_prev = nullptr;
     if (int e = tmp_alloc(ctx, &cur, n_src, "icp")) return e;
