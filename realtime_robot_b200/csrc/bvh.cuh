@@ -173,3 +173,140 @@ __device__ __forceinline__ unsigned long long wbvh_nearest_warp(const WbvhView& 
     return key;
 }
 #endif  // __CUDACC__
+
+// ----------------------------------------------------------------------------------------------------------------------
+// The same idea for a target of ANY size: a 32-ary hierarchy of boxes over the Morton-ordered points.  Level 0 holds the
+// leaves (32 consecutive points each), level l + 1 one node per 32 consecutive nodes of level l, up to a top level of at
+// most 32 nodes — 3 levels for 100 k points (3125 / 98 / 4 nodes), 3 for 1 M (31 250 / 977 / 31).  A warp tests the 32
+// children of a node at once (one box per lane), descends into the child with the smallest lower bound first and comes
+// back for every other child whose bound can still beat or tie the best distance, so the first descent already yields a
+// near-optimal bound and the rest of the tree is pruned against it.
+//
+// Why: ICP with PCL's defaults has NO correspondence cap (function.h:111-117), so a source point metres away from the
+// target still needs its exact nearest target point.  On a uniform grid that query walks every row of cells inside its
+// search sphere — 1 M scan points against a 100 k-point model cost 15 ms per iteration (14.8 ms of it in the far queries'
+// ring walks; bench.py icp_1m.scan_to_model_uncapped, round 2) — while here its cost is a handful of 32-wide box tests.
+// Exactness as above: bounds from the same monotone float sequence as dist2f, children opened while bound <= best,
+// candidates ordered by (d2 bits, original index).
+#define WIDE_MAX_LEVELS 6               // 32^6 leaves x 32 points: any int-indexed cloud
+struct WideBvh {
+    const float4* __restrict__ pts;     // n points in Morton order, .w = original index (int bits)
+    const float4* __restrict__ boxes;   // 2 float4 per node (minimum, maximum), level 0 first
+    int n;
+    int depth;                          // levels in use (>= 1); level depth - 1 has <= 32 nodes
+    int count[WIDE_MAX_LEVELS];         // nodes per level
+    int offset[WIDE_MAX_LEVELS];        // first node of each level in boxes
+};
+
+#ifdef __CUDACC__
+__global__ void k_wide_morton(const float4* __restrict__ pts, int n, float mnx, float mny, float mnz, float mxx, float mxy, float mxz,
+                              unsigned* __restrict__ keys, int* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float sx = mxx > mnx ? 1023.0f / (mxx - mnx) : 0.f, sy = mxy > mny ? 1023.0f / (mxy - mny) : 0.f, sz = mxz > mnz ? 1023.0f / (mxz - mnz) : 0.f;
+    const float4 p = __ldg(pts + i);
+    float fx = (p.x - mnx) * sx, fy = (p.y - mny) * sy, fz = (p.z - mnz) * sz;
+    fx = fx >= 0.f ? fminf(fx, 1023.f) : 0.f;          // NaN -> 0
+    fy = fy >= 0.f ? fminf(fy, 1023.f) : 0.f;
+    fz = fz >= 0.f ? fminf(fz, 1023.f) : 0.f;
+    keys[i] = (wbvh_expand10((unsigned)fx) << 2) | (wbvh_expand10((unsigned)fy) << 1) | wbvh_expand10((unsigned)fz);
+    vals[i] = i;
+}
+// one warp per leaf: its 32 points (one per lane, Morton order) and the box over the finite ones
+__global__ void k_wide_leaves(const float4* __restrict__ pts, const int* __restrict__ order, int n, int idx_base, float4* __restrict__ mpts,
+                              float4* __restrict__ boxes) {
+    const int lane = threadIdx.x & 31;
+    const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (l * WBVH_LEAF >= n) return;
+    const int s = l * WBVH_LEAF + lane;
+    const float inf = __int_as_float(0x7f800000);
+    float lx = inf, ly = inf, lz = inf, hx = -inf, hy = -inf, hz = -inf;
+    if (s < n) {
+        const int i = __ldg(order + s);
+        float4 p = __ldg(pts + i);
+        p.w = __int_as_float(idx_base + i);
+        mpts[s] = p;
+        lx = hx = p.x; ly = hy = p.y; lz = hz = p.z;              // fminf / fmaxf below ignore NaN coordinates
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)); ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o)); lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o));
+        hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o)); hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+    }
+    if (lane == 0) { boxes[2 * l] = make_float4(lx, ly, lz, 0.f); boxes[2 * l + 1] = make_float4(hx, hy, hz, 0.f); }
+}
+// one warp per node of the upper level: the union of its (up to 32) children
+__global__ void k_wide_level(const float4* __restrict__ lower, int n_lower, float4* __restrict__ upper) {
+    const int lane = threadIdx.x & 31;
+    const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (u * 32 >= n_lower) return;
+    const int c = u * 32 + lane;
+    const float inf = __int_as_float(0x7f800000);
+    float lx = inf, ly = inf, lz = inf, hx = -inf, hy = -inf, hz = -inf;
+    if (c < n_lower) {
+        const float4 lo = __ldg(lower + 2 * c), hi = __ldg(lower + 2 * c + 1);
+        lx = lo.x; ly = lo.y; lz = lo.z; hx = hi.x; hy = hi.y; hz = hi.z;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)); ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o)); lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o));
+        hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o)); hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+    }
+    if (lane == 0) { upper[2 * u] = make_float4(lx, ly, lz, 0.f); upper[2 * u + 1] = make_float4(hx, hy, hz, 0.f); }
+}
+
+// the 32 points of one leaf against the best candidate so far (kd: d2 bits, ki: original index)
+__device__ __forceinline__ void wide_scan_leaf(const WideBvh& B, int leaf, float qx, float qy, float qz, int lane, unsigned& kd, unsigned& ki) {
+    const int s = leaf * WBVH_LEAF + lane;
+    unsigned db = 0xffffffffu, id = 0xffffffffu;
+    if (s < B.n) {
+        const float4 p = __ldg(B.pts + s);
+        db = __float_as_uint(dist2f(qx, qy, qz, p.x, p.y, p.z));
+        id = (unsigned)__float_as_int(p.w);
+    }
+    const unsigned mdb = __reduce_min_sync(0xffffffffu, db);
+    if (mdb <= kd) {                           // warp-uniform
+        const unsigned mid = __reduce_min_sync(0xffffffffu, db == mdb ? id : 0xffffffffu);
+        if (mdb < kd || mid < ki) { kd = mdb; ki = mid; }
+    }
+}
+// children [node * 32, node * 32 + 32) of level L, nearest first
+template <int L>
+__device__ __forceinline__ void wide_visit(const WideBvh& B, int node, float qx, float qy, float qz, int lane, unsigned& kd, unsigned& ki) {
+    const int c = node * 32 + lane;
+    const float inf = __int_as_float(0x7f800000);
+    float b = inf;
+    if (c < B.count[L]) {
+        const float4* bx = B.boxes + 2 * (size_t)(B.offset[L] + c);
+        b = wbvh_box_d2(__ldg(bx), __ldg(bx + 1), qx, qy, qz);
+    }
+    for (;;) {
+        // kd holds the bits of a non-negative float or of +inf ("anything"): unsigned order == float order; an empty or
+        // visited child has b == +inf and stays closed even against kd == +inf
+        const unsigned ub = (b < inf && __float_as_uint(b) <= kd) ? __float_as_uint(b) : 0xffffffffu;
+        const unsigned m = __reduce_min_sync(0xffffffffu, ub);
+        if (m == 0xffffffffu) break;
+        const int src = __ffs(__ballot_sync(0xffffffffu, ub == m)) - 1;
+        if (lane == src) b = inf;
+        if constexpr (L == 0) wide_scan_leaf(B, node * 32 + src, qx, qy, qz, lane, kd, ki);
+        else wide_visit<L - 1>(B, node * 32 + src, qx, qy, qz, lane, kd, ki);
+    }
+}
+// Exact nearest neighbour of q for a whole warp (every lane passes the same q and key and receives the same answer).
+// key: (d2 bits << 32 | index) of the best candidate so far — a warm start, or (bits of the search radius^2 << 32 |
+// 0xffffffff) for "anything at or inside the radius", radius +inf for an unbounded search.  An index of 0xffffffff in the
+// result means nothing was found.
+__device__ __forceinline__ unsigned long long wide_nearest_warp(const WideBvh& B, float qx, float qy, float qz, int lane, unsigned long long key) {
+    unsigned kd = (unsigned)(key >> 32), ki = (unsigned)key;
+    switch (B.depth) {
+        case 1: wide_visit<0>(B, 0, qx, qy, qz, lane, kd, ki); break;
+        case 2: wide_visit<1>(B, 0, qx, qy, qz, lane, kd, ki); break;
+        case 3: wide_visit<2>(B, 0, qx, qy, qz, lane, kd, ki); break;
+        case 4: wide_visit<3>(B, 0, qx, qy, qz, lane, kd, ki); break;
+        case 5: wide_visit<4>(B, 0, qx, qy, qz, lane, kd, ki); break;
+        case 6: wide_visit<5>(B, 0, qx, qy, qz, lane, kd, ki); break;
+        default: break;
+    }
+    return ((unsigned long long)kd << 32) | ki;
+}
+#endif  // __CUDACC__

@@ -974,8 +974,10 @@ int rtr_nearest(rtr_cloud* target, const float* host_queries_xyz1, int nq, int* 
     if (int e = dev_alloc(ctx, &d_idx, nq, "nearest")) return e;
     if (int e = dev_alloc(ctx, &d_d2, nq, "nearest")) return e;
     RTR_CHECK(cudaMemcpyAsync(d_q, host_queries_xyz1, (size_t)nq * 16, cudaMemcpyHostToDevice, ctx->stream), "nearest");
-    const char* use_bvh = getenv("RTR_NEAREST_BVH");       // tests: answer from the small-target hierarchy of the ICP kernels (bvh.cuh)
-    if (use_bvh && use_bvh[0] == '1' && target->n <= 4096) {
+    // tests: answer from the hierarchies of the ICP kernels (bvh.cuh) — 1: the two-level one for targets of <= 4096 points,
+    // 2: the 32-ary one (any size)
+    const char* use_bvh = getenv("RTR_NEAREST_BVH");
+    if (use_bvh && ((use_bvh[0] == '1' && target->n <= 4096) || use_bvh[0] == '2')) {
         TmpScope tmp_scope(ctx);
         if (int e = rtr_nearest_bvh_dev(target, d_q, nq, d_idx, d_d2)) return e;
     } else {

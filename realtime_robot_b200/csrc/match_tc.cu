@@ -547,7 +547,8 @@ int rtr_match_tc_dev(rtr_context* ctx, const float* fa, int ns, const float* fb,
     // columns); the certificate decides as before whether a row is final, uncertified rows are redone exactly.  Measured on the
     // bench batch (74 786 model rows x 1909 scan rows, k = 5): lists of 16 / 8 / 6 / 4 -> 659 / 398 / 338 / 819 us with
     // 0 / 0 / 0 / 15 139 rows redone (4 < k cannot hold the answer of one group).
-    static const int keep_env = []() { const char* e = getenv("RTR_MATCH_KEEP"); return e ? atoi(e) : 0; }();
+    const char* keep_e = getenv("RTR_MATCH_KEEP");       // read per call: tools/bench_match_scale.py times several settings in one process
+    const int keep_env = keep_e ? atoi(keep_e) : 0;
     const int keep = (keep_env == 4 || keep_env == 6 || keep_env == 8 || keep_env == 16) ? keep_env : ((!merge && tgt_tiles <= 64 && k <= 5) ? 6 : 16);
     const int lists = merge ? splits : TC_EPI_GROUPS;
     if (int e = tmp_alloc(ctx, &cand_idx, (size_t)ns * lists * keep, "match.tc")) return e;

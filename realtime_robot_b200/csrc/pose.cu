@@ -753,12 +753,26 @@ __device__ __forceinline__ float box_dist2f(const Box6& b, float qx, float qy, f
     float ez = qz > b.mxz ? __fsub_rn(qz, b.mxz) : (qz < b.mnz ? __fsub_rn(qz, b.mnz) : 0.f);
     return __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
 }
+// Thread-per-query kernels, far queries: the lanes that still want a neighbour are served one after the other by the whole
+// warp through the 32-ary hierarchy (bvh.cuh).  bound2: this lane's search radius^2 (candidates with d2 <= bound2 count).
+// Every lane of the warp must call this (want == false: nothing to search).
+__device__ __forceinline__ void wide_nearest_lanes(const WideBvh& W, bool want, float4 q, float bound2, int lane, int& b, float& d2) {
+    unsigned todo = __ballot_sync(0xffffffffu, want);
+    while (todo) {
+        const int j = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const float x = __shfl_sync(0xffffffffu, q.x, j), y = __shfl_sync(0xffffffffu, q.y, j), z = __shfl_sync(0xffffffffu, q.z, j);
+        const unsigned rb = __shfl_sync(0xffffffffu, __float_as_uint(bound2), j);
+        const unsigned long long key = wide_nearest_warp(W, x, y, z, lane, ((unsigned long long)rb << 32) | 0xffffffffull);
+        if (lane == j && (unsigned)key != 0xffffffffu) { b = (int)(unsigned)key; d2 = __uint_as_float((unsigned)(key >> 32)); }
+    }
+}
 // correspondence estimation + accumulation.  Applies the previous iteration's step first (transformCloud in place).
 // A query farther from the target's bounding box than the cap is dropped before any cell is touched.
 template <int EST>
 __global__ void __launch_bounds__(ICP_THREADS, 4) k_icp_corr(GridView g, GridView gc, Box6 bb, float far2, const float4* __restrict__ tgt_normals, float4* __restrict__ cur, int n,
                                                            IcpState* st, double dmax2, float prune2, double* partials, unsigned* ticket,
-                                                           IcpSolveArgs sa) {
+                                                           IcpSolveArgs sa, const __grid_constant__ WideBvh W, const float4* __restrict__ tgt_pts) {
     constexpr int N = IcpSums<EST>::N;
     __shared__ float m[16];
     __shared__ double red[ICP_THREADS / 32][N];
@@ -773,16 +787,23 @@ __global__ void __launch_bounds__(ICP_THREADS, 4) k_icp_corr(GridView g, GridVie
 #pragma unroll
     for (int k = 0; k < N; ++k) acc[k] = 0.0;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        float4 q = cur[i];
-        if (have) { q = xform(m, q); cur[i] = q; }
-        int b; float d2; float4 t;
+    {
+        const bool live = i < n;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) {
+            q = cur[i];
+            if (have) { q = xform(m, q); cur[i] = q; }
+        }
+        int b = -1; float d2 = 0.f; float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
         // the grid copy carries the matched point's coordinates: the original-order target is never touched
         const float bd2 = box_dist2f(bb, q.x, q.y, q.z);
-        if (bd2 > prune2) b = -1;
-        else {
-            const GridView gg = bd2 > far2 ? gc : g;        // far from the target: coarse cells (see k_icp_fitness)
-            grid_nearest_ex(gg, q.x, q.y, q.z, prune2, b, d2, t);
+        const bool search = live && !(bd2 > prune2);
+        const bool far = bd2 > far2;                        // far from the target: coarse cells, or the 32-ary hierarchy (see k_icp_fitness)
+        if (search && !(far && W.n > 0)) grid_nearest_ex(far ? gc : g, q.x, q.y, q.z, prune2, b, d2, t);
+        if (W.n > 0) {                                      // warp-uniform
+            const bool mine = search && far;
+            wide_nearest_lanes(W, mine, q, prune2, threadIdx.x & 31, b, d2);
+            if (mine && b >= 0) t = __ldg(tgt_pts + b);
         }
         if (b >= 0 && (double)d2 <= dmax2) {
             float4 nrm = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1158,6 +1179,59 @@ static int wbvh_build_dev(rtr_context* ctx, const float4* pts, int n, int idx_ba
     out->boxes = boxes; out->pts = mpts; out->nleaf = nleaf; out->n = n;
     return 0;
 }
+// Build the 32-ary hierarchy of a target of any size: Morton codes, one radix sort, one warp per leaf, one warp per upper node.
+static int wide_build_dev(rtr_context* ctx, const float4* pts, int n, int idx_base, const float* bb_min, const float* bb_max, WideBvh* out) {
+    memset(out, 0, sizeof(*out));
+    if (n <= 0) return 0;
+    int count[WIDE_MAX_LEVELS], offset[WIDE_MAX_LEVELS], depth = 0, total = 0;
+    for (int c = nblk(n, WBVH_LEAF);; c = nblk(c, 32)) {
+        count[depth] = c; offset[depth] = total; total += c; ++depth;
+        if (c <= 32) break;
+        if (depth == WIDE_MAX_LEVELS) return rtr_fail("icp.wide", "hierarchy deeper than WIDE_MAX_LEVELS", RTR_ERR_INVALID);
+    }
+    unsigned *keys = nullptr, *keys2 = nullptr; int *vals = nullptr, *vals2 = nullptr; char* temp = nullptr;
+    float4 *boxes = nullptr, *mpts = nullptr;
+    if (int e = tmp_alloc(ctx, &keys, n, "icp.wide")) return e;
+    if (int e = tmp_alloc(ctx, &keys2, n, "icp.wide")) return e;
+    if (int e = tmp_alloc(ctx, &vals, n, "icp.wide")) return e;
+    if (int e = tmp_alloc(ctx, &vals2, n, "icp.wide")) return e;
+    if (int e = tmp_alloc(ctx, &boxes, (size_t)2 * total, "icp.wide")) return e;
+    if (int e = tmp_alloc(ctx, &mpts, n, "icp.wide")) return e;
+    k_wide_morton<<<nblk(n, 256), 256, 0, ctx->stream>>>(pts, n, bb_min[0], bb_min[1], bb_min[2], bb_max[0], bb_max[1], bb_max[2], keys, vals);
+    RTR_LAUNCH_CHECK(ctx, "icp.wide_keys");
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys2, vals, vals2, n, 0, 30, ctx->stream);
+    if (int e = tmp_alloc(ctx, &temp, tb, "icp.wide")) return e;
+    RTR_CHECK(cub::DeviceRadixSort::SortPairs(temp, tb, keys, keys2, vals, vals2, n, 0, 30, ctx->stream), "icp.wide_sort");
+    RTR_MARK(ctx, "icp.wide_sort");
+    k_wide_leaves<<<nblk((long long)count[0] * 32, 256), 256, 0, ctx->stream>>>(pts, vals2, n, idx_base, mpts, boxes);
+    RTR_LAUNCH_CHECK(ctx, "icp.wide_leaves");
+    for (int l = 1; l < depth; ++l) {
+        k_wide_level<<<nblk((long long)count[l] * 32, 256), 256, 0, ctx->stream>>>(boxes + 2 * (size_t)offset[l - 1], count[l - 1], boxes + 2 * (size_t)offset[l]);
+        RTR_LAUNCH_CHECK(ctx, "icp.wide_level");
+    }
+    dev_free(ctx, keys); dev_free(ctx, keys2); dev_free(ctx, vals); dev_free(ctx, vals2); dev_free(ctx, temp);
+    out->pts = mpts; out->boxes = boxes; out->n = n; out->depth = depth;
+    for (int l = 0; l < depth; ++l) { out->count[l] = count[l]; out->offset[l] = offset[l]; }
+    return 0;
+}
+// RTR_ICP_WIDE=0: far queries of the thread-per-query kernels walk the coarse grid instead of the 32-ary hierarchy (A/B runs, tests)
+static bool icp_wide_wanted() {
+    const char* e = getenv("RTR_ICP_WIDE");
+    return !(e && e[0] == '0');
+}
+__global__ void k_nearest_wide(const __grid_constant__ WideBvh B, const float4* __restrict__ q, int nq, int* __restrict__ idx, float* __restrict__ d2) {
+    const int lane = threadIdx.x & 31;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= nq) return;
+    const float4 p = __ldg(q + i);
+    const unsigned long long key = wide_nearest_warp(B, p.x, p.y, p.z, lane, ~0ull);
+    if (lane == 0) {
+        const bool found = (unsigned)key != 0xffffffffu;
+        idx[i] = found ? (int)(unsigned)key : -1;
+        d2[i] = found ? __uint_as_float((unsigned)(key >> 32)) : __int_as_float(0x7f800000);
+    }
+}
 // the hierarchy on its own (rtr_nearest with RTR_NEAREST_BVH=1: the tests compare it with the oracle's brute-force search)
 __global__ void k_nearest_wbvh(WbvhView B, const float4* __restrict__ q, int nq, int* __restrict__ idx, float* __restrict__ d2) {
     const int lane = threadIdx.x & 31;
@@ -1171,9 +1245,19 @@ __global__ void k_nearest_wbvh(WbvhView B, const float4* __restrict__ q, int nq,
 int rtr_nearest_bvh_dev(rtr_cloud* tgt, const float4* d_q, int nq, int* d_idx, float* d_d2) {
     rtr_context* ctx = tgt->ctx;
     if (int e = rtr_ensure_bbox(tgt)) return e;
+    const char* mode = getenv("RTR_NEAREST_BVH");
+    const bool force_wide = mode && mode[0] == '2';
+    if (tgt->n > WBVH_MAX_POINTS || force_wide) {       // any size: the 32-ary hierarchy
+        WideBvh W;
+        if (int e = wide_build_dev(ctx, tgt->pts, tgt->n, 0, tgt->bb_min, tgt->bb_max, &W)) return e;
+        if (W.n == 0) return rtr_fail("nearest", "empty target", RTR_ERR_INVALID);
+        k_nearest_wide<<<nblk((long long)nq * 32, 128), 128, 0, ctx->stream>>>(W, d_q, nq, d_idx, d_d2);
+        RTR_LAUNCH_CHECK(ctx, "nearest.wide");
+        return 0;
+    }
     WbvhView B;
     if (int e = wbvh_build_dev(ctx, tgt->pts, tgt->n, 0, tgt->bb_min, tgt->bb_max, &B)) return e;
-    if (B.n == 0) return rtr_fail("nearest", "the hierarchy serves clouds of 1..4096 points", RTR_ERR_INVALID);
+    if (B.n == 0) return rtr_fail("nearest", "empty target", RTR_ERR_INVALID);
     k_nearest_wbvh<<<nblk((long long)nq * 32, 128), 128, 0, ctx->stream>>>(B, d_q, nq, d_idx, d_d2);
     RTR_LAUNCH_CHECK(ctx, "nearest.bvh");
     return 0;
@@ -1190,7 +1274,7 @@ static bool icp_bvh_wanted() {
 // of them; cells four times wider mean 16x fewer rows (either grid gives the exact nearest neighbour).
 __global__ void __launch_bounds__(ICP_THREADS) k_icp_fitness(GridView g, GridView gc, Box6 bb, float far2, const float4* __restrict__ src, int n,
                                                              const IcpState* __restrict__ st, double* partials, unsigned* ticket,
-                                                             rtr_pose_result* res, int keep_ransac_fields) {
+                                                             rtr_pose_result* res, int keep_ransac_fields, const __grid_constant__ WideBvh W) {
     __shared__ float m[16];
     __shared__ double red[ICP_THREADS / 32][2];
     __shared__ double sums[2];
@@ -1204,11 +1288,14 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_fitness(GridView g, GridVie
     __syncthreads();
     double s = 0, c = 0;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        float4 q = xform(m, __ldg(src + i));
-        int b; float d2;
-        const GridView gg = box_dist2f(bb, q.x, q.y, q.z) > far2 ? gc : g;
-        grid_nearest(gg, q.x, q.y, q.z, b, d2);
+    {
+        const bool live = i < n;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) q = xform(m, __ldg(src + i));
+        int b = -1; float d2 = 0.f;
+        const bool far = box_dist2f(bb, q.x, q.y, q.z) > far2;
+        if (live && !(far && W.n > 0)) grid_nearest(far ? gc : g, q.x, q.y, q.z, b, d2);
+        if (W.n > 0) wide_nearest_lanes(W, live && far, q, __int_as_float(0x7f800000), threadIdx.x & 31, b, d2);
         if (b >= 0) { s = (double)d2; c = 1.0; }
     }
     s = warp_sum(s); c = warp_sum(c);
@@ -1300,6 +1387,8 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     // RTR_ICP_FAR_FACTOR <= 1 disables
     GridView vc = v;
     float far2 = FLT_MAX;
+    WideBvh W;
+    memset(&W, 0, sizeof(W));
     if (n >= 65536) {
         static const float far_factor = []() { const char* e = getenv("RTR_ICP_FAR_FACTOR"); return e ? (float)atof(e) : 4.0f; }();
         // worth building only if some of the source can be far from the target: judged on the untransformed bounding boxes
@@ -1308,7 +1397,11 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
         if (int e = rtr_ensure_bbox(src)) return e;
         for (int a = 0; a < 3; ++a)
             may_be_far |= src->bb_min[a] < tgt->bb_min[a] - 6.f * v.h || src->bb_max[a] > tgt->bb_max[a] + 6.f * v.h;
-        if (far_factor > 1.f && may_be_far) {
+        if (may_be_far && icp_wide_wanted()) {
+            // far queries: the 32-ary hierarchy (bvh.cuh) — a handful of 32-wide box tests per query instead of a ring walk
+            if (int e = wide_build_dev(ctx, tgt->pts, tgt->n, 0, tgt->bb_min, tgt->bb_max, &W)) return e;
+            far2 = (6.f * v.h) * (6.f * v.h);
+        } else if (far_factor > 1.f && may_be_far) {
             DevGrid* gcoarse;
             if (int e = rtr_get_grid(tgt, g->h * far_factor, &gcoarse)) return e;
             vc = rtr_view(gcoarse);
@@ -1388,14 +1481,14 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
                 if (plane) launch_pdl(k_icp_corr_warp<1>, nbw, ICPW_WARPS * 32, 0, ctx->stream, T, cur, nn_prev, n, st, dmax2, prune2, partials, ticket, sa);
                 else launch_pdl(k_icp_corr_warp<0>, nbw, ICPW_WARPS * 32, 0, ctx->stream, T, cur, nn_prev, n, st, dmax2, prune2, partials, ticket, sa);
             } else {
-                if (plane) launch_pdl(k_icp_corr<1>, nb, ICP_THREADS, 0, ctx->stream, v, vc, bb, far2, (const float4*)tgt->normals, cur, n, st, dmax2, prune2, partials, ticket, sa);
-                else launch_pdl(k_icp_corr<0>, nb, ICP_THREADS, 0, ctx->stream, v, vc, bb, far2, (const float4*)nullptr, cur, n, st, dmax2, prune2, partials, ticket, sa);
+                if (plane) launch_pdl(k_icp_corr<1>, nb, ICP_THREADS, 0, ctx->stream, v, vc, bb, far2, (const float4*)tgt->normals, cur, n, st, dmax2, prune2, partials, ticket, sa, W, (const float4*)tgt->pts);
+                else launch_pdl(k_icp_corr<0>, nb, ICP_THREADS, 0, ctx->stream, v, vc, bb, far2, (const float4*)nullptr, cur, n, st, dmax2, prune2, partials, ticket, sa, W, (const float4*)tgt->pts);
             }
             RTR_LAUNCH_CHECK(ctx, "icp.corr");
         }
     }
     if (warp_per_query) launch_pdl(k_icp_fitness_warp, nbw, ICPW_WARPS * 32, 0, ctx->stream, T, src_pts, (const float4*)cur, (const int*)nn_prev, n, (const IcpState*)st, partials, ticket, d_result, init_from_result);
-    else launch_pdl(k_icp_fitness, nb, ICP_THREADS, 0, ctx->stream, v, vc, bb, far2, src_pts, n, (const IcpState*)st, partials, ticket, d_result, init_from_result);
+    else launch_pdl(k_icp_fitness, nb, ICP_THREADS, 0, ctx->stream, v, vc, bb, far2, src_pts, n, (const IcpState*)st, partials, ticket, d_result, init_from_result, W);
     RTR_LAUNCH_CHECK(ctx, "icp.fitness");
     dev_free(ctx, cur); dev_free(ctx, src2); dev_free(ctx, st); dev_free(ctx, partials); dev_free(ctx, ticket); dev_free(ctx, nn_prev);
     return 0;

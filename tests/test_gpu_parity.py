@@ -902,6 +902,65 @@ def test_bvh_nearest_is_the_brute_force_answer(api, gpu_ctx, orc, clouds, monkey
 
 
 @pytest.mark.gpu
+def test_wide_hierarchy_nearest_is_the_brute_force_answer(api, gpu_ctx, orc, clouds, monkeypatch):
+    """bvh.cuh, second half — the 32-ary hierarchy for targets of any size (far queries of the large-source ICP kernels) — against
+    the oracle's exact search: one, two and three levels (1 .. 40 000 points), near and far queries, queries ON target points,
+    a lattice full of exact distance ties (ties -> lowest index), duplicates, a flat cloud."""
+    monkeypatch.setenv("RTR_NEAREST_BVH", "2")
+    rng = np.random.default_rng(5)
+    lattice = np.ones((1728, 4), np.float32)
+    lattice[:, :3] = np.stack(np.meshgrid(np.arange(12), np.arange(12), np.arange(12), indexing="ij"), -1).reshape(-1, 3) * np.float32(0.25)
+    lattice = lattice[rng.permutation(len(lattice))]
+    dup = clouds("chair4").copy(); dup[9000:] = dup[:len(dup) - 9000]
+    flat = random_cloud(5000, 4); flat[:, 2] = 0.5
+    cases = [clouds("mcloud"), clouds("chair4"), lattice, dup, flat, random_cloud(1, 1), random_cloud(33, 2), random_cloud(1025, 3),
+             random_cloud(40000, 5, 2.0)]
+    for tgt in cases:
+        c = api.Cloud(gpu_ctx, tgt)
+        lo, hi = tgt[:, :3].min(0), tgt[:, :3].max(0)
+        q = np.ones((2000, 4), np.float32)
+        q[:600, :3] = (lo + (hi - lo) * rng.random((600, 3))).astype(np.float32)                         # inside the box
+        q[600:1200, :3] = (lo - 3.0 + (hi - lo + 6.0) * rng.random((600, 3))).astype(np.float32)         # far outside
+        q[1200:1600] = tgt[rng.integers(0, len(tgt), 400)]                                               # on target points
+        q[1600:, :3] = (np.round((lo + (hi - lo) * rng.random((400, 3))) * 8) / 8).astype(np.float32)    # ties on the lattice
+        gi, gd = c.nearest(q)
+        oi, od = orc.nearest(tgt, q)
+        assert np.array_equal(gi, oi) and np.array_equal(gd, od), len(tgt)
+        c.free()
+
+
+@pytest.mark.gpu
+def test_icp_far_queries_hierarchy_and_coarse_grid_give_the_same_record(api, gpu_ctx):
+    """Large sources (>= 65 536 points) whose box sticks out of the target's: the far queries of k_icp_corr / k_icp_fitness go through
+    the 32-ary hierarchy; RTR_ICP_WIDE=0 sends them through the coarse grid instead.  Both searches are exact and the sums are taken
+    in the same shape: the records agree bit for bit — uncapped (PCL's default) and capped."""
+    import subprocess, sys, json
+    code = ("import sys, json; sys.path.insert(0, %r)\n"
+            "import numpy as np\n"
+            "from realtime_robot_b200 import api, synth\n"
+            "from realtime_robot_b200.params import IcpParams\n"
+            "rng = np.random.default_rng(11)\n"
+            "model = synth.sample_rects(synth.room_rects((1.0, 1.0, 1.0), n_boxes=3, seed=3), 20000, 4)\n"
+            "scan = np.ones((70000, 4), np.float32)\n"
+            "scan[:20000] = model; scan[:20000, :3] += rng.normal(0, 0.002, (20000, 3)).astype(np.float32) + np.float32(0.01)\n"
+            "scan[20000:, :3] = (rng.random((50000, 3)) * 6.0 - 2.5).astype(np.float32)\n"
+            "ctx = api.Context(0)\n"
+            "out = []\n"
+            "for cap in (0.0, 0.05):\n"
+            "    p = IcpParams(); p.max_iterations = 4; p.max_correspondence_distance = cap\n"
+            "    r = api.icp(api.Cloud(ctx, scan), api.Cloud(ctx, model), p)\n"
+            "    out.append(bytes(r).hex())\n"
+            "print(json.dumps(out))\n") % ROOT
+    outs = []
+    for wide in ("1", "0"):
+        env = dict(os.environ, RTR_ICP_WIDE=wide)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert outs[0] == outs[1]
+
+
+@pytest.mark.gpu
 def test_icp_bvh_and_brute_force_kernels_give_the_same_records(api, gpu_ctx, clouds):
     """RTR_ICP_BVH=0 keeps the plain brute-force scan of the target: both searches are exact and the kernels add their
     correspondences in the same order, so the records agree bit for bit."""
