@@ -754,25 +754,45 @@ __device__ __forceinline__ float box_dist2f(const Box6& b, float qx, float qy, f
     return __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
 }
 // Thread-per-query kernels, far queries: the lanes that still want a neighbour are served one after the other by the whole
-// warp through the 32-ary hierarchy (bvh.cuh).  bound2: this lane's search radius^2 (candidates with d2 <= bound2 count).
+// warp through the 32-ary hierarchy (bvh.cuh).  key0: this lane's start — (d2 bits << 32 | index) of a known target point
+// (warm start), or (bits of the search radius^2 << 32 | 0xffffffff) for "anything at or inside the radius".
 // Every lane of the warp must call this (want == false: nothing to search).
-__device__ __forceinline__ void wide_nearest_lanes(const WideBvh& W, bool want, float4 q, float bound2, int lane, int& b, float& d2) {
+__device__ __forceinline__ void wide_nearest_lanes(const WideBvh& W, bool want, float4 q, unsigned long long key0, int lane, int& b, float& d2) {
     unsigned todo = __ballot_sync(0xffffffffu, want);
     while (todo) {
         const int j = __ffs(todo) - 1;
         todo &= todo - 1;
         const float x = __shfl_sync(0xffffffffu, q.x, j), y = __shfl_sync(0xffffffffu, q.y, j), z = __shfl_sync(0xffffffffu, q.z, j);
-        const unsigned rb = __shfl_sync(0xffffffffu, __float_as_uint(bound2), j);
-        const unsigned long long key = wide_nearest_warp(W, x, y, z, lane, ((unsigned long long)rb << 32) | 0xffffffffull);
+        const unsigned long long k0 = __shfl_sync(0xffffffffu, key0, j);
+        const unsigned long long key = wide_nearest_warp(W, x, y, z, lane, k0);
         if (lane == j && (unsigned)key != 0xffffffffu) { b = (int)(unsigned)key; d2 = __uint_as_float((unsigned)(key >> 32)); }
     }
+}
+// The neighbour of the previous search as the first candidate of this one: its distance bounds the search sphere, so the
+// grid search skips the 27-cell block and walks only the rows the sphere touches (grid_nearest_far: typically one row and one
+// or two cells once ICP is converging, against 9 rows / 27 cells), and the hierarchy opens only the boxes inside it.  The
+// candidate is a target point like any other: the result is the exact nearest neighbour, ties -> lowest index, as without it.
+struct WarmStart { int b; float d2; float4 p; };
+__device__ __forceinline__ WarmStart icp_warm_start(const int* __restrict__ nn_prev, int i, bool use, const float4* __restrict__ tgt_pts, float4 q) {
+    WarmStart w;
+    w.b = -1; w.d2 = FLT_MAX; w.p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (use) {
+        const int pb = nn_prev[i];
+        if (pb >= 0) {
+            const float4 tp = __ldg(tgt_pts + pb);
+            const float d = dist2f(q.x, q.y, q.z, tp.x, tp.y, tp.z);
+            if (d < FLT_MAX) { w.b = pb; w.d2 = d; w.p = tp; }       // not for a NaN / overflowing distance
+        }
+    }
+    return w;
 }
 // correspondence estimation + accumulation.  Applies the previous iteration's step first (transformCloud in place).
 // A query farther from the target's bounding box than the cap is dropped before any cell is touched.
 template <int EST>
 __global__ void __launch_bounds__(ICP_THREADS, 4) k_icp_corr(GridView g, GridView gc, Box6 bb, float far2, const float4* __restrict__ tgt_normals, float4* __restrict__ cur, int n,
                                                            IcpState* st, double dmax2, float prune2, double* partials, unsigned* ticket,
-                                                           IcpSolveArgs sa, const __grid_constant__ WideBvh W, const float4* __restrict__ tgt_pts) {
+                                                           IcpSolveArgs sa, const __grid_constant__ WideBvh W, const float4* __restrict__ tgt_pts,
+                                                           int* __restrict__ nn_prev) {
     constexpr int N = IcpSums<EST>::N;
     __shared__ float m[16];
     __shared__ double red[ICP_THREADS / 32][N];
@@ -799,12 +819,19 @@ __global__ void __launch_bounds__(ICP_THREADS, 4) k_icp_corr(GridView g, GridVie
         const float bd2 = box_dist2f(bb, q.x, q.y, q.z);
         const bool search = live && !(bd2 > prune2);
         const bool far = bd2 > far2;                        // far from the target: coarse cells, or the 32-ary hierarchy (see k_icp_fitness)
-        if (search && !(far && W.n > 0)) grid_nearest_ex(far ? gc : g, q.x, q.y, q.z, prune2, b, d2, t);
+        const WarmStart ws = icp_warm_start(nn_prev, i, search && have && nn_prev != nullptr, tgt_pts, q);
+        if (search && !(far && W.n > 0)) {
+            if (ws.b >= 0) { b = ws.b; d2 = ws.d2; t = ws.p; grid_nearest_far(far ? gc : g, q.x, q.y, q.z, prune2, b, d2, t); }
+            else grid_nearest_ex(far ? gc : g, q.x, q.y, q.z, prune2, b, d2, t);
+        }
         if (W.n > 0) {                                      // warp-uniform
             const bool mine = search && far;
-            wide_nearest_lanes(W, mine, q, prune2, threadIdx.x & 31, b, d2);
+            const unsigned long long key0 = (ws.b >= 0 && ws.d2 <= prune2) ? (((unsigned long long)__float_as_uint(ws.d2) << 32) | (unsigned)ws.b)
+                                                                          : (((unsigned long long)__float_as_uint(prune2) << 32) | 0xffffffffull);
+            wide_nearest_lanes(W, mine, q, key0, threadIdx.x & 31, b, d2);
             if (mine && b >= 0) t = __ldg(tgt_pts + b);
         }
+        if (search && nn_prev) nn_prev[i] = b;              // (a query outside the cap's reach keeps its older entry: any target point is a valid start)
         if (b >= 0 && (double)d2 <= dmax2) {
             float4 nrm = make_float4(0.f, 0.f, 0.f, 0.f);
             if (EST == 1) nrm = __ldg(tgt_normals + b);
@@ -1274,7 +1301,8 @@ static bool icp_bvh_wanted() {
 // of them; cells four times wider mean 16x fewer rows (either grid gives the exact nearest neighbour).
 __global__ void __launch_bounds__(ICP_THREADS) k_icp_fitness(GridView g, GridView gc, Box6 bb, float far2, const float4* __restrict__ src, int n,
                                                              const IcpState* __restrict__ st, double* partials, unsigned* ticket,
-                                                             rtr_pose_result* res, int keep_ransac_fields, const __grid_constant__ WideBvh W) {
+                                                             rtr_pose_result* res, int keep_ransac_fields, const __grid_constant__ WideBvh W,
+                                                             const float4* __restrict__ tgt_pts, const int* __restrict__ nn_prev) {
     __shared__ float m[16];
     __shared__ double red[ICP_THREADS / 32][2];
     __shared__ double sums[2];
@@ -1294,8 +1322,16 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_fitness(GridView g, GridVie
         if (live) q = xform(m, __ldg(src + i));
         int b = -1; float d2 = 0.f;
         const bool far = box_dist2f(bb, q.x, q.y, q.z) > far2;
-        if (live && !(far && W.n > 0)) grid_nearest(far ? gc : g, q.x, q.y, q.z, b, d2);
-        if (W.n > 0) wide_nearest_lanes(W, live && far, q, __int_as_float(0x7f800000), threadIdx.x & 31, b, d2);
+        const WarmStart ws = icp_warm_start(nn_prev, i, live && nn_prev != nullptr, tgt_pts, q);
+        if (live && !(far && W.n > 0)) {
+            float4 t;
+            if (ws.b >= 0) { b = ws.b; d2 = ws.d2; t = ws.p; grid_nearest_far(far ? gc : g, q.x, q.y, q.z, FLT_MAX, b, d2, t); }
+            else grid_nearest(far ? gc : g, q.x, q.y, q.z, b, d2);
+        }
+        if (W.n > 0) {
+            const unsigned long long key0 = ws.b >= 0 ? (((unsigned long long)__float_as_uint(ws.d2) << 32) | (unsigned)ws.b) : 0x7f800000ffffffffull;
+            wide_nearest_lanes(W, live && far, q, key0, threadIdx.x & 31, b, d2);
+        }
         if (b >= 0) { s = (double)d2; c = 1.0; }
     }
     s = warp_sum(s); c = warp_sum(c);
@@ -1455,8 +1491,11 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
     IcpTarget T;
     T.g = v; T.brute = v.sorted; T.brute_n = (tgt->n <= RTR_BRUTE_NN_MAX) ? tgt->n : 0; T.pts = tgt->pts; T.normals = plane ? tgt->normals : nullptr;
     T.bvh.n = 0; T.bvh.nleaf = 0; T.bvh.boxes = nullptr; T.bvh.pts = nullptr;
+    // every query's neighbour at its last search: the next search starts from it (RTR_ICP_WARM=0: thread-per-query kernels search cold)
+    static const bool warm_large = []() { const char* e = getenv("RTR_ICP_WARM"); return !(e && e[0] == '0'); }();
     int* nn_prev = nullptr;
-    if (warp_per_query) if (int e = tmp_alloc(ctx, &nn_prev, n, "icp")) return e;
+    if (warp_per_query || warm_large) if (int e = tmp_alloc(ctx, &nn_prev, std::max(n, 1), "icp")) return e;
+    if (!warp_per_query && nn_prev) RTR_CHECK(cudaMemsetAsync(nn_prev, 0xFF, (size_t)std::max(n, 1) * sizeof(int), ctx->stream), "icp");      // -1: no neighbour yet
     // small targets (every scan the reference ships): the warp-per-query kernels search a two-level hierarchy of the target
     if (warp_per_query && tgt->n >= 1 && tgt->n <= WBVH_MAX_POINTS && icp_hierarchy_pays(n, p->max_iterations))
         if (int e = wbvh_build_dev(ctx, tgt->pts, tgt->n, 0, tgt->bb_min, tgt->bb_max, &T.bvh)) return e;
@@ -1481,14 +1520,15 @@ int rtr_icp_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_icp_params* p, const f
                 if (plane) launch_pdl(k_icp_corr_warp<1>, nbw, ICPW_WARPS * 32, 0, ctx->stream, T, cur, nn_prev, n, st, dmax2, prune2, partials, ticket, sa);
                 else launch_pdl(k_icp_corr_warp<0>, nbw, ICPW_WARPS * 32, 0, ctx->stream, T, cur, nn_prev, n, st, dmax2, prune2, partials, ticket, sa);
             } else {
-                if (plane) launch_pdl(k_icp_corr<1>, nb, ICP_THREADS, 0, ctx->stream, v, vc, bb, far2, (const float4*)tgt->normals, cur, n, st, dmax2, prune2, partials, ticket, sa, W, (const float4*)tgt->pts);
-                else launch_pdl(k_icp_corr<0>, nb, ICP_THREADS, 0, ctx->stream, v, vc, bb, far2, (const float4*)nullptr, cur, n, st, dmax2, prune2, partials, ticket, sa, W, (const float4*)tgt->pts);
+                if (plane) launch_pdl(k_icp_corr<1>, nb, ICP_THREADS, 0, ctx->stream, v, vc, bb, far2, (const float4*)tgt->normals, cur, n, st, dmax2, prune2, partials, ticket, sa, W, (const float4*)tgt->pts, nn_prev);
+                else launch_pdl(k_icp_corr<0>, nb, ICP_THREADS, 0, ctx->stream, v, vc, bb, far2, (const float4*)nullptr, cur, n, st, dmax2, prune2, partials, ticket, sa, W, (const float4*)tgt->pts, nn_prev);
             }
             RTR_LAUNCH_CHECK(ctx, "icp.corr");
         }
     }
     if (warp_per_query) launch_pdl(k_icp_fitness_warp, nbw, ICPW_WARPS * 32, 0, ctx->stream, T, src_pts, (const float4*)cur, (const int*)nn_prev, n, (const IcpState*)st, partials, ticket, d_result, init_from_result);
-    else launch_pdl(k_icp_fitness, nb, ICP_THREADS, 0, ctx->stream, v, vc, bb, far2, src_pts, n, (const IcpState*)st, partials, ticket, d_result, init_from_result, W);
+    else launch_pdl(k_icp_fitness, nb, ICP_THREADS, 0, ctx->stream, v, vc, bb, far2, src_pts, n, (const IcpState*)st, partials, ticket, d_result, init_from_result, W, (const float4*)tgt->pts,
+                    (const int*)nn_prev);
     RTR_LAUNCH_CHECK(ctx, "icp.fitness");
     dev_free(ctx, cur); dev_free(ctx, src2); dev_free(ctx, st); dev_free(ctx, partials); dev_free(ctx, ticket); dev_free(ctx, nn_prev);
     return 0;

@@ -932,8 +932,9 @@ def test_wide_hierarchy_nearest_is_the_brute_force_answer(api, gpu_ctx, orc, clo
 @pytest.mark.gpu
 def test_icp_far_queries_hierarchy_and_coarse_grid_give_the_same_record(api, gpu_ctx):
     """Large sources (>= 65 536 points) whose box sticks out of the target's: the far queries of k_icp_corr / k_icp_fitness go through
-    the 32-ary hierarchy; RTR_ICP_WIDE=0 sends them through the coarse grid instead.  Both searches are exact and the sums are taken
-    in the same shape: the records agree bit for bit — uncapped (PCL's default) and capped."""
+    the 32-ary hierarchy; RTR_ICP_WIDE=0 sends them through the coarse grid instead; RTR_ICP_WARM=0 starts every search cold instead
+    of from the query's previous neighbour.  All searches are exact and the sums are taken in the same shape: the records agree bit
+    for bit — uncapped (PCL's default) and capped."""
     import subprocess, sys, json
     code = ("import sys, json; sys.path.insert(0, %r)\n"
             "import numpy as np\n"
@@ -952,12 +953,12 @@ def test_icp_far_queries_hierarchy_and_coarse_grid_give_the_same_record(api, gpu
             "    out.append(bytes(r).hex())\n"
             "print(json.dumps(out))\n") % ROOT
     outs = []
-    for wide in ("1", "0"):
-        env = dict(os.environ, RTR_ICP_WIDE=wide)
+    for wide, warm in (("1", "1"), ("0", "1"), ("1", "0"), ("0", "0")):
+        env = dict(os.environ, RTR_ICP_WIDE=wide, RTR_ICP_WARM=warm)
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
-    assert outs[0] == outs[1]
+    assert outs[0] == outs[1] == outs[2] == outs[3]
 
 
 @pytest.mark.gpu
