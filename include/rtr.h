@@ -290,6 +290,20 @@ int rtr_register_many_end(rtr_context* ctx, rtr_pose_result* host_results, int c
  * back with the records (up to 64 per cloud; *n_keypoints is the full count, RTR_ERR_CAPACITY if not all fit). */
 int rtr_register_many_keypoints(rtr_context* ctx, int member, float* host_kp_xyz1, int capacity, int* n_keypoints);
 
+/* The reference's OFFLINE / ONLINE split.  Its commented-out second main (RealTimeRobot.cpp:124-165, "time to preprocess one
+ * database model") builds every database model's keypoints and descriptors once; the live main (:45-104) does the per-scan work
+ * against them.  rtr_cloud_prepare is the offline half: normals, Harris corners and FPFH rows of one cloud, computed with the
+ * stage parameters of *p (normal_radius, harris_*, fpfh_radius) and kept on the cloud until rtr_cloud_reset / rtr_cloud_free.
+ * rtr_register_prepared is the online half of rtr_register_many: every model must have been prepared with the same stage
+ * parameters (RTR_ERR_NOT_READY otherwise); the scan's stages run inside the call, once (or not at all if the scan was prepared
+ * too); then descriptor matching, RANSAC and ICP for all models in shared launches.  host_results[m] is what
+ * rtr_register_many / rtr_register return for that model, bit for bit.  At most 31 models per _begin; rtr_register_prepared
+ * takes any number (batches of 31).  _begin is completed by rtr_register_many_end; rtr_register_many_keypoints works as above. */
+int rtr_cloud_prepare(rtr_cloud* cloud, const rtr_register_params* p);
+int rtr_register_prepared(rtr_cloud* const* models, int n_models, rtr_cloud* scene, const rtr_register_params* p,
+                          rtr_pose_result* host_results);
+int rtr_register_prepared_begin(rtr_cloud* const* models, int n_models, rtr_cloud* scene, const rtr_register_params* p);
+
 /* ------------------------------------------------------------------ multi-GPU: one small all-gather
  * The path shards by candidate model cloud (rank r registers its models against the replicated scan) and by RANSAC hypothesis
  * range [hypothesis_begin, hypothesis_end); the only exchange is ONE ncclAllGather of the 128-byte records.  One process per

@@ -21,6 +21,7 @@ EXPORTS = [
     "rtr_native_pair_scores", "rtr_native_register", "rtr_plane_areas", "rtr_pcd_info", "rtr_pcd_read", "rtr_pcd_load", "rtr_pcd_write",
     "rtr_cloud_save", "rtr_register_begin", "rtr_register_host_begin", "rtr_register_end", "rtr_context_create_prio",
     "rtr_register_many", "rtr_register_many_host", "rtr_register_many_begin", "rtr_register_many_host_begin", "rtr_register_many_end",
+    "rtr_cloud_prepare", "rtr_register_prepared", "rtr_register_prepared_begin",
     "rtr_register_many_keypoints", "rtr_comm_unique_id", "rtr_comm_init", "rtr_comm_destroy", "rtr_comm_world", "rtr_allgather_results",
     "rtr_select_best_hypothesis", "rtr_normals_mode", "rtr_comm_gather_batches", "rtr_gathered_results",
 ]
@@ -88,6 +89,9 @@ def lib():
         L.rtr_register_many.argtypes = [C.POINTER(vp), C.c_int, vp, C.POINTER(RegisterParams), C.POINTER(PoseResult)]
         L.rtr_register_many_host.argtypes = [vp, C.POINTER(vp), ip, C.c_int, vp, C.c_int, C.POINTER(RegisterParams), C.POINTER(PoseResult)]
         L.rtr_register_many_begin.argtypes = [C.POINTER(vp), C.c_int, vp, C.POINTER(RegisterParams)]
+        L.rtr_cloud_prepare.argtypes = [vp, C.POINTER(RegisterParams)]
+        L.rtr_register_prepared.argtypes = [C.POINTER(vp), C.c_int, vp, C.POINTER(RegisterParams), C.POINTER(PoseResult)]
+        L.rtr_register_prepared_begin.argtypes = [C.POINTER(vp), C.c_int, vp, C.POINTER(RegisterParams)]
         L.rtr_register_many_host_begin.argtypes = [vp, C.POINTER(vp), ip, C.c_int, vp, C.c_int, C.POINTER(RegisterParams)]
         L.rtr_register_many_end.argtypes = [vp, C.POINTER(PoseResult), C.c_int]
         L.rtr_register_many_keypoints.argtypes = [vp, C.c_int, vp, C.c_int, ip]

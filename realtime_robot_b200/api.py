@@ -160,6 +160,11 @@ class Cloud:
         """pcl::io::savePCDFileASCII (mode 0) / binary (1) / binary_compressed (2) of the device cloud."""
         _lib.check("rtr_cloud_save", _lib.lib().rtr_cloud_save(self._h, os.fsencode(path), mode))
 
+    def prepare(self, params: RegisterParams) -> None:
+        """The offline half (RealTimeRobot.cpp:124-165): normals, Harris corners and FPFH rows with the stage parameters of
+        `params`, kept on the cloud until reset() / free() — what register_prepared expects of every model."""
+        _lib.check("rtr_cloud_prepare", _lib.lib().rtr_cloud_prepare(self._h, C.byref(params)))
+
     def reset(self):
         """Forget every cached stage (the points stay resident)."""
         _lib.check("rtr_cloud_reset", _lib.lib().rtr_cloud_reset(self._h))
@@ -288,6 +293,24 @@ def register_many(models, scene: Cloud, params: RegisterParams):
     res = (PoseResult * k)()
     _lib.check("rtr_register_many", _lib.lib().rtr_register_many(handles, k, scene._h, C.byref(params), res))
     return _records(res, k)
+
+
+def register_prepared(models, scene: Cloud, params: RegisterParams):
+    """The online half of register_many: every model went through Cloud.prepare(params); the scan's stages run here, once.
+    Same records as register_many / register, bit for bit."""
+    k = len(models)
+    handles = (C.c_void_p * k)(*[m._h for m in models])
+    res = (PoseResult * k)()
+    _lib.check("rtr_register_prepared", _lib.lib().rtr_register_prepared(handles, k, scene._h, C.byref(params), res))
+    return _records(res, k)
+
+
+def register_prepared_begin(models, scene: Cloud, params: RegisterParams) -> None:
+    """Enqueue only (at most 31 models); register_many_end(ctx) waits and returns the records."""
+    k = len(models)
+    handles = (C.c_void_p * k)(*[m._h for m in models])
+    scene.ctx._inflight_many = k
+    _lib.check("rtr_register_prepared_begin", _lib.lib().rtr_register_prepared_begin(handles, k, scene._h, C.byref(params)))
 
 
 def _host_batch(models_xyz1, scene_xyz1):

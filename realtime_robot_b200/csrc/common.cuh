@@ -170,6 +170,12 @@ struct rtr_cloud {
     const rtr_cloud* knn_target = nullptr;   long long knn_target_gen = -1;
     long long feature_gen = 0;                // process-wide unique stamp, renewed whenever this cloud's FPFH rows are recomputed or dropped
     int n_keypoints = -1;
+    // rtr_cloud_prepare (the offline phase, RealTimeRobot.cpp:124-165): normals, Harris corners and FPFH rows stay on the cloud
+    // together with the stage parameters they were computed with; kp_xyz holds the first RTR_KP_PREVIEW corners, kp_count their number
+    bool prepared = false;
+    float prep_normal_radius = 0.f, prep_harris_radius = 0.f, prep_harris_threshold = 0.f, prep_fpfh_radius = 0.f;
+    int prep_harris_nms = 0, prep_harris_refine = 0;
+    float4* kp_xyz = nullptr;    int* kp_count = nullptr;
     // A model set (rtr_register_many): the points of several clouds concatenated, seg_begin[k] .. seg_begin[k+1] is cloud k
     // (size nseg + 1; empty for an ordinary cloud).  Every per-point stage then runs on all member clouds in one launch,
     // through segmented grids; outputs (normals, response, FPFH) are concatenated in the same order.

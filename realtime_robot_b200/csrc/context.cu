@@ -422,6 +422,7 @@ void rtr_invalidate(rtr_cloud* c) {
     dev_free(ctx, c->fpfh); c->fpfh = nullptr; c->fpfh_radius = -1.f; c->feature_gen = rtr_next_generation();
     dev_free(ctx, c->knn); c->knn = nullptr; dev_free(ctx, c->knn_dist); c->knn_dist = nullptr; c->knn_k = 0; c->knn_target = nullptr;
     c->n_keypoints = -1;
+    dev_free(ctx, c->kp_xyz); c->kp_xyz = nullptr; dev_free(ctx, c->kp_count); c->kp_count = nullptr; c->prepared = false;
 }
 
 float rtr_icp_cell(const rtr_cloud* c) {

@@ -1554,11 +1554,14 @@ __global__ void k_icp_init_many(const __grid_constant__ IcpMany im, const float4
     }
 }
 
-static int icp_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const rtr_icp_params* p, rtr_pose_result* d_results) {
+// scan: nullptr — the target is member tgt_seg of the set, searched through the set's grids, neighbours named by set-wide index;
+// or the scan as a cloud of its own (prepared path: the set carries no grids and no normals) — its own grids and normals,
+// neighbours named by the scan's local index.  Lowest-index tie-breaking is the same in either index space: same records.
+static int icp_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const rtr_icp_params* p, rtr_pose_result* d_results, rtr_cloud* scan = nullptr) {
     RtrRange nvtx_range("rtr.icp.many");
     rtr_context* ctx = set->ctx;
     if (p->estimator != 0 && p->estimator != 1) return rtr_fail("icp", "estimator must be 0 (SVD) or 1 (point-to-plane LLS)", RTR_ERR_INVALID);
-    if (p->estimator == 1 && !set->normals) return rtr_fail("icp", "estimator 1 (point-to-plane) needs normals on the target", RTR_ERR_NOT_READY);
+    if (p->estimator == 1 && !(scan ? scan->normals : set->normals)) return rtr_fail("icp", "estimator 1 (point-to-plane) needs normals on the target", RTR_ERR_NOT_READY);
     const int t0 = set->seg_begin[tgt_seg], nt = set->seg_begin[tgt_seg + 1] - t0;
     const int n_src = set->seg_begin[n_models];
     // target search structure: scans up to RTR_BRUTE_NN_MAX points are searched without one (the kernels only stride over the
@@ -1577,17 +1580,19 @@ static int icp_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const rtr_icp
         // the repo scans against ~400 for the 0.10 FPFH grid, which made the warm start no faster than the brute-force pass)
         DevGrid* g = nullptr;
         const float lo = want * (cap == want ? 1.0f : 0.4f), hi = want * 1.7f;
-        for (auto& kv : set->grids) { DevGrid& c = kv.second; if (c.h >= lo && c.h <= hi && (!g || c.h < g->h)) g = &c; }
-        if (!g) if (int e = rtr_get_grid(set, want, &g)) return e;
-        v = rtr_segment_view(g, set, tgt_seg);
+        rtr_cloud* owner = scan ? scan : set;
+        for (auto& kv : owner->grids) { DevGrid& c = kv.second; if (c.h >= lo && c.h <= hi && (!g || c.h < g->h)) g = &c; }
+        if (!g) if (int e = rtr_get_grid(owner, want, &g)) return e;
+        v = scan ? rtr_view(g) : rtr_segment_view(g, set, tgt_seg);
     }
+    const int idx_base = scan ? 0 : t0;       // index space of the neighbours: the scan's own, or the set's
     IcpTarget T;
-    T.g = v; T.brute = v.sorted + t0; T.brute_n = (nt <= RTR_BRUTE_NN_MAX) ? nt : 0;     // the scan's slice of the cell-ordered copy
-    T.pts = set->pts; T.normals = (p->estimator == 1) ? set->normals : nullptr;
+    T.g = v; T.brute = v.sorted + idx_base; T.brute_n = (nt <= RTR_BRUTE_NN_MAX) ? nt : 0;     // the scan's (slice of the) cell-ordered copy
+    T.pts = set->pts + (t0 - idx_base); T.normals = (p->estimator == 1) ? (scan ? scan->normals : set->normals) : nullptr;
     T.bvh.n = 0; T.bvh.nleaf = 0; T.bvh.boxes = nullptr; T.bvh.pts = nullptr;
-    // small scans: the warp-per-query kernels search a two-level hierarchy of the scan (indices reported set-wide: + t0)
+    // small scans: the warp-per-query kernels search a two-level hierarchy of the scan (indices reported in the same space)
     if (nt >= 1 && nt <= WBVH_MAX_POINTS && icp_hierarchy_pays(n_src, p->max_iterations))
-        if (int e = wbvh_build_dev(ctx, set->pts + t0, nt, t0, &set->seg_bb[6 * tgt_seg], &set->seg_bb[6 * tgt_seg + 3], &T.bvh)) return e;
+        if (int e = wbvh_build_dev(ctx, set->pts + t0, nt, idx_base, &set->seg_bb[6 * tgt_seg], &set->seg_bb[6 * tgt_seg + 3], &T.bvh)) return e;
     IcpMany im;
     memset(&im, 0, sizeof(im));
     im.nseg = n_models;
@@ -1676,43 +1681,20 @@ __global__ void k_register_finish_many(const __grid_constant__ IcpMany im, rtr_p
     for (int i = threadIdx.x; i < min(cnt, RTR_KP_PREVIEW); i += blockDim.x) preview[k].xyz[i] = kp_xyz_all[first + i];
 }
 
-// set: n_models + 1 members, the scan last.  Queues everything on the context's stream, ends with the D2H of the records
-// (and the corner previews) into the context's pinned area.
-static int register_many_enqueue(rtr_cloud* set, int n_models, const rtr_register_params* p) {
-    RtrRange nvtx_range("rtr.register_many");
+// Second half of a batch, from the descriptor rows on: correspondences, prerejective RANSAC, ICP, the finishing kernel and the
+// D2H of the records (and the corner previews) into the context's pinned area.  d_cnt / d_xyz: corner count per member and
+// corner coordinates (member k's list starts at its first point index); join: waits for whatever produced them on the second
+// stream.  scan: see icp_many_dev.
+struct JoinGuard {
+    rtr_context* ctx; bool fork; bool joined;
+    void join() { if (fork && !joined) { cudaStreamWaitEvent(ctx->stream, ctx->join_event, 0); joined = true; } }
+    ~JoinGuard() { join(); }
+};
+static int register_many_back(rtr_cloud* set, int n_models, const rtr_register_params* p, const int* d_cnt, const float4* d_xyz, JoinGuard& join_guard,
+                              rtr_cloud* scan) {
     rtr_context* ctx = set->ctx;
     const int tgt = n_models, nseg = n_models + 1;
-    for (int k = 0; k < nseg; ++k)
-        if (set->seg_begin[k + 1] - set->seg_begin[k] >= 65536) return rtr_fail("register_many", "member clouds of a model set hold fewer than 65536 points", RTR_ERR_INVALID);
     const int n_src = set->seg_begin[n_models], nt = set->n - n_src;
-    float cells[3] = {p->normal_radius, p->fpfh_radius, p->harris_radius};
-    DevGrid* gs[3];
-    if (int e = rtr_get_grids(set, cells, p->harris_radius == p->normal_radius ? 2 : 3, gs)) return e;
-    if (int e = rtr_normals_dev(set, p->normal_radius)) return e;
-    // Harris (response, NMS, corner lists, refinement) needs only the normals and feeds nothing but the records' corner
-    // counts and previews: it runs on the context's second stream beside FPFH / matching / RANSAC / ICP and is joined before
-    // the finishing kernel.  Temporaries come from the bump arena, which hands nothing out twice inside one entry point.
-    int* d_idx = nullptr; float4* d_xyz = nullptr; int* d_cnt = nullptr;
-    const bool fork = !ctx->profile && ctx->aux_stream;
-    cudaStream_t main_stream = ctx->stream;
-    if (fork) {
-        RTR_CHECK(cudaEventRecord(ctx->fork_event, main_stream), "register_many.fork");
-        RTR_CHECK(cudaStreamWaitEvent(ctx->aux_stream, ctx->fork_event, 0), "register_many.fork");
-        ctx->stream = ctx->aux_stream;
-    }
-    int eh = rtr_harris_dev(set, p->harris_radius, p->harris_threshold, p->harris_nms, p->harris_refine, &d_idx, &d_xyz, &d_cnt);
-    ctx->stream = main_stream;
-    if (fork) {
-        cudaEventRecord(ctx->join_event, ctx->aux_stream);
-        // error paths below must not leave the second stream running behind a freed set: every return waits for the join
-    }
-    struct JoinGuard {
-        rtr_context* ctx; bool fork; bool joined;
-        void join() { if (fork && !joined) { cudaStreamWaitEvent(ctx->stream, ctx->join_event, 0); joined = true; } }
-        ~JoinGuard() { join(); }
-    } join_guard{ctx, fork, false};
-    if (eh) return eh;
-    if (int e = rtr_fpfh_dev(set, p->fpfh_radius)) return e;
     const int k = p->ransac.correspondence_k;
     int* knn = nullptr; float* knn_dist = nullptr;
     if (int e = tmp_alloc(ctx, &knn, (size_t)n_src * k, "register_many")) return e;
@@ -1722,7 +1704,7 @@ static int register_many_enqueue(rtr_cloud* set, int n_models, const rtr_registe
     if (int e = tmp_alloc(ctx, &d_res, n_models, "register_many")) return e;
     if (int e = tmp_alloc(ctx, &d_prev, nseg, "register_many")) return e;
     if (int e = ransac_many_dev(set, n_models, tgt, knn, k, &p->ransac, d_res)) return e;
-    if (p->run_icp) if (int e = icp_many_dev(set, n_models, tgt, &p->icp, d_res)) return e;
+    if (p->run_icp) if (int e = icp_many_dev(set, n_models, tgt, &p->icp, d_res, scan)) return e;
     IcpMany im;
     memset(&im, 0, sizeof(im));
     im.nseg = n_models;
@@ -1742,6 +1724,144 @@ static int register_many_enqueue(rtr_cloud* set, int n_models, const rtr_registe
         ctx->gathered_records = n_models * (ctx->comm ? ctx->comm_world : 1);
     }
     return 0;
+}
+
+// set: n_models + 1 members, the scan last.  Queues everything on the context's stream.
+static int register_many_enqueue(rtr_cloud* set, int n_models, const rtr_register_params* p) {
+    RtrRange nvtx_range("rtr.register_many");
+    rtr_context* ctx = set->ctx;
+    const int nseg = n_models + 1;
+    for (int k = 0; k < nseg; ++k)
+        if (set->seg_begin[k + 1] - set->seg_begin[k] >= 65536) return rtr_fail("register_many", "member clouds of a model set hold fewer than 65536 points", RTR_ERR_INVALID);
+    float cells[3] = {p->normal_radius, p->fpfh_radius, p->harris_radius};
+    DevGrid* gs[3];
+    if (int e = rtr_get_grids(set, cells, p->harris_radius == p->normal_radius ? 2 : 3, gs)) return e;
+    if (int e = rtr_normals_dev(set, p->normal_radius)) return e;
+    // Harris (response, NMS, corner lists, refinement) needs only the normals and feeds nothing but the records' corner
+    // counts and previews: it runs on the context's second stream beside FPFH / matching / RANSAC / ICP and is joined before
+    // the finishing kernel.  Temporaries come from the bump arena, which hands nothing out twice inside one entry point.
+    int* d_idx = nullptr; float4* d_xyz = nullptr; int* d_cnt = nullptr;
+    const bool fork = !ctx->profile && ctx->aux_stream;
+    cudaStream_t main_stream = ctx->stream;
+    if (fork) {
+        RTR_CHECK(cudaEventRecord(ctx->fork_event, main_stream), "register_many.fork");
+        RTR_CHECK(cudaStreamWaitEvent(ctx->aux_stream, ctx->fork_event, 0), "register_many.fork");
+        ctx->stream = ctx->aux_stream;
+    }
+    int eh = rtr_harris_dev(set, p->harris_radius, p->harris_threshold, p->harris_nms, p->harris_refine, &d_idx, &d_xyz, &d_cnt);
+    ctx->stream = main_stream;
+    if (fork) cudaEventRecord(ctx->join_event, ctx->aux_stream);
+    // error paths below must not leave the second stream running behind a freed set: every return waits for the join
+    JoinGuard join_guard{ctx, fork, false};
+    if (eh) return eh;
+    if (int e = rtr_fpfh_dev(set, p->fpfh_radius)) return e;
+    return register_many_back(set, n_models, p, d_cnt, d_xyz, join_guard, nullptr);
+}
+
+// ---- prepared clouds: the reference's offline / online split (RealTimeRobot.cpp:124-165 builds every database model's
+// keypoints and descriptors once; :45-104 does the per-scan work) --------------------------------------------------------
+static bool prepared_with(const rtr_cloud* c, const rtr_register_params* p) {
+    return c->prepared && c->normals && c->fpfh && c->kp_xyz && c->kp_count && c->prep_normal_radius == p->normal_radius &&
+           c->prep_harris_radius == p->harris_radius && c->prep_harris_threshold == p->harris_threshold && c->prep_harris_nms == p->harris_nms &&
+           c->prep_harris_refine == p->harris_refine && c->prep_fpfh_radius == p->fpfh_radius && c->normals_mode == 0;
+}
+__global__ void k_store_corners(const int* __restrict__ cnt, const float4* __restrict__ xyz, int* __restrict__ cnt_out, float4* __restrict__ xyz_out) {
+    const int c = *cnt;
+    if (threadIdx.x == 0) *cnt_out = c;
+    for (int i = threadIdx.x; i < min(c, RTR_KP_PREVIEW); i += blockDim.x) xyz_out[i] = xyz[i];
+}
+// Normals, Harris corners and FPFH rows of one cloud, kept on the cloud.  fork_harris: the corner stage runs on the context's
+// second stream (the caller joins before it reads kp_count / kp_xyz).
+static int cloud_prepare_dev(rtr_cloud* c, const rtr_register_params* p, bool fork_harris) {
+    rtr_context* ctx = c->ctx;
+    if (prepared_with(c, p)) return 0;
+    if (c->nseg() > 0) return rtr_fail("prepare", "a model set cannot be prepared", RTR_ERR_INVALID);
+    c->prepared = false;
+    if (int e = rtr_ensure_bbox(c)) return e;
+    if (int e = rtr_normals_dev(c, p->normal_radius)) return e;
+    if (!c->kp_xyz) if (int e = dev_alloc(ctx, &c->kp_xyz, RTR_KP_PREVIEW, "prepare")) return e;
+    if (!c->kp_count) if (int e = dev_alloc(ctx, &c->kp_count, 1, "prepare")) return e;
+    cudaStream_t main_stream = ctx->stream;
+    if (fork_harris) {
+        RTR_CHECK(cudaEventRecord(ctx->fork_event, main_stream), "prepare.fork");
+        RTR_CHECK(cudaStreamWaitEvent(ctx->aux_stream, ctx->fork_event, 0), "prepare.fork");
+        ctx->stream = ctx->aux_stream;
+    }
+    int* d_idx = nullptr; float4* d_xyz = nullptr; int* d_cnt = nullptr;
+    int eh = rtr_harris_dev(c, p->harris_radius, p->harris_threshold, p->harris_nms, p->harris_refine, &d_idx, &d_xyz, &d_cnt);
+    if (!eh) {
+        k_store_corners<<<1, 64, 0, ctx->stream>>>(d_cnt, d_xyz, c->kp_count, c->kp_xyz);
+        ctx->launches++;
+        if (ctx->profile) rtr_prof_mark(ctx, "prepare.corners");
+        if (cudaGetLastError() != cudaSuccess) eh = RTR_ERR_INVALID;
+    }
+    ctx->stream = main_stream;
+    if (fork_harris) cudaEventRecord(ctx->join_event, ctx->aux_stream);
+    if (eh) { if (fork_harris) cudaStreamWaitEvent(main_stream, ctx->join_event, 0); return eh; }
+    if (int e = rtr_fpfh_dev(c, p->fpfh_radius)) { if (fork_harris) cudaStreamWaitEvent(main_stream, ctx->join_event, 0); return e; }
+    c->prepared = true;
+    c->prep_normal_radius = p->normal_radius; c->prep_harris_radius = p->harris_radius; c->prep_harris_threshold = p->harris_threshold;
+    c->prep_harris_nms = p->harris_nms; c->prep_harris_refine = p->harris_refine; c->prep_fpfh_radius = p->fpfh_radius;
+    return 0;
+}
+struct PrepTable {
+    int nseg; int begin[RTR_MAX_SEGMENTS + 1];
+    const float* fpfh[RTR_MAX_SEGMENTS]; const float4* kp_xyz[RTR_MAX_SEGMENTS]; const int* kp_cnt[RTR_MAX_SEGMENTS];
+};
+// descriptor rows of all members, concatenated in member order
+__global__ void k_concat_rows(const __grid_constant__ PrepTable t, float* __restrict__ fpfh) {
+    const long long total = (long long)t.begin[RTR_MAX_SEGMENTS] * 33;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / 33);
+        int k = 0;
+#pragma unroll
+        for (int step = RTR_MAX_SEGMENTS / 2; step > 0; step >>= 1) if (i >= t.begin[k + step]) k += step;
+        fpfh[e] = __ldg(t.fpfh[k] + (e - (long long)t.begin[k] * 33));
+    }
+}
+// corner counts and previews of all members in the layout k_register_finish_many reads (member k's list at its first point)
+__global__ void k_gather_corners(const __grid_constant__ PrepTable t, int* __restrict__ cnt, float4* __restrict__ xyz_all) {
+    const int k = blockIdx.x;
+    const int c = *t.kp_cnt[k];
+    if (threadIdx.x == 0) cnt[k] = c;
+    for (int i = threadIdx.x; i < min(c, RTR_KP_PREVIEW); i += blockDim.x) xyz_all[t.begin[k] + i] = t.kp_xyz[k][i];
+}
+// The online phase: every model is prepared (same stage parameters); the scan's stages run here, once; then the second half of
+// a batch.  set: the points of models + scan (rtr_model_set_from_clouds); it receives the concatenated descriptor rows.
+static int register_prepared_enqueue(rtr_cloud* set, rtr_cloud* const* members, int n_models, const rtr_register_params* p) {
+    RtrRange nvtx_range("rtr.register_prepared");
+    rtr_context* ctx = set->ctx;
+    const int nseg = n_models + 1;
+    rtr_cloud* scan = members[n_models];
+    const bool fork = !ctx->profile && ctx->aux_stream && !prepared_with(scan, p);
+    int es = cloud_prepare_dev(scan, p, fork);
+    JoinGuard join_guard{ctx, fork, false};
+    if (es) return es;
+    PrepTable t;
+    memset(&t, 0, sizeof(t));
+    t.nseg = nseg;
+    for (int k = 0; k <= RTR_MAX_SEGMENTS; ++k) t.begin[k] = k < nseg ? set->seg_begin[k] : set->n;
+    for (int k = 0; k < nseg; ++k) { t.fpfh[k] = members[k]->fpfh; t.kp_xyz[k] = members[k]->kp_xyz; t.kp_cnt[k] = members[k]->kp_count; }
+    if (int e = dev_alloc(ctx, &set->fpfh, (size_t)set->n * 33, "register_prepared")) return e;
+    set->fpfh_radius = p->fpfh_radius;
+    if (set->n > 0) {
+        k_concat_rows<<<std::max(1, std::min(nblk((long long)set->n * 33, 256), 8 * ctx->sm_count)), 256, 0, ctx->stream>>>(t, set->fpfh);
+        RTR_LAUNCH_CHECK(ctx, "set.concat_rows");
+    }
+    int* d_cnt = nullptr; float4* d_xyz = nullptr;
+    if (int e = tmp_alloc(ctx, &d_cnt, nseg, "register_prepared")) return e;
+    if (int e = tmp_alloc(ctx, &d_xyz, std::max(set->n, 1), "register_prepared")) return e;
+    // the corners are only read by the finishing kernel: gathered on the second stream behind the scan's corner stage when forked
+    if (fork) {
+        k_gather_corners<<<nseg, 64, 0, ctx->aux_stream>>>(t, d_cnt, d_xyz);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) return RTR_ERR_INVALID;
+        cudaEventRecord(ctx->join_event, ctx->aux_stream);
+    } else {
+        k_gather_corners<<<nseg, 64, 0, ctx->stream>>>(t, d_cnt, d_xyz);
+        RTR_LAUNCH_CHECK(ctx, "set.corners");
+    }
+    return register_many_back(set, n_models, p, d_cnt, d_xyz, join_guard, scan);
 }
 
 static bool many_shape_ok(const int* ns, int n_models, int n_scene, const rtr_register_params* p) {
@@ -1801,6 +1921,60 @@ int rtr_register_many_host_begin(rtr_context* ctx, const float* const* host_mode
     rtr_cloud* set = nullptr;
     if (int e = rtr_model_set_from_host(ctx, ptrs, ns, n_models + 1, &set)) return e;
     return register_many_begin_set(ctx, set, n_models, p);
+}
+
+// ---- the offline / online split ------------------------------------------------------------------------------------------
+int rtr_cloud_prepare(rtr_cloud* c, const rtr_register_params* p) {
+    if (!c || !p) return rtr_fail("prepare", "bad argument", RTR_ERR_INVALID);
+    if (int e = rtr_validate_register_params(p)) return e;
+    rtr_context* ctx = c->ctx;
+    if (ctx->register_pending) return rtr_fail("prepare", "a registration is in flight on this context", RTR_ERR_INVALID);
+    RTR_CHECK(cudaSetDevice(ctx->device), "prepare");
+    TmpScope tmp_scope(ctx);
+    return cloud_prepare_dev(c, p, false);
+}
+
+int rtr_register_prepared_begin(rtr_cloud* const* models, int n_models, rtr_cloud* scene, const rtr_register_params* p) {
+    if (!models || !scene || !p || n_models < 1) return rtr_fail("register_prepared", "bad argument", RTR_ERR_INVALID);
+    if (int e = rtr_validate_register_params(p)) return e;
+    rtr_context* ctx = scene->ctx;
+    if (ctx->register_pending) return rtr_fail("register_prepared", "a registration is already in flight on this context", RTR_ERR_INVALID);
+    if (n_models > RTR_MAX_SEGMENTS - 1) return rtr_fail("register_prepared", "at most 31 models per batch", RTR_ERR_INVALID);
+    int ns[RTR_MAX_SEGMENTS];
+    rtr_cloud* members[RTR_MAX_SEGMENTS];
+    for (int k = 0; k < n_models; ++k) {
+        if (!models[k] || models[k]->ctx != ctx || models[k] == scene) return rtr_fail("register_prepared", "models and scene must be distinct clouds of one context", RTR_ERR_INVALID);
+        if (!prepared_with(models[k], p)) return rtr_fail("register_prepared", "every model needs rtr_cloud_prepare with these stage parameters first", RTR_ERR_NOT_READY);
+        ns[k] = models[k]->n; members[k] = models[k];
+        if (ns[k] < 3) return rtr_fail("register_prepared", "models need at least 3 points", RTR_ERR_INVALID);
+    }
+    members[n_models] = scene;
+    if (scene->n < 1 || !many_shape_ok(ns, n_models, scene->n, p))
+        return rtr_fail("register_prepared", "batch shape not supported (empty scan, clouds >= 65536 points or > 2^20 hypotheses)", RTR_ERR_INVALID);
+    RTR_CHECK(cudaSetDevice(ctx->device), "register_prepared");
+    rtr_cloud* set = nullptr;
+    if (int e = rtr_model_set_from_clouds(ctx, members, n_models + 1, &set)) return e;
+    int e;
+    {
+        TmpScope tmp_scope(ctx);
+        e = register_prepared_enqueue(set, members, n_models, p);
+    }
+    if (e) { cudaStreamSynchronize(ctx->stream); rtr_cloud_free(set); return e; }
+    ctx->pending_cloud[0] = set;
+    ctx->register_pending = n_models;
+    ctx->many_models = n_models;
+    return 0;
+}
+
+int rtr_register_prepared(rtr_cloud* const* models, int n_models, rtr_cloud* scene, const rtr_register_params* p, rtr_pose_result* host_results) {
+    if (!models || !scene || !p || !host_results || n_models < 1) return rtr_fail("register_prepared", "bad argument", RTR_ERR_INVALID);
+    for (int m0 = 0; m0 < n_models; m0 += RTR_MAX_SEGMENTS - 1) {
+        const int nb = std::min(n_models - m0, RTR_MAX_SEGMENTS - 1);
+        if (int e = rtr_register_prepared_begin(models + m0, nb, scene, p)) return e;
+        if (int e = rtr_register_many_end(scene->ctx, host_results + m0, nb)) return e;
+        for (int k = 0; k < nb; ++k) host_results[m0 + k].model_id = m0 + k;
+    }
+    return 0;
 }
 
 int rtr_register_many_end(rtr_context* ctx, rtr_pose_result* host_results, int capacity) {

@@ -181,3 +181,59 @@ def test_cpp_reference_signatures_run_mains_loops(api, gpu_ctx, clouds):
     assert pairs == w.evaluated and pairs > 0
     assert np.abs(got - w.matrix()).max() < 1e-4
     cm.free(); cs.free()
+
+
+def test_register_prepared_is_the_online_half_of_register_many(api, gpu_ctx, clouds):
+    """rtr_cloud_prepare + rtr_register_prepared — the reference's offline / online split (RealTimeRobot.cpp:124-165 vs :45-104):
+    models prepared once, scans streamed against them.  Records, corner counts and corner previews equal rtr_register_many's bit for
+    bit, for a fresh scan, for a prepared scan, for a second scan against the same prepared models, and through _begin / _end."""
+    from realtime_robot_b200._lib import RtrError
+    p = default_register_params()
+    hosts = [load(clouds, m) for m in MODELS]
+    scenes = [clouds("mcloud"), clouds("T0_m8111")]
+    cms = [api.Cloud(gpu_ctx, h) for h in hosts]
+    fresh = [api.Cloud(gpu_ctx, h) for h in hosts]           # never prepared: the reference batch
+    # not prepared yet: refused, nothing computed silently
+    with pytest.raises(RtrError):
+        api.register_prepared(cms, api.Cloud(gpu_ctx, scenes[0]), p)
+    for c in cms:
+        c.prepare(p)
+    for scene in scenes:
+        cs = api.Cloud(gpu_ctx, scene)
+        l0 = gpu_ctx.launches
+        want = api.register_many(fresh, cs, p)
+        launches_many = gpu_ctx.launches - l0
+        want_kp = [api.register_many_keypoints(gpu_ctx, m) for m in range(len(MODELS) + 1)]
+        cs.free()
+        cs = api.Cloud(gpu_ctx, scene)                        # a fresh scan: its stages run inside the call
+        l0 = gpu_ctx.launches
+        got = api.register_prepared(cms, cs, p)
+        launches = gpu_ctx.launches - l0
+        got_kp = [api.register_many_keypoints(gpu_ctx, m) for m in range(len(MODELS) + 1)]
+        for name, a, b in zip(MODELS, got, want):
+            assert bytes(a) == bytes(b), name
+        for (ka, na), (kb, nb) in zip(got_kp, want_kp):
+            assert na == nb and np.array_equal(ka, kb)
+        again = api.register_prepared(cms, cs, p)             # the scan is prepared now: nothing of it is recomputed
+        api.register_prepared_begin(cms, cs, p)
+        halves = api.register_many_end(gpu_ctx)
+        for a, b, c in zip(got, again, halves):
+            assert bytes(a) == bytes(b) == bytes(c)
+        assert launches <= launches_many + 4, (launches, launches_many)     # the scan's stages + two gathers: no per-model launches
+        cs.free()
+    # other stage parameters than the models were prepared with: refused; reset() drops the preparation
+    q = default_register_params()
+    q.fpfh_radius = 0.08
+    cs = api.Cloud(gpu_ctx, scenes[0])
+    with pytest.raises(RtrError):
+        api.register_prepared(cms, cs, q)
+    cms[2].reset()
+    with pytest.raises(RtrError):
+        api.register_prepared(cms, cs, p)
+    cms[2].prepare(p)
+    got = api.register_prepared(cms[:3], cs, p)               # a subset of the database
+    want = api.register_many(fresh[:3], api.Cloud(gpu_ctx, scenes[0]), p)
+    for a, b in zip(got, want):
+        assert bytes(a) == bytes(b)
+    for c in cms + fresh + [cs]:
+        c.free()

@@ -1,7 +1,7 @@
 #!/bin/bash
 cd /root/repo
 export PYTHONUNBUFFERED=1
-for f in 0.7 1.0 1.4; do
-RTR_ICP_CELL_FACTOR=$f timeout 300 python tools/bench_icp.py --reps 3 >> gpurun_out/f_icp_cell.log 2>&1
-done
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/h_tests.log
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/h_bench.json 2> gpurun_out/h_bench.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/h_bench_ref.json 2> gpurun_out/h_bench_ref.err
 echo done
