@@ -11,6 +11,9 @@
 //   match_by_* screens, then Ransac(pairpoint, 50, cloud, mcloud) — what a maintainer's unchanged call sites execute.
 //   realtime_robot --database <scan.pcd> <model1.pcd> [<model2.pcd> ...] [--hypotheses N]
 //   registers every database model against the scan in one batch (registerModelsToScene -> rtr_register_many_host).
+//   realtime_robot --database-online <model1.pcd> [<model2.pcd> ...] --scans <scan1.pcd> [<scan2.pcd> ...] [--hypotheses N]
+//   the reference's offline / online split: every model preprocessed once (RealTimeRobot.cpp:124-165 -> ModelDatabase::add ->
+//   rtr_cloud_prepare), then each scan matched against the prepared database (:45-104 -> ModelDatabase::match).
 #include <chrono>
 #include <cstdlib>
 #include <iostream>
@@ -43,8 +46,44 @@ static int run_database(int argc, char** argv) {
     return 0;
 }
 
+static int run_database_online(int argc, char** argv) {
+    rtr_register_params p;
+    rtr_default_register_params(&p);
+    std::vector<std::string> model_files, scan_files;
+    bool scans = false;
+    for (int i = 2; i < argc; ++i) {
+        std::string a = argv[i];
+        if (a == "--hypotheses" && i + 1 < argc) { p.ransac.max_iterations = atoll(argv[++i]); continue; }
+        if (a == "--scans") { scans = true; continue; }
+        (scans ? scan_files : model_files).push_back(a);
+    }
+    if (model_files.empty() || scan_files.empty()) return 2;
+    ModelDatabase db(p);
+    auto start = std::chrono::steady_clock::now();
+    for (const std::string& f : model_files) {
+        pcl::PointCloud<pcl::PointXYZ> m;
+        if (pcl::io::loadPCDFile(f, m) != 0 || !db.add(m)) return 1;
+    }
+    std::cout << "time to preprocess " << db.size() << " database models : " << std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count() << std::endl;    // RealTimeRobot.cpp:164
+    for (const std::string& f : scan_files) {
+        pcl::PointCloud<pcl::PointXYZ> scan;
+        if (pcl::io::loadPCDFile(f, scan) != 0) return 1;
+        start = std::chrono::steady_clock::now();
+        std::vector<Eigen::Matrix4f> poses;
+        std::vector<rtr_pose_result> rs;
+        if (!db.match(scan, poses, &rs)) return 1;
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+        for (size_t m = 0; m < rs.size(); ++m)
+            std::cout << "scan " << f << " model " << m << " converged " << (rs[m].converged != 0) << " hypothesis " << rs[m].hypothesis << " inliers " << rs[m].inliers
+                      << " fitness " << rs[m].fitness << "\n";
+        std::cout << "Running Time : " << secs << std::endl;
+    }
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc >= 2 && std::string(argv[1]) == "--database") return run_database(argc, argv);
+    if (argc >= 2 && std::string(argv[1]) == "--database-online") return run_database_online(argc, argv);
     if (argc < 3) { fprintf(stderr, "usage: %s <model.pcd> <scan.pcd> [--scale-model S] [--out file.pcd] [--hypotheses N] [--icp-only]\n", argv[0]); return 2; }
     std::string out;
     float scale = 1.0f, gate = 3.0f; long long hyp = 0; bool icp_only = false, native = false, reference_main = false;

@@ -318,6 +318,45 @@ inline bool registerModelsToScene(const std::vector<pcl::PointCloud<pcl::PointXY
     return true;
 }
 
+// The offline / online split of the reference's two mains: RealTimeRobot.cpp:124-165 preprocesses every database model once
+// ("time to preprocess one database model"), :45-104 matches one scan against them.  add() is the offline half of one model
+// (rtr_cloud_prepare: normals, Harris corners, FPFH rows stay on the device); match() the online half (rtr_register_prepared).
+// poses[m] / details[m] belong to the m-th model added; the records are those of registerModelsToScene, bit for bit.
+class ModelDatabase {
+public:
+    explicit ModelDatabase(const rtr_register_params& params) : params_(params) {}
+    ~ModelDatabase() { for (rtr_cloud* c : models_) rtr_cloud_free(c); }
+    ModelDatabase(const ModelDatabase&) = delete;
+    ModelDatabase& operator=(const ModelDatabase&) = delete;
+    size_t size() const { return models_.size(); }
+    bool add(const pcl::PointCloud<pcl::PointXYZ>& model) {
+        rtr_context* ctx = rtr_host::default_context();
+        if (!ctx || model.points.empty()) return false;
+        rtr_cloud* c = nullptr;
+        if (rtr_cloud_upload(ctx, &model.points[0].x, (int)model.size(), &c) != 0) return false;
+        if (rtr_cloud_prepare(c, &params_) != 0) { rtr_cloud_free(c); return false; }
+        models_.push_back(c);
+        return true;
+    }
+    bool match(const pcl::PointCloud<pcl::PointXYZ>& scene, std::vector<Eigen::Matrix4f>& poses, std::vector<rtr_pose_result>* details = nullptr) {
+        rtr_context* ctx = rtr_host::default_context();
+        poses.assign(models_.size(), Eigen::Matrix4f::Identity());
+        if (!ctx || models_.empty() || scene.points.empty()) return false;
+        rtr_cloud* scan = nullptr;
+        if (rtr_cloud_upload(ctx, &scene.points[0].x, (int)scene.size(), &scan) != 0) return false;
+        std::vector<rtr_pose_result> rs(models_.size());
+        const int rc = rtr_register_prepared(models_.data(), (int)models_.size(), scan, &params_, rs.data());
+        rtr_cloud_free(scan);
+        if (rc != 0) return false;
+        for (size_t m = 0; m < models_.size(); ++m) memcpy(poses[m].data(), rs[m].pose, sizeof(rs[m].pose));
+        if (details) *details = rs;
+        return true;
+    }
+private:
+    rtr_register_params params_;
+    std::vector<rtr_cloud*> models_;
+};
+
 // The north-star pipeline on two pcl clouds: model -> scene pose, mean squared fitness, RANSAC bookkeeping.
 inline bool registerModelToScene(const pcl::PointCloud<pcl::PointXYZ>& model, const pcl::PointCloud<pcl::PointXYZ>& scene,
                                  const rtr_register_params& params, Eigen::Matrix4f& pose, rtr_pose_result* details = nullptr) {

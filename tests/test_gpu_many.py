@@ -237,3 +237,29 @@ def test_register_prepared_is_the_online_half_of_register_many(api, gpu_ctx, clo
         assert bytes(a) == bytes(b)
     for c in cms + fresh + [cs]:
         c.free()
+
+
+def test_cpp_host_model_database_offline_online(api, gpu_ctx, clouds):
+    """The C++ host mirror's ModelDatabase (add = rtr_cloud_prepare, match = rtr_register_prepared) behind the Linux driver's
+    --database-online mode: two scans against three prepared models give the records of the ctypes batch path."""
+    import os
+    import re
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "realtime_robot_b200", "realtime_robot")
+    data = os.path.join(ROOT, "data", "clouds")
+    names, scans = ["chair1", "chair2", "desk1"], ["mcloud", "T0_m8111"]
+    r = subprocess.run([exe, "--database-online"] + [os.path.join(data, n + ".pcd") for n in names] + ["--scans"] +
+                       [os.path.join(data, s + ".pcd") for s in scans] + ["--hypotheses", "20000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert re.search(r"time to preprocess 3 database models", r.stdout)
+    p = default_register_params()
+    p.ransac.max_iterations = 20000
+    rows = re.findall(r"scan \S+ model (\d+) converged (\d) hypothesis (-?\d+) inliers (\d+) fitness (\S+)", r.stdout)
+    assert len(rows) == len(names) * len(scans), r.stdout
+    want = []
+    for s in scans:
+        want += api.register_many_host(gpu_ctx, [clouds(n) for n in names], clouds(s), p)
+    for row, w in zip(rows, want):
+        assert (int(row[1]) != 0, int(row[2]), int(row[3])) == (w.converged != 0, w.hypothesis, w.inliers)
+        assert abs(float(row[4]) - w.fitness) <= 1e-5 * max(1e-3, abs(w.fitness))        # six printed digits

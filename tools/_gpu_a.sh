@@ -1,7 +1,5 @@
 #!/bin/bash
 cd /root/repo
-export PYTHONUNBUFFERED=1
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/h_tests.log
-timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/h_bench.json 2> gpurun_out/h_bench.err
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/h_bench_ref.json 2> gpurun_out/h_bench_ref.err
-echo done
+D=data/clouds
+./realtime_robot_b200/realtime_robot --database-online $D/chair1.pcd $D/chair2.pcd $D/desk1.pcd --scans $D/mcloud.pcd $D/T0_m8111.pcd --hypotheses 20000 > gpurun_out/j_driver.log 2>&1
+echo rc $? >> gpurun_out/j_driver.log

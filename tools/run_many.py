@@ -28,12 +28,43 @@ ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--models", default=",".join(MODELS))
 ap.add_argument("--marks", action="store_true", help="print the per-operation device times of one step (profiling marks)")
+ap.add_argument("--prepared", action="store_true", help="the online half instead: models prepared once (rtr_cloud_prepare), a step = "
+                "upload of the scan + rtr_register_prepared")
 args = ap.parse_args()
 names = args.models.split(",")
 ctx = api.Context(0)
 scene = api.Cloud(ctx, load("mcloud"))
 models = [api.Cloud(ctx, load(m)) for m in names]
 p = api.default_register_params()
+if args.prepared:
+    scene_h = load("mcloud")
+    for m in models:
+        m.prepare(p)
+
+    def step():
+        cs = api.Cloud(ctx, scene_h)
+        r = api.register_prepared(models, cs, p)
+        cs.free()
+        return r
+    for _ in range(args.warmup):
+        step()
+    ts = []
+    for _ in range(10):
+        ctx.sync(); t0 = time.perf_counter(); step(); ts.append(1e3 * (time.perf_counter() - t0))
+    print("online step %.3f ms (min of 10, wall)" % min(ts), flush=True)
+    if args.marks:
+        ctx.profile_begin(); step(); pr = ctx.profile_end()
+        tot = sum(v[1] for v in pr.values())
+        for k, v in sorted(pr.items(), key=lambda kv: -kv[1][1]):
+            print("  %-22s x%-3d %8.1f us  %5.1f %%" % (k, v[0], 1e3 * v[1], 100 * v[1] / tot))
+        print("  serialised %.3f ms" % tot)
+    rt = ctypes.CDLL("libcudart.so")
+    rt.cudaProfilerStart()
+    for _ in range(args.steps):
+        step()
+    ctx.sync()
+    rt.cudaProfilerStop()
+    sys.exit(0)
 for _ in range(args.warmup):
     api.register_many(models, scene, p)
 ts = []
