@@ -147,6 +147,7 @@ struct rtr_context {
     // multi-GPU (comm.cu): an NCCL communicator on this context's stream + pre-allocated staging for the record all-gather
     void* comm = nullptr; int comm_world = 0, comm_rank = 0;
     void* comm_dev = nullptr; void* comm_pinned = nullptr;
+    void* comm_p2p = nullptr;             // peer-memory exchange over NVLink (comm.cu P2pState), nullptr: NCCL only
     int gather_batches = 0;               // rtr_comm_gather_batches: every batch ends with the in-stream all-gather of its records
     int model_id_base = 0;                // model_id of a batch's record k = base + k
     int gathered_records = 0;             // records of the last gathered batch (world x n_models; n_models without a communicator)

@@ -2,6 +2,7 @@
 cd /root/repo
 export PYTHONUNBUFFERED=1
 N=$1
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/m_scale_$N.json 2> gpurun_out/m_scale_$N.err
-echo "rc $?" >> gpurun_out/m_scale_$N.err
-tail -n 3 gpurun_out/m_scale_$N.err
+export RTR_COMM_VERBOSE=1
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 tools/check_comm.py > gpurun_out/p_check_$N.log 2>&1
+echo "rc $?" >> gpurun_out/p_check_$N.log
+grep -v "OMP_NUM\|^\*\*\*" gpurun_out/p_check_$N.log | tail -n 6
