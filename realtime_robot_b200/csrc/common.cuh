@@ -175,7 +175,7 @@ struct rtr_cloud {
     // together with the stage parameters they were computed with; kp_xyz holds the first RTR_KP_PREVIEW corners, kp_count their number
     bool prepared = false;
     float prep_normal_radius = 0.f, prep_harris_radius = 0.f, prep_harris_threshold = 0.f, prep_fpfh_radius = 0.f;
-    int prep_harris_nms = 0, prep_harris_refine = 0;
+    int prep_harris_nms = 0, prep_harris_refine = 0, prep_normals_version = -1;
     float4* kp_xyz = nullptr;    int* kp_count = nullptr;
     // A model set (rtr_register_many): the points of several clouds concatenated, seg_begin[k] .. seg_begin[k+1] is cloud k
     // (size nseg + 1; empty for an ordinary cloud).  Every per-point stage then runs on all member clouds in one launch,

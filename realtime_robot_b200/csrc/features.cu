@@ -714,7 +714,7 @@ __global__ void __launch_bounds__(FPFH_WARPS * 32) k_fpfh_weight(const __grid_co
                     unsigned mask = __ballot_sync(0xffffffffu, use);
                     if (mask) {
                         if (use) {
-                            double w = 1.0 / (double)d2;
+                            double w = __drcp_rn((double)d2);        // == 1.0 / d2 (both correctly rounded), without the general division's fix-up path
                             int e = (head + nq + __popc(mask & lt)) & 63;
                             FwEntry en;
                             en.w = w;
@@ -868,7 +868,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32) k_fpfh_weight_tiled(GridView g,
                                 const unsigned mask = __ballot_sync(0xffffffffu, use);
                                 if (mask) {
                                     if (use) {                  // lane = candidate: weight and bin 32's term, once per pair
-                                        const double w = 1.0 / (double)d2;
+                                        const double w = __drcp_rn((double)d2);
                                         const int e = (head + nring + __popc(mask & lt)) & 63;
                                         FwEntry en;
                                         en.w = w;

@@ -1763,7 +1763,8 @@ static int register_many_enqueue(rtr_cloud* set, int n_models, const rtr_registe
 static bool prepared_with(const rtr_cloud* c, const rtr_register_params* p) {
     return c->prepared && c->normals && c->fpfh && c->kp_xyz && c->kp_count && c->prep_normal_radius == p->normal_radius &&
            c->prep_harris_radius == p->harris_radius && c->prep_harris_threshold == p->harris_threshold && c->prep_harris_nms == p->harris_nms &&
-           c->prep_harris_refine == p->harris_refine && c->prep_fpfh_radius == p->fpfh_radius && c->normals_mode == 0;
+           c->prep_harris_refine == p->harris_refine && c->prep_fpfh_radius == p->fpfh_radius && c->normals_mode == 0 &&
+           c->normals_radius == p->normal_radius && c->fpfh_radius == p->fpfh_radius && c->normals_version == c->prep_normals_version;
 }
 __global__ void k_store_corners(const int* __restrict__ cnt, const float4* __restrict__ xyz, int* __restrict__ cnt_out, float4* __restrict__ xyz_out) {
     const int c = *cnt;
@@ -1802,6 +1803,7 @@ static int cloud_prepare_dev(rtr_cloud* c, const rtr_register_params* p, bool fo
     c->prepared = true;
     c->prep_normal_radius = p->normal_radius; c->prep_harris_radius = p->harris_radius; c->prep_harris_threshold = p->harris_threshold;
     c->prep_harris_nms = p->harris_nms; c->prep_harris_refine = p->harris_refine; c->prep_fpfh_radius = p->fpfh_radius;
+    c->prep_normals_version = c->normals_version;        // normals recomputed later (another radius or mode) end the preparation
     return 0;
 }
 struct PrepTable {
