@@ -235,7 +235,17 @@ def test_register_prepared_is_the_online_half_of_register_many(api, gpu_ctx, clo
     want = api.register_many(fresh[:3], api.Cloud(gpu_ctx, scenes[0]), p)
     for a, b in zip(got, want):
         assert bytes(a) == bytes(b)
-    for c in cms + fresh + [cs]:
+    # degenerate members are refused by the prepared path (rtr_register_many falls back to rtr_register for them instead)
+    tiny = api.Cloud(gpu_ctx, hosts[0][:2])
+    tiny.prepare(p)
+    with pytest.raises(RtrError):
+        api.register_prepared([tiny], cs, p)
+    empty = api.Cloud(gpu_ctx, np.zeros((0, 4), np.float32))
+    with pytest.raises(RtrError):
+        api.register_prepared(cms[:2], empty, p)
+    with pytest.raises(RtrError):
+        api.register_prepared([cms[0], cs], cs, p)           # the scan cannot be one of its own models
+    for c in cms + fresh + [cs, tiny, empty]:
         c.free()
 
 
