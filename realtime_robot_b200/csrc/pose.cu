@@ -112,10 +112,87 @@ __global__ void __launch_bounds__(64) k_ransac_pose(RansacArgs a, const int* __r
 // K3: getFitness — one CTA per (surviving hypothesis, slice of the source cloud), persistent over that work list.
 // With few survivors and a large source a CTA per hypothesis would leave most SMs idle, hence the slices; the per-slice
 // (inlier count, sum d2) partials are folded in slice order by K4.
+// Block lists of the target grid: for every cell, the points of its 3x3x3 block as ONE contiguous list.  The inlier test of a
+// transformed source point is "minimum distance to the points of my cell's block", and walking the block as 9 row ranges
+// (for_block27) costs a warp the MAXIMUM trip count over its lanes nine times over: 7 of 32 lanes were busy in the cell walk and
+// it was 70 % of k_ransac_eval_many's 148 M warp instructions (ncu, round 2).  With the block flattened once per scan a query is
+// one (begin, end) lookup and one loop.  27 x the target's points (825 KB for a 1909-point scan), built by two small kernels and
+// one scan; the candidate SET of a query is for_block27's, so the minimum — the only thing used — is the same bit for bit.
+struct BlockLists { const int* begin; const float4* pts; };      // begin: ncells + 1 entries; begin == nullptr: walk the grid
+__global__ void k_block_count(GridView g, int ncells, int* __restrict__ counts) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > ncells) return;
+    int cnt = 0;
+    if (c < ncells) {
+        const int x = c % g.dx, y = (c / g.dx) % g.dy, z = c / (g.dx * g.dy);
+        const int x0 = max(x - 1, 0), x1 = min(x + 1, g.dx - 1);
+        for (int zz = max(z - 1, 0); zz <= min(z + 1, g.dz - 1); ++zz)
+            for (int yy = max(y - 1, 0); yy <= min(y + 1, g.dy - 1); ++yy)
+                cnt += __ldg(g.cell_begin + cell_key(g, x1, yy, zz) + 1) - __ldg(g.cell_begin + cell_key(g, x0, yy, zz));
+    }
+    counts[c] = cnt;             // counts[ncells] = 0: the exclusive scan's last entry is the total
+}
+__global__ void k_block_fill(GridView g, int ncells, const int* __restrict__ begin, float4* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const int x = c % g.dx, y = (c / g.dx) % g.dy, z = c / (g.dx * g.dy);
+    const int x0 = max(x - 1, 0), x1 = min(x + 1, g.dx - 1);
+    int o = __ldg(begin + c);
+    for (int zz = max(z - 1, 0); zz <= min(z + 1, g.dz - 1); ++zz)
+        for (int yy = max(y - 1, 0); yy <= min(y + 1, g.dy - 1); ++yy) {
+            const int s0 = __ldg(g.cell_begin + cell_key(g, x0, yy, zz)), s1 = __ldg(g.cell_begin + cell_key(g, x1, yy, zz) + 1);
+            for (int s = s0; s < s1; ++s) out[o++] = __ldg(g.sorted + s);
+        }
+}
+// minimum squared distance from q to the points of its cell's block (FLT_MAX: none) — the candidates of for_block27(g, q)
+__device__ __forceinline__ float block_min_d2(const GridView& g, const BlockLists& bl, float qx, float qy, float qz) {
+    int cx = cell_coord(qx, g.mnx, g.inv_h), cy = cell_coord(qy, g.mny, g.inv_h), cz = cell_coord(qz, g.mnz, g.inv_h);
+    if (cx < -1 || cy < -1 || cz < -1 || cx > g.dx || cy > g.dy || cz > g.dz) return FLT_MAX;
+    cx = clampi(cx, 0, g.dx - 1); cy = clampi(cy, 0, g.dy - 1); cz = clampi(cz, 0, g.dz - 1);
+    const int key = cell_key(g, cx, cy, cz);
+    const int s0 = __ldg(bl.begin + key), s1 = __ldg(bl.begin + key + 1);
+    float best = FLT_MAX;
+    for (int s = s0; s < s1; ++s) {
+        const float4 p = __ldg(bl.pts + s);
+        const float d2 = dist2f(qx, qy, qz, p.x, p.y, p.z);
+        if (d2 < best) best = d2;
+    }
+    return best;
+}
+__device__ __forceinline__ float inlier_min_d2(const GridView& g, const BlockLists& bl, float qx, float qy, float qz) {
+    if (bl.begin) return block_min_d2(g, bl, qx, qy, qz);
+    float best = FLT_MAX;
+    for_block27(g, qx, qy, qz, [&](int, float4, float d2) { if (d2 < best) best = d2; });
+    return best;
+}
+// RTR_RANSAC_BLOCKLISTS=0 keeps the grid walk (A/B runs, tests).  Lists are built for grids of up to 4 M cells.
+static int block_lists_build_dev(rtr_context* ctx, const GridView& v, BlockLists* out) {
+    out->begin = nullptr; out->pts = nullptr;
+    static const bool wanted = []() { const char* e = getenv("RTR_RANSAC_BLOCKLISTS"); return !(e && e[0] == '0'); }();
+    const long long nc = (long long)v.dx * v.dy * v.dz;
+    if (!wanted || v.n <= 0 || nc <= 0 || nc > (1 << 22) || v.n > (1 << 21)) return 0;
+    const int ncells = (int)nc;
+    int *counts = nullptr, *begin = nullptr; float4* pts = nullptr; char* temp = nullptr;
+    if (int e = tmp_alloc(ctx, &counts, (size_t)ncells + 1, "ransac.blocks")) return e;
+    if (int e = tmp_alloc(ctx, &begin, (size_t)ncells + 1, "ransac.blocks")) return e;
+    if (int e = tmp_alloc(ctx, &pts, (size_t)27 * v.n, "ransac.blocks")) return e;
+    k_block_count<<<nblk((long long)ncells + 1, 256), 256, 0, ctx->stream>>>(v, ncells, counts);
+    RTR_LAUNCH_CHECK(ctx, "ransac.block_count");
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, counts, begin, ncells + 1, ctx->stream);
+    if (int e = tmp_alloc(ctx, &temp, tb, "ransac.blocks")) return e;
+    RTR_CHECK(cub::DeviceScan::ExclusiveSum(temp, tb, counts, begin, ncells + 1, ctx->stream), "ransac.blocks");
+    RTR_MARK(ctx, "ransac.block_scan");
+    k_block_fill<<<nblk(ncells, 256), 256, 0, ctx->stream>>>(v, ncells, begin, pts);
+    RTR_LAUNCH_CHECK(ctx, "ransac.block_fill");
+    out->begin = begin; out->pts = pts;
+    return 0;
+}
+
 #define EVAL_THREADS 256
 __global__ void __launch_bounds__(EVAL_THREADS) k_ransac_eval(RansacArgs a, GridView g, const int* __restrict__ count,
                                                               const float* __restrict__ poses, int split,
-                                                              double* __restrict__ psum, int* __restrict__ pcnt) {
+                                                              double* __restrict__ psum, int* __restrict__ pcnt, BlockLists bl) {
     __shared__ float m[16];
     __shared__ double wsum[EVAL_THREADS / 32];
     __shared__ int wcnt[EVAL_THREADS / 32];
@@ -131,8 +208,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_ransac_eval(RansacArgs a, Grid
         double sum = 0;
         for (int i = i0 + threadIdx.x; i < i1; i += EVAL_THREADS) {
             float4 q = xform(m, __ldg(a.src + i));
-            float best = FLT_MAX;
-            for_block27(g, q.x, q.y, q.z, [&](int, float4, float d2) { if (d2 < best) best = d2; });
+            const float best = inlier_min_d2(g, bl, q.x, q.y, q.z);
             if (best < a.dmax2) { ++cnt; sum += (double)best; }
         }
         cnt = warp_sum(cnt);
@@ -241,6 +317,9 @@ int rtr_ransac_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_ransac_params* p, r
     a.dmax2 = p->max_correspondence_distance * p->max_correspondence_distance;
     a.inlier_fraction = p->inlier_fraction;
     GridView v = rtr_view(g);
+    // large sweeps repay the flattened block lists (~20 us to build); a single registration's few hundred survivors do not
+    BlockLists bl{nullptr, nullptr};
+    if (h1 - h0 >= 200000) if (int e = block_lists_build_dev(ctx, v, &bl)) return e;
     for (long long base = h0; base < h1; base += CHUNK) {
         a.h_base = base; a.h_count = (int)std::min<long long>(CHUNK, h1 - base);
         RTR_CHECK(cudaMemsetAsync(count, 0, sizeof(int), ctx->stream), "ransac");
@@ -250,7 +329,7 @@ int rtr_ransac_dev(rtr_cloud* src, rtr_cloud* tgt, const rtr_ransac_params* p, r
         k_ransac_pose<<<nblk(a.h_count, 64), 64, 0, ctx->stream>>>(a, survivors, count, poses);
         RTR_LAUNCH_CHECK(ctx, "ransac.pose");
         int grid = (int)std::min<long long>((long long)a.h_count * split, ctx->sm_count * 8);
-        k_ransac_eval<<<grid, EVAL_THREADS, 0, ctx->stream>>>(a, v, count, poses, split, psum, pcnt);
+        k_ransac_eval<<<grid, EVAL_THREADS, 0, ctx->stream>>>(a, v, count, poses, split, psum, pcnt, bl);
         RTR_LAUNCH_CHECK(ctx, "ransac.eval");
         k_ransac_select<<<1, 1024, 0, ctx->stream>>>(a, survivors, count, poses, split, psum, pcnt, d_result);
         RTR_LAUNCH_CHECK(ctx, "ransac.select");
@@ -352,7 +431,7 @@ __global__ void __launch_bounds__(64) k_ransac_pose_many(const __grid_constant__
 __global__ void __launch_bounds__(EVAL_THREADS) k_ransac_eval_many(const __grid_constant__ RansacMany rm, RansacArgs common, GridView g,
                                                                    const int* __restrict__ survivors, const float* __restrict__ poses,
                                                                    const int* __restrict__ items, const int* __restrict__ n_items,
-                                                                   double* __restrict__ psum, int* __restrict__ pcnt) {
+                                                                   double* __restrict__ psum, int* __restrict__ pcnt, BlockLists bl) {
     __shared__ float m[16];
     __shared__ double wsum[EVAL_THREADS / 32];
     __shared__ int wcnt[EVAL_THREADS / 32];
@@ -373,8 +452,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_ransac_eval_many(const __grid_
         double sum = 0;
         for (int i = i0 + threadIdx.x; i < i1; i += EVAL_THREADS) {
             float4 q = xform(m, __ldg(src + i));
-            float best = FLT_MAX;
-            for_block27(g, q.x, q.y, q.z, [&](int, float4, float d2) { if (d2 < best) best = d2; });
+            const float best = inlier_min_d2(g, bl, q.x, q.y, q.z);
             if (best < common.dmax2) { ++cnt; sum += (double)best; }
         }
         cnt = warp_sum(cnt);
@@ -491,6 +569,8 @@ static int ransac_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const int*
     DevGrid* g;
     if (int e = rtr_get_grid(&scan_alias, p->max_correspondence_distance, &g)) return e;
     const GridView v = rtr_view(g);
+    BlockLists bl{nullptr, nullptr};
+    if (int e = block_lists_build_dev(ctx, v, &bl)) return e;
     RansacMany rm;
     memset(&rm, 0, sizeof(rm));
     rm.nseg = n_models;
@@ -524,7 +604,7 @@ static int ransac_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const int*
     RTR_LAUNCH_CHECK(ctx, "ransac.sample");
     k_ransac_pose_many<<<nblk(slots, 64), 64, 0, ctx->stream>>>(rm, a, survivors, counters, poses, item_first, items, counters + 1);
     RTR_LAUNCH_CHECK(ctx, "ransac.pose");
-    k_ransac_eval_many<<<ctx->sm_count * 8, EVAL_THREADS, 0, ctx->stream>>>(rm, a, v, survivors, poses, items, counters + 1, psum, pcnt);
+    k_ransac_eval_many<<<ctx->sm_count * 8, EVAL_THREADS, 0, ctx->stream>>>(rm, a, v, survivors, poses, items, counters + 1, psum, pcnt, bl);
     RTR_LAUNCH_CHECK(ctx, "ransac.eval");
     k_ransac_select_many<<<n_models, 1024, 0, ctx->stream>>>(rm, a, survivors, counters, poses, item_first, psum, pcnt, d_results);
     RTR_LAUNCH_CHECK(ctx, "ransac.select");

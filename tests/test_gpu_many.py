@@ -273,3 +273,32 @@ def test_cpp_host_model_database_offline_online(api, gpu_ctx, clouds):
     for row, w in zip(rows, want):
         assert (int(row[1]) != 0, int(row[2]), int(row[3])) == (w.converged != 0, w.hypothesis, w.inliers)
         assert abs(float(row[4]) - w.fitness) <= 1e-5 * max(1e-3, abs(w.fitness))        # six printed digits
+
+
+def test_ransac_block_lists_and_grid_walk_give_the_same_records(api, gpu_ctx):
+    """The prerejective inlier test reads the scan either as flattened 3x3x3 block lists (default for batches and large sweeps) or by
+    walking the grid's 9 row ranges (RTR_RANSAC_BLOCKLISTS=0): the candidate set of a query is the same, so are the records — a batch
+    of three models and a 250 000-hypothesis single registration, bit for bit."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = ("import sys, json; sys.path.insert(0, %r)\n"
+            "import os\n"
+            "from realtime_robot_b200 import api\n"
+            "from realtime_robot_b200.pcd import read_pcd_xyz, to_xyz1\n"
+            "load = lambda n: to_xyz1(read_pcd_xyz(os.path.join(%r, 'data', 'clouds', n + '.pcd')))\n"
+            "ctx = api.Context(0)\n"
+            "p = api.default_register_params()\n"
+            "p.ransac.max_iterations = 20000\n"
+            "rs = api.register_many_host(ctx, [load('chair1'), load('chair4'), load('desk1')], load('mcloud'), p)\n"
+            "p.ransac.max_iterations = 250000\n"
+            "rs.append(api.register_host(ctx, load('chair2'), load('mcloud'), p))\n"
+            "print(json.dumps([bytes(r).hex() for r in rs]))\n") % (ROOT, ROOT)
+    outs = []
+    for mode in ("1", "0"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, RTR_RANSAC_BLOCKLISTS=mode), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert outs[0] == outs[1] and len(outs[0]) == 4
