@@ -541,7 +541,7 @@ __global__ void k_result_init_many(rtr_pose_result* res, int n) {
 // set = model set whose members [0, n_models) are the sources; the target is member `tgt_seg` (the scan).  knn_all: the
 // members' correspondences (target-local indices), n_source_points x k.  d_results: n_models records.
 static int ransac_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const int* knn_all, int knn_k, const rtr_ransac_params* p,
-                           rtr_pose_result* d_results) {
+                           rtr_pose_result* d_results, const GridView* scan_grid, const BlockLists* scan_blocks) {
     RtrRange nvtx_range("rtr.ransac_prerejective.many");
     rtr_context* ctx = set->ctx;
     const long long h0 = p->hypothesis_begin, h1 = (p->hypothesis_end > 0) ? p->hypothesis_end : p->max_iterations;
@@ -554,23 +554,9 @@ static int ransac_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const int*
     }
     if (!(p->max_correspondence_distance > 0.f)) return rtr_fail("ransac", "max_correspondence_distance must be > 0", RTR_ERR_INVALID);
     if (H > (1 << 20) || (long long)n_models * H > (1LL << 24)) return rtr_fail("ransac", "model-set RANSAC takes at most 2^20 hypotheses per model", RTR_ERR_INVALID);
-    // target grid for the inlier test: the scan alone, gridded at exactly d_max (one small single-cloud build on an alias of
-    // the scan's slice of the set).  Every surviving hypothesis of every model walks this grid for every source point, so the
-    // 1.9x fewer candidates per 27-cell block than the normals grid (cells of 0.05 against d_max = 0.0365) repay the build;
-    // the inlier test itself is exact on any grid with cells >= d_max.
-    rtr_cloud scan_alias;
-    scan_alias.ctx = ctx; scan_alias.n = nt; scan_alias.pts = set->pts + set->seg_begin[tgt_seg];
-    for (int a = 0; a < 3; ++a) { scan_alias.bb_min[a] = set->seg_bb[6 * tgt_seg + a]; scan_alias.bb_max[a] = set->seg_bb[6 * tgt_seg + 3 + a]; }
-    scan_alias.bbox_valid = true;
-    struct AliasGuard {            // the points are borrowed from the set; the grid is the alias' own (released stream-ordered)
-        rtr_cloud* c;
-        ~AliasGuard() { c->pts = nullptr; rtr_invalidate(c); }
-    } alias_guard{&scan_alias};
-    DevGrid* g;
-    if (int e = rtr_get_grid(&scan_alias, p->max_correspondence_distance, &g)) return e;
-    const GridView v = rtr_view(g);
-    BlockLists bl{nullptr, nullptr};
-    if (int e = block_lists_build_dev(ctx, v, &bl)) return e;
+    // target grid for the inlier test and its block lists: built by the caller (ScanStructures)
+    const GridView v = *scan_grid;
+    const BlockLists bl = *scan_blocks;
     RansacMany rm;
     memset(&rm, 0, sizeof(rm));
     rm.nseg = n_models;
@@ -1637,7 +1623,8 @@ __global__ void k_icp_init_many(const __grid_constant__ IcpMany im, const float4
 // scan: nullptr — the target is member tgt_seg of the set, searched through the set's grids, neighbours named by set-wide index;
 // or the scan as a cloud of its own (prepared path: the set carries no grids and no normals) — its own grids and normals,
 // neighbours named by the scan's local index.  Lowest-index tie-breaking is the same in either index space: same records.
-static int icp_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const rtr_icp_params* p, rtr_pose_result* d_results, rtr_cloud* scan = nullptr) {
+static int icp_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const rtr_icp_params* p, rtr_pose_result* d_results, rtr_cloud* scan = nullptr,
+                        const WbvhView* scan_bvh = nullptr /* built by the caller in the index space described below */) {
     RtrRange nvtx_range("rtr.icp.many");
     rtr_context* ctx = set->ctx;
     if (p->estimator != 0 && p->estimator != 1) return rtr_fail("icp", "estimator must be 0 (SVD) or 1 (point-to-plane LLS)", RTR_ERR_INVALID);
@@ -1671,7 +1658,8 @@ static int icp_many_dev(rtr_cloud* set, int n_models, int tgt_seg, const rtr_icp
     T.pts = set->pts + (t0 - idx_base); T.normals = (p->estimator == 1) ? (scan ? scan->normals : set->normals) : nullptr;
     T.bvh.n = 0; T.bvh.nleaf = 0; T.bvh.boxes = nullptr; T.bvh.pts = nullptr;
     // small scans: the warp-per-query kernels search a two-level hierarchy of the scan (indices reported in the same space)
-    if (nt >= 1 && nt <= WBVH_MAX_POINTS && icp_hierarchy_pays(n_src, p->max_iterations))
+    if (scan_bvh) T.bvh = *scan_bvh;
+    else if (nt >= 1 && nt <= WBVH_MAX_POINTS && icp_hierarchy_pays(n_src, p->max_iterations))
         if (int e = wbvh_build_dev(ctx, set->pts + t0, nt, idx_base, &set->seg_bb[6 * tgt_seg], &set->seg_bb[6 * tgt_seg + 3], &T.bvh)) return e;
     IcpMany im;
     memset(&im, 0, sizeof(im));
@@ -1775,6 +1763,49 @@ static int register_many_back(rtr_cloud* set, int n_models, const rtr_register_p
     rtr_context* ctx = set->ctx;
     const int tgt = n_models, nseg = n_models + 1;
     const int n_src = set->seg_begin[n_models], nt = set->n - n_src;
+    // What RANSAC and ICP need of the scan alone — its grid at exactly d_max with the flattened block lists (the inlier test: every
+    // surviving hypothesis of every model reads it for every source point; 1.9x fewer candidates than the normals grid's cells of
+    // 0.05 against d_max = 0.0365), and the two-level hierarchy of the ICP kernels — depends on nothing but the scan's points: it is
+    // built on the context's second stream (behind the corner stage) while descriptor matching runs, ~60 us off the batch's chain.
+    rtr_cloud scan_alias;                  // the scan's slice of the set as a cloud of its own: borrowed points, its own grid
+    scan_alias.ctx = ctx; scan_alias.n = nt; scan_alias.pts = set->pts + n_src;
+    for (int a = 0; a < 3; ++a) { scan_alias.bb_min[a] = set->seg_bb[6 * tgt + a]; scan_alias.bb_max[a] = set->seg_bb[6 * tgt + 3 + a]; }
+    scan_alias.bbox_valid = true;
+    struct AliasGuard {                    // released stream-ordered on the main stream — on every path only after the join
+        rtr_cloud* c; JoinGuard* jg;
+        ~AliasGuard() { jg->join(); c->pts = nullptr; rtr_invalidate(c); }
+    } alias_guard{&scan_alias, &join_guard};
+    GridView scan_grid;
+    BlockLists scan_blocks{nullptr, nullptr};
+    WbvhView scan_bvh;
+    scan_bvh.n = 0; scan_bvh.nleaf = 0; scan_bvh.boxes = nullptr; scan_bvh.pts = nullptr;
+    memset(&scan_grid, 0, sizeof(scan_grid));
+    const long long H = ((p->ransac.hypothesis_end > 0) ? p->ransac.hypothesis_end : p->ransac.max_iterations) - p->ransac.hypothesis_begin;
+    const bool want_grid = H > 0 && nt >= 1 && p->ransac.max_correspondence_distance > 0.f;
+    const bool want_bvh = p->run_icp && nt >= 1 && nt <= WBVH_MAX_POINTS && icp_hierarchy_pays(n_src, p->icp.max_iterations);
+    {
+        const bool fork = !ctx->profile && ctx->aux_stream && (want_grid || want_bvh);
+        cudaStream_t main_stream = ctx->stream;
+        if (fork) {
+            RTR_CHECK(cudaEventRecord(ctx->fork_event, main_stream), "register_many.fork");        // the scan's points are in place
+            RTR_CHECK(cudaStreamWaitEvent(ctx->aux_stream, ctx->fork_event, 0), "register_many.fork");
+            ctx->stream = ctx->aux_stream;
+        }
+        int e = 0;
+        if (want_grid) {
+            DevGrid* g = nullptr;
+            e = rtr_get_grid(&scan_alias, p->ransac.max_correspondence_distance, &g);
+            if (!e) { scan_grid = rtr_view(g); e = block_lists_build_dev(ctx, scan_grid, &scan_blocks); }
+        }
+        // index space of the hierarchy: the scan's own when it comes as a cloud (prepared path), the set's otherwise (icp_many_dev)
+        if (!e && want_bvh) e = wbvh_build_dev(ctx, set->pts + n_src, nt, scan ? 0 : n_src, &set->seg_bb[6 * tgt], &set->seg_bb[6 * tgt + 3], &scan_bvh);
+        ctx->stream = main_stream;
+        if (fork) {
+            cudaEventRecord(ctx->join_event, ctx->aux_stream);      // behind everything the second stream was given so far
+            join_guard.fork = true; join_guard.joined = false;
+        }
+        if (e) return e;
+    }
     const int k = p->ransac.correspondence_k;
     int* knn = nullptr; float* knn_dist = nullptr;
     if (int e = tmp_alloc(ctx, &knn, (size_t)n_src * k, "register_many")) return e;
@@ -1783,8 +1814,9 @@ static int register_many_back(rtr_cloud* set, int n_models, const rtr_register_p
     rtr_pose_result* d_res = nullptr; KpPreview* d_prev = nullptr;
     if (int e = tmp_alloc(ctx, &d_res, n_models, "register_many")) return e;
     if (int e = tmp_alloc(ctx, &d_prev, nseg, "register_many")) return e;
-    if (int e = ransac_many_dev(set, n_models, tgt, knn, k, &p->ransac, d_res)) return e;
-    if (p->run_icp) if (int e = icp_many_dev(set, n_models, tgt, &p->icp, d_res, scan)) return e;
+    join_guard.join();                     // the scan's structures (and the corner stage before them) are complete
+    if (int e = ransac_many_dev(set, n_models, tgt, knn, k, &p->ransac, d_res, &scan_grid, &scan_blocks)) return e;
+    if (p->run_icp) if (int e = icp_many_dev(set, n_models, tgt, &p->icp, d_res, scan, want_bvh ? &scan_bvh : nullptr)) return e;
     IcpMany im;
     memset(&im, 0, sizeof(im));
     im.nseg = n_models;
